@@ -1,0 +1,761 @@
+// C ABI of libhcurl_b200.so: contexts, spaces, operators, PCG (see include/hcurl_b200.h).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "internal.h"
+
+namespace hcurl {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+bool cuda_ok(cudaError_t e, const char *what) {
+  if (e == cudaSuccess) return true;
+  set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+  return false;
+}
+
+// ------------------------------------------------------------- small kernels ----
+__global__ void encode_map_kernel(const int64_t n_elem, const int nd, const int64_t n_pad, const int transpose,
+                                  const int32_t *__restrict__ ldof, const int *__restrict__ loc,
+                                  const int *__restrict__ sgn, const int32_t *__restrict__ l2e,
+                                  uint32_t *__restrict__ out) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= n_elem * nd) return;
+  const int64_t e = gid / nd;
+  const int t = (int)(gid % nd);
+  const int l = loc ? loc[t] : t;
+  const int32_t v = ldof[e * nd + l];
+  const int32_t k = v >= 0 ? v : -1 - v;
+  bool neg = v < 0;
+  if (sgn && sgn[t] < 0) neg = !neg;
+  const uint32_t ext = l2e ? (uint32_t)l2e[k] : (uint32_t)k;
+  const uint32_t code = ext | (neg ? MAP_NEG : 0u);
+  if (transpose) out[(int64_t)t * n_pad + e] = code;
+  else out[gid] = code;
+}
+
+__global__ void permute_xyz_kernel(const int64_t n_elem, const double *__restrict__ in, double *__restrict__ out) {
+  // MFEM hex corner order -> tensor order (x fastest)
+  const int perm[8] = {0, 1, 3, 2, 4, 5, 7, 6};  // tensor node t holds corner perm[t]
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= n_elem * 24) return;
+  const int64_t e = gid / 24;
+  const int r = (int)(gid % 24), t = r / 3, d = r % 3;
+  out[gid] = in[e * 24 + perm[t] * 3 + d];
+}
+
+__global__ void flag_map_kernel(const int64_t n, const uint32_t *__restrict__ in, const double *__restrict__ flag,
+                                uint32_t *__restrict__ out) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= n) return;
+  const uint32_t m = in[gid];
+  out[gid] = (flag[m & MAP_IDX] != 0.0) ? (m | MAP_ESS) : m;
+}
+
+__global__ void set_flags_kernel(const int32_t n, const int32_t *__restrict__ idx, double *__restrict__ v, double val) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[idx[i]] = val;
+}
+__global__ void copy_idx_kernel(const int32_t n, const int32_t *__restrict__ idx, const double *__restrict__ src,
+                                double *__restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[idx[i]] = src[idx[i]];
+}
+__global__ void axpby_kernel(const int64_t n, const double a, const double *__restrict__ x, const double b,
+                             double *__restrict__ y) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = a * x[i] + b * y[i];
+}
+
+// ---- deterministic fused reductions ------------------------------------------------
+// Every reducing kernel ends with block_finish(): per-block partials are written,
+// the last block to arrive sums them in index order (fixed order => run-to-run
+// bit-reproducible for a fixed grid) and stores the result in out[slot].
+static constexpr int RED_THREADS = 256;
+
+__device__ __forceinline__ void block_finish(double v, double *partial, unsigned int *counter, double *out) {
+  __shared__ double sh[RED_THREADS / 32];
+  __shared__ bool last;
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < RED_THREADS / 32; i++) s += sh[i];
+    partial[blockIdx.x] = s;
+    __threadfence();
+    const unsigned int t = atomicInc(counter, gridDim.x - 1);
+    last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x < 32) {
+    __threadfence();
+    double s = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) s += ((volatile double *)partial)[i];
+    // fixed-order tree over lanes
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) *out = s;
+  }
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+dot_kernel(const int64_t n, const double *__restrict__ a, const double *__restrict__ b, double *partial,
+           unsigned int *counter, double *out) {
+  double s = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) s += a[i] * b[i];
+  block_finish(s, partial, counter, out);
+}
+// out = sum dinv * b * b   (<C b, b>)
+__global__ void __launch_bounds__(RED_THREADS)
+cdot_kernel(const int64_t n, const double *__restrict__ dinv, const double *__restrict__ b, double *partial,
+            unsigned int *counter, double *out) {
+  double s = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double bi = b[i];
+    s += (dinv ? dinv[i] : 1.0) * bi * bi;
+  }
+  block_finish(s, partial, counter, out);
+}
+// r = b - r (optional), p = C r, out = <r, p>
+__global__ void __launch_bounds__(RED_THREADS)
+pcg_init_kernel(const int64_t n, const int sub, const double *__restrict__ b, const double *__restrict__ dinv,
+                double *__restrict__ r, double *__restrict__ p, double *partial, unsigned int *counter, double *out) {
+  double s = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double ri = sub ? b[i] - r[i] : b[i];
+    const double pi = (dinv ? dinv[i] : 1.0) * ri;
+    r[i] = ri;
+    p[i] = pi;
+    s += ri * pi;
+  }
+  block_finish(s, partial, counter, out);
+}
+// alpha = S[0]/S[1]; x += alpha p; r -= alpha s; s = C r; out = <r, s>
+__global__ void __launch_bounds__(RED_THREADS)
+pcg_update_kernel(const int64_t n, const double *__restrict__ S, const double *__restrict__ dinv,
+                  const double *__restrict__ p, double *__restrict__ x, double *__restrict__ r, double *__restrict__ s,
+                  double *partial, unsigned int *counter, double *out) {
+  const double alpha = S[0] / S[1];
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    x[i] += alpha * p[i];
+    const double ri = r[i] - alpha * s[i];
+    const double zi = (dinv ? dinv[i] : 1.0) * ri;
+    r[i] = ri;
+    s[i] = zi;
+    acc += ri * zi;
+  }
+  block_finish(acc, partial, counter, out);
+}
+// p = s + beta p;  S[0] <- gamma_new
+__global__ void pcg_dir_kernel(const int64_t n, const double beta, const double gamma_new, double *S,
+                               const double *__restrict__ s, double *__restrict__ p) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = s[i] + beta * p[i];
+  if (blockIdx.x == 0 && threadIdx.x == 0) S[0] = gamma_new;
+}
+__global__ void invert_kernel(const int64_t n, double *__restrict__ d) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) d[i] = 1.0 / d[i];
+}
+
+// FP64 FMA peak micro-benchmark
+__global__ void dfma_kernel(double *out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double b = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; i++) {
+    a0 = a0 * b + c; a1 = a1 * b + c; a2 = a2 * b + c; a3 = a3 * b + c;
+    a4 = a4 * b + c; a5 = a5 * b + c; a6 = a6 * b + c; a7 = a7 * b + c;
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+static int red_grid(hcurl_ctx *ctx, int64_t n) {
+  int64_t g = (n + RED_THREADS * 4 - 1) / (RED_THREADS * 4);
+  if (g < 1) g = 1;
+  const int64_t cap = (int64_t)ctx->sm_count * 8;
+  if (g > cap) g = cap;
+  if (g > ctx->n_partial) g = ctx->n_partial;
+  return (int)g;
+}
+
+// ---- apply on extended device vectors -------------------------------------------------
+int op_apply_ext(hcurl_op *op, double *d_x, double *d_y, bool constrained, double scale, bool accumulate) {
+  hcurl_space *sp = op->sp;
+  hcurl_ctx *ctx = op->ctx;
+  const int64_t next = sp->n_ext();
+  if (exchange_broadcast(sp, d_x)) return 1;
+  if (!accumulate) HC_CUDA(cudaMemsetAsync(d_y, 0, sizeof(double) * next, ctx->stream));
+  else if (sp->n_ghost) HC_CUDA(cudaMemsetAsync(d_y + sp->n_tdof, 0, sizeof(double) * sp->n_ghost, ctx->stream));
+  const uint32_t *map = (constrained && op->d_map_ess) ? op->d_map_ess : sp->d_map;
+  if (op->timed) HC_CUDA(cudaEventRecord(op->ev0, ctx->stream));
+  int rc = (sp->geom == HCURL_GEOM_HEX) ? hex_apply_launch(op, map, d_x, d_y, scale) : tet_apply_launch(op, map, d_x, d_y, scale);
+  if (rc) return rc;
+  if (op->timed) HC_CUDA(cudaEventRecord(op->ev1, ctx->stream));
+  if (exchange_reduce(sp, d_y)) return 1;
+  if (constrained && op->n_ess > 0)
+    copy_idx_kernel<<<(op->n_ess + 255) / 256, 256, 0, ctx->stream>>>(op->n_ess, op->d_ess, d_x, d_y);
+  HC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int op_diag_ext(hcurl_op *op, double *d_diag) {
+  hcurl_space *sp = op->sp;
+  hcurl_ctx *ctx = op->ctx;
+  HC_CUDA(cudaMemsetAsync(d_diag, 0, sizeof(double) * sp->n_ext(), ctx->stream));
+  int rc = (sp->geom == HCURL_GEOM_HEX) ? hex_diag_launch(op, d_diag) : tet_diag_launch(op, d_diag);
+  if (rc) return rc;
+  if (exchange_reduce(sp, d_diag)) return 1;
+  if (op->n_ess > 0) set_flags_kernel<<<(op->n_ess + 255) / 256, 256, 0, ctx->stream>>>(op->n_ess, op->d_ess, d_diag, 1.0);
+  HC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int ensure_work(hcurl_op *op) {
+  const size_t bytes = sizeof(double) * (size_t)op->sp->n_ext();
+  if (!op->d_xin) HC_CUDA(cudaMalloc(&op->d_xin, bytes));
+  if (!op->d_yout) HC_CUDA(cudaMalloc(&op->d_yout, bytes));
+  return 0;
+}
+
+static cudaMemcpyKind kind_in(int where) { return where == HCURL_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice; }
+static cudaMemcpyKind kind_out(int where) { return where == HCURL_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost; }
+
+}  // namespace hcurl
+
+using namespace hcurl;
+
+extern "C" {
+
+const char *hcurl_version(void) { return "hcurl_b200 0.1 (sm_100a, FP64)"; }
+const char *hcurl_last_error(void) { return g_err; }
+
+int hcurl_comm_unique_id(void *id128) { return comm_unique_id(id128); }
+
+hcurl_ctx *hcurl_ctx_create(int device, const void *uid, int rank, int nranks) {
+  int ndev = 0;
+  if (!cuda_ok(cudaGetDeviceCount(&ndev), "cudaGetDeviceCount") || ndev <= 0) {
+    set_error("no CUDA device available (this library has no CPU fallback)");
+    return nullptr;
+  }
+  if (device < 0 || device >= ndev) { set_error("invalid device %d (have %d)", device, ndev); return nullptr; }
+  HC_CUDA_NULL(cudaSetDevice(device));
+  hcurl_ctx *ctx = new hcurl_ctx;
+  ctx->device = device; ctx->rank = rank; ctx->nranks = nranks < 1 ? 1 : nranks;
+  cudaDeviceProp prop;
+  HC_CUDA_NULL(cudaGetDeviceProperties(&prop, device));
+  ctx->sm_count = prop.multiProcessorCount;
+  HC_CUDA_NULL(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  HC_CUDA_NULL(cudaMalloc(&ctx->d_red, sizeof(double) * 16));
+  HC_CUDA_NULL(cudaMemset(ctx->d_red, 0, sizeof(double) * 16));
+  HC_CUDA_NULL(cudaMallocHost(&ctx->h_red, sizeof(double) * 16));
+  HC_CUDA_NULL(cudaMalloc(&ctx->d_counter, sizeof(unsigned int)));
+  HC_CUDA_NULL(cudaMemset(ctx->d_counter, 0, sizeof(unsigned int)));
+  ctx->n_partial = ctx->sm_count * 8;
+  HC_CUDA_NULL(cudaMalloc(&ctx->d_partial, sizeof(double) * ctx->n_partial));
+  if (comm_init(ctx, uid)) { delete ctx; return nullptr; }
+  return ctx;
+}
+
+void hcurl_ctx_destroy(hcurl_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  comm_destroy(ctx);
+  cudaFree(ctx->d_red); cudaFreeHost(ctx->h_red); cudaFree(ctx->d_counter); cudaFree(ctx->d_partial);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+int hcurl_ctx_device(const hcurl_ctx *ctx) { return ctx ? ctx->device : -1; }
+int hcurl_ctx_synchronize(hcurl_ctx *ctx) { HC_CUDA(cudaStreamSynchronize(ctx->stream)); return 0; }
+
+hcurl_space *hcurl_space_create(hcurl_ctx *ctx, int geom, int geom_order, int order, int64_t n_elem, const double *elem_xyz,
+                                const int32_t *elem_ldof, const int32_t *elem_verts, const int32_t *elem_face_base,
+                                int32_t n_ldof, const int32_t *ldof_ltdof, int32_t n_tdof, int n_nbr, const int32_t *nbr_rank,
+                                const int32_t *own_off, const int32_t *own_ldof, const int32_t *ghost_off,
+                                const int32_t *ghost_ldof, const int8_t *ghost_sign) {
+  if (!ctx) { set_error("null context"); return nullptr; }
+  if (geom == HCURL_GEOM_HEX) {
+    if (order < 1 || order > 4) { set_error("hex order must be 1..4 (got %d)", order); return nullptr; }
+    if (geom_order != 1 && geom_order != 2) { set_error("hex geometry order must be 1 or 2"); return nullptr; }
+  } else if (geom == HCURL_GEOM_TET) {
+    if (order < 1 || order > 3) { set_error("tet order must be 1..3 (got %d)", order); return nullptr; }
+    if (geom_order != 1) { set_error("tets must be straight (geometry order 1)"); return nullptr; }
+    if (order >= 2 && (!elem_verts || !elem_face_base)) {
+      set_error("tets of order >= 2 need elem_verts and elem_face_base (triangle-face DofTransformation)");
+      return nullptr;
+    }
+  } else { set_error("unknown geometry %d", geom); return nullptr; }
+  if (n_elem <= 0 || !elem_xyz || !elem_ldof) { set_error("empty mesh or null arrays"); return nullptr; }
+  if ((int64_t)n_ldof >= (int64_t)MAP_IDX) { set_error("too many local dofs for the 30-bit map encoding"); return nullptr; }
+  HC_CUDA_NULL(cudaSetDevice(ctx->device));
+  hcurl_space *sp = new hcurl_space;
+  sp->ctx = ctx; sp->geom = geom; sp->geom_order = geom_order; sp->order = order; sp->n_elem = n_elem;
+  sp->n_ldof = n_ldof;
+  const bool hex = geom == HCURL_GEOM_HEX;
+  sp->nd = hex ? nd_hex_ndof(order) : nd_tet_ndof(order);
+  sp->ngn = hex ? (geom_order == 1 ? 8 : 27) : 4;
+  sp->n_elem_pad = (n_elem + 31) / 32 * 32;
+  // ---- parallel layout
+  std::vector<int32_t> l2e;
+  if (ldof_ltdof) {
+    sp->n_tdof = n_tdof;
+    sp->n_nbr = n_nbr;
+    sp->nbr_rank.assign(nbr_rank, nbr_rank + n_nbr);
+    sp->own_off.assign(own_off, own_off + n_nbr + 1);
+    sp->ghost_off.assign(ghost_off, ghost_off + n_nbr + 1);
+    sp->n_ghost = n_nbr ? ghost_off[n_nbr] : 0;
+    l2e.assign(n_ldof, -1);
+    for (int32_t i = 0; i < n_ldof; i++) if (ldof_ltdof[i] >= 0) l2e[i] = ldof_ltdof[i];
+    for (int32_t g = 0; g < sp->n_ghost; g++) l2e[ghost_ldof[g]] = n_tdof + g;
+    for (int32_t i = 0; i < n_ldof; i++)
+      if (l2e[i] < 0) { set_error("ldof %d is neither owned nor listed as a ghost", i); delete sp; return nullptr; }
+    const int32_t n_own = n_nbr ? own_off[n_nbr] : 0;
+    if (n_own > 0) {
+      std::vector<int32_t> own_ext(n_own);
+      for (int32_t i = 0; i < n_own; i++) own_ext[i] = l2e[own_ldof[i]];
+      HC_CUDA_NULL(cudaMalloc(&sp->d_own_idx, sizeof(int32_t) * n_own));
+      HC_CUDA_NULL(cudaMemcpy(sp->d_own_idx, own_ext.data(), sizeof(int32_t) * n_own, cudaMemcpyHostToDevice));
+      HC_CUDA_NULL(cudaMalloc(&sp->d_sendbuf, sizeof(double) * n_own));
+      HC_CUDA_NULL(cudaMalloc(&sp->d_recvbuf, sizeof(double) * n_own));
+    }
+    if (ghost_sign && sp->n_ghost > 0) {
+      HC_CUDA_NULL(cudaMalloc(&sp->d_ghost_sign, sp->n_ghost));
+      HC_CUDA_NULL(cudaMemcpy(sp->d_ghost_sign, ghost_sign, sp->n_ghost, cudaMemcpyHostToDevice));
+    }
+    sp->ldof_to_ext = l2e;
+  } else {
+    sp->n_tdof = n_ldof;
+  }
+  // ---- geometry
+  const size_t nxyz = (size_t)n_elem * sp->ngn * 3;
+  HC_CUDA_NULL(cudaMalloc(&sp->d_xyz, sizeof(double) * nxyz));
+  if (hex && geom_order == 1) {
+    double *tmp = nullptr;
+    HC_CUDA_NULL(cudaMalloc(&tmp, sizeof(double) * nxyz));
+    HC_CUDA_NULL(cudaMemcpy(tmp, elem_xyz, sizeof(double) * nxyz, cudaMemcpyHostToDevice));
+    permute_xyz_kernel<<<(unsigned)((nxyz + 255) / 256), 256, 0, ctx->stream>>>(n_elem, tmp, sp->d_xyz);
+    HC_CUDA_NULL(cudaStreamSynchronize(ctx->stream));
+    cudaFree(tmp);
+  } else {
+    HC_CUDA_NULL(cudaMemcpy(sp->d_xyz, elem_xyz, sizeof(double) * nxyz, cudaMemcpyHostToDevice));
+  }
+  // ---- element -> dof map
+  {
+    const size_t nmap = (size_t)n_elem * sp->nd;
+    int32_t *d_ldof = nullptr;
+    HC_CUDA_NULL(cudaMalloc(&d_ldof, sizeof(int32_t) * nmap));
+    HC_CUDA_NULL(cudaMemcpy(d_ldof, elem_ldof, sizeof(int32_t) * nmap, cudaMemcpyHostToDevice));
+    int *d_loc = nullptr, *d_sgn = nullptr;
+    int32_t *d_l2e = nullptr;
+    if (hex) {
+      std::vector<int> loc, sgn;
+      nd_hex_dof_map(order, loc, sgn);
+      HC_CUDA_NULL(cudaMalloc(&d_loc, sizeof(int) * sp->nd));
+      HC_CUDA_NULL(cudaMalloc(&d_sgn, sizeof(int) * sp->nd));
+      HC_CUDA_NULL(cudaMemcpy(d_loc, loc.data(), sizeof(int) * sp->nd, cudaMemcpyHostToDevice));
+      HC_CUDA_NULL(cudaMemcpy(d_sgn, sgn.data(), sizeof(int) * sp->nd, cudaMemcpyHostToDevice));
+    }
+    if (!l2e.empty()) {
+      HC_CUDA_NULL(cudaMalloc(&d_l2e, sizeof(int32_t) * n_ldof));
+      HC_CUDA_NULL(cudaMemcpy(d_l2e, l2e.data(), sizeof(int32_t) * n_ldof, cudaMemcpyHostToDevice));
+    }
+    const size_t nout = hex ? nmap : (size_t)sp->nd * sp->n_elem_pad;
+    HC_CUDA_NULL(cudaMalloc(&sp->d_map, sizeof(uint32_t) * nout));
+    HC_CUDA_NULL(cudaMemsetAsync(sp->d_map, 0, sizeof(uint32_t) * nout, ctx->stream));
+    encode_map_kernel<<<(unsigned)((nmap + 255) / 256), 256, 0, ctx->stream>>>(n_elem, sp->nd, sp->n_elem_pad, hex ? 0 : 1, d_ldof,
+                                                                               d_loc, d_sgn, d_l2e, sp->d_map);
+    HC_CUDA_NULL(cudaGetLastError());
+    HC_CUDA_NULL(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_ldof); cudaFree(d_loc); cudaFree(d_sgn); cudaFree(d_l2e);
+  }
+  // ---- triangle-face dof transformations (tets, p >= 2)
+  if (!hex && order >= 2) {
+    const int nn = order * (order - 1) / 2;  // face nodes
+    sp->nf = 2 * nn;
+    std::vector<double> R((size_t)n_elem * 4 * sp->nf * sp->nf);
+    static const int TF[4][3] = {{1, 2, 3}, {0, 3, 2}, {0, 1, 3}, {0, 2, 1}};
+    for (int64_t e = 0; e < n_elem; e++)
+      for (int f = 0; f < 4; f++) {
+        int32_t lv[3] = {elem_verts[e * 4 + TF[f][0]], elem_verts[e * 4 + TF[f][1]], elem_verts[e * 4 + TF[f][2]]};
+        tri_face_transform(order, lv, elem_face_base + (e * 4 + f) * 3, &R[((size_t)e * 4 + f) * sp->nf * sp->nf]);
+      }
+    HC_CUDA_NULL(cudaMalloc(&sp->d_faceR, sizeof(double) * R.size()));
+    HC_CUDA_NULL(cudaMemcpy(sp->d_faceR, R.data(), sizeof(double) * R.size(), cudaMemcpyHostToDevice));
+  }
+  return sp;
+}
+
+void hcurl_space_destroy(hcurl_space *sp) {
+  if (!sp) return;
+  cudaSetDevice(sp->ctx->device);
+  cudaStreamSynchronize(sp->ctx->stream);
+  cudaFree(sp->d_xyz); cudaFree(sp->d_map); cudaFree(sp->d_faceR); cudaFree(sp->d_own_idx);
+  cudaFree(sp->d_ghost_sign); cudaFree(sp->d_sendbuf); cudaFree(sp->d_recvbuf);
+  delete sp;
+}
+int32_t hcurl_space_ndof_local(const hcurl_space *sp) { return sp->n_ldof; }
+int32_t hcurl_space_ndof_true(const hcurl_space *sp) { return sp->n_tdof; }
+int hcurl_space_elem_ndof(const hcurl_space *sp) { return sp->nd; }
+
+hcurl_op *hcurl_op_create(hcurl_ctx *ctx, hcurl_space *sp, int q) {
+  if (!ctx || !sp) { set_error("null context or space"); return nullptr; }
+  hcurl_op *op = new hcurl_op;
+  op->ctx = ctx; op->sp = sp;
+  const int p = sp->order;
+  if (sp->geom == HCURL_GEOM_HEX) {
+    if (q == 0) {
+      op->qc = p + 1;
+      op->qm = (sp->geom_order == 1) ? p + 2 : p + 3;  // order 3g-1+2p -> n = order/2+1 (odd-rounded)
+      op->single_rule = false;
+    } else if (q == p + 1 || q == p + 2) {
+      op->qc = op->qm = q;
+      op->single_rule = true;
+    } else {
+      set_error("quad_pts_per_dim must be 0, p+1 or p+2 (got %d for p=%d)", q, p);
+      delete op;
+      return nullptr;
+    }
+  }
+  HC_CUDA_NULL(cudaSetDevice(ctx->device));
+  HC_CUDA_NULL(cudaEventCreate(&op->ev0));
+  HC_CUDA_NULL(cudaEventCreate(&op->ev1));
+  op->timed = true;
+  return op;
+}
+
+void hcurl_op_destroy(hcurl_op *op) {
+  if (!op) return;
+  cudaSetDevice(op->ctx->device);
+  cudaStreamSynchronize(op->ctx->stream);
+  cudaFree(op->d_alpha); cudaFree(op->d_beta); cudaFree(op->d_map_ess); cudaFree(op->d_ess);
+  cudaFree(op->d_emat); cudaFree(op->d_xin); cudaFree(op->d_yout); cudaFree(op->d_tmp);
+  cudaEventDestroy(op->ev0); cudaEventDestroy(op->ev1);
+  delete op;
+}
+int hcurl_op_qpts_curl(const hcurl_op *op) { return op->sp->geom == HCURL_GEOM_HEX ? op->qc * op->qc * op->qc : 1; }
+int hcurl_op_qpts_mass(const hcurl_op *op) { return op->sp->geom == HCURL_GEOM_HEX ? op->qm * op->qm * op->qm : 1; }
+
+int hcurl_op_set_coefficients(hcurl_op *op, int layout, const double *alpha, const double *beta, int where) {
+  hcurl_space *sp = op->sp;
+  HC_CUDA(cudaSetDevice(op->ctx->device));
+  if (layout == HCURL_COEF_PER_QPT && sp->geom != HCURL_GEOM_HEX) { set_error("PER_QPT coefficients are hex-only"); return 1; }
+  if (layout != HCURL_COEF_PER_ELEM && layout != HCURL_COEF_PER_QPT) { set_error("bad coefficient layout %d", layout); return 1; }
+  op->coef_layout = layout;
+  const int64_t na = sp->n_elem * (layout == HCURL_COEF_PER_QPT ? hcurl_op_qpts_curl(op) : 1);
+  const int64_t nb = sp->n_elem * (layout == HCURL_COEF_PER_QPT ? hcurl_op_qpts_mass(op) : 1);
+  auto put = [&](const double *src, double *&dst, int64_t &cur, int64_t n) -> int {
+    if (!src) return 0;
+    if (cur != n) { cudaFree(dst); dst = nullptr; HC_CUDA(cudaMalloc(&dst, sizeof(double) * n)); cur = n; }
+    HC_CUDA(cudaMemcpyAsync(dst, src, sizeof(double) * n, kind_in(where), op->ctx->stream));
+    return 0;
+  };
+  if (put(alpha, op->d_alpha, op->n_alpha, na)) return 1;
+  if (put(beta, op->d_beta, op->n_beta, nb)) return 1;
+  op->has_alpha = alpha != nullptr;
+  op->has_beta = beta != nullptr;
+  HC_CUDA(cudaStreamSynchronize(op->ctx->stream));  // host buffers are borrowed for the call only
+  op->emat_valid = false;
+  return 0;
+}
+
+int hcurl_op_set_essential_tdofs(hcurl_op *op, const int32_t *ess, int32_t n_ess) {
+  hcurl_space *sp = op->sp;
+  hcurl_ctx *ctx = op->ctx;
+  HC_CUDA(cudaSetDevice(ctx->device));
+  for (int32_t i = 0; i < n_ess; i++)
+    if (ess[i] < 0 || ess[i] >= sp->n_tdof) { set_error("essential tdof %d out of range", ess[i]); return 1; }
+  cudaFree(op->d_ess); op->d_ess = nullptr;
+  cudaFree(op->d_map_ess); op->d_map_ess = nullptr;
+  op->n_ess = n_ess;
+  // flags live on the extended vector so that ghost copies of essential dofs are masked too
+  double *flag = nullptr;
+  HC_CUDA(cudaMalloc(&flag, sizeof(double) * sp->n_ext()));
+  HC_CUDA(cudaMemsetAsync(flag, 0, sizeof(double) * sp->n_ext(), ctx->stream));
+  if (n_ess > 0) {
+    HC_CUDA(cudaMalloc(&op->d_ess, sizeof(int32_t) * n_ess));
+    HC_CUDA(cudaMemcpyAsync(op->d_ess, ess, sizeof(int32_t) * n_ess, cudaMemcpyHostToDevice, ctx->stream));
+    set_flags_kernel<<<(n_ess + 255) / 256, 256, 0, ctx->stream>>>(n_ess, op->d_ess, flag, 1.0);
+  }
+  if (exchange_broadcast(sp, flag)) return 1;
+  // any rank may hold flagged ghosts even when it owns no essential dof
+  const size_t nmap = sp->geom == HCURL_GEOM_HEX ? (size_t)sp->n_elem * sp->nd : (size_t)sp->nd * sp->n_elem_pad;
+  HC_CUDA(cudaMalloc(&op->d_map_ess, sizeof(uint32_t) * nmap));
+  flag_map_kernel<<<(unsigned)((nmap + 255) / 256), 256, 0, ctx->stream>>>((int64_t)nmap, sp->d_map, flag, op->d_map_ess);
+  HC_CUDA(cudaGetLastError());
+  HC_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(flag);
+  return 0;
+}
+
+static int apply_common(hcurl_op *op, const double *x, double *y, int where, bool constrained, double scale, int accumulate) {
+  hcurl_space *sp = op->sp;
+  hcurl_ctx *ctx = op->ctx;
+  HC_CUDA(cudaSetDevice(ctx->device));
+  if (!op->has_alpha && !op->has_beta) { set_error("operator has no coefficients set"); return 1; }
+  const int64_t nt = sp->n_tdof;
+  if (where == HCURL_DEVICE && sp->n_ghost == 0) {
+    // zero-copy: the caller's device T-vectors are the extended vectors
+    return op_apply_ext(op, const_cast<double *>(x), y, constrained, scale, accumulate != 0);
+  }
+  if (ensure_work(op)) return 1;
+  HC_CUDA(cudaMemcpyAsync(op->d_xin, x, sizeof(double) * nt, kind_in(where), ctx->stream));
+  if (accumulate) HC_CUDA(cudaMemcpyAsync(op->d_yout, y, sizeof(double) * nt, kind_in(where), ctx->stream));
+  if (op_apply_ext(op, op->d_xin, op->d_yout, constrained, scale, accumulate != 0)) return 1;
+  HC_CUDA(cudaMemcpyAsync(y, op->d_yout, sizeof(double) * nt, kind_out(where), ctx->stream));
+  HC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int hcurl_op_apply(hcurl_op *op, const double *x, double *y, int where) {
+  return apply_common(op, x, y, where, true, 1.0, 0);
+}
+int hcurl_op_apply_unconstrained(hcurl_op *op, const double *x, double *y, double scale, int accumulate, int where) {
+  return apply_common(op, x, y, where, false, scale, accumulate);
+}
+
+int hcurl_op_apply_complex(hcurl_op *op_re, hcurl_op *op_im, const double *xr, const double *xi, double *yr, double *yi, int where) {
+  if (op_re->sp != op_im->sp) { set_error("complex apply: operators must share a space"); return 1; }
+  hcurl_space *sp = op_re->sp;
+  hcurl_ctx *ctx = op_re->ctx;
+  HC_CUDA(cudaSetDevice(ctx->device));
+  const int64_t nt = sp->n_tdof, next = sp->n_ext();
+  // work vectors: xr, xi, yr, yi on the extended layout
+  if (!op_re->d_tmp) HC_CUDA(cudaMalloc(&op_re->d_tmp, sizeof(double) * 4 * next));
+  double *dxr = op_re->d_tmp, *dxi = dxr + next, *dyr = dxi + next, *dyi = dyr + next;
+  HC_CUDA(cudaMemcpyAsync(dxr, xr, sizeof(double) * nt, kind_in(where), ctx->stream));
+  HC_CUDA(cudaMemcpyAsync(dxi, xi, sizeof(double) * nt, kind_in(where), ctx->stream));
+  // essential rows of the block system are identity on both parts: constrain Ar, and
+  // apply Ai with the same essential masking but no identity contribution
+  if (op_apply_ext(op_re, dxr, dyr, true, 1.0, false)) return 1;   // yr = Ar xr (ess: yr = xr)
+  if (op_apply_ext(op_re, dxi, dyi, true, 1.0, false)) return 1;   // yi = Ar xi (ess: yi = xi)
+  // masked Ai: use op_im's essential map if set, without the identity fix-up
+  {
+    const uint32_t *map = op_im->d_map_ess ? op_im->d_map_ess : sp->d_map;
+    if (exchange_broadcast(sp, dxr)) return 1;  // ghosts already valid, cheap for n_nbr = 0
+    auto run = [&](const double *xin, double *yacc, double scale) -> int {
+      if (sp->n_ghost) HC_CUDA(cudaMemsetAsync(yacc + sp->n_tdof, 0, sizeof(double) * sp->n_ghost, ctx->stream));
+      int rc = (sp->geom == HCURL_GEOM_HEX) ? hex_apply_launch(op_im, map, xin, yacc, scale) : tet_apply_launch(op_im, map, xin, yacc, scale);
+      if (rc) return rc;
+      return exchange_reduce(sp, yacc);
+    };
+    if (run(dxi, dyr, -1.0)) return 1;  // yr -= Ai xi
+    if (run(dxr, dyi, +1.0)) return 1;  // yi += Ai xr
+  }
+  HC_CUDA(cudaMemcpyAsync(yr, dyr, sizeof(double) * nt, kind_out(where), ctx->stream));
+  HC_CUDA(cudaMemcpyAsync(yi, dyi, sizeof(double) * nt, kind_out(where), ctx->stream));
+  HC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int hcurl_op_diagonal(hcurl_op *op, double *diag, int where) {
+  hcurl_space *sp = op->sp;
+  hcurl_ctx *ctx = op->ctx;
+  HC_CUDA(cudaSetDevice(ctx->device));
+  if (ensure_work(op)) return 1;
+  if (op_diag_ext(op, op->d_yout)) return 1;
+  HC_CUDA(cudaMemcpyAsync(diag, op->d_yout, sizeof(double) * sp->n_tdof, kind_out(where), ctx->stream));
+  HC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int hcurl_op_form_rhs(hcurl_op *op, const double *x_bc, const double *b, double *B, int where) {
+  hcurl_space *sp = op->sp;
+  hcurl_ctx *ctx = op->ctx;
+  HC_CUDA(cudaSetDevice(ctx->device));
+  if (ensure_work(op)) return 1;
+  const int64_t nt = sp->n_tdof, next = sp->n_ext();
+  // d_xin = x_bc restricted to essential dofs, d_yout = b - A_unconstrained d_xin, then B[ess] = x_bc[ess]
+  double *xfull = nullptr;
+  HC_CUDA(cudaMalloc(&xfull, sizeof(double) * next));
+  HC_CUDA(cudaMemcpyAsync(xfull, x_bc, sizeof(double) * nt, kind_in(where), ctx->stream));
+  HC_CUDA(cudaMemsetAsync(op->d_xin, 0, sizeof(double) * next, ctx->stream));
+  if (op->n_ess > 0) copy_idx_kernel<<<(op->n_ess + 255) / 256, 256, 0, ctx->stream>>>(op->n_ess, op->d_ess, xfull, op->d_xin);
+  HC_CUDA(cudaMemcpyAsync(op->d_yout, b, sizeof(double) * nt, kind_in(where), ctx->stream));
+  if (op_apply_ext(op, op->d_xin, op->d_yout, false, -1.0, true)) { cudaFree(xfull); return 1; }
+  if (op->n_ess > 0) copy_idx_kernel<<<(op->n_ess + 255) / 256, 256, 0, ctx->stream>>>(op->n_ess, op->d_ess, xfull, op->d_yout);
+  HC_CUDA(cudaMemcpyAsync(B, op->d_yout, sizeof(double) * nt, kind_out(where), ctx->stream));
+  HC_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(xfull);
+  return 0;
+}
+
+double hcurl_op_last_kernel_ms(hcurl_op *op) {
+  float ms = 0.f;
+  cudaSetDevice(op->ctx->device);
+  if (cudaEventSynchronize(op->ev1) != cudaSuccess) return -1.0;
+  if (cudaEventElapsedTime(&ms, op->ev0, op->ev1) != cudaSuccess) return -1.0;
+  return ms;
+}
+
+// ------------------------------------------------------------------------ PCG ----
+hcurl_pcg *hcurl_pcg_create(hcurl_ctx *ctx, hcurl_op *op, int precond) {
+  if (!ctx || !op) { set_error("null context or operator"); return nullptr; }
+  if (precond != HCURL_PC_NONE && precond != HCURL_PC_JACOBI) { set_error("unknown preconditioner %d", precond); return nullptr; }
+  HC_CUDA_NULL(cudaSetDevice(ctx->device));
+  hcurl_pcg *s = new hcurl_pcg;
+  s->ctx = ctx; s->op = op; s->precond = precond;
+  const size_t bytes = sizeof(double) * (size_t)op->sp->n_ext();
+  HC_CUDA_NULL(cudaMalloc(&s->d_r, bytes));
+  HC_CUDA_NULL(cudaMalloc(&s->d_p, bytes));
+  HC_CUDA_NULL(cudaMalloc(&s->d_s, bytes));
+  HC_CUDA_NULL(cudaMalloc(&s->d_x, bytes));
+  HC_CUDA_NULL(cudaMalloc(&s->d_b, bytes));
+  if (precond == HCURL_PC_JACOBI) HC_CUDA_NULL(cudaMalloc(&s->d_dinv, bytes));
+  HC_CUDA_NULL(cudaEventCreate(&s->ev0));
+  HC_CUDA_NULL(cudaEventCreate(&s->ev1));
+  return s;
+}
+void hcurl_pcg_destroy(hcurl_pcg *s) {
+  if (!s) return;
+  cudaSetDevice(s->ctx->device);
+  cudaStreamSynchronize(s->ctx->stream);
+  cudaFree(s->d_r); cudaFree(s->d_p); cudaFree(s->d_s); cudaFree(s->d_x); cudaFree(s->d_b); cudaFree(s->d_dinv);
+  cudaEventDestroy(s->ev0); cudaEventDestroy(s->ev1);
+  delete s;
+}
+int hcurl_pcg_set(hcurl_pcg *s, double rtol, double atol, int max_iter, int print_level) {
+  s->rtol = rtol; s->atol = atol; s->max_iter = max_iter; s->print_level = print_level;
+  return 0;
+}
+int hcurl_pcg_update(hcurl_pcg *s) { s->diag_valid = false; return 0; }
+
+int hcurl_pcg_solve(hcurl_pcg *s, const double *b, double *x, int zero_guess, int where, int *iters, double *final_rel,
+                    int *converged) {
+  hcurl_ctx *ctx = s->ctx;
+  hcurl_op *op = s->op;
+  hcurl_space *sp = op->sp;
+  HC_CUDA(cudaSetDevice(ctx->device));
+  const int64_t nt = sp->n_tdof;
+  cudaStream_t st = ctx->stream;
+  double *S = ctx->d_red;  // S[0]=gamma S[1]=<s,p> S[2]=gamma_new S[3]=bi_prod
+  const int g = red_grid(ctx, nt);
+  if (s->precond == HCURL_PC_JACOBI && !s->diag_valid) {
+    if (op_diag_ext(op, s->d_dinv)) return 1;
+    invert_kernel<<<g, RED_THREADS, 0, st>>>(nt, s->d_dinv);
+    s->diag_valid = true;
+  }
+  const double *dinv = s->precond == HCURL_PC_JACOBI ? s->d_dinv : nullptr;
+  HC_CUDA(cudaMemcpyAsync(s->d_b, b, sizeof(double) * nt, kind_in(where), st));
+  if (zero_guess) HC_CUDA(cudaMemsetAsync(s->d_x, 0, sizeof(double) * sp->n_ext(), st));
+  else HC_CUDA(cudaMemcpyAsync(s->d_x, x, sizeof(double) * nt, kind_in(where), st));
+  if (iters) *iters = 0;
+  if (final_rel) *final_rel = 0.0;
+  if (converged) *converged = 0;
+  // bi_prod = <C b, b>
+  cdot_kernel<<<g, RED_THREADS, 0, st>>>(nt, dinv, s->d_b, ctx->d_partial, ctx->d_counter, S + 3);
+  if (allreduce_sum(ctx, S + 3, 1)) return 1;
+  HC_CUDA(cudaMemcpyAsync(ctx->h_red, S, sizeof(double) * 4, cudaMemcpyDeviceToHost, st));
+  HC_CUDA(cudaStreamSynchronize(st));
+  const double bi_prod = ctx->h_red[3];
+  if (!(bi_prod > 0.0)) {
+    // hypre: zero right-hand side -> x = b
+    HC_CUDA(cudaMemcpyAsync(x, s->d_b, sizeof(double) * nt, kind_out(where), st));
+    HC_CUDA(cudaStreamSynchronize(st));
+    if (converged) *converged = 1;
+    return 0;
+  }
+  const double eps = fmax(s->rtol * s->rtol, s->atol * s->atol / bi_prod);
+  // r = b - A x ; p = C r ; gamma = <r,p>
+  if (!zero_guess) { if (op_apply_ext(op, s->d_x, s->d_r, true, 1.0, false)) return 1; }
+  pcg_init_kernel<<<g, RED_THREADS, 0, st>>>(nt, zero_guess ? 0 : 1, s->d_b, dinv, s->d_r, s->d_p, ctx->d_partial, ctx->d_counter, S + 0);
+  if (allreduce_sum(ctx, S + 0, 1)) return 1;
+  HC_CUDA(cudaMemcpyAsync(ctx->h_red, S, sizeof(double) * 4, cudaMemcpyDeviceToHost, st));
+  HC_CUDA(cudaStreamSynchronize(st));
+  double gamma = ctx->h_red[0];
+  int i = 0, conv = 0;
+  HC_CUDA(cudaEventRecord(s->ev0, st));
+  while (i + 1 <= s->max_iter) {
+    i++;
+    if (op_apply_ext(op, s->d_p, s->d_s, true, 1.0, false)) return 1;
+    dot_kernel<<<g, RED_THREADS, 0, st>>>(nt, s->d_s, s->d_p, ctx->d_partial, ctx->d_counter, S + 1);
+    if (allreduce_sum(ctx, S + 1, 1)) return 1;
+    pcg_update_kernel<<<g, RED_THREADS, 0, st>>>(nt, S, dinv, s->d_p, s->d_x, s->d_r, s->d_s, ctx->d_partial, ctx->d_counter, S + 2);
+    if (allreduce_sum(ctx, S + 2, 1)) return 1;
+    HC_CUDA(cudaMemcpyAsync(ctx->h_red, S, sizeof(double) * 4, cudaMemcpyDeviceToHost, st));
+    HC_CUDA(cudaStreamSynchronize(st));
+    const double sdotp = ctx->h_red[1], gamma_new = ctx->h_red[2];
+    if (sdotp == 0.0) { break; }
+    if (s->print_level > 1 && ctx->rank == 0) printf("  hcurl pcg it %d  rel res %.6e\n", i, sqrt(fabs(gamma_new) / bi_prod));
+    if (gamma_new / bi_prod < eps) { gamma = gamma_new; conv = 1; break; }
+    if (fabs(gamma_new) < 1e-292) { gamma = gamma_new; break; }
+    const double beta = gamma_new / gamma;
+    gamma = gamma_new;
+    pcg_dir_kernel<<<g, RED_THREADS, 0, st>>>(nt, beta, gamma_new, S, s->d_s, s->d_p);
+  }
+  HC_CUDA(cudaEventRecord(s->ev1, st));
+  HC_CUDA(cudaGetLastError());
+  HC_CUDA(cudaMemcpyAsync(x, s->d_x, sizeof(double) * nt, kind_out(where), st));
+  HC_CUDA(cudaStreamSynchronize(st));
+  cudaEventElapsedTime(&s->last_loop_ms, s->ev0, s->ev1);
+  if (iters) *iters = i;
+  if (final_rel) *final_rel = sqrt(fabs(gamma) / bi_prod);
+  if (converged) *converged = conv;
+  if (s->print_level > 0 && ctx->rank == 0)
+    printf("hcurl pcg: %d iterations, final relative residual %.6e%s\n", i, sqrt(fabs(gamma) / bi_prod), conv ? "" : " (not converged)");
+  return 0;
+}
+double hcurl_pcg_last_loop_ms(hcurl_pcg *s) { return s->last_loop_ms; }
+
+// --------------------------------------------------------------- vector helpers ----
+double *hcurl_device_alloc(hcurl_ctx *ctx, int64_t n) {
+  double *p = nullptr;
+  HC_CUDA_NULL(cudaSetDevice(ctx->device));
+  HC_CUDA_NULL(cudaMalloc(&p, sizeof(double) * (size_t)(n > 0 ? n : 1)));
+  return p;
+}
+void hcurl_device_free(hcurl_ctx *ctx, double *p) { cudaSetDevice(ctx->device); cudaFree(p); }
+int hcurl_copy_to_device(hcurl_ctx *ctx, double *dst, const double *src, int64_t n) {
+  HC_CUDA(cudaSetDevice(ctx->device));
+  HC_CUDA(cudaMemcpyAsync(dst, src, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+  HC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int hcurl_copy_to_host(hcurl_ctx *ctx, double *dst, const double *src, int64_t n) {
+  HC_CUDA(cudaSetDevice(ctx->device));
+  HC_CUDA(cudaMemcpyAsync(dst, src, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  HC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int hcurl_dot(hcurl_ctx *ctx, const double *a, const double *b, int64_t n, double *result) {
+  HC_CUDA(cudaSetDevice(ctx->device));
+  dot_kernel<<<red_grid(ctx, n), RED_THREADS, 0, ctx->stream>>>(n, a, b, ctx->d_partial, ctx->d_counter, ctx->d_red + 8);
+  if (allreduce_sum(ctx, ctx->d_red + 8, 1)) return 1;
+  HC_CUDA(cudaMemcpyAsync(ctx->h_red + 8, ctx->d_red + 8, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  HC_CUDA(cudaStreamSynchronize(ctx->stream));
+  *result = ctx->h_red[8];
+  return 0;
+}
+
+double hcurl_fp64_peak_tflops(hcurl_ctx *ctx) {
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return -1.0;
+  const int blocks = ctx->sm_count * 8, threads = 256, iters = 1 << 14;
+  double *out = nullptr;
+  if (cudaMalloc(&out, sizeof(double) * blocks * threads) != cudaSuccess) return -1.0;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  dfma_kernel<<<blocks, threads, 0, ctx->stream>>>(out, iters);
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; rep++) {
+    cudaEventRecord(e0, ctx->stream);
+    dfma_kernel<<<blocks, threads, 0, ctx->stream>>>(out, iters);
+    cudaEventRecord(e1, ctx->stream);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms < best) best = ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(out);
+  const double flops = 2.0 * 8.0 * iters * (double)blocks * threads;
+  return flops / (best * 1e-3) / 1e12;
+}
+
+}  // extern "C"

@@ -1,0 +1,157 @@
+// Internal declarations of libhcurl_b200 (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/hcurl_b200.h"
+
+namespace hcurl {
+
+void set_error(const char *fmt, ...);
+bool cuda_ok(cudaError_t e, const char *what);
+#define HC_CUDA(call)                                   \
+  do {                                                  \
+    if (!::hcurl::cuda_ok((call), #call)) return 1;     \
+  } while (0)
+#define HC_CUDA_NULL(call)                              \
+  do {                                                  \
+    if (!::hcurl::cuda_ok((call), #call)) return nullptr; \
+  } while (0)
+
+// encoded element->dof map entry: bits 0..29 index into the extended vector
+// [owned true dofs | ghosts], bit 30 essential, bit 31 sign flip
+static constexpr uint32_t MAP_IDX = 0x3fffffffu;
+static constexpr uint32_t MAP_ESS = 0x40000000u;
+static constexpr uint32_t MAP_NEG = 0x80000000u;
+
+// ---------------------------------------------------------------- basis ----
+void gauss_legendre01(int n, double *x, double *w);
+void gauss_lobatto01(int n, double *x);
+// B[q*n+i] = l_i(xq[q]), G = derivative
+void lagrange_tables(int n, const double *nodes, int nq, const double *xq, double *B, double *G);
+int nd_hex_ndof(int p);
+// loc[t] = MFEM local index of tensor-ordered basis function t, sgn[t] = +-1
+void nd_hex_dof_map(int p, std::vector<int> &loc, std::vector<int> &sgn);
+
+static constexpr int MAXQ = 7;
+static constexpr int MAXP1 = 5;
+struct HexTables {  // passed by value to kernels (copied to shared memory)
+  double Bo[MAXQ * MAXP1];   // [q][i], i < P      open basis at quad points
+  double Bc[MAXQ * MAXP1];   // [q][i], i < P+1    closed basis
+  double Gc[MAXQ * MAXP1];   // [q][i]             closed basis derivative
+  double Dq[MAXQ * MAXQ];    // [q][m] collocation derivative on the quad points
+  double Ng[MAXQ * 3];       // [q][a], a < G+1    geometry basis
+  double dNg[MAXQ * 3];
+  double wq[MAXQ];
+};
+void build_hex_tables(int p, int q, int g, HexTables &t);
+
+int nd_tet_ndof(int p);
+struct TetRef {
+  int p, nd, npk;  // npk = nd(nd+1)/2
+  // reference matrices, packed upper (i<=j) row-major: [6][npk]
+  // pair order (a,b): (0,0),(0,1),(0,2),(1,1),(1,2),(2,2); off-diagonal pairs
+  // hold the symmetrised sum  M^{ab}+M^{ba}
+  std::vector<double> Mref, Kref;
+};
+void build_tet_ref(int p, TetRef &r);
+// triangle-face dof transformation: R (nf x nf, row-major), x_local = R x_base
+void tri_face_transform(int p, const int32_t *local_verts, const int32_t *base_verts, double *R);
+
+// ----------------------------------------------------------------- NCCL ----
+struct Nccl;  // dlopen'ed function table (comm.cpp)
+
+}  // namespace hcurl
+
+struct hcurl_ctx {
+  int device = 0;
+  int rank = 0, nranks = 1;
+  cudaStream_t stream = nullptr;
+  cudaStream_t comm_stream = nullptr;
+  void *comm = nullptr;  // ncclComm_t
+  double *d_red = nullptr;   // device reduction scratch (few doubles)
+  double *h_red = nullptr;   // pinned host mirror
+  unsigned int *d_counter = nullptr;
+  double *d_partial = nullptr;  // per-block partial sums
+  int n_partial = 0;
+  int sm_count = 148;
+};
+
+struct hcurl_space {
+  hcurl_ctx *ctx = nullptr;
+  int geom = 0, geom_order = 1, order = 1;
+  int64_t n_elem = 0;
+  int nd = 0;
+  int ngn = 0;  // geometry nodes per element
+  int32_t n_ldof = 0, n_tdof = 0, n_ghost = 0;
+  int64_t n_ext() const { return (int64_t)n_tdof + n_ghost; }
+  double *d_xyz = nullptr;     // [n_elem][ngn][3]
+  uint32_t *d_map = nullptr;   // hex: [n_elem][nd] tensor order; tet: [nd][n_elem_pad]
+  int64_t n_elem_pad = 0;
+  // tets, order>=2: per element face transformation blocks, [n_elem][4][nf*nf]
+  double *d_faceR = nullptr;
+  int nf = 0;
+  // exchange
+  int n_nbr = 0;
+  std::vector<int> nbr_rank;
+  std::vector<int32_t> own_off, ghost_off;  // [n_nbr+1]
+  int32_t *d_own_idx = nullptr;             // ext indices of own-shared dofs (concatenated)
+  int8_t *d_ghost_sign = nullptr;           // [n_ghost] or null
+  double *d_sendbuf = nullptr, *d_recvbuf = nullptr;  // size own_off.back()
+  std::vector<int32_t> ldof_to_ext;  // host copy (for essential dofs etc.)
+};
+
+struct hcurl_op {
+  hcurl_ctx *ctx = nullptr;
+  hcurl_space *sp = nullptr;
+  int qc = 0, qm = 0;      // points per dim for curl / mass (hex)
+  bool single_rule = false;
+  int coef_layout = HCURL_COEF_PER_ELEM;
+  bool has_alpha = false, has_beta = false;
+  double *d_alpha = nullptr, *d_beta = nullptr;
+  int64_t n_alpha = 0, n_beta = 0;
+  uint32_t *d_map_ess = nullptr;  // copy of the map with essential flags (or null = none set)
+  int32_t *d_ess = nullptr;       // essential ext indices
+  int32_t n_ess = 0;
+  // tets: packed element matrices [npk][n_elem_pad]
+  double *d_emat = nullptr;
+  bool emat_valid = false;
+  // work vectors (extended length)
+  double *d_xin = nullptr, *d_yout = nullptr, *d_tmp = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+};
+
+struct hcurl_pcg {
+  hcurl_ctx *ctx = nullptr;
+  hcurl_op *op = nullptr;
+  int precond = HCURL_PC_JACOBI;
+  double rtol = 1e-9, atol = 1e-16;
+  int max_iter = 1000, print_level = 0;
+  double *d_dinv = nullptr, *d_r = nullptr, *d_p = nullptr, *d_s = nullptr, *d_x = nullptr, *d_b = nullptr;
+  bool diag_valid = false;
+  float last_loop_ms = 0.f;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace hcurl {
+// kernels / drivers implemented in the .cu files (all enqueue on ctx->stream)
+int hex_apply_launch(hcurl_op *op, const uint32_t *d_map, const double *d_x, double *d_y, double scale);
+int hex_diag_launch(hcurl_op *op, double *d_diag);
+int tet_build_emat(hcurl_op *op);
+int tet_apply_launch(hcurl_op *op, const uint32_t *d_map, const double *d_x, double *d_y, double scale);
+int tet_diag_launch(hcurl_op *op, double *d_diag);
+// exchange (comm.cu): broadcast owner->ghost on x_ext, reduce ghost->owner on y_ext
+int exchange_broadcast(hcurl_space *sp, double *d_ext);
+int exchange_reduce(hcurl_space *sp, double *d_ext);
+int allreduce_sum(hcurl_ctx *ctx, double *d_vals, int n);
+int comm_init(hcurl_ctx *ctx, const void *uid);
+void comm_destroy(hcurl_ctx *ctx);
+int comm_unique_id(void *out128);
+// the apply on extended device vectors, including exchange and essential handling
+int op_apply_ext(hcurl_op *op, double *d_x_ext, double *d_y_ext, bool constrained, double scale, bool accumulate);
+int op_diag_ext(hcurl_op *op, double *d_diag_ext);
+}  // namespace hcurl

@@ -1,0 +1,208 @@
+/*
+ * hcurl_b200.h -- C ABI of libhcurl_b200.so
+ *
+ * B200-native (sm_100a) matrix-free apply of the Nedelec H(curl) operator
+ *
+ *      A = (alpha curl u, curl v) + (beta u, v)
+ *
+ * and a device-resident Jacobi-preconditioned CG around it.  This is the
+ * drop-in boundary for ONE hot path of aurora-multiphysics/hephaestus
+ * (SURVEY.md section 8).  Every entry point names the reference interface it
+ * replaces (file:line under /root/reference).  Plain pointers and sizes only;
+ * no C++ or torch types cross this boundary.
+ *
+ * Conventions
+ *  - All functions returning int return 0 on success, non-zero on error;
+ *    hcurl_last_error() then describes the failure (thread-local string).
+ *    The reference's error behaviour is MFEM_ABORT; the C++ adaptor
+ *    (adaptor/heph_gpu_operator.hpp) turns non-zero into MFEM_ABORT.
+ *  - Handles are opaque, one set per rank/GPU, not thread-safe (the reference
+ *    is single-threaded per MPI rank), freed by the matching *_destroy.
+ *  - Host pointers are borrowed for the duration of the call only.
+ *  - Vectors are FP64.  Local indices are int32, global sizes int64.
+ *  - There is NO CPU fallback: every compute entry point fails if no CUDA
+ *    device is usable.
+ */
+#ifndef HCURL_B200_H
+#define HCURL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hcurl_ctx hcurl_ctx;
+typedef struct hcurl_space hcurl_space;
+typedef struct hcurl_op hcurl_op;
+typedef struct hcurl_pcg hcurl_pcg;
+
+/* element geometry kinds */
+enum { HCURL_GEOM_HEX = 0, HCURL_GEOM_TET = 1 };
+/* coefficient layouts: one value per element, or one per quadrature point
+ * (x-fastest tensor order of the operator's rule; curl rule for alpha, mass
+ * rule for beta).  PER_QPT is hex-only. */
+enum { HCURL_COEF_PER_ELEM = 0, HCURL_COEF_PER_QPT = 1 };
+/* preconditioners: HCURL_PC_JACOBI reproduces mfem::HypreDiagScale */
+enum { HCURL_PC_NONE = 0, HCURL_PC_JACOBI = 1 };
+/* where a vector argument lives */
+enum { HCURL_HOST = 0, HCURL_DEVICE = 1 };
+
+/* library / build info; never touches the GPU */
+const char *hcurl_version(void);
+const char *hcurl_last_error(void);
+
+/* ---- context -------------------------------------------------------------
+ * One per rank.  `device` is the CUDA ordinal.  For multi-GPU runs pass the
+ * 128-byte NCCL unique id obtained from hcurl_comm_unique_id() on rank 0 and
+ * broadcast by the host (MPI_Bcast in the reference's world,
+ * /root/reference/examples/team7/Main.cpp:155 creates the ParMesh on
+ * MPI_COMM_WORLD); pass NULL / nranks = 1 for a single GPU.
+ * Replaces: the implicit MPI communicator inside mfem::ParMesh /
+ * HypreParMatrix on the hot path. */
+int hcurl_comm_unique_id(void *id128);
+hcurl_ctx *hcurl_ctx_create(int device, const void *nccl_unique_id128, int rank, int nranks);
+void hcurl_ctx_destroy(hcurl_ctx *ctx);
+int hcurl_ctx_device(const hcurl_ctx *ctx);
+int hcurl_ctx_synchronize(hcurl_ctx *ctx);
+
+/* ---- finite element space --------------------------------------------------
+ * Replaces: the data `ParFiniteElementSpace` feeds to the assembly in
+ * `EquationSystem::BuildBilinearForms`
+ * (/root/reference/src/equation_systems/equation_system.cpp:324-347) for an
+ * "ND_3D_P<order>" collection
+ * (/root/reference/src/problem_builders/problem_builder_base.cpp:98-127).
+ *
+ *  geom        HCURL_GEOM_HEX | HCURL_GEOM_TET
+ *  geom_order  1 (8 / 4 corner nodes per element) or 2 (hex only: 27 nodes,
+ *              tensor order x-fastest on {0,1/2,1}^3)
+ *  order       Nedelec order p (hex 1..4, tet 1..3)
+ *  elem_xyz    [n_elem][n_geom_nodes][3] doubles: element node coordinates
+ *              (corner order = MFEM / Exodus HEX8 / TETRA4)
+ *  elem_ldof   [n_elem][nd] signed local dof ids in MFEM's element-local order
+ *              (edges | faces | interior); k >= 0 plain, -1-k sign flipped --
+ *              exactly FiniteElementSpace::GetElementDofs.
+ *  elem_face_base  tets with order >= 2 only, else NULL: [n_elem][4][3] global
+ *              vertex ids of each local face in the mesh's own (base) face
+ *              vertex order (Mesh::GetFaceVertices), and
+ *  elem_verts  [n_elem][4] global vertex ids of the element; the library
+ *              derives MFEM's ND triangle-face DofTransformation from them.
+ *  n_ldof      number of local (L-vector) dofs on this rank
+ *
+ * Parallel layout (ParFiniteElementSpace::GetLocalTDofNumber /
+ * GroupCommunicator semantics).  Pass n_nbr = 0 and
+ * ldof_ltdof = NULL on a single rank (T-vector == L-vector).
+ *  ldof_ltdof  [n_ldof] local true-dof index of each ldof this rank OWNS,
+ *              -1 for ldofs owned by another rank
+ *  n_tdof      number of true dofs owned by this rank
+ *  nbr_rank    [n_nbr] neighbour ranks
+ *  own_off     [n_nbr+1] offsets into own_ldof: ldofs this rank owns that
+ *              neighbour r also holds (this rank SENDS their values on
+ *              broadcast and RECEIVES partial sums on reduce)
+ *  ghost_off   [n_nbr+1] offsets into ghost_ldof/ghost_sign: ldofs owned by
+ *              neighbour r (received on broadcast, sent on reduce).  Both
+ *              sides must list a shared pair of ranks' dofs in the same order.
+ *  ghost_sign  [..] +1/-1: orientation of the local dof relative to the
+ *              owner's (ND sign flips across ranks), or NULL for all +1
+ */
+hcurl_space *hcurl_space_create(hcurl_ctx *ctx, int geom, int geom_order, int order, int64_t n_elem,
+                                const double *elem_xyz, const int32_t *elem_ldof,
+                                const int32_t *elem_verts, const int32_t *elem_face_base,
+                                int32_t n_ldof, const int32_t *ldof_ltdof, int32_t n_tdof, int n_nbr,
+                                const int32_t *nbr_rank, const int32_t *own_off, const int32_t *own_ldof,
+                                const int32_t *ghost_off, const int32_t *ghost_ldof,
+                                const int8_t *ghost_sign);
+void hcurl_space_destroy(hcurl_space *sp);
+int32_t hcurl_space_ndof_local(const hcurl_space *sp);
+int32_t hcurl_space_ndof_true(const hcurl_space *sp);
+int hcurl_space_elem_ndof(const hcurl_space *sp);
+
+/* ---- operator ----------------------------------------------------------------
+ * A = K(alpha) + M(beta) with essential rows/cols replaced by identity.
+ * Replaces: CurlCurlKernel::Apply (/root/reference/src/kernels/curl_curl_kernel.cpp:21-24),
+ * VectorFEMassKernel::Apply (/root/reference/src/kernels/vector_fe_mass_kernel.cpp:21-24),
+ * blf->Assemble() + FormLinearSystem + HypreParMatrixFromBlocks
+ * (/root/reference/src/equation_systems/equation_system.cpp:132-190, :345) and the
+ * operator the result is used as: EquationSystem::Mult / GetGradient (ibid. :200-210).
+ *
+ *  quad_pts_per_dim  0 = MFEM's full-assembly rules (curl-curl: p+1 points per
+ *                    dimension; mass: p+2 on trilinear hexes, p+3 on HEX27;
+ *                    exact rules on straight tets), or p+1 / p+2 to force one
+ *                    Gauss rule for both terms on hexes (p+1 is exact on
+ *                    affine hexes with per-element-constant coefficients).
+ */
+hcurl_op *hcurl_op_create(hcurl_ctx *ctx, hcurl_space *sp, int quad_pts_per_dim);
+void hcurl_op_destroy(hcurl_op *op);
+/* Number of coefficient values expected per element for PER_QPT layout. */
+int hcurl_op_qpts_curl(const hcurl_op *op);
+int hcurl_op_qpts_mass(const hcurl_op *op);
+/* alpha or beta may be NULL = term absent (magnetostatic: beta NULL,
+ * /root/reference/src/formulations/Magnetostatic/statics_formulation.cpp:145-148;
+ * mass solves: alpha NULL, /root/reference/src/auxsolvers/scaled_vector_gridfunction_aux.cpp:51-60).
+ * Cheap to call every time step (Coefficients::SetTime,
+ * /root/reference/src/problem_operators/time_domain_equation_system_problem_operator.cpp:43;
+ * dt change, equation_system.cpp:413-426): no rebuild, values only. */
+int hcurl_op_set_coefficients(hcurl_op *op, int layout, const double *alpha, const double *beta,
+                              int where);
+/* Essential true dofs (EquationSystem::_ess_tdof_lists,
+ * /root/reference/src/equation_systems/equation_system.hpp:94): rows/cols -> identity. */
+int hcurl_op_set_essential_tdofs(hcurl_op *op, const int32_t *ess_tdof, int32_t n_ess);
+/* y = A x on T-vectors (EquationSystem::Mult, equation_system.cpp:200-204). */
+int hcurl_op_apply(hcurl_op *op, const double *x, double *y, int where);
+/* y = K(alpha)+M(beta) applied WITHOUT essential elimination, scaled and
+ * accumulated: y = scale * A x + (accumulate ? y : 0).  This is the
+ * WeakCurlCurlKernel RHS term  lf -= K(alpha) u_n
+ * (/root/reference/src/kernels/weak_curl_curl_kernel.cpp:14-31) and the
+ * boundary lift  B -= A_e x_bc  of FormLinearSystem. */
+int hcurl_op_apply_unconstrained(hcurl_op *op, const double *x, double *y, double scale,
+                                 int accumulate, int where);
+/* Complex (HERMITIAN convention) block apply [[Ar, -Ai], [Ai, Ar]]
+ * (/root/reference/src/formulations/ComplexMaxwell/complex_maxwell_formulation.cpp:181-217):
+ * yr = Ar xr - Ai xi,  yi = Ai xr + Ar xi.  op_re and op_im share a space. */
+int hcurl_op_apply_complex(hcurl_op *op_re, hcurl_op *op_im, const double *xr, const double *xi,
+                           double *yr, double *yi, int where);
+/* diag(A) with essential entries = 1 (what mfem::HypreDiagScale reads). */
+int hcurl_op_diagonal(hcurl_op *op, double *diag, int where);
+/* FormLinearSystem RHS (equation_system.cpp:149-152):
+ * B = b - A_unconstrained * x_bc(ess only), B[ess] = x[ess]. */
+int hcurl_op_form_rhs(hcurl_op *op, const double *x_bc, const double *b, double *B, int where);
+/* average device time (ms) of the element kernel(s) of the most recent apply */
+double hcurl_op_last_kernel_ms(hcurl_op *op);
+
+/* ---- Krylov solver ---------------------------------------------------------------
+ * hypre PCG semantics (two_norm = 0) with optional Jacobi preconditioner.
+ * Replaces: mfem::HyprePCG + mfem::HypreDiagScale as configured by
+ * DefaultJacobiPCGSolver (/root/reference/src/solvers/hephaestus_solvers.hpp:34-57) and
+ * ProblemBuilder::ConstructJacobianSolverWithOptions
+ * (/root/reference/src/problem_builders/problem_builder_base.cpp:220-254), called from
+ * TimeDomainEquationSystemProblemOperator::ImplicitSolve
+ * (/root/reference/src/problem_operators/time_domain_equation_system_problem_operator.cpp:46-48). */
+hcurl_pcg *hcurl_pcg_create(hcurl_ctx *ctx, hcurl_op *op, int precond);
+void hcurl_pcg_destroy(hcurl_pcg *pcg);
+int hcurl_pcg_set(hcurl_pcg *pcg, double rtol, double atol, int max_iter, int print_level);
+/* Re-read the operator (new coefficients / essential dofs): recomputes the
+ * Jacobi diagonal.  mfem::Solver::SetOperator. */
+int hcurl_pcg_update(hcurl_pcg *pcg);
+/* Solve A x = b.  zero_initial_guess = !iterative_mode.  Outputs iteration
+ * count, final relative residual sqrt(<Cr,r>/<Cb,b>), converged flag. */
+int hcurl_pcg_solve(hcurl_pcg *pcg, const double *b, double *x, int zero_initial_guess, int where,
+                    int *iters, double *final_rel_res, int *converged);
+/* device time (ms) spent inside the iteration loop of the most recent solve */
+double hcurl_pcg_last_loop_ms(hcurl_pcg *pcg);
+
+/* ---- vector helpers (device memory owned by the library) --------------------- */
+double *hcurl_device_alloc(hcurl_ctx *ctx, int64_t n_doubles);
+void hcurl_device_free(hcurl_ctx *ctx, double *p);
+int hcurl_copy_to_device(hcurl_ctx *ctx, double *dst_dev, const double *src_host, int64_t n);
+int hcurl_copy_to_host(hcurl_ctx *ctx, double *dst_host, const double *src_dev, int64_t n);
+/* global dot product over true dofs (all-reduced across ranks) */
+int hcurl_dot(hcurl_ctx *ctx, const double *a_dev, const double *b_dev, int64_t n, double *result);
+
+/* FP64 FMA micro-benchmark used for the roofline co-bound:
+ * returns achieved TFLOP/s of dependent-chain-free DFMA on the device. */
+double hcurl_fp64_peak_tflops(hcurl_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HCURL_B200_H */

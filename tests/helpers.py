@@ -1,0 +1,34 @@
+"""Shared builders for the parity tests: the same seeded inputs go to the CUDA
+path (through the C ABI) and to the CPU oracle."""
+import numpy as np
+
+from hephaestus_b200 import fespace
+from oracle import mesh as om
+from oracle import space as osp
+
+
+def make_pair(kind, n, p, perturb=True, dims=(1.0, 0.7, 1.3), scramble=False):
+    """(product mesh/space, oracle mesh/space) built independently."""
+    nx, ny, nz = (n, n, n) if np.isscalar(n) else n
+    m = fespace.cartesian_hex_mesh(nx, ny, nz, *dims)
+    mo = om.cartesian_hex(nx, ny, nz, *dims)
+    if perturb:
+        m, mo = fespace.perturb_interior(m), om.perturb_interior(mo)
+    if kind == "tet":
+        m, mo = fespace.hex_to_tets(m), om.hex_to_tets(mo)
+    if scramble:
+        perm = np.random.default_rng(5).permutation(len(m.verts))
+        inv = np.empty_like(perm)
+        inv[perm] = np.arange(len(perm))
+        m = fespace.Mesh(kind, m.verts[perm], inv[m.elems], m.attr)
+        mo = om.Mesh(kind, mo.verts[perm], inv[mo.elems], mo.attr)
+    return m, fespace.NDSpace(m, p), mo, osp.NDSpace(mo, p)
+
+
+def coefficients(mesh, seed=3):
+    rng = np.random.default_rng(seed)
+    return rng.uniform(0.5, 2.0, mesh.n_elem), rng.uniform(0.5, 2.0, mesh.n_elem)
+
+
+def rel_err(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)

@@ -1,0 +1,177 @@
+"""GPU parity tests: the CUDA operator (through the C ABI) against the CPU oracle.
+Bar: FP64 relative error <= 1e-12 (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+from hephaestus_b200 import _lib as L
+from hephaestus_b200 import operators
+from oracle import assemble as oa
+
+from helpers import coefficients, make_pair, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def _check_apply(ctx, kind, n, p, q, perturb, scramble=False, ess=True, alpha_on=True, beta_on=True):
+    m, sp, mo, so = make_pair(kind, n, p, perturb, scramble=scramble)
+    assert np.array_equal(sp.signed_elem_dofs(), so.signed_elem_dofs())
+    a, b = coefficients(m)
+    gsp = operators.GpuNDSpace(ctx, sp)
+    op = operators.HephGpuOperator(ctx, gsp, q)
+    op.SetCoefficients(a if alpha_on else None, b if beta_on else None)
+    essd = sp.boundary_dofs(lambda c: c[:, 2] < 1e-9) if ess else np.zeros(0, np.int32)
+    op.SetEssentialTrueDofs(essd)
+    x = np.random.default_rng(12345).standard_normal(sp.ndof)
+    y = op.Mult(x)
+    A = oa.assemble(so, a if alpha_on else None, b if beta_on else None, q_override=q if q else None)
+    y_ref = oa.constrained_apply(A, essd, x)
+    err = rel_err(y, y_ref)
+    assert err < TOL, (kind, n, p, q, perturb, err)
+    # diagonal
+    d = op.Diagonal()
+    Ac, _ = oa.eliminate(A, essd)
+    assert rel_err(d, Ac.diagonal()) < TOL
+    # unconstrained scaled accumulate
+    y0 = np.random.default_rng(1).standard_normal(sp.ndof)
+    y2 = op.MultUnconstrained(x, y0.copy(), scale=-0.5, accumulate=True)
+    assert rel_err(y2, y0 - 0.5 * (A @ x)) < TOL
+    return op, A, essd, sp
+
+
+@pytest.mark.parametrize("p", [1, 2, 3, 4])
+@pytest.mark.parametrize("perturb", [False, True])
+def test_hex_apply_mfem_rule(ctx, p, perturb):
+    _check_apply(ctx, "hex", 3 if p < 4 else 2, p, 0, perturb)
+
+
+@pytest.mark.parametrize("p", [1, 2, 3, 4])
+def test_hex_apply_fast_rule(ctx, p):
+    _check_apply(ctx, "hex", 3 if p < 4 else 2, p, p + 1, True, scramble=True)
+
+
+@pytest.mark.parametrize("p", [1, 2])
+def test_hex_apply_q_p2(ctx, p):
+    _check_apply(ctx, "hex", 3, p, p + 2, True)
+
+
+def test_hex_affine_rules_agree(ctx):
+    """On affine hexes with per-element-constant coefficients p+1 points are exact:
+    the fast rule and MFEM's rule must give the same operator."""
+    m, sp, mo, so = make_pair("hex", 4, 2, perturb=False)
+    a, b = coefficients(m)
+    gsp = operators.GpuNDSpace(ctx, sp)
+    x = np.random.default_rng(0).standard_normal(sp.ndof)
+    ys = []
+    for q in (0, 3):
+        op = operators.HephGpuOperator(ctx, gsp, q)
+        op.SetCoefficients(a, b)
+        ys.append(op.Mult(x))
+    assert rel_err(ys[0], ys[1]) < TOL
+
+
+@pytest.mark.parametrize("terms", ["curl", "mass"])
+def test_hex_single_term(ctx, terms):
+    _check_apply(ctx, "hex", 3, 2, 0, True, alpha_on=terms == "curl", beta_on=terms == "mass")
+
+
+def test_hex_ragged_batch(ctx):
+    """element count not a multiple of the CTA batch; single element."""
+    _check_apply(ctx, "hex", (5, 3, 1), 2, 0, True)
+    _check_apply(ctx, "hex", (1, 1, 1), 2, 0, False, ess=False)
+    _check_apply(ctx, "hex", (1, 1, 1), 1, 0, False, ess=False)
+
+
+def test_hex_per_qpt_coefficients(ctx):
+    m, sp, mo, so = make_pair("hex", 3, 2, True)
+    gsp = operators.GpuNDSpace(ctx, sp)
+    op = operators.HephGpuOperator(ctx, gsp, 0)
+
+    def mu(X, attr=None):
+        return 1.0 / (1.0 + 0.5 * np.cos(np.pi * X[:, 0]) * np.cos(np.pi * X[:, 1]))
+
+    def sig(X, attr=None):
+        return 1.0 + X[:, 2] ** 2
+    # sample at the operator's quadrature points (x-fastest tensor order): the oracle's rule order
+    (cp, _), (mp, _) = oa.default_rules(so)
+    _, xc = oa.hex8_jacobians(mo.elem_coords(), cp)
+    _, xm = oa.hex8_jacobians(mo.elem_coords(), mp)
+    a = mu(xc.reshape(-1, 3)).reshape(m.n_elem, -1)
+    b = sig(xm.reshape(-1, 3)).reshape(m.n_elem, -1)
+    assert a.shape[1] == op.qpts_curl and b.shape[1] == op.qpts_mass
+    op.SetCoefficients(a, b, layout=L.PER_QPT)
+    x = np.random.default_rng(12345).standard_normal(sp.ndof)
+    y = op.Mult(x)
+    A = oa.assemble(so, mu, sig)
+    assert rel_err(y, A @ x) < TOL
+    assert rel_err(op.Diagonal(), A.diagonal()) < TOL
+
+
+@pytest.mark.parametrize("p", [1, 2, 3])
+@pytest.mark.parametrize("scramble", [False, True])
+def test_tet_apply(ctx, p, scramble):
+    _check_apply(ctx, "tet", 2, p, 0, True, scramble=scramble)
+
+
+def test_form_rhs(ctx):
+    op, A, essd, sp = _check_apply(ctx, "hex", 3, 2, 0, True)
+    rng = np.random.default_rng(7)
+    xbc, b = rng.standard_normal(sp.ndof), rng.standard_normal(sp.ndof)
+    B = op.FormRHS(xbc, b)
+    _, B_ref = oa.eliminate(A, essd, xbc, b)
+    assert rel_err(B, B_ref) < TOL
+
+
+def test_complex_apply(ctx):
+    """[[Ar,-Ai],[Ai,Ar]] with Ar = K(1/mu) - w^2 M(eps), Ai = w M(sigma)
+    (complex_maxwell_formulation.cpp:181-190)."""
+    m, sp, mo, so = make_pair("tet", 2, 1, True)
+    gsp = operators.GpuNDSpace(ctx, sp)
+    rng = np.random.default_rng(11)
+    nu, eps, sig = rng.uniform(.5, 2, m.n_elem), rng.uniform(.5, 2, m.n_elem), rng.uniform(.5, 2, m.n_elem)
+    w = 2.5
+    op_re = operators.HephGpuOperator(ctx, gsp, 0)
+    op_re.SetCoefficients(nu, -w * w * eps)
+    op_im = operators.HephGpuOperator(ctx, gsp, 0)
+    op_im.SetCoefficients(None, w * sig)
+    essd = sp.boundary_dofs(lambda c: c[:, 0] < 1e-9)
+    op_re.SetEssentialTrueDofs(essd)
+    op_im.SetEssentialTrueDofs(essd)
+    xr, xi = rng.standard_normal(sp.ndof), rng.standard_normal(sp.ndof)
+    yr, yi = operators.complex_mult(op_re, op_im, xr, xi)
+    Ar = oa.assemble(so, nu, -w * w * eps)
+    Ai = oa.assemble(so, None, w * sig)
+    Arc, _ = oa.eliminate(Ar, essd)
+    keep = np.ones(sp.ndof)
+    keep[essd] = 0
+    Aic = Ai.multiply(keep[:, None]).multiply(keep[None, :]).tocsr()
+    assert rel_err(yr, Arc @ xr - Aic @ xi) < TOL
+    assert rel_err(yi, Aic @ xr + Arc @ xi) < TOL
+
+
+def test_device_resident_apply_matches_host_path(ctx):
+    m, sp, mo, so = make_pair("hex", 4, 2, True)
+    a, b = coefficients(m)
+    gsp = operators.GpuNDSpace(ctx, sp)
+    op = operators.HephGpuOperator(ctx, gsp, 0)
+    op.SetCoefficients(a, b)
+    op.SetEssentialTrueDofs(sp.boundary_dofs())
+    x = np.random.default_rng(2).standard_normal(sp.ndof)
+    y_host = op.Mult(x)
+    dx, dy = ctx.alloc(sp.ndof).upload(x), ctx.alloc(sp.ndof)
+    op.Mult(dx, dy)
+    ctx.synchronize()
+    assert rel_err(dy.download(), y_host) < 1e-14
+    assert op.last_kernel_ms() > 0
+
+
+def test_errors_are_loud(ctx):
+    m, sp, mo, so = make_pair("hex", 2, 1, False)
+    gsp = operators.GpuNDSpace(ctx, sp)
+    with pytest.raises(L.HcurlError):
+        operators.HephGpuOperator(ctx, gsp, 7)
+    op = operators.HephGpuOperator(ctx, gsp, 0)
+    with pytest.raises(L.HcurlError):
+        op.Mult(np.zeros(sp.ndof))  # no coefficients yet
+    with pytest.raises(L.HcurlError):
+        op.SetEssentialTrueDofs(np.array([sp.ndof + 5], np.int32))

@@ -1,0 +1,93 @@
+"""GPU PCG (hypre semantics + Jacobi) against the oracle's restatement of
+DefaultJacobiPCGSolver (/root/reference/src/solvers/hephaestus_solvers.hpp:34-57)."""
+import numpy as np
+import pytest
+
+from hephaestus_b200 import operators
+from oracle import assemble as oa
+from oracle import pcg as opcg
+
+from helpers import coefficients, make_pair, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(ctx, kind, n, p, alpha_scale=1.0):
+    m, sp, mo, so = make_pair(kind, n, p, True)
+    a, b = coefficients(m)
+    a = a * alpha_scale
+    gsp = operators.GpuNDSpace(ctx, sp)
+    op = operators.HephGpuOperator(ctx, gsp, 0)
+    op.SetCoefficients(a, b)
+    ess = sp.boundary_dofs()
+    op.SetEssentialTrueDofs(ess)
+    A = oa.assemble(so, a, b)
+    Ac, _ = oa.eliminate(A, ess)
+    return op, Ac, sp
+
+
+@pytest.mark.parametrize("kind,n,p", [("hex", 4, 1), ("hex", 4, 2), ("hex", 3, 3), ("tet", 3, 1), ("tet", 2, 2)])
+def test_pcg_matches_oracle(ctx, kind, n, p):
+    op, Ac, sp = _setup(ctx, kind, n, p, alpha_scale=0.05)
+    b = Ac @ np.random.default_rng(54321).standard_normal(sp.ndof)
+    s = operators.HephGpuPCG(ctx, tol=1e-9, max_iter=5000)
+    s.SetOperator(op)
+    x = s.Mult(b)
+    xo, it, res, conv, hist = opcg.pcg(Ac, b, diag=Ac.diagonal(), rtol=s.tol, atol=s.abstol, max_iter=5000)
+    assert s.converged and conv
+    assert abs(s.num_iterations - it) <= max(2, it // 50), (s.num_iterations, it)
+    assert rel_err(x, xo) < 1e-6
+    # true residual meets the tolerance in the C-norm
+    r = b - Ac @ x
+    assert np.sqrt((r * r / Ac.diagonal()).sum() / (b * b / Ac.diagonal()).sum()) < 10 * s.tol
+
+
+def test_pcg_mass_only_and_unpreconditioned(ctx):
+    """The configuration the reference itself runs with Jacobi-PCG: H(curl) mass solves
+    (/root/reference/src/auxsolvers/scaled_vector_gridfunction_aux.cpp:51-60)."""
+    m, sp, mo, so = make_pair("hex", 4, 2, True)
+    _, b_ = coefficients(m)
+    gsp = operators.GpuNDSpace(ctx, sp)
+    op = operators.HephGpuOperator(ctx, gsp, 0)
+    op.SetCoefficients(None, b_)
+    op.SetEssentialTrueDofs(np.zeros(0, np.int32))
+    M = oa.assemble(so, None, b_)
+    rhs = M @ np.random.default_rng(1).standard_normal(sp.ndof)
+    for jac in (True, False):
+        s = operators.HephGpuPCG(ctx, tol=1e-9, max_iter=1000, jacobi=jac)
+        s.SetOperator(op)
+        x = s.Mult(rhs)
+        xo, it, _, conv, _ = opcg.pcg(M, rhs, diag=M.diagonal() if jac else None, rtol=s.tol, atol=s.abstol)
+        assert s.converged and conv and abs(s.num_iterations - it) <= 2
+        assert rel_err(x, xo) < 1e-7
+
+
+def test_pcg_max_iter_and_zero_rhs(ctx):
+    op, Ac, sp = _setup(ctx, "hex", 3, 2)
+    s = operators.HephGpuPCG(ctx, tol=1e-14, max_iter=3)
+    s.SetOperator(op)
+    b = Ac @ np.ones(sp.ndof)
+    s.Mult(b)
+    assert s.num_iterations == 3 and not s.converged
+    x = s.Mult(np.zeros(sp.ndof))
+    assert s.num_iterations == 0 and np.all(x == 0)
+
+
+def test_pcg_reuse_after_coefficient_update(ctx):
+    """dt / Coefficients::SetTime change: same operator handle, new values
+    (equation_system.cpp:413-435)."""
+    m, sp, mo, so = make_pair("hex", 3, 2, True)
+    a, b = coefficients(m)
+    gsp = operators.GpuNDSpace(ctx, sp)
+    op = operators.HephGpuOperator(ctx, gsp, 0)
+    ess = sp.boundary_dofs()
+    op.SetEssentialTrueDofs(ess)
+    s = operators.HephGpuPCG(ctx, tol=1e-10, max_iter=5000)
+    for dt in (0.05, 0.2):
+        op.SetCoefficients(dt * a, b)
+        s.SetOperator(op)
+        Ac, _ = oa.eliminate(oa.assemble(so, dt * a, b), ess)
+        rhs = Ac @ np.random.default_rng(4).standard_normal(sp.ndof)
+        x = s.Mult(rhs)
+        xo, it, _, _, _ = opcg.pcg(Ac, rhs, diag=Ac.diagonal(), rtol=s.tol, atol=s.abstol, max_iter=5000)
+        assert abs(s.num_iterations - it) <= 2 and rel_err(x, xo) < 1e-6
