@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- H(curl) operator-apply throughput (GDOF/s) on the synthetic
+structured hex cube of BASELINE.json (order-2 Nedelec, >= 50 M DOFs per GPU), with
+roofline, PCG iterations/s, the host-buffer end-to-end number and the CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    (N > 1: launched under torchrun, one rank per GPU)
+
+A "step" is one apply  y = A x  of  A = K(dt nu) + M(sigma)  (all six faces
+essential) over the whole mesh.  `value` is timed with the operands resident in HBM,
+`e2e` through the host-buffer C-ABI call (hcurl_op_apply, HCURL_HOST) with pinned host
+buffers.  Only the cpu_baseline / --impl reference legs touch oracle/.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DT = 0.05
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--n", type=int, default=128, help="hexes per edge of the per-GPU cube")
+    ap.add_argument("--order", type=int, default=2)
+    ap.add_argument("--perturbed", action="store_true", help="trilinearly perturbed mesh variant (general geometry)")
+    ap.add_argument("--quad", default="fast", choices=["fast", "mfem"])
+    ap.add_argument("--pcg-iters", type=int, default=50)
+    ap.add_argument("--cpu-n", type=int, default=24, help="cube size of the bounded CPU sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def coefficients(attr):
+    nu = np.where(attr == 1, 1.0, 2.0)
+    sigma = np.where(attr == 1, 1.0, 1.0e3)
+    return DT * nu, sigma
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get("hbm_gbs", 6650.0), "measured"
+    return 6650.0, "fallback"
+
+
+def algorithmic_bytes(n_dof, n_elem, nd, ngn=8):
+    """SURVEY.md 8d contract: x read + y written once (16 B/DOF) + per element the signed
+    int32 map (4 nd), the geometry nodes (8*3*ngn) and alpha, beta (16)."""
+    return 16.0 * n_dof + n_elem * (4.0 * nd + 8.0 * 3 * ngn + 16.0)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons with NVML while the timed regions run."""
+
+    def __init__(self, index=0, period=0.02):
+        super().__init__(daemon=True)
+        self.period, self.index = period, index
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._halt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake": 0x80, "sync_boost": 0x10}
+        while not self._halt.is_set():
+            try:
+                util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((mhz, util))
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=2)
+        loaded = [m for m, u in self.samples if u > 0] or [m for m, _ in self.samples]
+        return {"sm_mhz": float(np.median(loaded)) if loaded else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_sample(n, p, steps, warmup, pcg_iters, threads=None):
+    """The reference's algorithm on the host: assembled CSR SpMV + Jacobi-PCG (oracle port)."""
+    from oracle import assemble as oa
+    from oracle import csr as ocsr
+    from oracle import mesh as om
+    from oracle import space as osp
+    mesh = om.cartesian_hex(n, n, n)
+    space = osp.NDSpace(mesh, p)
+    alpha, beta = coefficients(mesh.attr)
+    A = oa.assemble(space, alpha, beta, q_override=p + 1)
+    ess = space.boundary_dofs()
+    Ac, _ = oa.eliminate(A, ess)
+    op = ocsr.CsrOperator(Ac)
+    if threads:
+        ocsr.lib().csr_set_threads(threads)
+    cores = ocsr.lib().csr_num_threads()
+    x = np.random.default_rng(12345).standard_normal(space.ndof)
+    y = np.empty_like(x)
+    for _ in range(warmup):
+        op.spmv(x, y)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        op.spmv(x, y)
+    t_apply = (time.perf_counter() - t0) / steps
+    b = Ac @ np.random.default_rng(54321).standard_normal(space.ndof)
+    dinv = 1.0 / Ac.diagonal()
+    t0 = time.perf_counter()
+    _, it, _, _ = op.pcg(b, dinv, rtol=0.0, atol=0.0, max_iter=pcg_iters)
+    t_pcg = (time.perf_counter() - t0) / max(it, 1)
+    return {"n_dof": int(space.ndof), "nnz": int(op.nnz), "cores": int(cores), "apply_s": t_apply, "pcg_iter_s": t_pcg}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; MFEM/hypre
+    cannot be built in this image), all host threads, bounded sample of the same workload."""
+    if rank != 0:
+        return
+    s = cpu_sample(args.cpu_n, args.order, args.steps, max(args.warmup, 3), args.pcg_iters)
+    gdofs = s["n_dof"] / s["apply_s"] / 1e9
+    sample = "structured hex cube n=%d order %d (%d DOFs, %d nnz): assembled CSR SpMV, all host threads" % (
+        args.cpu_n, args.order, s["n_dof"], s["nnz"])
+    line = {
+        "impl": "reference", "metric": "hcurl_apply_gdofs", "value": gdofs, "unit": "GDOF/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": s["apply_s"] * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, args.cpu_n, s["n_dof"], bounded=True),
+        "cpu_baseline": {"value": gdofs, "unit": "GDOF/s", "cores": s["cores"], "kind": "port", "sample": sample,
+                         "pcg_iters_per_s": 1.0 / s["pcg_iter_s"]},
+        "e2e": {"value": gdofs, "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, n, n_dof, bounded=False):
+    return {
+        "workload": "synthetic structured hex cube %d^3 per GPU%s, order-%d Nedelec, K(dt*nu)+M(sigma) apply, %d DOFs%s" % (
+            n, " (trilinearly perturbed)" if args.perturbed else "", args.order, n_dof,
+            " [bounded CPU sample of the n=%d workload]" % args.n if bounded else ""),
+        "mesh": "general unstructured storage (explicit connectivity, coordinates, signed int32 ND map)",
+        "order": args.order, "n_per_edge": n,
+        "quadrature": "p+1 Gauss points/dim for both terms (exact on affine hexes; equals MFEM's full-assembly rule to "
+                      "round-off, tests/test_gpu_apply.py::test_hex_affine_rules_agree)" if args.quad == "fast"
+        else "MFEM full-assembly rules (curl p+1, mass p+2 points/dim)",
+        "essential_bc": "all six faces", "l2_policy": "inputs larger than L2 (x, y, map each > 126 MB); no flush",
+        "parallelism": "dd%d" % args.gpus,
+    }
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    from hephaestus_b200 import fespace, operators
+    dist = None
+    uid = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        box = [operators.Context.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        uid = box[0]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    ctx = operators.Context(local_rank, uid, rank, world)
+    p, n = args.order, args.n
+    t_setup = time.perf_counter()
+    if world == 1:
+        mesh = fespace.cartesian_hex_mesh(n, n, n)
+        if args.perturbed:
+            mesh = fespace.perturb_interior(mesh)
+        space = fespace.NDSpace(mesh, p)
+        gsp = operators.GpuNDSpace(ctx, space)
+        ess = space.boundary_dofs()
+        attr = mesh.attr
+        n_dof_global, n_elem_local = space.ndof, mesh.n_elem
+        n_tdof = space.ndof
+    else:
+        from hephaestus_b200 import partition
+        lp = partition.brick_problem(rank, world, n, p, perturbed=args.perturbed)
+        space, mesh = lp.space, lp.space.mesh
+        gsp = operators.GpuNDSpace(ctx, space, lp.local)
+        ess = lp.ess_tdofs
+        attr = mesh.attr
+        n_elem_local = mesh.n_elem
+        n_tdof = lp.local.n_tdof
+        t = torch.tensor([n_tdof], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        n_dof_global = int(t.item())
+    op = operators.HephGpuOperator(ctx, gsp, p + 1 if args.quad == "fast" else 0)
+    alpha, beta = coefficients(attr)
+    op.SetCoefficients(alpha, beta)
+    op.SetEssentialTrueDofs(ess)
+    t_setup = time.perf_counter() - t_setup
+    nd = gsp.nd
+    rng = np.random.default_rng(12345 + rank)
+    x = rng.standard_normal(n_tdof)
+    next_ = gsp.n_ldof if world > 1 else n_tdof
+    dx, dy = ctx.alloc(max(next_, n_tdof)).upload(np.concatenate([x, np.zeros(max(next_, n_tdof) - n_tdof)])), ctx.alloc(max(next_, n_tdof))
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    # ---------------- device-resident apply: W warm-up, K timed steps -----------------
+    for _ in range(max(args.warmup, 3)):
+        op.Mult(dx, dy)
+    ctx.synchronize()
+    barrier()
+    op.kernel_stats_reset()
+    l0 = ctx.launch_count()
+    ctx.mark(0)
+    for _ in range(args.steps):
+        op.Mult(dx, dy)
+    ctx.mark(1)
+    ctx.synchronize()
+    ms_total = ctx.elapsed_ms()
+    launches = ctx.launch_count() - l0
+    barrier()
+    kern_ms, kern_n = op.kernel_stats_ms()
+    if dist is not None:
+        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = n_dof_global / (ms_step * 1e-3) / 1e9
+
+    # ---------------- PCG iterations/s (device-resident) --------------------------------
+    solver = operators.HephGpuPCG(ctx, tol=0.0, abstol=0.0, max_iter=args.pcg_iters)
+    solver.SetOperator(op)
+    xs = np.random.default_rng(54321 + rank).standard_normal(n_tdof)
+    dxs = ctx.alloc(max(next_, n_tdof)).upload(np.concatenate([xs, np.zeros(max(next_, n_tdof) - n_tdof)]))
+    db, dsol = ctx.alloc(max(next_, n_tdof)), ctx.alloc(max(next_, n_tdof))
+    op.Mult(dxs, db)
+    solver.max_iter = 3
+    L = operators.L
+    L.check(L.lib().hcurl_pcg_set(solver.h, 0.0, 0.0, 3, 0), "pcg_set")
+    solver.Mult(db, dsol)  # warm-up (diagonal build, allocations)
+    L.check(L.lib().hcurl_pcg_set(solver.h, 0.0, 0.0, args.pcg_iters, 0), "pcg_set")
+    barrier()
+    solver.Mult(db, dsol)
+    pcg_ms = solver.last_loop_ms()
+    if dist is not None:
+        t = torch.tensor([pcg_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        pcg_ms = float(t.item())
+    pcg_iter_ms = pcg_ms / max(solver.num_iterations, 1)
+
+    # ---------------- e2e: host buffers through the C ABI ---------------------------------
+    e2e = None
+    if not args.no_e2e:
+        hx, hy = operators.pinned_array(n_tdof), operators.pinned_array(n_tdof)
+        hx[:] = x
+        k_e2e = max(3, min(args.steps, 10))
+        op.Mult(hx, hy)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            op.Mult(hx, hy)  # H2D x, kernels, D2H y, stream sync -- all inside the call
+        t_e2e = (time.perf_counter() - t0) / k_e2e
+        if dist is not None:
+            t = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_e2e = float(t.item())
+        e2e = {"value": n_dof_global / t_e2e / 1e9, "unit": "GDOF/s", "h2d_bytes_per_step": int(8 * n_tdof),
+               "d2h_bytes_per_step": int(8 * n_tdof), "ms_per_step": t_e2e * 1e3, "steps": k_e2e,
+               "note": "hcurl_op_apply(HCURL_HOST): pinned host x -> device, apply, y -> pinned host; PCIe-bound"}
+    clocks = sampler.stop()
+
+    # ---------------- roofline of the dominant kernel ----------------------------------------
+    peak, peak_kind = peaks()
+    abytes = algorithmic_bytes(n_tdof, n_elem_local, nd)
+    achieved = abytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
+    fp64 = ctx.fp64_peak_tflops()
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_kind": "of " + peak_kind, "kernel": "hex element kernel (order %d)" % p,
+                "kernel_ms": kern_ms, "kernel_launches_timed": kern_n, "algorithmic_bytes_per_launch": abytes,
+                "bytes_per_dof": abytes / n_tdof, "kernel_share_of_step": kern_ms / ms_step if ms_step > 0 else None,
+                "fp64_fma_peak_tflops_measured": fp64}
+
+    if rank != 0:
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        s = cpu_sample(args.cpu_n, p, 10, 3, 20)
+        cpu = {"value": s["n_dof"] / s["apply_s"] / 1e9, "unit": "GDOF/s", "cores": s["cores"], "kind": "port",
+               "sample": "structured hex cube n=%d order %d (%d DOFs, %d nnz): assembled CSR SpMV (hypre-style row "
+                         "blocks, OpenMP), 10 timed applies" % (args.cpu_n, p, s["n_dof"], s["nnz"]),
+               "pcg_iters_per_s": 1.0 / s["pcg_iter_s"]}
+    line = {
+        "metric": "hcurl_apply_gdofs", "value": value, "unit": "GDOF/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, n, n_dof_global),
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "pcg": {"iters_per_s": 1e3 / pcg_iter_ms, "ms_per_iter": pcg_iter_ms, "iters": solver.num_iterations,
+                "precond": "jacobi", "gdofs": n_dof_global / (pcg_iter_ms * 1e-3) / 1e9},
+        "setup_s": t_setup,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -33,6 +33,9 @@ SIGNATURES = {
     "hcurl_ctx_destroy": (None, [_P]),
     "hcurl_ctx_device": (C.c_int, [_P]),
     "hcurl_ctx_synchronize": (C.c_int, [_P]),
+    "hcurl_ctx_mark": (C.c_int, [_P, C.c_int]),
+    "hcurl_ctx_elapsed_ms": (C.c_double, [_P]),
+    "hcurl_ctx_launch_count": (C.c_int64, [_P]),
     "hcurl_space_create": (_P, [_P, C.c_int, C.c_int, C.c_int, C.c_int64, _P, _P, _P, _P, C.c_int32, _P, C.c_int32,
                                 C.c_int, _P, _P, _P, _P, _P, _P]),
     "hcurl_space_destroy": (None, [_P]),
@@ -51,6 +54,8 @@ SIGNATURES = {
     "hcurl_op_diagonal": (C.c_int, [_P, _P, C.c_int]),
     "hcurl_op_form_rhs": (C.c_int, [_P, _P, _P, _P, C.c_int]),
     "hcurl_op_last_kernel_ms": (C.c_double, [_P]),
+    "hcurl_op_kernel_stats_reset": (C.c_int, [_P]),
+    "hcurl_op_kernel_stats_ms": (C.c_double, [_P, C.POINTER(C.c_int)]),
     "hcurl_pcg_create": (_P, [_P, _P, C.c_int]),
     "hcurl_pcg_destroy": (None, [_P]),
     "hcurl_pcg_set": (C.c_int, [_P, C.c_double, C.c_double, C.c_int, C.c_int]),
@@ -62,6 +67,8 @@ SIGNATURES = {
     "hcurl_device_free": (None, [_P, _P]),
     "hcurl_copy_to_device": (C.c_int, [_P, _P, _P, C.c_int64]),
     "hcurl_copy_to_host": (C.c_int, [_P, _P, _P, C.c_int64]),
+    "hcurl_host_alloc_pinned": (_P, [C.c_int64]),
+    "hcurl_host_free_pinned": (None, [_P]),
     "hcurl_dot": (C.c_int, [_P, _P, _P, C.c_int64, C.POINTER(C.c_double)]),
     "hcurl_fp64_peak_tflops": (C.c_double, [_P]),
 }

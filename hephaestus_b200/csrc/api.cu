@@ -195,13 +195,15 @@ int op_apply_ext(hcurl_op *op, double *d_x, double *d_y, bool constrained, doubl
   if (!accumulate) HC_CUDA(cudaMemsetAsync(d_y, 0, sizeof(double) * next, ctx->stream));
   else if (sp->n_ghost) HC_CUDA(cudaMemsetAsync(d_y + sp->n_tdof, 0, sizeof(double) * sp->n_ghost, ctx->stream));
   const uint32_t *map = (constrained && op->d_map_ess) ? op->d_map_ess : sp->d_map;
-  if (op->timed) HC_CUDA(cudaEventRecord(op->ev0, ctx->stream));
+  cudaEvent_t e0 = op->ev0, e1 = op->ev1;
+  if (op->ring_ok) { e0 = op->ring0[op->ring_n % hcurl_op::RING]; e1 = op->ring1[op->ring_n % hcurl_op::RING]; op->ring_n++; op->ev0 = e0; op->ev1 = e1; }
+  if (op->timed) HC_CUDA(cudaEventRecord(e0, ctx->stream));
   int rc = (sp->geom == HCURL_GEOM_HEX) ? hex_apply_launch(op, map, d_x, d_y, scale) : tet_apply_launch(op, map, d_x, d_y, scale);
   if (rc) return rc;
-  if (op->timed) HC_CUDA(cudaEventRecord(op->ev1, ctx->stream));
+  if (op->timed) HC_CUDA(cudaEventRecord(e1, ctx->stream));
   if (exchange_reduce(sp, d_y)) return 1;
   if (constrained && op->n_ess > 0)
-    copy_idx_kernel<<<(op->n_ess + 255) / 256, 256, 0, ctx->stream>>>(op->n_ess, op->d_ess, d_x, d_y);
+    { copy_idx_kernel<<<(op->n_ess + 255) / 256, 256, 0, ctx->stream>>>(op->n_ess, op->d_ess, d_x, d_y); ctx->launches++; }
   HC_CUDA(cudaGetLastError());
   return 0;
 }
@@ -260,6 +262,8 @@ hcurl_ctx *hcurl_ctx_create(int device, const void *uid, int rank, int nranks) {
   HC_CUDA_NULL(cudaMemset(ctx->d_counter, 0, sizeof(unsigned int)));
   ctx->n_partial = ctx->sm_count * 8;
   HC_CUDA_NULL(cudaMalloc(&ctx->d_partial, sizeof(double) * ctx->n_partial));
+  HC_CUDA_NULL(cudaEventCreate(&ctx->mark[0]));
+  HC_CUDA_NULL(cudaEventCreate(&ctx->mark[1]));
   if (comm_init(ctx, uid)) { delete ctx; return nullptr; }
   return ctx;
 }
@@ -275,6 +279,19 @@ void hcurl_ctx_destroy(hcurl_ctx *ctx) {
 }
 int hcurl_ctx_device(const hcurl_ctx *ctx) { return ctx ? ctx->device : -1; }
 int hcurl_ctx_synchronize(hcurl_ctx *ctx) { HC_CUDA(cudaStreamSynchronize(ctx->stream)); return 0; }
+int hcurl_ctx_mark(hcurl_ctx *ctx, int which) {
+  HC_CUDA(cudaSetDevice(ctx->device));
+  HC_CUDA(cudaEventRecord(ctx->mark[which ? 1 : 0], ctx->stream));
+  return 0;
+}
+double hcurl_ctx_elapsed_ms(hcurl_ctx *ctx) {
+  float ms = 0.f;
+  cudaSetDevice(ctx->device);
+  if (cudaEventSynchronize(ctx->mark[1]) != cudaSuccess) return -1.0;
+  if (cudaEventElapsedTime(&ms, ctx->mark[0], ctx->mark[1]) != cudaSuccess) return -1.0;
+  return ms;
+}
+int64_t hcurl_ctx_launch_count(const hcurl_ctx *ctx) { return ctx->launches; }
 
 hcurl_space *hcurl_space_create(hcurl_ctx *ctx, int geom, int geom_order, int order, int64_t n_elem, const double *elem_xyz,
                                 const int32_t *elem_ldof, const int32_t *elem_verts, const int32_t *elem_face_base,
@@ -425,8 +442,12 @@ hcurl_op *hcurl_op_create(hcurl_ctx *ctx, hcurl_space *sp, int q) {
     }
   }
   HC_CUDA_NULL(cudaSetDevice(ctx->device));
-  HC_CUDA_NULL(cudaEventCreate(&op->ev0));
-  HC_CUDA_NULL(cudaEventCreate(&op->ev1));
+  for (int i = 0; i < hcurl_op::RING; i++) {
+    HC_CUDA_NULL(cudaEventCreate(&op->ring0[i]));
+    HC_CUDA_NULL(cudaEventCreate(&op->ring1[i]));
+  }
+  op->ring_ok = true;
+  op->ev0 = op->ring0[0]; op->ev1 = op->ring1[0];
   op->timed = true;
   return op;
 }
@@ -437,7 +458,7 @@ void hcurl_op_destroy(hcurl_op *op) {
   cudaStreamSynchronize(op->ctx->stream);
   cudaFree(op->d_alpha); cudaFree(op->d_beta); cudaFree(op->d_map_ess); cudaFree(op->d_ess);
   cudaFree(op->d_emat); cudaFree(op->d_xin); cudaFree(op->d_yout); cudaFree(op->d_tmp);
-  cudaEventDestroy(op->ev0); cudaEventDestroy(op->ev1);
+  for (int i = 0; i < hcurl_op::RING; i++) { cudaEventDestroy(op->ring0[i]); cudaEventDestroy(op->ring1[i]); }
   delete op;
 }
 int hcurl_op_qpts_curl(const hcurl_op *op) { return op->sp->geom == HCURL_GEOM_HEX ? op->qc * op->qc * op->qc : 1; }
@@ -587,6 +608,21 @@ int hcurl_op_form_rhs(hcurl_op *op, const double *x_bc, const double *b, double 
   return 0;
 }
 
+int hcurl_op_kernel_stats_reset(hcurl_op *op) { op->ring_n = 0; return 0; }
+double hcurl_op_kernel_stats_ms(hcurl_op *op, int *count) {
+  cudaSetDevice(op->ctx->device);
+  const int n = op->ring_n < hcurl_op::RING ? op->ring_n : hcurl_op::RING;
+  if (count) *count = n;
+  if (n == 0) return 0.0;
+  cudaStreamSynchronize(op->ctx->stream);
+  double tot = 0.0;
+  for (int i = 0; i < n; i++) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, op->ring0[i], op->ring1[i]) != cudaSuccess) return -1.0;
+    tot += ms;
+  }
+  return tot / n;
+}
 double hcurl_op_last_kernel_ms(hcurl_op *op) {
   float ms = 0.f;
   cudaSetDevice(op->ctx->device);
@@ -676,6 +712,7 @@ int hcurl_pcg_solve(hcurl_pcg *s, const double *b, double *x, int zero_guess, in
     i++;
     if (op_apply_ext(op, s->d_p, s->d_s, true, 1.0, false)) return 1;
     dot_kernel<<<g, RED_THREADS, 0, st>>>(nt, s->d_s, s->d_p, ctx->d_partial, ctx->d_counter, S + 1);
+    ctx->launches += 2;  // dot + fused update below
     if (allreduce_sum(ctx, S + 1, 1)) return 1;
     pcg_update_kernel<<<g, RED_THREADS, 0, st>>>(nt, S, dinv, s->d_p, s->d_x, s->d_r, s->d_s, ctx->d_partial, ctx->d_counter, S + 2);
     if (allreduce_sum(ctx, S + 2, 1)) return 1;
@@ -689,6 +726,7 @@ int hcurl_pcg_solve(hcurl_pcg *s, const double *b, double *x, int zero_guess, in
     const double beta = gamma_new / gamma;
     gamma = gamma_new;
     pcg_dir_kernel<<<g, RED_THREADS, 0, st>>>(nt, beta, gamma_new, S, s->d_s, s->d_p);
+    ctx->launches++;
   }
   HC_CUDA(cudaEventRecord(s->ev1, st));
   HC_CUDA(cudaGetLastError());
@@ -724,6 +762,12 @@ int hcurl_copy_to_host(hcurl_ctx *ctx, double *dst, const double *src, int64_t n
   HC_CUDA(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
+double *hcurl_host_alloc_pinned(int64_t n) {
+  double *p = nullptr;
+  HC_CUDA_NULL(cudaMallocHost(&p, sizeof(double) * (size_t)(n > 0 ? n : 1)));
+  return p;
+}
+void hcurl_host_free_pinned(double *p) { cudaFreeHost(p); }
 int hcurl_dot(hcurl_ctx *ctx, const double *a, const double *b, int64_t n, double *result) {
   HC_CUDA(cudaSetDevice(ctx->device));
   dot_kernel<<<red_grid(ctx, n), RED_THREADS, 0, ctx->stream>>>(n, a, b, ctx->d_partial, ctx->d_counter, ctx->d_red + 8);

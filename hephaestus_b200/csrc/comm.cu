@@ -120,6 +120,7 @@ int exchange_broadcast(hcurl_space *sp, double *d_ext) {
   if (sp->n_nbr == 0) return 0;
   Nccl *N = nccl();
   const int32_t n_own = sp->own_off[sp->n_nbr];
+  if (n_own > 0) ctx->launches++;
   if (n_own > 0) pack_kernel<<<(n_own + 255) / 256, 256, 0, ctx->stream>>>(n_own, sp->d_own_idx, d_ext, sp->d_sendbuf);
   HC_NCCL(N->GroupStart());
   for (int r = 0; r < sp->n_nbr; r++) {
@@ -149,6 +150,7 @@ int exchange_reduce(hcurl_space *sp, double *d_ext) {
   }
   HC_NCCL(N->GroupEnd());
   const int32_t n_own = sp->own_off[sp->n_nbr];
+  if (n_own > 0) ctx->launches++;
   if (n_own > 0) unpack_add_kernel<<<(n_own + 255) / 256, 256, 0, ctx->stream>>>(n_own, sp->d_own_idx, sp->d_recvbuf, d_ext);
   HC_CUDA(cudaGetLastError());
   return 0;

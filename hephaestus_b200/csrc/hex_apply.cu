@@ -375,6 +375,7 @@ static int launch_one(hcurl_op *op, const uint32_t *d_map, const double *d_x, do
   kern<<<(unsigned)grid, dim3(Q * Q, C::E), C::SMEM, op->ctx->stream>>>(T, sp->n_elem, d_map, sp->d_xyz, op->d_alpha,
                                                                           op->d_beta, d_x, d_y, scale);
   HC_CUDA(cudaGetLastError());
+  op->ctx->launches++;
   return 0;
 }
 

@@ -78,6 +78,8 @@ struct hcurl_ctx {
   double *d_partial = nullptr;  // per-block partial sums
   int n_partial = 0;
   int sm_count = 148;
+  cudaEvent_t mark[2] = {nullptr, nullptr};
+  int64_t launches = 0;
 };
 
 struct hcurl_space {
@@ -123,6 +125,10 @@ struct hcurl_op {
   double *d_xin = nullptr, *d_yout = nullptr, *d_tmp = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
+  static constexpr int RING = 256;
+  cudaEvent_t ring0[RING], ring1[RING];
+  int ring_n = 0;      // samples recorded since reset (may exceed RING)
+  bool ring_ok = false;
 };
 
 struct hcurl_pcg {

@@ -197,6 +197,7 @@ int tet_apply_launch(hcurl_op *op, const uint32_t *d_map, const double *d_x, dou
   else
     tet_apply_kernel_generic<<<grid, 128, 0, st>>>(sp->nd, sp->n_elem, sp->n_elem_pad, d_map, op->d_emat, d_x, d_y, scale);
   HC_CUDA(cudaGetLastError());
+  op->ctx->launches++;
   return 0;
 }
 

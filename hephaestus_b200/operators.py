@@ -40,6 +40,15 @@ class Context:
     def alloc(self, n):
         return DeviceVector(self, n)
 
+    def mark(self, which):
+        L.check(L.lib().hcurl_ctx_mark(self.h, which), "hcurl_ctx_mark")
+
+    def elapsed_ms(self):
+        return L.lib().hcurl_ctx_elapsed_ms(self.h)
+
+    def launch_count(self):
+        return L.lib().hcurl_ctx_launch_count(self.h)
+
     def fp64_peak_tflops(self):
         return L.lib().hcurl_fp64_peak_tflops(self.h)
 
@@ -83,6 +92,18 @@ class DeviceVector:
             self.free()
         except Exception:
             pass
+
+
+def pinned_array(n):
+    """numpy view over page-locked host memory (freed when the array is collected)."""
+    p = L.check_ptr(L.lib().hcurl_host_alloc_pinned(int(n)), "hcurl_host_alloc_pinned")
+    buf = (C.c_double * int(n)).from_address(p)
+    arr = np.frombuffer(buf, dtype=np.float64)
+    _PINNED[arr.ctypes.data] = p
+    return arr
+
+
+_PINNED = {}
 
 
 class GpuNDSpace:
@@ -206,6 +227,14 @@ class HephGpuOperator:
 
     def last_kernel_ms(self):
         return L.lib().hcurl_op_last_kernel_ms(self.h)
+
+    def kernel_stats_reset(self):
+        L.lib().hcurl_op_kernel_stats_reset(self.h)
+
+    def kernel_stats_ms(self):
+        n = C.c_int(0)
+        ms = L.lib().hcurl_op_kernel_stats_ms(self.h, C.byref(n))
+        return ms, n.value
 
     def close(self):
         if self.h:

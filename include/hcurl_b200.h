@@ -65,6 +65,12 @@ hcurl_ctx *hcurl_ctx_create(int device, const void *nccl_unique_id128, int rank,
 void hcurl_ctx_destroy(hcurl_ctx *ctx);
 int hcurl_ctx_device(const hcurl_ctx *ctx);
 int hcurl_ctx_synchronize(hcurl_ctx *ctx);
+/* Measurement helpers (bench.py): CUDA events recorded on the stream every kernel of
+ * this context is launched on; elapsed time between mark 0 and mark 1 in ms (syncs). */
+int hcurl_ctx_mark(hcurl_ctx *ctx, int which);
+double hcurl_ctx_elapsed_ms(hcurl_ctx *ctx);
+/* number of library kernels launched on this context since creation */
+int64_t hcurl_ctx_launch_count(const hcurl_ctx *ctx);
 
 /* ---- finite element space --------------------------------------------------
  * Replaces: the data `ParFiniteElementSpace` feeds to the assembly in
@@ -168,6 +174,10 @@ int hcurl_op_diagonal(hcurl_op *op, double *diag, int where);
 int hcurl_op_form_rhs(hcurl_op *op, const double *x_bc, const double *b, double *B, int where);
 /* average device time (ms) of the element kernel(s) of the most recent apply */
 double hcurl_op_last_kernel_ms(hcurl_op *op);
+/* element-kernel time statistics since the last reset: CUDA events bracket the element
+ * kernel(s) of every apply (ring of 256 pairs).  Returns the mean ms, *count = samples. */
+int hcurl_op_kernel_stats_reset(hcurl_op *op);
+double hcurl_op_kernel_stats_ms(hcurl_op *op, int *count);
 
 /* ---- Krylov solver ---------------------------------------------------------------
  * hypre PCG semantics (two_norm = 0) with optional Jacobi preconditioner.
@@ -195,6 +205,9 @@ double *hcurl_device_alloc(hcurl_ctx *ctx, int64_t n_doubles);
 void hcurl_device_free(hcurl_ctx *ctx, double *p);
 int hcurl_copy_to_device(hcurl_ctx *ctx, double *dst_dev, const double *src_host, int64_t n);
 int hcurl_copy_to_host(hcurl_ctx *ctx, double *dst_host, const double *src_dev, int64_t n);
+/* page-locked host buffers for the host<->device legs of the HOST entry points */
+double *hcurl_host_alloc_pinned(int64_t n_doubles);
+void hcurl_host_free_pinned(double *p);
 /* global dot product over true dofs (all-reduced across ranks) */
 int hcurl_dot(hcurl_ctx *ctx, const double *a_dev, const double *b_dev, int64_t n, double *result);
 
