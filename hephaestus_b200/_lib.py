@@ -44,6 +44,7 @@ SIGNATURES = {
     "hcurl_space_elem_ndof": (C.c_int, [_P]),
     "hcurl_op_create": (_P, [_P, _P, C.c_int]),
     "hcurl_op_destroy": (None, [_P]),
+    "hcurl_op_set_kernel": (C.c_int, [_P, C.c_int]),
     "hcurl_op_qpts_curl": (C.c_int, [_P]),
     "hcurl_op_qpts_mass": (C.c_int, [_P]),
     "hcurl_op_set_coefficients": (C.c_int, [_P, C.c_int, _P, _P, C.c_int]),

@@ -198,7 +198,9 @@ int op_apply_ext(hcurl_op *op, double *d_x, double *d_y, bool constrained, doubl
   cudaEvent_t e0 = op->ev0, e1 = op->ev1;
   if (op->ring_ok) { e0 = op->ring0[op->ring_n % hcurl_op::RING]; e1 = op->ring1[op->ring_n % hcurl_op::RING]; op->ring_n++; op->ev0 = e0; op->ev1 = e1; }
   if (op->timed) HC_CUDA(cudaEventRecord(e0, ctx->stream));
-  int rc = (sp->geom == HCURL_GEOM_HEX) ? hex_apply_launch(op, map, d_x, d_y, scale) : tet_apply_launch(op, map, d_x, d_y, scale);
+  int rc;
+  if (hex_fast_eligible(op)) rc = hex_fast_launch(op, constrained, d_x, d_y, scale);
+  else rc = (sp->geom == HCURL_GEOM_HEX) ? hex_apply_launch(op, map, d_x, d_y, scale) : tet_apply_launch(op, map, d_x, d_y, scale);
   if (rc) return rc;
   if (op->timed) HC_CUDA(cudaEventRecord(e1, ctx->stream));
   if (exchange_reduce(sp, d_y)) return 1;
@@ -414,6 +416,7 @@ void hcurl_space_destroy(hcurl_space *sp) {
   if (!sp) return;
   cudaSetDevice(sp->ctx->device);
   cudaStreamSynchronize(sp->ctx->stream);
+  cudaFree(sp->d_mapT); cudaFree(sp->d_xyzT);
   cudaFree(sp->d_xyz); cudaFree(sp->d_map); cudaFree(sp->d_faceR); cudaFree(sp->d_own_idx);
   cudaFree(sp->d_ghost_sign); cudaFree(sp->d_sendbuf); cudaFree(sp->d_recvbuf);
   delete sp;
@@ -457,9 +460,15 @@ void hcurl_op_destroy(hcurl_op *op) {
   cudaSetDevice(op->ctx->device);
   cudaStreamSynchronize(op->ctx->stream);
   cudaFree(op->d_alpha); cudaFree(op->d_beta); cudaFree(op->d_map_ess); cudaFree(op->d_ess);
+  cudaFree(op->d_edata); cudaFree(op->d_mapT_ess);
   cudaFree(op->d_emat); cudaFree(op->d_xin); cudaFree(op->d_yout); cudaFree(op->d_tmp);
   for (int i = 0; i < hcurl_op::RING; i++) { cudaEventDestroy(op->ring0[i]); cudaEventDestroy(op->ring1[i]); }
   delete op;
+}
+int hcurl_op_set_kernel(hcurl_op *op, int which) {
+  if (which != 0 && which != 1) { set_error("kernel selector must be 0 (auto) or 1 (generic)"); return 1; }
+  op->force_generic = which == 1;
+  return 0;
 }
 int hcurl_op_qpts_curl(const hcurl_op *op) { return op->sp->geom == HCURL_GEOM_HEX ? op->qc * op->qc * op->qc : 1; }
 int hcurl_op_qpts_mass(const hcurl_op *op) { return op->sp->geom == HCURL_GEOM_HEX ? op->qm * op->qm * op->qm : 1; }
@@ -484,6 +493,7 @@ int hcurl_op_set_coefficients(hcurl_op *op, int layout, const double *alpha, con
   op->has_beta = beta != nullptr;
   HC_CUDA(cudaStreamSynchronize(op->ctx->stream));  // host buffers are borrowed for the call only
   op->emat_valid = false;
+  op->edata_valid = false;
   return 0;
 }
 
@@ -495,6 +505,7 @@ int hcurl_op_set_essential_tdofs(hcurl_op *op, const int32_t *ess, int32_t n_ess
     if (ess[i] < 0 || ess[i] >= sp->n_tdof) { set_error("essential tdof %d out of range", ess[i]); return 1; }
   cudaFree(op->d_ess); op->d_ess = nullptr;
   cudaFree(op->d_map_ess); op->d_map_ess = nullptr;
+  cudaFree(op->d_mapT_ess); op->d_mapT_ess = nullptr;
   op->n_ess = n_ess;
   // flags live on the extended vector so that ghost copies of essential dofs are masked too
   double *flag = nullptr;

@@ -104,6 +104,10 @@ struct hcurl_space {
   int8_t *d_ghost_sign = nullptr;           // [n_ghost] or null
   double *d_sendbuf = nullptr, *d_recvbuf = nullptr;  // size own_off.back()
   std::vector<int32_t> ldof_to_ext;  // host copy (for essential dofs etc.)
+  // fast order-2 path (hex_fast.cu): dof-major map / vertices, affine classification
+  bool fast_ready = false, all_affine = false;
+  uint32_t *d_mapT = nullptr;
+  double *d_xyzT = nullptr;
 };
 
 struct hcurl_op {
@@ -121,6 +125,11 @@ struct hcurl_op {
   // tets: packed element matrices [npk][n_elem_pad]
   double *d_emat = nullptr;
   bool emat_valid = false;
+  // fast order-2 hex path: per-element affine data [12][n_pad], dof-major essential map
+  double *d_edata = nullptr;
+  bool edata_valid = false;
+  uint32_t *d_mapT_ess = nullptr;
+  bool force_generic = false;
   // work vectors (extended length)
   double *d_xin = nullptr, *d_yout = nullptr, *d_tmp = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -147,6 +156,8 @@ namespace hcurl {
 // kernels / drivers implemented in the .cu files (all enqueue on ctx->stream)
 int hex_apply_launch(hcurl_op *op, const uint32_t *d_map, const double *d_x, double *d_y, double scale);
 int hex_diag_launch(hcurl_op *op, double *d_diag);
+bool hex_fast_eligible(const hcurl_op *op);
+int hex_fast_launch(hcurl_op *op, bool constrained, const double *d_x, double *d_y, double scale);
 int tet_build_emat(hcurl_op *op);
 int tet_apply_launch(hcurl_op *op, const uint32_t *d_map, const double *d_x, double *d_y, double scale);
 int tet_diag_launch(hcurl_op *op, double *d_diag);

@@ -186,6 +186,10 @@ class HephGpuOperator:
                 raise L.HcurlError("%s has %d values, expected %d" % (nm, v.size, ne * (nq if layout == L.PER_QPT else 1)))
         L.check(L.lib().hcurl_op_set_coefficients(self.h, layout, L.ptr(a), L.ptr(b), L.HOST), "hcurl_op_set_coefficients")
 
+    def SetKernel(self, which):
+        """0 = automatic (fast path where available), 1 = generic kernel."""
+        L.check(L.lib().hcurl_op_set_kernel(self.h, int(which)), "hcurl_op_set_kernel")
+
     def SetEssentialTrueDofs(self, ess):
         e = L.as_i32(ess)
         L.check(L.lib().hcurl_op_set_essential_tdofs(self.h, L.ptr(e), e.size), "hcurl_op_set_essential_tdofs")

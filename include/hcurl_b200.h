@@ -139,6 +139,10 @@ int hcurl_space_elem_ndof(const hcurl_space *sp);
  */
 hcurl_op *hcurl_op_create(hcurl_ctx *ctx, hcurl_space *sp, int quad_pts_per_dim);
 void hcurl_op_destroy(hcurl_op *op);
+/* Kernel selection: 0 = automatic (register-blocked fast path where one exists: order-2
+ * trilinear hexes with one p+1 rule and per-element coefficients), 1 = always the generic
+ * sum-factorised kernel.  Both compute the same operator; tests compare them. */
+int hcurl_op_set_kernel(hcurl_op *op, int which);
 /* Number of coefficient values expected per element for PER_QPT layout. */
 int hcurl_op_qpts_curl(const hcurl_op *op);
 int hcurl_op_qpts_mass(const hcurl_op *op);
