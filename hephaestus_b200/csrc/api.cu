@@ -199,7 +199,8 @@ int op_apply_ext(hcurl_op *op, double *d_x, double *d_y, bool constrained, doubl
   if (op->ring_ok) { e0 = op->ring0[op->ring_n % hcurl_op::RING]; e1 = op->ring1[op->ring_n % hcurl_op::RING]; op->ring_n++; op->ev0 = e0; op->ev1 = e1; }
   if (op->timed) HC_CUDA(cudaEventRecord(e0, ctx->stream));
   int rc;
-  if (hex_fast_eligible(op)) rc = hex_fast_launch(op, constrained, d_x, d_y, scale);
+  if (hex_patch_eligible(op)) rc = hex_patch_launch(op, constrained, d_x, d_y, scale, accumulate);
+  else if (hex_fast_eligible(op)) rc = hex_fast_launch(op, constrained, d_x, d_y, scale);
   else rc = (sp->geom == HCURL_GEOM_HEX) ? hex_apply_launch(op, map, d_x, d_y, scale) : tet_apply_launch(op, map, d_x, d_y, scale);
   if (rc) return rc;
   if (op->timed) HC_CUDA(cudaEventRecord(e1, ctx->stream));
@@ -395,6 +396,8 @@ hcurl_space *hcurl_space_create(hcurl_ctx *ctx, int geom, int geom_order, int or
     HC_CUDA_NULL(cudaStreamSynchronize(ctx->stream));
     cudaFree(d_ldof); cudaFree(d_loc); cudaFree(d_sgn); cudaFree(d_l2e);
   }
+  // ---- patch decomposition for the patch-based hex kernels (hex_patch.cu)
+  if (hex_patch_build(sp, elem_xyz, elem_ldof, l2e.empty() ? nullptr : l2e.data())) { hcurl_space_destroy(sp); return nullptr; }
   // ---- triangle-face dof transformations (tets, p >= 2)
   if (!hex && order >= 2) {
     const int nn = order * (order - 1) / 2;  // face nodes
@@ -416,6 +419,7 @@ void hcurl_space_destroy(hcurl_space *sp) {
   if (!sp) return;
   cudaSetDevice(sp->ctx->device);
   cudaStreamSynchronize(sp->ctx->stream);
+  hex_patch_free(sp);
   cudaFree(sp->d_mapT); cudaFree(sp->d_xyzT);
   cudaFree(sp->d_xyz); cudaFree(sp->d_map); cudaFree(sp->d_faceR); cudaFree(sp->d_own_idx);
   cudaFree(sp->d_ghost_sign); cudaFree(sp->d_sendbuf); cudaFree(sp->d_recvbuf);
@@ -460,14 +464,15 @@ void hcurl_op_destroy(hcurl_op *op) {
   cudaSetDevice(op->ctx->device);
   cudaStreamSynchronize(op->ctx->stream);
   cudaFree(op->d_alpha); cudaFree(op->d_beta); cudaFree(op->d_map_ess); cudaFree(op->d_ess);
-  cudaFree(op->d_edata); cudaFree(op->d_mapT_ess);
+  cudaFree(op->d_edata); cudaFree(op->d_mapT_ess); cudaFree(op->d_edataP); cudaFree(op->d_pdof_ess);
   cudaFree(op->d_emat); cudaFree(op->d_xin); cudaFree(op->d_yout); cudaFree(op->d_tmp);
   for (int i = 0; i < hcurl_op::RING; i++) { cudaEventDestroy(op->ring0[i]); cudaEventDestroy(op->ring1[i]); }
   delete op;
 }
 int hcurl_op_set_kernel(hcurl_op *op, int which) {
-  if (which != 0 && which != 1) { set_error("kernel selector must be 0 (auto) or 1 (generic)"); return 1; }
+  if (which < 0 || which > 3) { set_error("kernel selector must be 0 (auto), 1 (generic), 2 (element-wise fast) or 3 (patch)"); return 1; }
   op->force_generic = which == 1;
+  op->kernel_sel = which;
   return 0;
 }
 int hcurl_op_qpts_curl(const hcurl_op *op) { return op->sp->geom == HCURL_GEOM_HEX ? op->qc * op->qc * op->qc : 1; }
@@ -494,6 +499,7 @@ int hcurl_op_set_coefficients(hcurl_op *op, int layout, const double *alpha, con
   HC_CUDA(cudaStreamSynchronize(op->ctx->stream));  // host buffers are borrowed for the call only
   op->emat_valid = false;
   op->edata_valid = false;
+  op->edataP_valid = false;
   return 0;
 }
 
@@ -522,6 +528,7 @@ int hcurl_op_set_essential_tdofs(hcurl_op *op, const int32_t *ess, int32_t n_ess
   HC_CUDA(cudaMalloc(&op->d_map_ess, sizeof(uint32_t) * nmap));
   flag_map_kernel<<<(unsigned)((nmap + 255) / 256), 256, 0, ctx->stream>>>((int64_t)nmap, sp->d_map, flag, op->d_map_ess);
   HC_CUDA(cudaGetLastError());
+  if (hex_patch_flag_essential(op, flag)) return 1;
   HC_CUDA(cudaStreamSynchronize(ctx->stream));
   cudaFree(flag);
   return 0;

@@ -415,7 +415,7 @@ int hex_fast_prepare_space(hcurl_space *sp) {
 bool hex_fast_eligible(const hcurl_op *op) {
   const hcurl_space *sp = op->sp;
   return sp->geom == HCURL_GEOM_HEX && sp->order == 2 && sp->geom_order == 1 && op->single_rule && op->qc == 3 &&
-         op->coef_layout == HCURL_COEF_PER_ELEM && op->has_alpha && op->has_beta && !op->force_generic;
+         op->coef_layout == HCURL_COEF_PER_ELEM && op->has_alpha && op->has_beta && !op->force_generic && op->kernel_sel != 3;
 }
 
 int hex_fast_update_coefficients(hcurl_op *op) {

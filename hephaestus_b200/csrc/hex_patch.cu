@@ -1,0 +1,455 @@
+// Patch-based order-2 Nedelec hex apply:  y (+)= scale * (K(alpha) + M(beta)) x.
+//
+// Same operator as hex_apply.cu / hex_fast.cu (CurlCurlKernel + VectorFEMassKernel,
+// /root/reference/src/kernels/curl_curl_kernel.cpp:21-24, vector_fe_mass_kernel.cpp:21-24, applied as
+// EquationSystem::Mult, /root/reference/src/equation_systems/equation_system.cpp:200-204), organised
+// around what ncu showed to bound the element-wise kernels on sm_100a:
+//
+//  * L1tex lane rate of gathers / FP64 RED atomics  ->  one CTA per PATCH of FE adjacent elements
+//    (patch.cpp); x is gathered once per unique patch dof into a shared-memory E-vector, y is
+//    summed per patch dof from the E-vector, private dofs are plain stores, only patch-boundary
+//    dofs use RED.
+//  * FP64 pipe (36 TFLOP/s measured; the quadrature-based apply needs 2916 DFMA / element)  ->
+//    on AFFINE elements with per-element coefficients the element operator is applied in an
+//    orthonormal Legendre (modal) basis, where the mass matrix is a restricted identity and the
+//    curl has one term per mode:  A_e = T^T [ GM (x) I + C^T (GK (x) I) C ] T  with
+//    GK = alpha J^T J / det, GM = beta adj adj^T / det.  474 DFMA per thread, 1422 per element,
+//    exact (the p+1 Gauss rule it replaces is exact on these elements too).
+//  * instruction-cache misses of fully unrolled per-component code  ->  every thread works in the
+//    rotated frame (c, c+1, c+2) of its component c, so all warps run the same instruction stream.
+//
+// Thread layout: 3*FE threads; thread (c, e) owns component c of element e of the patch.
+// E-vector layout: E[(c*18 + t)*FE + e], t = i0 + 2*(i1 + 3*i2) with i0 the open index along axis c.
+#include <cstdlib>
+
+#include "internal.h"
+
+namespace hcurl {
+
+struct ModalTables {
+  double To[4];  // [m][i] nodal (Gauss-Legendre) -> orthonormal Legendre, open basis
+  double Tc[9];  // [m][j] nodal (Gauss-Lobatto)  -> orthonormal Legendre, closed basis
+  double d1, d2; // L1' = d1 L0, L2' = d2 L1
+};
+__constant__ ModalTables cM;
+
+int hex_rot_slot_to_tensor(int p, int slot) {
+  const int p1 = p + 1, nc = p * p1 * p1;
+  const int c = slot / nc, t = slot % nc;
+  int ir[3] = {t % p, (t / p) % p1, t / (p * p1)};  // along axes c, c+1, c+2
+  int idx[3];
+  for (int k = 0; k < 3; k++) idx[(c + k) % 3] = ir[k];
+  const int n0 = (c == 0) ? p : p1, n1 = (c == 1) ? p : p1;
+  return c * nc + idx[0] + n0 * (idx[1] + n1 * idx[2]);
+}
+
+__device__ __forceinline__ int sym6(int i, int j) {  // packed index of the symmetric pair (i,j)
+  const int lo = min(i, j), hi = max(i, j);
+  return lo * 3 - lo * (lo - 1) / 2 + (hi - lo);
+}
+
+#define IA(m0, m1, m2) ((m0) + 2 * ((m1) + 3 * (m2)))  // own component  [2][3][3]
+#define IB(m0, m1, m2) ((m0) + 3 * ((m1) + 2 * (m2)))  // component c+1  [3][2][3] (my frame)
+#define IC(m0, m1, m2) ((m0) + 3 * ((m1) + 3 * (m2)))  // component c+2  [3][3][2] (my frame)
+
+// nodal -> modal on own component (in place semantics: X -> A)
+__device__ __forceinline__ void modal_fwd(const double *X, double *A) {
+  double a[18], b[18];
+#pragma unroll
+  for (int r = 0; r < 9; r++)
+#pragma unroll
+    for (int m = 0; m < 2; m++) a[m + 2 * r] = fma(cM.To[m * 2 + 1], X[1 + 2 * r], cM.To[m * 2] * X[2 * r]);
+#pragma unroll
+  for (int i2 = 0; i2 < 3; i2++)
+#pragma unroll
+    for (int m1 = 0; m1 < 3; m1++)
+#pragma unroll
+      for (int m0 = 0; m0 < 2; m0++)
+        b[IA(m0, m1, i2)] = fma(cM.Tc[m1 * 3 + 2], a[IA(m0, 2, i2)], fma(cM.Tc[m1 * 3 + 1], a[IA(m0, 1, i2)], cM.Tc[m1 * 3] * a[IA(m0, 0, i2)]));
+#pragma unroll
+  for (int m2 = 0; m2 < 3; m2++)
+#pragma unroll
+    for (int r = 0; r < 6; r++)
+      A[r + 6 * m2] = fma(cM.Tc[m2 * 3 + 2], b[r + 12], fma(cM.Tc[m2 * 3 + 1], b[r + 6], cM.Tc[m2 * 3] * b[r]));
+}
+// modal -> nodal test functions (transpose)
+__device__ __forceinline__ void modal_bwd(const double *Yh, double *Y) {
+  double a[18], b[18];
+#pragma unroll
+  for (int i2 = 0; i2 < 3; i2++)
+#pragma unroll
+    for (int r = 0; r < 6; r++)
+      a[r + 6 * i2] = fma(cM.Tc[6 + i2], Yh[r + 12], fma(cM.Tc[3 + i2], Yh[r + 6], cM.Tc[i2] * Yh[r]));
+#pragma unroll
+  for (int i2 = 0; i2 < 3; i2++)
+#pragma unroll
+    for (int i1 = 0; i1 < 3; i1++)
+#pragma unroll
+      for (int m0 = 0; m0 < 2; m0++)
+        b[IA(m0, i1, i2)] = fma(cM.Tc[6 + i1], a[IA(m0, 2, i2)], fma(cM.Tc[3 + i1], a[IA(m0, 1, i2)], cM.Tc[i1] * a[IA(m0, 0, i2)]));
+#pragma unroll
+  for (int r = 0; r < 9; r++)
+#pragma unroll
+    for (int i0 = 0; i0 < 2; i0++) Y[i0 + 2 * r] = fma(cM.To[2 + i0], b[1 + 2 * r], cM.To[i0] * b[2 * r]);
+}
+
+// modal element operator for component a0 = c: reads own (Am) and the other two components' modal
+// coefficients (Bm = comp c+1, Cm = comp c+2, in my frame), G = scaled geometry factors
+__device__ __forceinline__ void modal_op(const double *Am, const double *Bm, const double *Cm, const double M00,
+                                         const double M01, const double M02, const double K11, const double K10,
+                                         const double K12, const double K22, const double K20, const double K21,
+                                         double *Yh) {
+  const double d1 = cM.d1, d2 = cM.d2;
+#define DD(n) ((n) == 1 ? d1 : d2)
+  double r0[8], r1[12], r2[12];
+#pragma unroll
+  for (int m0 = 0; m0 < 2; m0++) {
+#pragma unroll
+    for (int m1 = 0; m1 < 2; m1++)
+#pragma unroll
+      for (int m2 = 0; m2 < 2; m2++)
+        r0[m0 + 2 * (m1 + 2 * m2)] = fma(DD(m1 + 1), Cm[IC(m0, m1 + 1, m2)], -DD(m2 + 1) * Bm[IB(m0, m1, m2 + 1)]);
+#pragma unroll
+    for (int m1 = 0; m1 < 3; m1++)
+#pragma unroll
+      for (int m2 = 0; m2 < 2; m2++)
+        r1[m0 + 2 * (m1 + 3 * m2)] = fma(DD(m2 + 1), Am[IA(m0, m1, m2 + 1)], -DD(m0 + 1) * Cm[IC(m0 + 1, m1, m2)]);
+#pragma unroll
+    for (int m1 = 0; m1 < 2; m1++)
+#pragma unroll
+      for (int m2 = 0; m2 < 3; m2++)
+        r2[m0 + 2 * (m1 + 2 * m2)] = fma(DD(m0 + 1), Bm[IB(m0 + 1, m1, m2)], -DD(m1 + 1) * Am[IA(m0, m1 + 1, m2)]);
+  }
+  double w1[12], w2[12];
+#pragma unroll
+  for (int m0 = 0; m0 < 2; m0++) {
+#pragma unroll
+    for (int m1 = 0; m1 < 3; m1++)
+#pragma unroll
+      for (int m2 = 0; m2 < 2; m2++) {
+        double v = K11 * r1[m0 + 2 * (m1 + 3 * m2)];
+        if (m1 < 2) v = fma(K12, r2[m0 + 2 * (m1 + 2 * m2)], fma(K10, r0[m0 + 2 * (m1 + 2 * m2)], v));
+        w1[m0 + 2 * (m1 + 3 * m2)] = v;
+      }
+#pragma unroll
+    for (int m1 = 0; m1 < 2; m1++)
+#pragma unroll
+      for (int m2 = 0; m2 < 3; m2++) {
+        double v = K22 * r2[m0 + 2 * (m1 + 2 * m2)];
+        if (m2 < 2) v = fma(K21, r1[m0 + 2 * (m1 + 3 * m2)], fma(K20, r0[m0 + 2 * (m1 + 2 * m2)], v));
+        w2[m0 + 2 * (m1 + 2 * m2)] = v;
+      }
+  }
+#pragma unroll
+  for (int n2 = 0; n2 < 3; n2++)
+#pragma unroll
+    for (int n1 = 0; n1 < 3; n1++)
+#pragma unroll
+      for (int n0 = 0; n0 < 2; n0++) {
+        double v = M00 * Am[IA(n0, n1, n2)];
+        if (n1 < 2) v = fma(M01, Bm[IB(n0, n1, n2)], v);
+        if (n2 < 2) v = fma(M02, Cm[IC(n0, n1, n2)], v);
+        if (n2 >= 1) v = fma(DD(n2), w1[n0 + 2 * (n1 + 3 * (n2 - 1))], v);
+        if (n1 >= 1) v = fma(-DD(n1), w2[n0 + 2 * ((n1 - 1) + 2 * n2)], v);
+        Yh[IA(n0, n1, n2)] = v;
+      }
+#undef DD
+}
+
+struct PatchArgs {
+  int64_t n_elem;           // number of real elements (patch positions >= n_elem are padding... see perm)
+  int64_t n_pos;            // n_patch * FE
+  const int32_t *perm;      // element at each patch position (-1 padding)
+  const uint32_t *off, *npriv, *dof;
+  const uint16_t *start, *slots;
+  const double *edata;      // [12][n_pos] affine geometry factors in patch order
+  const double *x;
+  double *y;
+  double scale;
+};
+
+template <int FE, bool ACC>
+__global__ void __launch_bounds__(3 * FE)
+hex_patch_modal_p2_kernel(const PatchArgs a) {
+  extern __shared__ double E[];  // [54][FE]
+  constexpr int NT = 3 * FE;
+  const int tid = threadIdx.x;
+  const int64_t k = blockIdx.x;
+  const uint32_t o = a.off[k], U = a.off[k + 1] - o, npriv = a.npriv[k];
+  const uint32_t *pdof = a.dof + o;
+  const uint16_t *pst = a.start + o + k;
+  const uint16_t *psl = a.slots + k * (int64_t)(FE * 54);
+  // ---- A: gather x per unique patch dof, push to the element slots
+  for (uint32_t u = tid; u < U; u += NT) {
+    const uint32_t m = __ldg(pdof + u);
+    const double v = (m & MAP_ESS) ? 0.0 : __ldg(a.x + (m & MAP_IDX));
+    const int s0 = __ldg(pst + u), s1 = __ldg(pst + u + 1);
+    for (int s = s0; s < s1; s++) {
+      const uint32_t sl = __ldg(psl + s);
+      E[sl & 0x7fffu] = (sl & 0x8000u) ? -v : v;
+    }
+  }
+  __syncthreads();
+  // ---- element operator: component c of patch element el
+  const int c = tid / FE, el = tid - c * FE;
+  const int64_t pos = k * FE + el;
+  const bool ok = __ldg(a.perm + pos) >= 0;
+  double *Eown = E + (c * 18) * FE + el;
+  double Am[18];
+  if (ok) {
+    double X[18];
+#pragma unroll
+    for (int t = 0; t < 18; t++) X[t] = Eown[t * FE];
+    modal_fwd(X, Am);
+#pragma unroll
+    for (int t = 0; t < 18; t++) Eown[t * FE] = Am[t];
+  }
+  __syncthreads();
+  double Y[18];
+  if (ok) {
+    const int c1 = c == 2 ? 0 : c + 1, c2 = c == 0 ? 2 : c - 1;
+    const double *E1 = E + (c1 * 18) * FE + el, *E2 = E + (c2 * 18) * FE + el;
+    double Bm[18], Cm[18];
+    // owner frames: comp c+1 stores (m1, m2, m0), comp c+2 stores (m2, m0, m1)
+#pragma unroll
+    for (int m2 = 0; m2 < 3; m2++)
+#pragma unroll
+      for (int m1 = 0; m1 < 2; m1++)
+#pragma unroll
+        for (int m0 = 0; m0 < 3; m0++) Bm[IB(m0, m1, m2)] = E1[(m1 + 2 * (m2 + 3 * m0)) * FE];
+#pragma unroll
+    for (int m2 = 0; m2 < 2; m2++)
+#pragma unroll
+      for (int m1 = 0; m1 < 3; m1++)
+#pragma unroll
+        for (int m0 = 0; m0 < 3; m0++) Cm[IC(m0, m1, m2)] = E2[(m2 + 2 * (m0 + 3 * m1)) * FE];
+    const double *g = a.edata + pos;
+    const int64_t np = a.n_pos;
+    const double sc = a.scale;
+    const double K11 = sc * __ldg(g + sym6(c1, c1) * np), K10 = sc * __ldg(g + sym6(c1, c) * np),
+                 K12 = sc * __ldg(g + sym6(c1, c2) * np), K22 = sc * __ldg(g + sym6(c2, c2) * np),
+                 K20 = sc * __ldg(g + sym6(c2, c) * np), K21 = K12;
+    const double M00 = sc * __ldg(g + (6 + sym6(c, c)) * np), M01 = sc * __ldg(g + (6 + sym6(c, c1)) * np),
+                 M02 = sc * __ldg(g + (6 + sym6(c, c2)) * np);
+    double Yh[18];
+    modal_op(Am, Bm, Cm, M00, M01, M02, K11, K10, K12, K22, K20, K21, Yh);
+    modal_bwd(Yh, Y);
+  }
+  __syncthreads();  // everyone has read the modal coefficients
+  if (ok) {
+#pragma unroll
+    for (int t = 0; t < 18; t++) Eown[t * FE] = Y[t];
+  }
+  __syncthreads();
+  // ---- C: sum the slots of every patch dof; private dofs are plain stores, shared ones RED
+  for (uint32_t u = tid; u < U; u += NT) {
+    const uint32_t m = __ldg(pdof + u);
+    if (m & MAP_ESS) continue;
+    const int s0 = __ldg(pst + u), s1 = __ldg(pst + u + 1);
+    double v = 0.0;
+    for (int s = s0; s < s1; s++) {
+      const uint32_t sl = __ldg(psl + s);
+      const double t = E[sl & 0x7fffu];
+      v += (sl & 0x8000u) ? -t : t;
+    }
+    double *dst = a.y + (m & MAP_IDX);
+    if (u < npriv) *dst = ACC ? *dst + v : v;
+    else atomicAdd(dst, v);
+  }
+}
+
+// ---- setup ---------------------------------------------------------------------------------------
+// affine geometry factors in patch order: S = alpha J^T J/det (6), M = beta adj adj^T/det (6)
+__global__ void patch_edata_kernel(const int64_t n_pos, const int32_t *__restrict__ perm, const double *__restrict__ xyz,
+                                   const double *__restrict__ alpha, const double *__restrict__ beta,
+                                   double *__restrict__ edata) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_pos) return;
+  const int32_t e = perm[j];
+  if (e < 0) {
+    for (int s = 0; s < 12; s++) edata[(int64_t)s * n_pos + j] = 0.0;
+    return;
+  }
+  const double *X = xyz + (int64_t)e * 24;  // tensor order
+  double c0[3], c1[3], c2[3];
+  for (int d = 0; d < 3; d++) { c0[d] = X[3 + d] - X[d]; c1[d] = X[6 + d] - X[d]; c2[d] = X[12 + d] - X[d]; }
+  const double a0[3] = {c1[1] * c2[2] - c1[2] * c2[1], c1[2] * c2[0] - c1[0] * c2[2], c1[0] * c2[1] - c1[1] * c2[0]};
+  const double a1[3] = {c2[1] * c0[2] - c2[2] * c0[1], c2[2] * c0[0] - c2[0] * c0[2], c2[0] * c0[1] - c2[1] * c0[0]};
+  const double a2[3] = {c0[1] * c1[2] - c0[2] * c1[1], c0[2] * c1[0] - c0[0] * c1[2], c0[0] * c1[1] - c0[1] * c1[0]};
+  const double det = c0[0] * a0[0] + c0[1] * a0[1] + c0[2] * a0[2];
+  const double al = alpha ? alpha[e] / det : 0.0, be = beta ? beta[e] / det : 0.0;
+  const double *c[3] = {c0, c1, c2};
+  const double *ad[3] = {a0, a1, a2};
+  int s = 0;
+  for (int i = 0; i < 3; i++)
+    for (int jj = i; jj < 3; jj++, s++) {
+      edata[(int64_t)s * n_pos + j] = al * (c[i][0] * c[jj][0] + c[i][1] * c[jj][1] + c[i][2] * c[jj][2]);
+      edata[(int64_t)(6 + s) * n_pos + j] = be * (ad[i][0] * ad[jj][0] + ad[i][1] * ad[jj][1] + ad[i][2] * ad[jj][2]);
+    }
+}
+
+__global__ void patch_flag_kernel(const int64_t n, const uint32_t *__restrict__ in, const double *__restrict__ flag,
+                                  uint32_t *__restrict__ out) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= n) return;
+  const uint32_t m = in[gid];
+  out[gid] = (flag[m & MAP_IDX] != 0.0) ? (m | MAP_ESS) : m;
+}
+
+static bool g_modal_set = false;
+static int set_modal_tables() {
+  if (g_modal_set) return 0;
+  // orthonormal shifted Legendre on [0,1]: L0 = 1, L1 = sqrt3 (2x-1), L2 = sqrt5 (6x^2-6x+1);
+  // T[m][j] = int_0^1 L_m l_j, by a 5-point Gauss rule (exact)
+  double xq[5], wq[5], gl[2], wl[2], gll[3];
+  gauss_legendre01(5, xq, wq);
+  gauss_legendre01(2, gl, wl);
+  gauss_lobatto01(3, gll);
+  double Bo[5 * 2], Bc[5 * 3];
+  lagrange_tables(2, gl, 5, xq, Bo, nullptr);
+  lagrange_tables(3, gll, 5, xq, Bc, nullptr);
+  ModalTables T;
+  for (int m = 0; m < 3; m++) {
+    for (int j = 0; j < 3; j++) T.Tc[m * 3 + j] = 0.0;
+    if (m < 2) for (int i = 0; i < 2; i++) T.To[m * 2 + i] = 0.0;
+  }
+  for (int q = 0; q < 5; q++) {
+    const double t = 2.0 * xq[q] - 1.0;
+    const double L[3] = {1.0, sqrt(3.0) * t, sqrt(5.0) * 0.5 * (3.0 * t * t - 1.0)};
+    for (int m = 0; m < 3; m++) {
+      for (int j = 0; j < 3; j++) T.Tc[m * 3 + j] += wq[q] * L[m] * Bc[q * 3 + j];
+      if (m < 2) for (int i = 0; i < 2; i++) T.To[m * 2 + i] += wq[q] * L[m] * Bo[q * 2 + i];
+    }
+  }
+  T.d1 = 2.0 * sqrt(3.0);
+  T.d2 = 2.0 * sqrt(15.0);
+  HC_CUDA(cudaMemcpyToSymbol(cM, &T, sizeof(T)));
+  g_modal_set = true;
+  return 0;
+}
+
+template <class T>
+static int upload(T *&dst, const std::vector<T> &src) {
+  HC_CUDA(cudaMalloc(&dst, sizeof(T) * (src.size() ? src.size() : 1)));
+  HC_CUDA(cudaMemcpy(dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int hex_patch_build(hcurl_space *sp, const double *elem_xyz, const int32_t *elem_ldof, const int32_t *l2e) {
+  if (sp->geom != HCURL_GEOM_HEX || sp->order != 2 || sp->geom_order != 1) return 0;
+  const char *off = getenv("HCURL_NO_PATCH");
+  if (off && off[0] == '1') return 0;
+  int FE = 64;
+  if (const char *s = getenv("HCURL_PATCH_FE")) FE = atoi(s);
+  if (FE != 32 && FE != 64 && FE != 128) { set_error("HCURL_PATCH_FE must be 32, 64 or 128"); return 1; }
+  const int nd = sp->nd, p = sp->order;
+  const int64_t ne = sp->n_elem;
+  std::vector<int> loc, sgn;
+  nd_hex_dof_map(p, loc, sgn);
+  std::vector<int> tens(nd);
+  for (int s = 0; s < nd; s++) tens[s] = hex_rot_slot_to_tensor(p, s);
+  std::vector<uint32_t> code((size_t)ne * nd);
+  std::vector<double> cen((size_t)ne * 3);
+  for (int64_t e = 0; e < ne; e++) {
+    for (int s = 0; s < nd; s++) {
+      const int t = tens[s];
+      const int32_t v = elem_ldof[e * nd + loc[t]];
+      const int32_t kk = v >= 0 ? v : -1 - v;
+      bool neg = v < 0;
+      if (sgn[t] < 0) neg = !neg;
+      const uint32_t ext = l2e ? (uint32_t)l2e[kk] : (uint32_t)kk;
+      code[(size_t)e * nd + s] = ext | (neg ? MAP_NEG : 0u);
+    }
+    for (int d = 0; d < 3; d++) {
+      double c = 0.0;
+      for (int v = 0; v < 8; v++) c += elem_xyz[(e * 8 + v) * 3 + d];
+      cen[(size_t)e * 3 + d] = 0.125 * c;
+    }
+  }
+  PatchHost H;
+  if (build_patches(nd, ne, FE, sp->n_ext(), cen.data(), code.data(), H)) return 1;
+  HC_CUDA(cudaSetDevice(sp->ctx->device));
+  PatchSet &P = sp->patch;
+  P.FE = FE; P.n_patch = H.n_patch; P.n_pd = (int64_t)H.dof.size();
+  if (upload(P.d_perm, H.perm) || upload(P.d_off, H.off) || upload(P.d_npriv, H.npriv) || upload(P.d_dof, H.dof) ||
+      upload(P.d_start, H.start) || upload(P.d_slots, H.slots))
+    return 1;
+  sp->has_patches = true;
+  return 0;
+}
+
+void hex_patch_free(hcurl_space *sp) {
+  PatchSet &P = sp->patch;
+  cudaFree(P.d_perm); cudaFree(P.d_off); cudaFree(P.d_npriv); cudaFree(P.d_dof); cudaFree(P.d_start); cudaFree(P.d_slots);
+  cudaFree(sp->d_xyzP);
+  P = PatchSet();
+  sp->has_patches = false;
+}
+
+bool hex_patch_eligible(const hcurl_op *op) {
+  const hcurl_space *sp = op->sp;
+  if (!(sp->has_patches && op->single_rule && op->qc == 3 && op->coef_layout == HCURL_COEF_PER_ELEM && op->has_alpha &&
+        op->has_beta))
+    return false;
+  if (op->kernel_sel == 1 || op->kernel_sel == 2) return false;
+  // affine meshes only (modal operator); checked lazily by hex_fast_prepare_space
+  if (!sp->fast_ready && hex_fast_prepare_space(const_cast<hcurl_space *>(sp))) return false;
+  return sp->all_affine;
+}
+
+template <int FE>
+static int launch_fe(const PatchArgs &a, int64_t n_patch, bool acc, cudaStream_t st) {
+  const size_t smem = sizeof(double) * 54 * FE;
+  auto k0 = hex_patch_modal_p2_kernel<FE, false>;
+  auto k1 = hex_patch_modal_p2_kernel<FE, true>;
+  static bool attr = false;
+  if (!attr) {
+    HC_CUDA(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HC_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  if (acc) k1<<<(unsigned)n_patch, 3 * FE, smem, st>>>(a);
+  else k0<<<(unsigned)n_patch, 3 * FE, smem, st>>>(a);
+  return 0;
+}
+
+int hex_patch_launch(hcurl_op *op, bool constrained, const double *d_x, double *d_y, double scale, bool accumulate) {
+  hcurl_space *sp = op->sp;
+  hcurl_ctx *ctx = op->ctx;
+  PatchSet &P = sp->patch;
+  if (set_modal_tables()) return 1;
+  const int64_t n_pos = P.n_patch * P.FE;
+  if (!op->edataP_valid) {
+    if (!op->d_edataP) HC_CUDA(cudaMalloc(&op->d_edataP, sizeof(double) * 12 * n_pos));
+    patch_edata_kernel<<<(unsigned)((n_pos + 255) / 256), 256, 0, ctx->stream>>>(n_pos, P.d_perm, sp->d_xyz, op->d_alpha, op->d_beta,
+                                                                                op->d_edataP);
+    HC_CUDA(cudaGetLastError());
+    op->edataP_valid = true;
+  }
+  PatchArgs a;
+  a.n_elem = sp->n_elem; a.n_pos = n_pos; a.perm = P.d_perm; a.off = P.d_off; a.npriv = P.d_npriv;
+  a.dof = (constrained && op->d_pdof_ess) ? op->d_pdof_ess : P.d_dof;
+  a.start = P.d_start; a.slots = P.d_slots; a.edata = op->d_edataP; a.x = d_x; a.y = d_y; a.scale = scale;
+  int rc = 1;
+  if (P.FE == 32) rc = launch_fe<32>(a, P.n_patch, accumulate, ctx->stream);
+  else if (P.FE == 64) rc = launch_fe<64>(a, P.n_patch, accumulate, ctx->stream);
+  else if (P.FE == 128) rc = launch_fe<128>(a, P.n_patch, accumulate, ctx->stream);
+  if (rc) return rc;
+  HC_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return 0;
+}
+
+// essential flags on the patch dof list (called from hcurl_op_set_essential_tdofs with the flag vector)
+int hex_patch_flag_essential(hcurl_op *op, const double *d_flag) {
+  hcurl_space *sp = op->sp;
+  if (!sp->has_patches) return 0;
+  PatchSet &P = sp->patch;
+  cudaFree(op->d_pdof_ess); op->d_pdof_ess = nullptr;
+  HC_CUDA(cudaMalloc(&op->d_pdof_ess, sizeof(uint32_t) * (P.n_pd ? P.n_pd : 1)));
+  patch_flag_kernel<<<(unsigned)((P.n_pd + 255) / 256), 256, 0, op->ctx->stream>>>(P.n_pd, P.d_dof, d_flag, op->d_pdof_ess);
+  HC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace hcurl

@@ -61,6 +61,31 @@ void build_tet_ref(int p, TetRef &r);
 // triangle-face dof transformation: R (nf x nf, row-major), x_local = R x_base
 void tri_face_transform(int p, const int32_t *local_verts, const int32_t *base_verts, double *R);
 
+// ---------------------------------------------------------------- patches ----
+// Host result of build_patches() (patch.cpp); uploaded into a PatchSet by hex_patch.cu.
+struct PatchHost {
+  int FE = 0, nd = 0;
+  int64_t n_patch = 0;
+  std::vector<int32_t> perm;     // [n_patch*FE] element at each patch position, -1 = padding
+  std::vector<uint32_t> off;     // [n_patch+1] first patch dof
+  std::vector<uint32_t> npriv;   // [n_patch] number of private dofs (listed first)
+  std::vector<uint32_t> dof;     // [n_pd] extended-vector index
+  std::vector<uint16_t> start;   // [n_pd + n_patch] slot-list offsets, U+1 per patch
+  std::vector<uint16_t> slots;   // [n_patch*FE*nd] E-vector slot | 0x8000 sign flip
+};
+int build_patches(int nd, int64_t n_elem, int FE, int64_t n_ext, const double *centroid, const uint32_t *slot_code,
+                  PatchHost &out);
+// slot s of the rotated per-component layout (hex_patch.cu) -> standard tensor index
+int hex_rot_slot_to_tensor(int p, int slot);
+
+struct PatchSet {  // device copy
+  int FE = 0;
+  int64_t n_patch = 0, n_pd = 0;
+  int32_t *d_perm = nullptr;
+  uint32_t *d_off = nullptr, *d_npriv = nullptr, *d_dof = nullptr;
+  uint16_t *d_start = nullptr, *d_slots = nullptr;
+};
+
 // ----------------------------------------------------------------- NCCL ----
 struct Nccl;  // dlopen'ed function table (comm.cpp)
 
@@ -108,6 +133,10 @@ struct hcurl_space {
   bool fast_ready = false, all_affine = false;
   uint32_t *d_mapT = nullptr;
   double *d_xyzT = nullptr;
+  // patch path (hex_patch.cu): built at creation for order-2 trilinear hexes
+  bool has_patches = false;
+  hcurl::PatchSet patch;
+  double *d_xyzP = nullptr;  // [24][n_patch*FE] vertices in patch order (non-affine meshes)
 };
 
 struct hcurl_op {
@@ -129,6 +158,10 @@ struct hcurl_op {
   double *d_edata = nullptr;
   bool edata_valid = false;
   uint32_t *d_mapT_ess = nullptr;
+  uint32_t *d_pdof_ess = nullptr;  // patch dof list with essential flags
+  double *d_edataP = nullptr;      // [12][n_patch*FE] affine geometry factors in patch order
+  bool edataP_valid = false;
+  int kernel_sel = 0;              // 0 auto, 1 generic, 2 element-wise fast path, 3 patch path
   bool force_generic = false;
   // work vectors (extended length)
   double *d_xin = nullptr, *d_yout = nullptr, *d_tmp = nullptr;
@@ -158,6 +191,14 @@ int hex_apply_launch(hcurl_op *op, const uint32_t *d_map, const double *d_x, dou
 int hex_diag_launch(hcurl_op *op, double *d_diag);
 bool hex_fast_eligible(const hcurl_op *op);
 int hex_fast_launch(hcurl_op *op, bool constrained, const double *d_x, double *d_y, double scale);
+int hex_patch_build(hcurl_space *sp, const double *elem_xyz, const int32_t *elem_ldof, const int32_t *l2e);
+void hex_patch_free(hcurl_space *sp);
+bool hex_patch_eligible(const hcurl_op *op);
+// y (+)= scale * A x through the patch path; when !accumulate every dof of y is written
+// (private dofs) or must have been zeroed by the caller (shared dofs)
+int hex_patch_launch(hcurl_op *op, bool constrained, const double *d_x, double *d_y, double scale, bool accumulate);
+int hex_patch_flag_essential(hcurl_op *op, const double *d_flag);
+int hex_fast_prepare_space(hcurl_space *sp);
 int tet_build_emat(hcurl_op *op);
 int tet_apply_launch(hcurl_op *op, const uint32_t *d_map, const double *d_x, double *d_y, double scale);
 int tet_diag_launch(hcurl_op *op, double *d_diag);

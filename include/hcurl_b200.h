@@ -139,9 +139,10 @@ int hcurl_space_elem_ndof(const hcurl_space *sp);
  */
 hcurl_op *hcurl_op_create(hcurl_ctx *ctx, hcurl_space *sp, int quad_pts_per_dim);
 void hcurl_op_destroy(hcurl_op *op);
-/* Kernel selection: 0 = automatic (register-blocked fast path where one exists: order-2
- * trilinear hexes with one p+1 rule and per-element coefficients), 1 = always the generic
- * sum-factorised kernel.  Both compute the same operator; tests compare them. */
+/* Kernel selection: 0 = automatic (fastest eligible: patch kernels for order-2 trilinear hexes
+ * with one p+1 rule and per-element coefficients), 1 = always the generic sum-factorised
+ * kernel, 2 = element-wise register-blocked kernel, 3 = patch kernel.  All compute the same
+ * operator; tests compare them. */
 int hcurl_op_set_kernel(hcurl_op *op, int which);
 /* Number of coefficient values expected per element for PER_QPT layout. */
 int hcurl_op_qpts_curl(const hcurl_op *op);
@@ -214,6 +215,27 @@ double *hcurl_host_alloc_pinned(int64_t n_doubles);
 void hcurl_host_free_pinned(double *p);
 /* global dot product over true dofs (all-reduced across ranks) */
 int hcurl_dot(hcurl_ctx *ctx, const double *a_dev, const double *b_dev, int64_t n, double *result);
+
+/* ---- host-side setup helper: patch decomposition (no GPU needed) ---------------------
+ * Groups elements into patches of `elems_per_patch` spatially adjacent elements (Morton
+ * order of the centroids) and lists, per patch, its unique dofs with the element slots
+ * each one feeds -- the structure the patch kernels use instead of the per-element
+ * gather / atomic scatter through FiniteElementSpace::GetElementDofs
+ * (what blf->Assemble() resolves through the CSR sparsity in the reference,
+ * /root/reference/src/equation_systems/equation_system.cpp:345).
+ *  slot_code  [n_elem][nd]: dof index (bits 0..29) | sign flip (bit 31) of each element slot
+ *  outputs    perm [n_patch*epp] element at each patch position (-1 padding);
+ *             off [n_patch+1]; npriv [n_patch] (dofs touched by this patch only, listed
+ *             first); dof [off[n_patch]]; start [off[n_patch] + n_patch] (U+1 per patch);
+ *             slots [n_patch*epp*nd] = (slot*epp + position) | 0x8000 sign flip. */
+typedef struct hcurl_host_patches hcurl_host_patches;
+hcurl_host_patches *hcurl_host_patches_create(int nd, int64_t n_elem, int elems_per_patch, int64_t n_dof,
+                                              const double *centroid, const uint32_t *slot_code);
+void hcurl_host_patches_destroy(hcurl_host_patches *p);
+int64_t hcurl_host_patches_count(const hcurl_host_patches *p);
+int64_t hcurl_host_patches_ndof_entries(const hcurl_host_patches *p);
+int hcurl_host_patches_copy(const hcurl_host_patches *p, int32_t *perm, uint32_t *off, uint32_t *npriv,
+                            uint32_t *dof, uint16_t *start, uint16_t *slots);
 
 /* FP64 FMA micro-benchmark used for the roofline co-bound:
  * returns achieved TFLOP/s of dependent-chain-free DFMA on the device. */

@@ -179,31 +179,63 @@ def test_errors_are_loud(ctx):
 
 @pytest.mark.parametrize("perturb", [False, True])
 @pytest.mark.parametrize("n", [(3, 3, 3), (5, 4, 3), (7, 5, 1)])
-def test_hex_p2_fast_path_matches_generic_and_oracle(ctx, perturb, n):
-    """The register-blocked order-2 kernel (hex_fast.cu; affine and trilinear variants)
-    against the generic kernel and the oracle, incl. ragged CTA batches."""
+def test_hex_p2_fast_paths_match_generic_and_oracle(ctx, perturb, n):
+    """Order-2 fast kernels -- patch kernel (hex_patch.cu: modal affine variant) and the
+    element-wise register-blocked kernel (hex_fast.cu: affine and trilinear variants) --
+    against the generic kernel and the oracle, incl. ragged CTA batches / partial patches."""
     m, sp, mo, so = make_pair("hex", n, 2, perturb, scramble=True)
     a, b = coefficients(m)
     gsp = operators.GpuNDSpace(ctx, sp)
     essd = sp.boundary_dofs(lambda c: c[:, 0] < 1e-9)
     x = np.random.default_rng(12345).standard_normal(sp.ndof)
-    ys = []
-    for which in (0, 1):
+    A = oa.assemble(so, a, b, q_override=3)
+    y_ref = oa.constrained_apply(A, essd, x)
+    y0 = np.random.default_rng(1).standard_normal(sp.ndof)
+    yu_ref = y0 - 0.5 * (A @ x)
+    for which in (0, 1, 2, 3):
         op = operators.HephGpuOperator(ctx, gsp, 3)
         op.SetKernel(which)
         op.SetCoefficients(a, b)
         op.SetEssentialTrueDofs(essd)
-        ys.append(op.Mult(x))
-        y0 = np.random.default_rng(1).standard_normal(sp.ndof)
+        assert rel_err(op.Mult(x), y_ref) < TOL, which
         yu = op.MultUnconstrained(x, y0.copy(), scale=-0.5, accumulate=True)
-        ys.append(yu)
-    A = oa.assemble(so, a, b, q_override=3)
-    y_ref = oa.constrained_apply(A, essd, x)
-    assert rel_err(ys[0], y_ref) < TOL and rel_err(ys[2], y_ref) < TOL
-    assert rel_err(ys[0], ys[2]) < 1e-13
-    assert rel_err(ys[1], ys[3]) < 1e-13
+        assert rel_err(yu, yu_ref) < TOL, which
     # coefficient update reuses the handle
     op.SetKernel(0)
     op.SetCoefficients(2.0 * a, 0.5 * b)
     A2 = oa.assemble(so, 2.0 * a, 0.5 * b, q_override=3)
     assert rel_err(op.Mult(x), oa.constrained_apply(A2, essd, x)) < TOL
+
+
+@pytest.mark.parametrize("fe", [32, 64, 128])
+def test_hex_p2_patch_kernel_patch_sizes(ctx, fe, monkeypatch):
+    """Patch kernel with 32 / 64 / 128 elements per patch on a mesh with several patches,
+    a skewed (non axis-aligned) affine geometry and a device-resident repeat (determinism of the
+    private-dof stores, RED only on patch-boundary dofs)."""
+    monkeypatch.setenv("HCURL_PATCH_FE", str(fe))
+    from hephaestus_b200 import fespace
+    from oracle import mesh as om, space as osp
+    n = (9, 8, 6)
+    shear = np.array([[1.0, 0.3, 0.1], [0.0, 0.8, 0.2], [0.1, 0.0, 1.2]])
+    m = fespace.cartesian_hex_mesh(*n)
+    m = fespace.Mesh("hex", m.verts @ shear.T, m.elems, m.attr)
+    mo = om.cartesian_hex(*n)
+    mo = om.Mesh("hex", mo.verts @ shear.T, mo.elems, mo.attr)
+    sp, so = fespace.NDSpace(m, 2), osp.NDSpace(mo, 2)
+    a, b = coefficients(m)
+    gsp = operators.GpuNDSpace(ctx, sp)
+    op = operators.HephGpuOperator(ctx, gsp, 3)
+    op.SetKernel(3)
+    op.SetCoefficients(a, b)
+    essd = sp.boundary_dofs()
+    op.SetEssentialTrueDofs(essd)
+    x = np.random.default_rng(7).standard_normal(sp.ndof)
+    A = oa.assemble(so, a, b, q_override=3)
+    y_ref = oa.constrained_apply(A, essd, x)
+    y = op.Mult(x)
+    assert rel_err(y, y_ref) < TOL
+    dx, dy = ctx.alloc(sp.ndof).upload(x), ctx.alloc(sp.ndof)
+    for _ in range(3):
+        op.Mult(dx, dy)
+    ctx.synchronize()
+    assert rel_err(dy.download(), y_ref) < TOL
