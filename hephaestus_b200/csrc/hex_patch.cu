@@ -19,7 +19,8 @@
 //    rotated frame (c, c+1, c+2) of its component c, so all warps run the same instruction stream.
 //
 // Thread layout: 3*FE threads; thread (c, e) owns component c of element e of the patch.
-// E-vector layout: E[(c*18 + t)*FE + e], t = i0 + 2*(i1 + 3*i2) with i0 the open index along axis c.
+// E-vector layout: E[(c*18 + t)*(FE+1) + e], t = i0 + 2*(i1 + 3*i2) with i0 the open index along axis c
+// (stride FE+1: lanes of the per-dof phases that hit different slots of one element fall in different banks).
 #include <cstdlib>
 
 #include "internal.h"
@@ -157,58 +158,143 @@ __device__ __forceinline__ void modal_op(const double *Am, const double *Bm, con
 }
 
 struct PatchArgs {
-  int64_t n_elem;           // number of real elements (patch positions >= n_elem are padding... see perm)
   int64_t n_pos;            // n_patch * FE
   const int32_t *perm;      // element at each patch position (-1 padding)
-  const uint32_t *off, *npriv, *dof;
-  const uint16_t *start, *slots;
+  const uint32_t *hdr, *dof, *e32, *ovf;
+  const uint16_t *e16;
+  const uint64_t *e64;
   const double *edata;      // [12][n_pos] affine geometry factors in patch order
   const double *x;
   double *y;
   double scale;
 };
 
-template <int FE, bool ACC>
-__global__ void __launch_bounds__(3 * FE)
-hex_patch_modal_p2_kernel(const PatchArgs a) {
-  extern __shared__ double E[];  // [54][FE]
-  constexpr int NT = 3 * FE;
-  const int tid = threadIdx.x;
-  const int64_t k = blockIdx.x;
-  const uint32_t o = a.off[k], U = a.off[k + 1] - o, npriv = a.npriv[k];
-  const uint32_t *pdof = a.dof + o;
-  const uint16_t *pst = a.start + o + k;
-  const uint16_t *psl = a.slots + k * (int64_t)(FE * 54);
-  // ---- A: gather x per unique patch dof, push to the element slots
-  for (uint32_t u = tid; u < U; u += NT) {
-    const uint32_t m = __ldg(pdof + u);
-    const double v = (m & MAP_ESS) ? 0.0 : __ldg(a.x + (m & MAP_IDX));
-    const int s0 = __ldg(pst + u), s1 = __ldg(pst + u + 1);
-    for (int s = s0; s < s1; s++) {
-      const uint32_t sl = __ldg(psl + s);
-      E[sl & 0x7fffu] = (sl & 0x8000u) ? -v : v;
+// sign flip carried in bit 15 of a slot entry
+__device__ __forceinline__ double apply_sign(double v, uint32_t entry) {
+  return __hiloint2double(__double2hiint(v) ^ (int)((entry << 16) & 0x80000000u), __double2loint(v));
+}
+template <int W> struct EntryT;
+template <> struct EntryT<1> { typedef uint16_t type; };
+template <> struct EntryT<2> { typedef uint32_t type; };
+template <> struct EntryT<4> { typedef uint64_t type; };
+
+// gather x once per patch dof of one group and push it to the W element slots it feeds
+template <int NT, int W>
+__device__ __forceinline__ void gather_group(const int tid, const uint32_t n, const uint32_t *__restrict__ dof,
+                                             const typename EntryT<W>::type *__restrict__ ent,
+                                             const double *__restrict__ x, double *E) {
+  constexpr int UNR = 4;
+  for (uint32_t u0 = tid; u0 < n; u0 += UNR * NT) {
+    uint32_t m[UNR];
+    uint64_t w[UNR];
+    double v[UNR];
+#pragma unroll
+    for (int i = 0; i < UNR; i++) {
+      const uint32_t u = u0 + i * NT;
+      m[i] = u < n ? __ldg(dof + u) : MAP_ESS;
+      w[i] = u < n ? (uint64_t)__ldg(ent + u) : 0;
+    }
+#pragma unroll
+    for (int i = 0; i < UNR; i++) v[i] = (m[i] & MAP_ESS) ? 0.0 : __ldg(x + (m[i] & MAP_IDX));
+#pragma unroll
+    for (int i = 0; i < UNR; i++)
+      if (u0 + i * NT < n) {
+#pragma unroll
+        for (int j = 0; j < W; j++) {
+          const uint32_t sl = (uint32_t)(w[i] >> (16 * j)) & 0xffffu;
+          if (W == 4 && j == 3 && sl == 0xffffu) continue;
+          E[sl & 0x7fffu] = apply_sign(v[i], sl);
+        }
+      }
+  }
+}
+
+// sum the W slots of every patch dof of one group; private dofs are plain stores, shared ones RED
+template <int NT, int W, bool PRIV, bool ACC>
+__device__ __forceinline__ void scatter_group(const int tid, const uint32_t n, const uint32_t *__restrict__ dof,
+                                              const typename EntryT<W>::type *__restrict__ ent, const double *E,
+                                              double *__restrict__ y) {
+  constexpr int UNR = 4;
+  for (uint32_t u0 = tid; u0 < n; u0 += UNR * NT) {
+    uint32_t m[UNR];
+    uint64_t w[UNR];
+#pragma unroll
+    for (int i = 0; i < UNR; i++) {
+      const uint32_t u = u0 + i * NT;
+      m[i] = u < n ? __ldg(dof + u) : MAP_ESS;
+      w[i] = u < n ? (uint64_t)__ldg(ent + u) : 0;
+    }
+#pragma unroll
+    for (int i = 0; i < UNR; i++) {
+      if (m[i] & MAP_ESS) continue;
+      double v = 0.0;
+#pragma unroll
+      for (int j = 0; j < W; j++) {
+        const uint32_t sl = (uint32_t)(w[i] >> (16 * j)) & 0xffffu;
+        if (W == 4 && j == 3 && sl == 0xffffu) continue;
+        const double t = apply_sign(E[sl & 0x7fffu], sl);
+        v = j == 0 ? t : v + t;
+      }
+      double *dst = y + (m[i] & MAP_IDX);
+      if (PRIV) *dst = ACC ? *dst + v : v;
+      else atomicAdd(dst, v);
     }
   }
-  __syncthreads();
-  // ---- element operator: component c of patch element el
+}
+
+template <int FE, int MINB, bool ACC>
+__global__ void __launch_bounds__(3 * FE, MINB)
+hex_patch_modal_p2_kernel(const PatchArgs a) {
+  extern __shared__ double E[];  // [54][FE + 1]
+  constexpr int NT = 3 * FE, ST = FE + 1;
+  const int tid = threadIdx.x;
+  const int64_t k = blockIdx.x;
+  // component c of patch element el; its geometry factors are fetched first (consumed after phase A)
   const int c = tid / FE, el = tid - c * FE;
+  const int c1 = c == 2 ? 0 : c + 1, c2 = c == 0 ? 2 : c - 1;
   const int64_t pos = k * FE + el;
   const bool ok = __ldg(a.perm + pos) >= 0;
-  double *Eown = E + (c * 18) * FE + el;
+  const double *g = a.edata + pos;
+  const int64_t np = a.n_pos;
+  double K11 = __ldg(g + sym6(c1, c1) * np), K10 = __ldg(g + sym6(c1, c) * np), K12 = __ldg(g + sym6(c1, c2) * np),
+         K22 = __ldg(g + sym6(c2, c2) * np), K20 = __ldg(g + sym6(c2, c) * np);
+  double M00 = __ldg(g + (6 + sym6(c, c)) * np), M01 = __ldg(g + (6 + sym6(c, c1)) * np), M02 = __ldg(g + (6 + sym6(c, c2)) * np);
+  const uint32_t *h = a.hdr + k * PatchHost::HDR;
+  const uint32_t nP1 = __ldg(h + 6), nP2 = __ldg(h + 7), nP4 = __ldg(h + 8), nS1 = __ldg(h + 9), nS2 = __ldg(h + 10), nS4 = __ldg(h + 11);
+  const uint32_t *dP1 = a.dof + __ldg(h), *dP2 = dP1 + nP1, *dP4 = dP2 + nP2, *dS1 = dP4 + nP4, *dS2 = dS1 + nS1, *dS4 = dS2 + nS2;
+  const uint16_t *eP1 = a.e16 + __ldg(h + 1), *eS1 = eP1 + nP1;
+  const uint32_t *eP2 = a.e32 + __ldg(h + 2), *eS2 = eP2 + nP2;
+  const uint64_t *eP4 = a.e64 + __ldg(h + 3), *eS4 = eP4 + nP4;
+  const uint32_t *ovf = a.ovf + __ldg(h + 4);
+  const uint32_t nov = __ldg(h + 5);
+  // ---- A: gather
+  gather_group<NT, 1>(tid, nP1, dP1, eP1, a.x, E);
+  gather_group<NT, 2>(tid, nP2, dP2, eP2, a.x, E);
+  gather_group<NT, 4>(tid, nP4, dP4, eP4, a.x, E);
+  gather_group<NT, 1>(tid, nS1, dS1, eS1, a.x, E);
+  gather_group<NT, 2>(tid, nS2, dS2, eS2, a.x, E);
+  gather_group<NT, 4>(tid, nS4, dS4, eS4, a.x, E);
+  for (uint32_t t = tid; t < nov; t += NT) {  // slots beyond four (unstructured meshes)
+    const uint32_t e = __ldg(ovf + t), m = __ldg(dP1 + (e >> 16));
+    const double v = (m & MAP_ESS) ? 0.0 : __ldg(a.x + (m & MAP_IDX));
+    E[e & 0x7fffu] = apply_sign(v, e);
+  }
+  __syncthreads();
+  // ---- element operator
+  double *Eown = E + (c * 18) * ST + el;
   double Am[18];
   if (ok) {
     double X[18];
 #pragma unroll
-    for (int t = 0; t < 18; t++) X[t] = Eown[t * FE];
+    for (int t = 0; t < 18; t++) X[t] = Eown[t * ST];
     modal_fwd(X, Am);
 #pragma unroll
-    for (int t = 0; t < 18; t++) Eown[t * FE] = Am[t];
+    for (int t = 0; t < 18; t++) Eown[t * ST] = Am[t];
   }
   __syncthreads();
   double Y[18];
   if (ok) {
-    const int c1 = c == 2 ? 0 : c + 1, c2 = c == 0 ? 2 : c - 1;
-    const double *E1 = E + (c1 * 18) * FE + el, *E2 = E + (c2 * 18) * FE + el;
+    const double *E1 = E + (c1 * 18) * ST + el, *E2 = E + (c2 * 18) * ST + el;
     double Bm[18], Cm[18];
     // owner frames: comp c+1 stores (m1, m2, m0), comp c+2 stores (m2, m0, m1)
 #pragma unroll
@@ -216,45 +302,36 @@ hex_patch_modal_p2_kernel(const PatchArgs a) {
 #pragma unroll
       for (int m1 = 0; m1 < 2; m1++)
 #pragma unroll
-        for (int m0 = 0; m0 < 3; m0++) Bm[IB(m0, m1, m2)] = E1[(m1 + 2 * (m2 + 3 * m0)) * FE];
+        for (int m0 = 0; m0 < 3; m0++) Bm[IB(m0, m1, m2)] = E1[(m1 + 2 * (m2 + 3 * m0)) * ST];
 #pragma unroll
     for (int m2 = 0; m2 < 2; m2++)
 #pragma unroll
       for (int m1 = 0; m1 < 3; m1++)
 #pragma unroll
-        for (int m0 = 0; m0 < 3; m0++) Cm[IC(m0, m1, m2)] = E2[(m2 + 2 * (m0 + 3 * m1)) * FE];
-    const double *g = a.edata + pos;
-    const int64_t np = a.n_pos;
+        for (int m0 = 0; m0 < 3; m0++) Cm[IC(m0, m1, m2)] = E2[(m2 + 2 * (m0 + 3 * m1)) * ST];
     const double sc = a.scale;
-    const double K11 = sc * __ldg(g + sym6(c1, c1) * np), K10 = sc * __ldg(g + sym6(c1, c) * np),
-                 K12 = sc * __ldg(g + sym6(c1, c2) * np), K22 = sc * __ldg(g + sym6(c2, c2) * np),
-                 K20 = sc * __ldg(g + sym6(c2, c) * np), K21 = K12;
-    const double M00 = sc * __ldg(g + (6 + sym6(c, c)) * np), M01 = sc * __ldg(g + (6 + sym6(c, c1)) * np),
-                 M02 = sc * __ldg(g + (6 + sym6(c, c2)) * np);
+    K11 *= sc; K10 *= sc; K12 *= sc; K22 *= sc; K20 *= sc; M00 *= sc; M01 *= sc; M02 *= sc;
     double Yh[18];
-    modal_op(Am, Bm, Cm, M00, M01, M02, K11, K10, K12, K22, K20, K21, Yh);
+    modal_op(Am, Bm, Cm, M00, M01, M02, K11, K10, K12, K22, K20, K12, Yh);
     modal_bwd(Yh, Y);
   }
   __syncthreads();  // everyone has read the modal coefficients
   if (ok) {
 #pragma unroll
-    for (int t = 0; t < 18; t++) Eown[t * FE] = Y[t];
+    for (int t = 0; t < 18; t++) Eown[t * ST] = Y[t];
   }
   __syncthreads();
-  // ---- C: sum the slots of every patch dof; private dofs are plain stores, shared ones RED
-  for (uint32_t u = tid; u < U; u += NT) {
-    const uint32_t m = __ldg(pdof + u);
+  // ---- C: scatter
+  scatter_group<NT, 1, true, ACC>(tid, nP1, dP1, eP1, E, a.y);
+  scatter_group<NT, 2, true, ACC>(tid, nP2, dP2, eP2, E, a.y);
+  scatter_group<NT, 4, true, ACC>(tid, nP4, dP4, eP4, E, a.y);
+  scatter_group<NT, 1, false, ACC>(tid, nS1, dS1, eS1, E, a.y);
+  scatter_group<NT, 2, false, ACC>(tid, nS2, dS2, eS2, E, a.y);
+  scatter_group<NT, 4, false, ACC>(tid, nS4, dS4, eS4, E, a.y);
+  for (uint32_t t = tid; t < nov; t += NT) {
+    const uint32_t e = __ldg(ovf + t), m = __ldg(dP1 + (e >> 16));
     if (m & MAP_ESS) continue;
-    const int s0 = __ldg(pst + u), s1 = __ldg(pst + u + 1);
-    double v = 0.0;
-    for (int s = s0; s < s1; s++) {
-      const uint32_t sl = __ldg(psl + s);
-      const double t = E[sl & 0x7fffu];
-      v += (sl & 0x8000u) ? -t : t;
-    }
-    double *dst = a.y + (m & MAP_IDX);
-    if (u < npriv) *dst = ACC ? *dst + v : v;
-    else atomicAdd(dst, v);
+    atomicAdd(a.y + (m & MAP_IDX), apply_sign(E[e & 0x7fffu], e));
   }
 }
 
@@ -367,12 +444,12 @@ int hex_patch_build(hcurl_space *sp, const double *elem_xyz, const int32_t *elem
     }
   }
   PatchHost H;
-  if (build_patches(nd, ne, FE, sp->n_ext(), cen.data(), code.data(), H)) return 1;
+  if (build_patches(nd, ne, FE, FE + 1, sp->n_ext(), cen.data(), code.data(), H)) return 1;
   HC_CUDA(cudaSetDevice(sp->ctx->device));
   PatchSet &P = sp->patch;
-  P.FE = FE; P.n_patch = H.n_patch; P.n_pd = (int64_t)H.dof.size();
-  if (upload(P.d_perm, H.perm) || upload(P.d_off, H.off) || upload(P.d_npriv, H.npriv) || upload(P.d_dof, H.dof) ||
-      upload(P.d_start, H.start) || upload(P.d_slots, H.slots))
+  P.FE = FE; P.stride = H.stride; P.n_patch = H.n_patch; P.n_pd = (int64_t)H.dof.size();
+  if (upload(P.d_perm, H.perm) || upload(P.d_hdr, H.hdr) || upload(P.d_dof, H.dof) || upload(P.d_e16, H.e16) ||
+      upload(P.d_e32, H.e32) || upload(P.d_e64, H.e64) || upload(P.d_ovf, H.ovf))
     return 1;
   sp->has_patches = true;
   return 0;
@@ -380,7 +457,7 @@ int hex_patch_build(hcurl_space *sp, const double *elem_xyz, const int32_t *elem
 
 void hex_patch_free(hcurl_space *sp) {
   PatchSet &P = sp->patch;
-  cudaFree(P.d_perm); cudaFree(P.d_off); cudaFree(P.d_npriv); cudaFree(P.d_dof); cudaFree(P.d_start); cudaFree(P.d_slots);
+  cudaFree(P.d_perm); cudaFree(P.d_hdr); cudaFree(P.d_dof); cudaFree(P.d_e16); cudaFree(P.d_e32); cudaFree(P.d_e64); cudaFree(P.d_ovf);
   cudaFree(sp->d_xyzP);
   P = PatchSet();
   sp->has_patches = false;
@@ -397,11 +474,11 @@ bool hex_patch_eligible(const hcurl_op *op) {
   return sp->all_affine;
 }
 
-template <int FE>
+template <int FE, int MINB>
 static int launch_fe(const PatchArgs &a, int64_t n_patch, bool acc, cudaStream_t st) {
-  const size_t smem = sizeof(double) * 54 * FE;
-  auto k0 = hex_patch_modal_p2_kernel<FE, false>;
-  auto k1 = hex_patch_modal_p2_kernel<FE, true>;
+  const size_t smem = sizeof(double) * 54 * (FE + 1);
+  auto k0 = hex_patch_modal_p2_kernel<FE, MINB, false>;
+  auto k1 = hex_patch_modal_p2_kernel<FE, MINB, true>;
   static bool attr = false;
   if (!attr) {
     HC_CUDA(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -427,13 +504,13 @@ int hex_patch_launch(hcurl_op *op, bool constrained, const double *d_x, double *
     op->edataP_valid = true;
   }
   PatchArgs a;
-  a.n_elem = sp->n_elem; a.n_pos = n_pos; a.perm = P.d_perm; a.off = P.d_off; a.npriv = P.d_npriv;
+  a.n_pos = n_pos; a.perm = P.d_perm; a.hdr = P.d_hdr;
   a.dof = (constrained && op->d_pdof_ess) ? op->d_pdof_ess : P.d_dof;
-  a.start = P.d_start; a.slots = P.d_slots; a.edata = op->d_edataP; a.x = d_x; a.y = d_y; a.scale = scale;
+  a.e16 = P.d_e16; a.e32 = P.d_e32; a.e64 = P.d_e64; a.ovf = P.d_ovf; a.edata = op->d_edataP; a.x = d_x; a.y = d_y; a.scale = scale;
   int rc = 1;
-  if (P.FE == 32) rc = launch_fe<32>(a, P.n_patch, accumulate, ctx->stream);
-  else if (P.FE == 64) rc = launch_fe<64>(a, P.n_patch, accumulate, ctx->stream);
-  else if (P.FE == 128) rc = launch_fe<128>(a, P.n_patch, accumulate, ctx->stream);
+  if (P.FE == 32) rc = launch_fe<32, 6>(a, P.n_patch, accumulate, ctx->stream);
+  else if (P.FE == 64) rc = launch_fe<64, 3>(a, P.n_patch, accumulate, ctx->stream);
+  else if (P.FE == 128) rc = launch_fe<128, 1>(a, P.n_patch, accumulate, ctx->stream);
   if (rc) return rc;
   HC_CUDA(cudaGetLastError());
   ctx->launches++;

@@ -64,17 +64,19 @@ void tri_face_transform(int p, const int32_t *local_verts, const int32_t *base_v
 // ---------------------------------------------------------------- patches ----
 // Host result of build_patches() (patch.cpp); uploaded into a PatchSet by hex_patch.cu.
 struct PatchHost {
-  int FE = 0, nd = 0;
+  int FE = 0, stride = 0, nd = 0;
   int64_t n_patch = 0;
-  std::vector<int32_t> perm;     // [n_patch*FE] element at each patch position, -1 = padding
-  std::vector<uint32_t> off;     // [n_patch+1] first patch dof
-  std::vector<uint32_t> npriv;   // [n_patch] number of private dofs (listed first)
-  std::vector<uint32_t> dof;     // [n_pd] extended-vector index
-  std::vector<uint16_t> start;   // [n_pd + n_patch] slot-list offsets, U+1 per patch
-  std::vector<uint16_t> slots;   // [n_patch*FE*nd] E-vector slot | 0x8000 sign flip
+  static constexpr int HDR = 12;  // words per patch header
+  std::vector<int32_t> perm;      // [n_patch*FE] element at each patch position, -1 = padding
+  std::vector<uint32_t> hdr;      // [n_patch][HDR]: dof_off, e16_off, e32_off, e64_off, ovf_off, n_ovf, nP1, nP2, nP4, nS1, nS2, nS4
+  std::vector<uint32_t> dof;      // extended-vector index of every patch dof (groups concatenated)
+  std::vector<uint16_t> e16;      // 1-slot dofs: E-vector index | 0x8000 sign flip   (per patch: private then shared)
+  std::vector<uint32_t> e32;      // 2-slot dofs: two 16-bit entries
+  std::vector<uint64_t> e64;      // 3..4-slot dofs: four 16-bit entries, 0xffff = unused
+  std::vector<uint32_t> ovf;      // (patch dof u << 16) | entry, for slots beyond four
 };
-int build_patches(int nd, int64_t n_elem, int FE, int64_t n_ext, const double *centroid, const uint32_t *slot_code,
-                  PatchHost &out);
+int build_patches(int nd, int64_t n_elem, int FE, int stride, int64_t n_ext, const double *centroid,
+                  const uint32_t *slot_code, PatchHost &out);
 // slot s of the rotated per-component layout (hex_patch.cu) -> standard tensor index
 int hex_rot_slot_to_tensor(int p, int slot);
 
@@ -82,8 +84,10 @@ struct PatchSet {  // device copy
   int FE = 0;
   int64_t n_patch = 0, n_pd = 0;
   int32_t *d_perm = nullptr;
-  uint32_t *d_off = nullptr, *d_npriv = nullptr, *d_dof = nullptr;
-  uint16_t *d_start = nullptr, *d_slots = nullptr;
+  int stride = 0;
+  uint32_t *d_hdr = nullptr, *d_dof = nullptr, *d_e32 = nullptr, *d_ovf = nullptr;
+  uint16_t *d_e16 = nullptr;
+  uint64_t *d_e64 = nullptr;
 };
 
 // ----------------------------------------------------------------- NCCL ----

@@ -14,11 +14,17 @@
 //   * after the element kernels, every patch dof sums its slots; dofs whose elements all lie
 //     in this patch ("private") are written with plain stores, only patch-boundary dofs use
 //     RED atomics.
-// This file builds, for any mesh, the per-patch lists
-//   dof[u]   : global (extended-vector) index | MAP_NEG never set here | flags
-//   start[u] : first entry of u in slots[] (relative to the patch), U+1 entries
-//   slots[s] : E-vector slot (bits 0..14) | sign flip (bit 15), grouped by dof
-// with private dofs first, each class sorted by global index.
+// This file builds, for any mesh, the per-patch lists.  The dofs of a patch are split into six
+// groups -- (private | shared) x (1 | 2 | 3..4 element slots) -- each sorted by global index so
+// that consecutive lanes touch consecutive addresses; a group's slot entries have a fixed width
+// (16 / 32 / 64 bits), so the loads of different dofs are independent (a CSR start/slot chain
+// made the kernel latency-bound) and no lane unpacks unused slots:
+//   hdr[k] : 12 words: offsets of patch k in dof/e16/e32/e64/ovf, overflow count, 6 group sizes
+//   dof[u] : global (extended-vector) index of patch dof u (groups concatenated)
+//   e16/e32/e64 : per dof 1 / 2 / 4 entries of 16 bits: E-vector index (bits 0..14) | sign flip
+//            (bit 15), 0xffff = unused (a 3-slot dof in the 64-bit group)
+//   ovf[]  : (u << 16 | entry) for the slots beyond four (edge valence > 4 inside one patch, only
+//            on unstructured meshes); such dofs are classed shared and their overflow is RED-added.
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -62,11 +68,12 @@ static void parallel_for(int64_t n, F f) {
 }
 
 // centroid[e*3+d]; slot_dof[e*nd + s] = extended dof index of element slot s, slot_neg = sign flip
-int build_patches(int nd, int64_t n_elem, int FE, int64_t n_ext, const double *centroid, const uint32_t *slot_code,
-                  PatchHost &out) {
-  if ((int64_t)FE * nd > 32767) { set_error("patch too large for the 15-bit slot encoding"); return 1; }
+int build_patches(int nd, int64_t n_elem, int FE, int stride, int64_t n_ext, const double *centroid,
+                  const uint32_t *slot_code, PatchHost &out) {
+  if (stride < FE) { set_error("slot stride must be >= elements per patch"); return 1; }
+  if ((int64_t)stride * nd > 32767) { set_error("patch too large for the 15-bit slot encoding"); return 1; }
   const int64_t n_patch = (n_elem + FE - 1) / FE;
-  out.FE = FE; out.nd = nd; out.n_patch = n_patch;
+  out.FE = FE; out.stride = stride; out.nd = nd; out.n_patch = n_patch;
   // ---- Morton order of the centroids
   double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
   for (int64_t e = 0; e < n_elem; e++)
@@ -111,7 +118,7 @@ int build_patches(int nd, int64_t n_elem, int FE, int64_t n_ext, const double *c
       if (e < 0) continue;
       for (int s = 0; s < nd; s++) {
         const uint32_t code = slot_code[(size_t)e * nd + s];
-        const uint16_t sl = (uint16_t)(s * FE + j) | ((code & MAP_NEG) ? 0x8000u : 0u);
+        const uint16_t sl = (uint16_t)(s * stride + j) | ((code & MAP_NEG) ? 0x8000u : 0u);
         ent.push_back({code & MAP_IDX, sl});
       }
     }
@@ -126,43 +133,75 @@ int build_patches(int nd, int64_t n_elem, int FE, int64_t n_ext, const double *c
     }
     us.push_back((uint16_t)ent.size());
   });
-  // ---- which dofs are private to one patch
+  // ---- which dofs are private to one patch; dofs with more than four slots in a patch are
+  // treated as shared everywhere (their overflow slots are RED-added separately)
   std::vector<int32_t> owner((size_t)n_ext, -1);
   std::vector<uint8_t> multi((size_t)n_ext, 0);
-  for (int64_t k = 0; k < n_patch; k++)
-    for (uint32_t d : udof[(size_t)k]) {
+  for (int64_t k = 0; k < n_patch; k++) {
+    const auto &ud = udof[(size_t)k];
+    const auto &us = ustart[(size_t)k];
+    for (size_t i = 0; i < ud.size(); i++) {
+      const uint32_t d = ud[i];
       if (owner[d] < 0) owner[d] = (int32_t)k;
       else if (owner[d] != (int32_t)k) multi[d] = 1;
+      if (us[i + 1] - us[i] > 4) multi[d] = 1;
     }
+  }
   owner.clear(); owner.shrink_to_fit();
-  // ---- offsets, final arrays (private first, each class ascending)
-  out.off.assign((size_t)n_patch + 1, 0);
-  for (int64_t k = 0; k < n_patch; k++) out.off[(size_t)k + 1] = out.off[(size_t)k] + (uint32_t)udof[(size_t)k].size();
-  const size_t n_pd = out.off[(size_t)n_patch];
-  out.npriv.assign((size_t)n_patch, 0);
-  out.dof.assign(n_pd, 0);
-  out.start.assign(n_pd + (size_t)n_patch, 0);
-  out.slots.assign((size_t)n_patch * per, 0);
+  // ---- group the patch dofs: (private | shared) x (1 | 2 | 3-4 slots), ascending inside a group
+  auto group_of = [&](uint32_t d, int nslot) { return (multi[d] ? 3 : 0) + (nslot <= 1 ? 0 : (nslot == 2 ? 1 : 2)); };
+  out.hdr.assign((size_t)n_patch * PatchHost::HDR, 0);
+  uint32_t o_dof = 0, o16 = 0, o32 = 0, o64 = 0, o_ovf = 0;
+  for (int64_t k = 0; k < n_patch; k++) {
+    const auto &ud = udof[(size_t)k];
+    const auto &us = ustart[(size_t)k];
+    uint32_t *h = out.hdr.data() + (size_t)k * PatchHost::HDR;
+    h[0] = o_dof; h[1] = o16; h[2] = o32; h[3] = o64; h[4] = o_ovf;
+    for (size_t i = 0; i < ud.size(); i++) {
+      const int ns = us[i + 1] - us[i];
+      h[6 + group_of(ud[i], ns)]++;
+      if (ns > 4) h[5] += ns - 4;
+    }
+    o_dof += (uint32_t)ud.size();
+    o16 += h[6] + h[9]; o32 += h[7] + h[10]; o64 += h[8] + h[11]; o_ovf += h[5];
+  }
+  out.dof.assign(o_dof, 0);
+  out.e16.assign(o16, 0);
+  out.e32.assign(o32, 0);
+  out.e64.assign(o64, 0);
+  out.ovf.assign(o_ovf, 0);
   parallel_for(n_patch, [&](int64_t k) {
     const auto &ud = udof[(size_t)k];
     const auto &us = ustart[(size_t)k];
     const auto &sl = uslots[(size_t)k];
-    uint32_t *pd = out.dof.data() + out.off[(size_t)k];
-    uint16_t *ps = out.start.data() + out.off[(size_t)k] + k;
-    uint16_t *pl = out.slots.data() + (size_t)k * per;
-    uint32_t u = 0;
-    uint16_t pos = 0;
-    for (int pass = 0; pass < 2; pass++) {
-      for (size_t i = 0; i < ud.size(); i++) {
-        if ((multi[ud[i]] != 0) != (pass == 1)) continue;
-        pd[u] = ud[i];
-        ps[u] = pos;
-        for (uint16_t s = us[i]; s < us[i + 1]; s++) pl[pos++] = sl[s];
-        u++;
+    const uint32_t *h = out.hdr.data() + (size_t)k * PatchHost::HDR;
+    uint32_t *pd = out.dof.data() + h[0];
+    uint16_t *p16 = out.e16.data() + h[1];
+    uint32_t *p32 = out.e32.data() + h[2];
+    uint64_t *p64 = out.e64.data() + h[3];
+    uint32_t *po = out.ovf.data() + h[4];
+    // first patch-local index of each group, entry cursor per width
+    uint32_t gstart[6], u = 0;
+    for (int g = 0; g < 6; g++) { gstart[g] = u; u += h[6 + g]; }
+    uint32_t cur[6];
+    for (int g = 0; g < 6; g++) cur[g] = gstart[g];
+    uint32_t c16[2] = {0, h[6]}, c32[2] = {0, h[7]}, c64[2] = {0, h[8]};
+    for (size_t i = 0; i < ud.size(); i++) {
+      const int ns = us[i + 1] - us[i];
+      const int g = group_of(ud[i], ns), cls = g / 3, w = g % 3;
+      const uint32_t ul = cur[g]++;
+      pd[ul] = ud[i];
+      if (w == 0) p16[c16[cls]++] = sl[us[i]];
+      else if (w == 1) p32[c32[cls]++] = (uint32_t)sl[us[i]] | ((uint32_t)sl[us[i] + 1] << 16);
+      else {
+        uint64_t v = ~0ULL;
+        for (int j = 0; j < ns; j++) {
+          if (j < 4) v = (v & ~(0xffffULL << (16 * j))) | ((uint64_t)sl[us[i] + j] << (16 * j));
+          else *po++ = (ul << 16) | sl[us[i] + j];
+        }
+        p64[c64[cls]++] = v;
       }
-      if (pass == 0) out.npriv[(size_t)k] = u;
     }
-    ps[u] = pos;
   });
   return 0;
 }
@@ -174,27 +213,33 @@ int build_patches(int nd, int64_t n_elem, int FE, int64_t n_ext, const double *c
 struct hcurl_host_patches { hcurl::PatchHost h; };
 
 extern "C" {
-hcurl_host_patches *hcurl_host_patches_create(int nd, int64_t n_elem, int elems_per_patch, int64_t n_dof,
+hcurl_host_patches *hcurl_host_patches_create(int nd, int64_t n_elem, int elems_per_patch, int slot_stride, int64_t n_dof,
                                               const double *centroid, const uint32_t *slot_code) {
   if (nd <= 0 || n_elem <= 0 || !centroid || !slot_code) { hcurl::set_error("hcurl_host_patches_create: bad arguments"); return nullptr; }
   for (int64_t i = 0; i < n_elem * nd; i++)
     if ((int64_t)(slot_code[i] & hcurl::MAP_IDX) >= n_dof) { hcurl::set_error("hcurl_host_patches_create: dof index out of range"); return nullptr; }
   hcurl_host_patches *p = new hcurl_host_patches;
-  if (hcurl::build_patches(nd, n_elem, elems_per_patch, n_dof, centroid, slot_code, p->h)) { delete p; return nullptr; }
+  if (hcurl::build_patches(nd, n_elem, elems_per_patch, slot_stride, n_dof, centroid, slot_code, p->h)) { delete p; return nullptr; }
   return p;
 }
 void hcurl_host_patches_destroy(hcurl_host_patches *p) { delete p; }
 int64_t hcurl_host_patches_count(const hcurl_host_patches *p) { return p->h.n_patch; }
-int64_t hcurl_host_patches_ndof_entries(const hcurl_host_patches *p) { return (int64_t)p->h.dof.size(); }
-int hcurl_host_patches_copy(const hcurl_host_patches *p, int32_t *perm, uint32_t *off, uint32_t *npriv, uint32_t *dof,
-                            uint16_t *start, uint16_t *slots) {
+/* sizes[5] = entries of dof, e16, e32, e64, ovf */
+void hcurl_host_patches_sizes(const hcurl_host_patches *p, int64_t *sizes) {
+  const hcurl::PatchHost &h = p->h;
+  sizes[0] = (int64_t)h.dof.size(); sizes[1] = (int64_t)h.e16.size(); sizes[2] = (int64_t)h.e32.size();
+  sizes[3] = (int64_t)h.e64.size(); sizes[4] = (int64_t)h.ovf.size();
+}
+int hcurl_host_patches_copy(const hcurl_host_patches *p, int32_t *perm, uint32_t *hdr, uint32_t *dof, uint16_t *e16,
+                            uint32_t *e32, uint64_t *e64, uint32_t *ovf) {
   const hcurl::PatchHost &h = p->h;
   if (perm) memcpy(perm, h.perm.data(), sizeof(int32_t) * h.perm.size());
-  if (off) memcpy(off, h.off.data(), sizeof(uint32_t) * h.off.size());
-  if (npriv) memcpy(npriv, h.npriv.data(), sizeof(uint32_t) * h.npriv.size());
+  if (hdr) memcpy(hdr, h.hdr.data(), sizeof(uint32_t) * h.hdr.size());
   if (dof) memcpy(dof, h.dof.data(), sizeof(uint32_t) * h.dof.size());
-  if (start) memcpy(start, h.start.data(), sizeof(uint16_t) * h.start.size());
-  if (slots) memcpy(slots, h.slots.data(), sizeof(uint16_t) * h.slots.size());
+  if (e16) memcpy(e16, h.e16.data(), sizeof(uint16_t) * h.e16.size());
+  if (e32) memcpy(e32, h.e32.data(), sizeof(uint32_t) * h.e32.size());
+  if (e64) memcpy(e64, h.e64.data(), sizeof(uint64_t) * h.e64.size());
+  if (ovf) memcpy(ovf, h.ovf.data(), sizeof(uint32_t) * h.ovf.size());
   return 0;
 }
 }

@@ -32,3 +32,22 @@ def coefficients(mesh, seed=3):
 
 def rel_err(a, b):
     return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+def star_mesh(layers=3, cls=None):
+    """Six 60-degree rhombic prisms around a central edge (all elements affine, the central
+    edges have valence 6 > ELL width), stacked in z."""
+    ang = np.pi / 3 * np.arange(6)
+    ring1 = np.stack([np.cos(ang), np.sin(ang)], 1)
+    ring2 = ring1 + np.roll(ring1, -1, axis=0)
+    pts2 = np.concatenate([[[0.0, 0.0]], ring1, ring2])
+    nl = len(pts2)
+    verts = np.concatenate([np.column_stack([pts2, np.full(nl, float(z))]) for z in range(layers + 1)])
+    elems = []
+    for z in range(layers):
+        for k in range(6):
+            q = [0, 1 + k, 7 + k, 1 + (k + 1) % 6]  # counter-clockwise rhombus
+            elems.append([z * nl + v for v in q] + [(z + 1) * nl + v for v in q])
+    return (cls or fespace.Mesh)("hex", verts, np.array(elems))
+
+

@@ -7,7 +7,7 @@ from hephaestus_b200 import _lib as L
 from hephaestus_b200 import operators
 from oracle import assemble as oa
 
-from helpers import coefficients, make_pair, rel_err
+from helpers import coefficients, make_pair, rel_err, star_mesh
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-12
@@ -239,3 +239,25 @@ def test_hex_p2_patch_kernel_patch_sizes(ctx, fe, monkeypatch):
         op.Mult(dx, dy)
     ctx.synchronize()
     assert rel_err(dy.download(), y_ref) < TOL
+
+
+@pytest.mark.parametrize("which", [1, 2, 3])
+def test_hex_p2_unstructured_affine_valence6(ctx, which, monkeypatch):
+    """Unstructured affine hex mesh (six rhombic prisms around each central edge): patch dofs with
+    more than four element slots take the overflow path of the patch kernel."""
+    monkeypatch.setenv("HCURL_PATCH_FE", "32")
+    from hephaestus_b200 import fespace
+    from oracle import mesh as om, space as osp
+    m, mo = star_mesh(6), star_mesh(6, cls=om.Mesh)
+    sp, so = fespace.NDSpace(m, 2), osp.NDSpace(mo, 2)
+    assert np.array_equal(sp.signed_elem_dofs(), so.signed_elem_dofs())
+    a, b = coefficients(m)
+    gsp = operators.GpuNDSpace(ctx, sp)
+    op = operators.HephGpuOperator(ctx, gsp, 3)
+    op.SetKernel(which)
+    op.SetCoefficients(a, b)
+    essd = sp.boundary_dofs(lambda c: c[:, 2] < 1e-9)
+    op.SetEssentialTrueDofs(essd)
+    x = np.random.default_rng(3).standard_normal(sp.ndof)
+    A = oa.assemble(so, a, b, q_override=3)
+    assert rel_err(op.Mult(x), oa.constrained_apply(A, essd, x)) < TOL

@@ -10,30 +10,55 @@ import pytest
 from hephaestus_b200 import _lib as L
 from hephaestus_b200 import fespace
 
+from helpers import star_mesh
+
 NEG = 0x80000000
 
 
-def build(space, fe, slot_code, centroid):
+def build(space, fe, slot_code, centroid, stride=None):
     lib = L.lib()
     ne, nd = slot_code.shape
-    h = L.check_ptr(lib.hcurl_host_patches_create(nd, ne, fe, space.ndof, L.ptr(centroid), L.ptr(slot_code)), "patches")
+    stride = stride or fe + 1
+    h = L.check_ptr(lib.hcurl_host_patches_create(nd, ne, fe, stride, space.ndof, L.ptr(centroid), L.ptr(slot_code)), "patches")
     npatch = lib.hcurl_host_patches_count(h)
-    npd = lib.hcurl_host_patches_ndof_entries(h)
+    sizes = np.zeros(5, np.int64)
+    lib.hcurl_host_patches_sizes(h, L.ptr(sizes))
     perm = np.zeros(npatch * fe, np.int32)
-    off = np.zeros(npatch + 1, np.uint32)
-    npriv = np.zeros(npatch, np.uint32)
-    dof = np.zeros(npd, np.uint32)
-    start = np.zeros(npd + npatch, np.uint16)
-    slots = np.zeros(npatch * fe * nd, np.uint16)
-    L.check(lib.hcurl_host_patches_copy(h, L.ptr(perm), L.ptr(off), L.ptr(npriv), L.ptr(dof), L.ptr(start), L.ptr(slots)), "copy")
+    hdr = np.zeros((npatch, 12), np.uint32)
+    dof = np.zeros(sizes[0], np.uint32)
+    e16 = np.zeros(max(sizes[1], 1), np.uint16)
+    e32 = np.zeros(max(sizes[2], 1), np.uint32)
+    e64 = np.zeros(max(sizes[3], 1), np.uint64)
+    ovf = np.zeros(max(sizes[4], 1), np.uint32)
+    L.check(lib.hcurl_host_patches_copy(h, L.ptr(perm), L.ptr(hdr), L.ptr(dof), L.ptr(e16), L.ptr(e32), L.ptr(e64), L.ptr(ovf)), "copy")
     lib.hcurl_host_patches_destroy(h)
-    return perm, off, npriv, dof, start, slots
+    return perm, hdr.astype(np.int64), dof, e16, e32, e64, ovf[:sizes[4]], stride
+
+
+def patch_groups(k, hdr, dof, e16, e32, e64):
+    """[(private?, dof ids, entries (n, W))] of the six groups of patch k, in kernel order."""
+    o_dof, o16, o32, o64 = hdr[k, :4]
+    n = hdr[k, 6:12]
+    sh = 16 * np.arange(4, dtype=np.uint64)
+    ent = {1: e16[o16:o16 + n[0] + n[3]].astype(np.int64)[:, None],
+           2: (e32[o32:o32 + n[1] + n[4], None].astype(np.uint64) >> sh[None, :2]).astype(np.int64) & 0xFFFF,
+           4: (e64[o64:o64 + n[2] + n[5], None] >> sh[None]).astype(np.int64) & 0xFFFF}
+    out, u = [], 0
+    cur = {1: 0, 2: 0, 4: 0}
+    for gi, (priv, w) in enumerate([(True, 1), (True, 2), (True, 4), (False, 1), (False, 2), (False, 4)]):
+        out.append((priv, u, dof[o_dof + u:o_dof + u + n[gi]].astype(np.int64), ent[w][cur[w]:cur[w] + n[gi]]))
+        u += n[gi]
+        cur[w] += n[gi]
+    return out, u
 
 
 def make(kind, n, p, perturb):
-    m = fespace.cartesian_hex_mesh(*n)
-    if perturb:
-        m = fespace.perturb_interior(m)
+    if kind == "star":
+        m = star_mesh(*n)
+    else:
+        m = fespace.cartesian_hex_mesh(*n)
+        if perturb:
+            m = fespace.perturb_interior(m)
     if kind == "tet":
         m = fespace.hex_to_tets(m)
     sp = fespace.NDSpace(m, p)
@@ -45,14 +70,19 @@ def make(kind, n, p, perturb):
 
 
 @pytest.mark.parametrize("kind,n,p,fe", [("hex", (4, 4, 4), 2, 64), ("hex", (5, 3, 7), 2, 32), ("hex", (8, 8, 4), 2, 128),
-                                         ("hex", (3, 3, 3), 1, 32), ("hex", (3, 2, 2), 3, 32), ("tet", (3, 3, 2), 2, 64)])
+                                         ("hex", (3, 3, 3), 1, 32), ("hex", (3, 2, 2), 3, 32), ("tet", (3, 3, 2), 2, 64),
+                                         ("star", (5,), 2, 32), ("star", (2,), 1, 64)])
 @pytest.mark.parametrize("perturb", [False, True])
 def test_patch_lists_reproduce_gather_and_scatter(kind, n, p, fe, perturb):
     m, sp, code, cen, idx, sgn = make(kind, n, p, perturb)
     ne, nd = code.shape
-    perm, off, npriv, dof, start, slots = build(sp, fe, code, cen)
-    npatch = len(npriv)
+    perm, hdr, dof, e16, e32, e64, ovf, st = build(sp, fe, code, cen)
+    npatch = len(hdr)
     assert npatch == (ne + fe - 1) // fe
+    if kind in ("star", "tet"):
+        assert len(ovf) > 0  # these meshes have dofs with more than four slots in a patch
+    elif kind == "hex":
+        assert len(ovf) == 0
     # perm is a permutation of the elements (+ padding)
     real = perm[perm >= 0]
     assert np.array_equal(np.sort(real), np.arange(ne))
@@ -64,38 +94,6 @@ def test_patch_lists_reproduce_gather_and_scatter(kind, n, p, fe, perturb):
     np.add.at(y_ref, idx.ravel(), (sgn * ye).ravel())
     y = np.zeros(sp.ndof)
     touched = np.zeros(sp.ndof, np.int64)
-    for k in range(npatch):
-        o, U = int(off[k]), int(off[k + 1] - off[k])
-        st = start[o + k:o + k + U + 1].astype(np.int64)
-        sl = slots[k * fe * nd:(k + 1) * fe * nd]
-        pd = dof[o:o + U].astype(np.int64)
-        assert st[0] == 0 and np.all(np.diff(st) >= 1)
-        el = perm[k * fe:(k + 1) * fe]
-        n_real = int((el >= 0).sum())
-        assert st[-1] == n_real * nd
-        # classes sorted ascending, private first
-        assert np.all(np.diff(pd[:npriv[k]]) > 0) and np.all(np.diff(pd[npriv[k]:]) > 0)
-        E = np.full(nd * fe, np.nan)
-        Ey = np.zeros(nd * fe)
-        for j in range(n_real):
-            Ey[np.arange(nd) * fe + j] = ye[el[j]]
-        for u in range(U):
-            ent = sl[st[u]:st[u + 1]].astype(np.int64)
-            pos, neg = ent & 0x7FFF, (ent & 0x8000) != 0
-            E[pos] = np.where(neg, -x[pd[u]], x[pd[u]])
-            v = np.sum(np.where(neg, -Ey[pos], Ey[pos]))
-            if u < npriv[k]:
-                assert touched[pd[u]] == 0
-                y[pd[u]] = v
-            else:
-                y[pd[u]] += v
-            touched[pd[u]] += 1
-        for j in range(n_real):
-            xe = E[np.arange(nd) * fe + j]
-            assert np.array_equal(xe, sgn[el[j]] * x[idx[el[j]]])
-    assert np.all(touched >= 1)
-    np.testing.assert_allclose(y, y_ref, rtol=0, atol=1e-13)
-    # every dof listed as private really belongs to one patch only
     elem_patch = np.empty(ne, np.int64)
     elem_patch[perm[perm >= 0]] = np.nonzero(perm >= 0)[0] // fe
     pmin = np.full(sp.ndof, 1 << 40)
@@ -103,31 +101,72 @@ def test_patch_lists_reproduce_gather_and_scatter(kind, n, p, fe, perturb):
     np.minimum.at(pmin, idx.ravel(), np.repeat(elem_patch, nd))
     np.maximum.at(pmax, idx.ravel(), np.repeat(elem_patch, nd))
     for k in range(npatch):
-        o = int(off[k])
-        pd = dof[o:o + int(off[k + 1] - off[k])].astype(np.int64)
-        assert np.all(pmin[pd[:npriv[k]]] == pmax[pd[:npriv[k]]])
-        assert np.all(pmin[pd[npriv[k]:]] != pmax[pd[npriv[k]:]])
+        groups, U = patch_groups(k, hdr, dof, e16, e32, e64)
+        ov = ovf[hdr[k, 4]:hdr[k, 4] + hdr[k, 5]].astype(np.int64)
+        pd_all = dof[hdr[k, 0]:hdr[k, 0] + U].astype(np.int64)
+        el = perm[k * fe:(k + 1) * fe]
+        n_real = int((el >= 0).sum())
+        E = np.full(nd * st, np.nan)
+        Ey = np.zeros(nd * st)
+        for j in range(n_real):
+            Ey[np.arange(nd) * st + j] = ye[el[j]]
+        n_slots = 0
+        for priv, u0, pd, ent in groups:
+            assert np.all(np.diff(pd) > 0)                     # ascending inside a group
+            W = ent.shape[1]
+            used = ent != 0xFFFF
+            if W < 4:
+                assert used.all()
+            else:
+                assert used[:, :3].all()                         # only the 4th entry may be unused
+            n_slots += int(used.sum())
+            if priv:
+                assert np.all(pmin[pd] == pmax[pd]) and np.all(touched[pd] == 0)
+            elif kind == "hex":
+                assert np.all(pmin[pd] != pmax[pd])
+            for u in range(len(pd)):
+                e = ent[u][used[u]]
+                pos, neg = e & 0x7FFF, (e & 0x8000) != 0
+                E[pos] = np.where(neg, -x[pd[u]], x[pd[u]])
+                v = np.sum(np.where(neg, -Ey[pos], Ey[pos]))
+                if priv:
+                    y[pd[u]] = v
+                else:
+                    y[pd[u]] += v
+                touched[pd[u]] += 1
+        assert n_slots + len(ov) == n_real * nd
+        n_priv = sum(len(pd) for priv, _, pd, _ in groups if priv)
+        assert np.all((ov >> 16) >= n_priv)                     # dofs with overflow are never private
+        for w in ov:
+            u, pos, neg = w >> 16, w & 0x7FFF, (w & 0x8000) != 0
+            E[pos] = -x[pd_all[u]] if neg else x[pd_all[u]]
+            y[pd_all[u]] += -Ey[pos] if neg else Ey[pos]
+        for j in range(n_real):
+            xe = E[np.arange(nd) * st + j]
+            assert np.array_equal(xe, sgn[el[j]] * x[idx[el[j]]])
+    assert np.all(touched >= 1)
+    np.testing.assert_allclose(y, y_ref, rtol=0, atol=1e-13)
 
 
 def test_structured_cube_patches_are_blocks():
     """On a power-of-two structured cube the Morton patches are 4x4x4 element blocks."""
     m, sp, code, cen, idx, sgn = make("hex", (8, 8, 8), 2, False)
-    perm, off, npriv, dof, start, slots = build(sp, 64, code, cen)
-    for k in range(len(npriv)):
+    perm, hdr, dof, e16, e32, e64, ovf, st = build(sp, 64, code, cen)
+    for k in range(len(hdr)):
         c = cen[perm[k * 64:(k + 1) * 64]]
         ext = c.max(0) - c.min(0)
         np.testing.assert_allclose(ext, 3.0 / 8, atol=1e-12)
     # 4x4x4 block of order-2 hexes: 1944 unique dofs, 1176 of them interior to the block
     # (here blocks touch the domain boundary, which only adds private dofs)
-    assert np.all(np.diff(off) == 1944)
-    assert npriv.min() >= 1176
+    assert np.all(hdr[:, 6:12].sum(axis=1) == 1944)
+    assert hdr[:, 6:9].sum(axis=1).min() >= 1176
 
 
 def test_bad_arguments_are_reported():
     lib = L.lib()
     code = np.array([[5, 1]], dtype=np.uint32)
     cen = np.zeros((1, 3))
-    assert not lib.hcurl_host_patches_create(2, 1, 32, 3, L.ptr(cen), L.ptr(code))
+    assert not lib.hcurl_host_patches_create(2, 1, 32, 33, 3, L.ptr(cen), L.ptr(code))
     assert b"out of range" in lib.hcurl_last_error()
-    assert not lib.hcurl_host_patches_create(2, 1, 20000, 8, L.ptr(cen), L.ptr(code))
+    assert not lib.hcurl_host_patches_create(2, 1, 20000, 20000, 8, L.ptr(cen), L.ptr(code))
     assert b"too large" in lib.hcurl_last_error()
