@@ -75,8 +75,9 @@ SIGNATURES = {
     "hcurl_host_patches_create": (_P, [C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int64, _P, _P]),
     "hcurl_host_patches_destroy": (None, [_P]),
     "hcurl_host_patches_count": (C.c_int64, [_P]),
-    "hcurl_host_patches_sizes": (None, [_P, _P]),
-    "hcurl_host_patches_copy": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
+    "hcurl_host_patches_blob_words": (C.c_int64, [_P]),
+    "hcurl_host_patches_max_blob_words": (C.c_int64, [_P]),
+    "hcurl_host_patches_copy": (C.c_int, [_P, _P, _P, _P]),
 }
 
 HEX, TET = 0, 1

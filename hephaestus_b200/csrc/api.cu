@@ -464,7 +464,7 @@ void hcurl_op_destroy(hcurl_op *op) {
   cudaSetDevice(op->ctx->device);
   cudaStreamSynchronize(op->ctx->stream);
   cudaFree(op->d_alpha); cudaFree(op->d_beta); cudaFree(op->d_map_ess); cudaFree(op->d_ess);
-  cudaFree(op->d_edata); cudaFree(op->d_mapT_ess); cudaFree(op->d_edataP); cudaFree(op->d_pdof_ess);
+  cudaFree(op->d_edata); cudaFree(op->d_mapT_ess); cudaFree(op->d_edataP); cudaFree(op->d_blob_ess);
   cudaFree(op->d_emat); cudaFree(op->d_xin); cudaFree(op->d_yout); cudaFree(op->d_tmp);
   for (int i = 0; i < hcurl_op::RING; i++) { cudaEventDestroy(op->ring0[i]); cudaEventDestroy(op->ring1[i]); }
   delete op;

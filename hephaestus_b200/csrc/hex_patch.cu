@@ -158,98 +158,59 @@ __device__ __forceinline__ void modal_op(const double *Am, const double *Bm, con
 }
 
 struct PatchArgs {
-  int64_t n_pos;            // n_patch * FE
-  const int32_t *perm;      // element at each patch position (-1 padding)
-  const uint32_t *hdr, *dof, *e32, *ovf;
-  const uint16_t *e16;
-  const uint64_t *e64;
-  const double *edata;      // [12][n_pos] affine geometry factors in patch order
+  int64_t n_pos;             // n_patch * FE
+  const int32_t *perm;       // element at each patch position (-1 padding)
+  const uint32_t *blob_off;  // [n_patch+1] in 16-byte units
+  const uint32_t *blob;      // patch blobs (patch.cpp)
+  const double *edata;       // [12][n_pos] affine geometry factors in patch order
   const double *x;
   double *y;
   double scale;
+  uint32_t blob_cap_bytes;   // shared-memory room reserved for one blob (multiple of 16)
 };
 
 // sign flip carried in bit 15 of a slot entry
 __device__ __forceinline__ double apply_sign(double v, uint32_t entry) {
   return __hiloint2double(__double2hiint(v) ^ (int)((entry << 16) & 0x80000000u), __double2loint(v));
 }
-template <int W> struct EntryT;
-template <> struct EntryT<1> { typedef uint16_t type; };
-template <> struct EntryT<2> { typedef uint32_t type; };
-template <> struct EntryT<4> { typedef uint64_t type; };
 
-// gather x once per patch dof of one group and push it to the W element slots it feeds
-template <int NT, int W>
-__device__ __forceinline__ void gather_group(const int tid, const uint32_t n, const uint32_t *__restrict__ dof,
-                                             const typename EntryT<W>::type *__restrict__ ent,
-                                             const double *__restrict__ x, double *E) {
-  constexpr int UNR = 4;
-  for (uint32_t u0 = tid; u0 < n; u0 += UNR * NT) {
-    uint32_t m[UNR];
-    uint64_t w[UNR];
-    double v[UNR];
-#pragma unroll
-    for (int i = 0; i < UNR; i++) {
-      const uint32_t u = u0 + i * NT;
-      m[i] = u < n ? __ldg(dof + u) : MAP_ESS;
-      w[i] = u < n ? (uint64_t)__ldg(ent + u) : 0;
-    }
-#pragma unroll
-    for (int i = 0; i < UNR; i++) v[i] = (m[i] & MAP_ESS) ? 0.0 : __ldg(x + (m[i] & MAP_IDX));
-#pragma unroll
-    for (int i = 0; i < UNR; i++)
-      if (u0 + i * NT < n) {
-#pragma unroll
-        for (int j = 0; j < W; j++) {
-          const uint32_t sl = (uint32_t)(w[i] >> (16 * j)) & 0xffffu;
-          if (W == 4 && j == 3 && sl == 0xffffu) continue;
-          E[sl & 0x7fffu] = apply_sign(v[i], sl);
-        }
-      }
-  }
+// ---- bulk async copy (TMA engine, 1-D) of the patch blob into shared memory ----------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void blob_load_async(uint64_t *mbar, void *dst, const void *src, uint32_t bytes) {
+  const uint32_t mb = smem_addr(mbar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+               "l"(src), "r"(bytes), "r"(mb)
+               : "memory");
 }
-
-// sum the W slots of every patch dof of one group; private dofs are plain stores, shared ones RED
-template <int NT, int W, bool PRIV, bool ACC>
-__device__ __forceinline__ void scatter_group(const int tid, const uint32_t n, const uint32_t *__restrict__ dof,
-                                              const typename EntryT<W>::type *__restrict__ ent, const double *E,
-                                              double *__restrict__ y) {
-  constexpr int UNR = 4;
-  for (uint32_t u0 = tid; u0 < n; u0 += UNR * NT) {
-    uint32_t m[UNR];
-    uint64_t w[UNR];
-#pragma unroll
-    for (int i = 0; i < UNR; i++) {
-      const uint32_t u = u0 + i * NT;
-      m[i] = u < n ? __ldg(dof + u) : MAP_ESS;
-      w[i] = u < n ? (uint64_t)__ldg(ent + u) : 0;
-    }
-#pragma unroll
-    for (int i = 0; i < UNR; i++) {
-      if (m[i] & MAP_ESS) continue;
-      double v = 0.0;
-#pragma unroll
-      for (int j = 0; j < W; j++) {
-        const uint32_t sl = (uint32_t)(w[i] >> (16 * j)) & 0xffffu;
-        if (W == 4 && j == 3 && sl == 0xffffu) continue;
-        const double t = apply_sign(E[sl & 0x7fffu], sl);
-        v = j == 0 ? t : v + t;
-      }
-      double *dst = y + (m[i] & MAP_IDX);
-      if (PRIV) *dst = ACC ? *dst + v : v;
-      else atomicAdd(dst, v);
-    }
-  }
+__device__ __forceinline__ void mbar_wait(uint64_t *mbar, uint32_t parity) {
+  const uint32_t mb = smem_addr(mbar);
+  uint32_t done;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done)
+                 : "r"(mb), "r"(parity)
+                 : "memory");
+  } while (!done);
 }
 
 template <int FE, int MINB, bool ACC>
 __global__ void __launch_bounds__(3 * FE, MINB)
 hex_patch_modal_p2_kernel(const PatchArgs a) {
-  extern __shared__ double E[];  // [54][FE + 1]
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NT = 3 * FE, ST = FE + 1;
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw);
+  const uint32_t *B = reinterpret_cast<const uint32_t *>(smem_raw + 16);
+  double *E = reinterpret_cast<double *>(smem_raw + 16 + a.blob_cap_bytes);  // [54][FE + 1]
   const int tid = threadIdx.x;
   const int64_t k = blockIdx.x;
-  // component c of patch element el; its geometry factors are fetched first (consumed after phase A)
+  if (tid == 0) {
+    const uint32_t o0 = __ldg(a.blob_off + k), o1 = __ldg(a.blob_off + k + 1);
+    blob_load_async(mbar, smem_raw + 16, a.blob + (size_t)o0 * 4, (o1 - o0) * 16u);
+  }
+  // component c of patch element el; its geometry factors are fetched now, consumed after phase A
   const int c = tid / FE, el = tid - c * FE;
   const int c1 = c == 2 ? 0 : c + 1, c2 = c == 0 ? 2 : c - 1;
   const int64_t pos = k * FE + el;
@@ -259,25 +220,50 @@ hex_patch_modal_p2_kernel(const PatchArgs a) {
   double K11 = __ldg(g + sym6(c1, c1) * np), K10 = __ldg(g + sym6(c1, c) * np), K12 = __ldg(g + sym6(c1, c2) * np),
          K22 = __ldg(g + sym6(c2, c2) * np), K20 = __ldg(g + sym6(c2, c) * np);
   double M00 = __ldg(g + (6 + sym6(c, c)) * np), M01 = __ldg(g + (6 + sym6(c, c1)) * np), M02 = __ldg(g + (6 + sym6(c, c2)) * np);
-  const uint32_t *h = a.hdr + k * PatchHost::HDR;
-  const uint32_t nP1 = __ldg(h + 6), nP2 = __ldg(h + 7), nP4 = __ldg(h + 8), nS1 = __ldg(h + 9), nS2 = __ldg(h + 10), nS4 = __ldg(h + 11);
-  const uint32_t *dP1 = a.dof + __ldg(h), *dP2 = dP1 + nP1, *dP4 = dP2 + nP2, *dS1 = dP4 + nP4, *dS2 = dS1 + nS1, *dS4 = dS2 + nS2;
-  const uint16_t *eP1 = a.e16 + __ldg(h + 1), *eS1 = eP1 + nP1;
-  const uint32_t *eP2 = a.e32 + __ldg(h + 2), *eS2 = eP2 + nP2;
-  const uint64_t *eP4 = a.e64 + __ldg(h + 3), *eS4 = eP4 + nP4;
-  const uint32_t *ovf = a.ovf + __ldg(h + 4);
-  const uint32_t nov = __ldg(h + 5);
-  // ---- A: gather
-  gather_group<NT, 1>(tid, nP1, dP1, eP1, a.x, E);
-  gather_group<NT, 2>(tid, nP2, dP2, eP2, a.x, E);
-  gather_group<NT, 4>(tid, nP4, dP4, eP4, a.x, E);
-  gather_group<NT, 1>(tid, nS1, dS1, eS1, a.x, E);
-  gather_group<NT, 2>(tid, nS2, dS2, eS2, a.x, E);
-  gather_group<NT, 4>(tid, nS4, dS4, eS4, a.x, E);
-  for (uint32_t t = tid; t < nov; t += NT) {  // slots beyond four (unstructured meshes)
-    const uint32_t e = __ldg(ovf + t), m = __ldg(dP1 + (e >> 16));
-    const double v = (m & MAP_ESS) ? 0.0 : __ldg(a.x + (m & MAP_IDX));
-    E[e & 0x7fffu] = apply_sign(v, e);
+  __syncthreads();  // mbarrier initialised
+  mbar_wait(mbar, 0);
+  const uint32_t U = B[0], b1 = B[1], b2 = B[1] + B[2], nP1 = B[4], nP2 = B[5], nP4 = B[6], nov = B[7];
+  const uint32_t *dof = B + PatchHost::HDR;
+  const uint16_t *e16 = reinterpret_cast<const uint16_t *>(B + B[8]);
+  const uint32_t *e32 = B + B[9];
+  const uint64_t *e64 = reinterpret_cast<const uint64_t *>(B + B[10]);
+  const uint32_t *ovf = B + B[11];
+  // ---- A: gather x once per unique patch dof (all loads of a chunk in flight together), push the
+  // value to the element slots the dof feeds
+  {
+    constexpr int UNR = 6;
+    for (uint32_t u0 = tid; u0 < U; u0 += UNR * NT) {
+      uint32_t m[UNR];
+      double v[UNR];
+#pragma unroll
+      for (int i = 0; i < UNR; i++) m[i] = (u0 + i * NT < U) ? dof[u0 + i * NT] : MAP_ESS;
+#pragma unroll
+      for (int i = 0; i < UNR; i++) v[i] = (m[i] & MAP_ESS) ? 0.0 : __ldg(a.x + (m[i] & MAP_IDX));
+#pragma unroll
+      for (int i = 0; i < UNR; i++) {
+        const uint32_t u = u0 + i * NT;
+        if (u < b1) {
+          const uint32_t sl = e16[u];
+          E[sl & 0x7fffu] = apply_sign(v[i], sl);
+        } else if (u < b2) {
+          const uint32_t w = e32[u - b1];
+          E[w & 0x7fffu] = apply_sign(v[i], w);
+          E[(w >> 16) & 0x7fffu] = apply_sign(v[i], w >> 16);
+        } else if (u < U) {
+          const uint64_t w = e64[u - b2];
+          const uint32_t lo = (uint32_t)w, hi = (uint32_t)(w >> 32);
+          E[lo & 0x7fffu] = apply_sign(v[i], lo);
+          E[(lo >> 16) & 0x7fffu] = apply_sign(v[i], lo >> 16);
+          E[hi & 0x7fffu] = apply_sign(v[i], hi);
+          if ((hi >> 16) != 0xffffu) E[(hi >> 16) & 0x7fffu] = apply_sign(v[i], hi >> 16);
+        }
+      }
+    }
+    for (uint32_t t = tid; t < nov; t += NT) {  // slots beyond four (unstructured meshes)
+      const uint32_t e = ovf[t], m = dof[e >> 16];
+      const double v = (m & MAP_ESS) ? 0.0 : __ldg(a.x + (m & MAP_IDX));
+      E[e & 0x7fffu] = apply_sign(v, e);
+    }
   }
   __syncthreads();
   // ---- element operator
@@ -321,15 +307,34 @@ hex_patch_modal_p2_kernel(const PatchArgs a) {
     for (int t = 0; t < 18; t++) Eown[t * ST] = Y[t];
   }
   __syncthreads();
-  // ---- C: scatter
-  scatter_group<NT, 1, true, ACC>(tid, nP1, dP1, eP1, E, a.y);
-  scatter_group<NT, 2, true, ACC>(tid, nP2, dP2, eP2, E, a.y);
-  scatter_group<NT, 4, true, ACC>(tid, nP4, dP4, eP4, E, a.y);
-  scatter_group<NT, 1, false, ACC>(tid, nS1, dS1, eS1, E, a.y);
-  scatter_group<NT, 2, false, ACC>(tid, nS2, dS2, eS2, E, a.y);
-  scatter_group<NT, 4, false, ACC>(tid, nS4, dS4, eS4, E, a.y);
+  // ---- C: sum the slots of every patch dof; private dofs are plain stores, shared ones RED
+#pragma unroll 2
+  for (uint32_t u = tid; u < U; u += NT) {
+    const uint32_t m = dof[u];
+    if (m & MAP_ESS) continue;
+    double v;
+    bool priv;
+    if (u < b1) {
+      const uint32_t sl = e16[u];
+      v = apply_sign(E[sl & 0x7fffu], sl);
+      priv = u < nP1;
+    } else if (u < b2) {
+      const uint32_t w = e32[u - b1];
+      v = apply_sign(E[w & 0x7fffu], w) + apply_sign(E[(w >> 16) & 0x7fffu], w >> 16);
+      priv = u - b1 < nP2;
+    } else {
+      const uint64_t w = e64[u - b2];
+      const uint32_t lo = (uint32_t)w, hi = (uint32_t)(w >> 32);
+      v = apply_sign(E[lo & 0x7fffu], lo) + apply_sign(E[(lo >> 16) & 0x7fffu], lo >> 16) + apply_sign(E[hi & 0x7fffu], hi);
+      if ((hi >> 16) != 0xffffu) v += apply_sign(E[(hi >> 16) & 0x7fffu], hi >> 16);
+      priv = u - b2 < nP4;
+    }
+    double *dst = a.y + (m & MAP_IDX);
+    if (priv) *dst = ACC ? *dst + v : v;
+    else atomicAdd(dst, v);
+  }
   for (uint32_t t = tid; t < nov; t += NT) {
-    const uint32_t e = __ldg(ovf + t), m = __ldg(dP1 + (e >> 16));
+    const uint32_t e = ovf[t], m = dof[e >> 16];
     if (m & MAP_ESS) continue;
     atomicAdd(a.y + (m & MAP_IDX), apply_sign(E[e & 0x7fffu], e));
   }
@@ -365,12 +370,15 @@ __global__ void patch_edata_kernel(const int64_t n_pos, const int32_t *__restric
     }
 }
 
-__global__ void patch_flag_kernel(const int64_t n, const uint32_t *__restrict__ in, const double *__restrict__ flag,
-                                  uint32_t *__restrict__ out) {
-  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= n) return;
-  const uint32_t m = in[gid];
-  out[gid] = (flag[m & MAP_IDX] != 0.0) ? (m | MAP_ESS) : m;
+// OR the essential flag into the dof words of every patch blob (one CTA per patch)
+__global__ void patch_flag_kernel(const uint32_t *__restrict__ blob_off, const double *__restrict__ flag,
+                                  uint32_t *__restrict__ blob) {
+  uint32_t *B = blob + (size_t)blob_off[blockIdx.x] * 4;
+  const uint32_t U = B[0];
+  for (uint32_t u = threadIdx.x; u < U; u += blockDim.x) {
+    const uint32_t m = B[PatchHost::HDR + u];
+    if (flag[m & MAP_IDX] != 0.0) B[PatchHost::HDR + u] = m | MAP_ESS;
+  }
 }
 
 static bool g_modal_set = false;
@@ -447,17 +455,17 @@ int hex_patch_build(hcurl_space *sp, const double *elem_xyz, const int32_t *elem
   if (build_patches(nd, ne, FE, FE + 1, sp->n_ext(), cen.data(), code.data(), H)) return 1;
   HC_CUDA(cudaSetDevice(sp->ctx->device));
   PatchSet &P = sp->patch;
-  P.FE = FE; P.stride = H.stride; P.n_patch = H.n_patch; P.n_pd = (int64_t)H.dof.size();
-  if (upload(P.d_perm, H.perm) || upload(P.d_hdr, H.hdr) || upload(P.d_dof, H.dof) || upload(P.d_e16, H.e16) ||
-      upload(P.d_e32, H.e32) || upload(P.d_e64, H.e64) || upload(P.d_ovf, H.ovf))
-    return 1;
+  P.FE = FE; P.stride = H.stride; P.n_patch = H.n_patch;
+  P.blob_words = (int64_t)H.blob.size(); P.max_blob_words = H.max_blob_words;
+  if ((size_t)H.max_blob_words * 4 + sizeof(double) * 54 * (FE + 1) + 16 > 200 * 1024) return 0;  // patch path unavailable
+  if (upload(P.d_perm, H.perm) || upload(P.d_blob_off, H.blob_off) || upload(P.d_blob, H.blob)) return 1;
   sp->has_patches = true;
   return 0;
 }
 
 void hex_patch_free(hcurl_space *sp) {
   PatchSet &P = sp->patch;
-  cudaFree(P.d_perm); cudaFree(P.d_hdr); cudaFree(P.d_dof); cudaFree(P.d_e16); cudaFree(P.d_e32); cudaFree(P.d_e64); cudaFree(P.d_ovf);
+  cudaFree(P.d_perm); cudaFree(P.d_blob_off); cudaFree(P.d_blob);
   cudaFree(sp->d_xyzP);
   P = PatchSet();
   sp->has_patches = false;
@@ -476,14 +484,14 @@ bool hex_patch_eligible(const hcurl_op *op) {
 
 template <int FE, int MINB>
 static int launch_fe(const PatchArgs &a, int64_t n_patch, bool acc, cudaStream_t st) {
-  const size_t smem = sizeof(double) * 54 * (FE + 1);
+  const size_t smem = 16 + a.blob_cap_bytes + sizeof(double) * 54 * (FE + 1);
   auto k0 = hex_patch_modal_p2_kernel<FE, MINB, false>;
   auto k1 = hex_patch_modal_p2_kernel<FE, MINB, true>;
-  static bool attr = false;
-  if (!attr) {
+  static size_t attr = 0;
+  if (attr < smem) {
     HC_CUDA(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     HC_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
+    attr = smem;
   }
   if (acc) k1<<<(unsigned)n_patch, 3 * FE, smem, st>>>(a);
   else k0<<<(unsigned)n_patch, 3 * FE, smem, st>>>(a);
@@ -504,9 +512,10 @@ int hex_patch_launch(hcurl_op *op, bool constrained, const double *d_x, double *
     op->edataP_valid = true;
   }
   PatchArgs a;
-  a.n_pos = n_pos; a.perm = P.d_perm; a.hdr = P.d_hdr;
-  a.dof = (constrained && op->d_pdof_ess) ? op->d_pdof_ess : P.d_dof;
-  a.e16 = P.d_e16; a.e32 = P.d_e32; a.e64 = P.d_e64; a.ovf = P.d_ovf; a.edata = op->d_edataP; a.x = d_x; a.y = d_y; a.scale = scale;
+  a.n_pos = n_pos; a.perm = P.d_perm; a.blob_off = P.d_blob_off;
+  a.blob = (constrained && op->d_blob_ess) ? op->d_blob_ess : P.d_blob;
+  a.blob_cap_bytes = (P.max_blob_words * 4 + 15u) & ~15u;
+  a.edata = op->d_edataP; a.x = d_x; a.y = d_y; a.scale = scale;
   int rc = 1;
   if (P.FE == 32) rc = launch_fe<32, 6>(a, P.n_patch, accumulate, ctx->stream);
   else if (P.FE == 64) rc = launch_fe<64, 3>(a, P.n_patch, accumulate, ctx->stream);
@@ -522,9 +531,10 @@ int hex_patch_flag_essential(hcurl_op *op, const double *d_flag) {
   hcurl_space *sp = op->sp;
   if (!sp->has_patches) return 0;
   PatchSet &P = sp->patch;
-  cudaFree(op->d_pdof_ess); op->d_pdof_ess = nullptr;
-  HC_CUDA(cudaMalloc(&op->d_pdof_ess, sizeof(uint32_t) * (P.n_pd ? P.n_pd : 1)));
-  patch_flag_kernel<<<(unsigned)((P.n_pd + 255) / 256), 256, 0, op->ctx->stream>>>(P.n_pd, P.d_dof, d_flag, op->d_pdof_ess);
+  cudaFree(op->d_blob_ess); op->d_blob_ess = nullptr;
+  HC_CUDA(cudaMalloc(&op->d_blob_ess, sizeof(uint32_t) * P.blob_words));
+  HC_CUDA(cudaMemcpyAsync(op->d_blob_ess, P.d_blob, sizeof(uint32_t) * P.blob_words, cudaMemcpyDeviceToDevice, op->ctx->stream));
+  patch_flag_kernel<<<(unsigned)P.n_patch, 128, 0, op->ctx->stream>>>(P.d_blob_off, d_flag, op->d_blob_ess);
   HC_CUDA(cudaGetLastError());
   return 0;
 }

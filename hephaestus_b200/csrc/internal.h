@@ -66,14 +66,11 @@ void tri_face_transform(int p, const int32_t *local_verts, const int32_t *base_v
 struct PatchHost {
   int FE = 0, stride = 0, nd = 0;
   int64_t n_patch = 0;
-  static constexpr int HDR = 12;  // words per patch header
+  static constexpr int HDR = 16;  // header words per patch blob
   std::vector<int32_t> perm;      // [n_patch*FE] element at each patch position, -1 = padding
-  std::vector<uint32_t> hdr;      // [n_patch][HDR]: dof_off, e16_off, e32_off, e64_off, ovf_off, n_ovf, nP1, nP2, nP4, nS1, nS2, nS4
-  std::vector<uint32_t> dof;      // extended-vector index of every patch dof (groups concatenated)
-  std::vector<uint16_t> e16;      // 1-slot dofs: E-vector index | 0x8000 sign flip   (per patch: private then shared)
-  std::vector<uint32_t> e32;      // 2-slot dofs: two 16-bit entries
-  std::vector<uint64_t> e64;      // 3..4-slot dofs: four 16-bit entries, 0xffff = unused
-  std::vector<uint32_t> ovf;      // (patch dof u << 16) | entry, for slots beyond four
+  std::vector<uint32_t> blob_off; // [n_patch+1] start of each patch blob in 16-byte units
+  std::vector<uint32_t> blob;     // see patch.cpp for the layout
+  uint32_t max_blob_words = 0;
 };
 int build_patches(int nd, int64_t n_elem, int FE, int stride, int64_t n_ext, const double *centroid,
                   const uint32_t *slot_code, PatchHost &out);
@@ -85,9 +82,9 @@ struct PatchSet {  // device copy
   int64_t n_patch = 0, n_pd = 0;
   int32_t *d_perm = nullptr;
   int stride = 0;
-  uint32_t *d_hdr = nullptr, *d_dof = nullptr, *d_e32 = nullptr, *d_ovf = nullptr;
-  uint16_t *d_e16 = nullptr;
-  uint64_t *d_e64 = nullptr;
+  uint32_t *d_blob_off = nullptr, *d_blob = nullptr;
+  int64_t blob_words = 0;
+  uint32_t max_blob_words = 0;
 };
 
 // ----------------------------------------------------------------- NCCL ----
@@ -162,7 +159,7 @@ struct hcurl_op {
   double *d_edata = nullptr;
   bool edata_valid = false;
   uint32_t *d_mapT_ess = nullptr;
-  uint32_t *d_pdof_ess = nullptr;  // patch dof list with essential flags
+  uint32_t *d_blob_ess = nullptr;  // copy of the patch blobs with essential flags on the dof words
   double *d_edataP = nullptr;      // [12][n_patch*FE] affine geometry factors in patch order
   bool edataP_valid = false;
   int kernel_sel = 0;              // 0 auto, 1 generic, 2 element-wise fast path, 3 patch path

@@ -14,17 +14,20 @@
 //   * after the element kernels, every patch dof sums its slots; dofs whose elements all lie
 //     in this patch ("private") are written with plain stores, only patch-boundary dofs use
 //     RED atomics.
-// This file builds, for any mesh, the per-patch lists.  The dofs of a patch are split into six
-// groups -- (private | shared) x (1 | 2 | 3..4 element slots) -- each sorted by global index so
-// that consecutive lanes touch consecutive addresses; a group's slot entries have a fixed width
-// (16 / 32 / 64 bits), so the loads of different dofs are independent (a CSR start/slot chain
-// made the kernel latency-bound) and no lane unpacks unused slots:
-//   hdr[k] : 12 words: offsets of patch k in dof/e16/e32/e64/ovf, overflow count, 6 group sizes
-//   dof[u] : global (extended-vector) index of patch dof u (groups concatenated)
-//   e16/e32/e64 : per dof 1 / 2 / 4 entries of 16 bits: E-vector index (bits 0..14) | sign flip
-//            (bit 15), 0xffff = unused (a 3-slot dof in the 64-bit group)
-//   ovf[]  : (u << 16 | entry) for the slots beyond four (edge valence > 4 inside one patch, only
-//            on unstructured meshes); such dofs are classed shared and their overflow is RED-added.
+// This file builds, for any mesh, one contiguous BLOB per patch (so the kernel can stage it in
+// shared memory with a single cp.async.bulk).  The dofs of a patch are ordered by slot count --
+// 1 | 2 | 3..4 element slots -- and inside each width private dofs come first; every group is
+// sorted by global index so that consecutive lanes touch consecutive addresses.  Slot entries have
+// a fixed width per section (16 / 32 / 64 bits), so no lane unpacks unused slots.  Blob layout in
+// 32-bit words, every section starting on a 16-byte boundary:
+//   [0] U  [1] n1  [2] n2  [3] n4      number of patch dofs, and of 1- / 2- / 3..4-slot dofs
+//   [4] nP1 [5] nP2 [6] nP4            private dofs at the head of each width section
+//   [7] n_ovf  [8..11] word offsets of the e16 / e32 / e64 / ovf sections  [12..15] 0
+//   [16 ..] dof[U]   extended-vector index of every patch dof
+//   e16[n1], e32[n2], e64[n4]  per dof 1 / 2 / 4 entries of 16 bits: E-vector index (bits 0..14)
+//            | sign flip (bit 15); 0xffff = unused (a 3-slot dof in the 64-bit section)
+//   ovf[n_ovf]  (u << 16 | entry) for the slots beyond four (edge valence > 4 inside one patch,
+//            only on unstructured meshes); such dofs are classed shared, overflow is RED-added.
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -148,58 +151,66 @@ int build_patches(int nd, int64_t n_elem, int FE, int stride, int64_t n_ext, con
     }
   }
   owner.clear(); owner.shrink_to_fit();
-  // ---- group the patch dofs: (private | shared) x (1 | 2 | 3-4 slots), ascending inside a group
-  auto group_of = [&](uint32_t d, int nslot) { return (multi[d] ? 3 : 0) + (nslot <= 1 ? 0 : (nslot == 2 ? 1 : 2)); };
-  out.hdr.assign((size_t)n_patch * PatchHost::HDR, 0);
-  uint32_t o_dof = 0, o16 = 0, o32 = 0, o64 = 0, o_ovf = 0;
+  // ---- emit one blob per patch
+  auto width_of = [](int nslot) { return nslot <= 1 ? 0 : (nslot == 2 ? 1 : 2); };
+  auto align4 = [](uint32_t w) { return (w + 3u) & ~3u; };  // words -> 16-byte boundary
+  std::vector<uint32_t> words((size_t)n_patch);
+  out.blob_off.assign((size_t)n_patch + 1, 0);
+  out.max_blob_words = 0;
   for (int64_t k = 0; k < n_patch; k++) {
     const auto &ud = udof[(size_t)k];
     const auto &us = ustart[(size_t)k];
-    uint32_t *h = out.hdr.data() + (size_t)k * PatchHost::HDR;
-    h[0] = o_dof; h[1] = o16; h[2] = o32; h[3] = o64; h[4] = o_ovf;
+    uint32_t n[3] = {0, 0, 0}, nov = 0;
     for (size_t i = 0; i < ud.size(); i++) {
       const int ns = us[i + 1] - us[i];
-      h[6 + group_of(ud[i], ns)]++;
-      if (ns > 4) h[5] += ns - 4;
+      n[width_of(ns)]++;
+      if (ns > 4) nov += ns - 4;
     }
-    o_dof += (uint32_t)ud.size();
-    o16 += h[6] + h[9]; o32 += h[7] + h[10]; o64 += h[8] + h[11]; o_ovf += h[5];
+    const uint32_t w = PatchHost::HDR + align4((uint32_t)ud.size()) + align4((n[0] + 1) / 2) + align4(n[1]) + align4(2 * n[2]) + align4(nov);
+    words[(size_t)k] = w;
+    out.blob_off[(size_t)k + 1] = out.blob_off[(size_t)k] + w / 4;
+    out.max_blob_words = std::max(out.max_blob_words, w);
   }
-  out.dof.assign(o_dof, 0);
-  out.e16.assign(o16, 0);
-  out.e32.assign(o32, 0);
-  out.e64.assign(o64, 0);
-  out.ovf.assign(o_ovf, 0);
+  out.blob.assign((size_t)out.blob_off[(size_t)n_patch] * 4, 0);
   parallel_for(n_patch, [&](int64_t k) {
     const auto &ud = udof[(size_t)k];
     const auto &us = ustart[(size_t)k];
     const auto &sl = uslots[(size_t)k];
-    const uint32_t *h = out.hdr.data() + (size_t)k * PatchHost::HDR;
-    uint32_t *pd = out.dof.data() + h[0];
-    uint16_t *p16 = out.e16.data() + h[1];
-    uint32_t *p32 = out.e32.data() + h[2];
-    uint64_t *p64 = out.e64.data() + h[3];
-    uint32_t *po = out.ovf.data() + h[4];
-    // first patch-local index of each group, entry cursor per width
-    uint32_t gstart[6], u = 0;
-    for (int g = 0; g < 6; g++) { gstart[g] = u; u += h[6 + g]; }
-    uint32_t cur[6];
-    for (int g = 0; g < 6; g++) cur[g] = gstart[g];
-    uint32_t c16[2] = {0, h[6]}, c32[2] = {0, h[7]}, c64[2] = {0, h[8]};
+    uint32_t *B = out.blob.data() + (size_t)out.blob_off[(size_t)k] * 4;
+    // group sizes: [width][private|shared]
+    uint32_t cnt[3][2] = {{0, 0}, {0, 0}, {0, 0}}, nov = 0;
     for (size_t i = 0; i < ud.size(); i++) {
       const int ns = us[i + 1] - us[i];
-      const int g = group_of(ud[i], ns), cls = g / 3, w = g % 3;
-      const uint32_t ul = cur[g]++;
+      cnt[width_of(ns)][multi[ud[i]] ? 1 : 0]++;
+      if (ns > 4) nov += ns - 4;
+    }
+    const uint32_t U = (uint32_t)ud.size(), n1 = cnt[0][0] + cnt[0][1], n2 = cnt[1][0] + cnt[1][1], n4 = cnt[2][0] + cnt[2][1];
+    const uint32_t o16 = PatchHost::HDR + align4(U), o32 = o16 + align4((n1 + 1) / 2), o64 = o32 + align4(n2), oov = o64 + align4(2 * n4);
+    B[0] = U; B[1] = n1; B[2] = n2; B[3] = n4; B[4] = cnt[0][0]; B[5] = cnt[1][0]; B[6] = cnt[2][0]; B[7] = nov;
+    B[8] = o16; B[9] = o32; B[10] = o64; B[11] = oov;
+    uint32_t *pd = B + PatchHost::HDR;
+    uint16_t *p16 = (uint16_t *)(B + o16);
+    uint32_t *p32 = B + o32;
+    uint64_t *p64 = (uint64_t *)(B + o64);
+    uint32_t *po = B + oov;
+    // cursor of each (width, class) group in the dof list and in its entry array
+    uint32_t base[3] = {0, n1, n1 + n2};
+    uint32_t cur[3][2] = {{0, cnt[0][0]}, {0, cnt[1][0]}, {0, cnt[2][0]}};
+    for (size_t i = 0; i < ud.size(); i++) {
+      const int ns = us[i + 1] - us[i];
+      const int w = width_of(ns), cls = multi[ud[i]] ? 1 : 0;
+      const uint32_t r = cur[w][cls]++;  // index inside the width section
+      const uint32_t ul = base[w] + r;   // patch-local dof index
       pd[ul] = ud[i];
-      if (w == 0) p16[c16[cls]++] = sl[us[i]];
-      else if (w == 1) p32[c32[cls]++] = (uint32_t)sl[us[i]] | ((uint32_t)sl[us[i] + 1] << 16);
+      if (w == 0) p16[r] = sl[us[i]];
+      else if (w == 1) p32[r] = (uint32_t)sl[us[i]] | ((uint32_t)sl[us[i] + 1] << 16);
       else {
         uint64_t v = ~0ULL;
         for (int j = 0; j < ns; j++) {
           if (j < 4) v = (v & ~(0xffffULL << (16 * j))) | ((uint64_t)sl[us[i] + j] << (16 * j));
           else *po++ = (ul << 16) | sl[us[i] + j];
         }
-        p64[c64[cls]++] = v;
+        p64[r] = v;
       }
     }
   });
@@ -224,22 +235,14 @@ hcurl_host_patches *hcurl_host_patches_create(int nd, int64_t n_elem, int elems_
 }
 void hcurl_host_patches_destroy(hcurl_host_patches *p) { delete p; }
 int64_t hcurl_host_patches_count(const hcurl_host_patches *p) { return p->h.n_patch; }
-/* sizes[5] = entries of dof, e16, e32, e64, ovf */
-void hcurl_host_patches_sizes(const hcurl_host_patches *p, int64_t *sizes) {
-  const hcurl::PatchHost &h = p->h;
-  sizes[0] = (int64_t)h.dof.size(); sizes[1] = (int64_t)h.e16.size(); sizes[2] = (int64_t)h.e32.size();
-  sizes[3] = (int64_t)h.e64.size(); sizes[4] = (int64_t)h.ovf.size();
-}
-int hcurl_host_patches_copy(const hcurl_host_patches *p, int32_t *perm, uint32_t *hdr, uint32_t *dof, uint16_t *e16,
-                            uint32_t *e32, uint64_t *e64, uint32_t *ovf) {
+/* total blob size in 32-bit words; largest single patch blob in words */
+int64_t hcurl_host_patches_blob_words(const hcurl_host_patches *p) { return (int64_t)p->h.blob.size(); }
+int64_t hcurl_host_patches_max_blob_words(const hcurl_host_patches *p) { return (int64_t)p->h.max_blob_words; }
+int hcurl_host_patches_copy(const hcurl_host_patches *p, int32_t *perm, uint32_t *blob_off, uint32_t *blob) {
   const hcurl::PatchHost &h = p->h;
   if (perm) memcpy(perm, h.perm.data(), sizeof(int32_t) * h.perm.size());
-  if (hdr) memcpy(hdr, h.hdr.data(), sizeof(uint32_t) * h.hdr.size());
-  if (dof) memcpy(dof, h.dof.data(), sizeof(uint32_t) * h.dof.size());
-  if (e16) memcpy(e16, h.e16.data(), sizeof(uint16_t) * h.e16.size());
-  if (e32) memcpy(e32, h.e32.data(), sizeof(uint32_t) * h.e32.size());
-  if (e64) memcpy(e64, h.e64.data(), sizeof(uint64_t) * h.e64.size());
-  if (ovf) memcpy(ovf, h.ovf.data(), sizeof(uint32_t) * h.ovf.size());
+  if (blob_off) memcpy(blob_off, h.blob_off.data(), sizeof(uint32_t) * h.blob_off.size());
+  if (blob) memcpy(blob, h.blob.data(), sizeof(uint32_t) * h.blob.size());
   return 0;
 }
 }

@@ -226,20 +226,17 @@ int hcurl_dot(hcurl_ctx *ctx, const double *a_dev, const double *b_dev, int64_t 
  *  slot_code  [n_elem][nd]: dof index (bits 0..29) | sign flip (bit 31) of each element slot
  *  slot_stride  >= elems_per_patch: E-vector index of (slot s, patch position j) = s*slot_stride + j
  *  outputs    perm [n_patch*epp] element at each patch position (-1 padding);
- *             hdr [n_patch][12]: offsets of the patch in dof/e16/e32/e64/ovf, overflow count, sizes
- *             of its six dof groups (private | shared) x (1 | 2 | 3..4 slots);
- *             dof: dof index per patch dof; e16/e32/e64: 1/2/4 16-bit entries per dof,
- *             E-vector index | 0x8000 sign flip, 0xffff unused; ovf: (patch dof << 16 | entry) for
- *             the slots beyond four. */
+ *             blob_off [n_patch+1] start of each patch blob in 16-byte units; blob: per patch a
+ *             16-word header, the dof list and the 16/32/64-bit slot-entry sections (layout in
+ *             hephaestus_b200/csrc/patch.cpp). */
 typedef struct hcurl_host_patches hcurl_host_patches;
 hcurl_host_patches *hcurl_host_patches_create(int nd, int64_t n_elem, int elems_per_patch, int slot_stride,
                                               int64_t n_dof, const double *centroid, const uint32_t *slot_code);
 void hcurl_host_patches_destroy(hcurl_host_patches *p);
 int64_t hcurl_host_patches_count(const hcurl_host_patches *p);
-/* sizes[5] = number of entries of dof, e16, e32, e64, ovf */
-void hcurl_host_patches_sizes(const hcurl_host_patches *p, int64_t *sizes);
-int hcurl_host_patches_copy(const hcurl_host_patches *p, int32_t *perm, uint32_t *hdr, uint32_t *dof, uint16_t *e16,
-                            uint32_t *e32, uint64_t *e64, uint32_t *ovf);
+int64_t hcurl_host_patches_blob_words(const hcurl_host_patches *p);
+int64_t hcurl_host_patches_max_blob_words(const hcurl_host_patches *p);
+int hcurl_host_patches_copy(const hcurl_host_patches *p, int32_t *perm, uint32_t *blob_off, uint32_t *blob);
 
 /* FP64 FMA micro-benchmark used for the roofline co-bound:
  * returns achieved TFLOP/s of dependent-chain-free DFMA on the device. */

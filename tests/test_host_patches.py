@@ -21,35 +21,32 @@ def build(space, fe, slot_code, centroid, stride=None):
     stride = stride or fe + 1
     h = L.check_ptr(lib.hcurl_host_patches_create(nd, ne, fe, stride, space.ndof, L.ptr(centroid), L.ptr(slot_code)), "patches")
     npatch = lib.hcurl_host_patches_count(h)
-    sizes = np.zeros(5, np.int64)
-    lib.hcurl_host_patches_sizes(h, L.ptr(sizes))
+    nw = lib.hcurl_host_patches_blob_words(h)
     perm = np.zeros(npatch * fe, np.int32)
-    hdr = np.zeros((npatch, 12), np.uint32)
-    dof = np.zeros(sizes[0], np.uint32)
-    e16 = np.zeros(max(sizes[1], 1), np.uint16)
-    e32 = np.zeros(max(sizes[2], 1), np.uint32)
-    e64 = np.zeros(max(sizes[3], 1), np.uint64)
-    ovf = np.zeros(max(sizes[4], 1), np.uint32)
-    L.check(lib.hcurl_host_patches_copy(h, L.ptr(perm), L.ptr(hdr), L.ptr(dof), L.ptr(e16), L.ptr(e32), L.ptr(e64), L.ptr(ovf)), "copy")
+    off = np.zeros(npatch + 1, np.uint32)
+    blob = np.zeros(nw, np.uint32)
+    L.check(lib.hcurl_host_patches_copy(h, L.ptr(perm), L.ptr(off), L.ptr(blob)), "copy")
+    assert lib.hcurl_host_patches_max_blob_words(h) == int(np.diff(off.astype(np.int64)).max()) * 4
     lib.hcurl_host_patches_destroy(h)
-    return perm, hdr.astype(np.int64), dof, e16, e32, e64, ovf[:sizes[4]], stride
+    return perm, off.astype(np.int64), blob, stride
 
 
-def patch_groups(k, hdr, dof, e16, e32, e64):
-    """[(private?, dof ids, entries (n, W))] of the six groups of patch k, in kernel order."""
-    o_dof, o16, o32, o64 = hdr[k, :4]
-    n = hdr[k, 6:12]
+def decode_patch(k, off, blob):
+    """Blob of patch k (layout: hephaestus_b200/csrc/patch.cpp) ->
+    (dof ids (U,), [(private?, first u, dof ids, entries (n, W))] in kernel order, overflow words)."""
+    B = blob[off[k] * 4:off[k + 1] * 4]
+    U, n1, n2, n4, nP1, nP2, nP4, nov, o16, o32, o64, oov = [int(v) for v in B[:12]]
+    assert np.all(B[12:16] == 0) and U == n1 + n2 + n4
+    assert o16 % 4 == 0 and o32 % 4 == 0 and o64 % 4 == 0 and oov % 4 == 0 and len(B) % 4 == 0
+    dof = B[16:16 + U].astype(np.int64)
     sh = 16 * np.arange(4, dtype=np.uint64)
-    ent = {1: e16[o16:o16 + n[0] + n[3]].astype(np.int64)[:, None],
-           2: (e32[o32:o32 + n[1] + n[4], None].astype(np.uint64) >> sh[None, :2]).astype(np.int64) & 0xFFFF,
-           4: (e64[o64:o64 + n[2] + n[5], None] >> sh[None]).astype(np.int64) & 0xFFFF}
-    out, u = [], 0
-    cur = {1: 0, 2: 0, 4: 0}
-    for gi, (priv, w) in enumerate([(True, 1), (True, 2), (True, 4), (False, 1), (False, 2), (False, 4)]):
-        out.append((priv, u, dof[o_dof + u:o_dof + u + n[gi]].astype(np.int64), ent[w][cur[w]:cur[w] + n[gi]]))
-        u += n[gi]
-        cur[w] += n[gi]
-    return out, u
+    e16 = B[o16:o16 + (n1 + 1) // 2].view(np.uint16)[:n1].astype(np.int64)[:, None]
+    e32 = (B[o32:o32 + n2, None].astype(np.uint64) >> sh[None, :2]).astype(np.int64) & 0xFFFF
+    e64 = (B[o64:o64 + 2 * n4].view(np.uint64)[:, None] >> sh[None]).astype(np.int64) & 0xFFFF
+    groups = [(True, 0, dof[:nP1], e16[:nP1]), (False, nP1, dof[nP1:n1], e16[nP1:]),
+              (True, n1, dof[n1:n1 + nP2], e32[:nP2]), (False, n1 + nP2, dof[n1 + nP2:n1 + n2], e32[nP2:]),
+              (True, n1 + n2, dof[n1 + n2:n1 + n2 + nP4], e64[:nP4]), (False, n1 + n2 + nP4, dof[n1 + n2 + nP4:], e64[nP4:])]
+    return dof, groups, B[oov:oov + nov].astype(np.int64)
 
 
 def make(kind, n, p, perturb):
@@ -76,13 +73,14 @@ def make(kind, n, p, perturb):
 def test_patch_lists_reproduce_gather_and_scatter(kind, n, p, fe, perturb):
     m, sp, code, cen, idx, sgn = make(kind, n, p, perturb)
     ne, nd = code.shape
-    perm, hdr, dof, e16, e32, e64, ovf, st = build(sp, fe, code, cen)
-    npatch = len(hdr)
+    perm, off, blob, st = build(sp, fe, code, cen)
+    npatch = len(off) - 1
     assert npatch == (ne + fe - 1) // fe
+    n_ovf = sum(len(decode_patch(k, off, blob)[2]) for k in range(npatch))
     if kind in ("star", "tet"):
-        assert len(ovf) > 0  # these meshes have dofs with more than four slots in a patch
+        assert n_ovf > 0  # these meshes have dofs with more than four slots in a patch
     elif kind == "hex":
-        assert len(ovf) == 0
+        assert n_ovf == 0
     # perm is a permutation of the elements (+ padding)
     real = perm[perm >= 0]
     assert np.array_equal(np.sort(real), np.arange(ne))
@@ -101,9 +99,7 @@ def test_patch_lists_reproduce_gather_and_scatter(kind, n, p, fe, perturb):
     np.minimum.at(pmin, idx.ravel(), np.repeat(elem_patch, nd))
     np.maximum.at(pmax, idx.ravel(), np.repeat(elem_patch, nd))
     for k in range(npatch):
-        groups, U = patch_groups(k, hdr, dof, e16, e32, e64)
-        ov = ovf[hdr[k, 4]:hdr[k, 4] + hdr[k, 5]].astype(np.int64)
-        pd_all = dof[hdr[k, 0]:hdr[k, 0] + U].astype(np.int64)
+        pd_all, groups, ov = decode_patch(k, off, blob)
         el = perm[k * fe:(k + 1) * fe]
         n_real = int((el >= 0).sum())
         E = np.full(nd * st, np.nan)
@@ -135,8 +131,8 @@ def test_patch_lists_reproduce_gather_and_scatter(kind, n, p, fe, perturb):
                     y[pd[u]] += v
                 touched[pd[u]] += 1
         assert n_slots + len(ov) == n_real * nd
-        n_priv = sum(len(pd) for priv, _, pd, _ in groups if priv)
-        assert np.all((ov >> 16) >= n_priv)                     # dofs with overflow are never private
+        n4_priv_end = groups[4][1] + len(groups[4][2])
+        assert np.all((ov >> 16) >= n4_priv_end)                # dofs with overflow are shared 3..4-slot dofs
         for w in ov:
             u, pos, neg = w >> 16, w & 0x7FFF, (w & 0x8000) != 0
             E[pos] = -x[pd_all[u]] if neg else x[pd_all[u]]
@@ -151,15 +147,16 @@ def test_patch_lists_reproduce_gather_and_scatter(kind, n, p, fe, perturb):
 def test_structured_cube_patches_are_blocks():
     """On a power-of-two structured cube the Morton patches are 4x4x4 element blocks."""
     m, sp, code, cen, idx, sgn = make("hex", (8, 8, 8), 2, False)
-    perm, hdr, dof, e16, e32, e64, ovf, st = build(sp, 64, code, cen)
-    for k in range(len(hdr)):
+    perm, off, blob, st = build(sp, 64, code, cen)
+    for k in range(len(off) - 1):
         c = cen[perm[k * 64:(k + 1) * 64]]
         ext = c.max(0) - c.min(0)
         np.testing.assert_allclose(ext, 3.0 / 8, atol=1e-12)
-    # 4x4x4 block of order-2 hexes: 1944 unique dofs, 1176 of them interior to the block
-    # (here blocks touch the domain boundary, which only adds private dofs)
-    assert np.all(hdr[:, 6:12].sum(axis=1) == 1944)
-    assert hdr[:, 6:9].sum(axis=1).min() >= 1176
+        # 4x4x4 block of order-2 hexes: 1944 unique dofs, 1176 of them interior to the block
+        # (here blocks touch the domain boundary, which only adds private dofs)
+        pd, groups, ov = decode_patch(k, off, blob)
+        assert len(pd) == 1944
+        assert sum(len(g[2]) for g in groups if g[0]) >= 1176
 
 
 def test_bad_arguments_are_reported():
