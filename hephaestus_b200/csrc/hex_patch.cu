@@ -28,9 +28,13 @@
 namespace hcurl {
 
 struct ModalTables {
-  double To[4];  // [m][i] nodal (Gauss-Legendre) -> orthonormal Legendre, open basis
-  double Tc[9];  // [m][j] nodal (Gauss-Lobatto)  -> orthonormal Legendre, closed basis
-  double d1, d2; // L1' = d1 L0, L2' = d2 L1
+  // closed basis (Gauss-Lobatto nodes 0, 1/2, 1) -> orthonormal Legendre L0, L1, L2:
+  //   T = [[a0, a1, a0], [-b, 0, b], [c0, c1, c0]]   (symmetry of the nodes)
+  // open basis (2 Gauss-Legendre nodes) -> L0, L1 is [[1/2, 1/2], [-1/2, 1/2]]; the kernel applies
+  // [[1, 1], [-1, 1]] (adds only) and folds the two factors 1/2 (trial and test side) into the
+  // geometry factors.
+  double a0, a1, b, c0, c1;
+  double d1, d2;  // L1' = d1 L0, L2' = d2 L1
 };
 __constant__ ModalTables cM;
 
@@ -53,45 +57,45 @@ __device__ __forceinline__ int sym6(int i, int j) {  // packed index of the symm
 #define IB(m0, m1, m2) ((m0) + 3 * ((m1) + 2 * (m2)))  // component c+1  [3][2][3] (my frame)
 #define IC(m0, m1, m2) ((m0) + 3 * ((m1) + 3 * (m2)))  // component c+2  [3][3][2] (my frame)
 
-// nodal -> modal on own component (in place semantics: X -> A)
+// 1-D closed transform of a line (x0, x1, x2) -> (m0, m1, m2), 7 FP64 instructions
+__device__ __forceinline__ void tc_fwd(const double x0, const double x1, const double x2, double &m0, double &m1, double &m2) {
+  const double s = x0 + x2, d = x2 - x0;
+  m0 = fma(cM.a1, x1, cM.a0 * s);
+  m1 = cM.b * d;
+  m2 = fma(cM.c1, x1, cM.c0 * s);
+}
+// transpose: (y0, y1, y2) modal test values -> nodal
+__device__ __forceinline__ void tc_bwd(const double y0, const double y1, const double y2, double &x0, double &x1, double &x2) {
+  const double p = fma(cM.c0, y2, cM.a0 * y0), q = cM.b * y1;
+  x0 = p - q;
+  x2 = p + q;
+  x1 = fma(cM.c1, y2, cM.a1 * y0);
+}
+// nodal -> (2x) modal on own component
 __device__ __forceinline__ void modal_fwd(const double *X, double *A) {
   double a[18], b[18];
 #pragma unroll
-  for (int r = 0; r < 9; r++)
-#pragma unroll
-    for (int m = 0; m < 2; m++) a[m + 2 * r] = fma(cM.To[m * 2 + 1], X[1 + 2 * r], cM.To[m * 2] * X[2 * r]);
+  for (int r = 0; r < 9; r++) { a[2 * r] = X[2 * r] + X[2 * r + 1]; a[2 * r + 1] = X[2 * r + 1] - X[2 * r]; }
 #pragma unroll
   for (int i2 = 0; i2 < 3; i2++)
 #pragma unroll
-    for (int m1 = 0; m1 < 3; m1++)
+    for (int m0 = 0; m0 < 2; m0++)
+      tc_fwd(a[IA(m0, 0, i2)], a[IA(m0, 1, i2)], a[IA(m0, 2, i2)], b[IA(m0, 0, i2)], b[IA(m0, 1, i2)], b[IA(m0, 2, i2)]);
 #pragma unroll
-      for (int m0 = 0; m0 < 2; m0++)
-        b[IA(m0, m1, i2)] = fma(cM.Tc[m1 * 3 + 2], a[IA(m0, 2, i2)], fma(cM.Tc[m1 * 3 + 1], a[IA(m0, 1, i2)], cM.Tc[m1 * 3] * a[IA(m0, 0, i2)]));
-#pragma unroll
-  for (int m2 = 0; m2 < 3; m2++)
-#pragma unroll
-    for (int r = 0; r < 6; r++)
-      A[r + 6 * m2] = fma(cM.Tc[m2 * 3 + 2], b[r + 12], fma(cM.Tc[m2 * 3 + 1], b[r + 6], cM.Tc[m2 * 3] * b[r]));
+  for (int r = 0; r < 6; r++) tc_fwd(b[r], b[r + 6], b[r + 12], A[r], A[r + 6], A[r + 12]);
 }
-// modal -> nodal test functions (transpose)
+// modal -> nodal test functions (transpose, again with the open transform scaled by 2)
 __device__ __forceinline__ void modal_bwd(const double *Yh, double *Y) {
   double a[18], b[18];
 #pragma unroll
-  for (int i2 = 0; i2 < 3; i2++)
-#pragma unroll
-    for (int r = 0; r < 6; r++)
-      a[r + 6 * i2] = fma(cM.Tc[6 + i2], Yh[r + 12], fma(cM.Tc[3 + i2], Yh[r + 6], cM.Tc[i2] * Yh[r]));
+  for (int r = 0; r < 6; r++) tc_bwd(Yh[r], Yh[r + 6], Yh[r + 12], a[r], a[r + 6], a[r + 12]);
 #pragma unroll
   for (int i2 = 0; i2 < 3; i2++)
 #pragma unroll
-    for (int i1 = 0; i1 < 3; i1++)
+    for (int m0 = 0; m0 < 2; m0++)
+      tc_bwd(a[IA(m0, 0, i2)], a[IA(m0, 1, i2)], a[IA(m0, 2, i2)], b[IA(m0, 0, i2)], b[IA(m0, 1, i2)], b[IA(m0, 2, i2)]);
 #pragma unroll
-      for (int m0 = 0; m0 < 2; m0++)
-        b[IA(m0, i1, i2)] = fma(cM.Tc[6 + i1], a[IA(m0, 2, i2)], fma(cM.Tc[3 + i1], a[IA(m0, 1, i2)], cM.Tc[i1] * a[IA(m0, 0, i2)]));
-#pragma unroll
-  for (int r = 0; r < 9; r++)
-#pragma unroll
-    for (int i0 = 0; i0 < 2; i0++) Y[i0 + 2 * r] = fma(cM.To[2 + i0], b[1 + 2 * r], cM.To[i0] * b[2 * r]);
+  for (int r = 0; r < 9; r++) { Y[2 * r] = b[2 * r] - b[2 * r + 1]; Y[2 * r + 1] = b[2 * r] + b[2 * r + 1]; }
 }
 
 // modal element operator for component a0 = c: reads own (Am) and the other two components' modal
@@ -295,7 +299,7 @@ hex_patch_modal_p2_kernel(const PatchArgs a) {
       for (int m1 = 0; m1 < 3; m1++)
 #pragma unroll
         for (int m0 = 0; m0 < 3; m0++) Cm[IC(m0, m1, m2)] = E2[(m2 + 2 * (m0 + 3 * m1)) * ST];
-    const double sc = a.scale;
+    const double sc = 0.25 * a.scale;  // 1/4: the open transforms are applied without their 1/2
     K11 *= sc; K10 *= sc; K12 *= sc; K22 *= sc; K20 *= sc; M00 *= sc; M01 *= sc; M02 *= sc;
     double Yh[18];
     modal_op(Am, Bm, Cm, M00, M01, M02, K11, K10, K12, K22, K20, K12, Yh);
@@ -393,19 +397,24 @@ static int set_modal_tables() {
   double Bo[5 * 2], Bc[5 * 3];
   lagrange_tables(2, gl, 5, xq, Bo, nullptr);
   lagrange_tables(3, gll, 5, xq, Bc, nullptr);
-  ModalTables T;
-  for (int m = 0; m < 3; m++) {
-    for (int j = 0; j < 3; j++) T.Tc[m * 3 + j] = 0.0;
-    if (m < 2) for (int i = 0; i < 2; i++) T.To[m * 2 + i] = 0.0;
-  }
+  double Tc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, To[4] = {0, 0, 0, 0};
   for (int q = 0; q < 5; q++) {
     const double t = 2.0 * xq[q] - 1.0;
     const double L[3] = {1.0, sqrt(3.0) * t, sqrt(5.0) * 0.5 * (3.0 * t * t - 1.0)};
     for (int m = 0; m < 3; m++) {
-      for (int j = 0; j < 3; j++) T.Tc[m * 3 + j] += wq[q] * L[m] * Bc[q * 3 + j];
-      if (m < 2) for (int i = 0; i < 2; i++) T.To[m * 2 + i] += wq[q] * L[m] * Bo[q * 2 + i];
+      for (int j = 0; j < 3; j++) Tc[m * 3 + j] += wq[q] * L[m] * Bc[q * 3 + j];
+      if (m < 2) for (int i = 0; i < 2; i++) To[m * 2 + i] += wq[q] * L[m] * Bo[q * 2 + i];
     }
   }
+  // the kernel hard-wires the structure of these tables; check it
+  const double tol = 1e-14;
+  if (fabs(To[0] - 0.5) > tol || fabs(To[1] - 0.5) > tol || fabs(To[2] + 0.5) > tol || fabs(To[3] - 0.5) > tol ||
+      fabs(Tc[0] - Tc[2]) > tol || fabs(Tc[3] + Tc[5]) > tol || fabs(Tc[4]) > tol || fabs(Tc[6] - Tc[8]) > tol) {
+    set_error("modal tables do not have the expected symmetric structure");
+    return 1;
+  }
+  ModalTables T;
+  T.a0 = 0.5 * (Tc[0] + Tc[2]); T.a1 = Tc[1]; T.b = 0.5 * (Tc[5] - Tc[3]); T.c0 = 0.5 * (Tc[6] + Tc[8]); T.c1 = Tc[7];
   T.d1 = 2.0 * sqrt(3.0);
   T.d2 = 2.0 * sqrt(15.0);
   HC_CUDA(cudaMemcpyToSymbol(cM, &T, sizeof(T)));
@@ -491,6 +500,8 @@ static int launch_fe(const PatchArgs &a, int64_t n_patch, bool acc, cudaStream_t
   if (attr < smem) {
     HC_CUDA(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     HC_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HC_CUDA(cudaFuncSetAttribute(k0, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    HC_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     attr = smem;
   }
   if (acc) k1<<<(unsigned)n_patch, 3 * FE, smem, st>>>(a);
@@ -517,8 +528,8 @@ int hex_patch_launch(hcurl_op *op, bool constrained, const double *d_x, double *
   a.blob_cap_bytes = (P.max_blob_words * 4 + 15u) & ~15u;
   a.edata = op->d_edataP; a.x = d_x; a.y = d_y; a.scale = scale;
   int rc = 1;
-  if (P.FE == 32) rc = launch_fe<32, 6>(a, P.n_patch, accumulate, ctx->stream);
-  else if (P.FE == 64) rc = launch_fe<64, 3>(a, P.n_patch, accumulate, ctx->stream);
+  if (P.FE == 32) rc = launch_fe<32, 8>(a, P.n_patch, accumulate, ctx->stream);
+  else if (P.FE == 64) rc = launch_fe<64, 4>(a, P.n_patch, accumulate, ctx->stream);
   else if (P.FE == 128) rc = launch_fe<128, 1>(a, P.n_patch, accumulate, ctx->stream);
   if (rc) return rc;
   HC_CUDA(cudaGetLastError());

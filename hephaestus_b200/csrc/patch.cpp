@@ -31,6 +31,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 
@@ -193,26 +194,33 @@ int build_patches(int nd, int64_t n_elem, int FE, int stride, int64_t n_ext, con
     uint32_t *p32 = B + o32;
     uint64_t *p64 = (uint64_t *)(B + o64);
     uint32_t *po = B + oov;
-    // cursor of each (width, class) group in the dof list and in its entry array
-    uint32_t base[3] = {0, n1, n1 + n2};
-    uint32_t cur[3][2] = {{0, cnt[0][0]}, {0, cnt[1][0]}, {0, cnt[2][0]}};
-    for (size_t i = 0; i < ud.size(); i++) {
-      const int ns = us[i + 1] - us[i];
-      const int w = width_of(ns), cls = multi[ud[i]] ? 1 : 0;
-      const uint32_t r = cur[w][cls]++;  // index inside the width section
-      const uint32_t ul = base[w] + r;   // patch-local dof index
-      pd[ul] = ud[i];
-      if (w == 0) p16[r] = sl[us[i]];
-      else if (w == 1) p32[r] = (uint32_t)sl[us[i]] | ((uint32_t)sl[us[i] + 1] << 16);
-      else {
-        uint64_t v = ~0ULL;
-        for (int j = 0; j < ns; j++) {
-          if (j < 4) v = (v & ~(0xffffULL << (16 * j))) | ((uint64_t)sl[us[i] + j] << (16 * j));
-          else *po++ = (ul << 16) | sl[us[i] + j];
+    // order inside each (width, class) group: ascending global index (consecutive lanes gather
+    // consecutive addresses).  A bank-aware local permutation of this order was tried: it cut the
+    // shared-memory conflicts of the slot stores/loads by 20% but cost more in global-load sectors
+    // (measured 0.58 ms vs 0.54 ms per apply), so plain ascending order stays.
+    std::vector<uint32_t> grp[3][2];
+    for (size_t i = 0; i < ud.size(); i++) grp[width_of(us[i + 1] - us[i])][multi[ud[i]] ? 1 : 0].push_back((uint32_t)i);
+    const uint32_t base[3] = {0, n1, n1 + n2};
+    for (int w = 0; w < 3; w++)
+      for (int cls = 0; cls < 2; cls++) {
+        uint32_t r = cls ? cnt[w][0] : 0;  // index inside the width section
+        for (uint32_t i : grp[w][cls]) {
+          const int ns = us[i + 1] - us[i];
+          const uint32_t ul = base[w] + r;  // patch-local dof index
+          pd[ul] = ud[i];
+          if (w == 0) p16[r] = sl[us[i]];
+          else if (w == 1) p32[r] = (uint32_t)sl[us[i]] | ((uint32_t)sl[us[i] + 1] << 16);
+          else {
+            uint64_t v = ~0ULL;
+            for (int j = 0; j < ns; j++) {
+              if (j < 4) v = (v & ~(0xffffULL << (16 * j))) | ((uint64_t)sl[us[i] + j] << (16 * j));
+              else *po++ = (ul << 16) | sl[us[i] + j];
+            }
+            p64[r] = v;
+          }
+          r++;
         }
-        p64[r] = v;
       }
-    }
   });
   return 0;
 }
