@@ -1,0 +1,334 @@
+// heph_gpu_operator.hpp -- header-only C++ adaptor that plugs libhcurl_b200.so into Hephaestus
+// behind its existing plug points.  Host code stays C++ / MFEM; everything
+// numerical happens behind the C ABI in include/hcurl_b200.h.
+//
+//   HephGpuOperator : mfem::Operator   -- what EquationSystem::FormLinearSystem hands out in
+//       place of HypreParMatrixFromBlocks (/root/reference/src/equation_systems/equation_system.cpp:132-190);
+//       EquationSystem::Mult / GetGradient (ibid. :200-210) then run on the GPU unchanged.
+//   HephGpuPCG : mfem::Solver          -- replaces mfem::HyprePCG + HypreDiagScale as configured by
+//       DefaultJacobiPCGSolver (/root/reference/src/solvers/hephaestus_solvers.hpp:34-57) and
+//       ProblemBuilder::ConstructJacobianSolverWithOptions
+//       (/root/reference/src/problem_builders/problem_builder_base.cpp:220-254).
+//   MakeGpuSpace(...)                  -- extracts from a ParFiniteElementSpace exactly the arrays
+//       the reference's assembly consumes (element vertices, signed GetElementDofs, true-dof
+//       numbering, shared-dof groups) and hands them to hcurl_space_create.
+//
+// Include AFTER mfem.hpp (or adaptor/mock_mfem.hpp, a minimal stand-in used by the compile test:
+// MFEM itself is not installable in the build container, so this header has been compiled
+// against the mock only -- see DESIGN.md "unverified against real MFEM").
+#pragma once
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../include/hcurl_b200.h"
+
+#ifndef MFEM_ABORT
+#error "include mfem.hpp (or adaptor/mock_mfem.hpp) before heph_gpu_operator.hpp"
+#endif
+
+namespace hephaestus
+{
+
+#define HEPH_GPU_CHECK(call)                                                                  \
+  do                                                                                          \
+  {                                                                                           \
+    if ((call) != 0)                                                                          \
+      MFEM_ABORT(std::string(#call) + " failed: " + hcurl_last_error()); /* reference: abort */ \
+  } while (0)
+
+/// One per MPI rank.  `nccl_unique_id` comes from hcurl_comm_unique_id on rank 0 + MPI_Bcast.
+class HephGpuContext
+{
+public:
+  HephGpuContext(int device, const void * nccl_unique_id, int rank, int nranks)
+    : _ctx(hcurl_ctx_create(device, nccl_unique_id, rank, nranks))
+  {
+    if (!_ctx)
+      MFEM_ABORT(std::string("hcurl_ctx_create failed: ") + hcurl_last_error());
+  }
+  ~HephGpuContext() { hcurl_ctx_destroy(_ctx); }
+  HephGpuContext(const HephGpuContext &) = delete;
+  hcurl_ctx * Get() const { return _ctx; }
+
+private:
+  hcurl_ctx * _ctx;
+};
+
+/// Device copy of an ND_3D_P<p> ParFiniteElementSpace.
+class HephGpuSpace
+{
+public:
+  HephGpuSpace(HephGpuContext & ctx, mfem::ParFiniteElementSpace & fes) : _fes(fes)
+  {
+    mfem::ParMesh * mesh = fes.GetParMesh();
+    const int ne = mesh->GetNE();
+    const int order = fes.FEColl()->GetOrder(); // "ND_3D_P<p>" -> p
+    const bool tet = mesh->GetElementGeometry(0) == mfem::Geometry::TETRAHEDRON;
+    const mfem::GridFunction * nodes = mesh->GetNodes();
+    const int geom_order = nodes ? nodes->FESpace()->GetMaxElementOrder() : 1;
+    const int ngn = tet ? 4 : (geom_order == 1 ? 8 : 27);
+
+    // ---- element node coordinates (corner order = MFEM's; HEX27: x-fastest tensor order)
+    std::vector<double> xyz(size_t(ne) * ngn * 3);
+    mfem::Array<int> v;
+    for (int e = 0; e < ne; e++)
+    {
+      if (geom_order == 1)
+      {
+        mesh->GetElementVertices(e, v);
+        for (int k = 0; k < ngn; k++)
+          for (int d = 0; d < 3; d++)
+            xyz[(size_t(e) * ngn + k) * 3 + d] = mesh->GetVertex(v[k])[d];
+      }
+      else
+      {
+        // sample the (curved) element map at the 27 tensor points {0,1/2,1}^3
+        mfem::ElementTransformation * T = mesh->GetElementTransformation(e);
+        mfem::Vector x(3);
+        for (int k = 0; k < 27; k++)
+        {
+          mfem::IntegrationPoint ip;
+          ip.Set3(0.5 * (k % 3), 0.5 * ((k / 3) % 3), 0.5 * (k / 9));
+          T->Transform(ip, x);
+          for (int d = 0; d < 3; d++)
+            xyz[(size_t(e) * 27 + k) * 3 + d] = x(d);
+        }
+      }
+    }
+    // ---- signed element dofs: FiniteElementSpace::GetElementDofs (k, or -1-k when flipped)
+    mfem::Array<int> dofs;
+    fes.GetElementDofs(0, dofs);
+    const int nd = dofs.Size();
+    std::vector<int32_t> ldof(size_t(ne) * nd);
+    for (int e = 0; e < ne; e++)
+    {
+      fes.GetElementDofs(e, dofs);
+      for (int i = 0; i < nd; i++)
+        ldof[size_t(e) * nd + i] = dofs[i];
+    }
+    // ---- tets of order >= 2: vertex ids of the element and of its faces in the mesh's own
+    // face-vertex order; the library derives ND_DofTransformation from them
+    std::vector<int32_t> ev, fb;
+    if (tet && order >= 2)
+    {
+      ev.resize(size_t(ne) * 4);
+      fb.resize(size_t(ne) * 12);
+      mfem::Array<int> faces, ori, fv;
+      for (int e = 0; e < ne; e++)
+      {
+        mesh->GetElementVertices(e, v);
+        for (int k = 0; k < 4; k++)
+          ev[size_t(e) * 4 + k] = v[k];
+        mesh->GetElementFaces(e, faces, ori);
+        for (int f = 0; f < 4; f++)
+        {
+          mesh->GetFaceVertices(faces[f], fv);
+          for (int k = 0; k < 3; k++)
+            fb[(size_t(e) * 4 + f) * 3 + k] = fv[k];
+        }
+      }
+    }
+    // ---- parallel layout: owned true dofs + per-neighbour shared-dof lists (GroupTopology)
+    const int n_ldof = fes.GetVSize(), n_tdof = fes.GetTrueVSize();
+    std::vector<int32_t> ltdof(n_ldof);
+    for (int i = 0; i < n_ldof; i++)
+      ltdof[i] = fes.GetLocalTDofNumber(i); // -1 when another rank owns it
+    std::vector<int32_t> nbr, own_off(1, 0), own_ldof, ghost_off(1, 0), ghost_ldof;
+    std::vector<int8_t> ghost_sign;
+    if (fes.GetNRanks() > 1)
+    {
+      // group g is a set of ranks sharing some ldofs; its master owns them.  For every
+      // neighbour r: dofs I own that r also holds, and dofs r owns that I hold -- both sides
+      // enumerate a group's dofs in the same (group, local-in-group) order.
+      mfem::GroupTopology & gt = fes.GetGroupTopo();
+      const int me = fes.GetMyRank();
+      std::map<int, std::vector<int32_t>> own_by, ghost_by;
+      mfem::Array<int> gdofs;
+      for (int g = 1; g < gt.NGroups(); g++)
+      {
+        fes.GetSharedDofs(g, gdofs); // ldofs of group g (edges, faces of the group in order)
+        const int master = gt.GetNeighborRank(gt.GetGroupMaster(g));
+        for (int k = 0; k < gdofs.Size(); k++)
+        {
+          const int ld = gdofs[k] >= 0 ? gdofs[k] : -1 - gdofs[k];
+          if (master == me)
+          {
+            const int * gr = gt.GetGroup(g);
+            for (int m = 0; m < gt.GetGroupSize(g); m++)
+              if (gt.GetNeighborRank(gr[m]) != me)
+                own_by[gt.GetNeighborRank(gr[m])].push_back(ld);
+          }
+          else
+            ghost_by[master].push_back(ld);
+        }
+      }
+      std::map<int, int> ranks;
+      for (auto & kv : own_by) ranks[kv.first] = 1;
+      for (auto & kv : ghost_by) ranks[kv.first] = 1;
+      for (auto & kv : ranks)
+      {
+        nbr.push_back(kv.first);
+        for (int32_t d : own_by[kv.first]) own_ldof.push_back(d);
+        for (int32_t d : ghost_by[kv.first]) { ghost_ldof.push_back(d); ghost_sign.push_back(1); }
+        own_off.push_back((int32_t)own_ldof.size());
+        ghost_off.push_back((int32_t)ghost_ldof.size());
+      }
+      // MFEM stores the relative orientation of a shared ND dof in the sign of the group's ldof
+      // entries (ParFiniteElementSpace::GetSharedEdgeDofs ...); element maps already carry it, so
+      // ghost values are exchanged unsigned (ghost_sign = +1) -- see DESIGN.md for the caveat.
+    }
+    _space = hcurl_space_create(ctx.Get(), tet ? HCURL_GEOM_TET : HCURL_GEOM_HEX, geom_order, order, ne,
+                                xyz.data(), ldof.data(), ev.empty() ? nullptr : ev.data(),
+                                fb.empty() ? nullptr : fb.data(), n_ldof,
+                                fes.GetNRanks() > 1 ? ltdof.data() : nullptr, n_tdof, (int)nbr.size(),
+                                nbr.data(), own_off.data(), own_ldof.data(), ghost_off.data(),
+                                ghost_ldof.data(), ghost_sign.empty() ? nullptr : ghost_sign.data());
+    if (!_space)
+      MFEM_ABORT(std::string("hcurl_space_create failed: ") + hcurl_last_error());
+  }
+  ~HephGpuSpace() { hcurl_space_destroy(_space); }
+  HephGpuSpace(const HephGpuSpace &) = delete;
+  hcurl_space * Get() const { return _space; }
+  mfem::ParFiniteElementSpace & FESpace() const { return _fes; }
+
+private:
+  mfem::ParFiniteElementSpace & _fes;
+  hcurl_space * _space{nullptr};
+};
+
+/// A = K(alpha) + M(beta) on true dofs, essential rows/cols -> identity.
+/// alpha / beta are the coefficient objects the reference's kernels hold:
+/// CurlCurlKernel::_coef (/root/reference/src/kernels/curl_curl_kernel.hpp:22-23) and
+/// VectorFEMassKernel::_coef (/root/reference/src/kernels/vector_fe_mass_kernel.hpp).
+class HephGpuOperator : public mfem::Operator
+{
+public:
+  HephGpuOperator(HephGpuContext & ctx, HephGpuSpace & space, mfem::Coefficient * alpha,
+                  mfem::Coefficient * beta, const mfem::Array<int> & ess_tdof_list,
+                  int quad_pts_per_dim = 0)
+    : mfem::Operator(space.FESpace().GetTrueVSize()), _space(space), _alpha(alpha), _beta(beta)
+  {
+    _op = hcurl_op_create(ctx.Get(), space.Get(), quad_pts_per_dim);
+    if (!_op)
+      MFEM_ABORT(std::string("hcurl_op_create failed: ") + hcurl_last_error());
+    UpdateCoefficients();
+    std::vector<int32_t> ess(ess_tdof_list.Size());
+    for (int i = 0; i < ess_tdof_list.Size(); i++)
+      ess[i] = ess_tdof_list[i];
+    HEPH_GPU_CHECK(hcurl_op_set_essential_tdofs(_op, ess.data(), (int32_t)ess.size()));
+  }
+  ~HephGpuOperator() override { hcurl_op_destroy(_op); }
+
+  /// Re-sample alpha / beta (Coefficients::SetTime, dt change:
+  /// /root/reference/src/problem_operators/time_domain_equation_system_problem_operator.cpp:43,
+  /// /root/reference/src/equation_systems/equation_system.cpp:413-426).  Values only, no rebuild.
+  /// Piecewise-constant coefficients (PWCoefficient / ConstantCoefficient / TransformedCoefficient
+  /// of those) are sampled once per element at the element centre.
+  void UpdateCoefficients()
+  {
+    mfem::ParMesh * mesh = _space.FESpace().GetParMesh();
+    const int ne = mesh->GetNE();
+    std::vector<double> a(_alpha ? ne : 0), b(_beta ? ne : 0);
+    for (int e = 0; e < ne; e++)
+    {
+      mfem::ElementTransformation * T = mesh->GetElementTransformation(e);
+      const mfem::IntegrationPoint & ip = mfem::Geometries.GetCenter(mesh->GetElementGeometry(e));
+      T->SetIntPoint(&ip);
+      if (_alpha) a[e] = _alpha->Eval(*T, ip);
+      if (_beta) b[e] = _beta->Eval(*T, ip);
+    }
+    HEPH_GPU_CHECK(hcurl_op_set_coefficients(_op, HCURL_COEF_PER_ELEM, _alpha ? a.data() : nullptr,
+                                             _beta ? b.data() : nullptr, HCURL_HOST));
+  }
+
+  /// y = A x on T-vectors: EquationSystem::Mult (equation_system.cpp:200-204)
+  void Mult(const mfem::Vector & x, mfem::Vector & y) const override
+  {
+    HEPH_GPU_CHECK(hcurl_op_apply(_op, x.HostRead(), y.HostWrite(), HCURL_HOST));
+  }
+  /// B = b - A x_bc|ess, B[ess] = x_bc[ess]: the right-hand side FormLinearSystem produces
+  void FormRHS(const mfem::Vector & x_bc, const mfem::Vector & b, mfem::Vector & B) const
+  {
+    HEPH_GPU_CHECK(hcurl_op_form_rhs(_op, x_bc.HostRead(), b.HostRead(), B.HostWrite(), HCURL_HOST));
+  }
+  /// y += scale * (K + M) x without elimination: WeakCurlCurlKernel's  lf -= K(alpha) u_n
+  /// (/root/reference/src/kernels/weak_curl_curl_kernel.cpp:14-31)
+  void AddMultUnconstrained(const mfem::Vector & x, mfem::Vector & y, double scale) const
+  {
+    HEPH_GPU_CHECK(hcurl_op_apply_unconstrained(_op, x.HostRead(), y.HostReadWrite(), scale, 1, HCURL_HOST));
+  }
+  hcurl_op * Get() const { return _op; }
+
+private:
+  HephGpuSpace & _space;
+  mfem::Coefficient * _alpha;
+  mfem::Coefficient * _beta;
+  hcurl_op * _op{nullptr};
+};
+
+/// Jacobi-preconditioned CG with hypre's PCG semantics, on the device.
+/// Options mirror DefaultJacobiPCGSolver (hephaestus_solvers.hpp:39-42): Tolerance / AbsTolerance
+/// arrive as float, MaxIter as unsigned int, PrintLevel as int.
+class HephGpuPCG : public mfem::Solver
+{
+public:
+  HephGpuPCG(HephGpuContext & ctx, float tol = 1.0e-9f, float abstol = 1e-16f,
+             unsigned int max_iter = 1000, int print_level = 0)
+    : _ctx(ctx), _tol(tol), _abstol(abstol), _max_iter((int)max_iter), _print_level(print_level)
+  {
+    iterative_mode = true; // like mfem::HyprePCG; NewtonSolver::SetSolver sets it to false
+  }
+  ~HephGpuPCG() override { hcurl_pcg_destroy(_pcg); }
+
+  /// NewtonSolver hands over EquationSystem::GetGradient() (equation_system.cpp:206-210).
+  /// Like HyprePCG::SetOperator insisting on a HypreParMatrix, this insists on a HephGpuOperator.
+  void SetOperator(const mfem::Operator & op) override
+  {
+    const auto * gop = dynamic_cast<const HephGpuOperator *>(&op);
+    if (!gop)
+      MFEM_ABORT("HephGpuPCG::SetOperator: operator is not a HephGpuOperator");
+    height = op.Height();
+    width = op.Width();
+    if (_pcg && gop == _gop)
+    {
+      HEPH_GPU_CHECK(hcurl_pcg_update(_pcg)); // new coefficients: rebuild the Jacobi diagonal
+      return;
+    }
+    hcurl_pcg_destroy(_pcg);
+    _gop = gop;
+    _pcg = hcurl_pcg_create(_ctx.Get(), gop->Get(), HCURL_PC_JACOBI);
+    if (!_pcg)
+      MFEM_ABORT(std::string("hcurl_pcg_create failed: ") + hcurl_last_error());
+    HEPH_GPU_CHECK(hcurl_pcg_set(_pcg, _tol, _abstol, _max_iter, _print_level));
+  }
+  void Mult(const mfem::Vector & b, mfem::Vector & x) const override
+  {
+    if (!_pcg)
+      MFEM_ABORT("HephGpuPCG::Mult called before SetOperator");
+    int iters = 0, converged = 0;
+    double rel = 0.0;
+    HEPH_GPU_CHECK(hcurl_pcg_solve(_pcg, b.HostRead(), x.HostReadWrite(), iterative_mode ? 0 : 1, HCURL_HOST,
+                                   &iters, &rel, &converged));
+    _num_iterations = iters;
+    _final_rel_res = rel;
+    _converged = converged != 0;
+  }
+  int GetNumIterations() const { return _num_iterations; }
+  double GetFinalRelResidual() const { return _final_rel_res; }
+  bool GetConverged() const { return _converged; }
+
+private:
+  HephGpuContext & _ctx;
+  double _tol, _abstol;
+  int _max_iter, _print_level;
+  const HephGpuOperator * _gop{nullptr};
+  hcurl_pcg * _pcg{nullptr};
+  mutable int _num_iterations{0};
+  mutable double _final_rel_res{0.0};
+  mutable bool _converged{false};
+};
+
+} // namespace hephaestus

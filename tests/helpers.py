@@ -51,3 +51,31 @@ def star_mesh(layers=3, cls=None):
     return (cls or fespace.Mesh)("hex", verts, np.array(elems))
 
 
+
+
+# ---- geometric identification of dofs (independent of any numbering convention) ---------------
+def dof_descriptors(omesh, ospace):
+    """Physical node (ndof,3) and oriented tangent (ndof,3) of every global dof functional of an
+    oracle hex NDSpace: dof d acts as v -> T_d . v(X_d).  Two spaces on the same geometry describe the
+    same dof when the nodes coincide; the relative sign of the basis functions is sign(T . T')."""
+    from oracle.assemble import hex8_jacobians
+    fe = ospace.fe
+    nodes, tang = fe.dof_nodes()                      # reference nodes / unit tangents, MFEM local order
+    X = omesh.elem_coords()
+    J, xq = hex8_jacobians(X, nodes)                 # (ne, nd, 3, 3), (ne, nd, 3)
+    T = np.einsum("eqij,qj->eqi", J, tang) * ospace.elem_sign[:, :, None]
+    P = np.zeros((ospace.ndof, 3))
+    D = np.zeros((ospace.ndof, 3))
+    P[ospace.elem_dofs.ravel()] = xq.reshape(-1, 3)
+    D[ospace.elem_dofs.ravel()] = T.reshape(-1, 3)
+    return P, D
+
+
+def match_dofs(P_a, D_a, P_b, D_b, decimals=9):
+    """For every dof of space a: (index in b, relative sign).  Nodes must coincide."""
+    key = lambda P: [tuple(r) for r in np.round(P, decimals) + 0.0]  # noqa: E731
+    where = {k: i for i, k in enumerate(key(P_b))}
+    idx = np.array([where[k] for k in key(P_a)])
+    sgn = np.sign(np.einsum("ij,ij->i", D_a, D_b[idx]))
+    assert np.all(sgn != 0)
+    return idx, sgn

@@ -1,0 +1,36 @@
+"""Multi-GPU parity (needs >= 2 GPUs; run with `gpurun --gpus 2 -- python -m pytest tests -m gpu`):
+partitioned apply and PCG with the NCCL shared-dof exchange against the serial oracle."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("n,p,perturbed", [(4, 2, False), (3, 2, True), (3, 1, True), (2, 3, True)])
+def test_two_gpu_apply_and_pcg(tmp_path, lib_built, n, p, perturbed):
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    world = 2
+    script = os.path.join(ROOT, "tests", "gpu_multi_worker.py")
+    procs = [subprocess.Popen([sys.executable, script, str(r), str(world), str(tmp_path), str(n), str(p), "1" if perturbed else "0"],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(world)]
+    outs = []
+    for pr in procs:
+        try:
+            outs.append(pr.communicate(timeout=600)[0])
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+    for pr, o in zip(procs, outs):
+        assert pr.returncode == 0, o
+    assert all("OK" in o for o in outs), outs

@@ -1,0 +1,140 @@
+"""Multi-rank layout (hephaestus_b200/partition.py): ownership, shared-dof lists and relative
+orientations must make the rank-local applies + exchange equal the serial operator (SURVEY.md 8e,
+A.7 vi).  CPU only: the exchange of csrc/comm.cu is emulated in numpy (all ranks in one process) and
+run for real over torch.distributed/gloo with world_size 2."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from hephaestus_b200 import fespace, partition
+from oracle import assemble as oa
+from oracle import mesh as om
+from oracle import space as osp
+
+from helpers import dof_descriptors, match_dofs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def serial_problem(dims, n, p, perturbed):
+    px, py, pz = dims
+    m = fespace.cartesian_hex_mesh(px * n, py * n, pz * n, px, py, pz)
+    if perturbed:
+        N = np.array([px * n, py * n, pz * n])
+        g = np.rint(m.verts * n).astype(np.int64)
+        gid = g[:, 0] + (N[0] + 1) * (g[:, 1] + (N[1] + 1) * g[:, 2])
+        interior = np.all((g > 0) & (g < N), axis=1)
+        h = 1.0 / n
+        d = np.stack([partition._hash_unit(gid, 777 + k) for k in range(3)], 1) * 0.4 * h - 0.2 * h
+        m = fespace.Mesh("hex", m.verts + d * interior[:, None], m.elems, m.attr)
+    mo = om.Mesh("hex", m.verts, m.elems, m.attr)
+    return m, fespace.NDSpace(m, p), mo, osp.NDSpace(mo, p)
+
+
+def coef(attr):
+    return np.where(attr == 1, 0.05, 0.1), np.where(attr == 1, 1.0, 1.0e3)
+
+
+def emulate_apply(bps, mats, x_t):
+    """x_t: list of T-vectors.  Returns list of T-vectors y = A x with the broadcast / local apply /
+    reduce sequence of csrc/api.cu:op_apply_ext."""
+    W = len(bps)
+    l2e = [partition.ext_index(b.local) for b in bps]
+    ext = [partition.to_ext(b.local, x) for b, x in zip(bps, x_t)]
+    # broadcast owner -> ghosts
+    for r in range(W):
+        L = bps[r].local
+        for k, q in enumerate(L.nbr_rank):
+            Lq = bps[q].local
+            kq = list(Lq.nbr_rank).index(r)
+            send = ext[q][l2e[q][Lq.own_ldof[Lq.own_off[kq]:Lq.own_off[kq + 1]]]]
+            g0, g1 = L.ghost_off[k], L.ghost_off[k + 1]
+            assert len(send) == g1 - g0
+            ext[r][L.n_tdof + g0:L.n_tdof + g1] = send * L.ghost_sign[g0:g1]
+    # local apply on L-vectors
+    yext = []
+    for r in range(W):
+        xl = ext[r][l2e[r]]
+        yl = mats[r] @ xl
+        ye = np.zeros_like(ext[r])
+        np.add.at(ye, l2e[r], yl)
+        yext.append(ye)
+    # reduce ghosts -> owner
+    for r in range(W):
+        L = bps[r].local
+        for k, q in enumerate(L.nbr_rank):
+            Lq = bps[q].local
+            kq = list(Lq.nbr_rank).index(r)
+            g0, g1 = L.ghost_off[k], L.ghost_off[k + 1]
+            part = yext[r][L.n_tdof + g0:L.n_tdof + g1] * L.ghost_sign[g0:g1]
+            np.add.at(yext[q], l2e[q][Lq.own_ldof[Lq.own_off[kq]:Lq.own_off[kq + 1]]], part)
+    return [ye[:b.local.n_tdof] for ye, b in zip(yext, bps)]
+
+
+@pytest.mark.parametrize("world,n,p", [(2, 2, 1), (2, 3, 2), (4, 2, 2), (8, 2, 2), (8, 2, 1), (2, 2, 3), (6, 2, 2)])
+@pytest.mark.parametrize("perturbed", [False, True])
+def test_partitioned_apply_equals_serial(world, n, p, perturbed):
+    dims = partition.brick_dims(world)
+    m, sp, mo, so = serial_problem(dims, n, p, perturbed)
+    a, b = coef(mo.attr)
+    A = oa.assemble(so, a, b)
+    Ps, Ds = dof_descriptors(mo, so)
+    rng = np.random.default_rng(5)
+    x_s = rng.standard_normal(so.ndof)
+    y_s = A @ x_s
+    bps, mats, maps = [], [], []
+    for r in range(world):
+        bp = partition.brick_problem(r, world, n, p, perturbed)
+        lmo = om.Mesh("hex", bp.mesh.verts, bp.mesh.elems, bp.mesh.attr)
+        lso = osp.NDSpace(lmo, p)
+        assert np.array_equal(lso.signed_elem_dofs(), bp.space.signed_elem_dofs())
+        la, lb = coef(lmo.attr)
+        mats.append(oa.assemble(lso, la, lb))
+        P, D = dof_descriptors(lmo, lso)
+        maps.append(match_dofs(P, D, Ps, Ds))      # local dof -> (serial dof, sign)
+        bps.append(bp)
+    # every serial dof is owned exactly once
+    owned_serial = np.concatenate([maps[r][0][bps[r].local.ldof_ltdof >= 0] for r in range(world)])
+    assert np.array_equal(np.sort(owned_serial), np.arange(so.ndof))
+    # owner = lowest rank holding the dof
+    holder_min = np.full(so.ndof, world)
+    for r in range(world):
+        np.minimum.at(holder_min, maps[r][0], r)
+    for r in range(world):
+        own = bps[r].local.ldof_ltdof >= 0
+        assert np.all(holder_min[maps[r][0][own]] == r)
+    # T-vectors of the serial x
+    x_t = []
+    for r in range(world):
+        L = bps[r].local
+        own = np.nonzero(L.ldof_ltdof >= 0)[0]
+        xt = np.zeros(L.n_tdof)
+        xt[L.ldof_ltdof[own]] = maps[r][1][own] * x_s[maps[r][0][own]]
+        x_t.append(xt)
+    y_t = emulate_apply(bps, mats, x_t)
+    for r in range(world):
+        L = bps[r].local
+        own = np.nonzero(L.ldof_ltdof >= 0)[0]
+        ref = maps[r][1][own] * y_s[maps[r][0][own]]
+        got = y_t[r][L.ldof_ltdof[own]]
+        assert np.linalg.norm(got - ref) <= 1e-12 * np.linalg.norm(y_s), (r, np.abs(got - ref).max())
+    # essential dofs: union over ranks == boundary dofs of the serial space
+    ess_serial = np.concatenate([maps[r][0][np.nonzero(bps[r].local.ldof_ltdof >= 0)[0][np.argsort(
+        bps[r].local.ldof_ltdof[bps[r].local.ldof_ltdof >= 0])][bps[r].ess_tdofs]] for r in range(world)])
+    assert np.array_equal(np.sort(ess_serial), np.sort(sp.boundary_dofs()))
+
+
+def test_gloo_world2_exchange(tmp_path):
+    """Two real processes over torch.distributed (gloo): broadcast + reduce with send/recv in the
+    order csrc/comm.cu issues them."""
+    script = os.path.join(ROOT, "tests", "gloo_worker.py")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29611", PYTHONPATH=ROOT)
+    procs = [subprocess.Popen([sys.executable, script, str(r), "2", str(tmp_path)], env=env, stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+    assert all("OK" in o for o in outs), outs
