@@ -1,0 +1,145 @@
+"""Method-of-manufactured-solutions pieces of the oracle (TEST INFRASTRUCTURE ONLY).
+
+Restates, on the CPU, the setting the reference's own MMS tests pin the H(curl) path with
+(/root/reference/test/integration/test_aform_source.cpp:19-49 exact solution / source / mu,
+:130-208 the refinement loop and the accepted convergence window r in (1.85, 3.0);
+test_hform_source.cpp:20-50,143-220 is the same with a variable sigma):
+
+  * the time-discretised weak form of the HCurl formulations
+    (/root/reference/src/formulations/HCurl/hcurl_formulation.cpp:1-38):
+        (beta k, v) + (alpha dt curl k, curl v) = (s_{n+1}, v) - (alpha curl u_n, curl v),
+        u_{n+1} = u_n + dt k,   essential BC on the tangential trace of k;
+  * the domain load vector  (s, v)  [mfem::VectorFEDomainLFIntegrator, MFEM-upstream];
+  * uniform tetrahedral refinement (mfem::Mesh::UniformRefinement, 8 children per tet) -- only
+    the resulting mesh size matters for a convergence RATE;
+  * the L2 error  ||u_h - u||  [GridFunction::ComputeL2Error, MFEM-upstream].
+"""
+import numpy as np
+
+from .assemble import hex8_jacobians, hex_tensor_rule, tet_jacobians
+from .mesh import Mesh
+from .quadrature import tet_rule
+
+
+def _rule_and_jac(space, degree):
+    mesh = space.mesh
+    X = mesh.elem_coords()
+    if mesh.kind == "tet":
+        pts, wts = tet_rule(degree)
+        J, xq = tet_jacobians(X, pts)
+    else:
+        assert mesh.geom_nodes is None
+        pts, wts = hex_tensor_rule(degree // 2 + 1)
+        J, xq = hex8_jacobians(X, pts)
+    return pts, wts, J, xq
+
+
+def _to_global(space, loc):
+    """element-local load/test vectors -> global (transpose of x_local = R x_global)"""
+    if space.elem_R is not None:
+        return np.einsum("eki,ek->ei", space.elem_R, loc)
+    return loc * space.elem_sign
+
+
+def _to_local(space, x):
+    xe = x[space.elem_dofs]
+    if space.elem_R is not None:
+        return np.einsum("eij,ej->ei", space.elem_R, xe)
+    return xe * space.elem_sign
+
+
+def load_vector(space, func, degree=None):
+    """b_i = int f . phi_i  with phi = J^-T phi_hat (covariant Piola)."""
+    degree = degree if degree is not None else 2 * space.p + 3
+    pts, wts, J, xq = _rule_and_jac(space, degree)
+    V, _ = space.fe.shape_and_curl(pts)
+    det = np.linalg.det(J)
+    F = np.asarray(func(xq.reshape(-1, 3))).reshape(xq.shape)
+    JiF = np.linalg.solve(J, F[..., None])[..., 0]  # J^-1 f, so that (J^-T v).f = v.(J^-1 f)
+    loc = np.einsum("q,eq,eqd,qnd->en", wts, det, JiF, V)
+    out = np.zeros(space.ndof)
+    np.add.at(out, space.elem_dofs.reshape(-1), _to_global(space, loc).reshape(-1))
+    return out
+
+
+def l2_error(space, x, func, degree=None):
+    degree = degree if degree is not None else 2 * space.p + 3
+    pts, wts, J, xq = _rule_and_jac(space, degree)
+    V, _ = space.fe.shape_and_curl(pts)
+    det = np.linalg.det(J)
+    uh_ref = np.einsum("en,qnd->eqd", _to_local(space, x), V)
+    uh = np.linalg.solve(np.swapaxes(J, -1, -2), uh_ref[..., None])[..., 0]  # J^-T u_hat
+    U = np.asarray(func(xq.reshape(-1, 3))).reshape(xq.shape)
+    return float(np.sqrt(np.einsum("q,eq,eqd->", wts, np.abs(det), (uh - U) ** 2)))
+
+
+def refine_tets(mesh):
+    """Uniform (red) refinement: every tet -> 4 corner tets + 4 from the inner octahedron."""
+    verts = [tuple(v) for v in mesh.verts]
+    mid = {}
+
+    def m(a, b):
+        key = (min(a, b), max(a, b))
+        if key not in mid:
+            mid[key] = len(verts)
+            verts.append(tuple(0.5 * (mesh.verts[a] + mesh.verts[b])))
+        return mid[key]
+
+    elems, attr = [], []
+    for ev, a in zip(mesh.elems, mesh.attr):
+        v0, v1, v2, v3 = (int(i) for i in ev)
+        m01, m02, m03, m12, m13, m23 = m(v0, v1), m(v0, v2), m(v0, v3), m(v1, v2), m(v1, v3), m(v2, v3)
+        kids = [[v0, m01, m02, m03], [m01, v1, m12, m13], [m02, m12, v2, m23], [m03, m13, m23, v3]]
+        # inner octahedron: three possible diagonals; like MFEM's UniformRefinement (which picks the
+        # split by child aspect ratio [MFEM-upstream]) take the one whose children are best shaped:
+        # smallest worst-case sigma_max/sigma_min of the child Jacobians.  A fixed diagonal degrades
+        # the children of non-Kuhn-ordered tets and with it the pre-asymptotic error.
+        P = np.array([verts[i] for i in (m01, m02, m03, m12, m13, m23)])
+        ids = (m01, m02, m03, m12, m13, m23)
+        options = [((0, 5), (1, 2, 4, 3)), ((1, 4), (0, 2, 5, 3)), ((2, 3), (0, 1, 5, 4))]
+        best = None
+        for (da, db), ring in options:
+            worst = 0.0
+            for i in range(4):
+                J = np.array([P[db] - P[da], P[ring[i]] - P[da], P[ring[(i + 1) % 4]] - P[da]])
+                sv = np.linalg.svd(J, compute_uv=False)
+                worst = max(worst, sv[0] / sv[2])
+            if best is None or worst < best[0] - 1e-12:
+                best = (worst, da, db, ring)
+        _, da, db, ring = best
+        for i in range(4):
+            kids.append([ids[da], ids[db], ids[ring[i]], ids[ring[(i + 1) % 4]]])
+        elems += kids
+        attr += [a] * 8
+    V = np.array(verts)
+    E = np.array(elems)
+    # positive orientation
+    X = V[E]
+    neg = np.linalg.det(X[:, 1:] - X[:, :1]) < 0
+    E[neg] = E[neg][:, [0, 1, 3, 2]]
+    return Mesh("tet", V, E, attr)
+
+
+# ---- the reference's manufactured problem (test_aform_source.cpp:19-49) ---------------------
+def adot_exact(X):
+    out = np.zeros_like(X)
+    out[:, 0] = np.sin(np.pi * X[:, 1]) * np.sin(np.pi * X[:, 2])
+    return out
+
+
+def a_exact(X, t):
+    return adot_exact(X) * t
+
+
+def mu_expr(X, attr=None):
+    return 1.0 / (1.0 + 0.5 * np.cos(np.pi * X[:, 0]) * np.cos(np.pi * X[:, 1]))
+
+
+def source_field(X, t):
+    vs, pi = 0.5, np.pi
+    x, y, z = X[:, 0], X[:, 1], X[:, 2]
+    f = np.zeros_like(X)
+    f[:, 0] = t * pi * pi * np.sin(pi * y) * np.sin(pi * z) * (3 * vs * np.cos(pi * x) * np.cos(pi * y) + 2) + np.sin(pi * y) * np.sin(pi * z)
+    f[:, 1] = -vs * pi * pi * t * np.sin(pi * x) * np.cos(pi * y) * np.cos(pi * y) * np.sin(pi * z)
+    f[:, 2] = -0.5 * vs * pi * pi * t * np.sin(pi * x) * np.sin(2 * pi * y) * np.cos(pi * z)
+    return f
