@@ -171,7 +171,14 @@ struct PatchArgs {
   double *y;
   double scale;
   uint32_t blob_cap_bytes;   // shared-memory room reserved for one blob (multiple of 16)
+  unsigned long long *prof;  // null, or 8 counters: cycles of thread 0 per phase summed over CTAs (scripts/phase_profile.py)
 };
+#define PROF_MARK(i)                                                                         \
+  if (a.prof && tid == 0) {                                                                  \
+    const long long t_now = clock64();                                                       \
+    atomicAdd(a.prof + (i), (unsigned long long)(t_now - t_prev));                           \
+    t_prev = t_now;                                                                          \
+  }
 
 // sign flip carried in bit 15 of a slot entry
 __device__ __forceinline__ double apply_sign(double v, uint32_t entry) {
@@ -210,6 +217,7 @@ hex_patch_modal_p2_kernel(const PatchArgs a) {
   double *E = reinterpret_cast<double *>(smem_raw + 16 + a.blob_cap_bytes);  // [54][FE + 1]
   const int tid = threadIdx.x;
   const int64_t k = blockIdx.x;
+  long long t_prev = a.prof ? clock64() : 0;
   if (tid == 0) {
     const uint32_t o0 = __ldg(a.blob_off + k), o1 = __ldg(a.blob_off + k + 1);
     blob_load_async(mbar, smem_raw + 16, a.blob + (size_t)o0 * 4, (o1 - o0) * 16u);
@@ -226,6 +234,7 @@ hex_patch_modal_p2_kernel(const PatchArgs a) {
   double M00 = __ldg(g + (6 + sym6(c, c)) * np), M01 = __ldg(g + (6 + sym6(c, c1)) * np), M02 = __ldg(g + (6 + sym6(c, c2)) * np);
   __syncthreads();  // mbarrier initialised
   mbar_wait(mbar, 0);
+  PROF_MARK(0)  // blob arrival
   const uint32_t U = B[0], b1 = B[1], b2 = B[1] + B[2], nP1 = B[4], nP2 = B[5], nP4 = B[6], nov = B[7];
   const uint32_t *dof = B + PatchHost::HDR;
   const uint16_t *e16 = reinterpret_cast<const uint16_t *>(B + B[8]);
@@ -270,6 +279,7 @@ hex_patch_modal_p2_kernel(const PatchArgs a) {
     }
   }
   __syncthreads();
+  PROF_MARK(1)  // phase A: gather
   // ---- element operator
   double *Eown = E + (c * 18) * ST + el;
   double Am[18];
@@ -306,6 +316,7 @@ hex_patch_modal_p2_kernel(const PatchArgs a) {
     modal_bwd(Yh, Y);
   }
   __syncthreads();  // everyone has read the modal coefficients
+  PROF_MARK(3)  // exchange + modal operator + backward transform
   if (ok) {
 #pragma unroll
     for (int t = 0; t < 18; t++) Eown[t * ST] = Y[t];
@@ -342,6 +353,7 @@ hex_patch_modal_p2_kernel(const PatchArgs a) {
     if (m & MAP_ESS) continue;
     atomicAdd(a.y + (m & MAP_IDX), apply_sign(E[e & 0x7fffu], e));
   }
+  PROF_MARK(5)  // phase C: scatter (thread 0's share)
 }
 
 // ---- setup ---------------------------------------------------------------------------------------
@@ -385,6 +397,7 @@ __global__ void patch_flag_kernel(const uint32_t *__restrict__ blob_off, const d
   }
 }
 
+unsigned long long *g_patch_prof = nullptr;  // set by hcurl_debug_patch_profile (debug.cu)
 static bool g_modal_set = false;
 static int set_modal_tables() {
   if (g_modal_set) return 0;
@@ -527,6 +540,7 @@ int hex_patch_launch(hcurl_op *op, bool constrained, const double *d_x, double *
   a.blob = (constrained && op->d_blob_ess) ? op->d_blob_ess : P.d_blob;
   a.blob_cap_bytes = (P.max_blob_words * 4 + 15u) & ~15u;
   a.edata = op->d_edataP; a.x = d_x; a.y = d_y; a.scale = scale;
+  a.prof = g_patch_prof;
   int rc = 1;
   if (P.FE == 32) rc = launch_fe<32, 8>(a, P.n_patch, accumulate, ctx->stream);
   else if (P.FE == 64) rc = launch_fe<64, 4>(a, P.n_patch, accumulate, ctx->stream);
