@@ -77,6 +77,7 @@ SIGNATURES = {
     "hcurl_host_patches_count": (C.c_int64, [_P]),
     "hcurl_host_patches_blob_words": (C.c_int64, [_P]),
     "hcurl_host_patches_max_blob_words": (C.c_int64, [_P]),
+    "hcurl_host_patches_max_dofs": (C.c_int64, [_P]),
     "hcurl_host_patches_copy": (C.c_int, [_P, _P, _P, _P]),
 }
 

@@ -5,10 +5,14 @@
 // EquationSystem::Mult, /root/reference/src/equation_systems/equation_system.cpp:200-204), organised
 // around what ncu showed to bound the element-wise kernels on sm_100a:
 //
-//  * L1tex lane rate of gathers / FP64 RED atomics  ->  one CTA per PATCH of FE adjacent elements
-//    (patch.cpp); x is gathered once per unique patch dof into a shared-memory E-vector, y is
-//    summed per patch dof from the E-vector, private dofs are plain stores, only patch-boundary
-//    dofs use RED.
+//  * L1tex lane rate of gathers / FP64 RED atomics  ->  one CTA works on PATCHES of FE adjacent elements
+//    (patch.cpp); x is gathered once per unique patch dof into a shared-memory staging vector, the
+//    element side pulls its 54 inputs from it through a per-slot table, y is summed per patch dof from
+//    a shared-memory E-vector; private dofs are plain stores, only patch-boundary dofs use RED.
+//  * memory latency (62 % of a CTA's life in the one-patch-per-CTA version, profiles/r1g)  ->  the
+//    kernel is PERSISTENT and software-pipelined: blob + geometry factors arrive by TMA bulk copies
+//    (cp.async.bulk + mbarrier) two patches ahead, the x gather of the next patch runs as 8-byte
+//    cp.async copies while the current patch is computed and scattered.
 //  * FP64 pipe (36 TFLOP/s measured; the quadrature-based apply needs 2916 DFMA / element)  ->
 //    on AFFINE elements with per-element coefficients the element operator is applied in an
 //    orthonormal Legendre (modal) basis, where the mass matrix is a restricted identity and the
@@ -19,8 +23,8 @@
 //    rotated frame (c, c+1, c+2) of its component c, so all warps run the same instruction stream.
 //
 // Thread layout: 3*FE threads; thread (c, e) owns component c of element e of the patch.
-// E-vector layout: E[(c*18 + t)*(FE+1) + e], t = i0 + 2*(i1 + 3*i2) with i0 the open index along axis c
-// (stride FE+1: lanes of the per-dof phases that hit different slots of one element fall in different banks).
+// E-vector layout (double2): E2[(c*9 + r)*(FE+1) + e] = slots t = 2r, 2r+1 of component c, t = i0 + 2*(i1 + 3*i2)
+// with i0 the open index along axis c: the element side moves 16-byte vectors, conflict-free.
 #include <cstdlib>
 
 #include "internal.h"
@@ -162,38 +166,41 @@ __device__ __forceinline__ void modal_op(const double *Am, const double *Bm, con
 }
 
 struct PatchArgs {
-  int64_t n_pos;             // n_patch * FE
-  const int32_t *perm;       // element at each patch position (-1 padding)
+  int64_t n_patch;
   const uint32_t *blob_off;  // [n_patch+1] in 16-byte units
   const uint32_t *blob;      // patch blobs (patch.cpp)
-  const double *edata;       // [12][n_pos] affine geometry factors in patch order
+  const double *edata;       // [n_patch][12][FE] affine geometry factors in patch order
   const double *x;
   double *y;
   double scale;
   uint32_t blob_cap_bytes;   // shared-memory room reserved for one blob (multiple of 16)
-  unsigned long long *prof;  // null, or 8 counters: cycles of thread 0 per phase summed over CTAs (scripts/phase_profile.py)
+  uint32_t xs_cap_bytes;     // room for the x staging vector (max patch dofs * 8, multiple of 16)
+  unsigned long long *prof;  // null, or 8 counters: cycles of thread 0 per phase summed over patches (scripts/phase_profile.py)
 };
 #define PROF_MARK(i)                                                                         \
-  if (a.prof && tid == 0) {                                                                  \
+  if (PROF && tid == 0) {                                                                    \
     const long long t_now = clock64();                                                       \
-    atomicAdd(a.prof + (i), (unsigned long long)(t_now - t_prev));                           \
+    prof_acc[i] += (unsigned long long)(t_now - t_prev);                                     \
     t_prev = t_now;                                                                          \
   }
 
-// sign flip carried in bit 15 of a slot entry
+// sign flip carried in bit 15 of a 16-bit table entry
 __device__ __forceinline__ double apply_sign(double v, uint32_t entry) {
   return __hiloint2double(__double2hiint(v) ^ (int)((entry << 16) & 0x80000000u), __double2loint(v));
 }
 
-// ---- bulk async copy (TMA engine, 1-D) of the patch blob into shared memory ----------------
+// ---- async copies -----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void blob_load_async(uint64_t *mbar, void *dst, const void *src, uint32_t bytes) {
-  const uint32_t mb = smem_addr(mbar);
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_init(uint64_t *mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(mbar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(mbar)), "r"(bytes) : "memory");
+}
+// 1-D bulk copy through the TMA engine, completion counted on an mbarrier
+__device__ __forceinline__ void bulk_load(uint64_t *mbar, void *dst, const void *src, uint32_t bytes) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
-               "l"(src), "r"(bytes), "r"(mb)
+               "l"(src), "r"(bytes), "r"(smem_addr(mbar))
                : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *mbar, uint32_t parity) {
@@ -206,166 +213,245 @@ __device__ __forceinline__ void mbar_wait(uint64_t *mbar, uint32_t parity) {
                  : "memory");
   } while (!done);
 }
+// 8-byte asynchronous gather global -> shared (LDGSTS), no register staging
+__device__ __forceinline__ void gather8_async(double *dst, const double *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void gather_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void gather_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-template <int FE, int MINB, bool ACC>
+// Persistent, software-pipelined patch kernel.  One CTA walks patches k = blockIdx.x, += gridDim.x.
+// While patch i is being computed, the blob of patch i+1 (TMA bulk copy, issued an iteration ago)
+// is used to launch the x gather of patch i+1 as 8-byte cp.async copies into the staging vector Xs,
+// and the blob + geometry factors of patch i+2 are requested when patch i retires.
+//   Xs  [max dofs]        patch-local x, position u = order of the blob's dof list
+//   E   [27][FE+1] x 2    element slot pairs (double2): modal coefficients, then element results
+template <int FE, int MINB, bool ACC, bool PROF>
 __global__ void __launch_bounds__(3 * FE, MINB)
 hex_patch_modal_p2_kernel(const PatchArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NT = 3 * FE, ST = FE + 1;
-  uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw);
-  const uint32_t *B = reinterpret_cast<const uint32_t *>(smem_raw + 16);
-  double *E = reinterpret_cast<double *>(smem_raw + 16 + a.blob_cap_bytes);  // [54][FE + 1]
+  constexpr uint32_t EDATA_BYTES = 12 * FE * sizeof(double);
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw);  // [2]
+  unsigned char *blobB = smem_raw + 16;
+  unsigned char *edataB = blobB + 2 * (size_t)a.blob_cap_bytes;
+  double *Xs = reinterpret_cast<double *>(edataB + 2 * EDATA_BYTES);
+  double2 *E2 = reinterpret_cast<double2 *>(reinterpret_cast<unsigned char *>(Xs) + a.xs_cap_bytes);
+  const unsigned char *Eb = reinterpret_cast<const unsigned char *>(E2);
   const int tid = threadIdx.x;
-  const int64_t k = blockIdx.x;
-  long long t_prev = a.prof ? clock64() : 0;
-  if (tid == 0) {
-    const uint32_t o0 = __ldg(a.blob_off + k), o1 = __ldg(a.blob_off + k + 1);
-    blob_load_async(mbar, smem_raw + 16, a.blob + (size_t)o0 * 4, (o1 - o0) * 16u);
-  }
-  // component c of patch element el; its geometry factors are fetched now, consumed after phase A
+  long long t_prev = PROF ? clock64() : 0;
+  unsigned long long prof_acc[6] = {0, 0, 0, 0, 0, 0};
+  const int64_t k0 = blockIdx.x, kstep = gridDim.x;
+  const int n_it = (int)((a.n_patch - k0 + kstep - 1) / kstep);
+  // component c of patch element el, in the rotated frame (c, c+1, c+2)
   const int c = tid / FE, el = tid - c * FE;
   const int c1 = c == 2 ? 0 : c + 1, c2 = c == 0 ? 2 : c - 1;
-  const int64_t pos = k * FE + el;
-  const bool ok = __ldg(a.perm + pos) >= 0;
-  const double *g = a.edata + pos;
-  const int64_t np = a.n_pos;
-  double K11 = __ldg(g + sym6(c1, c1) * np), K10 = __ldg(g + sym6(c1, c) * np), K12 = __ldg(g + sym6(c1, c2) * np),
-         K22 = __ldg(g + sym6(c2, c2) * np), K20 = __ldg(g + sym6(c2, c) * np);
-  double M00 = __ldg(g + (6 + sym6(c, c)) * np), M01 = __ldg(g + (6 + sym6(c, c1)) * np), M02 = __ldg(g + (6 + sym6(c, c2)) * np);
-  __syncthreads();  // mbarrier initialised
+  const int oK11 = sym6(c1, c1) * FE + el, oK10 = sym6(c1, c) * FE + el, oK12 = sym6(c1, c2) * FE + el, oK22 = sym6(c2, c2) * FE + el,
+            oK20 = sym6(c2, c) * FE + el, oM00 = (6 + sym6(c, c)) * FE + el, oM01 = (6 + sym6(c, c1)) * FE + el,
+            oM02 = (6 + sym6(c, c2)) * FE + el;
+
+  // request blob + geometry factors of patch k into buffer b (thread 0)
+  auto request = [&](int64_t k, int b, uint32_t o0, uint32_t o1) {
+    const uint32_t bytes = (o1 - o0) * 16u;
+    mbar_expect_tx(mbar + b, bytes + EDATA_BYTES);
+    bulk_load(mbar + b, blobB + (size_t)b * a.blob_cap_bytes, a.blob + (size_t)o0 * 4, bytes);
+    bulk_load(mbar + b, edataB + (size_t)b * EDATA_BYTES, a.edata + (size_t)k * 12 * FE, EDATA_BYTES);
+  };
+  // launch the x gather of the patch whose blob sits in buffer b
+  auto gather = [&](int b) {
+    const uint32_t *B = reinterpret_cast<const uint32_t *>(blobB + (size_t)b * a.blob_cap_bytes);
+    const uint32_t U = B[0];
+    const uint32_t *dof = B + PatchHost::HDR;
+#pragma unroll 4
+    for (uint32_t u = tid; u < U; u += NT) {
+      const uint32_t m = dof[u];
+      if (m & MAP_ESS) Xs[u] = 0.0;
+      else gather8_async(Xs + u, a.x + (m & MAP_IDX));
+    }
+    gather_commit();
+  };
+
+  if (tid == 0) {
+    mbar_init(mbar, 1);
+    mbar_init(mbar + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    request(k0, 0, __ldg(a.blob_off + k0), __ldg(a.blob_off + k0 + 1));
+    if (n_it > 1) request(k0 + kstep, 1, __ldg(a.blob_off + k0 + kstep), __ldg(a.blob_off + k0 + kstep + 1));
+  }
+  __syncthreads();  // mbarriers initialised
   mbar_wait(mbar, 0);
-  PROF_MARK(0)  // blob arrival
-  const uint32_t U = B[0], b1 = B[1], b2 = B[1] + B[2], nP1 = B[4], nP2 = B[5], nP4 = B[6], nov = B[7];
-  const uint32_t *dof = B + PatchHost::HDR;
-  const uint16_t *e16 = reinterpret_cast<const uint16_t *>(B + B[8]);
-  const uint32_t *e32 = B + B[9];
-  const uint64_t *e64 = reinterpret_cast<const uint64_t *>(B + B[10]);
-  const uint32_t *ovf = B + B[11];
-  // ---- A: gather x once per unique patch dof (all loads of a chunk in flight together), push the
-  // value to the element slots the dof feeds
-  {
-    constexpr int UNR = 6;
-    for (uint32_t u0 = tid; u0 < U; u0 += UNR * NT) {
-      uint32_t m[UNR];
-      double v[UNR];
+  gather(0);
+  PROF_MARK(0)  // prologue
+
+  for (int it = 0; it < n_it; it++) {
+    const int b = it & 1;
+    const int64_t k = k0 + (int64_t)it * kstep;
+    const uint32_t *B = reinterpret_cast<const uint32_t *>(blobB + (size_t)b * a.blob_cap_bytes);
+    const double *g = reinterpret_cast<const double *>(edataB + (size_t)b * EDATA_BYTES);
+    uint32_t q0 = 0, q1 = 0;  // blob extent of the patch requested when this one retires
+    if (tid == 0 && it + 2 < n_it) { q0 = __ldg(a.blob_off + k + 2 * kstep); q1 = __ldg(a.blob_off + k + 2 * kstep + 1); }
+    gather_wait_all();
+    __syncthreads();  // Xs complete and visible
+    PROF_MARK(1)  // wait for the x gather
+    const bool ok = (uint32_t)el < B[13];
+    // ---- pull the element inputs through the per-slot table, forward transform
+    double Am[18];
+    double K11, K10, K12, K22, K20, M00, M01, M02;
+    if (ok) {
+      const uint16_t *lidx = reinterpret_cast<const uint16_t *>(B + B[12]) + (c * 18) * FE + el;
+      double X[18];
 #pragma unroll
-      for (int i = 0; i < UNR; i++) m[i] = (u0 + i * NT < U) ? dof[u0 + i * NT] : MAP_ESS;
-#pragma unroll
-      for (int i = 0; i < UNR; i++) v[i] = (m[i] & MAP_ESS) ? 0.0 : __ldg(a.x + (m[i] & MAP_IDX));
-#pragma unroll
-      for (int i = 0; i < UNR; i++) {
-        const uint32_t u = u0 + i * NT;
-        if (u < b1) {
-          const uint32_t sl = e16[u];
-          E[sl & 0x7fffu] = apply_sign(v[i], sl);
-        } else if (u < b2) {
-          const uint32_t w = e32[u - b1];
-          E[w & 0x7fffu] = apply_sign(v[i], w);
-          E[(w >> 16) & 0x7fffu] = apply_sign(v[i], w >> 16);
-        } else if (u < U) {
-          const uint64_t w = e64[u - b2];
-          const uint32_t lo = (uint32_t)w, hi = (uint32_t)(w >> 32);
-          E[lo & 0x7fffu] = apply_sign(v[i], lo);
-          E[(lo >> 16) & 0x7fffu] = apply_sign(v[i], lo >> 16);
-          E[hi & 0x7fffu] = apply_sign(v[i], hi);
-          if ((hi >> 16) != 0xffffu) E[(hi >> 16) & 0x7fffu] = apply_sign(v[i], hi >> 16);
-        }
+      for (int t = 0; t < 18; t++) {
+        const uint32_t l = lidx[t * FE];
+        X[t] = apply_sign(Xs[l & 0x7fffu], l);
       }
+      const double sc = 0.25 * a.scale;  // 1/4: the open transforms are applied without their 1/2
+      K11 = sc * g[oK11]; K10 = sc * g[oK10]; K12 = sc * g[oK12]; K22 = sc * g[oK22]; K20 = sc * g[oK20];
+      M00 = sc * g[oM00]; M01 = sc * g[oM01]; M02 = sc * g[oM02];
+      modal_fwd(X, Am);
+      double2 *Eown = E2 + (c * 9) * ST + el;
+#pragma unroll
+      for (int r = 0; r < 9; r++) Eown[r * ST] = make_double2(Am[2 * r], Am[2 * r + 1]);
     }
-    for (uint32_t t = tid; t < nov; t += NT) {  // slots beyond four (unstructured meshes)
-      const uint32_t e = ovf[t], m = dof[e >> 16];
-      const double v = (m & MAP_ESS) ? 0.0 : __ldg(a.x + (m & MAP_IDX));
-      E[e & 0x7fffu] = apply_sign(v, e);
-    }
-  }
-  __syncthreads();
-  PROF_MARK(1)  // phase A: gather
-  // ---- element operator
-  double *Eown = E + (c * 18) * ST + el;
-  double Am[18];
-  if (ok) {
-    double X[18];
+    __syncthreads();  // modal coefficients visible; Xs free
+    PROF_MARK(2)  // pull + forward transform
+    double Y[18];
+    if (ok) {
+      const double2 *E1 = E2 + (c1 * 9) * ST + el, *E2c = E2 + (c2 * 9) * ST + el;
+      double Bm[18], Cm[18];
+      // owner frames: comp c+1 stores (m1, m2, m0), comp c+2 stores (m2, m0, m1); the fastest owner index is the pair
 #pragma unroll
-    for (int t = 0; t < 18; t++) X[t] = Eown[t * ST];
-    modal_fwd(X, Am);
+      for (int m2 = 0; m2 < 3; m2++)
 #pragma unroll
-    for (int t = 0; t < 18; t++) Eown[t * ST] = Am[t];
-  }
-  __syncthreads();
-  double Y[18];
-  if (ok) {
-    const double *E1 = E + (c1 * 18) * ST + el, *E2 = E + (c2 * 18) * ST + el;
-    double Bm[18], Cm[18];
-    // owner frames: comp c+1 stores (m1, m2, m0), comp c+2 stores (m2, m0, m1)
-#pragma unroll
-    for (int m2 = 0; m2 < 3; m2++)
-#pragma unroll
-      for (int m1 = 0; m1 < 2; m1++)
-#pragma unroll
-        for (int m0 = 0; m0 < 3; m0++) Bm[IB(m0, m1, m2)] = E1[(m1 + 2 * (m2 + 3 * m0)) * ST];
-#pragma unroll
-    for (int m2 = 0; m2 < 2; m2++)
+        for (int m0 = 0; m0 < 3; m0++) {
+          const double2 v = E1[(m2 + 3 * m0) * ST];
+          Bm[IB(m0, 0, m2)] = v.x;
+          Bm[IB(m0, 1, m2)] = v.y;
+        }
 #pragma unroll
       for (int m1 = 0; m1 < 3; m1++)
 #pragma unroll
-        for (int m0 = 0; m0 < 3; m0++) Cm[IC(m0, m1, m2)] = E2[(m2 + 2 * (m0 + 3 * m1)) * ST];
-    const double sc = 0.25 * a.scale;  // 1/4: the open transforms are applied without their 1/2
-    K11 *= sc; K10 *= sc; K12 *= sc; K22 *= sc; K20 *= sc; M00 *= sc; M01 *= sc; M02 *= sc;
-    double Yh[18];
-    modal_op(Am, Bm, Cm, M00, M01, M02, K11, K10, K12, K22, K20, K12, Yh);
-    modal_bwd(Yh, Y);
-  }
-  __syncthreads();  // everyone has read the modal coefficients
-  PROF_MARK(3)  // exchange + modal operator + backward transform
-  if (ok) {
-#pragma unroll
-    for (int t = 0; t < 18; t++) Eown[t * ST] = Y[t];
-  }
-  __syncthreads();
-  // ---- C: sum the slots of every patch dof; private dofs are plain stores, shared ones RED
-#pragma unroll 2
-  for (uint32_t u = tid; u < U; u += NT) {
-    const uint32_t m = dof[u];
-    if (m & MAP_ESS) continue;
-    double v;
-    bool priv;
-    if (u < b1) {
-      const uint32_t sl = e16[u];
-      v = apply_sign(E[sl & 0x7fffu], sl);
-      priv = u < nP1;
-    } else if (u < b2) {
-      const uint32_t w = e32[u - b1];
-      v = apply_sign(E[w & 0x7fffu], w) + apply_sign(E[(w >> 16) & 0x7fffu], w >> 16);
-      priv = u - b1 < nP2;
-    } else {
-      const uint64_t w = e64[u - b2];
-      const uint32_t lo = (uint32_t)w, hi = (uint32_t)(w >> 32);
-      v = apply_sign(E[lo & 0x7fffu], lo) + apply_sign(E[(lo >> 16) & 0x7fffu], lo >> 16) + apply_sign(E[hi & 0x7fffu], hi);
-      if ((hi >> 16) != 0xffffu) v += apply_sign(E[(hi >> 16) & 0x7fffu], hi >> 16);
-      priv = u - b2 < nP4;
+        for (int m0 = 0; m0 < 3; m0++) {
+          const double2 v = E2c[(m0 + 3 * m1) * ST];
+          Cm[IC(m0, m1, 0)] = v.x;
+          Cm[IC(m0, m1, 1)] = v.y;
+        }
+      double Yh[18];
+      modal_op(Am, Bm, Cm, M00, M01, M02, K11, K10, K12, K22, K20, K12, Yh);
+      modal_bwd(Yh, Y);
     }
-    double *dst = a.y + (m & MAP_IDX);
-    if (priv) *dst = ACC ? *dst + v : v;
-    else atomicAdd(dst, v);
+    // ---- start the x gather of the next patch: it lands while this patch is scattered
+    if (it + 1 < n_it) {
+      mbar_wait(mbar + (b ^ 1), ((it + 1) >> 1) & 1);
+      gather(b ^ 1);
+    }
+    __syncthreads();  // everyone has read the modal coefficients
+    PROF_MARK(3)  // exchange + modal operator + backward transform + next gather issue
+    if (ok) {
+      const uint16_t *lidx = reinterpret_cast<const uint16_t *>(B + B[12]) + (c * 18) * FE + el;
+      double2 *Eown = E2 + (c * 9) * ST + el;
+#pragma unroll
+      for (int r = 0; r < 9; r++)
+        Eown[r * ST] = make_double2(apply_sign(Y[2 * r], lidx[(2 * r) * FE]), apply_sign(Y[2 * r + 1], lidx[(2 * r + 1) * FE]));
+    }
+    __syncthreads();
+    PROF_MARK(4)  // element results to shared memory
+    // ---- sum the slots of every patch dof; private dofs are plain stores, shared ones RED
+    {
+      const uint32_t n1 = B[1], n2 = B[2], n4 = B[3], nov = B[7];
+      const uint32_t *dof = B + PatchHost::HDR;
+      const uint16_t *e16 = reinterpret_cast<const uint16_t *>(B + B[8]);
+      const uint32_t *e32 = B + B[9];
+      const uint2 *e64 = reinterpret_cast<const uint2 *>(B + B[10]);
+      const uint32_t *ovf = B + B[11];
+#define E_AT(off) (*reinterpret_cast<const double *>(Eb + (off)))
+#define EMIT(m, v)                                                            \
+  if (!((m) & MAP_ESS)) {                                                     \
+    double *dst = a.y + ((m) & MAP_IDX);                                      \
+    if ((m) & PATCH_SHARED) atomicAdd(dst, (v));                              \
+    else *dst = ACC ? *dst + (v) : (v);                                       \
   }
-  for (uint32_t t = tid; t < nov; t += NT) {
-    const uint32_t e = ovf[t], m = dof[e >> 16];
-    if (m & MAP_ESS) continue;
-    atomicAdd(a.y + (m & MAP_IDX), apply_sign(E[e & 0x7fffu], e));
+      constexpr int UN = 4;  // dofs in flight per thread: table reads, then E reads, then the stores
+      for (uint32_t r0 = tid; r0 < n1; r0 += UN * NT) {
+        uint32_t m[UN], o[UN];
+        double v[UN];
+#pragma unroll
+        for (int i = 0; i < UN; i++) {
+          const uint32_t r = r0 + i * NT;
+          m[i] = r < n1 ? dof[r] : MAP_ESS;
+          o[i] = r < n1 ? e16[r] : 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < UN; i++) v[i] = E_AT(o[i]);
+#pragma unroll
+        for (int i = 0; i < UN; i++) EMIT(m[i], v[i])
+      }
+      dof += n1;
+      for (uint32_t r0 = tid; r0 < n2; r0 += UN * NT) {
+        uint32_t m[UN], o[UN];
+        double v[UN];
+#pragma unroll
+        for (int i = 0; i < UN; i++) {
+          const uint32_t r = r0 + i * NT;
+          m[i] = r < n2 ? dof[r] : MAP_ESS;
+          o[i] = r < n2 ? e32[r] : 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < UN; i++) v[i] = E_AT(o[i] & 0xffffu) + E_AT(o[i] >> 16);
+#pragma unroll
+        for (int i = 0; i < UN; i++) EMIT(m[i], v[i])
+      }
+      dof += n2;
+      for (uint32_t r0 = tid; r0 < n4; r0 += 2 * NT) {
+        uint32_t m[2];
+        uint2 o[2];
+        double v[2];
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+          const uint32_t r = r0 + i * NT;
+          m[i] = r < n4 ? dof[r] : MAP_ESS;
+          o[i] = r < n4 ? e64[r] : make_uint2(0u, 0xffff0000u);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+          v[i] = (E_AT(o[i].x & 0xffffu) + E_AT(o[i].x >> 16)) + E_AT(o[i].y & 0xffffu);
+          if ((o[i].y >> 16) != 0xffffu) v[i] += E_AT(o[i].y >> 16);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; i++) EMIT(m[i], v[i])
+      }
+      dof = B + PatchHost::HDR;
+      for (uint32_t t = tid; t < nov; t += NT) {  // slots beyond four (unstructured meshes)
+        const uint32_t e = ovf[t], m = dof[e >> 16];
+        if (m & MAP_ESS) continue;
+        atomicAdd(a.y + (m & MAP_IDX), E_AT(e & 0xffffu));
+      }
+#undef EMIT
+#undef E_AT
+    }
+    __syncthreads();  // blob buffer b and E are free
+    PROF_MARK(5)  // dof sums + stores
+    if (tid == 0 && it + 2 < n_it) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      request(k + 2 * kstep, b, q0, q1);
+    }
   }
-  PROF_MARK(5)  // phase C: scatter (thread 0's share)
+  if (PROF && tid == 0)
+    for (int i = 0; i < 6; i++) atomicAdd(a.prof + i, prof_acc[i]);
 }
 
 // ---- setup ---------------------------------------------------------------------------------------
 // affine geometry factors in patch order: S = alpha J^T J/det (6), M = beta adj adj^T/det (6)
-__global__ void patch_edata_kernel(const int64_t n_pos, const int32_t *__restrict__ perm, const double *__restrict__ xyz,
+__global__ void patch_edata_kernel(const int64_t n_pos, const int FE, const int32_t *__restrict__ perm, const double *__restrict__ xyz,
                                    const double *__restrict__ alpha, const double *__restrict__ beta,
                                    double *__restrict__ edata) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n_pos) return;
   const int32_t e = perm[j];
+  double *out = edata + (j / FE) * 12 * FE + j % FE;  // [patch][12][FE]
   if (e < 0) {
-    for (int s = 0; s < 12; s++) edata[(int64_t)s * n_pos + j] = 0.0;
+    for (int s = 0; s < 12; s++) out[s * FE] = 0.0;
     return;
   }
   const double *X = xyz + (int64_t)e * 24;  // tensor order
@@ -381,8 +467,8 @@ __global__ void patch_edata_kernel(const int64_t n_pos, const int32_t *__restric
   int s = 0;
   for (int i = 0; i < 3; i++)
     for (int jj = i; jj < 3; jj++, s++) {
-      edata[(int64_t)s * n_pos + j] = al * (c[i][0] * c[jj][0] + c[i][1] * c[jj][1] + c[i][2] * c[jj][2]);
-      edata[(int64_t)(6 + s) * n_pos + j] = be * (ad[i][0] * ad[jj][0] + ad[i][1] * ad[jj][1] + ad[i][2] * ad[jj][2]);
+      out[s * FE] = al * (c[i][0] * c[jj][0] + c[i][1] * c[jj][1] + c[i][2] * c[jj][2]);
+      out[(6 + s) * FE] = be * (ad[i][0] * ad[jj][0] + ad[i][1] * ad[jj][1] + ad[i][2] * ad[jj][2]);
     }
 }
 
@@ -442,6 +528,12 @@ static int upload(T *&dst, const std::vector<T> &src) {
   return 0;
 }
 
+// dynamic shared memory of the patch kernel: 2 mbarriers | 2 blob buffers | 2 geometry buffers | Xs | E
+static size_t patch_smem_bytes(int FE, uint32_t max_blob_words, uint32_t max_dofs) {
+  const size_t blob_cap = ((size_t)max_blob_words * 4 + 15u) & ~(size_t)15u, xs_cap = ((size_t)max_dofs * 8 + 15u) & ~(size_t)15u;
+  return 16 + 2 * blob_cap + 2 * (size_t)12 * FE * sizeof(double) + xs_cap + (size_t)27 * (FE + 1) * 16;
+}
+
 int hex_patch_build(hcurl_space *sp, const double *elem_xyz, const int32_t *elem_ldof, const int32_t *l2e) {
   if (sp->geom != HCURL_GEOM_HEX || sp->order != 2 || sp->geom_order != 1) return 0;
   const char *off = getenv("HCURL_NO_PATCH");
@@ -478,8 +570,8 @@ int hex_patch_build(hcurl_space *sp, const double *elem_xyz, const int32_t *elem
   HC_CUDA(cudaSetDevice(sp->ctx->device));
   PatchSet &P = sp->patch;
   P.FE = FE; P.stride = H.stride; P.n_patch = H.n_patch;
-  P.blob_words = (int64_t)H.blob.size(); P.max_blob_words = H.max_blob_words;
-  if ((size_t)H.max_blob_words * 4 + sizeof(double) * 54 * (FE + 1) + 16 > 200 * 1024) return 0;  // patch path unavailable
+  P.blob_words = (int64_t)H.blob.size(); P.max_blob_words = H.max_blob_words; P.max_dofs = H.max_dofs;
+  if (patch_smem_bytes(FE, H.max_blob_words, H.max_dofs) > 227 * 1024) return 0;  // patch path unavailable
   if (upload(P.d_perm, H.perm) || upload(P.d_blob_off, H.blob_off) || upload(P.d_blob, H.blob)) return 1;
   sp->has_patches = true;
   return 0;
@@ -505,20 +597,30 @@ bool hex_patch_eligible(const hcurl_op *op) {
 }
 
 template <int FE, int MINB>
-static int launch_fe(const PatchArgs &a, int64_t n_patch, bool acc, cudaStream_t st) {
-  const size_t smem = 16 + a.blob_cap_bytes + sizeof(double) * 54 * (FE + 1);
-  auto k0 = hex_patch_modal_p2_kernel<FE, MINB, false>;
-  auto k1 = hex_patch_modal_p2_kernel<FE, MINB, true>;
+static int launch_fe(const PatchArgs &a, int64_t n_patch, int sm_count, size_t smem, bool acc, cudaStream_t st) {
+  auto k0 = hex_patch_modal_p2_kernel<FE, MINB, false, false>;
+  auto k1 = hex_patch_modal_p2_kernel<FE, MINB, true, false>;
+  auto kp = hex_patch_modal_p2_kernel<FE, MINB, false, true>;
   static size_t attr = 0;
+  static int per_sm = 0;
   if (attr < smem) {
     HC_CUDA(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     HC_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HC_CUDA(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     HC_CUDA(cudaFuncSetAttribute(k0, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     HC_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    HC_CUDA(cudaFuncSetAttribute(kp, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    HC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k0, 3 * FE, smem));
+    if (per_sm < 1) { set_error("patch kernel does not fit on an SM (%zu bytes of shared memory)", smem); return 1; }
     attr = smem;
   }
-  if (acc) k1<<<(unsigned)n_patch, 3 * FE, smem, st>>>(a);
-  else k0<<<(unsigned)n_patch, 3 * FE, smem, st>>>(a);
+  // persistent CTAs: every SM holds per_sm of them, each walks patches blockIdx.x, += gridDim.x
+  int64_t grid = (int64_t)per_sm * sm_count;
+  if (const char *s = getenv("HCURL_PATCH_CTAS_PER_SM")) { const int v = atoi(s); if (v >= 1 && v <= per_sm) grid = (int64_t)v * sm_count; }
+  if (grid > n_patch) grid = n_patch;
+  if (a.prof) kp<<<(unsigned)grid, 3 * FE, smem, st>>>(a);
+  else if (acc) k1<<<(unsigned)grid, 3 * FE, smem, st>>>(a);
+  else k0<<<(unsigned)grid, 3 * FE, smem, st>>>(a);
   return 0;
 }
 
@@ -530,21 +632,24 @@ int hex_patch_launch(hcurl_op *op, bool constrained, const double *d_x, double *
   const int64_t n_pos = P.n_patch * P.FE;
   if (!op->edataP_valid) {
     if (!op->d_edataP) HC_CUDA(cudaMalloc(&op->d_edataP, sizeof(double) * 12 * n_pos));
-    patch_edata_kernel<<<(unsigned)((n_pos + 255) / 256), 256, 0, ctx->stream>>>(n_pos, P.d_perm, sp->d_xyz, op->d_alpha, op->d_beta,
+    patch_edata_kernel<<<(unsigned)((n_pos + 255) / 256), 256, 0, ctx->stream>>>(n_pos, P.FE, P.d_perm, sp->d_xyz, op->d_alpha, op->d_beta,
                                                                                 op->d_edataP);
     HC_CUDA(cudaGetLastError());
     op->edataP_valid = true;
   }
   PatchArgs a;
-  a.n_pos = n_pos; a.perm = P.d_perm; a.blob_off = P.d_blob_off;
+  a.n_patch = P.n_patch; a.blob_off = P.d_blob_off;
   a.blob = (constrained && op->d_blob_ess) ? op->d_blob_ess : P.d_blob;
   a.blob_cap_bytes = (P.max_blob_words * 4 + 15u) & ~15u;
+  a.xs_cap_bytes = (P.max_dofs * 8 + 15u) & ~15u;
   a.edata = op->d_edataP; a.x = d_x; a.y = d_y; a.scale = scale;
   a.prof = g_patch_prof;
+  if (a.prof && accumulate) a.prof = nullptr;
+  const size_t smem = patch_smem_bytes(P.FE, P.max_blob_words, P.max_dofs);
   int rc = 1;
-  if (P.FE == 32) rc = launch_fe<32, 8>(a, P.n_patch, accumulate, ctx->stream);
-  else if (P.FE == 64) rc = launch_fe<64, 4>(a, P.n_patch, accumulate, ctx->stream);
-  else if (P.FE == 128) rc = launch_fe<128, 1>(a, P.n_patch, accumulate, ctx->stream);
+  if (P.FE == 32) rc = launch_fe<32, 4>(a, P.n_patch, ctx->sm_count, smem, accumulate, ctx->stream);
+  else if (P.FE == 64) rc = launch_fe<64, 2>(a, P.n_patch, ctx->sm_count, smem, accumulate, ctx->stream);
+  else if (P.FE == 128) rc = launch_fe<128, 1>(a, P.n_patch, ctx->sm_count, smem, accumulate, ctx->stream);
   if (rc) return rc;
   HC_CUDA(cudaGetLastError());
   ctx->launches++;

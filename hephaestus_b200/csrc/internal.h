@@ -26,6 +26,8 @@ bool cuda_ok(cudaError_t e, const char *what);
 static constexpr uint32_t MAP_IDX = 0x3fffffffu;
 static constexpr uint32_t MAP_ESS = 0x40000000u;
 static constexpr uint32_t MAP_NEG = 0x80000000u;
+// patch blobs (patch.cpp): dof words carry no sign; bit 31 marks dofs shared with other patches
+static constexpr uint32_t PATCH_SHARED = 0x80000000u;
 
 // ---------------------------------------------------------------- basis ----
 void gauss_legendre01(int n, double *x, double *w);
@@ -71,6 +73,7 @@ struct PatchHost {
   std::vector<uint32_t> blob_off; // [n_patch+1] start of each patch blob in 16-byte units
   std::vector<uint32_t> blob;     // see patch.cpp for the layout
   uint32_t max_blob_words = 0;
+  uint32_t max_dofs = 0;          // largest number of unique dofs of one patch
 };
 int build_patches(int nd, int64_t n_elem, int FE, int stride, int64_t n_ext, const double *centroid,
                   const uint32_t *slot_code, PatchHost &out);
@@ -84,7 +87,7 @@ struct PatchSet {  // device copy
   int stride = 0;
   uint32_t *d_blob_off = nullptr, *d_blob = nullptr;
   int64_t blob_words = 0;
-  uint32_t max_blob_words = 0;
+  uint32_t max_blob_words = 0, max_dofs = 0;
 };
 
 // ----------------------------------------------------------------- NCCL ----
@@ -160,7 +163,7 @@ struct hcurl_op {
   bool edata_valid = false;
   uint32_t *d_mapT_ess = nullptr;
   uint32_t *d_blob_ess = nullptr;  // copy of the patch blobs with essential flags on the dof words
-  double *d_edataP = nullptr;      // [12][n_patch*FE] affine geometry factors in patch order
+  double *d_edataP = nullptr;      // [n_patch][12][FE] affine geometry factors in patch order
   bool edataP_valid = false;
   int kernel_sel = 0;              // 0 auto, 1 generic, 2 element-wise fast path, 3 patch path
   bool force_generic = false;

@@ -16,18 +16,29 @@
 //     RED atomics.
 // This file builds, for any mesh, one contiguous BLOB per patch (so the kernel can stage it in
 // shared memory with a single cp.async.bulk).  The dofs of a patch are ordered by slot count --
-// 1 | 2 | 3..4 element slots -- and inside each width private dofs come first; every group is
-// sorted by global index so that consecutive lanes touch consecutive addresses.  Slot entries have
-// a fixed width per section (16 / 32 / 64 bits), so no lane unpacks unused slots.  Blob layout in
-// 32-bit words, every section starting on a 16-byte boundary:
+// 1 | 2 | 3..4 element slots -- each class in ascending global index up to a bank-spreading
+// permutation inside aligned runs of 16 (see below), so that consecutive lanes touch consecutive
+// addresses.  Position u in this order is also the dof's place in the patch-local x staging vector Xs.
+//
+// E-vector layout (doubles): slot s of patch position j sits at  (s>>1)*(2*stride) + 2*j + (s&1),
+// i.e. slots are stored in PAIRS so that the element side moves 16-byte vectors and the two dofs of
+// an order-2 edge/face pair fall in adjacent banks on the dof side.  Sign flips are applied on the
+// element side (gather: lidx bit 15; scatter: the same bit), so the dof side only sums.
+//
+// Blob layout in 32-bit words, every section starting on a 16-byte boundary:
 //   [0] U  [1] n1  [2] n2  [3] n4      number of patch dofs, and of 1- / 2- / 3..4-slot dofs
-//   [4] nP1 [5] nP2 [6] nP4            private dofs at the head of each width section
-//   [7] n_ovf  [8..11] word offsets of the e16 / e32 / e64 / ovf sections  [12..15] 0
-//   [16 ..] dof[U]   extended-vector index of every patch dof
-//   e16[n1], e32[n2], e64[n4]  per dof 1 / 2 / 4 entries of 16 bits: E-vector index (bits 0..14)
-//            | sign flip (bit 15); 0xffff = unused (a 3-slot dof in the 64-bit section)
-//   ovf[n_ovf]  (u << 16 | entry) for the slots beyond four (edge valence > 4 inside one patch,
+//   [4] nP1 [5] nP2 [6] nP4            number of private dofs in each width section (informational)
+//   [7] n_ovf  [8..11] word offsets of the e16 / e32 / e64 / ovf sections
+//   [12] word offset of lidx  [13] number of real (non-padding) elements of the patch  [14..15] 0
+//   [16 ..] dof[U]   extended-vector index of every patch dof (bits 0..29) | PATCH_SHARED (bit 31) when
+//            other patches also touch the dof, i.e. its sum must be RED-added; bit 30 is the essential
+//            flag the operator ORs in (hex_patch.cu)
+//   e16[n1], e32[n2], e64[n4]  per dof 1 / 2 / 4 entries of 16 bits: BYTE offset of the slot in the
+//            E-vector; 0xffff = unused (a 3-slot dof in the 64-bit section)
+//   ovf[n_ovf]  (u << 16 | byte offset) for the slots beyond four (edge valence > 4 inside one patch,
 //            only on unstructured meshes); such dofs are classed shared, overflow is RED-added.
+//   lidx[nd][FE] 16 bits per element slot: Xs position u of the slot's dof (bits 0..14) | sign flip
+//            (bit 15); the element side PULLS its inputs through this table.
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -75,7 +86,7 @@ static void parallel_for(int64_t n, F f) {
 int build_patches(int nd, int64_t n_elem, int FE, int stride, int64_t n_ext, const double *centroid,
                   const uint32_t *slot_code, PatchHost &out) {
   if (stride < FE) { set_error("slot stride must be >= elements per patch"); return 1; }
-  if ((int64_t)stride * nd > 32767) { set_error("patch too large for the 15-bit slot encoding"); return 1; }
+  if ((int64_t)stride * (nd + (nd & 1)) * 8 > 65534 || (int64_t)FE * nd > 32767) { set_error("patch too large for the 16-bit slot encoding"); return 1; }
   const int64_t n_patch = (n_elem + FE - 1) / FE;
   out.FE = FE; out.stride = stride; out.nd = nd; out.n_patch = n_patch;
   // ---- Morton order of the centroids
@@ -107,13 +118,12 @@ int build_patches(int nd, int64_t n_elem, int FE, int stride, int64_t n_ext, con
   key.clear(); key.shrink_to_fit();
 
   // ---- per patch: entries sorted by dof, unique list
-  struct Ent { uint32_t dof; uint16_t slot; };
+  struct Ent { uint32_t dof; uint16_t slot; uint16_t sj; };  // slot = E byte offset, sj = s*FE + j | sign
   const int per = FE * nd;
   std::vector<std::vector<uint32_t>> udof((size_t)n_patch);     // unique dofs (ascending)
   std::vector<std::vector<uint16_t>> ustart((size_t)n_patch);   // U+1
-  std::vector<std::vector<uint16_t>> uslots((size_t)n_patch);   // grouped by dof
-  const int comp = nd / 3;  // E-vector index = (slot)*FE + element position
-  (void)comp;
+  std::vector<std::vector<uint16_t>> uslots((size_t)n_patch);   // E byte offsets, grouped by dof
+  std::vector<std::vector<uint16_t>> usj((size_t)n_patch);      // s*FE + j | sign, same grouping
   parallel_for(n_patch, [&](int64_t k) {
     std::vector<Ent> ent;
     ent.reserve(per);
@@ -122,18 +132,21 @@ int build_patches(int nd, int64_t n_elem, int FE, int stride, int64_t n_ext, con
       if (e < 0) continue;
       for (int s = 0; s < nd; s++) {
         const uint32_t code = slot_code[(size_t)e * nd + s];
-        const uint16_t sl = (uint16_t)(s * stride + j) | ((code & MAP_NEG) ? 0x8000u : 0u);
-        ent.push_back({code & MAP_IDX, sl});
+        const uint16_t sl = (uint16_t)(((s >> 1) * (2 * stride) + 2 * j + (s & 1)) * 8);
+        ent.push_back({code & MAP_IDX, sl, (uint16_t)((uint32_t)(s * FE + j) | ((code & MAP_NEG) ? 0x8000u : 0u))});
       }
     }
     std::sort(ent.begin(), ent.end(), [](const Ent &a, const Ent &b) { return a.dof < b.dof || (a.dof == b.dof && a.slot < b.slot); });
     auto &ud = udof[(size_t)k];
     auto &us = ustart[(size_t)k];
     auto &sl = uslots[(size_t)k];
+    auto &sj = usj[(size_t)k];
     sl.resize(ent.size());
+    sj.resize(ent.size());
     for (size_t i = 0; i < ent.size(); i++) {
       if (i == 0 || ent[i].dof != ent[i - 1].dof) { ud.push_back(ent[i].dof); us.push_back((uint16_t)i); }
       sl[i] = ent[i].slot;
+      sj[i] = ent[i].sj;
     }
     us.push_back((uint16_t)ent.size());
   });
@@ -155,9 +168,10 @@ int build_patches(int nd, int64_t n_elem, int FE, int stride, int64_t n_ext, con
   // ---- emit one blob per patch
   auto width_of = [](int nslot) { return nslot <= 1 ? 0 : (nslot == 2 ? 1 : 2); };
   auto align4 = [](uint32_t w) { return (w + 3u) & ~3u; };  // words -> 16-byte boundary
-  std::vector<uint32_t> words((size_t)n_patch);
+  const uint32_t lidx_words = align4((uint32_t)(per + 1) / 2);
   out.blob_off.assign((size_t)n_patch + 1, 0);
   out.max_blob_words = 0;
+  out.max_dofs = 0;
   for (int64_t k = 0; k < n_patch; k++) {
     const auto &ud = udof[(size_t)k];
     const auto &us = ustart[(size_t)k];
@@ -167,16 +181,18 @@ int build_patches(int nd, int64_t n_elem, int FE, int stride, int64_t n_ext, con
       n[width_of(ns)]++;
       if (ns > 4) nov += ns - 4;
     }
-    const uint32_t w = PatchHost::HDR + align4((uint32_t)ud.size()) + align4((n[0] + 1) / 2) + align4(n[1]) + align4(2 * n[2]) + align4(nov);
-    words[(size_t)k] = w;
+    const uint32_t w = PatchHost::HDR + align4((uint32_t)ud.size()) + align4((n[0] + 1) / 2) + align4(n[1]) + align4(2 * n[2]) +
+                       align4(nov) + lidx_words;
     out.blob_off[(size_t)k + 1] = out.blob_off[(size_t)k] + w / 4;
     out.max_blob_words = std::max(out.max_blob_words, w);
+    out.max_dofs = std::max(out.max_dofs, (uint32_t)ud.size());
   }
   out.blob.assign((size_t)out.blob_off[(size_t)n_patch] * 4, 0);
   parallel_for(n_patch, [&](int64_t k) {
     const auto &ud = udof[(size_t)k];
     const auto &us = ustart[(size_t)k];
     const auto &sl = uslots[(size_t)k];
+    const auto &sj = usj[(size_t)k];
     uint32_t *B = out.blob.data() + (size_t)out.blob_off[(size_t)k] * 4;
     // group sizes: [width][private|shared]
     uint32_t cnt[3][2] = {{0, 0}, {0, 0}, {0, 0}}, nov = 0;
@@ -187,40 +203,98 @@ int build_patches(int nd, int64_t n_elem, int FE, int stride, int64_t n_ext, con
     }
     const uint32_t U = (uint32_t)ud.size(), n1 = cnt[0][0] + cnt[0][1], n2 = cnt[1][0] + cnt[1][1], n4 = cnt[2][0] + cnt[2][1];
     const uint32_t o16 = PatchHost::HDR + align4(U), o32 = o16 + align4((n1 + 1) / 2), o64 = o32 + align4(n2), oov = o64 + align4(2 * n4);
+    const uint32_t olx = oov + align4(nov);
+    uint32_t n_real = 0;
+    for (int j = 0; j < FE; j++) n_real += out.perm[(size_t)k * FE + j] >= 0;
     B[0] = U; B[1] = n1; B[2] = n2; B[3] = n4; B[4] = cnt[0][0]; B[5] = cnt[1][0]; B[6] = cnt[2][0]; B[7] = nov;
-    B[8] = o16; B[9] = o32; B[10] = o64; B[11] = oov;
+    B[8] = o16; B[9] = o32; B[10] = o64; B[11] = oov; B[12] = olx; B[13] = n_real;
     uint32_t *pd = B + PatchHost::HDR;
     uint16_t *p16 = (uint16_t *)(B + o16);
     uint32_t *p32 = B + o32;
     uint64_t *p64 = (uint64_t *)(B + o64);
     uint32_t *po = B + oov;
-    // order inside each (width, class) group: ascending global index (consecutive lanes gather
-    // consecutive addresses).  A bank-aware local permutation of this order was tried: it cut the
-    // shared-memory conflicts of the slot stores/loads by 20% but cost more in global-load sectors
-    // (measured 0.58 ms vs 0.54 ms per apply), so plain ascending order stays.
-    std::vector<uint32_t> grp[3][2];
-    for (size_t i = 0; i < ud.size(); i++) grp[width_of(us[i + 1] - us[i])][multi[ud[i]] ? 1 : 0].push_back((uint32_t)i);
-    const uint32_t base[3] = {0, n1, n1 + n2};
+    uint16_t *plx = (uint16_t *)(B + olx);
+    // order inside each width class: ascending global index (consecutive lanes gather / store
+    // consecutive addresses); private and shared dofs are told apart by the PATCH_SHARED bit of the
+    // dof word.  The position of a dof in this order is also its place in the staging vector Xs, so
+    // its shared-memory bank on the element side (the pull through lidx) is position mod 16.  Sorted
+    // order makes the pull 4.4-way bank conflicted on structured meshes (strided dof numbering), so
+    // inside every aligned run of 16 positions the dofs are PERMUTED to spread, for each
+    // (slot, half-warp of elements) access group, the dofs it reads over distinct banks.  A warp of the
+    // dof side still touches the same 32 dofs, i.e. the same global sectors.
+    std::vector<uint32_t> order;  // position -> index into ud
+    order.reserve(U);
     for (int w = 0; w < 3; w++)
-      for (int cls = 0; cls < 2; cls++) {
-        uint32_t r = cls ? cnt[w][0] : 0;  // index inside the width section
-        for (uint32_t i : grp[w][cls]) {
-          const int ns = us[i + 1] - us[i];
-          const uint32_t ul = base[w] + r;  // patch-local dof index
-          pd[ul] = ud[i];
-          if (w == 0) p16[r] = sl[us[i]];
-          else if (w == 1) p32[r] = (uint32_t)sl[us[i]] | ((uint32_t)sl[us[i] + 1] << 16);
-          else {
-            uint64_t v = ~0ULL;
-            for (int j = 0; j < ns; j++) {
-              if (j < 4) v = (v & ~(0xffffULL << (16 * j))) | ((uint64_t)sl[us[i] + j] << (16 * j));
-              else *po++ = (ul << 16) | sl[us[i] + j];
-            }
-            p64[r] = v;
-          }
-          r++;
+      for (size_t i = 0; i < ud.size(); i++)
+        if (width_of(us[i + 1] - us[i]) == w) order.push_back((uint32_t)i);
+    {
+      const int HG = (FE + 15) / 16;
+      std::vector<uint8_t> cnt((size_t)nd * HG * 16, 0);
+      auto groups_of = [&](uint32_t i, int *g) {  // distinct access groups reading dof i
+        int n = 0;
+        for (int q = us[i]; q < us[i + 1] && n < 8; q++) {
+          const int v = sj[q] & 0x7fff, gid = (v / FE) * HG + (v % FE) / 16;
+          bool dup = false;
+          for (int t = 0; t < n; t++) dup |= g[t] == gid;
+          if (!dup) g[n++] = gid;
         }
+        return n;
+      };
+      auto add = [&](uint32_t i, int bank, int v) {
+        int g[8];
+        const int n = groups_of(i, g);
+        for (int t = 0; t < n; t++) cnt[(size_t)g[t] * 16 + bank] = (uint8_t)(cnt[(size_t)g[t] * 16 + bank] + v);
+      };
+      const uint32_t cls_end[3] = {n1, n1 + n2, U};
+      for (int pass = 0; pass < 2; pass++) {
+        uint32_t p0 = 0;
+        for (int w = 0; w < 3; w++)
+          while (p0 < cls_end[w]) {
+            const uint32_t p1 = std::min(cls_end[w], (p0 / 16 + 1) * 16);
+            const int m = (int)(p1 - p0);
+            uint32_t ds[16];
+            for (int t = 0; t < m; t++) ds[t] = order[p0 + t];
+            if (pass > 0) for (int t = 0; t < m; t++) add(ds[t], (int)((p0 + t) & 15), -1);
+            bool used[16] = {false};
+            // dofs read by more groups first
+            std::stable_sort(ds, ds + m, [&](uint32_t a, uint32_t b) { return us[a + 1] - us[a] > us[b + 1] - us[b]; });
+            for (int t = 0; t < m; t++) {
+              int g[8];
+              const int n = groups_of(ds[t], g);
+              int best = -1, best_cost = 1 << 30;
+              for (int q = 0; q < m; q++) {
+                if (used[q]) continue;
+                const int bank = (int)((p0 + q) & 15);
+                int c = 0;
+                for (int r = 0; r < n; r++) c += 2 * cnt[(size_t)g[r] * 16 + bank] + 1;
+                if (c < best_cost) { best_cost = c; best = q; }
+              }
+              used[best] = true;
+              order[p0 + best] = ds[t];
+              add(ds[t], (int)((p0 + best) & 15), +1);
+            }
+            p0 = p1;
+          }
       }
+    }
+    const uint32_t base[3] = {0, n1, n1 + n2};
+    for (uint32_t ul = 0; ul < U; ul++) {
+      const uint32_t i = order[ul];
+      const int ns = us[i + 1] - us[i], w = width_of(ns);
+      const uint32_t r = ul - base[w];  // index inside the width section
+      pd[ul] = ud[i] | (multi[ud[i]] ? PATCH_SHARED : 0u);
+      for (int j = 0; j < ns; j++) plx[sj[us[i] + j] & 0x7fffu] = (uint16_t)(ul | (sj[us[i] + j] & 0x8000u));
+      if (w == 0) p16[r] = sl[us[i]];
+      else if (w == 1) p32[r] = (uint32_t)sl[us[i]] | ((uint32_t)sl[us[i] + 1] << 16);
+      else {
+        uint64_t v = ~0ULL;
+        for (int j = 0; j < ns; j++) {
+          if (j < 4) v = (v & ~(0xffffULL << (16 * j))) | ((uint64_t)sl[us[i] + j] << (16 * j));
+          else *po++ = (ul << 16) | sl[us[i] + j];
+        }
+        p64[r] = v;
+      }
+    }
   });
   return 0;
 }
@@ -246,6 +320,7 @@ int64_t hcurl_host_patches_count(const hcurl_host_patches *p) { return p->h.n_pa
 /* total blob size in 32-bit words; largest single patch blob in words */
 int64_t hcurl_host_patches_blob_words(const hcurl_host_patches *p) { return (int64_t)p->h.blob.size(); }
 int64_t hcurl_host_patches_max_blob_words(const hcurl_host_patches *p) { return (int64_t)p->h.max_blob_words; }
+int64_t hcurl_host_patches_max_dofs(const hcurl_host_patches *p) { return (int64_t)p->h.max_dofs; }
 int hcurl_host_patches_copy(const hcurl_host_patches *p, int32_t *perm, uint32_t *blob_off, uint32_t *blob) {
   const hcurl::PatchHost &h = p->h;
   if (perm) memcpy(perm, h.perm.data(), sizeof(int32_t) * h.perm.size());

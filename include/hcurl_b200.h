@@ -224,11 +224,12 @@ int hcurl_dot(hcurl_ctx *ctx, const double *a_dev, const double *b_dev, int64_t 
  * (what blf->Assemble() resolves through the CSR sparsity in the reference,
  * /root/reference/src/equation_systems/equation_system.cpp:345).
  *  slot_code  [n_elem][nd]: dof index (bits 0..29) | sign flip (bit 31) of each element slot
- *  slot_stride  >= elems_per_patch: E-vector index of (slot s, patch position j) = s*slot_stride + j
+ *  slot_stride  >= elems_per_patch: E-vector index (in doubles) of (slot s, patch position j)
+ *             = (s>>1)*(2*slot_stride) + 2*j + (s&1)   (slots stored in pairs)
  *  outputs    perm [n_patch*epp] element at each patch position (-1 padding);
  *             blob_off [n_patch+1] start of each patch blob in 16-byte units; blob: per patch a
- *             16-word header, the dof list and the 16/32/64-bit slot-entry sections (layout in
- *             hephaestus_b200/csrc/patch.cpp). */
+ *             16-word header, the dof list, the 16/32/64-bit slot-entry sections (dof side) and the
+ *             per-slot local dof index table (element side); layout in hephaestus_b200/csrc/patch.cpp. */
 typedef struct hcurl_host_patches hcurl_host_patches;
 hcurl_host_patches *hcurl_host_patches_create(int nd, int64_t n_elem, int elems_per_patch, int slot_stride,
                                               int64_t n_dof, const double *centroid, const uint32_t *slot_code);
@@ -236,6 +237,8 @@ void hcurl_host_patches_destroy(hcurl_host_patches *p);
 int64_t hcurl_host_patches_count(const hcurl_host_patches *p);
 int64_t hcurl_host_patches_blob_words(const hcurl_host_patches *p);
 int64_t hcurl_host_patches_max_blob_words(const hcurl_host_patches *p);
+/* largest number of unique dofs in one patch (sizes the shared-memory x staging vector) */
+int64_t hcurl_host_patches_max_dofs(const hcurl_host_patches *p);
 int hcurl_host_patches_copy(const hcurl_host_patches *p, int32_t *perm, uint32_t *blob_off, uint32_t *blob);
 
 /* FP64 FMA micro-benchmark used for the roofline co-bound:

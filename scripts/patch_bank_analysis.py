@@ -1,39 +1,47 @@
-"""Offline model of the shared-memory wavefronts / global sectors of the per-dof gather (A) and
-scatter (C) phases of the patch kernel, from the host-built patch blobs (no GPU needed)."""
+"""Offline model of the shared-memory wavefronts of the patch kernel's two irregular phases, from the
+host-built patch blobs (no GPU needed):
+  pull  element side reads Xs[lidx[s][el]] (lanes = consecutive el; equal addresses broadcast)
+  sums  dof side reads E at the byte offsets of each dof's slots (lanes = consecutive dofs of a width class)
+8-byte accesses are served per half-warp; wavefronts = max distinct addresses falling in one of 16 banks."""
 import sys, os
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
-from hephaestus_b200 import fespace
 from test_host_patches import build, decode_patch, make
 
-def analyse(n=16, fe=64, nsample=40):
+
+def half_wavefronts(addr):
+    """addr: word (8-byte) addresses of one half-warp (distinct or equal) -> wavefronts"""
+    a = np.unique(addr)
+    return np.bincount(a % 16, minlength=16).max() if len(a) else 0
+
+
+def analyse(n=16, fe=64, nsample=24, nd=54):
     m, sp, code, cen, idx, sgn = make("hex", (n, n, n), 2, False)
-    # slot order used by the kernel does not matter for the statistics of random scatter, but use the real one
     perm, off, blob, st = build(sp, fe, code, cen)
     npatch = len(off) - 1
     rng = np.random.default_rng(0)
-    tot = dict(wf=0, ideal=0, sectors=0, reqs=0)
-    for k in rng.choice(npatch, min(nsample, npatch), replace=False):
-        dof, groups, ov = decode_patch(k, off, blob)
-        U = len(dof)
-        ent = np.full((U, 4), -1, np.int64)
-        for priv, u0, pd, e in groups:
-            ent[u0:u0 + len(pd), :e.shape[1]] = np.where(e == 0xFFFF, -1, e & 0x7FFF)
-        for w0 in range(0, U, 32):
-            lanes = np.arange(w0, min(U, w0 + 32))
-            tot["sectors"] += len(np.unique(dof[lanes] // 4)); tot["reqs"] += 1
-            for kk in range(4):
-                a = ent[lanes, kk]
-                if (a >= 0).sum() == 0: continue
-                for h in (lanes[:16], lanes[16:]):
-                    aa = ent[h, kk]; aa = aa[aa >= 0]
-                    if len(aa) == 0: continue
-                    tot["wf"] += np.bincount(aa % 16, minlength=16).max()
-                    tot["ideal"] += 1
-    ns = min(nsample, npatch)
-    print("n=%d fe=%d: per patch: slot wavefronts %.0f (ideal %.0f, x%.2f) per phase; gather sectors/request %.1f (%d requests)" % (
-        n, fe, tot["wf"] / ns, tot["ideal"] / ns, tot["wf"] / tot["ideal"], tot["sectors"] / tot["reqs"], tot["reqs"] / ns))
+    pull = ideal_pull = sums = ideal_sums = 0
+    ks = rng.choice(npatch, min(nsample, npatch), replace=False)
+    for k in ks:
+        dof, groups, ov, lidx, n_real = decode_patch(k, off, blob, nd, fe)
+        pos = lidx & 0x7FFF
+        for s in range(nd):
+            for h0 in range(0, n_real, 16):
+                pull += half_wavefronts(pos[s, h0:min(n_real, h0 + 16)]); ideal_pull += 1
+        # the kernel walks each width class separately
+        for w in range(3):
+            ent = groups[w][3]
+            for h0 in range(0, len(ent), 16):
+                for kk in range(ent.shape[1]):
+                    a = ent[h0:h0 + 16, kk]; a = a[a != 0xFFFF] // 8
+                    if len(a):
+                        sums += half_wavefronts(a); ideal_sums += 1
+    ns = len(ks)
+    print("n=%d fe=%d: wavefronts per patch: pull %.0f (ideal %.0f, x%.2f)   dof sums %.0f (ideal %.0f, x%.2f)" % (
+        n, fe, pull / ns, ideal_pull / ns, pull / ideal_pull, sums / ns, ideal_sums / ns, sums / ideal_sums))
+    return pull / ns, sums / ns
+
 
 if __name__ == "__main__":
     for fe in (32, 64):

@@ -40,8 +40,8 @@ ms2, _ = op.kernel_stats_ms()
 out = (C.c_ulonglong * 8)()
 lib.hcurl_debug_patch_profile(ctx.h, 0, out)
 tot = float(sum(out[:6]))
-names = ["blob wait", "A gather", "fwd transform", "exchange+op+bwd", "E store", "C scatter"]
-print("  with profiling %.4f ms; per-CTA cycles (share):" % ms2)
+names = ["prologue (per CTA)", "wait x gather", "pull + fwd", "op + bwd + next gather", "E store", "dof sums + stores"]
+print("  with profiling %.4f ms; cycles of thread 0 per patch (share):" % ms2)
 npatch = (mesh.n_elem + int(os.environ.get("HCURL_PATCH_FE", "64")) - 1) // int(os.environ.get("HCURL_PATCH_FE", "64"))
 for i, nm in enumerate(names):
-    print("  %-18s %9.0f  %5.1f%%" % (nm, out[i] / reps / npatch, 100.0 * out[i] / tot))
+    print("  %-24s %9.0f  %5.1f%%" % (nm, out[i] / reps / npatch, 100.0 * out[i] / tot))

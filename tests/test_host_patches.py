@@ -27,26 +27,43 @@ def build(space, fe, slot_code, centroid, stride=None):
     blob = np.zeros(nw, np.uint32)
     L.check(lib.hcurl_host_patches_copy(h, L.ptr(perm), L.ptr(off), L.ptr(blob)), "copy")
     assert lib.hcurl_host_patches_max_blob_words(h) == int(np.diff(off.astype(np.int64)).max()) * 4
+    assert lib.hcurl_host_patches_max_dofs(h) == max(int(blob[int(o) * 4]) for o in off[:-1])
     lib.hcurl_host_patches_destroy(h)
     return perm, off.astype(np.int64), blob, stride
 
 
-def decode_patch(k, off, blob):
+SHARED = 0x80000000
+
+
+def decode_patch(k, off, blob, nd=None, fe=None):
     """Blob of patch k (layout: hephaestus_b200/csrc/patch.cpp) ->
-    (dof ids (U,), [(private?, first u, dof ids, entries (n, W))] in kernel order, overflow words)."""
+    (dof ids (U,), [(first u, dof ids, private?, E byte offsets (n, W))] per width class, overflow words
+     [, lidx (nd, fe), number of real elements -- when nd and fe are given])."""
     B = blob[off[k] * 4:off[k + 1] * 4]
-    U, n1, n2, n4, nP1, nP2, nP4, nov, o16, o32, o64, oov = [int(v) for v in B[:12]]
-    assert np.all(B[12:16] == 0) and U == n1 + n2 + n4
-    assert o16 % 4 == 0 and o32 % 4 == 0 and o64 % 4 == 0 and oov % 4 == 0 and len(B) % 4 == 0
-    dof = B[16:16 + U].astype(np.int64)
+    U, n1, n2, n4, nP1, nP2, nP4, nov, o16, o32, o64, oov, olx, n_real = [int(v) for v in B[:14]]
+    assert np.all(B[14:16] == 0) and U == n1 + n2 + n4
+    assert o16 % 4 == 0 and o32 % 4 == 0 and o64 % 4 == 0 and oov % 4 == 0 and olx % 4 == 0 and len(B) % 4 == 0
+    word = B[16:16 + U].astype(np.int64)
+    assert np.all(word & 0x40000000 == 0)                        # essential flags are set by the operator
+    dof, priv = word & 0x3FFFFFFF, (word & SHARED) == 0
     sh = 16 * np.arange(4, dtype=np.uint64)
     e16 = B[o16:o16 + (n1 + 1) // 2].view(np.uint16)[:n1].astype(np.int64)[:, None]
     e32 = (B[o32:o32 + n2, None].astype(np.uint64) >> sh[None, :2]).astype(np.int64) & 0xFFFF
     e64 = (B[o64:o64 + 2 * n4].view(np.uint64)[:, None] >> sh[None]).astype(np.int64) & 0xFFFF
-    groups = [(True, 0, dof[:nP1], e16[:nP1]), (False, nP1, dof[nP1:n1], e16[nP1:]),
-              (True, n1, dof[n1:n1 + nP2], e32[:nP2]), (False, n1 + nP2, dof[n1 + nP2:n1 + n2], e32[nP2:]),
-              (True, n1 + n2, dof[n1 + n2:n1 + n2 + nP4], e64[:nP4]), (False, n1 + n2 + nP4, dof[n1 + n2 + nP4:], e64[nP4:])]
-    return dof, groups, B[oov:oov + nov].astype(np.int64)
+    groups = [(0, dof[:n1], priv[:n1], e16), (n1, dof[n1:n1 + n2], priv[n1:n1 + n2], e32),
+              (n1 + n2, dof[n1 + n2:], priv[n1 + n2:], e64)]
+    assert [int(g[2].sum()) for g in groups] == [nP1, nP2, nP4]
+    ov = B[oov:oov + nov].astype(np.int64)
+    if nd is None:
+        return dof, groups, ov
+    lidx = B[olx:olx + (nd * fe + 1) // 2].view(np.uint16)[:nd * fe].astype(np.int64).reshape(nd, fe)
+    assert olx + (nd * fe + 1) // 2 <= len(B)
+    return dof, groups, ov, lidx, n_real
+
+
+def e_index(s, j, st):
+    """E-vector position (in doubles) of slot s of patch position j: slots are stored in pairs."""
+    return (s >> 1) * (2 * st) + 2 * j + (s & 1)
 
 
 def make(kind, n, p, perturb):
@@ -98,48 +115,56 @@ def test_patch_lists_reproduce_gather_and_scatter(kind, n, p, fe, perturb):
     pmax = np.full(sp.ndof, -1)
     np.minimum.at(pmin, idx.ravel(), np.repeat(elem_patch, nd))
     np.maximum.at(pmax, idx.ravel(), np.repeat(elem_patch, nd))
+    sl = np.arange(nd)
     for k in range(npatch):
-        pd_all, groups, ov = decode_patch(k, off, blob)
+        pd_all, groups, ov, lidx, n_real_blob = decode_patch(k, off, blob, nd, fe)
         el = perm[k * fe:(k + 1) * fe]
         n_real = int((el >= 0).sum())
-        E = np.full(nd * st, np.nan)
-        Ey = np.zeros(nd * st)
+        assert n_real == n_real_blob
+        # element side: pull x through lidx (position in the patch dof list | sign bit 15)
+        Xs = x[pd_all]
+        neg_l = (lidx & 0x8000) != 0
+        pos_l = lidx & 0x7FFF
+        assert np.all(pos_l[:, :n_real] < len(pd_all))
         for j in range(n_real):
-            Ey[np.arange(nd) * st + j] = ye[el[j]]
+            xe = np.where(neg_l[:, j], -Xs[pos_l[:, j]], Xs[pos_l[:, j]])
+            assert np.array_equal(xe, sgn[el[j]] * x[idx[el[j]]])
+        # element results, signed on the element side, in the paired E layout
+        Ey = np.full((nd + (nd & 1)) * st, np.nan)
+        for j in range(n_real):
+            Ey[e_index(sl, j, st)] = np.where(neg_l[:, j], -ye[el[j]], ye[el[j]])
         n_slots = 0
-        for priv, u0, pd, ent in groups:
-            assert np.all(np.diff(pd) > 0)                     # ascending inside a group
+        for u0, pd, priv, ent in groups:
+            # ascending global index up to the bank-spreading permutation inside aligned runs of 16 positions
+            run = (u0 + np.arange(len(pd))) // 16
+            srt = np.sort(pd)
+            assert np.all(np.diff(srt) > 0)
+            for r in np.unique(run):
+                assert np.array_equal(np.sort(pd[run == r]), srt[run == r])
+            assert np.array_equal(pd, pd_all[u0:u0 + len(pd)])
             W = ent.shape[1]
             used = ent != 0xFFFF
             if W < 4:
                 assert used.all()
             else:
                 assert used[:, :3].all()                         # only the 4th entry may be unused
+            assert np.all(ent[used] % 8 == 0)
             n_slots += int(used.sum())
-            if priv:
-                assert np.all(pmin[pd] == pmax[pd]) and np.all(touched[pd] == 0)
-            elif kind == "hex":
-                assert np.all(pmin[pd] != pmax[pd])
+            assert np.all(pmin[pd[priv]] == pmax[pd[priv]]) and np.all(touched[pd[priv]] == 0)
+            if kind == "hex":
+                assert np.all(pmin[pd[~priv]] != pmax[pd[~priv]])
             for u in range(len(pd)):
-                e = ent[u][used[u]]
-                pos, neg = e & 0x7FFF, (e & 0x8000) != 0
-                E[pos] = np.where(neg, -x[pd[u]], x[pd[u]])
-                v = np.sum(np.where(neg, -Ey[pos], Ey[pos]))
-                if priv:
+                v = np.sum(Ey[ent[u][used[u]] // 8])
+                if priv[u]:
                     y[pd[u]] = v
                 else:
                     y[pd[u]] += v
                 touched[pd[u]] += 1
         assert n_slots + len(ov) == n_real * nd
-        n4_priv_end = groups[4][1] + len(groups[4][2])
-        assert np.all((ov >> 16) >= n4_priv_end)                # dofs with overflow are shared 3..4-slot dofs
+        u_ov = ov >> 16
+        assert np.all(u_ov >= groups[2][0]) and not np.any(groups[2][2][u_ov - groups[2][0]])   # overflow: shared 3..4-slot dofs
         for w in ov:
-            u, pos, neg = w >> 16, w & 0x7FFF, (w & 0x8000) != 0
-            E[pos] = -x[pd_all[u]] if neg else x[pd_all[u]]
-            y[pd_all[u]] += -Ey[pos] if neg else Ey[pos]
-        for j in range(n_real):
-            xe = E[np.arange(nd) * st + j]
-            assert np.array_equal(xe, sgn[el[j]] * x[idx[el[j]]])
+            y[pd_all[w >> 16]] += Ey[(w & 0xFFFF) // 8]
     assert np.all(touched >= 1)
     np.testing.assert_allclose(y, y_ref, rtol=0, atol=1e-13)
 
@@ -156,7 +181,7 @@ def test_structured_cube_patches_are_blocks():
         # (here blocks touch the domain boundary, which only adds private dofs)
         pd, groups, ov = decode_patch(k, off, blob)
         assert len(pd) == 1944
-        assert sum(len(g[2]) for g in groups if g[0]) >= 1176
+        assert sum(int(g[2].sum()) for g in groups) >= 1176
 
 
 def test_bad_arguments_are_reported():
