@@ -199,9 +199,10 @@ int op_apply_ext(hcurl_op *op, double *d_x, double *d_y, bool constrained, doubl
   if (op->ring_ok) { e0 = op->ring0[op->ring_n % hcurl_op::RING]; e1 = op->ring1[op->ring_n % hcurl_op::RING]; op->ring_n++; op->ev0 = e0; op->ev1 = e1; }
   if (op->timed) HC_CUDA(cudaEventRecord(e0, ctx->stream));
   int rc;
-  if (hex_patch_eligible(op)) rc = hex_patch_launch(op, constrained, d_x, d_y, scale, accumulate);
-  else if (hex_fast_eligible(op)) rc = hex_fast_launch(op, constrained, d_x, d_y, scale);
-  else rc = (sp->geom == HCURL_GEOM_HEX) ? hex_apply_launch(op, map, d_x, d_y, scale) : tet_apply_launch(op, map, d_x, d_y, scale);
+  // the patch kernel moves aligned pairs of doubles
+  if (hex_patch_eligible(op) && (((uintptr_t)d_x | (uintptr_t)d_y) & 15) == 0) { op->last_kernel = 3; rc = hex_patch_launch(op, constrained, d_x, d_y, scale, accumulate); }
+  else if (hex_fast_eligible(op)) { op->last_kernel = 2; rc = hex_fast_launch(op, constrained, d_x, d_y, scale); }
+  else { op->last_kernel = 1; rc = (sp->geom == HCURL_GEOM_HEX) ? hex_apply_launch(op, map, d_x, d_y, scale) : tet_apply_launch(op, map, d_x, d_y, scale); }
   if (rc) return rc;
   if (op->timed) HC_CUDA(cudaEventRecord(e1, ctx->stream));
   if (exchange_reduce(sp, d_y)) return 1;
@@ -475,6 +476,7 @@ int hcurl_op_set_kernel(hcurl_op *op, int which) {
   op->kernel_sel = which;
   return 0;
 }
+int hcurl_op_last_kernel(const hcurl_op *op) { return op->last_kernel; }
 int hcurl_op_qpts_curl(const hcurl_op *op) { return op->sp->geom == HCURL_GEOM_HEX ? op->qc * op->qc * op->qc : 1; }
 int hcurl_op_qpts_mass(const hcurl_op *op) { return op->sp->geom == HCURL_GEOM_HEX ? op->qm * op->qm * op->qm : 1; }
 

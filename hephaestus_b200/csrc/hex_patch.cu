@@ -9,6 +9,10 @@
 //    (patch.cpp); x is gathered once per unique patch dof into a shared-memory staging vector, the
 //    element side pulls its 54 inputs from it through a per-slot table, y is summed per patch dof from
 //    a shared-memory E-vector; private dofs are plain stores, only patch-boundary dofs use RED.
+//  * shared-memory wavefronts and table bytes of that dof side  ->  the unit of the dof side is a PAIR:
+//    the two order-2 dofs along one edge / face line / interior line sit next to each other in the
+//    global numbering and are always used together (possibly swapped and sign-flipped by the element's
+//    orientation), so gathers, staging, tables, sums and private stores all work on aligned double2.
 //  * memory latency (62 % of a CTA's life in the one-patch-per-CTA version, profiles/r1g)  ->  the
 //    kernel is PERSISTENT and software-pipelined: blob + geometry factors arrive by TMA bulk copies
 //    (cp.async.bulk + mbarrier) two patches ahead, the x gather of the next patch runs as 8-byte
@@ -174,7 +178,7 @@ struct PatchArgs {
   double *y;
   double scale;
   uint32_t blob_cap_bytes;   // shared-memory room reserved for one blob (multiple of 16)
-  uint32_t xs_cap_bytes;     // room for the x staging vector (max patch dofs * 8, multiple of 16)
+  uint32_t xs_cap_bytes;     // room for the x staging vector (max patch pairs * 16)
   unsigned long long *prof;  // null, or 8 counters: cycles of thread 0 per phase summed over patches (scripts/phase_profile.py)
 };
 #define PROF_MARK(i)                                                                         \
@@ -184,9 +188,20 @@ struct PatchArgs {
     t_prev = t_now;                                                                          \
   }
 
-// sign flip carried in bit 15 of a 16-bit table entry
-__device__ __forceinline__ double apply_sign(double v, uint32_t entry) {
-  return __hiloint2double(__double2hiint(v) ^ (int)((entry << 16) & 0x80000000u), __double2loint(v));
+// orientation of an element slot pair relative to its global pair, carried in bits 13..15 of a lidx entry
+// (PAIR_SWAP / PAIR_NEG1 / PAIR_NEG0 of the slot code >> 16): local = (s0 * g[swap], s1 * g[!swap])
+__device__ __forceinline__ double flip(double v, uint32_t sign_bit31) {
+  return __hiloint2double(__double2hiint(v) ^ (int)sign_bit31, __double2loint(v));
+}
+__device__ __forceinline__ void pair_to_local(const double2 g, const uint32_t l, double &x0, double &x1) {
+  const bool sw = l & 0x2000u;
+  x0 = flip(sw ? g.y : g.x, (l << 16) & 0x80000000u);
+  x1 = flip(sw ? g.x : g.y, (l << 17) & 0x80000000u);
+}
+__device__ __forceinline__ double2 local_to_pair(const double y0, const double y1, const uint32_t l) {
+  const bool sw = l & 0x2000u;
+  const double a = flip(y0, (l << 16) & 0x80000000u), b = flip(y1, (l << 17) & 0x80000000u);
+  return sw ? make_double2(b, a) : make_double2(a, b);
 }
 
 // ---- async copies -----------------------------------------------------------------------------
@@ -213,31 +228,31 @@ __device__ __forceinline__ void mbar_wait(uint64_t *mbar, uint32_t parity) {
                  : "memory");
   } while (!done);
 }
-// 8-byte asynchronous gather global -> shared (LDGSTS), no register staging
-__device__ __forceinline__ void gather8_async(double *dst, const double *src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
+// 16-byte asynchronous gather global -> shared (LDGSTS, L1 bypassed), no register staging
+__device__ __forceinline__ void gather16_async(double2 *dst, const double2 *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void gather_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void gather_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // Persistent, software-pipelined patch kernel.  One CTA walks patches k = blockIdx.x, += gridDim.x.
 // While patch i is being computed, the blob of patch i+1 (TMA bulk copy, issued an iteration ago)
-// is used to launch the x gather of patch i+1 as 8-byte cp.async copies into the staging vector Xs,
-// and the blob + geometry factors of patch i+2 are requested when patch i retires.
-//   Xs  [max dofs]        patch-local x, position u = order of the blob's dof list
-//   E   [27][FE+1] x 2    element slot pairs (double2): modal coefficients, then element results
+// is used to launch the x gather of patch i+1 as 16-byte cp.async copies into the staging vector Xs,
+// and the blob of patch i+2 is requested when patch i retires.
+//   Xs  [max pairs]       patch-local x pairs, position u = order of the blob's dof list
+//   E   [27][FE+1]        element slot pairs (double2): modal coefficients, then element results
 template <int FE, int MINB, bool ACC, bool PROF>
-__global__ void __launch_bounds__(3 * FE, MINB)
+__global__ void __maxnreg__(MINB >= 3 ? 112 : 168)
 hex_patch_modal_p2_kernel(const PatchArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NT = 3 * FE, ST = FE + 1;
-  constexpr uint32_t EDATA_BYTES = 12 * FE * sizeof(double);
   uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw);  // [2]
   unsigned char *blobB = smem_raw + 16;
-  unsigned char *edataB = blobB + 2 * (size_t)a.blob_cap_bytes;
-  double *Xs = reinterpret_cast<double *>(edataB + 2 * EDATA_BYTES);
+  double2 *Xs = reinterpret_cast<double2 *>(blobB + 2 * (size_t)a.blob_cap_bytes);
   double2 *E2 = reinterpret_cast<double2 *>(reinterpret_cast<unsigned char *>(Xs) + a.xs_cap_bytes);
   const unsigned char *Eb = reinterpret_cast<const unsigned char *>(E2);
+  const double2 *x2 = reinterpret_cast<const double2 *>(a.x);
+  double2 *y2 = reinterpret_cast<double2 *>(a.y);
   const int tid = threadIdx.x;
   long long t_prev = PROF ? clock64() : 0;
   unsigned long long prof_acc[6] = {0, 0, 0, 0, 0, 0};
@@ -250,23 +265,30 @@ hex_patch_modal_p2_kernel(const PatchArgs a) {
             oK20 = sym6(c2, c) * FE + el, oM00 = (6 + sym6(c, c)) * FE + el, oM01 = (6 + sym6(c, c1)) * FE + el,
             oM02 = (6 + sym6(c, c2)) * FE + el;
 
-  // request blob + geometry factors of patch k into buffer b (thread 0)
-  auto request = [&](int64_t k, int b, uint32_t o0, uint32_t o1) {
+  // request the blob of patch k into buffer b (thread 0)
+  auto request = [&](int b, uint32_t o0, uint32_t o1) {
     const uint32_t bytes = (o1 - o0) * 16u;
-    mbar_expect_tx(mbar + b, bytes + EDATA_BYTES);
+    mbar_expect_tx(mbar + b, bytes);
     bulk_load(mbar + b, blobB + (size_t)b * a.blob_cap_bytes, a.blob + (size_t)o0 * 4, bytes);
-    bulk_load(mbar + b, edataB + (size_t)b * EDATA_BYTES, a.edata + (size_t)k * 12 * FE, EDATA_BYTES);
   };
   // launch the x gather of the patch whose blob sits in buffer b
   auto gather = [&](int b) {
     const uint32_t *B = reinterpret_cast<const uint32_t *>(blobB + (size_t)b * a.blob_cap_bytes);
     const uint32_t U = B[0];
     const uint32_t *dof = B + PatchHost::HDR;
-#pragma unroll 4
+#pragma unroll 2
     for (uint32_t u = tid; u < U; u += NT) {
       const uint32_t m = dof[u];
-      if (m & MAP_ESS) Xs[u] = 0.0;
-      else gather8_async(Xs + u, a.x + (m & MAP_IDX));
+      if (!(m & (PATCH_ESS0 | PATCH_ESS1))) gather16_async(Xs + u, x2 + (m & PATCH_IDX));
+      else {  // essential dofs enter as zeros (rare: synchronous)
+        double2 v = make_double2(0.0, 0.0);
+        if ((m & (PATCH_ESS0 | PATCH_ESS1)) != (PATCH_ESS0 | PATCH_ESS1)) {
+          v = __ldg(x2 + (m & PATCH_IDX));
+          if (m & PATCH_ESS0) v.x = 0.0;
+          if (m & PATCH_ESS1) v.y = 0.0;
+        }
+        Xs[u] = v;
+      }
     }
     gather_commit();
   };
@@ -276,8 +298,8 @@ hex_patch_modal_p2_kernel(const PatchArgs a) {
     mbar_init(mbar + 1, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    request(k0, 0, __ldg(a.blob_off + k0), __ldg(a.blob_off + k0 + 1));
-    if (n_it > 1) request(k0 + kstep, 1, __ldg(a.blob_off + k0 + kstep), __ldg(a.blob_off + k0 + kstep + 1));
+    request(0, __ldg(a.blob_off + k0), __ldg(a.blob_off + k0 + 1));
+    if (n_it > 1) request(1, __ldg(a.blob_off + k0 + kstep), __ldg(a.blob_off + k0 + kstep + 1));
   }
   __syncthreads();  // mbarriers initialised
   mbar_wait(mbar, 0);
@@ -288,27 +310,26 @@ hex_patch_modal_p2_kernel(const PatchArgs a) {
     const int b = it & 1;
     const int64_t k = k0 + (int64_t)it * kstep;
     const uint32_t *B = reinterpret_cast<const uint32_t *>(blobB + (size_t)b * a.blob_cap_bytes);
-    const double *g = reinterpret_cast<const double *>(edataB + (size_t)b * EDATA_BYTES);
     uint32_t q0 = 0, q1 = 0;  // blob extent of the patch requested when this one retires
     if (tid == 0 && it + 2 < n_it) { q0 = __ldg(a.blob_off + k + 2 * kstep); q1 = __ldg(a.blob_off + k + 2 * kstep + 1); }
+    // affine geometry factors of my element: issued now, consumed after the forward transform
+    const double *g = a.edata + (size_t)k * 12 * FE;
+    double K11 = __ldg(g + oK11), K10 = __ldg(g + oK10), K12 = __ldg(g + oK12), K22 = __ldg(g + oK22), K20 = __ldg(g + oK20),
+           M00 = __ldg(g + oM00), M01 = __ldg(g + oM01), M02 = __ldg(g + oM02);
     gather_wait_all();
     __syncthreads();  // Xs complete and visible
     PROF_MARK(1)  // wait for the x gather
     const bool ok = (uint32_t)el < B[13];
     // ---- pull the element inputs through the per-slot table, forward transform
     double Am[18];
-    double K11, K10, K12, K22, K20, M00, M01, M02;
+    uint32_t lx[9];
     if (ok) {
-      const uint16_t *lidx = reinterpret_cast<const uint16_t *>(B + B[12]) + (c * 18) * FE + el;
+      const uint16_t *lidx = reinterpret_cast<const uint16_t *>(B + B[12]) + (c * 9) * FE + el;
       double X[18];
 #pragma unroll
-      for (int t = 0; t < 18; t++) {
-        const uint32_t l = lidx[t * FE];
-        X[t] = apply_sign(Xs[l & 0x7fffu], l);
-      }
-      const double sc = 0.25 * a.scale;  // 1/4: the open transforms are applied without their 1/2
-      K11 = sc * g[oK11]; K10 = sc * g[oK10]; K12 = sc * g[oK12]; K22 = sc * g[oK22]; K20 = sc * g[oK20];
-      M00 = sc * g[oM00]; M01 = sc * g[oM01]; M02 = sc * g[oM02];
+      for (int r = 0; r < 9; r++) lx[r] = lidx[r * FE];
+#pragma unroll
+      for (int r = 0; r < 9; r++) pair_to_local(Xs[lx[r] & 0x1fffu], lx[r], X[2 * r], X[2 * r + 1]);
       modal_fwd(X, Am);
       double2 *Eown = E2 + (c * 9) * ST + el;
 #pragma unroll
@@ -337,6 +358,8 @@ hex_patch_modal_p2_kernel(const PatchArgs a) {
           Cm[IC(m0, m1, 0)] = v.x;
           Cm[IC(m0, m1, 1)] = v.y;
         }
+      const double sc = 0.25 * a.scale;  // 1/4: the open transforms are applied without their 1/2
+      K11 *= sc; K10 *= sc; K12 *= sc; K22 *= sc; K20 *= sc; M00 *= sc; M01 *= sc; M02 *= sc;
       double Yh[18];
       modal_op(Am, Bm, Cm, M00, M01, M02, K11, K10, K12, K22, K20, K12, Yh);
       modal_bwd(Yh, Y);
@@ -349,15 +372,13 @@ hex_patch_modal_p2_kernel(const PatchArgs a) {
     __syncthreads();  // everyone has read the modal coefficients
     PROF_MARK(3)  // exchange + modal operator + backward transform + next gather issue
     if (ok) {
-      const uint16_t *lidx = reinterpret_cast<const uint16_t *>(B + B[12]) + (c * 18) * FE + el;
       double2 *Eown = E2 + (c * 9) * ST + el;
 #pragma unroll
-      for (int r = 0; r < 9; r++)
-        Eown[r * ST] = make_double2(apply_sign(Y[2 * r], lidx[(2 * r) * FE]), apply_sign(Y[2 * r + 1], lidx[(2 * r + 1) * FE]));
+      for (int r = 0; r < 9; r++) Eown[r * ST] = local_to_pair(Y[2 * r], Y[2 * r + 1], lx[r]);
     }
     __syncthreads();
     PROF_MARK(4)  // element results to shared memory
-    // ---- sum the slots of every patch dof; private dofs are plain stores, shared ones RED
+    // ---- sum the slots of every patch pair; private pairs are plain 16-byte stores, shared ones RED
     {
       const uint32_t n1 = B[1], n2 = B[2], n4 = B[3], nov = B[7];
       const uint32_t *dof = B + PatchHost::HDR;
@@ -365,76 +386,80 @@ hex_patch_modal_p2_kernel(const PatchArgs a) {
       const uint32_t *e32 = B + B[9];
       const uint2 *e64 = reinterpret_cast<const uint2 *>(B + B[10]);
       const uint32_t *ovf = B + B[11];
-#define E_AT(off) (*reinterpret_cast<const double *>(Eb + (off)))
-#define EMIT(m, v)                                                            \
-  if (!((m) & MAP_ESS)) {                                                     \
-    double *dst = a.y + ((m) & MAP_IDX);                                      \
-    if ((m) & PATCH_SHARED) atomicAdd(dst, (v));                              \
-    else *dst = ACC ? *dst + (v) : (v);                                       \
-  }
-      constexpr int UN = 4;  // dofs in flight per thread: table reads, then E reads, then the stores
+      constexpr uint32_t SKIP = PATCH_ESS0 | PATCH_ESS1;
+#define E_AT(off) (*reinterpret_cast<const double2 *>(Eb + (off)))
+      auto emit = [&](const uint32_t m, const double2 v) {
+        double2 *dst = y2 + (m & PATCH_IDX);
+        if (!(m & (SKIP | PATCH_SHARED))) {
+          if (ACC) { const double2 o = *dst; *dst = make_double2(o.x + v.x, o.y + v.y); }
+          else *dst = v;
+        } else if ((m & SKIP) != SKIP) {
+          if (m & PATCH_SHARED) {
+            if (!(m & PATCH_ESS0)) atomicAdd(&dst->x, v.x);
+            if (!(m & PATCH_ESS1)) atomicAdd(&dst->y, v.y);
+          } else {
+            if (!(m & PATCH_ESS0)) dst->x = ACC ? dst->x + v.x : v.x;
+            if (!(m & PATCH_ESS1)) dst->y = ACC ? dst->y + v.y : v.y;
+          }
+        }
+      };
+      constexpr int UN = 2;  // pairs in flight per thread: table reads, then E reads, then the stores
       for (uint32_t r0 = tid; r0 < n1; r0 += UN * NT) {
         uint32_t m[UN], o[UN];
-        double v[UN];
+        double2 v[UN];
 #pragma unroll
         for (int i = 0; i < UN; i++) {
           const uint32_t r = r0 + i * NT;
-          m[i] = r < n1 ? dof[r] : MAP_ESS;
+          m[i] = r < n1 ? dof[r] : SKIP;
           o[i] = r < n1 ? e16[r] : 0u;
         }
 #pragma unroll
         for (int i = 0; i < UN; i++) v[i] = E_AT(o[i]);
 #pragma unroll
-        for (int i = 0; i < UN; i++) EMIT(m[i], v[i])
+        for (int i = 0; i < UN; i++) emit(m[i], v[i]);
       }
       dof += n1;
       for (uint32_t r0 = tid; r0 < n2; r0 += UN * NT) {
         uint32_t m[UN], o[UN];
-        double v[UN];
+        double2 v[UN];
 #pragma unroll
         for (int i = 0; i < UN; i++) {
           const uint32_t r = r0 + i * NT;
-          m[i] = r < n2 ? dof[r] : MAP_ESS;
+          m[i] = r < n2 ? dof[r] : SKIP;
           o[i] = r < n2 ? e32[r] : 0u;
         }
 #pragma unroll
-        for (int i = 0; i < UN; i++) v[i] = E_AT(o[i] & 0xffffu) + E_AT(o[i] >> 16);
+        for (int i = 0; i < UN; i++) {
+          const double2 p = E_AT(o[i] & 0xffffu), q = E_AT(o[i] >> 16);
+          v[i] = make_double2(p.x + q.x, p.y + q.y);
+        }
 #pragma unroll
-        for (int i = 0; i < UN; i++) EMIT(m[i], v[i])
+        for (int i = 0; i < UN; i++) emit(m[i], v[i]);
       }
       dof += n2;
-      for (uint32_t r0 = tid; r0 < n4; r0 += 2 * NT) {
-        uint32_t m[2];
-        uint2 o[2];
-        double v[2];
-#pragma unroll
-        for (int i = 0; i < 2; i++) {
-          const uint32_t r = r0 + i * NT;
-          m[i] = r < n4 ? dof[r] : MAP_ESS;
-          o[i] = r < n4 ? e64[r] : make_uint2(0u, 0xffff0000u);
-        }
-#pragma unroll
-        for (int i = 0; i < 2; i++) {
-          v[i] = (E_AT(o[i].x & 0xffffu) + E_AT(o[i].x >> 16)) + E_AT(o[i].y & 0xffffu);
-          if ((o[i].y >> 16) != 0xffffu) v[i] += E_AT(o[i].y >> 16);
-        }
-#pragma unroll
-        for (int i = 0; i < 2; i++) EMIT(m[i], v[i])
+      for (uint32_t r = tid; r < n4; r += NT) {
+        const uint32_t m = dof[r];
+        const uint2 o = e64[r];
+        const double2 p = E_AT(o.x & 0xffffu), q = E_AT(o.x >> 16), s = E_AT(o.y & 0xffffu);
+        double2 v = make_double2((p.x + q.x) + s.x, (p.y + q.y) + s.y);
+        if ((o.y >> 16) != 0xffffu) { const double2 t = E_AT(o.y >> 16); v.x += t.x; v.y += t.y; }
+        emit(m, v);
       }
       dof = B + PatchHost::HDR;
       for (uint32_t t = tid; t < nov; t += NT) {  // slots beyond four (unstructured meshes)
         const uint32_t e = ovf[t], m = dof[e >> 16];
-        if (m & MAP_ESS) continue;
-        atomicAdd(a.y + (m & MAP_IDX), E_AT(e & 0xffffu));
+        const double2 v = E_AT(e & 0xffffu);
+        double2 *dst = y2 + (m & PATCH_IDX);
+        if (!(m & PATCH_ESS0)) atomicAdd(&dst->x, v.x);
+        if (!(m & PATCH_ESS1)) atomicAdd(&dst->y, v.y);
       }
-#undef EMIT
 #undef E_AT
     }
     __syncthreads();  // blob buffer b and E are free
     PROF_MARK(5)  // dof sums + stores
     if (tid == 0 && it + 2 < n_it) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      request(k + 2 * kstep, b, q0, q1);
+      request(b, q0, q1);
     }
   }
   if (PROF && tid == 0)
@@ -472,14 +497,17 @@ __global__ void patch_edata_kernel(const int64_t n_pos, const int FE, const int3
     }
 }
 
-// OR the essential flag into the dof words of every patch blob (one CTA per patch)
+// OR the essential flags of both doubles into the pair words of every patch blob (one CTA per patch)
 __global__ void patch_flag_kernel(const uint32_t *__restrict__ blob_off, const double *__restrict__ flag,
                                   uint32_t *__restrict__ blob) {
   uint32_t *B = blob + (size_t)blob_off[blockIdx.x] * 4;
   const uint32_t U = B[0];
   for (uint32_t u = threadIdx.x; u < U; u += blockDim.x) {
-    const uint32_t m = B[PatchHost::HDR + u];
-    if (flag[m & MAP_IDX] != 0.0) B[PatchHost::HDR + u] = m | MAP_ESS;
+    uint32_t m = B[PatchHost::HDR + u];
+    const double2 f = reinterpret_cast<const double2 *>(flag)[m & PATCH_IDX];
+    if (f.x != 0.0) m |= PATCH_ESS0;
+    if (f.y != 0.0) m |= PATCH_ESS1;
+    B[PatchHost::HDR + u] = m;
   }
 }
 
@@ -528,12 +556,18 @@ static int upload(T *&dst, const std::vector<T> &src) {
   return 0;
 }
 
-// dynamic shared memory of the patch kernel: 2 mbarriers | 2 blob buffers | 2 geometry buffers | Xs | E
-static size_t patch_smem_bytes(int FE, uint32_t max_blob_words, uint32_t max_dofs) {
-  const size_t blob_cap = ((size_t)max_blob_words * 4 + 15u) & ~(size_t)15u, xs_cap = ((size_t)max_dofs * 8 + 15u) & ~(size_t)15u;
-  return 16 + 2 * blob_cap + 2 * (size_t)12 * FE * sizeof(double) + xs_cap + (size_t)27 * (FE + 1) * 16;
+// dynamic shared memory of the patch kernel: 2 mbarriers | 2 blob buffers | Xs | E
+static size_t patch_smem_bytes(int FE, uint32_t max_blob_words, uint32_t max_units) {
+  const size_t blob_cap = ((size_t)max_blob_words * 4 + 15u) & ~(size_t)15u;
+  return 16 + 2 * blob_cap + (size_t)max_units * 16 + (size_t)27 * (FE + 1) * 16;
 }
 
+// The dof side of the patch kernel works on aligned PAIRS of doubles.  In the rotated slot layout the
+// slots 2r, 2r+1 of an element are the two order-2 dofs along one line (open index 0, 1); MFEM numbers
+// the dofs of an edge / face / interior consecutively, so they are the doubles 2q, 2q+1 of the
+// extended vector -- in this order, or swapped when the element sees the line reversed -- each with its
+// own sign.  Checked here for every element slot pair; a map that does not have this structure (or an
+// odd-length vector) simply does not get the patch path.
 int hex_patch_build(hcurl_space *sp, const double *elem_xyz, const int32_t *elem_ldof, const int32_t *l2e) {
   if (sp->geom != HCURL_GEOM_HEX || sp->order != 2 || sp->geom_order != 1) return 0;
   const char *off = getenv("HCURL_NO_PATCH");
@@ -541,23 +575,30 @@ int hex_patch_build(hcurl_space *sp, const double *elem_xyz, const int32_t *elem
   int FE = 64;
   if (const char *s = getenv("HCURL_PATCH_FE")) FE = atoi(s);
   if (FE != 32 && FE != 64 && FE != 128) { set_error("HCURL_PATCH_FE must be 32, 64 or 128"); return 1; }
-  const int nd = sp->nd, p = sp->order;
+  const int nd = sp->nd, p = sp->order, np = nd / 2;
   const int64_t ne = sp->n_elem;
+  if (sp->n_ext() & 1) return 0;
   std::vector<int> loc, sgn;
   nd_hex_dof_map(p, loc, sgn);
   std::vector<int> tens(nd);
   for (int s = 0; s < nd; s++) tens[s] = hex_rot_slot_to_tensor(p, s);
-  std::vector<uint32_t> code((size_t)ne * nd);
+  std::vector<uint32_t> code((size_t)ne * np);
   std::vector<double> cen((size_t)ne * 3);
   for (int64_t e = 0; e < ne; e++) {
-    for (int s = 0; s < nd; s++) {
-      const int t = tens[s];
-      const int32_t v = elem_ldof[e * nd + loc[t]];
-      const int32_t kk = v >= 0 ? v : -1 - v;
-      bool neg = v < 0;
-      if (sgn[t] < 0) neg = !neg;
-      const uint32_t ext = l2e ? (uint32_t)l2e[kk] : (uint32_t)kk;
-      code[(size_t)e * nd + s] = ext | (neg ? MAP_NEG : 0u);
+    for (int r = 0; r < np; r++) {
+      uint32_t ext[2];
+      bool neg[2];
+      for (int h = 0; h < 2; h++) {
+        const int t = tens[2 * r + h];
+        const int32_t v = elem_ldof[e * nd + loc[t]];
+        const int32_t kk = v >= 0 ? v : -1 - v;
+        neg[h] = (v < 0) != (sgn[t] < 0);
+        ext[h] = l2e ? (uint32_t)l2e[kk] : (uint32_t)kk;
+      }
+      const bool swap = ext[0] > ext[1];
+      const uint32_t lo = swap ? ext[1] : ext[0], hi = swap ? ext[0] : ext[1];
+      if ((lo & 1u) || hi != lo + 1) return 0;  // not an aligned pair: no patch path for this space
+      code[(size_t)e * np + r] = (lo >> 1) | (swap ? PAIR_SWAP : 0u) | (neg[0] ? PAIR_NEG0 : 0u) | (neg[1] ? PAIR_NEG1 : 0u);
     }
     for (int d = 0; d < 3; d++) {
       double c = 0.0;
@@ -566,7 +607,7 @@ int hex_patch_build(hcurl_space *sp, const double *elem_xyz, const int32_t *elem
     }
   }
   PatchHost H;
-  if (build_patches(nd, ne, FE, FE + 1, sp->n_ext(), cen.data(), code.data(), H)) return 1;
+  if (build_patches(np, ne, FE, FE + 1, 16, sp->n_ext() / 2, cen.data(), code.data(), H)) return 1;
   HC_CUDA(cudaSetDevice(sp->ctx->device));
   PatchSet &P = sp->patch;
   P.FE = FE; P.stride = H.stride; P.n_patch = H.n_patch;
@@ -641,14 +682,18 @@ int hex_patch_launch(hcurl_op *op, bool constrained, const double *d_x, double *
   a.n_patch = P.n_patch; a.blob_off = P.d_blob_off;
   a.blob = (constrained && op->d_blob_ess) ? op->d_blob_ess : P.d_blob;
   a.blob_cap_bytes = (P.max_blob_words * 4 + 15u) & ~15u;
-  a.xs_cap_bytes = (P.max_dofs * 8 + 15u) & ~15u;
+  a.xs_cap_bytes = P.max_dofs * 16u;
   a.edata = op->d_edataP; a.x = d_x; a.y = d_y; a.scale = scale;
   a.prof = g_patch_prof;
   if (a.prof && accumulate) a.prof = nullptr;
   const size_t smem = patch_smem_bytes(P.FE, P.max_blob_words, P.max_dofs);
   int rc = 1;
-  if (P.FE == 32) rc = launch_fe<32, 4>(a, P.n_patch, ctx->sm_count, smem, accumulate, ctx->stream);
-  else if (P.FE == 64) rc = launch_fe<64, 2>(a, P.n_patch, ctx->sm_count, smem, accumulate, ctx->stream);
+  // register budget: 168 per thread (2 CTAs of 192 threads per SM) or 112 (3 CTAs); the tighter one spills
+  static const bool dense = [] { const char *s = getenv("HCURL_PATCH_DENSE"); return s && s[0] == '1'; }();
+  if (P.FE == 32) rc = dense ? launch_fe<32, 6>(a, P.n_patch, ctx->sm_count, smem, accumulate, ctx->stream)
+                             : launch_fe<32, 4>(a, P.n_patch, ctx->sm_count, smem, accumulate, ctx->stream);
+  else if (P.FE == 64) rc = dense ? launch_fe<64, 3>(a, P.n_patch, ctx->sm_count, smem, accumulate, ctx->stream)
+                                  : launch_fe<64, 2>(a, P.n_patch, ctx->sm_count, smem, accumulate, ctx->stream);
   else if (P.FE == 128) rc = launch_fe<128, 1>(a, P.n_patch, ctx->sm_count, smem, accumulate, ctx->stream);
   if (rc) return rc;
   HC_CUDA(cudaGetLastError());

@@ -26,8 +26,13 @@ bool cuda_ok(cudaError_t e, const char *what);
 static constexpr uint32_t MAP_IDX = 0x3fffffffu;
 static constexpr uint32_t MAP_ESS = 0x40000000u;
 static constexpr uint32_t MAP_NEG = 0x80000000u;
-// patch blobs (patch.cpp): dof words carry no sign; bit 31 marks dofs shared with other patches
+// patch blobs (patch.cpp): unit index in bits 0..28, bits 29/30 essential flags of the unit's first /
+// second double, bit 31 marks units shared with other patches.  Slot codes handed to build_patches
+// carry orientation flags in bits 29..31 instead.
+static constexpr uint32_t PATCH_IDX = 0x1fffffffu;
+static constexpr uint32_t PATCH_ESS0 = 0x20000000u, PATCH_ESS1 = 0x40000000u;
 static constexpr uint32_t PATCH_SHARED = 0x80000000u;
+static constexpr uint32_t PAIR_SWAP = 0x20000000u, PAIR_NEG1 = 0x40000000u, PAIR_NEG0 = 0x80000000u;
 
 // ---------------------------------------------------------------- basis ----
 void gauss_legendre01(int n, double *x, double *w);
@@ -75,7 +80,7 @@ struct PatchHost {
   uint32_t max_blob_words = 0;
   uint32_t max_dofs = 0;          // largest number of unique dofs of one patch
 };
-int build_patches(int nd, int64_t n_elem, int FE, int stride, int64_t n_ext, const double *centroid,
+int build_patches(int nd, int64_t n_elem, int FE, int stride, int unit_bytes, int64_t n_ext, const double *centroid,
                   const uint32_t *slot_code, PatchHost &out);
 // slot s of the rotated per-component layout (hex_patch.cu) -> standard tensor index
 int hex_rot_slot_to_tensor(int p, int slot);
@@ -166,6 +171,7 @@ struct hcurl_op {
   double *d_edataP = nullptr;      // [n_patch][12][FE] affine geometry factors in patch order
   bool edataP_valid = false;
   int kernel_sel = 0;              // 0 auto, 1 generic, 2 element-wise fast path, 3 patch path
+  int last_kernel = 0;             // which of them the most recent apply launched
   bool force_generic = false;
   // work vectors (extended length)
   double *d_xin = nullptr, *d_yout = nullptr, *d_tmp = nullptr;

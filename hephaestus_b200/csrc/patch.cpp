@@ -15,30 +15,32 @@
 //     in this patch ("private") are written with plain stores, only patch-boundary dofs use
 //     RED atomics.
 // This file builds, for any mesh, one contiguous BLOB per patch (so the kernel can stage it in
-// shared memory with a single cp.async.bulk).  The dofs of a patch are ordered by slot count --
-// 1 | 2 | 3..4 element slots -- each class in ascending global index up to a bank-spreading
-// permutation inside aligned runs of 16 (see below), so that consecutive lanes touch consecutive
-// addresses.  Position u in this order is also the dof's place in the patch-local x staging vector Xs.
+// shared memory with a single cp.async.bulk).  The builder works on abstract UNITS of `unit_bytes`
+// (8: a dof is one double; 16: a dof is an aligned PAIR of doubles -- the two order-2 Nedelec dofs
+// along one edge / face line / interior line, which always travel together, see hex_patch.cu).
+// The units of a patch are ordered by slot count -- 1 | 2 | 3..4 element slots -- each class in
+// ascending global index up to a bank-spreading permutation inside aligned 128-byte runs (see
+// below), so that consecutive lanes touch consecutive addresses.  Position u in this order is also
+// the unit's place in the patch-local x staging vector Xs.
 //
-// E-vector layout (doubles): slot s of patch position j sits at  (s>>1)*(2*stride) + 2*j + (s&1),
-// i.e. slots are stored in PAIRS so that the element side moves 16-byte vectors and the two dofs of
-// an order-2 edge/face pair fall in adjacent banks on the dof side.  Sign flips are applied on the
-// element side (gather: lidx bit 15; scatter: the same bit), so the dof side only sums.
+// E-vector layout: slot s of patch position j sits at unit index s*stride + j (byte offset times
+// unit_bytes).  Orientation flags (sign flips, pair swap) are applied on the element side (lidx bits
+// 13..15, for the gather and for the scatter), so the dof side only sums.
 //
 // Blob layout in 32-bit words, every section starting on a 16-byte boundary:
-//   [0] U  [1] n1  [2] n2  [3] n4      number of patch dofs, and of 1- / 2- / 3..4-slot dofs
-//   [4] nP1 [5] nP2 [6] nP4            number of private dofs in each width section (informational)
+//   [0] U  [1] n1  [2] n2  [3] n4      number of patch units, and of 1- / 2- / 3..4-slot units
+//   [4] nP1 [5] nP2 [6] nP4            number of private units in each width section (informational)
 //   [7] n_ovf  [8..11] word offsets of the e16 / e32 / e64 / ovf sections
 //   [12] word offset of lidx  [13] number of real (non-padding) elements of the patch  [14..15] 0
-//   [16 ..] dof[U]   extended-vector index of every patch dof (bits 0..29) | PATCH_SHARED (bit 31) when
-//            other patches also touch the dof, i.e. its sum must be RED-added; bit 30 is the essential
-//            flag the operator ORs in (hex_patch.cu)
-//   e16[n1], e32[n2], e64[n4]  per dof 1 / 2 / 4 entries of 16 bits: BYTE offset of the slot in the
-//            E-vector; 0xffff = unused (a 3-slot dof in the 64-bit section)
+//   [16 ..] dof[U]   global unit index (bits 0..28) | PATCH_SHARED (bit 31) when other patches also
+//            touch the unit, i.e. its sum must be RED-added; bits 29, 30 are the essential flags the
+//            operator ORs in (hex_patch.cu)
+//   e16[n1], e32[n2], e64[n4]  per unit 1 / 2 / 4 entries of 16 bits: BYTE offset of the slot in the
+//            E-vector; 0xffff = unused (a 3-slot unit in the 64-bit section)
 //   ovf[n_ovf]  (u << 16 | byte offset) for the slots beyond four (edge valence > 4 inside one patch,
-//            only on unstructured meshes); such dofs are classed shared, overflow is RED-added.
-//   lidx[nd][FE] 16 bits per element slot: Xs position u of the slot's dof (bits 0..14) | sign flip
-//            (bit 15); the element side PULLS its inputs through this table.
+//            only on unstructured meshes); such units are classed shared, overflow is RED-added.
+//   lidx[nd][FE] 16 bits per element slot: Xs position u of the slot's unit (bits 0..12) | the slot
+//            code's flag bits 29..31 (bits 13..15); the element side PULLS its inputs through this table.
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -83,10 +85,12 @@ static void parallel_for(int64_t n, F f) {
 }
 
 // centroid[e*3+d]; slot_dof[e*nd + s] = extended dof index of element slot s, slot_neg = sign flip
-int build_patches(int nd, int64_t n_elem, int FE, int stride, int64_t n_ext, const double *centroid,
+int build_patches(int nd, int64_t n_elem, int FE, int stride, int unit_bytes, int64_t n_ext, const double *centroid,
                   const uint32_t *slot_code, PatchHost &out) {
   if (stride < FE) { set_error("slot stride must be >= elements per patch"); return 1; }
-  if ((int64_t)stride * (nd + (nd & 1)) * 8 > 65534 || (int64_t)FE * nd > 32767) { set_error("patch too large for the 16-bit slot encoding"); return 1; }
+  if (unit_bytes != 8 && unit_bytes != 16) { set_error("unit size must be 8 or 16 bytes"); return 1; }
+  if ((int64_t)stride * nd * unit_bytes > 65534 || (int64_t)FE * nd > 8191) { set_error("patch too large for the 16-bit slot encoding"); return 1; }
+  if (n_ext > (int64_t)PATCH_IDX + 1) { set_error("too many units for the patch dof words"); return 1; }
   const int64_t n_patch = (n_elem + FE - 1) / FE;
   out.FE = FE; out.stride = stride; out.nd = nd; out.n_patch = n_patch;
   // ---- Morton order of the centroids
@@ -118,12 +122,12 @@ int build_patches(int nd, int64_t n_elem, int FE, int stride, int64_t n_ext, con
   key.clear(); key.shrink_to_fit();
 
   // ---- per patch: entries sorted by dof, unique list
-  struct Ent { uint32_t dof; uint16_t slot; uint16_t sj; };  // slot = E byte offset, sj = s*FE + j | sign
+  struct Ent { uint32_t dof; uint16_t slot; uint16_t sj; };  // slot = E byte offset, sj = s*FE + j | flags << 13
   const int per = FE * nd;
   std::vector<std::vector<uint32_t>> udof((size_t)n_patch);     // unique dofs (ascending)
   std::vector<std::vector<uint16_t>> ustart((size_t)n_patch);   // U+1
   std::vector<std::vector<uint16_t>> uslots((size_t)n_patch);   // E byte offsets, grouped by dof
-  std::vector<std::vector<uint16_t>> usj((size_t)n_patch);      // s*FE + j | sign, same grouping
+  std::vector<std::vector<uint16_t>> usj((size_t)n_patch);      // s*FE + j | flags, same grouping
   parallel_for(n_patch, [&](int64_t k) {
     std::vector<Ent> ent;
     ent.reserve(per);
@@ -132,8 +136,8 @@ int build_patches(int nd, int64_t n_elem, int FE, int stride, int64_t n_ext, con
       if (e < 0) continue;
       for (int s = 0; s < nd; s++) {
         const uint32_t code = slot_code[(size_t)e * nd + s];
-        const uint16_t sl = (uint16_t)(((s >> 1) * (2 * stride) + 2 * j + (s & 1)) * 8);
-        ent.push_back({code & MAP_IDX, sl, (uint16_t)((uint32_t)(s * FE + j) | ((code & MAP_NEG) ? 0x8000u : 0u))});
+        const uint16_t sl = (uint16_t)((s * stride + j) * unit_bytes);
+        ent.push_back({code & PATCH_IDX, sl, (uint16_t)((uint32_t)(s * FE + j) | ((code >> 29) << 13))});
       }
     }
     std::sort(ent.begin(), ent.end(), [](const Ent &a, const Ent &b) { return a.dof < b.dof || (a.dof == b.dof && a.slot < b.slot); });
@@ -215,25 +219,26 @@ int build_patches(int nd, int64_t n_elem, int FE, int stride, int64_t n_ext, con
     uint32_t *po = B + oov;
     uint16_t *plx = (uint16_t *)(B + olx);
     // order inside each width class: ascending global index (consecutive lanes gather / store
-    // consecutive addresses); private and shared dofs are told apart by the PATCH_SHARED bit of the
-    // dof word.  The position of a dof in this order is also its place in the staging vector Xs, so
-    // its shared-memory bank on the element side (the pull through lidx) is position mod 16.  Sorted
-    // order makes the pull 4.4-way bank conflicted on structured meshes (strided dof numbering), so
-    // inside every aligned run of 16 positions the dofs are PERMUTED to spread, for each
-    // (slot, half-warp of elements) access group, the dofs it reads over distinct banks.  A warp of the
-    // dof side still touches the same 32 dofs, i.e. the same global sectors.
+    // consecutive addresses); private and shared units are told apart by the PATCH_SHARED bit of the
+    // dof word.  The position of a unit in this order is also its place in the staging vector Xs, so
+    // its shared-memory bank on the element side (the pull through lidx) is position mod NB, NB =
+    // 128 / unit_bytes lanes being served per wavefront.  Sorted order makes the pull 4.4-way bank
+    // conflicted on structured meshes (strided dof numbering), so inside every aligned run of NB
+    // positions the units are PERMUTED to spread, for each (slot, NB consecutive elements) access
+    // group, the units it reads over distinct banks.  A warp of the dof side still touches the same
+    // 32 units, i.e. the same global sectors.
     std::vector<uint32_t> order;  // position -> index into ud
     order.reserve(U);
     for (int w = 0; w < 3; w++)
       for (size_t i = 0; i < ud.size(); i++)
         if (width_of(us[i + 1] - us[i]) == w) order.push_back((uint32_t)i);
     {
-      const int HG = (FE + 15) / 16;
+      const int NB = 128 / unit_bytes, HG = (FE + NB - 1) / NB;
       std::vector<uint8_t> cnt((size_t)nd * HG * 16, 0);
       auto groups_of = [&](uint32_t i, int *g) {  // distinct access groups reading dof i
         int n = 0;
         for (int q = us[i]; q < us[i + 1] && n < 8; q++) {
-          const int v = sj[q] & 0x7fff, gid = (v / FE) * HG + (v % FE) / 16;
+          const int v = sj[q] & 0x1fff, gid = (v / FE) * HG + (v % FE) / NB;
           bool dup = false;
           for (int t = 0; t < n; t++) dup |= g[t] == gid;
           if (!dup) g[n++] = gid;
@@ -250,11 +255,11 @@ int build_patches(int nd, int64_t n_elem, int FE, int stride, int64_t n_ext, con
         uint32_t p0 = 0;
         for (int w = 0; w < 3; w++)
           while (p0 < cls_end[w]) {
-            const uint32_t p1 = std::min(cls_end[w], (p0 / 16 + 1) * 16);
+            const uint32_t p1 = std::min(cls_end[w], (p0 / NB + 1) * NB);
             const int m = (int)(p1 - p0);
             uint32_t ds[16];
             for (int t = 0; t < m; t++) ds[t] = order[p0 + t];
-            if (pass > 0) for (int t = 0; t < m; t++) add(ds[t], (int)((p0 + t) & 15), -1);
+            if (pass > 0) for (int t = 0; t < m; t++) add(ds[t], (int)((p0 + t) % NB), -1);
             bool used[16] = {false};
             // dofs read by more groups first
             std::stable_sort(ds, ds + m, [&](uint32_t a, uint32_t b) { return us[a + 1] - us[a] > us[b + 1] - us[b]; });
@@ -264,14 +269,14 @@ int build_patches(int nd, int64_t n_elem, int FE, int stride, int64_t n_ext, con
               int best = -1, best_cost = 1 << 30;
               for (int q = 0; q < m; q++) {
                 if (used[q]) continue;
-                const int bank = (int)((p0 + q) & 15);
+                const int bank = (int)((p0 + q) % NB);
                 int c = 0;
                 for (int r = 0; r < n; r++) c += 2 * cnt[(size_t)g[r] * 16 + bank] + 1;
                 if (c < best_cost) { best_cost = c; best = q; }
               }
               used[best] = true;
               order[p0 + best] = ds[t];
-              add(ds[t], (int)((p0 + best) & 15), +1);
+              add(ds[t], (int)((p0 + best) % NB), +1);
             }
             p0 = p1;
           }
@@ -283,7 +288,7 @@ int build_patches(int nd, int64_t n_elem, int FE, int stride, int64_t n_ext, con
       const int ns = us[i + 1] - us[i], w = width_of(ns);
       const uint32_t r = ul - base[w];  // index inside the width section
       pd[ul] = ud[i] | (multi[ud[i]] ? PATCH_SHARED : 0u);
-      for (int j = 0; j < ns; j++) plx[sj[us[i] + j] & 0x7fffu] = (uint16_t)(ul | (sj[us[i] + j] & 0x8000u));
+      for (int j = 0; j < ns; j++) plx[sj[us[i] + j] & 0x1fffu] = (uint16_t)(ul | (sj[us[i] + j] & 0xe000u));
       if (w == 0) p16[r] = sl[us[i]];
       else if (w == 1) p32[r] = (uint32_t)sl[us[i]] | ((uint32_t)sl[us[i] + 1] << 16);
       else {
@@ -306,13 +311,13 @@ int build_patches(int nd, int64_t n_elem, int FE, int stride, int64_t n_ext, con
 struct hcurl_host_patches { hcurl::PatchHost h; };
 
 extern "C" {
-hcurl_host_patches *hcurl_host_patches_create(int nd, int64_t n_elem, int elems_per_patch, int slot_stride, int64_t n_dof,
-                                              const double *centroid, const uint32_t *slot_code) {
+hcurl_host_patches *hcurl_host_patches_create(int nd, int64_t n_elem, int elems_per_patch, int slot_stride, int unit_bytes,
+                                              int64_t n_dof, const double *centroid, const uint32_t *slot_code) {
   if (nd <= 0 || n_elem <= 0 || !centroid || !slot_code) { hcurl::set_error("hcurl_host_patches_create: bad arguments"); return nullptr; }
   for (int64_t i = 0; i < n_elem * nd; i++)
-    if ((int64_t)(slot_code[i] & hcurl::MAP_IDX) >= n_dof) { hcurl::set_error("hcurl_host_patches_create: dof index out of range"); return nullptr; }
+    if ((int64_t)(slot_code[i] & hcurl::PATCH_IDX) >= n_dof) { hcurl::set_error("hcurl_host_patches_create: dof index out of range"); return nullptr; }
   hcurl_host_patches *p = new hcurl_host_patches;
-  if (hcurl::build_patches(nd, n_elem, elems_per_patch, slot_stride, n_dof, centroid, slot_code, p->h)) { delete p; return nullptr; }
+  if (hcurl::build_patches(nd, n_elem, elems_per_patch, slot_stride, unit_bytes, n_dof, centroid, slot_code, p->h)) { delete p; return nullptr; }
   return p;
 }
 void hcurl_host_patches_destroy(hcurl_host_patches *p) { delete p; }

@@ -190,6 +190,10 @@ class HephGpuOperator:
         """0 = automatic (fast path where available), 1 = generic kernel."""
         L.check(L.lib().hcurl_op_set_kernel(self.h, int(which)), "hcurl_op_set_kernel")
 
+    def LastKernel(self):
+        """Which kernel the most recent apply launched: 1 generic, 2 element-wise fast, 3 patch (0 = none yet)."""
+        return int(L.lib().hcurl_op_last_kernel(self.h))
+
     def SetEssentialTrueDofs(self, ess):
         e = L.as_i32(ess)
         L.check(L.lib().hcurl_op_set_essential_tdofs(self.h, L.ptr(e), e.size), "hcurl_op_set_essential_tdofs")

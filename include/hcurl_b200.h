@@ -144,6 +144,8 @@ void hcurl_op_destroy(hcurl_op *op);
  * kernel, 2 = element-wise register-blocked kernel, 3 = patch kernel.  All compute the same
  * operator; tests compare them. */
 int hcurl_op_set_kernel(hcurl_op *op, int which);
+/* which kernel the most recent apply launched (1, 2, 3 as above; 0 = none yet) */
+int hcurl_op_last_kernel(const hcurl_op *op);
 /* Number of coefficient values expected per element for PER_QPT layout. */
 int hcurl_op_qpts_curl(const hcurl_op *op);
 int hcurl_op_qpts_mass(const hcurl_op *op);
@@ -223,16 +225,19 @@ int hcurl_dot(hcurl_ctx *ctx, const double *a_dev, const double *b_dev, int64_t 
  * gather / atomic scatter through FiniteElementSpace::GetElementDofs
  * (what blf->Assemble() resolves through the CSR sparsity in the reference,
  * /root/reference/src/equation_systems/equation_system.cpp:345).
- *  slot_code  [n_elem][nd]: dof index (bits 0..29) | sign flip (bit 31) of each element slot
- *  slot_stride  >= elems_per_patch: E-vector index (in doubles) of (slot s, patch position j)
- *             = (s>>1)*(2*slot_stride) + 2*j + (s&1)   (slots stored in pairs)
+ *  unit_bytes  8: the gathered / scattered unit is one double; 16: an aligned pair of doubles (the
+ *             order-2 hex kernel works on pairs, see hephaestus_b200/csrc/hex_patch.cu)
+ *  slot_code  [n_elem][nd]: unit index (bits 0..28) | orientation flags (bits 29..31; for 8-byte units
+ *             bit 31 = sign flip) of each element slot
+ *  slot_stride  >= elems_per_patch: E-vector index (in units) of (slot s, patch position j) = s*slot_stride + j
  *  outputs    perm [n_patch*epp] element at each patch position (-1 padding);
  *             blob_off [n_patch+1] start of each patch blob in 16-byte units; blob: per patch a
- *             16-word header, the dof list, the 16/32/64-bit slot-entry sections (dof side) and the
- *             per-slot local dof index table (element side); layout in hephaestus_b200/csrc/patch.cpp. */
+ *             16-word header, the unit list, the 16/32/64-bit slot-entry sections (dof side) and the
+ *             per-slot local unit index table (element side); layout in hephaestus_b200/csrc/patch.cpp. */
 typedef struct hcurl_host_patches hcurl_host_patches;
 hcurl_host_patches *hcurl_host_patches_create(int nd, int64_t n_elem, int elems_per_patch, int slot_stride,
-                                              int64_t n_dof, const double *centroid, const uint32_t *slot_code);
+                                              int unit_bytes, int64_t n_dof, const double *centroid,
+                                              const uint32_t *slot_code);
 void hcurl_host_patches_destroy(hcurl_host_patches *p);
 int64_t hcurl_host_patches_count(const hcurl_host_patches *p);
 int64_t hcurl_host_patches_blob_words(const hcurl_host_patches *p);

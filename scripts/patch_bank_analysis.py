@@ -25,7 +25,7 @@ def analyse(n=16, fe=64, nsample=24, nd=54):
     ks = rng.choice(npatch, min(nsample, npatch), replace=False)
     for k in ks:
         dof, groups, ov, lidx, n_real = decode_patch(k, off, blob, nd, fe)
-        pos = lidx & 0x7FFF
+        pos = lidx & 0x1FFF
         for s in range(nd):
             for h0 in range(0, n_real, 16):
                 pull += half_wavefronts(pos[s, h0:min(n_real, h0 + 16)]); ideal_pull += 1

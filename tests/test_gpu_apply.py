@@ -198,6 +198,9 @@ def test_hex_p2_fast_paths_match_generic_and_oracle(ctx, perturb, n):
         op.SetCoefficients(a, b)
         op.SetEssentialTrueDofs(essd)
         assert rel_err(op.Mult(x), y_ref) < TOL, which
+        # the kernel asked for is the one that ran (patch kernel: affine meshes only)
+        if which in (1, 2) or not perturb:
+            assert op.LastKernel() == which or (which == 0 and op.LastKernel() == 3), (which, op.LastKernel())
         yu = op.MultUnconstrained(x, y0.copy(), scale=-0.5, accumulate=True)
         assert rel_err(yu, yu_ref) < TOL, which
     # coefficient update reuses the handle
@@ -234,11 +237,19 @@ def test_hex_p2_patch_kernel_patch_sizes(ctx, fe, monkeypatch):
     y_ref = oa.constrained_apply(A, essd, x)
     y = op.Mult(x)
     assert rel_err(y, y_ref) < TOL
+    assert op.LastKernel() == 3
     dx, dy = ctx.alloc(sp.ndof).upload(x), ctx.alloc(sp.ndof)
     for _ in range(3):
         op.Mult(dx, dy)
     ctx.synchronize()
     assert rel_err(dy.download(), y_ref) < TOL
+    # an arbitrary essential set splits dof pairs (one double constrained, its partner free)
+    ess2 = np.sort(np.random.default_rng(11).choice(sp.ndof, sp.ndof // 5, replace=False)).astype(np.int32)
+    op.SetEssentialTrueDofs(ess2)
+    assert rel_err(op.Mult(x), oa.constrained_apply(A, ess2, x)) < TOL
+    assert op.LastKernel() == 3
+    y0 = np.random.default_rng(2).standard_normal(sp.ndof)
+    assert rel_err(op.MultUnconstrained(x, y0.copy(), scale=2.0, accumulate=True), y0 + 2.0 * (A @ x)) < TOL
 
 
 @pytest.mark.parametrize("which", [1, 2, 3])
@@ -261,3 +272,4 @@ def test_hex_p2_unstructured_affine_valence6(ctx, which, monkeypatch):
     x = np.random.default_rng(3).standard_normal(sp.ndof)
     A = oa.assemble(so, a, b, q_override=3)
     assert rel_err(op.Mult(x), oa.constrained_apply(A, essd, x)) < TOL
+    assert op.LastKernel() == which

@@ -15,11 +15,12 @@ from helpers import star_mesh
 NEG = 0x80000000
 
 
-def build(space, fe, slot_code, centroid, stride=None):
+def build(space, fe, slot_code, centroid, stride=None, unit=8, n_units=None):
     lib = L.lib()
     ne, nd = slot_code.shape
     stride = stride or fe + 1
-    h = L.check_ptr(lib.hcurl_host_patches_create(nd, ne, fe, stride, space.ndof, L.ptr(centroid), L.ptr(slot_code)), "patches")
+    h = L.check_ptr(lib.hcurl_host_patches_create(nd, ne, fe, stride, unit, n_units or space.ndof, L.ptr(centroid), L.ptr(slot_code)),
+                    "patches")
     npatch = lib.hcurl_host_patches_count(h)
     nw = lib.hcurl_host_patches_blob_words(h)
     perm = np.zeros(npatch * fe, np.int32)
@@ -44,8 +45,8 @@ def decode_patch(k, off, blob, nd=None, fe=None):
     assert np.all(B[14:16] == 0) and U == n1 + n2 + n4
     assert o16 % 4 == 0 and o32 % 4 == 0 and o64 % 4 == 0 and oov % 4 == 0 and olx % 4 == 0 and len(B) % 4 == 0
     word = B[16:16 + U].astype(np.int64)
-    assert np.all(word & 0x40000000 == 0)                        # essential flags are set by the operator
-    dof, priv = word & 0x3FFFFFFF, (word & SHARED) == 0
+    assert np.all(word & 0x60000000 == 0)                        # essential flags are set by the operator
+    dof, priv = word & 0x1FFFFFFF, (word & SHARED) == 0
     sh = 16 * np.arange(4, dtype=np.uint64)
     e16 = B[o16:o16 + (n1 + 1) // 2].view(np.uint16)[:n1].astype(np.int64)[:, None]
     e32 = (B[o32:o32 + n2, None].astype(np.uint64) >> sh[None, :2]).astype(np.int64) & 0xFFFF
@@ -62,8 +63,8 @@ def decode_patch(k, off, blob, nd=None, fe=None):
 
 
 def e_index(s, j, st):
-    """E-vector position (in doubles) of slot s of patch position j: slots are stored in pairs."""
-    return (s >> 1) * (2 * st) + 2 * j + (s & 1)
+    """E-vector position (in units) of slot s of patch position j."""
+    return s * st + j
 
 
 def make(kind, n, p, perturb):
@@ -124,13 +125,14 @@ def test_patch_lists_reproduce_gather_and_scatter(kind, n, p, fe, perturb):
         # element side: pull x through lidx (position in the patch dof list | sign bit 15)
         Xs = x[pd_all]
         neg_l = (lidx & 0x8000) != 0
-        pos_l = lidx & 0x7FFF
+        pos_l = lidx & 0x1FFF
+        assert np.all(lidx & 0x6000 == 0)                       # 8-byte units: only the sign flag
         assert np.all(pos_l[:, :n_real] < len(pd_all))
         for j in range(n_real):
             xe = np.where(neg_l[:, j], -Xs[pos_l[:, j]], Xs[pos_l[:, j]])
             assert np.array_equal(xe, sgn[el[j]] * x[idx[el[j]]])
         # element results, signed on the element side, in the paired E layout
-        Ey = np.full((nd + (nd & 1)) * st, np.nan)
+        Ey = np.full(nd * st, np.nan)
         for j in range(n_real):
             Ey[e_index(sl, j, st)] = np.where(neg_l[:, j], -ye[el[j]], ye[el[j]])
         n_slots = 0
@@ -188,7 +190,66 @@ def test_bad_arguments_are_reported():
     lib = L.lib()
     code = np.array([[5, 1]], dtype=np.uint32)
     cen = np.zeros((1, 3))
-    assert not lib.hcurl_host_patches_create(2, 1, 32, 33, 3, L.ptr(cen), L.ptr(code))
+    assert not lib.hcurl_host_patches_create(2, 1, 32, 33, 8, 3, L.ptr(cen), L.ptr(code))
     assert b"out of range" in lib.hcurl_last_error()
-    assert not lib.hcurl_host_patches_create(2, 1, 20000, 20000, 8, L.ptr(cen), L.ptr(code))
+    assert not lib.hcurl_host_patches_create(2, 1, 20000, 20000, 8, 8, L.ptr(cen), L.ptr(code))
     assert b"too large" in lib.hcurl_last_error()
+    assert not lib.hcurl_host_patches_create(2, 1, 32, 33, 12, 8, L.ptr(cen), L.ptr(code))
+    assert b"unit size" in lib.hcurl_last_error()
+
+
+SWAP, NEG1, NEG0 = 0x20000000, 0x40000000, 0x80000000
+
+
+@pytest.mark.parametrize("n,fe", [((4, 4, 4), 64), ((5, 3, 4), 32)])
+def test_pair_units_with_orientation_flags(n, fe):
+    """16-byte units: the dof side moves aligned pairs of doubles; each element slot pair carries a
+    swap flag and one sign per entry (hex_patch.cu builds these from the order-2 map; here random
+    flags exercise every combination)."""
+    m = fespace.cartesian_hex_mesh(*n)
+    sp = fespace.NDSpace(m, 2)
+    sd = sp.signed_elem_dofs().astype(np.int64)
+    ne = sd.shape[0]
+    npair, n_units = 27, sp.ndof // 2
+    rng = np.random.default_rng(5)
+    # any map from element slot pairs to global pairs will do for the builder: reuse the even dofs
+    idx = np.where(sd >= 0, sd, -1 - sd)[:, ::2] // 2
+    flags = rng.integers(0, 8, size=idx.shape).astype(np.uint32) << 29
+    code = np.ascontiguousarray((idx.astype(np.uint32) | flags).astype(np.uint32))
+    cen = np.ascontiguousarray(m.verts[m.elems].mean(axis=1))
+    perm, off, blob, st = build(sp, fe, code, cen, unit=16, n_units=n_units)
+    x = rng.standard_normal((n_units, 2))
+    ye = rng.standard_normal((ne, npair, 2))
+    sw, n1, n0 = (flags & SWAP) != 0, (flags & NEG1) != 0, (flags & NEG0) != 0
+    s0, s1 = np.where(n0, -1.0, 1.0), np.where(n1, -1.0, 1.0)
+    # reference: local = (s0 * g[swap], s1 * g[!swap]);  scatter is the transpose
+    g = x[idx]
+    xe_ref = np.stack([s0 * np.where(sw, g[..., 1], g[..., 0]), s1 * np.where(sw, g[..., 0], g[..., 1])], axis=-1)
+    contrib = np.stack([np.where(sw, s1 * ye[..., 1], s0 * ye[..., 0]), np.where(sw, s0 * ye[..., 0], s1 * ye[..., 1])], axis=-1)
+    y_ref = np.zeros((n_units, 2))
+    np.add.at(y_ref, idx.ravel(), contrib.reshape(-1, 2))
+    y = np.zeros((n_units, 2))
+    sl = np.arange(npair)
+    for k in range(len(off) - 1):
+        pd_all, groups, ov, lidx, n_real = decode_patch(k, off, blob, npair, fe)
+        el = perm[k * fe:(k + 1) * fe]
+        Xs = x[pd_all]
+        pos = lidx & 0x1FFF
+        lsw, ln1, ln0 = (lidx & 0x2000) != 0, (lidx & 0x4000) != 0, (lidx & 0x8000) != 0
+        Ey = np.full((npair * st, 2), np.nan)
+        for j in range(n_real):
+            gj = Xs[pos[:, j]]
+            a0 = np.where(ln0[:, j], -1.0, 1.0) * np.where(lsw[:, j], gj[:, 1], gj[:, 0])
+            a1 = np.where(ln1[:, j], -1.0, 1.0) * np.where(lsw[:, j], gj[:, 0], gj[:, 1])
+            assert np.array_equal(np.stack([a0, a1], -1), xe_ref[el[j]])
+            b0 = np.where(ln0[:, j], -1.0, 1.0) * ye[el[j], :, 0]
+            b1 = np.where(ln1[:, j], -1.0, 1.0) * ye[el[j], :, 1]
+            Ey[e_index(sl, j, st)] = np.where(lsw[:, j, None], np.stack([b1, b0], -1), np.stack([b0, b1], -1))
+        for u0, pd, priv, ent in groups:
+            used = ent != 0xFFFF
+            assert np.all(ent[used] % 16 == 0)
+            for u in range(len(pd)):
+                y[pd[u]] += Ey[ent[u][used[u]] // 16].sum(axis=0)
+        for w in ov:
+            y[pd_all[w >> 16]] += Ey[(w & 0xFFFF) // 16]
+    np.testing.assert_allclose(y, y_ref, rtol=0, atol=1e-13)
