@@ -228,7 +228,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t *mbar, uint32_t parity) {
                  : "memory");
   } while (!done);
 }
-// 16-byte asynchronous gather global -> shared (LDGSTS, L1 bypassed), no register staging
+// 16-byte asynchronous gather global -> shared (LDGSTS, L1 bypassed), no register staging.  (The L1-allocating
+// .ca form was measured 7-9 % slower per apply although ncu counts fewer shared-memory wavefronts for it.)
 __device__ __forceinline__ void gather16_async(double2 *dst, const double2 *src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
 }
@@ -240,17 +241,20 @@ __device__ __forceinline__ void gather_wait_all() { asm volatile("cp.async.wait_
 // is used to launch the x gather of patch i+1 as 16-byte cp.async copies into the staging vector Xs,
 // and the blob of patch i+2 is requested when patch i retires.
 //   Xs  [max pairs]       patch-local x pairs, position u = order of the blob's dof list
-//   E   [27][FE+1]        element slot pairs (double2): modal coefficients, then element results
+//   E   [27][FE+1]        element slot pairs (double2): modal coefficients exchanged between the component threads
+//   EY  [27][FE+1]        element slot pairs: element results, summed per dof pair
+// (two buffers so that a patch needs three CTA barriers, not five)
 template <int FE, int MINB, bool ACC, bool PROF>
-__global__ void __maxnreg__(MINB >= 3 ? 112 : 168)
+__global__ void __maxnreg__(168)
 hex_patch_modal_p2_kernel(const PatchArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NT = 3 * FE, ST = FE + 1;
   uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw);  // [2]
   unsigned char *blobB = smem_raw + 16;
   double2 *Xs = reinterpret_cast<double2 *>(blobB + 2 * (size_t)a.blob_cap_bytes);
-  double2 *E2 = reinterpret_cast<double2 *>(reinterpret_cast<unsigned char *>(Xs) + a.xs_cap_bytes);
-  const unsigned char *Eb = reinterpret_cast<const unsigned char *>(E2);
+  double2 *E2 = reinterpret_cast<double2 *>(reinterpret_cast<unsigned char *>(Xs) + a.xs_cap_bytes);  // modal exchange
+  double2 *EY = E2 + 27 * ST;                                                                            // element results
+  const unsigned char *Eb = reinterpret_cast<const unsigned char *>(EY);
   const double2 *x2 = reinterpret_cast<const double2 *>(a.x);
   double2 *y2 = reinterpret_cast<double2 *>(a.y);
   const int tid = threadIdx.x;
@@ -304,6 +308,8 @@ hex_patch_modal_p2_kernel(const PatchArgs a) {
   __syncthreads();  // mbarriers initialised
   mbar_wait(mbar, 0);
   gather(0);
+  gather_wait_all();
+  __syncthreads();  // Xs of the first patch complete and visible
   PROF_MARK(0)  // prologue
 
   for (int it = 0; it < n_it; it++) {
@@ -316,9 +322,6 @@ hex_patch_modal_p2_kernel(const PatchArgs a) {
     const double *g = a.edata + (size_t)k * 12 * FE;
     double K11 = __ldg(g + oK11), K10 = __ldg(g + oK10), K12 = __ldg(g + oK12), K22 = __ldg(g + oK22), K20 = __ldg(g + oK20),
            M00 = __ldg(g + oM00), M01 = __ldg(g + oM01), M02 = __ldg(g + oM02);
-    gather_wait_all();
-    __syncthreads();  // Xs complete and visible
-    PROF_MARK(1)  // wait for the x gather
     const bool ok = (uint32_t)el < B[13];
     // ---- pull the element inputs through the per-slot table, forward transform
     double Am[18];
@@ -369,15 +372,13 @@ hex_patch_modal_p2_kernel(const PatchArgs a) {
       mbar_wait(mbar + (b ^ 1), ((it + 1) >> 1) & 1);
       gather(b ^ 1);
     }
-    __syncthreads();  // everyone has read the modal coefficients
-    PROF_MARK(3)  // exchange + modal operator + backward transform + next gather issue
     if (ok) {
-      double2 *Eown = E2 + (c * 9) * ST + el;
+      double2 *Eown = EY + (c * 9) * ST + el;
 #pragma unroll
       for (int r = 0; r < 9; r++) Eown[r * ST] = local_to_pair(Y[2 * r], Y[2 * r + 1], lx[r]);
     }
-    __syncthreads();
-    PROF_MARK(4)  // element results to shared memory
+    __syncthreads();  // element results visible; everyone has read the modal coefficients
+    PROF_MARK(3)  // exchange + modal operator + backward transform + next gather issue + results to shared memory
     // ---- sum the slots of every patch pair; private pairs are plain 16-byte stores, shared ones RED
     {
       const uint32_t n1 = B[1], n2 = B[2], n4 = B[3], nov = B[7];
@@ -455,8 +456,9 @@ hex_patch_modal_p2_kernel(const PatchArgs a) {
       }
 #undef E_AT
     }
-    __syncthreads();  // blob buffer b and E are free
-    PROF_MARK(5)  // dof sums + stores
+    gather_wait_all();
+    __syncthreads();  // blob buffer b and EY are free; Xs of the next patch complete and visible
+    PROF_MARK(5)  // dof sums + stores + wait for the x gather
     if (tid == 0 && it + 2 < n_it) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       request(b, q0, q1);
@@ -556,10 +558,10 @@ static int upload(T *&dst, const std::vector<T> &src) {
   return 0;
 }
 
-// dynamic shared memory of the patch kernel: 2 mbarriers | 2 blob buffers | Xs | E
+// dynamic shared memory of the patch kernel: 2 mbarriers | 2 blob buffers | Xs | E | EY
 static size_t patch_smem_bytes(int FE, uint32_t max_blob_words, uint32_t max_units) {
   const size_t blob_cap = ((size_t)max_blob_words * 4 + 15u) & ~(size_t)15u;
-  return 16 + 2 * blob_cap + (size_t)max_units * 16 + (size_t)27 * (FE + 1) * 16;
+  return 16 + 2 * blob_cap + (size_t)max_units * 16 + 2 * (size_t)27 * (FE + 1) * 16;
 }
 
 // The dof side of the patch kernel works on aligned PAIRS of doubles.  In the rotated slot layout the
@@ -572,7 +574,7 @@ int hex_patch_build(hcurl_space *sp, const double *elem_xyz, const int32_t *elem
   if (sp->geom != HCURL_GEOM_HEX || sp->order != 2 || sp->geom_order != 1) return 0;
   const char *off = getenv("HCURL_NO_PATCH");
   if (off && off[0] == '1') return 0;
-  int FE = 64;
+  int FE = 32;  // 32-element patches, 4 CTAs of 96 threads per SM: fastest of 32 / 64 / 128 (profiles/README.md)
   if (const char *s = getenv("HCURL_PATCH_FE")) FE = atoi(s);
   if (FE != 32 && FE != 64 && FE != 128) { set_error("HCURL_PATCH_FE must be 32, 64 or 128"); return 1; }
   const int nd = sp->nd, p = sp->order, np = nd / 2;
@@ -688,12 +690,10 @@ int hex_patch_launch(hcurl_op *op, bool constrained, const double *d_x, double *
   if (a.prof && accumulate) a.prof = nullptr;
   const size_t smem = patch_smem_bytes(P.FE, P.max_blob_words, P.max_dofs);
   int rc = 1;
-  // register budget: 168 per thread (2 CTAs of 192 threads per SM) or 112 (3 CTAs); the tighter one spills
-  static const bool dense = [] { const char *s = getenv("HCURL_PATCH_DENSE"); return s && s[0] == '1'; }();
-  if (P.FE == 32) rc = dense ? launch_fe<32, 6>(a, P.n_patch, ctx->sm_count, smem, accumulate, ctx->stream)
-                             : launch_fe<32, 4>(a, P.n_patch, ctx->sm_count, smem, accumulate, ctx->stream);
-  else if (P.FE == 64) rc = dense ? launch_fe<64, 3>(a, P.n_patch, ctx->sm_count, smem, accumulate, ctx->stream)
-                                  : launch_fe<64, 2>(a, P.n_patch, ctx->sm_count, smem, accumulate, ctx->stream);
+  // 168 registers per thread: 2 CTAs of 192 threads per SM.  (A 3-CTA variant capped at 112 / 104 registers spilled
+  // and ran 45 % slower, profiles/README.md.)
+  if (P.FE == 32) rc = launch_fe<32, 4>(a, P.n_patch, ctx->sm_count, smem, accumulate, ctx->stream);
+  else if (P.FE == 64) rc = launch_fe<64, 2>(a, P.n_patch, ctx->sm_count, smem, accumulate, ctx->stream);
   else if (P.FE == 128) rc = launch_fe<128, 1>(a, P.n_patch, ctx->sm_count, smem, accumulate, ctx->stream);
   if (rc) return rc;
   HC_CUDA(cudaGetLastError());

@@ -30,7 +30,7 @@ op.kernel_stats_reset()
 for _ in range(10):
     op.Mult(dx, dy)
 ms, cnt = op.kernel_stats_ms()
-print("FE=%s n=%d: kernel %.4f ms (no profiling)" % (os.environ.get("HCURL_PATCH_FE", "64"), n, ms))
+print("FE=%s n=%d: kernel %.4f ms (no profiling)" % (os.environ.get("HCURL_PATCH_FE", "32"), n, ms))
 lib.hcurl_debug_patch_profile(ctx.h, 1, None)
 reps = 5
 op.kernel_stats_reset()
@@ -40,8 +40,8 @@ ms2, _ = op.kernel_stats_ms()
 out = (C.c_ulonglong * 8)()
 lib.hcurl_debug_patch_profile(ctx.h, 0, out)
 tot = float(sum(out[:6]))
-names = ["prologue (per CTA)", "wait x gather", "pull + fwd", "op + bwd + next gather", "E store", "dof sums + stores"]
+names = ["prologue (per CTA)", "-", "pull + fwd", "op + bwd + next gather + Y store", "-", "dof sums + stores + gather wait"]
 print("  with profiling %.4f ms; cycles of thread 0 per patch (share):" % ms2)
-npatch = (mesh.n_elem + int(os.environ.get("HCURL_PATCH_FE", "64")) - 1) // int(os.environ.get("HCURL_PATCH_FE", "64"))
+npatch = (mesh.n_elem + int(os.environ.get("HCURL_PATCH_FE", "32")) - 1) // int(os.environ.get("HCURL_PATCH_FE", "32"))
 for i, nm in enumerate(names):
     print("  %-24s %9.0f  %5.1f%%" % (nm, out[i] / reps / npatch, 100.0 * out[i] / tot))
