@@ -192,15 +192,20 @@ int op_apply_ext(hcurl_op *op, double *d_x, double *d_y, bool constrained, doubl
   hcurl_ctx *ctx = op->ctx;
   const int64_t next = sp->n_ext();
   if (exchange_broadcast(sp, d_x)) return 1;
-  if (!accumulate) HC_CUDA(cudaMemsetAsync(d_y, 0, sizeof(double) * next, ctx->stream));
+  // the patch kernel stores every private pair itself: only what it accumulates into must be cleared (plus, on
+  // several GPUs, the ghost tail that the reduction sends back); the other kernels RED-add everything
+  const bool patch_path = hex_patch_eligible(op) && (((uintptr_t)d_x | (uintptr_t)d_y) & 15) == 0;
+  if (!accumulate && patch_path) {
+    if (hex_patch_zero_shared(op, d_y)) return 1;
+    if (sp->n_ghost) HC_CUDA(cudaMemsetAsync(d_y + sp->n_tdof, 0, sizeof(double) * sp->n_ghost, ctx->stream));
+  } else if (!accumulate) HC_CUDA(cudaMemsetAsync(d_y, 0, sizeof(double) * next, ctx->stream));
   else if (sp->n_ghost) HC_CUDA(cudaMemsetAsync(d_y + sp->n_tdof, 0, sizeof(double) * sp->n_ghost, ctx->stream));
   const uint32_t *map = (constrained && op->d_map_ess) ? op->d_map_ess : sp->d_map;
   cudaEvent_t e0 = op->ev0, e1 = op->ev1;
   if (op->ring_ok) { e0 = op->ring0[op->ring_n % hcurl_op::RING]; e1 = op->ring1[op->ring_n % hcurl_op::RING]; op->ring_n++; op->ev0 = e0; op->ev1 = e1; }
   if (op->timed) HC_CUDA(cudaEventRecord(e0, ctx->stream));
   int rc;
-  // the patch kernel moves aligned pairs of doubles
-  if (hex_patch_eligible(op) && (((uintptr_t)d_x | (uintptr_t)d_y) & 15) == 0) { op->last_kernel = 3; rc = hex_patch_launch(op, constrained, d_x, d_y, scale, accumulate); }
+  if (patch_path) { op->last_kernel = 3; rc = hex_patch_launch(op, constrained, d_x, d_y, scale, accumulate); }
   else if (hex_fast_eligible(op)) { op->last_kernel = 2; rc = hex_fast_launch(op, constrained, d_x, d_y, scale); }
   else { op->last_kernel = 1; rc = (sp->geom == HCURL_GEOM_HEX) ? hex_apply_launch(op, map, d_x, d_y, scale) : tet_apply_launch(op, map, d_x, d_y, scale); }
   if (rc) return rc;

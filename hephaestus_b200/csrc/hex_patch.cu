@@ -326,13 +326,23 @@ hex_patch_modal_p2_kernel(const PatchArgs a) {
     // ---- pull the element inputs through the per-slot table, forward transform
     double Am[18];
     uint32_t lx[9];
+    uint32_t fl = 0;
     if (ok) {
       const uint16_t *lidx = reinterpret_cast<const uint16_t *>(B + B[12]) + (c * 9) * FE + el;
+#pragma unroll
+      for (int r = 0; r < 9; r++) { lx[r] = lidx[r * FE]; fl |= lx[r]; }
+    }
+    // warp-uniform: no element of this warp sees a pair swapped or sign-flipped (consistently oriented meshes)
+    const bool plain = __all_sync(0xffffffffu, (fl & 0xe000u) == 0u);
+    if (ok) {
       double X[18];
+      if (plain) {
 #pragma unroll
-      for (int r = 0; r < 9; r++) lx[r] = lidx[r * FE];
+        for (int r = 0; r < 9; r++) { const double2 v = Xs[lx[r]]; X[2 * r] = v.x; X[2 * r + 1] = v.y; }
+      } else {
 #pragma unroll
-      for (int r = 0; r < 9; r++) pair_to_local(Xs[lx[r] & 0x1fffu], lx[r], X[2 * r], X[2 * r + 1]);
+        for (int r = 0; r < 9; r++) pair_to_local(Xs[lx[r] & 0x1fffu], lx[r], X[2 * r], X[2 * r + 1]);
+      }
       modal_fwd(X, Am);
       double2 *Eown = E2 + (c * 9) * ST + el;
 #pragma unroll
@@ -374,8 +384,13 @@ hex_patch_modal_p2_kernel(const PatchArgs a) {
     }
     if (ok) {
       double2 *Eown = EY + (c * 9) * ST + el;
+      if (plain) {
 #pragma unroll
-      for (int r = 0; r < 9; r++) Eown[r * ST] = local_to_pair(Y[2 * r], Y[2 * r + 1], lx[r]);
+        for (int r = 0; r < 9; r++) Eown[r * ST] = make_double2(Y[2 * r], Y[2 * r + 1]);
+      } else {
+#pragma unroll
+        for (int r = 0; r < 9; r++) Eown[r * ST] = local_to_pair(Y[2 * r], Y[2 * r + 1], lx[r]);
+      }
     }
     __syncthreads();  // element results visible; everyone has read the modal coefficients
     PROF_MARK(3)  // exchange + modal operator + backward transform + next gather issue + results to shared memory
@@ -615,14 +630,15 @@ int hex_patch_build(hcurl_space *sp, const double *elem_xyz, const int32_t *elem
   P.FE = FE; P.stride = H.stride; P.n_patch = H.n_patch;
   P.blob_words = (int64_t)H.blob.size(); P.max_blob_words = H.max_blob_words; P.max_dofs = H.max_dofs;
   if (patch_smem_bytes(FE, H.max_blob_words, H.max_dofs) > 227 * 1024) return 0;  // patch path unavailable
-  if (upload(P.d_perm, H.perm) || upload(P.d_blob_off, H.blob_off) || upload(P.d_blob, H.blob)) return 1;
+  if (upload(P.d_perm, H.perm) || upload(P.d_blob_off, H.blob_off) || upload(P.d_blob, H.blob) || upload(P.d_shared, H.shared_units)) return 1;
+  P.n_shared = (int64_t)H.shared_units.size();
   sp->has_patches = true;
   return 0;
 }
 
 void hex_patch_free(hcurl_space *sp) {
   PatchSet &P = sp->patch;
-  cudaFree(P.d_perm); cudaFree(P.d_blob_off); cudaFree(P.d_blob);
+  cudaFree(P.d_perm); cudaFree(P.d_blob_off); cudaFree(P.d_blob); cudaFree(P.d_shared);
   cudaFree(sp->d_xyzP);
   P = PatchSet();
   sp->has_patches = false;
@@ -698,6 +714,23 @@ int hex_patch_launch(hcurl_op *op, bool constrained, const double *d_x, double *
   if (rc) return rc;
   HC_CUDA(cudaGetLastError());
   ctx->launches++;
+  return 0;
+}
+
+__global__ void patch_zero_shared_kernel(const int64_t n, const uint32_t *__restrict__ idx, double2 *__restrict__ y2) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y2[idx[i]] = make_double2(0.0, 0.0);
+}
+
+// Private pairs are stored, shared pairs are RED-added by the patch kernel: only the latter (about a fifth of the
+// vector) need to start from zero, so a full memset of y (a quarter of the vector traffic of an apply) is avoided.
+int hex_patch_zero_shared(hcurl_op *op, double *d_y) {
+  PatchSet &P = op->sp->patch;
+  if (P.n_shared == 0) return 0;
+  patch_zero_shared_kernel<<<(unsigned)((P.n_shared + 255) / 256), 256, 0, op->ctx->stream>>>(P.n_shared, P.d_shared,
+                                                                                             reinterpret_cast<double2 *>(d_y));
+  HC_CUDA(cudaGetLastError());
+  op->ctx->launches++;
   return 0;
 }
 

@@ -79,6 +79,7 @@ struct PatchHost {
   std::vector<uint32_t> blob;     // see patch.cpp for the layout
   uint32_t max_blob_words = 0;
   uint32_t max_dofs = 0;          // largest number of unique dofs of one patch
+  std::vector<uint32_t> shared_units;  // units touched by more than one patch (their sums are RED-added), ascending
 };
 int build_patches(int nd, int64_t n_elem, int FE, int stride, int unit_bytes, int64_t n_ext, const double *centroid,
                   const uint32_t *slot_code, PatchHost &out);
@@ -93,6 +94,8 @@ struct PatchSet {  // device copy
   uint32_t *d_blob_off = nullptr, *d_blob = nullptr;
   int64_t blob_words = 0;
   uint32_t max_blob_words = 0, max_dofs = 0;
+  uint32_t *d_shared = nullptr;  // pairs whose sums are RED-added: the only part of y that must be zero before an apply
+  int64_t n_shared = 0;
 };
 
 // ----------------------------------------------------------------- NCCL ----
@@ -208,6 +211,8 @@ bool hex_patch_eligible(const hcurl_op *op);
 // (private dofs) or must have been zeroed by the caller (shared dofs)
 int hex_patch_launch(hcurl_op *op, bool constrained, const double *d_x, double *d_y, double scale, bool accumulate);
 int hex_patch_flag_essential(hcurl_op *op, const double *d_flag);
+// zero what the patch kernel accumulates into (instead of clearing all of y)
+int hex_patch_zero_shared(hcurl_op *op, double *d_y);
 int hex_fast_prepare_space(hcurl_space *sp);
 int tet_build_emat(hcurl_op *op);
 int tet_apply_launch(hcurl_op *op, const uint32_t *d_map, const double *d_x, double *d_y, double scale);

@@ -169,6 +169,9 @@ int build_patches(int nd, int64_t n_elem, int FE, int stride, int unit_bytes, in
     }
   }
   owner.clear(); owner.shrink_to_fit();
+  out.shared_units.clear();
+  for (int64_t d = 0; d < n_ext; d++)
+    if (multi[(size_t)d]) out.shared_units.push_back((uint32_t)d);
   // ---- emit one blob per patch
   auto width_of = [](int nslot) { return nslot <= 1 ? 0 : (nslot == 2 ? 1 : 2); };
   auto align4 = [](uint32_t w) { return (w + 3u) & ~3u; };  // words -> 16-byte boundary

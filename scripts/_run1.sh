@@ -1,9 +1,8 @@
-run() { env "$@" timeout 100 python bench.py --steps 30 --warmup 5 --no-cpu --no-e2e --pcg-iters 0 2>/dev/null | python -c "
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; tail -5 gpurun_out/pytest_gpu.log
+run() { env "$@" timeout 100 python bench.py --steps 30 --warmup 5 --no-cpu --no-e2e --pcg-iters 20 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
-print('$*', 'GDOF/s %.2f'%d['value'], 'kernel_ms %.4f'%d['roofline']['kernel_ms'], 'step_ms %.4f'%d['ms_per_step'])"; }
-run HCURL_PATCH_FE=64
-run HCURL_PATCH_FE=64 HCURL_GATHER_CG=1
+print('$*', 'GDOF/s %.2f'%d['value'], 'kernel_ms %.4f'%d['roofline']['kernel_ms'], 'step_ms %.4f'%d['ms_per_step'], 'pcg ms/it %.4f'%d['pcg']['ms_per_iter'], 'setup %.1f'%d['setup_s'])"; }
 run HCURL_PATCH_FE=32
-run HCURL_PATCH_FE=32 HCURL_GATHER_CG=1
-run HCURL_PATCH_FE=128 HCURL_GATHER_CG=1
+run HCURL_PATCH_FE=64
