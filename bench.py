@@ -333,7 +333,8 @@ def main():
         "config": workload_config(args, n, n_dof_global),
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "pcg": {"iters_per_s": 1e3 / pcg_iter_ms, "ms_per_iter": pcg_iter_ms, "iters": solver.num_iterations,
-                "precond": "jacobi", "gdofs": n_dof_global / (pcg_iter_ms * 1e-3) / 1e9},
+                "precond": "jacobi", "gdofs": n_dof_global / (pcg_iter_ms * 1e-3) / 1e9,
+                "final_rel_res": solver.final_rel_res},
         "setup_s": t_setup,
     }
     print(json.dumps(line))

@@ -80,7 +80,8 @@ __global__ void axpby_kernel(const int64_t n, const double a, const double *__re
 // bit-reproducible for a fixed grid) and stores the result in out[slot].
 static constexpr int RED_THREADS = 256;
 
-__device__ __forceinline__ void block_finish(double v, double *partial, unsigned int *counter, double *out) {
+// add_to != nullptr: the result is added to *add_to instead of stored in *out
+__device__ __forceinline__ void block_finish(double v, double *partial, unsigned int *counter, double *out, double *add_to = nullptr) {
   __shared__ double sh[RED_THREADS / 32];
   __shared__ bool last;
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
@@ -102,7 +103,10 @@ __device__ __forceinline__ void block_finish(double v, double *partial, unsigned
     for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) s += ((volatile double *)partial)[i];
     // fixed-order tree over lanes
     for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-    if (threadIdx.x == 0) *out = s;
+    if (threadIdx.x == 0) {
+      if (add_to) *add_to += s;
+      else *out = s;
+    }
   }
 }
 
@@ -112,6 +116,18 @@ dot_kernel(const int64_t n, const double *__restrict__ a, const double *__restri
   double s = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) s += a[i] * b[i];
   block_finish(s, partial, counter, out);
+}
+// dst[idx] = src[idx];  *out += sum src[idx]^2
+__global__ void __launch_bounds__(RED_THREADS)
+copy_idx_dot_kernel(const int32_t n, const int32_t *__restrict__ idx, const double *__restrict__ src, double *__restrict__ dst,
+                    double *partial, unsigned int *counter, double *out) {
+  double s = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double v = src[idx[i]];
+    dst[idx[i]] = v;
+    s += v * v;
+  }
+  block_finish(s, partial, counter, nullptr, out);
 }
 // out = sum dinv * b * b   (<C b, b>)
 __global__ void __launch_bounds__(RED_THREADS)
@@ -138,29 +154,45 @@ pcg_init_kernel(const int64_t n, const int sub, const double *__restrict__ b, co
   }
   block_finish(s, partial, counter, out);
 }
-// alpha = S[0]/S[1]; x += alpha p; r -= alpha s; s = C r; out = <r, s>
+// alpha = gamma/<s,p>; x += alpha p; r -= alpha s; s = C r; out = <r, s>
+// Five read and three write streams: 16-byte accesses, all loads of an iteration issued before its stores (left to
+// itself the compiler interleaves them load by load, which cost 30 % of the bandwidth in one build and not in the next).
 __global__ void __launch_bounds__(RED_THREADS)
-pcg_update_kernel(const int64_t n, const double *__restrict__ S, const double *__restrict__ dinv,
+pcg_update_kernel(const int64_t n, const double *__restrict__ gamma, const double *__restrict__ sdotp, const double *__restrict__ dinv,
                   const double *__restrict__ p, double *__restrict__ x, double *__restrict__ r, double *__restrict__ s,
                   double *partial, unsigned int *counter, double *out) {
-  const double alpha = S[0] / S[1];
-  double acc = 0.0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  const double alpha = *gamma / *sdotp;
+  double acc0 = 0.0, acc1 = 0.0;
+  const int64_t n2 = n >> 1;
+  const double2 *p2 = reinterpret_cast<const double2 *>(p), *d2 = reinterpret_cast<const double2 *>(dinv);
+  double2 *x2 = reinterpret_cast<double2 *>(x), *r2 = reinterpret_cast<double2 *>(r), *s2 = reinterpret_cast<double2 *>(s);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
+    const double2 pv = __ldg(p2 + i), xv = x2[i], rv = r2[i], sv = s2[i];
+    const double2 dv = dinv ? __ldg(d2 + i) : make_double2(1.0, 1.0);
+    const double2 rn = make_double2(rv.x - alpha * sv.x, rv.y - alpha * sv.y);
+    const double2 zn = make_double2(dv.x * rn.x, dv.y * rn.y);
+    x2[i] = make_double2(xv.x + alpha * pv.x, xv.y + alpha * pv.y);
+    r2[i] = rn;
+    s2[i] = zn;
+    acc0 = fma(rn.x, zn.x, acc0);
+    acc1 = fma(rn.y, zn.y, acc1);
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const int64_t i = n - 1;
     x[i] += alpha * p[i];
-    const double ri = r[i] - alpha * s[i];
-    const double zi = (dinv ? dinv[i] : 1.0) * ri;
+    const double ri = r[i] - alpha * s[i], zi = (dinv ? dinv[i] : 1.0) * ri;
     r[i] = ri;
     s[i] = zi;
-    acc += ri * zi;
+    acc0 = fma(ri, zi, acc0);
   }
-  block_finish(acc, partial, counter, out);
+  block_finish(acc0 + acc1, partial, counter, out);
 }
-// p = s + beta p;  S[0] <- gamma_new
-__global__ void pcg_dir_kernel(const int64_t n, const double beta, const double gamma_new, double *S,
+// p = s + beta p, beta = gamma_new / gamma taken from the device (the host has not seen gamma_new yet)
+__global__ void pcg_dir_kernel(const int64_t n, const double *__restrict__ gamma_new, const double *__restrict__ gamma,
                                const double *__restrict__ s, double *__restrict__ p) {
+  const double beta = *gamma_new / *gamma;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     p[i] = s[i] + beta * p[i];
-  if (blockIdx.x == 0 && threadIdx.x == 0) S[0] = gamma_new;
 }
 __global__ void invert_kernel(const int64_t n, double *__restrict__ d) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) d[i] = 1.0 / d[i];
@@ -187,7 +219,8 @@ static int red_grid(hcurl_ctx *ctx, int64_t n) {
 }
 
 // ---- apply on extended device vectors -------------------------------------------------
-int op_apply_ext(hcurl_op *op, double *d_x, double *d_y, bool constrained, double scale, bool accumulate) {
+int op_apply_ext(hcurl_op *op, double *d_x, double *d_y, bool constrained, double scale, bool accumulate, double *d_dot,
+                 bool *dot_done) {
   hcurl_space *sp = op->sp;
   hcurl_ctx *ctx = op->ctx;
   const int64_t next = sp->n_ext();
@@ -205,14 +238,22 @@ int op_apply_ext(hcurl_op *op, double *d_x, double *d_y, bool constrained, doubl
   if (op->ring_ok) { e0 = op->ring0[op->ring_n % hcurl_op::RING]; e1 = op->ring1[op->ring_n % hcurl_op::RING]; op->ring_n++; op->ev0 = e0; op->ev1 = e1; }
   if (op->timed) HC_CUDA(cudaEventRecord(e0, ctx->stream));
   int rc;
-  if (patch_path) { op->last_kernel = 3; rc = hex_patch_launch(op, constrained, d_x, d_y, scale, accumulate); }
+  const bool fuse_dot = patch_path && d_dot && !accumulate;
+  if (dot_done) *dot_done = fuse_dot;
+  if (patch_path) { op->last_kernel = 3; rc = hex_patch_launch(op, constrained, d_x, d_y, scale, accumulate, fuse_dot ? d_dot : nullptr); }
   else if (hex_fast_eligible(op)) { op->last_kernel = 2; rc = hex_fast_launch(op, constrained, d_x, d_y, scale); }
   else { op->last_kernel = 1; rc = (sp->geom == HCURL_GEOM_HEX) ? hex_apply_launch(op, map, d_x, d_y, scale) : tet_apply_launch(op, map, d_x, d_y, scale); }
   if (rc) return rc;
   if (op->timed) HC_CUDA(cudaEventRecord(e1, ctx->stream));
   if (exchange_reduce(sp, d_y)) return 1;
-  if (constrained && op->n_ess > 0)
-    { copy_idx_kernel<<<(op->n_ess + 255) / 256, 256, 0, ctx->stream>>>(op->n_ess, op->d_ess, d_x, d_y); ctx->launches++; }
+  if (constrained && op->n_ess > 0) {
+    if (fuse_dot) {  // essential rows are identity: y = x there, and <x, y> gains x^2
+      int g = (op->n_ess + RED_THREADS * 4 - 1) / (RED_THREADS * 4);
+      if (g > ctx->n_partial) g = ctx->n_partial;
+      copy_idx_dot_kernel<<<g, RED_THREADS, 0, ctx->stream>>>(op->n_ess, op->d_ess, d_x, d_y, ctx->d_partial, ctx->d_counter, d_dot);
+    } else copy_idx_kernel<<<(op->n_ess + 255) / 256, 256, 0, ctx->stream>>>(op->n_ess, op->d_ess, d_x, d_y);
+    ctx->launches++;
+  }
   HC_CUDA(cudaGetLastError());
   return 0;
 }
@@ -680,6 +721,7 @@ void hcurl_pcg_destroy(hcurl_pcg *s) {
   cudaStreamSynchronize(s->ctx->stream);
   cudaFree(s->d_r); cudaFree(s->d_p); cudaFree(s->d_s); cudaFree(s->d_x); cudaFree(s->d_b); cudaFree(s->d_dinv);
   cudaEventDestroy(s->ev0); cudaEventDestroy(s->ev1);
+  if (s->ev_red) cudaEventDestroy(s->ev_red);
   delete s;
 }
 int hcurl_pcg_set(hcurl_pcg *s, double rtol, double atol, int max_iter, int print_level) {
@@ -732,26 +774,38 @@ int hcurl_pcg_solve(hcurl_pcg *s, const double *b, double *x, int zero_guess, in
   HC_CUDA(cudaStreamSynchronize(st));
   double gamma = ctx->h_red[0];
   int i = 0, conv = 0;
+  // The loop follows hypre's PCG step by step; what differs is where the numbers live:
+  //  * <p, A p> comes out of the patch kernel itself when it runs (summed per element in modal space);
+  //  * gamma alternates between S[0] and S[2], so that beta = gamma_new / gamma is formed on the device and the
+  //    direction update is enqueued BEFORE the host has read gamma_new: the host's convergence test (same test,
+  //    same iteration count) overlaps with it instead of draining the GPU every iteration.  When the test says
+  //    stop, the direction update already in flight only touched p, which is dead by then.
+  if (!s->ev_red) HC_CUDA(cudaEventCreateWithFlags(&s->ev_red, cudaEventDisableTiming));
   HC_CUDA(cudaEventRecord(s->ev0, st));
+  int go = 0;  // S[go] holds gamma, S[2 - go] receives gamma_new
   while (i + 1 <= s->max_iter) {
     i++;
-    if (op_apply_ext(op, s->d_p, s->d_s, true, 1.0, false)) return 1;
-    dot_kernel<<<g, RED_THREADS, 0, st>>>(nt, s->d_s, s->d_p, ctx->d_partial, ctx->d_counter, S + 1);
-    ctx->launches += 2;  // dot + fused update below
+    bool fused = false;
+    static const bool want_fused = [] { const char *e = getenv("HCURL_PCG_FUSED_DOT"); return !(e && e[0] == '0'); }();
+    if (op_apply_ext(op, s->d_p, s->d_s, true, 1.0, false, want_fused ? S + 1 : nullptr, &fused)) return 1;
+    if (!fused) { dot_kernel<<<g, RED_THREADS, 0, st>>>(nt, s->d_s, s->d_p, ctx->d_partial, ctx->d_counter, S + 1); ctx->launches++; }
     if (allreduce_sum(ctx, S + 1, 1)) return 1;
-    pcg_update_kernel<<<g, RED_THREADS, 0, st>>>(nt, S, dinv, s->d_p, s->d_x, s->d_r, s->d_s, ctx->d_partial, ctx->d_counter, S + 2);
-    if (allreduce_sum(ctx, S + 2, 1)) return 1;
+    pcg_update_kernel<<<g, RED_THREADS, 0, st>>>(nt, S + go, S + 1, dinv, s->d_p, s->d_x, s->d_r, s->d_s, ctx->d_partial, ctx->d_counter,
+                                                 S + 2 - go);
+    ctx->launches++;
+    if (allreduce_sum(ctx, S + 2 - go, 1)) return 1;
     HC_CUDA(cudaMemcpyAsync(ctx->h_red, S, sizeof(double) * 4, cudaMemcpyDeviceToHost, st));
-    HC_CUDA(cudaStreamSynchronize(st));
-    const double sdotp = ctx->h_red[1], gamma_new = ctx->h_red[2];
+    HC_CUDA(cudaEventRecord(s->ev_red, st));
+    pcg_dir_kernel<<<g, RED_THREADS, 0, st>>>(nt, S + 2 - go, S + go, s->d_s, s->d_p);
+    ctx->launches++;
+    HC_CUDA(cudaEventSynchronize(s->ev_red));
+    const double sdotp = ctx->h_red[1], gamma_new = ctx->h_red[2 - go];
     if (sdotp == 0.0) { break; }
     if (s->print_level > 1 && ctx->rank == 0) printf("  hcurl pcg it %d  rel res %.6e\n", i, sqrt(fabs(gamma_new) / bi_prod));
     if (gamma_new / bi_prod < eps) { gamma = gamma_new; conv = 1; break; }
     if (fabs(gamma_new) < 1e-292) { gamma = gamma_new; break; }
-    const double beta = gamma_new / gamma;
     gamma = gamma_new;
-    pcg_dir_kernel<<<g, RED_THREADS, 0, st>>>(nt, beta, gamma_new, S, s->d_s, s->d_p);
-    ctx->launches++;
+    go = 2 - go;
   }
   HC_CUDA(cudaEventRecord(s->ev1, st));
   HC_CUDA(cudaGetLastError());

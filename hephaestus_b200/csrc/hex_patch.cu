@@ -179,6 +179,10 @@ struct PatchArgs {
   double scale;
   uint32_t blob_cap_bytes;   // shared-memory room reserved for one blob (multiple of 16)
   uint32_t xs_cap_bytes;     // room for the x staging vector (max patch pairs * 16)
+  // fused <x, y> (PCG's <p, A p>): per-CTA partial sums, arrival counter, result (null = not wanted)
+  double *dot_partial;
+  unsigned int *dot_counter;
+  double *dot_out;
   unsigned long long *prof;  // null, or 8 counters: cycles of thread 0 per phase summed over patches (scripts/phase_profile.py)
 };
 #define PROF_MARK(i)                                                                         \
@@ -233,6 +237,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *mbar, uint32_t parity) {
 __device__ __forceinline__ void gather16_async(double2 *dst, const double2 *src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
 }
+// fire-and-forget FP64 add (REDG).  Spelled in PTX: once a kernel variant contains fences (the fused dot product's
+// last-CTA reduction) nvcc turns atomicAdd() with an unused result into returning ATOMG, which made that variant
+// 37 % slower.
+__device__ __forceinline__ void red_add(double *p, double v) {
+  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
 __device__ __forceinline__ void gather_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void gather_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -244,7 +254,7 @@ __device__ __forceinline__ void gather_wait_all() { asm volatile("cp.async.wait_
 //   E   [27][FE+1]        element slot pairs (double2): modal coefficients exchanged between the component threads
 //   EY  [27][FE+1]        element slot pairs: element results, summed per dof pair
 // (two buffers so that a patch needs three CTA barriers, not five)
-template <int FE, int MINB, bool ACC, bool PROF>
+template <int FE, int MINB, bool ACC, bool PROF, bool DOT>
 __global__ void __maxnreg__(168)
 hex_patch_modal_p2_kernel(const PatchArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -260,6 +270,7 @@ hex_patch_modal_p2_kernel(const PatchArgs a) {
   const int tid = threadIdx.x;
   long long t_prev = PROF ? clock64() : 0;
   unsigned long long prof_acc[6] = {0, 0, 0, 0, 0, 0};
+  double dacc = 0.0;  // DOT: my share of x^T A x, summed in modal space (x_e^T A_e x_e = Am^T Yh)
   const int64_t k0 = blockIdx.x, kstep = gridDim.x;
   const int n_it = (int)((a.n_patch - k0 + kstep - 1) / kstep);
   // component c of patch element el, in the rotated frame (c, c+1, c+2)
@@ -375,6 +386,12 @@ hex_patch_modal_p2_kernel(const PatchArgs a) {
       K11 *= sc; K10 *= sc; K12 *= sc; K22 *= sc; K20 *= sc; M00 *= sc; M01 *= sc; M02 *= sc;
       double Yh[18];
       modal_op(Am, Bm, Cm, M00, M01, M02, K11, K10, K12, K22, K20, K12, Yh);
+      if (DOT) {
+        double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+        for (int t = 0; t < 18; t += 2) { d0 = fma(Am[t], Yh[t], d0); d1 = fma(Am[t + 1], Yh[t + 1], d1); }
+        dacc += d0 + d1;
+      }
       modal_bwd(Yh, Y);
     }
     // ---- start the x gather of the next patch: it lands while this patch is scattered
@@ -411,8 +428,8 @@ hex_patch_modal_p2_kernel(const PatchArgs a) {
           else *dst = v;
         } else if ((m & SKIP) != SKIP) {
           if (m & PATCH_SHARED) {
-            if (!(m & PATCH_ESS0)) atomicAdd(&dst->x, v.x);
-            if (!(m & PATCH_ESS1)) atomicAdd(&dst->y, v.y);
+            if (!(m & PATCH_ESS0)) red_add(&dst->x, v.x);
+            if (!(m & PATCH_ESS1)) red_add(&dst->y, v.y);
           } else {
             if (!(m & PATCH_ESS0)) dst->x = ACC ? dst->x + v.x : v.x;
             if (!(m & PATCH_ESS1)) dst->y = ACC ? dst->y + v.y : v.y;
@@ -466,8 +483,8 @@ hex_patch_modal_p2_kernel(const PatchArgs a) {
         const uint32_t e = ovf[t], m = dof[e >> 16];
         const double2 v = E_AT(e & 0xffffu);
         double2 *dst = y2 + (m & PATCH_IDX);
-        if (!(m & PATCH_ESS0)) atomicAdd(&dst->x, v.x);
-        if (!(m & PATCH_ESS1)) atomicAdd(&dst->y, v.y);
+        if (!(m & PATCH_ESS0)) red_add(&dst->x, v.x);
+        if (!(m & PATCH_ESS1)) red_add(&dst->y, v.y);
       }
 #undef E_AT
     }
@@ -481,6 +498,30 @@ hex_patch_modal_p2_kernel(const PatchArgs a) {
   }
   if (PROF && tid == 0)
     for (int i = 0; i < 6; i++) atomicAdd(a.prof + i, prof_acc[i]);
+  if (DOT) {
+    // deterministic for a fixed grid: fixed-order sums inside the CTA, per-CTA partials, the last CTA to arrive
+    // adds them in index order (same protocol as block_finish() of the vector kernels, api.cu)
+    double *red = reinterpret_cast<double *>(E2);  // all patches retired: E is free
+    __shared__ bool last;
+    for (int o = 16; o > 0; o >>= 1) dacc += __shfl_down_sync(0xffffffffu, dacc, o);
+    if ((tid & 31) == 0) red[tid >> 5] = dacc;
+    __syncthreads();
+    if (tid == 0) {
+      double v = 0.0;
+      for (int w = 0; w < NT / 32; w++) v += red[w];
+      a.dot_partial[blockIdx.x] = v;
+      __threadfence();
+      last = atomicInc(a.dot_counter, gridDim.x - 1) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && tid < 32) {
+      __threadfence();
+      double v = 0.0;
+      for (int i = tid; i < (int)gridDim.x; i += 32) v += ((volatile double *)a.dot_partial)[i];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      if (tid == 0) *a.dot_out = v;
+    }
+  }
 }
 
 // ---- setup ---------------------------------------------------------------------------------------
@@ -657,15 +698,18 @@ bool hex_patch_eligible(const hcurl_op *op) {
 
 template <int FE, int MINB>
 static int launch_fe(const PatchArgs &a, int64_t n_patch, int sm_count, size_t smem, bool acc, cudaStream_t st) {
-  auto k0 = hex_patch_modal_p2_kernel<FE, MINB, false, false>;
-  auto k1 = hex_patch_modal_p2_kernel<FE, MINB, true, false>;
-  auto kp = hex_patch_modal_p2_kernel<FE, MINB, false, true>;
+  auto k0 = hex_patch_modal_p2_kernel<FE, MINB, false, false, false>;
+  auto k1 = hex_patch_modal_p2_kernel<FE, MINB, true, false, false>;
+  auto kp = hex_patch_modal_p2_kernel<FE, MINB, false, true, false>;
+  auto kd = hex_patch_modal_p2_kernel<FE, MINB, false, false, true>;
   static size_t attr = 0;
   static int per_sm = 0;
   if (attr < smem) {
     HC_CUDA(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     HC_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     HC_CUDA(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HC_CUDA(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HC_CUDA(cudaFuncSetAttribute(kd, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     HC_CUDA(cudaFuncSetAttribute(k0, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     HC_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     HC_CUDA(cudaFuncSetAttribute(kp, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -677,13 +721,16 @@ static int launch_fe(const PatchArgs &a, int64_t n_patch, int sm_count, size_t s
   int64_t grid = (int64_t)per_sm * sm_count;
   if (const char *s = getenv("HCURL_PATCH_CTAS_PER_SM")) { const int v = atoi(s); if (v >= 1 && v <= per_sm) grid = (int64_t)v * sm_count; }
   if (grid > n_patch) grid = n_patch;
-  if (a.prof) kp<<<(unsigned)grid, 3 * FE, smem, st>>>(a);
+  if (a.dot_out) {
+    if (acc) { set_error("patch kernel: fused dot product is not available with accumulation"); return 1; }
+    kd<<<(unsigned)grid, 3 * FE, smem, st>>>(a);
+  } else if (a.prof) kp<<<(unsigned)grid, 3 * FE, smem, st>>>(a);
   else if (acc) k1<<<(unsigned)grid, 3 * FE, smem, st>>>(a);
   else k0<<<(unsigned)grid, 3 * FE, smem, st>>>(a);
   return 0;
 }
 
-int hex_patch_launch(hcurl_op *op, bool constrained, const double *d_x, double *d_y, double scale, bool accumulate) {
+int hex_patch_launch(hcurl_op *op, bool constrained, const double *d_x, double *d_y, double scale, bool accumulate, double *d_dot) {
   hcurl_space *sp = op->sp;
   hcurl_ctx *ctx = op->ctx;
   PatchSet &P = sp->patch;
@@ -703,6 +750,8 @@ int hex_patch_launch(hcurl_op *op, bool constrained, const double *d_x, double *
   a.xs_cap_bytes = P.max_dofs * 16u;
   a.edata = op->d_edataP; a.x = d_x; a.y = d_y; a.scale = scale;
   a.prof = g_patch_prof;
+  a.dot_out = d_dot; a.dot_partial = ctx->d_partial; a.dot_counter = ctx->d_counter;
+  if (d_dot && ctx->n_partial < 8 * ctx->sm_count) { set_error("reduction scratch too small for the patch grid"); return 1; }
   if (a.prof && accumulate) a.prof = nullptr;
   const size_t smem = patch_smem_bytes(P.FE, P.max_blob_words, P.max_dofs);
   int rc = 1;

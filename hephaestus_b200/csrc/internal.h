@@ -195,7 +195,7 @@ struct hcurl_pcg {
   double *d_dinv = nullptr, *d_r = nullptr, *d_p = nullptr, *d_s = nullptr, *d_x = nullptr, *d_b = nullptr;
   bool diag_valid = false;
   float last_loop_ms = 0.f;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_red = nullptr;
 };
 
 namespace hcurl {
@@ -209,7 +209,9 @@ void hex_patch_free(hcurl_space *sp);
 bool hex_patch_eligible(const hcurl_op *op);
 // y (+)= scale * A x through the patch path; when !accumulate every dof of y is written
 // (private dofs) or must have been zeroed by the caller (shared dofs)
-int hex_patch_launch(hcurl_op *op, bool constrained, const double *d_x, double *d_y, double scale, bool accumulate);
+// d_dot (optional, device): receives <x, y_elements> = sum over elements of x_e^T A_e x_e, computed inside the kernel
+int hex_patch_launch(hcurl_op *op, bool constrained, const double *d_x, double *d_y, double scale, bool accumulate,
+                     double *d_dot = nullptr);
 int hex_patch_flag_essential(hcurl_op *op, const double *d_flag);
 // zero what the patch kernel accumulates into (instead of clearing all of y)
 int hex_patch_zero_shared(hcurl_op *op, double *d_y);
@@ -225,6 +227,9 @@ int comm_init(hcurl_ctx *ctx, const void *uid);
 void comm_destroy(hcurl_ctx *ctx);
 int comm_unique_id(void *out128);
 // the apply on extended device vectors, including exchange and essential handling
-int op_apply_ext(hcurl_op *op, double *d_x_ext, double *d_y_ext, bool constrained, double scale, bool accumulate);
+// d_dot (optional, device scalar): on return of the stream work holds <x, y> over this rank's share (elements + owned
+// essential dofs) when the patch kernel ran (*dot_done = true); otherwise untouched
+int op_apply_ext(hcurl_op *op, double *d_x_ext, double *d_y_ext, bool constrained, double scale, bool accumulate,
+                 double *d_dot = nullptr, bool *dot_done = nullptr);
 int op_diag_ext(hcurl_op *op, double *d_diag_ext);
 }  // namespace hcurl
