@@ -32,7 +32,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--n", type=int, default=128, help="hexes per edge of the per-GPU cube")
+    ap.add_argument("--n", type=int, default=int(os.environ.get("HCURL_BENCH_N", "128")), help="hexes per edge of the per-GPU cube")
     ap.add_argument("--order", type=int, default=2)
     ap.add_argument("--perturbed", action="store_true", help="trilinearly perturbed mesh variant (general geometry)")
     ap.add_argument("--quad", default="fast", choices=["fast", "mfem"])
@@ -318,6 +318,7 @@ def main():
                 "fp64_fma_peak_tflops_measured": fp64}
 
     if rank != 0:
+        _finish(dist)
         return
     cpu = None
     if world == 1 and not args.no_cpu:
@@ -338,8 +339,21 @@ def main():
         "setup_s": t_setup,
     }
     print(json.dumps(line))
+    _finish(dist)
+
+
+def _finish(dist):
+    """Every rank leaves the same way: flush, meet at a barrier, and exit without running the NCCL communicator
+    destructors (two communicators -- torch's and the library's -- torn down in interpreter-exit order used to leave
+    one rank waiting for the other until the launcher's timeout)."""
+    sys.stdout.flush()
+    sys.stderr.flush()
     if dist is not None:
-        dist.destroy_process_group()
+        try:
+            dist.barrier()
+        except Exception:
+            pass
+        os._exit(0)
 
 
 if __name__ == "__main__":

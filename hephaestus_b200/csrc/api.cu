@@ -264,7 +264,7 @@ int op_diag_ext(hcurl_op *op, double *d_diag) {
   HC_CUDA(cudaMemsetAsync(d_diag, 0, sizeof(double) * sp->n_ext(), ctx->stream));
   int rc = (sp->geom == HCURL_GEOM_HEX) ? hex_diag_launch(op, d_diag) : tet_diag_launch(op, d_diag);
   if (rc) return rc;
-  if (exchange_reduce(sp, d_diag)) return 1;
+  if (exchange_reduce(sp, d_diag, false)) return 1;  // diagonal entries are orientation-independent
   if (op->n_ess > 0) set_flags_kernel<<<(op->n_ess + 255) / 256, 256, 0, ctx->stream>>>(op->n_ess, op->d_ess, d_diag, 1.0);
   HC_CUDA(cudaGetLastError());
   return 0;
@@ -796,10 +796,13 @@ int hcurl_pcg_solve(hcurl_pcg *s, const double *b, double *x, int zero_guess, in
     if (allreduce_sum(ctx, S + 2 - go, 1)) return 1;
     HC_CUDA(cudaMemcpyAsync(ctx->h_red, S, sizeof(double) * 4, cudaMemcpyDeviceToHost, st));
     HC_CUDA(cudaEventRecord(s->ev_red, st));
+    static const bool nospec = [] { const char *e = getenv("HCURL_PCG_NOSPEC"); return e && e[0] == '1'; }();
+    if (nospec) HC_CUDA(cudaStreamSynchronize(st));
     pcg_dir_kernel<<<g, RED_THREADS, 0, st>>>(nt, S + 2 - go, S + go, s->d_s, s->d_p);
     ctx->launches++;
     HC_CUDA(cudaEventSynchronize(s->ev_red));
     const double sdotp = ctx->h_red[1], gamma_new = ctx->h_red[2 - go];
+    if (s->print_level > 2) printf("  [rank %d] it %d  <p,Ap> %.17g  gamma_new %.17g  gamma %.17g  bi_prod %.17g  eps %.3g\n", ctx->rank, i, sdotp, gamma_new, gamma, bi_prod, eps);
     if (sdotp == 0.0) { break; }
     if (s->print_level > 1 && ctx->rank == 0) printf("  hcurl pcg it %d  rel res %.6e\n", i, sqrt(fabs(gamma_new) / bi_prod));
     if (gamma_new / bi_prod < eps) { gamma = gamma_new; conv = 1; break; }

@@ -135,12 +135,14 @@ int exchange_broadcast(hcurl_space *sp, double *d_ext) {
   return 0;
 }
 
-// y_ext: ghosts -> owner (sum)
-int exchange_reduce(hcurl_space *sp, double *d_ext) {
+// y_ext: ghosts -> owner (sum).  signed_values: the entries are components of a vector in the local orientation of
+// each dof (flip the ghosts that are oriented against their owner); false for quantities that do not change sign with
+// the orientation (the operator diagonal).
+int exchange_reduce(hcurl_space *sp, double *d_ext, bool signed_values) {
   hcurl_ctx *ctx = sp->ctx;
   if (sp->n_nbr == 0) return 0;
   Nccl *N = nccl();
-  if (sp->d_ghost_sign && sp->n_ghost > 0)
+  if (signed_values && sp->d_ghost_sign && sp->n_ghost > 0)
     sign_kernel<<<(sp->n_ghost + 255) / 256, 256, 0, ctx->stream>>>(sp->n_ghost, sp->d_ghost_sign, d_ext + sp->n_tdof);
   HC_NCCL(N->GroupStart());
   for (int r = 0; r < sp->n_nbr; r++) {

@@ -671,8 +671,8 @@ int hex_patch_build(hcurl_space *sp, const double *elem_xyz, const int32_t *elem
   P.FE = FE; P.stride = H.stride; P.n_patch = H.n_patch;
   P.blob_words = (int64_t)H.blob.size(); P.max_blob_words = H.max_blob_words; P.max_dofs = H.max_dofs;
   if (patch_smem_bytes(FE, H.max_blob_words, H.max_dofs) > 227 * 1024) return 0;  // patch path unavailable
-  if (upload(P.d_perm, H.perm) || upload(P.d_blob_off, H.blob_off) || upload(P.d_blob, H.blob) || upload(P.d_shared, H.shared_units)) return 1;
-  P.n_shared = (int64_t)H.shared_units.size();
+  if (upload(P.d_perm, H.perm) || upload(P.d_blob_off, H.blob_off) || upload(P.d_blob, H.blob) || upload(P.d_shared, H.shared_lines)) return 1;
+  P.n_shared = (int64_t)H.shared_lines.size();
   sp->has_patches = true;
   return 0;
 }
@@ -766,18 +766,24 @@ int hex_patch_launch(hcurl_op *op, bool constrained, const double *d_x, double *
   return 0;
 }
 
-__global__ void patch_zero_shared_kernel(const int64_t n, const uint32_t *__restrict__ idx, double2 *__restrict__ y2) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) y2[idx[i]] = make_double2(0.0, 0.0);
+// eight lanes clear one 128-byte line (the last line of the vector may be partial)
+__global__ void patch_zero_shared_kernel(const int64_t n_lines, const uint32_t *__restrict__ line, double2 *__restrict__ y2,
+                                         const int64_t n_pairs) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_lines * 8) return;
+  const int64_t q = (int64_t)line[t >> 3] * 8 + (t & 7);
+  if (q < n_pairs) y2[q] = make_double2(0.0, 0.0);
 }
 
-// Private pairs are stored, shared pairs are RED-added by the patch kernel: only the latter (about a fifth of the
-// vector) need to start from zero, so a full memset of y (a quarter of the vector traffic of an apply) is avoided.
+// Private pairs are stored, shared pairs are RED-added by the patch kernel: only the latter need to start from zero.
+// Whole 128-byte lines holding a shared pair are cleared (full-sector writes; private pairs in them are stored later by
+// the kernel anyway) instead of all of y.
 int hex_patch_zero_shared(hcurl_op *op, double *d_y) {
   PatchSet &P = op->sp->patch;
   if (P.n_shared == 0) return 0;
-  patch_zero_shared_kernel<<<(unsigned)((P.n_shared + 255) / 256), 256, 0, op->ctx->stream>>>(P.n_shared, P.d_shared,
-                                                                                             reinterpret_cast<double2 *>(d_y));
+  const int64_t nt = P.n_shared * 8;
+  patch_zero_shared_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, op->ctx->stream>>>(P.n_shared, P.d_shared, reinterpret_cast<double2 *>(d_y),
+                                                                                     op->sp->n_ext() / 2);
   HC_CUDA(cudaGetLastError());
   op->ctx->launches++;
   return 0;

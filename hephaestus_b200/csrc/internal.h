@@ -79,7 +79,7 @@ struct PatchHost {
   std::vector<uint32_t> blob;     // see patch.cpp for the layout
   uint32_t max_blob_words = 0;
   uint32_t max_dofs = 0;          // largest number of unique dofs of one patch
-  std::vector<uint32_t> shared_units;  // units touched by more than one patch (their sums are RED-added), ascending
+  std::vector<uint32_t> shared_lines;  // 128-byte lines of the vector holding a unit touched by more than one patch (RED-added)
 };
 int build_patches(int nd, int64_t n_elem, int FE, int stride, int unit_bytes, int64_t n_ext, const double *centroid,
                   const uint32_t *slot_code, PatchHost &out);
@@ -94,7 +94,7 @@ struct PatchSet {  // device copy
   uint32_t *d_blob_off = nullptr, *d_blob = nullptr;
   int64_t blob_words = 0;
   uint32_t max_blob_words = 0, max_dofs = 0;
-  uint32_t *d_shared = nullptr;  // pairs whose sums are RED-added: the only part of y that must be zero before an apply
+  uint32_t *d_shared = nullptr;  // 128-byte lines holding RED-added pairs: the only part of y that must be zero before an apply
   int64_t n_shared = 0;
 };
 
@@ -221,7 +221,7 @@ int tet_apply_launch(hcurl_op *op, const uint32_t *d_map, const double *d_x, dou
 int tet_diag_launch(hcurl_op *op, double *d_diag);
 // exchange (comm.cu): broadcast owner->ghost on x_ext, reduce ghost->owner on y_ext
 int exchange_broadcast(hcurl_space *sp, double *d_ext);
-int exchange_reduce(hcurl_space *sp, double *d_ext);
+int exchange_reduce(hcurl_space *sp, double *d_ext, bool signed_values = true);
 int allreduce_sum(hcurl_ctx *ctx, double *d_vals, int n);
 int comm_init(hcurl_ctx *ctx, const void *uid);
 void comm_destroy(hcurl_ctx *ctx);

@@ -169,9 +169,16 @@ int build_patches(int nd, int64_t n_elem, int FE, int stride, int unit_bytes, in
     }
   }
   owner.clear(); owner.shrink_to_fit();
-  out.shared_units.clear();
-  for (int64_t d = 0; d < n_ext; d++)
-    if (multi[(size_t)d]) out.shared_units.push_back((uint32_t)d);
+  // 128-byte lines of the vector that hold at least one shared unit (ascending)
+  out.shared_lines.clear();
+  {
+    const int64_t per_line = 128 / unit_bytes;
+    for (int64_t l = 0; l * per_line < n_ext; l++) {
+      bool any = false;
+      for (int64_t d = l * per_line; d < std::min(n_ext, (l + 1) * per_line); d++) any |= multi[(size_t)d] != 0;
+      if (any) out.shared_lines.push_back((uint32_t)l);
+    }
+  }
   // ---- emit one blob per patch
   auto width_of = [](int nslot) { return nslot <= 1 ? 0 : (nslot == 2 ? 1 : 2); };
   auto align4 = [](uint32_t w) { return (w + 3u) & ~3u; };  // words -> 16-byte boundary

@@ -54,7 +54,7 @@ def main():
     # PCG: same iteration count / solution as the serial oracle solve
     Ac, _ = oa.eliminate(A, ess)
     b_s = Ac @ np.random.default_rng(54321).standard_normal(so.ndof)
-    solver = operators.HephGpuPCG(ctx, tol=1e-9, max_iter=3000)
+    solver = operators.HephGpuPCG(ctx, tol=1e-9, max_iter=3000, print_level=int(os.environ.get("HCURL_TEST_PCG_PRINT", "0")))
     solver.SetOperator(op)
     xs = solver.Mult(sgn[own] * b_s[idx[own]])
     xo, it_o, _, conv_o, _ = opcg.pcg(Ac, b_s, diag=Ac.diagonal(), rtol=solver.tol, atol=solver.abstol, max_iter=3000)
