@@ -38,6 +38,7 @@ SIGNATURES = {
     "hcurl_ctx_launch_count": (C.c_int64, [_P]),
     "hcurl_space_create": (_P, [_P, C.c_int, C.c_int, C.c_int, C.c_int64, _P, _P, _P, _P, C.c_int32, _P, C.c_int32,
                                 C.c_int, _P, _P, _P, _P, _P, _P]),
+    "hcurl_space_ext_size": (C.c_int64, [_P]),
     "hcurl_space_destroy": (None, [_P]),
     "hcurl_space_ndof_local": (C.c_int32, [_P]),
     "hcurl_space_ndof_true": (C.c_int32, [_P]),
@@ -79,13 +80,14 @@ SIGNATURES = {
     "hcurl_host_patches_blob_words": (C.c_int64, [_P]),
     "hcurl_host_patches_max_blob_words": (C.c_int64, [_P]),
     "hcurl_host_patches_max_dofs": (C.c_int64, [_P]),
+    "hcurl_host_patches_swizzle": (C.c_int, [_P, _P, _P]),
     "hcurl_host_patches_copy": (C.c_int, [_P, _P, _P, _P]),
 }
 
 HEX, TET = 0, 1
 PER_ELEM, PER_QPT = 0, 1
 PC_NONE, PC_JACOBI = 0, 1
-HOST, DEVICE = 0, 1
+HOST, DEVICE, DEVICE_EXT = 0, 1, 2
 
 
 def lib():

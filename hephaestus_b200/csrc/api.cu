@@ -277,8 +277,8 @@ static int ensure_work(hcurl_op *op) {
   return 0;
 }
 
-static cudaMemcpyKind kind_in(int where) { return where == HCURL_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice; }
-static cudaMemcpyKind kind_out(int where) { return where == HCURL_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost; }
+static cudaMemcpyKind kind_in(int where) { return where != HCURL_HOST ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice; }
+static cudaMemcpyKind kind_out(int where) { return where != HCURL_HOST ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost; }
 
 }  // namespace hcurl
 
@@ -462,6 +462,7 @@ hcurl_space *hcurl_space_create(hcurl_ctx *ctx, int geom, int geom_order, int or
   return sp;
 }
 
+int64_t hcurl_space_ext_size(const hcurl_space *sp) { return sp->n_ext(); }
 void hcurl_space_destroy(hcurl_space *sp) {
   if (!sp) return;
   cudaSetDevice(sp->ctx->device);
@@ -588,8 +589,8 @@ static int apply_common(hcurl_op *op, const double *x, double *y, int where, boo
   HC_CUDA(cudaSetDevice(ctx->device));
   if (!op->has_alpha && !op->has_beta) { set_error("operator has no coefficients set"); return 1; }
   const int64_t nt = sp->n_tdof;
-  if (where == HCURL_DEVICE && sp->n_ghost == 0) {
-    // zero-copy: the caller's device T-vectors are the extended vectors
+  if ((where == HCURL_DEVICE && sp->n_ghost == 0) || where == HCURL_DEVICE_EXT) {
+    // zero-copy: the caller's device vectors are (or have room for) the extended vectors
     return op_apply_ext(op, const_cast<double *>(x), y, constrained, scale, accumulate != 0);
   }
   if (ensure_work(op)) return 1;

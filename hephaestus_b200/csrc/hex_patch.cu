@@ -30,6 +30,7 @@
 // E-vector layout (double2): E2[(c*9 + r)*(FE+1) + e] = slots t = 2r, 2r+1 of component c, t = i0 + 2*(i1 + 3*i2)
 // with i0 the open index along axis c: the element side moves 16-byte vectors, conflict-free.
 #include <cstdlib>
+#include <cstring>
 
 #include "internal.h"
 
@@ -183,6 +184,9 @@ struct PatchArgs {
   double *dot_partial;
   unsigned int *dot_counter;
   double *dot_out;
+  // EY position of (slot pair s, element e) is s*(FE+1) + (e ^ swz_row[s] ^ swz_grp[e >> 3]): chosen by patch.cpp so
+  // that the dof side's reads of EY spread over the banks
+  uint8_t swz_row[27], swz_grp[16];
   unsigned long long *prof;  // null, or 8 counters: cycles of thread 0 per phase summed over patches (scripts/phase_profile.py)
 };
 #define PROF_MARK(i)                                                                         \
@@ -233,7 +237,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t *mbar, uint32_t parity) {
   } while (!done);
 }
 // 16-byte asynchronous gather global -> shared (LDGSTS, L1 bypassed), no register staging.  (The L1-allocating
-// .ca form was measured 7-9 % slower per apply although ncu counts fewer shared-memory wavefronts for it.)
+// .ca form was measured 7-9 % slower per apply although ncu counts fewer shared-memory wavefronts for it; staging
+// through registers -- LDG.128 where the gather is issued, STS.128 at the end of the iteration -- 57 % slower.)
 __device__ __forceinline__ void gather16_async(double2 *dst, const double2 *src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
 }
@@ -307,7 +312,6 @@ hex_patch_modal_p2_kernel(const PatchArgs a) {
     }
     gather_commit();
   };
-
   if (tid == 0) {
     mbar_init(mbar, 1);
     mbar_init(mbar + 1, 1);
@@ -400,13 +404,14 @@ hex_patch_modal_p2_kernel(const PatchArgs a) {
       gather(b ^ 1);
     }
     if (ok) {
-      double2 *Eown = EY + (c * 9) * ST + el;
+      double2 *Eown = EY + (c * 9) * ST;
+      const int elx = el ^ a.swz_grp[el >> 3];
       if (plain) {
 #pragma unroll
-        for (int r = 0; r < 9; r++) Eown[r * ST] = make_double2(Y[2 * r], Y[2 * r + 1]);
+        for (int r = 0; r < 9; r++) Eown[r * ST + (elx ^ a.swz_row[c * 9 + r])] = make_double2(Y[2 * r], Y[2 * r + 1]);
       } else {
 #pragma unroll
-        for (int r = 0; r < 9; r++) Eown[r * ST] = local_to_pair(Y[2 * r], Y[2 * r + 1], lx[r]);
+        for (int r = 0; r < 9; r++) Eown[r * ST + (elx ^ a.swz_row[c * 9 + r])] = local_to_pair(Y[2 * r], Y[2 * r + 1], lx[r]);
       }
     }
     __syncthreads();  // element results visible; everyone has read the modal coefficients
@@ -670,6 +675,8 @@ int hex_patch_build(hcurl_space *sp, const double *elem_xyz, const int32_t *elem
   PatchSet &P = sp->patch;
   P.FE = FE; P.stride = H.stride; P.n_patch = H.n_patch;
   P.blob_words = (int64_t)H.blob.size(); P.max_blob_words = H.max_blob_words; P.max_dofs = H.max_dofs;
+  for (int i = 0; i < 27; i++) P.swz_row[i] = H.swz_row[(size_t)i];
+  for (size_t i = 0; i < 16; i++) P.swz_grp[i] = i < H.swz_grp.size() ? H.swz_grp[i] : 0;
   if (patch_smem_bytes(FE, H.max_blob_words, H.max_dofs) > 227 * 1024) return 0;  // patch path unavailable
   if (upload(P.d_perm, H.perm) || upload(P.d_blob_off, H.blob_off) || upload(P.d_blob, H.blob) || upload(P.d_shared, H.shared_lines)) return 1;
   P.n_shared = (int64_t)H.shared_lines.size();
@@ -750,6 +757,7 @@ int hex_patch_launch(hcurl_op *op, bool constrained, const double *d_x, double *
   a.xs_cap_bytes = P.max_dofs * 16u;
   a.edata = op->d_edataP; a.x = d_x; a.y = d_y; a.scale = scale;
   a.prof = g_patch_prof;
+  memcpy(a.swz_row, P.swz_row, sizeof(a.swz_row)); memcpy(a.swz_grp, P.swz_grp, sizeof(a.swz_grp));
   a.dot_out = d_dot; a.dot_partial = ctx->d_partial; a.dot_counter = ctx->d_counter;
   if (d_dot && ctx->n_partial < 8 * ctx->sm_count) { set_error("reduction scratch too small for the patch grid"); return 1; }
   if (a.prof && accumulate) a.prof = nullptr;

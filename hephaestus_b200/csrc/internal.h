@@ -79,6 +79,9 @@ struct PatchHost {
   std::vector<uint32_t> blob;     // see patch.cpp for the layout
   uint32_t max_blob_words = 0;
   uint32_t max_dofs = 0;          // largest number of unique dofs of one patch
+  // E-vector swizzle: slot s of patch position j sits at unit s*stride + (j ^ swz_row[s] ^ swz_grp[j / NB]), NB = 128 /
+  // unit_bytes (values < NB, so positions stay inside their aligned run of NB: the element side remains conflict-free)
+  std::vector<uint8_t> swz_row, swz_grp;
   std::vector<uint32_t> shared_lines;  // 128-byte lines of the vector holding a unit touched by more than one patch (RED-added)
 };
 int build_patches(int nd, int64_t n_elem, int FE, int stride, int unit_bytes, int64_t n_ext, const double *centroid,
@@ -94,6 +97,7 @@ struct PatchSet {  // device copy
   uint32_t *d_blob_off = nullptr, *d_blob = nullptr;
   int64_t blob_words = 0;
   uint32_t max_blob_words = 0, max_dofs = 0;
+  uint8_t swz_row[27] = {0}, swz_grp[16] = {0};
   uint32_t *d_shared = nullptr;  // 128-byte lines holding RED-added pairs: the only part of y that must be zero before an apply
   int64_t n_shared = 0;
 };

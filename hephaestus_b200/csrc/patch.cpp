@@ -126,7 +126,6 @@ int build_patches(int nd, int64_t n_elem, int FE, int stride, int unit_bytes, in
   const int per = FE * nd;
   std::vector<std::vector<uint32_t>> udof((size_t)n_patch);     // unique dofs (ascending)
   std::vector<std::vector<uint16_t>> ustart((size_t)n_patch);   // U+1
-  std::vector<std::vector<uint16_t>> uslots((size_t)n_patch);   // E byte offsets, grouped by dof
   std::vector<std::vector<uint16_t>> usj((size_t)n_patch);      // s*FE + j | flags, same grouping
   parallel_for(n_patch, [&](int64_t k) {
     std::vector<Ent> ent;
@@ -143,13 +142,10 @@ int build_patches(int nd, int64_t n_elem, int FE, int stride, int unit_bytes, in
     std::sort(ent.begin(), ent.end(), [](const Ent &a, const Ent &b) { return a.dof < b.dof || (a.dof == b.dof && a.slot < b.slot); });
     auto &ud = udof[(size_t)k];
     auto &us = ustart[(size_t)k];
-    auto &sl = uslots[(size_t)k];
     auto &sj = usj[(size_t)k];
-    sl.resize(ent.size());
     sj.resize(ent.size());
     for (size_t i = 0; i < ent.size(); i++) {
       if (i == 0 || ent[i].dof != ent[i - 1].dof) { ud.push_back(ent[i].dof); us.push_back((uint16_t)i); }
-      sl[i] = ent[i].slot;
       sj[i] = ent[i].sj;
     }
     us.push_back((uint16_t)ent.size());
@@ -201,43 +197,13 @@ int build_patches(int nd, int64_t n_elem, int FE, int stride, int unit_bytes, in
     out.max_blob_words = std::max(out.max_blob_words, w);
     out.max_dofs = std::max(out.max_dofs, (uint32_t)ud.size());
   }
-  out.blob.assign((size_t)out.blob_off[(size_t)n_patch] * 4, 0);
-  parallel_for(n_patch, [&](int64_t k) {
+  // position -> index into ud, for patch k (n1 / n2: sizes of the 1- and 2-slot classes)
+  auto make_order = [&](int64_t k, uint32_t n1, uint32_t n2, std::vector<uint32_t> &order) {
     const auto &ud = udof[(size_t)k];
     const auto &us = ustart[(size_t)k];
-    const auto &sl = uslots[(size_t)k];
     const auto &sj = usj[(size_t)k];
-    uint32_t *B = out.blob.data() + (size_t)out.blob_off[(size_t)k] * 4;
-    // group sizes: [width][private|shared]
-    uint32_t cnt[3][2] = {{0, 0}, {0, 0}, {0, 0}}, nov = 0;
-    for (size_t i = 0; i < ud.size(); i++) {
-      const int ns = us[i + 1] - us[i];
-      cnt[width_of(ns)][multi[ud[i]] ? 1 : 0]++;
-      if (ns > 4) nov += ns - 4;
-    }
-    const uint32_t U = (uint32_t)ud.size(), n1 = cnt[0][0] + cnt[0][1], n2 = cnt[1][0] + cnt[1][1], n4 = cnt[2][0] + cnt[2][1];
-    const uint32_t o16 = PatchHost::HDR + align4(U), o32 = o16 + align4((n1 + 1) / 2), o64 = o32 + align4(n2), oov = o64 + align4(2 * n4);
-    const uint32_t olx = oov + align4(nov);
-    uint32_t n_real = 0;
-    for (int j = 0; j < FE; j++) n_real += out.perm[(size_t)k * FE + j] >= 0;
-    B[0] = U; B[1] = n1; B[2] = n2; B[3] = n4; B[4] = cnt[0][0]; B[5] = cnt[1][0]; B[6] = cnt[2][0]; B[7] = nov;
-    B[8] = o16; B[9] = o32; B[10] = o64; B[11] = oov; B[12] = olx; B[13] = n_real;
-    uint32_t *pd = B + PatchHost::HDR;
-    uint16_t *p16 = (uint16_t *)(B + o16);
-    uint32_t *p32 = B + o32;
-    uint64_t *p64 = (uint64_t *)(B + o64);
-    uint32_t *po = B + oov;
-    uint16_t *plx = (uint16_t *)(B + olx);
-    // order inside each width class: ascending global index (consecutive lanes gather / store
-    // consecutive addresses); private and shared units are told apart by the PATCH_SHARED bit of the
-    // dof word.  The position of a unit in this order is also its place in the staging vector Xs, so
-    // its shared-memory bank on the element side (the pull through lidx) is position mod NB, NB =
-    // 128 / unit_bytes lanes being served per wavefront.  Sorted order makes the pull 4.4-way bank
-    // conflicted on structured meshes (strided dof numbering), so inside every aligned run of NB
-    // positions the units are PERMUTED to spread, for each (slot, NB consecutive elements) access
-    // group, the units it reads over distinct banks.  A warp of the dof side still touches the same
-    // 32 units, i.e. the same global sectors.
-    std::vector<uint32_t> order;  // position -> index into ud
+    const uint32_t U = (uint32_t)ud.size();
+    order.clear();
     order.reserve(U);
     for (int w = 0; w < 3; w++)
       for (size_t i = 0; i < ud.size(); i++)
@@ -292,6 +258,105 @@ int build_patches(int nd, int64_t n_elem, int FE, int stride, int unit_bytes, in
           }
       }
     }
+  };
+  auto class_sizes = [&](int64_t k, uint32_t *n) {
+    const auto &us = ustart[(size_t)k];
+    n[0] = n[1] = n[2] = 0;
+    for (size_t i = 0; i + 1 < us.size(); i++) n[width_of(us[i + 1] - us[i])]++;
+  };
+  // ---- swizzle of the E-vector positions (see PatchHost::swz_row): coordinate descent on the bank conflicts of the
+  // dof side's slot reads -- lanes = NB consecutive units of a width class, one read per slot rank -- over a sample
+  // of patches.  Structured meshes number dofs in strides that make neighbouring units hit the same bank (2.8
+  // wavefronts per read measured); one global swizzle removes about half of the excess.
+  {
+    const int NB = 128 / unit_bytes, NG = (FE + NB - 1) / NB;
+    out.swz_row.assign((size_t)nd, 0);
+    out.swz_grp.assign((size_t)NG, 0);
+    struct Acc { uint16_t s, j; };
+    std::vector<std::vector<Acc>> wins;  // one entry per (window, slot rank): the slots read together
+    const int64_t n_sample = std::min<int64_t>(n_patch, 48);
+    std::vector<uint32_t> order;
+    for (int64_t q = 0; q < n_sample; q++) {
+      const int64_t k = q * n_patch / n_sample;
+      const auto &us = ustart[(size_t)k];
+      const auto &sj = usj[(size_t)k];
+      uint32_t n[3];
+      class_sizes(k, n);
+      make_order(k, n[0], n[1], order);
+      const uint32_t base[4] = {0, n[0], n[0] + n[1], n[0] + n[1] + n[2]};
+      for (int w = 0; w < 3; w++)
+        for (uint32_t p0 = base[w]; p0 < base[w + 1]; p0 += NB)
+          for (int kk = 0; kk < (w == 0 ? 1 : (w == 1 ? 2 : 4)); kk++) {
+            std::vector<Acc> acc;
+            for (uint32_t ul = p0; ul < std::min(base[w + 1], p0 + NB); ul++) {
+              const uint32_t i = order[ul];
+              if (us[i] + kk < us[i + 1]) { const int v = sj[us[i] + kk] & 0x1fff; acc.push_back({(uint16_t)(v / FE), (uint16_t)(v % FE)}); }
+            }
+            if (acc.size() > 1) wins.push_back(acc);
+          }
+    }
+    auto cost = [&]() {
+      int64_t c = 0;
+      for (const auto &acc : wins) {
+        int cnt[16] = {0}, mx = 0;
+        for (const Acc &e : acc) {
+          const int pos = e.j ^ out.swz_row[e.s] ^ out.swz_grp[e.j / NB];
+          mx = std::max(mx, ++cnt[(e.s * stride + pos) % NB]);
+        }
+        c += mx;
+      }
+      return c;
+    };
+    int64_t best = cost();
+    for (int sweep = 0; sweep < 3; sweep++)
+      for (int var = 0; var < nd + NG; var++) {
+        uint8_t &x = var < nd ? out.swz_row[(size_t)var] : out.swz_grp[(size_t)(var - nd)];
+        uint8_t keep = x;
+        for (int v = 0; v < NB; v++) {
+          x = (uint8_t)v;
+          const int64_t c = cost();
+          if (c < best) { best = c; keep = (uint8_t)v; }
+        }
+        x = keep;
+      }
+  }
+  out.blob.assign((size_t)out.blob_off[(size_t)n_patch] * 4, 0);
+  parallel_for(n_patch, [&](int64_t k) {
+    const auto &ud = udof[(size_t)k];
+    const auto &us = ustart[(size_t)k];
+    const auto &sj = usj[(size_t)k];
+    uint32_t *B = out.blob.data() + (size_t)out.blob_off[(size_t)k] * 4;
+    // group sizes: [width][private|shared]
+    uint32_t cnt[3][2] = {{0, 0}, {0, 0}, {0, 0}}, nov = 0;
+    for (size_t i = 0; i < ud.size(); i++) {
+      const int ns = us[i + 1] - us[i];
+      cnt[width_of(ns)][multi[ud[i]] ? 1 : 0]++;
+      if (ns > 4) nov += ns - 4;
+    }
+    const uint32_t U = (uint32_t)ud.size(), n1 = cnt[0][0] + cnt[0][1], n2 = cnt[1][0] + cnt[1][1], n4 = cnt[2][0] + cnt[2][1];
+    const uint32_t o16 = PatchHost::HDR + align4(U), o32 = o16 + align4((n1 + 1) / 2), o64 = o32 + align4(n2), oov = o64 + align4(2 * n4);
+    const uint32_t olx = oov + align4(nov);
+    uint32_t n_real = 0;
+    for (int j = 0; j < FE; j++) n_real += out.perm[(size_t)k * FE + j] >= 0;
+    B[0] = U; B[1] = n1; B[2] = n2; B[3] = n4; B[4] = cnt[0][0]; B[5] = cnt[1][0]; B[6] = cnt[2][0]; B[7] = nov;
+    B[8] = o16; B[9] = o32; B[10] = o64; B[11] = oov; B[12] = olx; B[13] = n_real;
+    uint32_t *pd = B + PatchHost::HDR;
+    uint16_t *p16 = (uint16_t *)(B + o16);
+    uint32_t *p32 = B + o32;
+    uint64_t *p64 = (uint64_t *)(B + o64);
+    uint32_t *po = B + oov;
+    uint16_t *plx = (uint16_t *)(B + olx);
+    // order inside each width class: ascending global index (consecutive lanes gather / store
+    // consecutive addresses); private and shared units are told apart by the PATCH_SHARED bit of the
+    // dof word.  The position of a unit in this order is also its place in the staging vector Xs, so
+    // its shared-memory bank on the element side (the pull through lidx) is position mod NB, NB =
+    // 128 / unit_bytes lanes being served per wavefront.  Sorted order makes the pull 4.4-way bank
+    // conflicted on structured meshes (strided dof numbering), so inside every aligned run of NB
+    // positions the units are PERMUTED to spread, for each (slot, NB consecutive elements) access
+    // group, the units it reads over distinct banks.  A warp of the dof side still touches the same
+    // 32 units, i.e. the same global sectors.
+    std::vector<uint32_t> order;  // position -> index into ud
+    make_order(k, n1, n2, order);
     const uint32_t base[3] = {0, n1, n1 + n2};
     for (uint32_t ul = 0; ul < U; ul++) {
       const uint32_t i = order[ul];
@@ -299,13 +364,17 @@ int build_patches(int nd, int64_t n_elem, int FE, int stride, int unit_bytes, in
       const uint32_t r = ul - base[w];  // index inside the width section
       pd[ul] = ud[i] | (multi[ud[i]] ? PATCH_SHARED : 0u);
       for (int j = 0; j < ns; j++) plx[sj[us[i] + j] & 0x1fffu] = (uint16_t)(ul | (sj[us[i] + j] & 0xe000u));
-      if (w == 0) p16[r] = sl[us[i]];
-      else if (w == 1) p32[r] = (uint32_t)sl[us[i]] | ((uint32_t)sl[us[i] + 1] << 16);
+      auto off = [&](int q) {  // byte offset of the slot in the (swizzled) E-vector
+        const int v = sj[q] & 0x1fff, ss = v / FE, jj = v % FE;
+        return (uint32_t)((ss * stride + (jj ^ out.swz_row[(size_t)ss] ^ out.swz_grp[(size_t)(jj / (128 / unit_bytes))])) * unit_bytes);
+      };
+      if (w == 0) p16[r] = (uint16_t)off(us[i]);
+      else if (w == 1) p32[r] = off(us[i]) | (off(us[i] + 1) << 16);
       else {
         uint64_t v = ~0ULL;
         for (int j = 0; j < ns; j++) {
-          if (j < 4) v = (v & ~(0xffffULL << (16 * j))) | ((uint64_t)sl[us[i] + j] << (16 * j));
-          else *po++ = (ul << 16) | sl[us[i] + j];
+          if (j < 4) v = (v & ~(0xffffULL << (16 * j))) | ((uint64_t)off(us[i] + j) << (16 * j));
+          else *po++ = (ul << 16) | off(us[i] + j);
         }
         p64[r] = v;
       }
@@ -336,6 +405,11 @@ int64_t hcurl_host_patches_count(const hcurl_host_patches *p) { return p->h.n_pa
 int64_t hcurl_host_patches_blob_words(const hcurl_host_patches *p) { return (int64_t)p->h.blob.size(); }
 int64_t hcurl_host_patches_max_blob_words(const hcurl_host_patches *p) { return (int64_t)p->h.max_blob_words; }
 int64_t hcurl_host_patches_max_dofs(const hcurl_host_patches *p) { return (int64_t)p->h.max_dofs; }
+int hcurl_host_patches_swizzle(const hcurl_host_patches *p, uint8_t *row, uint8_t *grp) {
+  memcpy(row, p->h.swz_row.data(), p->h.swz_row.size());
+  memcpy(grp, p->h.swz_grp.data(), p->h.swz_grp.size());
+  return 0;
+}
 int hcurl_host_patches_copy(const hcurl_host_patches *p, int32_t *perm, uint32_t *blob_off, uint32_t *blob) {
   const hcurl::PatchHost &h = p->h;
   if (perm) memcpy(perm, h.perm.data(), sizeof(int32_t) * h.perm.size());

@@ -203,7 +203,10 @@ class HephGpuOperator:
         DeviceVector in -> DeviceVector out (device-resident path)."""
         if isinstance(x, DeviceVector):
             assert isinstance(y, DeviceVector)
-            L.check(L.lib().hcurl_op_apply(self.h, C.c_void_p(x.ptr), C.c_void_p(y.ptr), L.DEVICE), "hcurl_op_apply")
+            # vectors with room for the ghosts are used in place (no staging copies on ranks that hold ghosts)
+            n_ext = int(L.lib().hcurl_space_ext_size(self.space.h))
+            where = L.DEVICE_EXT if min(x.n, y.n) >= n_ext else L.DEVICE
+            L.check(L.lib().hcurl_op_apply(self.h, C.c_void_p(x.ptr), C.c_void_p(y.ptr), where), "hcurl_op_apply")
             return y
         x = L.as_f64(x)
         if x.size != self.space.n_tdof:

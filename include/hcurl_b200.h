@@ -45,8 +45,12 @@ enum { HCURL_GEOM_HEX = 0, HCURL_GEOM_TET = 1 };
 enum { HCURL_COEF_PER_ELEM = 0, HCURL_COEF_PER_QPT = 1 };
 /* preconditioners: HCURL_PC_JACOBI reproduces mfem::HypreDiagScale */
 enum { HCURL_PC_NONE = 0, HCURL_PC_JACOBI = 1 };
-/* where a vector argument lives */
-enum { HCURL_HOST = 0, HCURL_DEVICE = 1 };
+/* where a vector argument lives.  HCURL_DEVICE_EXT (apply entry points only): device vectors with room for
+ * hcurl_space_ext_size() entries -- the owned true dofs followed by the rank's ghost dofs -- which the
+ * library uses in place (the ghost tail of x is overwritten by the shared-dof exchange, that of y is
+ * scratch); on one GPU it equals HCURL_DEVICE.  It saves the two device copies per apply that
+ * HCURL_DEVICE needs on ranks that hold ghosts. */
+enum { HCURL_HOST = 0, HCURL_DEVICE = 1, HCURL_DEVICE_EXT = 2 };
 
 /* library / build info; never touches the GPU */
 const char *hcurl_version(void);
@@ -118,6 +122,8 @@ hcurl_space *hcurl_space_create(hcurl_ctx *ctx, int geom, int geom_order, int or
                                 const int32_t *nbr_rank, const int32_t *own_off, const int32_t *own_ldof,
                                 const int32_t *ghost_off, const int32_t *ghost_ldof,
                                 const int8_t *ghost_sign);
+/* length of the extended vector [owned true dofs | ghosts] of this rank */
+int64_t hcurl_space_ext_size(const hcurl_space *sp);
 void hcurl_space_destroy(hcurl_space *sp);
 int32_t hcurl_space_ndof_local(const hcurl_space *sp);
 int32_t hcurl_space_ndof_true(const hcurl_space *sp);
@@ -229,7 +235,8 @@ int hcurl_dot(hcurl_ctx *ctx, const double *a_dev, const double *b_dev, int64_t 
  *             order-2 hex kernel works on pairs, see hephaestus_b200/csrc/hex_patch.cu)
  *  slot_code  [n_elem][nd]: unit index (bits 0..28) | orientation flags (bits 29..31; for 8-byte units
  *             bit 31 = sign flip) of each element slot
- *  slot_stride  >= elems_per_patch: E-vector index (in units) of (slot s, patch position j) = s*slot_stride + j
+ *  slot_stride  >= elems_per_patch: E-vector index (in units) of (slot s, patch position j) = s*slot_stride + j',
+ *             j' = j up to the bank swizzle reported by hcurl_host_patches_swizzle()
  *  outputs    perm [n_patch*epp] element at each patch position (-1 padding);
  *             blob_off [n_patch+1] start of each patch blob in 16-byte units; blob: per patch a
  *             16-word header, the unit list, the 16/32/64-bit slot-entry sections (dof side) and the
@@ -244,6 +251,9 @@ int64_t hcurl_host_patches_blob_words(const hcurl_host_patches *p);
 int64_t hcurl_host_patches_max_blob_words(const hcurl_host_patches *p);
 /* largest number of unique dofs in one patch (sizes the shared-memory x staging vector) */
 int64_t hcurl_host_patches_max_dofs(const hcurl_host_patches *p);
+/* E-vector swizzle chosen by the builder: (slot s, position j) sits at unit s*slot_stride + (j ^ row[s] ^ grp[j / NB]),
+ * NB = 128 / unit_bytes; row has nd entries, grp ceil(elems_per_patch / NB) */
+int hcurl_host_patches_swizzle(const hcurl_host_patches *p, uint8_t *row, uint8_t *grp);
 int hcurl_host_patches_copy(const hcurl_host_patches *p, int32_t *perm, uint32_t *blob_off, uint32_t *blob);
 
 /* FP64 FMA micro-benchmark used for the roofline co-bound:

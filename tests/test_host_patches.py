@@ -29,6 +29,11 @@ def build(space, fe, slot_code, centroid, stride=None, unit=8, n_units=None):
     L.check(lib.hcurl_host_patches_copy(h, L.ptr(perm), L.ptr(off), L.ptr(blob)), "copy")
     assert lib.hcurl_host_patches_max_blob_words(h) == int(np.diff(off.astype(np.int64)).max()) * 4
     assert lib.hcurl_host_patches_max_dofs(h) == max(int(blob[int(o) * 4]) for o in off[:-1])
+    nb = 128 // unit
+    row, grp = np.zeros(nd, np.uint8), np.zeros((fe + nb - 1) // nb, np.uint8)
+    L.check(lib.hcurl_host_patches_swizzle(h, L.ptr(row), L.ptr(grp)), "swizzle")
+    assert row.max(initial=0) < nb and grp.max(initial=0) < nb
+    SWIZZLE.update(row=row.astype(np.int64), grp=grp.astype(np.int64), nb=nb)
     lib.hcurl_host_patches_destroy(h)
     return perm, off.astype(np.int64), blob, stride
 
@@ -62,9 +67,12 @@ def decode_patch(k, off, blob, nd=None, fe=None):
     return dof, groups, ov, lidx, n_real
 
 
+SWIZZLE = {}   # bank swizzle of the most recent build(): row[s], grp[j // nb]
+
+
 def e_index(s, j, st):
-    """E-vector position (in units) of slot s of patch position j."""
-    return s * st + j
+    """E-vector position (in units) of slot s of patch position j (swizzled inside aligned runs of nb positions)."""
+    return s * st + (j ^ SWIZZLE["row"][s] ^ SWIZZLE["grp"][j // SWIZZLE["nb"]])
 
 
 def make(kind, n, p, perturb):
