@@ -57,6 +57,20 @@ def peaks():
     return 6650.0, "fallback"
 
 
+def measured_traffic(order, n, kernel_id):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this command
+    (profiles/r1_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum), or None when no capture exists for
+    the configuration being run."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        for e in json.load(f):
+            if e["order"] == order and e["n_per_edge"] == n and e["kernel"] == kernel_id:
+                return e["dram_bytes_per_launch"]
+    return None
+
+
 def algorithmic_bytes(n_dof, n_elem, nd, ngn=8):
     """SURVEY.md 8d contract: x read + y written once (16 B/DOF) + per element the signed
     int32 map (4 nd), the geometry nodes (8*3*ngn) and alpha, beta (16)."""
@@ -312,7 +326,9 @@ def main():
     achieved = abytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
     fp64 = ctx.fp64_peak_tflops()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_kind": "of " + peak_kind, "kernel": "hex element kernel (order %d)" % p,
+                "traffic": measured_traffic(p, n, op.LastKernel()) if world == 1 and not args.perturbed and args.quad == "fast" else None,
+                "peak_kind": "of " + peak_kind, "kernel": "hex element kernel (order %d; %s)" % (
+                    p, {1: "generic sum-factorised", 2: "element-wise register-blocked", 3: "patch, modal, persistent"}.get(op.LastKernel(), "?")),
                 "kernel_ms": kern_ms, "kernel_launches_timed": kern_n, "algorithmic_bytes_per_launch": abytes,
                 "bytes_per_dof": abytes / n_tdof, "kernel_share_of_step": kern_ms / ms_step if ms_step > 0 else None,
                 "fp64_fma_peak_tflops_measured": fp64}
