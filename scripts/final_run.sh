@@ -1,0 +1,26 @@
+#!/bin/bash
+# Round-end evidence on one B200 (run under gpurun): GPU tests, the bench line, the reference arm, ncu launch list and
+# full capture of the dominant kernel, phase profile, sweep over the other orders.  Outputs under gpurun_out/.
+tag=${1:-r1}
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu_$tag.log 2>&1; tail -3 gpurun_out/pytest_gpu_$tag.log
+timeout 400 python bench.py > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err; tail -c 300 gpurun_out/bench_$tag.err
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$tag.json 2> gpurun_out/bench_ref_$tag.err; tail -c 300 gpurun_out/bench_ref_$tag.err
+BENCH="python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e --pcg-iters 3"
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$tag.csv $BENCH > gpurun_out/launches_$tag.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'hex_patch_modal' -s 3 -c 1 -f -o gpurun_out/prof_$tag $BENCH > gpurun_out/prof_$tag.log 2>&1
+timeout 120 python scripts/phase_profile.py 128 > gpurun_out/phase_$tag.txt 2>&1
+for cfg in "1 255" "3 85" "4 64"; do set -- $cfg; timeout 200 python bench.py --order $1 --n $2 --steps 20 --no-cpu --no-e2e --pcg-iters 10 > gpurun_out/bench_p$1_$tag.json 2>gpurun_out/bench_p$1_$tag.err; done
+timeout 200 python bench.py --perturbed --steps 20 --no-cpu --no-e2e --pcg-iters 10 > gpurun_out/bench_p2pert_$tag.json 2>/dev/null
+timeout 200 python bench.py --quad mfem --steps 20 --no-cpu --no-e2e --pcg-iters 10 > gpurun_out/bench_p2mfem_$tag.json 2>/dev/null
+for f in gpurun_out/bench_$tag.json gpurun_out/bench_p*_$tag.json; do python - "$f" <<'PY'
+import sys, json
+try:
+    d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    print(sys.argv[1], 'order', d['config']['order'], 'GDOF/s %.2f' % d['value'], 'frac %.3f' % d['roofline']['frac'], 'kern_ms %.4f' % d['roofline']['kernel_ms'],
+          'step_ms %.4f' % d['ms_per_step'], 'pcg it/s %.1f' % d['pcg']['iters_per_s'], d['roofline']['kernel'])
+except Exception as e:
+    print(sys.argv[1], 'FAILED', e)
+PY
+done
+cat gpurun_out/bench_ref_$tag.json | tail -1 | cut -c1-400
