@@ -34,6 +34,7 @@ def parse():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--n", type=int, default=int(os.environ.get("HCURL_BENCH_N", "128")), help="hexes per edge of the per-GPU cube")
     ap.add_argument("--order", type=int, default=2)
+    ap.add_argument("--geom", default="hex", choices=["hex", "tet"], help="tet: every hex of the cube split into 6 tets (SURVEY.md 8d, input S2)")
     ap.add_argument("--perturbed", action="store_true", help="trilinearly perturbed mesh variant (general geometry)")
     ap.add_argument("--quad", default="fast", choices=["fast", "mfem"])
     ap.add_argument("--pcg-iters", type=int, default=50)
@@ -75,6 +76,11 @@ def algorithmic_bytes(n_dof, n_elem, nd, ngn=8):
     """SURVEY.md 8d contract: x read + y written once (16 B/DOF) + per element the signed
     int32 map (4 nd), the geometry nodes (8*3*ngn) and alpha, beta (16)."""
     return 16.0 * n_dof + n_elem * (4.0 * nd + 8.0 * 3 * ngn + 16.0)
+
+
+def algorithmic_bytes_tet(n_dof, n_elem, nd):
+    """vectors (16 B/DOF) + per element the packed-symmetric element matrix and the int32 map."""
+    return 16.0 * n_dof + n_elem * (8.0 * nd * (nd + 1) / 2 + 4.0 * nd)
 
 
 class ClockSampler(threading.Thread):
@@ -180,8 +186,8 @@ def run_reference(args, rank, world):
 
 def workload_config(args, n, n_dof, bounded=False):
     return {
-        "workload": "synthetic structured hex cube %d^3 per GPU%s, order-%d Nedelec, K(dt*nu)+M(sigma) apply, %d DOFs%s" % (
-            n, " (trilinearly perturbed)" if args.perturbed else "", args.order, n_dof,
+        "workload": "synthetic structured %s cube %d^3 per GPU%s, order-%d Nedelec, K(dt*nu)+M(sigma) apply, %d DOFs%s" % (
+            "hex" if args.geom == "hex" else "tet (6 tets per hex)", n, " (trilinearly perturbed)" if args.perturbed else "", args.order, n_dof,
             " [bounded CPU sample of the n=%d workload]" % args.n if bounded else ""),
         "mesh": "general unstructured storage (explicit connectivity, coordinates, signed int32 ND map)",
         "order": args.order, "n_per_edge": n,
@@ -224,6 +230,8 @@ def main():
         mesh = fespace.cartesian_hex_mesh(n, n, n)
         if args.perturbed:
             mesh = fespace.perturb_interior(mesh)
+        if args.geom == "tet":
+            mesh = fespace.hex_to_tets(mesh)
         space = fespace.NDSpace(mesh, p)
         gsp = operators.GpuNDSpace(ctx, space)
         ess = space.boundary_dofs()
@@ -242,7 +250,7 @@ def main():
         t = torch.tensor([n_tdof], dtype=torch.int64, device="cuda")
         dist.all_reduce(t)
         n_dof_global = int(t.item())
-    op = operators.HephGpuOperator(ctx, gsp, p + 1 if args.quad == "fast" else 0)
+    op = operators.HephGpuOperator(ctx, gsp, p + 1 if args.quad == "fast" and args.geom == "hex" else 0)
     alpha, beta = coefficients(attr)
     op.SetCoefficients(alpha, beta)
     op.SetEssentialTrueDofs(ess)
@@ -322,12 +330,14 @@ def main():
 
     # ---------------- roofline of the dominant kernel ----------------------------------------
     peak, peak_kind = peaks()
-    abytes = algorithmic_bytes(n_tdof, n_elem_local, nd)
+    abytes = algorithmic_bytes(n_tdof, n_elem_local, nd) if args.geom == "hex" else algorithmic_bytes_tet(n_tdof, n_elem_local, nd)
     achieved = abytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
     fp64 = ctx.fp64_peak_tflops()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": measured_traffic(p, n, op.LastKernel()) if world == 1 and not args.perturbed and args.quad == "fast" else None,
-                "peak_kind": "of " + peak_kind, "kernel": "hex element kernel (order %d; %s)" % (
+                "peak_kind": "of " + peak_kind,
+                "kernel": "tet batched packed-symmetric element-matrix kernel (order %d)" % p if args.geom == "tet" else
+                "hex element kernel (order %d; %s)" % (
                     p, {1: "generic sum-factorised", 2: "element-wise register-blocked", 3: "patch, modal, persistent"}.get(op.LastKernel(), "?")),
                 "kernel_ms": kern_ms, "kernel_launches_timed": kern_n, "algorithmic_bytes_per_launch": abytes,
                 "bytes_per_dof": abytes / n_tdof, "kernel_share_of_step": kern_ms / ms_step if ms_step > 0 else None,
