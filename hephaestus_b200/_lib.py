@@ -74,9 +74,10 @@ SIGNATURES = {
     "hcurl_host_free_pinned": (None, [_P]),
     "hcurl_dot": (C.c_int, [_P, _P, _P, C.c_int64, C.POINTER(C.c_double)]),
     "hcurl_fp64_peak_tflops": (C.c_double, [_P]),
-    "hcurl_host_patches_create": (_P, [C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int64, _P, _P]),
+    "hcurl_host_patches_create": (_P, [C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int64, _P, _P, _P]),
     "hcurl_host_patches_destroy": (None, [_P]),
     "hcurl_host_patches_count": (C.c_int64, [_P]),
+    "hcurl_host_patches_boundary_count": (C.c_int64, [_P]),
     "hcurl_host_patches_blob_words": (C.c_int64, [_P]),
     "hcurl_host_patches_max_blob_words": (C.c_int64, [_P]),
     "hcurl_host_patches_max_dofs": (C.c_int64, [_P]),

@@ -115,22 +115,23 @@ __global__ void sign_kernel(const int32_t n, const int8_t *__restrict__ sgn, dou
 }
 
 // x_ext: owner -> ghosts
-int exchange_broadcast(hcurl_space *sp, double *d_ext) {
+int exchange_broadcast(hcurl_space *sp, double *d_ext, cudaStream_t stream) {
   hcurl_ctx *ctx = sp->ctx;
   if (sp->n_nbr == 0) return 0;
+  const cudaStream_t st = stream ? stream : ctx->stream;
   Nccl *N = nccl();
   const int32_t n_own = sp->own_off[sp->n_nbr];
   if (n_own > 0) ctx->launches++;
-  if (n_own > 0) pack_kernel<<<(n_own + 255) / 256, 256, 0, ctx->stream>>>(n_own, sp->d_own_idx, d_ext, sp->d_sendbuf);
+  if (n_own > 0) pack_kernel<<<(n_own + 255) / 256, 256, 0, st>>>(n_own, sp->d_own_idx, d_ext, sp->d_sendbuf);
   HC_NCCL(N->GroupStart());
   for (int r = 0; r < sp->n_nbr; r++) {
     const int32_t ns = sp->own_off[r + 1] - sp->own_off[r], ng = sp->ghost_off[r + 1] - sp->ghost_off[r];
-    if (ns > 0) HC_NCCL(N->Send(sp->d_sendbuf + sp->own_off[r], (size_t)ns, NCCL_FLOAT64, sp->nbr_rank[r], ctx->comm, ctx->stream));
-    if (ng > 0) HC_NCCL(N->Recv(d_ext + sp->n_tdof + sp->ghost_off[r], (size_t)ng, NCCL_FLOAT64, sp->nbr_rank[r], ctx->comm, ctx->stream));
+    if (ns > 0) HC_NCCL(N->Send(sp->d_sendbuf + sp->own_off[r], (size_t)ns, NCCL_FLOAT64, sp->nbr_rank[r], ctx->comm, st));
+    if (ng > 0) HC_NCCL(N->Recv(d_ext + sp->n_tdof + sp->ghost_off[r], (size_t)ng, NCCL_FLOAT64, sp->nbr_rank[r], ctx->comm, st));
   }
   HC_NCCL(N->GroupEnd());
   if (sp->d_ghost_sign && sp->n_ghost > 0)
-    sign_kernel<<<(sp->n_ghost + 255) / 256, 256, 0, ctx->stream>>>(sp->n_ghost, sp->d_ghost_sign, d_ext + sp->n_tdof);
+    sign_kernel<<<(sp->n_ghost + 255) / 256, 256, 0, st>>>(sp->n_ghost, sp->d_ghost_sign, d_ext + sp->n_tdof);
   HC_CUDA(cudaGetLastError());
   return 0;
 }
@@ -138,22 +139,23 @@ int exchange_broadcast(hcurl_space *sp, double *d_ext) {
 // y_ext: ghosts -> owner (sum).  signed_values: the entries are components of a vector in the local orientation of
 // each dof (flip the ghosts that are oriented against their owner); false for quantities that do not change sign with
 // the orientation (the operator diagonal).
-int exchange_reduce(hcurl_space *sp, double *d_ext, bool signed_values) {
+int exchange_reduce(hcurl_space *sp, double *d_ext, bool signed_values, cudaStream_t stream) {
   hcurl_ctx *ctx = sp->ctx;
   if (sp->n_nbr == 0) return 0;
+  const cudaStream_t st = stream ? stream : ctx->stream;
   Nccl *N = nccl();
   if (signed_values && sp->d_ghost_sign && sp->n_ghost > 0)
-    sign_kernel<<<(sp->n_ghost + 255) / 256, 256, 0, ctx->stream>>>(sp->n_ghost, sp->d_ghost_sign, d_ext + sp->n_tdof);
+    sign_kernel<<<(sp->n_ghost + 255) / 256, 256, 0, st>>>(sp->n_ghost, sp->d_ghost_sign, d_ext + sp->n_tdof);
   HC_NCCL(N->GroupStart());
   for (int r = 0; r < sp->n_nbr; r++) {
     const int32_t ns = sp->own_off[r + 1] - sp->own_off[r], ng = sp->ghost_off[r + 1] - sp->ghost_off[r];
-    if (ng > 0) HC_NCCL(N->Send(d_ext + sp->n_tdof + sp->ghost_off[r], (size_t)ng, NCCL_FLOAT64, sp->nbr_rank[r], ctx->comm, ctx->stream));
-    if (ns > 0) HC_NCCL(N->Recv(sp->d_recvbuf + sp->own_off[r], (size_t)ns, NCCL_FLOAT64, sp->nbr_rank[r], ctx->comm, ctx->stream));
+    if (ng > 0) HC_NCCL(N->Send(d_ext + sp->n_tdof + sp->ghost_off[r], (size_t)ng, NCCL_FLOAT64, sp->nbr_rank[r], ctx->comm, st));
+    if (ns > 0) HC_NCCL(N->Recv(sp->d_recvbuf + sp->own_off[r], (size_t)ns, NCCL_FLOAT64, sp->nbr_rank[r], ctx->comm, st));
   }
   HC_NCCL(N->GroupEnd());
   const int32_t n_own = sp->own_off[sp->n_nbr];
   if (n_own > 0) ctx->launches++;
-  if (n_own > 0) unpack_add_kernel<<<(n_own + 255) / 256, 256, 0, ctx->stream>>>(n_own, sp->d_own_idx, sp->d_recvbuf, d_ext);
+  if (n_own > 0) unpack_add_kernel<<<(n_own + 255) / 256, 256, 0, st>>>(n_own, sp->d_own_idx, sp->d_recvbuf, d_ext);
   HC_CUDA(cudaGetLastError());
   return 0;
 }

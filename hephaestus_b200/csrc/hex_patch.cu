@@ -171,7 +171,9 @@ __device__ __forceinline__ void modal_op(const double *Am, const double *Bm, con
 }
 
 struct PatchArgs {
-  int64_t n_patch;
+  int64_t n_patch;           // patches [k_begin, n_patch) are processed by this launch
+  int64_t k_begin;
+  int dot_add;               // fused dot product: add to *dot_out instead of storing (second / third launch of an apply)
   const uint32_t *blob_off;  // [n_patch+1] in 16-byte units
   const uint32_t *blob;      // patch blobs (patch.cpp)
   const double *edata;       // [n_patch][12][FE] affine geometry factors in patch order
@@ -276,7 +278,7 @@ hex_patch_modal_p2_kernel(const PatchArgs a) {
   long long t_prev = PROF ? clock64() : 0;
   unsigned long long prof_acc[6] = {0, 0, 0, 0, 0, 0};
   double dacc = 0.0;  // DOT: my share of x^T A x, summed in modal space (x_e^T A_e x_e = Am^T Yh)
-  const int64_t k0 = blockIdx.x, kstep = gridDim.x;
+  const int64_t k0 = a.k_begin + blockIdx.x, kstep = gridDim.x;
   const int n_it = (int)((a.n_patch - k0 + kstep - 1) / kstep);
   // component c of patch element el, in the rotated frame (c, c+1, c+2)
   const int c = tid / FE, el = tid - c * FE;
@@ -524,7 +526,7 @@ hex_patch_modal_p2_kernel(const PatchArgs a) {
       double v = 0.0;
       for (int i = tid; i < (int)gridDim.x; i += 32) v += ((volatile double *)a.dot_partial)[i];
       for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-      if (tid == 0) *a.dot_out = v;
+      if (tid == 0) *a.dot_out = a.dot_add ? *a.dot_out + v : v;
     }
   }
 }
@@ -669,11 +671,18 @@ int hex_patch_build(hcurl_space *sp, const double *elem_xyz, const int32_t *elem
       cen[(size_t)e * 3 + d] = 0.125 * c;
     }
   }
+  // pairs that take part in the inter-rank exchange: ghosts, and owned pairs other ranks hold as ghosts
+  std::vector<uint8_t> xch;
+  if (sp->n_nbr > 0) {
+    xch.assign((size_t)(sp->n_ext() / 2), 0);
+    for (int64_t u = sp->n_tdof / 2; u < sp->n_ext() / 2; u++) xch[(size_t)u] = 1;
+    for (int32_t d : sp->own_ext) xch[(size_t)(d / 2)] = 1;
+  }
   PatchHost H;
-  if (build_patches(np, ne, FE, FE + 1, 16, sp->n_ext() / 2, cen.data(), code.data(), H)) return 1;
+  if (build_patches(np, ne, FE, FE + 1, 16, sp->n_ext() / 2, cen.data(), code.data(), xch.empty() ? nullptr : xch.data(), H)) return 1;
   HC_CUDA(cudaSetDevice(sp->ctx->device));
   PatchSet &P = sp->patch;
-  P.FE = FE; P.stride = H.stride; P.n_patch = H.n_patch;
+  P.FE = FE; P.stride = H.stride; P.n_patch = H.n_patch; P.n_boundary = H.n_boundary;
   P.blob_words = (int64_t)H.blob.size(); P.max_blob_words = H.max_blob_words; P.max_dofs = H.max_dofs;
   for (int i = 0; i < 27; i++) P.swz_row[i] = H.swz_row[(size_t)i];
   for (size_t i = 0; i < 16; i++) P.swz_grp[i] = i < H.swz_grp.size() ? H.swz_grp[i] : 0;
@@ -737,7 +746,8 @@ static int launch_fe(const PatchArgs &a, int64_t n_patch, int sm_count, size_t s
   return 0;
 }
 
-int hex_patch_launch(hcurl_op *op, bool constrained, const double *d_x, double *d_y, double scale, bool accumulate, double *d_dot) {
+int hex_patch_launch(hcurl_op *op, bool constrained, const double *d_x, double *d_y, double scale, bool accumulate, double *d_dot,
+                     int64_t k_begin, int64_t k_end, bool dot_add) {
   hcurl_space *sp = op->sp;
   hcurl_ctx *ctx = op->ctx;
   PatchSet &P = sp->patch;
@@ -751,7 +761,8 @@ int hex_patch_launch(hcurl_op *op, bool constrained, const double *d_x, double *
     op->edataP_valid = true;
   }
   PatchArgs a;
-  a.n_patch = P.n_patch; a.blob_off = P.d_blob_off;
+  a.n_patch = k_end < 0 ? P.n_patch : k_end; a.k_begin = k_begin; a.dot_add = dot_add ? 1 : 0; a.blob_off = P.d_blob_off;
+  if (a.n_patch <= a.k_begin) return 0;
   a.blob = (constrained && op->d_blob_ess) ? op->d_blob_ess : P.d_blob;
   a.blob_cap_bytes = (P.max_blob_words * 4 + 15u) & ~15u;
   a.xs_cap_bytes = P.max_dofs * 16u;
@@ -765,9 +776,10 @@ int hex_patch_launch(hcurl_op *op, bool constrained, const double *d_x, double *
   int rc = 1;
   // 168 registers per thread: 2 CTAs of 192 threads per SM.  (A 3-CTA variant capped at 112 / 104 registers spilled
   // and ran 45 % slower, profiles/README.md.)
-  if (P.FE == 32) rc = launch_fe<32, 4>(a, P.n_patch, ctx->sm_count, smem, accumulate, ctx->stream);
-  else if (P.FE == 64) rc = launch_fe<64, 2>(a, P.n_patch, ctx->sm_count, smem, accumulate, ctx->stream);
-  else if (P.FE == 128) rc = launch_fe<128, 1>(a, P.n_patch, ctx->sm_count, smem, accumulate, ctx->stream);
+  const int64_t n_run = a.n_patch - a.k_begin;
+  if (P.FE == 32) rc = launch_fe<32, 4>(a, n_run, ctx->sm_count, smem, accumulate, ctx->stream);
+  else if (P.FE == 64) rc = launch_fe<64, 2>(a, n_run, ctx->sm_count, smem, accumulate, ctx->stream);
+  else if (P.FE == 128) rc = launch_fe<128, 1>(a, n_run, ctx->sm_count, smem, accumulate, ctx->stream);
   if (rc) return rc;
   HC_CUDA(cudaGetLastError());
   ctx->launches++;

@@ -73,6 +73,7 @@ void tri_face_transform(int p, const int32_t *local_verts, const int32_t *base_v
 struct PatchHost {
   int FE = 0, stride = 0, nd = 0;
   int64_t n_patch = 0;
+  int64_t n_boundary = 0;         // patches [0, n_boundary) touch units of the inter-rank exchange
   static constexpr int HDR = 16;  // header words per patch blob
   std::vector<int32_t> perm;      // [n_patch*FE] element at each patch position, -1 = padding
   std::vector<uint32_t> blob_off; // [n_patch+1] start of each patch blob in 16-byte units
@@ -85,13 +86,13 @@ struct PatchHost {
   std::vector<uint32_t> shared_lines;  // 128-byte lines of the vector holding a unit touched by more than one patch (RED-added)
 };
 int build_patches(int nd, int64_t n_elem, int FE, int stride, int unit_bytes, int64_t n_ext, const double *centroid,
-                  const uint32_t *slot_code, PatchHost &out);
+                  const uint32_t *slot_code, const uint8_t *exchange_units, PatchHost &out);
 // slot s of the rotated per-component layout (hex_patch.cu) -> standard tensor index
 int hex_rot_slot_to_tensor(int p, int slot);
 
 struct PatchSet {  // device copy
   int FE = 0;
-  int64_t n_patch = 0, n_pd = 0;
+  int64_t n_patch = 0, n_pd = 0, n_boundary = 0;
   int32_t *d_perm = nullptr;
   int stride = 0;
   uint32_t *d_blob_off = nullptr, *d_blob = nullptr;
@@ -120,6 +121,7 @@ struct hcurl_ctx {
   int n_partial = 0;
   int sm_count = 148;
   cudaEvent_t mark[2] = {nullptr, nullptr};
+  cudaEvent_t ev_x[4] = {nullptr, nullptr, nullptr, nullptr};  // main <-> comm stream hand-offs of an overlapped apply
   int64_t launches = 0;
 };
 
@@ -145,6 +147,7 @@ struct hcurl_space {
   int8_t *d_ghost_sign = nullptr;           // [n_ghost] or null
   double *d_sendbuf = nullptr, *d_recvbuf = nullptr;  // size own_off.back()
   std::vector<int32_t> ldof_to_ext;  // host copy (for essential dofs etc.)
+  std::vector<int32_t> own_ext;      // host copy of d_own_idx
   // fast order-2 path (hex_fast.cu): dof-major map / vertices, affine classification
   bool fast_ready = false, all_affine = false;
   uint32_t *d_mapT = nullptr;
@@ -214,8 +217,9 @@ bool hex_patch_eligible(const hcurl_op *op);
 // y (+)= scale * A x through the patch path; when !accumulate every dof of y is written
 // (private dofs) or must have been zeroed by the caller (shared dofs)
 // d_dot (optional, device): receives <x, y_elements> = sum over elements of x_e^T A_e x_e, computed inside the kernel
+// [k_begin, k_end): the patches to process (k_end < 0: all); dot_add: add to *d_dot instead of storing
 int hex_patch_launch(hcurl_op *op, bool constrained, const double *d_x, double *d_y, double scale, bool accumulate,
-                     double *d_dot = nullptr);
+                     double *d_dot = nullptr, int64_t k_begin = 0, int64_t k_end = -1, bool dot_add = false);
 int hex_patch_flag_essential(hcurl_op *op, const double *d_flag);
 // zero what the patch kernel accumulates into (instead of clearing all of y)
 int hex_patch_zero_shared(hcurl_op *op, double *d_y);
@@ -224,8 +228,9 @@ int tet_build_emat(hcurl_op *op);
 int tet_apply_launch(hcurl_op *op, const uint32_t *d_map, const double *d_x, double *d_y, double scale);
 int tet_diag_launch(hcurl_op *op, double *d_diag);
 // exchange (comm.cu): broadcast owner->ghost on x_ext, reduce ghost->owner on y_ext
-int exchange_broadcast(hcurl_space *sp, double *d_ext);
-int exchange_reduce(hcurl_space *sp, double *d_ext, bool signed_values = true);
+// stream: where the exchange is enqueued (null = the context's main stream)
+int exchange_broadcast(hcurl_space *sp, double *d_ext, cudaStream_t stream = nullptr);
+int exchange_reduce(hcurl_space *sp, double *d_ext, bool signed_values = true, cudaStream_t stream = nullptr);
 int allreduce_sum(hcurl_ctx *ctx, double *d_vals, int n);
 int comm_init(hcurl_ctx *ctx, const void *uid);
 void comm_destroy(hcurl_ctx *ctx);

@@ -86,7 +86,7 @@ static void parallel_for(int64_t n, F f) {
 
 // centroid[e*3+d]; slot_dof[e*nd + s] = extended dof index of element slot s, slot_neg = sign flip
 int build_patches(int nd, int64_t n_elem, int FE, int stride, int unit_bytes, int64_t n_ext, const double *centroid,
-                  const uint32_t *slot_code, PatchHost &out) {
+                  const uint32_t *slot_code, const uint8_t *exchange_units, PatchHost &out) {
   if (stride < FE) { set_error("slot stride must be >= elements per patch"); return 1; }
   if (unit_bytes != 8 && unit_bytes != 16) { set_error("unit size must be 8 or 16 bytes"); return 1; }
   if ((int64_t)stride * nd * unit_bytes > 65534 || (int64_t)FE * nd > 8191) { set_error("patch too large for the 16-bit slot encoding"); return 1; }
@@ -120,6 +120,31 @@ int build_patches(int nd, int64_t n_elem, int FE, int stride, int unit_bytes, in
   out.perm.assign((size_t)n_patch * FE, -1);
   for (int64_t i = 0; i < n_elem; i++) out.perm[(size_t)i] = key[(size_t)i].second;
   key.clear(); key.shrink_to_fit();
+  // ---- patches that touch a unit taking part in the inter-rank exchange (ghosts, owned units other ranks hold as
+  // ghosts) come first, so that they can run between the two halves of the exchange while the rest overlaps with it
+  out.n_boundary = 0;
+  if (exchange_units) {
+    std::vector<uint8_t> bdr((size_t)n_patch, 0);
+    parallel_for(n_patch, [&](int64_t k) {
+      for (int j = 0; j < FE && !bdr[(size_t)k]; j++) {
+        const int32_t e = out.perm[(size_t)k * FE + j];
+        if (e < 0) continue;
+        for (int s = 0; s < nd; s++)
+          if (exchange_units[slot_code[(size_t)e * nd + s] & PATCH_IDX]) { bdr[(size_t)k] = 1; break; }
+      }
+    });
+    std::vector<int32_t> perm2((size_t)n_patch * FE, -1);
+    int64_t q = 0;
+    // the padded patch (the last one in Morton order) keeps its place at the end of its group
+    for (int pass = 1; pass >= 0; pass--)
+      for (int64_t k = 0; k < n_patch; k++)
+        if (bdr[(size_t)k] == pass) {
+          std::copy(out.perm.begin() + k * FE, out.perm.begin() + (k + 1) * FE, perm2.begin() + q * FE);
+          q++;
+          if (pass == 1) out.n_boundary++;
+        }
+    out.perm.swap(perm2);
+  }
 
   // ---- per patch: entries sorted by dof, unique list
   struct Ent { uint32_t dof; uint16_t slot; uint16_t sj; };  // slot = E byte offset, sj = s*FE + j | flags << 13
@@ -391,16 +416,18 @@ struct hcurl_host_patches { hcurl::PatchHost h; };
 
 extern "C" {
 hcurl_host_patches *hcurl_host_patches_create(int nd, int64_t n_elem, int elems_per_patch, int slot_stride, int unit_bytes,
-                                              int64_t n_dof, const double *centroid, const uint32_t *slot_code) {
+                                              int64_t n_dof, const double *centroid, const uint32_t *slot_code,
+                                              const uint8_t *exchange_units) {
   if (nd <= 0 || n_elem <= 0 || !centroid || !slot_code) { hcurl::set_error("hcurl_host_patches_create: bad arguments"); return nullptr; }
   for (int64_t i = 0; i < n_elem * nd; i++)
     if ((int64_t)(slot_code[i] & hcurl::PATCH_IDX) >= n_dof) { hcurl::set_error("hcurl_host_patches_create: dof index out of range"); return nullptr; }
   hcurl_host_patches *p = new hcurl_host_patches;
-  if (hcurl::build_patches(nd, n_elem, elems_per_patch, slot_stride, unit_bytes, n_dof, centroid, slot_code, p->h)) { delete p; return nullptr; }
+  if (hcurl::build_patches(nd, n_elem, elems_per_patch, slot_stride, unit_bytes, n_dof, centroid, slot_code, exchange_units, p->h)) { delete p; return nullptr; }
   return p;
 }
 void hcurl_host_patches_destroy(hcurl_host_patches *p) { delete p; }
 int64_t hcurl_host_patches_count(const hcurl_host_patches *p) { return p->h.n_patch; }
+int64_t hcurl_host_patches_boundary_count(const hcurl_host_patches *p) { return p->h.n_boundary; }
 /* total blob size in 32-bit words; largest single patch blob in words */
 int64_t hcurl_host_patches_blob_words(const hcurl_host_patches *p) { return (int64_t)p->h.blob.size(); }
 int64_t hcurl_host_patches_max_blob_words(const hcurl_host_patches *p) { return (int64_t)p->h.max_blob_words; }

@@ -237,6 +237,9 @@ int hcurl_dot(hcurl_ctx *ctx, const double *a_dev, const double *b_dev, int64_t 
  *             bit 31 = sign flip) of each element slot
  *  slot_stride  >= elems_per_patch: E-vector index (in units) of (slot s, patch position j) = s*slot_stride + j',
  *             j' = j up to the bank swizzle reported by hcurl_host_patches_swizzle()
+ *  exchange_units  NULL, or one flag per unit: patches touching a flagged unit (ghosts, units other ranks hold as
+ *             ghosts) are placed first -- hcurl_host_patches_boundary_count() of them -- so that an apply can overlap the
+ *             inter-rank exchange with the remaining patches
  *  outputs    perm [n_patch*epp] element at each patch position (-1 padding);
  *             blob_off [n_patch+1] start of each patch blob in 16-byte units; blob: per patch a
  *             16-word header, the unit list, the 16/32/64-bit slot-entry sections (dof side) and the
@@ -244,9 +247,10 @@ int hcurl_dot(hcurl_ctx *ctx, const double *a_dev, const double *b_dev, int64_t 
 typedef struct hcurl_host_patches hcurl_host_patches;
 hcurl_host_patches *hcurl_host_patches_create(int nd, int64_t n_elem, int elems_per_patch, int slot_stride,
                                               int unit_bytes, int64_t n_dof, const double *centroid,
-                                              const uint32_t *slot_code);
+                                              const uint32_t *slot_code, const uint8_t *exchange_units);
 void hcurl_host_patches_destroy(hcurl_host_patches *p);
 int64_t hcurl_host_patches_count(const hcurl_host_patches *p);
+int64_t hcurl_host_patches_boundary_count(const hcurl_host_patches *p);
 int64_t hcurl_host_patches_blob_words(const hcurl_host_patches *p);
 int64_t hcurl_host_patches_max_blob_words(const hcurl_host_patches *p);
 /* largest number of unique dofs in one patch (sizes the shared-memory x staging vector) */

@@ -15,12 +15,13 @@ from helpers import star_mesh
 NEG = 0x80000000
 
 
-def build(space, fe, slot_code, centroid, stride=None, unit=8, n_units=None):
+def build(space, fe, slot_code, centroid, stride=None, unit=8, n_units=None, exchange=None):
     lib = L.lib()
     ne, nd = slot_code.shape
     stride = stride or fe + 1
-    h = L.check_ptr(lib.hcurl_host_patches_create(nd, ne, fe, stride, unit, n_units or space.ndof, L.ptr(centroid), L.ptr(slot_code)),
-                    "patches")
+    h = L.check_ptr(lib.hcurl_host_patches_create(nd, ne, fe, stride, unit, n_units or space.ndof, L.ptr(centroid), L.ptr(slot_code),
+                                                  None if exchange is None else L.ptr(exchange)), "patches")
+    SWIZZLE["n_boundary"] = int(lib.hcurl_host_patches_boundary_count(h))
     npatch = lib.hcurl_host_patches_count(h)
     nw = lib.hcurl_host_patches_blob_words(h)
     perm = np.zeros(npatch * fe, np.int32)
@@ -198,11 +199,11 @@ def test_bad_arguments_are_reported():
     lib = L.lib()
     code = np.array([[5, 1]], dtype=np.uint32)
     cen = np.zeros((1, 3))
-    assert not lib.hcurl_host_patches_create(2, 1, 32, 33, 8, 3, L.ptr(cen), L.ptr(code))
+    assert not lib.hcurl_host_patches_create(2, 1, 32, 33, 8, 3, L.ptr(cen), L.ptr(code), None)
     assert b"out of range" in lib.hcurl_last_error()
-    assert not lib.hcurl_host_patches_create(2, 1, 20000, 20000, 8, 8, L.ptr(cen), L.ptr(code))
+    assert not lib.hcurl_host_patches_create(2, 1, 20000, 20000, 8, 8, L.ptr(cen), L.ptr(code), None)
     assert b"too large" in lib.hcurl_last_error()
-    assert not lib.hcurl_host_patches_create(2, 1, 32, 33, 12, 8, L.ptr(cen), L.ptr(code))
+    assert not lib.hcurl_host_patches_create(2, 1, 32, 33, 12, 8, L.ptr(cen), L.ptr(code), None)
     assert b"unit size" in lib.hcurl_last_error()
 
 
@@ -261,3 +262,22 @@ def test_pair_units_with_orientation_flags(n, fe):
         for w in ov:
             y[pd_all[w >> 16]] += Ey[(w & 0xFFFF) // 16]
     np.testing.assert_allclose(y, y_ref, rtol=0, atol=1e-13)
+
+
+def test_exchange_patches_come_first():
+    """Patches touching a flagged (exchange) unit are placed first; the decomposition stays a valid one."""
+    m, sp, code, cen, idx, sgn = make("hex", (16, 4, 4), 2, False)
+    ne, nd = code.shape
+    flags = np.zeros(sp.ndof, np.uint8)
+    on_plane = np.nonzero(np.isclose(m.verts[m.elems].max(axis=1)[:, 0], 1.0))[0]      # elements touching the face x = 1
+    flags[np.unique(idx[on_plane])] = 1
+    perm, off, blob, st = build(sp, 32, code, cen, exchange=flags)
+    nb = SWIZZLE["n_boundary"]
+    npatch = len(off) - 1
+    assert 0 < nb < npatch
+    real = perm[perm >= 0]
+    assert np.array_equal(np.sort(real), np.arange(ne))
+    for k in range(npatch):
+        el = perm[k * 32:(k + 1) * 32]
+        touches = bool(flags[idx[el[el >= 0]]].any())
+        assert touches == (k < nb), (k, nb, touches)
