@@ -14,9 +14,9 @@
 //    global numbering and are always used together (possibly swapped and sign-flipped by the element's
 //    orientation), so gathers, staging, tables, sums and private stores all work on aligned double2.
 //  * memory latency (62 % of a CTA's life in the one-patch-per-CTA version, profiles/r1g)  ->  the
-//    kernel is PERSISTENT and software-pipelined: blob + geometry factors arrive by TMA bulk copies
-//    (cp.async.bulk + mbarrier) two patches ahead, the x gather of the next patch runs as 8-byte
-//    cp.async copies while the current patch is computed and scattered.
+//    kernel is PERSISTENT and software-pipelined: the blob of a patch arrives by a TMA bulk copy
+//    (cp.async.bulk + mbarrier) two patches ahead, the x gather of the next patch runs as 16-byte
+//    cp.async copies while the current patch is computed and scattered; three CTA barriers per patch.
 //  * FP64 pipe (36 TFLOP/s measured; the quadrature-based apply needs 2916 DFMA / element)  ->
 //    on AFFINE elements with per-element coefficients the element operator is applied in an
 //    orthonormal Legendre (modal) basis, where the mass matrix is a restricted identity and the
@@ -27,8 +27,11 @@
 //    rotated frame (c, c+1, c+2) of its component c, so all warps run the same instruction stream.
 //
 // Thread layout: 3*FE threads; thread (c, e) owns component c of element e of the patch.
-// E-vector layout (double2): E2[(c*9 + r)*(FE+1) + e] = slots t = 2r, 2r+1 of component c, t = i0 + 2*(i1 + 3*i2)
-// with i0 the open index along axis c: the element side moves 16-byte vectors, conflict-free.
+// Exchange / result buffers (double2): E2[(c*9 + r)*(FE+1) + e] = slots t = 2r, 2r+1 of component c,
+// t = i0 + 2*(i1 + 3*i2) with i0 the open index along axis c: the element side moves 16-byte vectors,
+// conflict-free; the result buffer EY is additionally XOR-swizzled inside aligned runs of 8 elements
+// (PatchArgs::swz_*) for the dof side's reads.
+// Measured state and the variants that were tried and rejected: profiles/README.md.
 #include <cstdlib>
 #include <cstring>
 
@@ -182,6 +185,10 @@ struct PatchArgs {
   double scale;
   uint32_t blob_cap_bytes;   // shared-memory room reserved for one blob (multiple of 16)
   uint32_t xs_cap_bytes;     // room for the x staging vector (max patch pairs * 16)
+  // split-blob variant: begin of the slot-offset lists and of the per-slot table of every patch (16-byte units, absolute),
+  // room for one header + pair list, and for one set of lists
+  const uint32_t *part_off;
+  uint32_t d_cap_bytes, l_cap_bytes;
   // fused <x, y> (PCG's <p, A p>): per-CTA partial sums, arrival counter, result (null = not wanted)
   double *dot_partial;
   unsigned int *dot_counter;
@@ -531,6 +538,299 @@ hex_patch_modal_p2_kernel(const PatchArgs a) {
   }
 }
 
+// Variant with the blob split by lifetime (HCURL_PATCH_SPLIT=1 when the space is created; NOT YET MEASURED -- written at
+// the end of round 1 after the GPU budget was spent): the pair list (needed from the gather of a patch
+// until its sums) stays double-buffered, the slot-offset lists (sums only) and the per-slot table (pull only) get one
+// buffer each and are requested one iteration ahead; rows of the two 27-row buffers are not padded.  44 KB of shared
+// memory and 128 registers: five 96-thread CTAs per SM instead of four.
+template <int FE, bool ACC, bool DOT>
+__global__ void __maxnreg__(128)
+hex_patch_split_p2_kernel(const PatchArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NT = 3 * FE, ST = FE;  // no row padding: the element side is conflict-free anyway, the swizzle serves the dof side
+  constexpr uint32_t T_CAP = (27 * FE * 2 + 15) & ~15;
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw);  // [0], [1]: pair-list buffers; [2]: slot-offset lists; [3]: per-slot table
+  unsigned char *blobB = smem_raw + 32;                     // 2 x (header + pair list)
+  unsigned char *listB = blobB + 2 * (size_t)a.d_cap_bytes; // e16 | e32 | e64 | ovf of the patch being summed
+  unsigned char *tabB = listB + a.l_cap_bytes;              // lidx of the patch being pulled
+  double2 *Xs = reinterpret_cast<double2 *>(tabB + T_CAP);
+  double2 *E2 = reinterpret_cast<double2 *>(reinterpret_cast<unsigned char *>(Xs) + a.xs_cap_bytes);  // modal exchange
+  double2 *EY = E2 + 27 * ST;                                                                            // element results
+  const unsigned char *Eb = reinterpret_cast<const unsigned char *>(EY);
+  const double2 *x2 = reinterpret_cast<const double2 *>(a.x);
+  double2 *y2 = reinterpret_cast<double2 *>(a.y);
+  const int tid = threadIdx.x;
+  double dacc = 0.0;  // DOT: my share of x^T A x, summed in modal space (x_e^T A_e x_e = Am^T Yh)
+  const int64_t k0 = a.k_begin + blockIdx.x, kstep = gridDim.x;
+  const int n_it = (int)((a.n_patch - k0 + kstep - 1) / kstep);
+  // component c of patch element el, in the rotated frame (c, c+1, c+2)
+  const int c = tid / FE, el = tid - c * FE;
+  const int c1 = c == 2 ? 0 : c + 1, c2 = c == 0 ? 2 : c - 1;
+  const int oK11 = sym6(c1, c1) * FE + el, oK10 = sym6(c1, c) * FE + el, oK12 = sym6(c1, c2) * FE + el, oK22 = sym6(c2, c2) * FE + el,
+            oK20 = sym6(c2, c) * FE + el, oM00 = (6 + sym6(c, c)) * FE + el, oM01 = (6 + sym6(c, c1)) * FE + el,
+            oM02 = (6 + sym6(c, c2)) * FE + el;
+
+  // the three parts of a patch blob (offsets in 16-byte units: begin | lists | table | end), thread 0
+  auto request = [&](int b, uint32_t o0, uint32_t oL) {  // header + pair list -> buffer b
+    const uint32_t bytes = (oL - o0) * 16u;
+    mbar_expect_tx(mbar + b, bytes);
+    bulk_load(mbar + b, blobB + (size_t)b * a.d_cap_bytes, a.blob + (size_t)o0 * 4, bytes);
+  };
+  auto request_lists = [&](uint32_t oL, uint32_t oT) {
+    const uint32_t bytes = (oT - oL) * 16u;
+    mbar_expect_tx(mbar + 2, bytes);
+    if (bytes) bulk_load(mbar + 2, listB, a.blob + (size_t)oL * 4, bytes);
+  };
+  auto request_table = [&](uint32_t oT, uint32_t o1) {
+    const uint32_t bytes = (o1 - oT) * 16u;
+    mbar_expect_tx(mbar + 3, bytes);
+    bulk_load(mbar + 3, tabB, a.blob + (size_t)oT * 4, bytes);
+  };
+  // launch the x gather of the patch whose blob sits in buffer b
+  auto gather = [&](int b) {
+    const uint32_t *B = reinterpret_cast<const uint32_t *>(blobB + (size_t)b * a.d_cap_bytes);
+    const uint32_t U = B[0];
+    const uint32_t *dof = B + PatchHost::HDR;
+#pragma unroll 2
+    for (uint32_t u = tid; u < U; u += NT) {
+      const uint32_t m = dof[u];
+      if (!(m & (PATCH_ESS0 | PATCH_ESS1))) gather16_async(Xs + u, x2 + (m & PATCH_IDX));
+      else {  // essential dofs enter as zeros (rare: synchronous)
+        double2 v = make_double2(0.0, 0.0);
+        if ((m & (PATCH_ESS0 | PATCH_ESS1)) != (PATCH_ESS0 | PATCH_ESS1)) {
+          v = __ldg(x2 + (m & PATCH_IDX));
+          if (m & PATCH_ESS0) v.x = 0.0;
+          if (m & PATCH_ESS1) v.y = 0.0;
+        }
+        Xs[u] = v;
+      }
+    }
+    gather_commit();
+  };
+  if (tid == 0) {
+    for (int i = 0; i < 4; i++) mbar_init(mbar + i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    request(0, __ldg(a.blob_off + k0), __ldg(a.part_off + 2 * k0));
+    request_lists(__ldg(a.part_off + 2 * k0), __ldg(a.part_off + 2 * k0 + 1));
+    request_table(__ldg(a.part_off + 2 * k0 + 1), __ldg(a.blob_off + k0 + 1));
+    if (n_it > 1) request(1, __ldg(a.blob_off + k0 + kstep), __ldg(a.part_off + 2 * (k0 + kstep)));
+  }
+  __syncthreads();  // mbarriers initialised
+  mbar_wait(mbar, 0);
+  gather(0);
+  gather_wait_all();
+  __syncthreads();  // Xs of the first patch complete and visible
+
+  for (int it = 0; it < n_it; it++) {
+    const int b = it & 1;
+    const int64_t k = k0 + (int64_t)it * kstep;
+    const uint32_t *B = reinterpret_cast<const uint32_t *>(blobB + (size_t)b * a.d_cap_bytes);
+    uint32_t q0 = 0, q1 = 0;  // pair-list extent of patch it+2, requested when this one retires
+    uint32_t nL = 0, nT = 0, nE = 0;  // lists | table | end of patch it+1 (requested after the sums / after the pull)
+    if (tid == 0 && it + 2 < n_it) { q0 = __ldg(a.blob_off + k + 2 * kstep); q1 = __ldg(a.part_off + 2 * (k + 2 * kstep)); }
+    if (tid == 0 && it + 1 < n_it) {
+      nL = __ldg(a.part_off + 2 * (k + kstep)); nT = __ldg(a.part_off + 2 * (k + kstep) + 1); nE = __ldg(a.blob_off + k + kstep + 1);
+    }
+    // affine geometry factors of my element: issued now, consumed after the forward transform
+    const double *g = a.edata + (size_t)k * 12 * FE;
+    double K11 = __ldg(g + oK11), K10 = __ldg(g + oK10), K12 = __ldg(g + oK12), K22 = __ldg(g + oK22), K20 = __ldg(g + oK20),
+           M00 = __ldg(g + oM00), M01 = __ldg(g + oM01), M02 = __ldg(g + oM02);
+    const bool ok = (uint32_t)el < B[13];
+    // ---- pull the element inputs through the per-slot table, forward transform
+    double Am[18];
+    uint32_t lx[9];
+    uint32_t fl = 0;
+    mbar_wait(mbar + 3, it & 1);  // per-slot table of this patch
+    if (ok) {
+      const uint16_t *lidx = reinterpret_cast<const uint16_t *>(tabB) + (c * 9) * FE + el;
+#pragma unroll
+      for (int r = 0; r < 9; r++) { lx[r] = lidx[r * FE]; fl |= lx[r]; }
+    }
+    // warp-uniform: no element of this warp sees a pair swapped or sign-flipped (consistently oriented meshes)
+    const bool plain = __all_sync(0xffffffffu, (fl & 0xe000u) == 0u);
+    if (ok) {
+      double X[18];
+      if (plain) {
+#pragma unroll
+        for (int r = 0; r < 9; r++) { const double2 v = Xs[lx[r]]; X[2 * r] = v.x; X[2 * r + 1] = v.y; }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 9; r++) pair_to_local(Xs[lx[r] & 0x1fffu], lx[r], X[2 * r], X[2 * r + 1]);
+      }
+      modal_fwd(X, Am);
+      double2 *Eown = E2 + (c * 9) * ST + el;
+#pragma unroll
+      for (int r = 0; r < 9; r++) Eown[r * ST] = make_double2(Am[2 * r], Am[2 * r + 1]);
+    }
+    __syncthreads();  // modal coefficients visible; Xs and the per-slot table free
+    if (tid == 0 && it + 1 < n_it) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      request_table(nT, nE);
+    }
+    double Y[18];
+    if (ok) {
+      const double2 *E1 = E2 + (c1 * 9) * ST + el, *E2c = E2 + (c2 * 9) * ST + el;
+      double Bm[18], Cm[18];
+      // owner frames: comp c+1 stores (m1, m2, m0), comp c+2 stores (m2, m0, m1); the fastest owner index is the pair
+#pragma unroll
+      for (int m2 = 0; m2 < 3; m2++)
+#pragma unroll
+        for (int m0 = 0; m0 < 3; m0++) {
+          const double2 v = E1[(m2 + 3 * m0) * ST];
+          Bm[IB(m0, 0, m2)] = v.x;
+          Bm[IB(m0, 1, m2)] = v.y;
+        }
+#pragma unroll
+      for (int m1 = 0; m1 < 3; m1++)
+#pragma unroll
+        for (int m0 = 0; m0 < 3; m0++) {
+          const double2 v = E2c[(m0 + 3 * m1) * ST];
+          Cm[IC(m0, m1, 0)] = v.x;
+          Cm[IC(m0, m1, 1)] = v.y;
+        }
+      const double sc = 0.25 * a.scale;  // 1/4: the open transforms are applied without their 1/2
+      K11 *= sc; K10 *= sc; K12 *= sc; K22 *= sc; K20 *= sc; M00 *= sc; M01 *= sc; M02 *= sc;
+      double Yh[18];
+      modal_op(Am, Bm, Cm, M00, M01, M02, K11, K10, K12, K22, K20, K12, Yh);
+      if (DOT) {
+        double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+        for (int t = 0; t < 18; t += 2) { d0 = fma(Am[t], Yh[t], d0); d1 = fma(Am[t + 1], Yh[t + 1], d1); }
+        dacc += d0 + d1;
+      }
+      modal_bwd(Yh, Y);
+    }
+    // ---- start the x gather of the next patch: it lands while this patch is scattered
+    if (it + 1 < n_it) {
+      mbar_wait(mbar + (b ^ 1), ((it + 1) >> 1) & 1);
+      gather(b ^ 1);
+    }
+    if (ok) {
+      double2 *Eown = EY + (c * 9) * ST;
+      const int elx = el ^ a.swz_grp[el >> 3];
+      if (plain) {
+#pragma unroll
+        for (int r = 0; r < 9; r++) Eown[r * ST + (elx ^ a.swz_row[c * 9 + r])] = make_double2(Y[2 * r], Y[2 * r + 1]);
+      } else {
+#pragma unroll
+        for (int r = 0; r < 9; r++) Eown[r * ST + (elx ^ a.swz_row[c * 9 + r])] = local_to_pair(Y[2 * r], Y[2 * r + 1], lx[r]);
+      }
+    }
+    __syncthreads();  // element results visible; everyone has read the modal coefficients
+    // ---- sum the slots of every patch pair; private pairs are plain 16-byte stores, shared ones RED
+    {
+      const uint32_t n1 = B[1], n2 = B[2], n4 = B[3], nov = B[7];
+      const uint32_t *dof = B + PatchHost::HDR;
+      mbar_wait(mbar + 2, it & 1);  // slot-offset lists of this patch
+      const uint32_t *Lw = reinterpret_cast<const uint32_t *>(listB) - B[8];  // the lists start at word B[8] of the blob
+      const uint16_t *e16 = reinterpret_cast<const uint16_t *>(Lw + B[8]);
+      const uint32_t *e32 = Lw + B[9];
+      const uint2 *e64 = reinterpret_cast<const uint2 *>(Lw + B[10]);
+      const uint32_t *ovf = Lw + B[11];
+      constexpr uint32_t SKIP = PATCH_ESS0 | PATCH_ESS1;
+#define E_AT(off) (*reinterpret_cast<const double2 *>(Eb + (off)))
+      auto emit = [&](const uint32_t m, const double2 v) {
+        double2 *dst = y2 + (m & PATCH_IDX);
+        if (!(m & (SKIP | PATCH_SHARED))) {
+          if (ACC) { const double2 o = *dst; *dst = make_double2(o.x + v.x, o.y + v.y); }
+          else *dst = v;
+        } else if ((m & SKIP) != SKIP) {
+          if (m & PATCH_SHARED) {
+            if (!(m & PATCH_ESS0)) red_add(&dst->x, v.x);
+            if (!(m & PATCH_ESS1)) red_add(&dst->y, v.y);
+          } else {
+            if (!(m & PATCH_ESS0)) dst->x = ACC ? dst->x + v.x : v.x;
+            if (!(m & PATCH_ESS1)) dst->y = ACC ? dst->y + v.y : v.y;
+          }
+        }
+      };
+      constexpr int UN = 2;  // pairs in flight per thread: table reads, then E reads, then the stores
+      for (uint32_t r0 = tid; r0 < n1; r0 += UN * NT) {
+        uint32_t m[UN], o[UN];
+        double2 v[UN];
+#pragma unroll
+        for (int i = 0; i < UN; i++) {
+          const uint32_t r = r0 + i * NT;
+          m[i] = r < n1 ? dof[r] : SKIP;
+          o[i] = r < n1 ? e16[r] : 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < UN; i++) v[i] = E_AT(o[i]);
+#pragma unroll
+        for (int i = 0; i < UN; i++) emit(m[i], v[i]);
+      }
+      dof += n1;
+      for (uint32_t r0 = tid; r0 < n2; r0 += UN * NT) {
+        uint32_t m[UN], o[UN];
+        double2 v[UN];
+#pragma unroll
+        for (int i = 0; i < UN; i++) {
+          const uint32_t r = r0 + i * NT;
+          m[i] = r < n2 ? dof[r] : SKIP;
+          o[i] = r < n2 ? e32[r] : 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < UN; i++) {
+          const double2 p = E_AT(o[i] & 0xffffu), q = E_AT(o[i] >> 16);
+          v[i] = make_double2(p.x + q.x, p.y + q.y);
+        }
+#pragma unroll
+        for (int i = 0; i < UN; i++) emit(m[i], v[i]);
+      }
+      dof += n2;
+      for (uint32_t r = tid; r < n4; r += NT) {
+        const uint32_t m = dof[r];
+        const uint2 o = e64[r];
+        const double2 p = E_AT(o.x & 0xffffu), q = E_AT(o.x >> 16), s = E_AT(o.y & 0xffffu);
+        double2 v = make_double2((p.x + q.x) + s.x, (p.y + q.y) + s.y);
+        if ((o.y >> 16) != 0xffffu) { const double2 t = E_AT(o.y >> 16); v.x += t.x; v.y += t.y; }
+        emit(m, v);
+      }
+      dof = B + PatchHost::HDR;
+      for (uint32_t t = tid; t < nov; t += NT) {  // slots beyond four (unstructured meshes)
+        const uint32_t e = ovf[t], m = dof[e >> 16];
+        const double2 v = E_AT(e & 0xffffu);
+        double2 *dst = y2 + (m & PATCH_IDX);
+        if (!(m & PATCH_ESS0)) red_add(&dst->x, v.x);
+        if (!(m & PATCH_ESS1)) red_add(&dst->y, v.y);
+      }
+#undef E_AT
+    }
+    gather_wait_all();
+    __syncthreads();  // pair-list buffer b, the lists and EY are free; Xs of the next patch complete and visible
+    if (tid == 0 && it + 1 < n_it) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      request_lists(nL, nT);
+      if (it + 2 < n_it) request(b, q0, q1);
+    }
+  }
+  if (DOT) {
+    // deterministic for a fixed grid: fixed-order sums inside the CTA, per-CTA partials, the last CTA to arrive
+    // adds them in index order (same protocol as block_finish() of the vector kernels, api.cu)
+    double *red = reinterpret_cast<double *>(E2);  // all patches retired: E is free
+    __shared__ bool last;
+    for (int o = 16; o > 0; o >>= 1) dacc += __shfl_down_sync(0xffffffffu, dacc, o);
+    if ((tid & 31) == 0) red[tid >> 5] = dacc;
+    __syncthreads();
+    if (tid == 0) {
+      double v = 0.0;
+      for (int w = 0; w < NT / 32; w++) v += red[w];
+      a.dot_partial[blockIdx.x] = v;
+      __threadfence();
+      last = atomicInc(a.dot_counter, gridDim.x - 1) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && tid < 32) {
+      __threadfence();
+      double v = 0.0;
+      for (int i = tid; i < (int)gridDim.x; i += 32) v += ((volatile double *)a.dot_partial)[i];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      if (tid == 0) *a.dot_out = a.dot_add ? *a.dot_out + v : v;
+    }
+  }
+}
+
 // ---- setup ---------------------------------------------------------------------------------------
 // affine geometry factors in patch order: S = alpha J^T J/det (6), M = beta adj adj^T/det (6)
 __global__ void patch_edata_kernel(const int64_t n_pos, const int FE, const int32_t *__restrict__ perm, const double *__restrict__ xyz,
@@ -678,11 +978,15 @@ int hex_patch_build(hcurl_space *sp, const double *elem_xyz, const int32_t *elem
     for (int64_t u = sp->n_tdof / 2; u < sp->n_ext() / 2; u++) xch[(size_t)u] = 1;
     for (int32_t d : sp->own_ext) xch[(size_t)(d / 2)] = 1;
   }
+  const char *spl = getenv("HCURL_PATCH_SPLIT");
+  const bool split = spl && spl[0] == '1' && FE == 32;  // experimental variant, see hex_patch_split_p2_kernel
   PatchHost H;
-  if (build_patches(np, ne, FE, FE + 1, 16, sp->n_ext() / 2, cen.data(), code.data(), xch.empty() ? nullptr : xch.data(), H)) return 1;
+  if (build_patches(np, ne, FE, split ? FE : FE + 1, 16, sp->n_ext() / 2, cen.data(), code.data(), xch.empty() ? nullptr : xch.data(), H)) return 1;
   HC_CUDA(cudaSetDevice(sp->ctx->device));
   PatchSet &P = sp->patch;
   P.FE = FE; P.stride = H.stride; P.n_patch = H.n_patch; P.n_boundary = H.n_boundary;
+  P.split = split; P.max_d_words = H.max_d_words; P.max_l_words = H.max_l_words;
+  if (split && upload(P.d_part_off, H.part_off)) return 1;
   P.blob_words = (int64_t)H.blob.size(); P.max_blob_words = H.max_blob_words; P.max_dofs = H.max_dofs;
   for (int i = 0; i < 27; i++) P.swz_row[i] = H.swz_row[(size_t)i];
   for (size_t i = 0; i < 16; i++) P.swz_grp[i] = i < H.swz_grp.size() ? H.swz_grp[i] : 0;
@@ -695,7 +999,7 @@ int hex_patch_build(hcurl_space *sp, const double *elem_xyz, const int32_t *elem
 
 void hex_patch_free(hcurl_space *sp) {
   PatchSet &P = sp->patch;
-  cudaFree(P.d_perm); cudaFree(P.d_blob_off); cudaFree(P.d_blob); cudaFree(P.d_shared);
+  cudaFree(P.d_perm); cudaFree(P.d_blob_off); cudaFree(P.d_blob); cudaFree(P.d_shared); cudaFree(P.d_part_off);
   cudaFree(sp->d_xyzP);
   P = PatchSet();
   sp->has_patches = false;
@@ -746,6 +1050,40 @@ static int launch_fe(const PatchArgs &a, int64_t n_patch, int sm_count, size_t s
   return 0;
 }
 
+// split-blob variant: 2 mbarrier pairs | 2 pair-list buffers | lists | table | Xs | E | EY (unpadded rows)
+static size_t patch_split_smem_bytes(int FE, const PatchSet &P) {
+  const size_t d_cap = ((size_t)P.max_d_words * 4 + 15u) & ~(size_t)15u, l_cap = ((size_t)P.max_l_words * 4 + 15u) & ~(size_t)15u;
+  return 32 + 2 * d_cap + l_cap + (((size_t)27 * FE * 2 + 15) & ~(size_t)15) + (size_t)P.max_dofs * 16 + 2 * (size_t)27 * FE * 16;
+}
+template <int FE>
+static int launch_split(const PatchArgs &a, int64_t n_run, int sm_count, size_t smem, bool acc, cudaStream_t st) {
+  auto k0 = hex_patch_split_p2_kernel<FE, false, false>;
+  auto k1 = hex_patch_split_p2_kernel<FE, true, false>;
+  auto kd = hex_patch_split_p2_kernel<FE, false, true>;
+  static size_t attr = 0;
+  static int per_sm = 0;
+  if (attr < smem) {
+    HC_CUDA(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HC_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HC_CUDA(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HC_CUDA(cudaFuncSetAttribute(k0, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    HC_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    HC_CUDA(cudaFuncSetAttribute(kd, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    HC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kd, 3 * FE, smem));
+    if (per_sm < 1) { set_error("split patch kernel does not fit on an SM (%zu bytes of shared memory)", smem); return 1; }
+    attr = smem;
+  }
+  int64_t grid = (int64_t)per_sm * sm_count;
+  if (const char *s = getenv("HCURL_PATCH_CTAS_PER_SM")) { const int v = atoi(s); if (v >= 1 && v <= per_sm) grid = (int64_t)v * sm_count; }
+  if (grid > n_run) grid = n_run;
+  if (a.dot_out) {
+    if (acc) { set_error("patch kernel: fused dot product is not available with accumulation"); return 1; }
+    kd<<<(unsigned)grid, 3 * FE, smem, st>>>(a);
+  } else if (acc) k1<<<(unsigned)grid, 3 * FE, smem, st>>>(a);
+  else k0<<<(unsigned)grid, 3 * FE, smem, st>>>(a);
+  return 0;
+}
+
 int hex_patch_launch(hcurl_op *op, bool constrained, const double *d_x, double *d_y, double scale, bool accumulate, double *d_dot,
                      int64_t k_begin, int64_t k_end, bool dot_add) {
   hcurl_space *sp = op->sp;
@@ -772,12 +1110,16 @@ int hex_patch_launch(hcurl_op *op, bool constrained, const double *d_x, double *
   a.dot_out = d_dot; a.dot_partial = ctx->d_partial; a.dot_counter = ctx->d_counter;
   if (d_dot && ctx->n_partial < 8 * ctx->sm_count) { set_error("reduction scratch too small for the patch grid"); return 1; }
   if (a.prof && accumulate) a.prof = nullptr;
-  const size_t smem = patch_smem_bytes(P.FE, P.max_blob_words, P.max_dofs);
+  a.part_off = P.d_part_off;
+  a.d_cap_bytes = (P.max_d_words * 4 + 15u) & ~15u;
+  a.l_cap_bytes = (P.max_l_words * 4 + 15u) & ~15u;
+  const size_t smem = P.split ? patch_split_smem_bytes(P.FE, P) : patch_smem_bytes(P.FE, P.max_blob_words, P.max_dofs);
   int rc = 1;
   // 168 registers per thread: 2 CTAs of 192 threads per SM.  (A 3-CTA variant capped at 112 / 104 registers spilled
   // and ran 45 % slower, profiles/README.md.)
   const int64_t n_run = a.n_patch - a.k_begin;
-  if (P.FE == 32) rc = launch_fe<32, 4>(a, n_run, ctx->sm_count, smem, accumulate, ctx->stream);
+  if (P.split) rc = launch_split<32>(a, n_run, ctx->sm_count, smem, accumulate, ctx->stream);
+  else if (P.FE == 32) rc = launch_fe<32, 4>(a, n_run, ctx->sm_count, smem, accumulate, ctx->stream);
   else if (P.FE == 64) rc = launch_fe<64, 2>(a, n_run, ctx->sm_count, smem, accumulate, ctx->stream);
   else if (P.FE == 128) rc = launch_fe<128, 1>(a, n_run, ctx->sm_count, smem, accumulate, ctx->stream);
   if (rc) return rc;

@@ -80,6 +80,10 @@ struct PatchHost {
   std::vector<uint32_t> blob;     // see patch.cpp for the layout
   uint32_t max_blob_words = 0;
   uint32_t max_dofs = 0;          // largest number of unique dofs of one patch
+  // the blob of patch k by lifetime: [blob_off[k], part_off[2k]) header + unit list, [part_off[2k], part_off[2k+1])
+  // slot-offset lists, [part_off[2k+1], blob_off[k+1]) per-slot table (16-byte units); largest first two parts in words
+  std::vector<uint32_t> part_off;
+  uint32_t max_d_words = 0, max_l_words = 0;
   // E-vector swizzle: slot s of patch position j sits at unit s*stride + (j ^ swz_row[s] ^ swz_grp[j / NB]), NB = 128 /
   // unit_bytes (values < NB, so positions stay inside their aligned run of NB: the element side remains conflict-free)
   std::vector<uint8_t> swz_row, swz_grp;
@@ -98,6 +102,9 @@ struct PatchSet {  // device copy
   uint32_t *d_blob_off = nullptr, *d_blob = nullptr;
   int64_t blob_words = 0;
   uint32_t max_blob_words = 0, max_dofs = 0;
+  bool split = false;            // blobs built for the split-blob kernel variant (unpadded rows)
+  uint32_t *d_part_off = nullptr;
+  uint32_t max_d_words = 0, max_l_words = 0;
   uint8_t swz_row[27] = {0}, swz_grp[16] = {0};
   uint32_t *d_shared = nullptr;  // 128-byte lines holding RED-added pairs: the only part of y that must be zero before an apply
   int64_t n_shared = 0;

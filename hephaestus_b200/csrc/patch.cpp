@@ -207,6 +207,8 @@ int build_patches(int nd, int64_t n_elem, int FE, int stride, int unit_bytes, in
   out.blob_off.assign((size_t)n_patch + 1, 0);
   out.max_blob_words = 0;
   out.max_dofs = 0;
+  out.max_d_words = out.max_l_words = 0;
+  out.part_off.assign((size_t)n_patch * 2, 0);
   for (int64_t k = 0; k < n_patch; k++) {
     const auto &ud = udof[(size_t)k];
     const auto &us = ustart[(size_t)k];
@@ -219,6 +221,12 @@ int build_patches(int nd, int64_t n_elem, int FE, int stride, int unit_bytes, in
     const uint32_t w = PatchHost::HDR + align4((uint32_t)ud.size()) + align4((n[0] + 1) / 2) + align4(n[1]) + align4(2 * n[2]) +
                        align4(nov) + lidx_words;
     out.blob_off[(size_t)k + 1] = out.blob_off[(size_t)k] + w / 4;
+    // parts by lifetime: [header + unit list | slot-offset lists | per-slot table]
+    const uint32_t wd = PatchHost::HDR + align4((uint32_t)ud.size()), wl = w - wd - lidx_words;
+    out.part_off[(size_t)k * 2] = out.blob_off[(size_t)k] + wd / 4;
+    out.part_off[(size_t)k * 2 + 1] = out.blob_off[(size_t)k] + (wd + wl) / 4;
+    out.max_d_words = std::max(out.max_d_words, wd);
+    out.max_l_words = std::max(out.max_l_words, wl);
     out.max_blob_words = std::max(out.max_blob_words, w);
     out.max_dofs = std::max(out.max_dofs, (uint32_t)ud.size());
   }

@@ -210,8 +210,8 @@ def test_bad_arguments_are_reported():
 SWAP, NEG1, NEG0 = 0x20000000, 0x40000000, 0x80000000
 
 
-@pytest.mark.parametrize("n,fe", [((4, 4, 4), 64), ((5, 3, 4), 32)])
-def test_pair_units_with_orientation_flags(n, fe):
+@pytest.mark.parametrize("n,fe,padded", [((4, 4, 4), 64, True), ((5, 3, 4), 32, True), ((5, 3, 4), 32, False)])
+def test_pair_units_with_orientation_flags(n, fe, padded):
     """16-byte units: the dof side moves aligned pairs of doubles; each element slot pair carries a
     swap flag and one sign per entry (hex_patch.cu builds these from the order-2 map; here random
     flags exercise every combination)."""
@@ -226,7 +226,7 @@ def test_pair_units_with_orientation_flags(n, fe):
     flags = rng.integers(0, 8, size=idx.shape).astype(np.uint32) << 29
     code = np.ascontiguousarray((idx.astype(np.uint32) | flags).astype(np.uint32))
     cen = np.ascontiguousarray(m.verts[m.elems].mean(axis=1))
-    perm, off, blob, st = build(sp, fe, code, cen, unit=16, n_units=n_units)
+    perm, off, blob, st = build(sp, fe, code, cen, stride=None if padded else fe, unit=16, n_units=n_units)   # unpadded rows: split-blob kernel
     x = rng.standard_normal((n_units, 2))
     ye = rng.standard_normal((ne, npair, 2))
     sw, n1, n0 = (flags & SWAP) != 0, (flags & NEG1) != 0, (flags & NEG0) != 0
