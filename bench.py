@@ -232,7 +232,12 @@ def main():
             mesh = fespace.perturb_interior(mesh)
         if args.geom == "tet":
             mesh = fespace.hex_to_tets(mesh)
-        space = fespace.NDSpace(mesh, p)
+        # hexes: the library's host-side C++ generator (same map as fespace.NDSpace, tests/test_ndspace.py)
+        try:
+            space = fespace.NativeHexNDSpace(mesh, p) if args.geom == "hex" else fespace.NDSpace(mesh, p)
+        except Exception as exc:  # setup only: the Python generator builds the identical map
+            print("native ND space generator unavailable (%s); using fespace.NDSpace" % exc, file=sys.stderr)
+            space = fespace.NDSpace(mesh, p)
         gsp = operators.GpuNDSpace(ctx, space)
         ess = space.boundary_dofs()
         attr = mesh.attr

@@ -74,6 +74,14 @@ SIGNATURES = {
     "hcurl_host_free_pinned": (None, [_P]),
     "hcurl_dot": (C.c_int, [_P, _P, _P, C.c_int64, C.POINTER(C.c_double)]),
     "hcurl_fp64_peak_tflops": (C.c_double, [_P]),
+    "hcurl_host_ndspace_create_hex": (_P, [C.c_int, C.c_int64, _P]),
+    "hcurl_host_ndspace_destroy": (None, [_P]),
+    "hcurl_host_ndspace_nd": (C.c_int, [_P]),
+    "hcurl_host_ndspace_ndof": (C.c_int64, [_P]),
+    "hcurl_host_ndspace_n_edges": (C.c_int64, [_P]),
+    "hcurl_host_ndspace_n_faces": (C.c_int64, [_P]),
+    "hcurl_host_ndspace_elem_dofs": (C.c_int, [_P, _P]),
+    "hcurl_host_ndspace_boundary_dofs": (C.c_int64, [_P, _P]),
     "hcurl_host_patches_create": (_P, [C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int64, _P, _P, _P]),
     "hcurl_host_patches_destroy": (None, [_P]),
     "hcurl_host_patches_count": (C.c_int64, [_P]),

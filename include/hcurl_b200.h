@@ -260,6 +260,23 @@ int64_t hcurl_host_patches_max_dofs(const hcurl_host_patches *p);
 int hcurl_host_patches_swizzle(const hcurl_host_patches *p, uint8_t *row, uint8_t *grp);
 int hcurl_host_patches_copy(const hcurl_host_patches *p, int32_t *perm, uint32_t *blob_off, uint32_t *blob);
 
+/* ---- host-side setup helper: ND space on a hex mesh (no GPU needed) ------------------
+ * What mfem::ParFiniteElementSpace hands the assembly once ProblemBuilder::AddFESpace("ND_3D_P<p>") has run
+ * (/root/reference/src/problem_builders/problem_builder_base.cpp:98-127): global edge / face enumeration and the
+ * signed FiniteElementSpace::GetElementDofs map (k, or -1-k when the element sees the dof flipped), in MFEM's
+ * conventions.  For callers that are not handed MFEM's arrays (stand-alone benchmarks, SURVEY.md
+ * 8 f4); the result feeds hcurl_space_create().  elem_verts: [n_elem][8] corner ids in MFEM's hexahedron order. */
+typedef struct hcurl_host_ndspace hcurl_host_ndspace;
+hcurl_host_ndspace *hcurl_host_ndspace_create_hex(int order, int64_t n_elem, const int32_t *elem_verts);
+void hcurl_host_ndspace_destroy(hcurl_host_ndspace *s);
+int hcurl_host_ndspace_nd(const hcurl_host_ndspace *s);          /* dofs per element, 3p(p+1)^2 */
+int64_t hcurl_host_ndspace_ndof(const hcurl_host_ndspace *s);
+int64_t hcurl_host_ndspace_n_edges(const hcurl_host_ndspace *s);
+int64_t hcurl_host_ndspace_n_faces(const hcurl_host_ndspace *s);
+int hcurl_host_ndspace_elem_dofs(const hcurl_host_ndspace *s, int32_t *signed_dofs /* [n_elem][nd] */);
+/* dofs on boundary faces and their edges, ascending; returns the count (out may be NULL; room for ndof entries) */
+int64_t hcurl_host_ndspace_boundary_dofs(const hcurl_host_ndspace *s, int32_t *out);
+
 /* FP64 FMA micro-benchmark used for the roofline co-bound:
  * returns achieved TFLOP/s of dependent-chain-free DFMA on the device. */
 double hcurl_fp64_peak_tflops(hcurl_ctx *ctx);

@@ -1,0 +1,86 @@
+"""Host-side C++ ND hex space (hephaestus_b200/csrc/ndspace.cpp) against the Python generator and the oracle:
+bit-identical signed element -> dof maps, counts and boundary dofs (runs without a GPU)."""
+import os
+
+import numpy as np
+import pytest
+
+from hephaestus_b200 import _lib as L
+from hephaestus_b200 import fespace
+from oracle import mesh as om, space as osp
+
+from helpers import star_mesh
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def cpp_space(mesh, p):
+    lib = L.lib()
+    ev = np.ascontiguousarray(mesh.elems, dtype=np.int32)
+    h = L.check_ptr(lib.hcurl_host_ndspace_create_hex(p, len(ev), L.ptr(ev)), "ndspace")
+    nd, ndof = lib.hcurl_host_ndspace_nd(h), lib.hcurl_host_ndspace_ndof(h)
+    dofs = np.zeros((len(ev), nd), np.int32)
+    L.check(lib.hcurl_host_ndspace_elem_dofs(h, L.ptr(dofs)), "elem_dofs")
+    nb = lib.hcurl_host_ndspace_boundary_dofs(h, None)
+    bd = np.zeros(nb, np.int32)
+    assert lib.hcurl_host_ndspace_boundary_dofs(h, L.ptr(bd)) == nb
+    out = dict(nd=nd, ndof=ndof, n_edges=lib.hcurl_host_ndspace_n_edges(h), n_faces=lib.hcurl_host_ndspace_n_faces(h), dofs=dofs, bdr=bd)
+    lib.hcurl_host_ndspace_destroy(h)
+    return out
+
+
+def scrambled(mesh, seed=5):
+    perm = np.random.default_rng(seed).permutation(len(mesh.verts))
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(len(perm))
+    return fespace.Mesh("hex", mesh.verts[perm], inv[mesh.elems], mesh.attr)
+
+
+@pytest.mark.parametrize("p", [1, 2, 3, 4])
+@pytest.mark.parametrize("kind", ["cube", "scrambled", "star"])
+def test_matches_python_generator_and_oracle(kind, p):
+    mesh = star_mesh(3) if kind == "star" else fespace.cartesian_hex_mesh(4, 3, 5)
+    if kind == "scrambled":
+        mesh = scrambled(mesh)     # random vertex numbering: every edge / face orientation code occurs
+    ref = fespace.NDSpace(mesh, p)
+    got = cpp_space(mesh, p)
+    assert (got["nd"], got["ndof"], got["n_edges"], got["n_faces"]) == (ref.nd, ref.ndof, ref.n_edges, ref.n_faces)
+    assert np.array_equal(got["dofs"], ref.signed_elem_dofs())
+    assert np.array_equal(got["bdr"], ref.boundary_dofs())
+    omesh = om.Mesh("hex", mesh.verts, mesh.elems, mesh.attr)
+    assert np.array_equal(got["dofs"], osp.NDSpace(omesh, p).signed_elem_dofs())
+    if kind == "scrambled":
+        assert (got["dofs"] < 0).any() and (got["dofs"] >= 0).any()
+
+
+@pytest.mark.parametrize("p", [1, 2, 3])
+def test_reference_mesh_cylinder_hex(p):
+    """The reference's hex mesh data/cylinder-hex-q2.gen (golden fixture of its connectivity): 6 882 ND2 dofs
+    (SURVEY.md App. C), same map as the Python generator."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "cylinder_hex_q2.npz"))
+    mesh = fespace.Mesh("hex", z["verts"], z["elems"], z["attr"])
+    got = cpp_space(mesh, p)
+    ref = fespace.NDSpace(mesh, p)
+    if p == 2:
+        assert got["ndof"] == 6882
+    assert got["ndof"] == ref.ndof
+    assert np.array_equal(got["dofs"], ref.signed_elem_dofs())
+    assert np.array_equal(got["bdr"], ref.boundary_dofs())
+
+
+def test_bad_arguments():
+    lib = L.lib()
+    ev = np.zeros((1, 8), np.int32)
+    assert not lib.hcurl_host_ndspace_create_hex(7, 1, L.ptr(ev))
+    assert b"bad arguments" in lib.hcurl_last_error()
+    ev[0, 3] = -2
+    assert not lib.hcurl_host_ndspace_create_hex(1, 1, L.ptr(ev))
+    assert b"negative" in lib.hcurl_last_error()
+
+
+def test_python_wrapper_is_a_drop_in():
+    mesh = scrambled(fespace.cartesian_hex_mesh(3, 4, 2))
+    a, b = fespace.NativeHexNDSpace(mesh, 2), fespace.NDSpace(mesh, 2)
+    assert (a.nd, a.ndof, a.p) == (b.nd, b.ndof, b.p)
+    assert np.array_equal(a.signed_elem_dofs(), b.signed_elem_dofs())
+    assert np.array_equal(a.boundary_dofs(), b.boundary_dofs())
