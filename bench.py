@@ -232,9 +232,9 @@ def main():
             mesh = fespace.perturb_interior(mesh)
         if args.geom == "tet":
             mesh = fespace.hex_to_tets(mesh)
-        # hexes: the library's host-side C++ generator (same map as fespace.NDSpace, tests/test_ndspace.py)
+        # the library's host-side C++ generator (same map as fespace.NDSpace, tests/test_ndspace.py)
         try:
-            space = fespace.NativeHexNDSpace(mesh, p) if args.geom == "hex" else fespace.NDSpace(mesh, p)
+            space = fespace.NativeNDSpace(mesh, p)
         except Exception as exc:  # setup only: the Python generator builds the identical map
             print("native ND space generator unavailable (%s); using fespace.NDSpace" % exc, file=sys.stderr)
             space = fespace.NDSpace(mesh, p)

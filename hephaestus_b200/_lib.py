@@ -75,6 +75,8 @@ SIGNATURES = {
     "hcurl_dot": (C.c_int, [_P, _P, _P, C.c_int64, C.POINTER(C.c_double)]),
     "hcurl_fp64_peak_tflops": (C.c_double, [_P]),
     "hcurl_host_ndspace_create_hex": (_P, [C.c_int, C.c_int64, _P]),
+    "hcurl_host_ndspace_create_tet": (_P, [C.c_int, C.c_int64, _P]),
+    "hcurl_host_ndspace_elem_face_base": (C.c_int, [_P, _P]),
     "hcurl_host_ndspace_destroy": (None, [_P]),
     "hcurl_host_ndspace_nd": (C.c_int, [_P]),
     "hcurl_host_ndspace_ndof": (C.c_int64, [_P]),

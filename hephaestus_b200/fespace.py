@@ -396,18 +396,20 @@ class NDSpace:
         return np.unique(np.concatenate(out)).astype(np.int32)
 
 
-class NativeHexNDSpace:
-    """ND space on a hex mesh generated by the library's host-side C++ code (csrc/ndspace.cpp,
-    hcurl_host_ndspace_*): same numbering, signs and boundary dofs as NDSpace (tests/test_ndspace.py checks
-    them bit for bit), about 7x faster at 2 M elements.  Offers what GpuNDSpace / the bench need."""
+class NativeNDSpace:
+    """ND space on a hex or tet mesh generated by the library's host-side C++ code (csrc/ndspace.cpp,
+    hcurl_host_ndspace_*): same numbering, signs, boundary dofs and per-face base vertex order as NDSpace
+    (tests/test_ndspace.py checks them bit for bit), about 7x faster at 2 M hexes.  Offers what GpuNDSpace / the
+    bench need."""
 
     def __init__(self, mesh, p):
         from . import _lib as L
-        assert mesh.kind == "hex"
         self.mesh, self.p = mesh, p
         lib = L.lib()
+        hexa = mesh.kind == "hex"
         ev = np.ascontiguousarray(mesh.elems, dtype=np.int32)
-        h = L.check_ptr(lib.hcurl_host_ndspace_create_hex(p, len(ev), L.ptr(ev)), "hcurl_host_ndspace_create_hex")
+        create = lib.hcurl_host_ndspace_create_hex if hexa else lib.hcurl_host_ndspace_create_tet
+        h = L.check_ptr(create(p, len(ev), L.ptr(ev)), "hcurl_host_ndspace_create")
         try:
             self.nd = int(lib.hcurl_host_ndspace_nd(h))
             self.ndof = int(lib.hcurl_host_ndspace_ndof(h))
@@ -417,12 +419,18 @@ class NativeHexNDSpace:
             nb = int(lib.hcurl_host_ndspace_boundary_dofs(h, None))
             self._bdr = np.empty(nb, np.int32)
             lib.hcurl_host_ndspace_boundary_dofs(h, L.ptr(self._bdr))
+            self.elem_face_base = None
+            if not hexa:
+                self.elem_face_base = np.empty((len(ev), 4, 3), np.int32)
+                L.check(lib.hcurl_host_ndspace_elem_face_base(h, L.ptr(self.elem_face_base)), "hcurl_host_ndspace_elem_face_base")
         finally:
             lib.hcurl_host_ndspace_destroy(h)
-        self.elem_face_base = None
 
     def signed_elem_dofs(self):
         return self._dofs
 
     def boundary_dofs(self):
         return self._bdr
+
+
+NativeHexNDSpace = NativeNDSpace

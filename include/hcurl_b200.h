@@ -260,7 +260,7 @@ int64_t hcurl_host_patches_max_dofs(const hcurl_host_patches *p);
 int hcurl_host_patches_swizzle(const hcurl_host_patches *p, uint8_t *row, uint8_t *grp);
 int hcurl_host_patches_copy(const hcurl_host_patches *p, int32_t *perm, uint32_t *blob_off, uint32_t *blob);
 
-/* ---- host-side setup helper: ND space on a hex mesh (no GPU needed) ------------------
+/* ---- host-side setup helper: ND space on a hex or tet mesh (no GPU needed) ------------------
  * What mfem::ParFiniteElementSpace hands the assembly once ProblemBuilder::AddFESpace("ND_3D_P<p>") has run
  * (/root/reference/src/problem_builders/problem_builder_base.cpp:98-127): global edge / face enumeration and the
  * signed FiniteElementSpace::GetElementDofs map (k, or -1-k when the element sees the dof flipped), in MFEM's
@@ -268,6 +268,11 @@ int hcurl_host_patches_copy(const hcurl_host_patches *p, int32_t *perm, uint32_t
  * 8 f4); the result feeds hcurl_space_create().  elem_verts: [n_elem][8] corner ids in MFEM's hexahedron order. */
 typedef struct hcurl_host_ndspace hcurl_host_ndspace;
 hcurl_host_ndspace *hcurl_host_ndspace_create_hex(int order, int64_t n_elem, const int32_t *elem_verts);
+/* tetrahedra, orders 1..3: elem_verts [n_elem][4]; face dofs stay in the frame of the face's first occurrence (its
+ * base vertex order) -- hcurl_space_create() applies the triangle-face DofTransformation from
+ * hcurl_host_ndspace_elem_face_base() ([n_elem][4][3]; for hexes [n_elem][6][4], informational) */
+hcurl_host_ndspace *hcurl_host_ndspace_create_tet(int order, int64_t n_elem, const int32_t *elem_verts);
+int hcurl_host_ndspace_elem_face_base(const hcurl_host_ndspace *s, int32_t *out);
 void hcurl_host_ndspace_destroy(hcurl_host_ndspace *s);
 int hcurl_host_ndspace_nd(const hcurl_host_ndspace *s);          /* dofs per element, 3p(p+1)^2 */
 int64_t hcurl_host_ndspace_ndof(const hcurl_host_ndspace *s);

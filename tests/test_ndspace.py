@@ -17,14 +17,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def cpp_space(mesh, p):
     lib = L.lib()
     ev = np.ascontiguousarray(mesh.elems, dtype=np.int32)
-    h = L.check_ptr(lib.hcurl_host_ndspace_create_hex(p, len(ev), L.ptr(ev)), "ndspace")
+    create = lib.hcurl_host_ndspace_create_hex if mesh.kind == "hex" else lib.hcurl_host_ndspace_create_tet
+    h = L.check_ptr(create(p, len(ev), L.ptr(ev)), "ndspace")
     nd, ndof = lib.hcurl_host_ndspace_nd(h), lib.hcurl_host_ndspace_ndof(h)
     dofs = np.zeros((len(ev), nd), np.int32)
     L.check(lib.hcurl_host_ndspace_elem_dofs(h, L.ptr(dofs)), "elem_dofs")
     nb = lib.hcurl_host_ndspace_boundary_dofs(h, None)
     bd = np.zeros(nb, np.int32)
     assert lib.hcurl_host_ndspace_boundary_dofs(h, L.ptr(bd)) == nb
-    out = dict(nd=nd, ndof=ndof, n_edges=lib.hcurl_host_ndspace_n_edges(h), n_faces=lib.hcurl_host_ndspace_n_faces(h), dofs=dofs, bdr=bd)
+    fb = np.zeros((len(ev), 6, 4) if mesh.kind == "hex" else (len(ev), 4, 3), np.int32)
+    L.check(lib.hcurl_host_ndspace_elem_face_base(h, L.ptr(fb)), "face_base")
+    out = dict(nd=nd, ndof=ndof, n_edges=lib.hcurl_host_ndspace_n_edges(h), n_faces=lib.hcurl_host_ndspace_n_faces(h), dofs=dofs, bdr=bd,
+               face_base=fb)
     lib.hcurl_host_ndspace_destroy(h)
     return out
 
@@ -78,9 +82,38 @@ def test_bad_arguments():
     assert b"negative" in lib.hcurl_last_error()
 
 
-def test_python_wrapper_is_a_drop_in():
+@pytest.mark.parametrize("kind", ["hex", "tet"])
+def test_python_wrapper_is_a_drop_in(kind):
     mesh = scrambled(fespace.cartesian_hex_mesh(3, 4, 2))
-    a, b = fespace.NativeHexNDSpace(mesh, 2), fespace.NDSpace(mesh, 2)
+    if kind == "tet":
+        mesh = fespace.hex_to_tets(mesh)
+    a, b = fespace.NativeNDSpace(mesh, 2), fespace.NDSpace(mesh, 2)
     assert (a.nd, a.ndof, a.p) == (b.nd, b.ndof, b.p)
     assert np.array_equal(a.signed_elem_dofs(), b.signed_elem_dofs())
     assert np.array_equal(a.boundary_dofs(), b.boundary_dofs())
+    if kind == "tet":
+        assert np.array_equal(a.elem_face_base, b.elem_face_base) and a.elem_face_base.dtype == np.int32
+    else:
+        assert a.elem_face_base is None
+
+
+@pytest.mark.parametrize("p", [1, 2, 3])
+@pytest.mark.parametrize("src", ["kuhn", "beam_tet", "team7"])
+def test_tets_match_python_generator(src, p):
+    """Tetrahedra: same edge / face enumeration, dofs and per-face base vertex order (what the triangle-face
+    DofTransformation needs) as the Python generator, on a Kuhn-split cube and on the reference's tet meshes."""
+    if src == "kuhn":
+        mesh = fespace.hex_to_tets(fespace.cartesian_hex_mesh(3, 2, 4))
+    else:
+        if src == "team7" and p > 1:
+            pytest.skip("one order is enough for the large mesh")
+        z = np.load(os.path.join(ROOT, "tests", "golden", src + ".npz"))
+        mesh = fespace.Mesh("tet", z["verts"], z["elems"], z["attr"])
+    ref = fespace.NDSpace(mesh, p)
+    got = cpp_space(mesh, p)
+    assert (got["nd"], got["ndof"], got["n_edges"], got["n_faces"]) == (ref.nd, ref.ndof, ref.n_edges, ref.n_faces)
+    assert np.array_equal(got["dofs"], ref.signed_elem_dofs())
+    assert np.array_equal(got["bdr"], ref.boundary_dofs())
+    assert np.array_equal(got["face_base"], ref.elem_face_base)
+    if src == "team7":
+        assert got["ndof"] == 68547          # SURVEY.md App. C
