@@ -74,6 +74,10 @@ SIGNATURES = {
     "hcurl_host_free_pinned": (None, [_P]),
     "hcurl_dot": (C.c_int, [_P, _P, _P, C.c_int64, C.POINTER(C.c_double)]),
     "hcurl_fp64_peak_tflops": (C.c_double, [_P]),
+    "hcurl_host_exodus_open": (_P, [C.c_char_p]),
+    "hcurl_host_exodus_close": (None, [_P]),
+    "hcurl_host_exodus_counts": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "hcurl_host_exodus_read": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "hcurl_host_ndspace_create_hex": (_P, [C.c_int, C.c_int64, _P]),
     "hcurl_host_ndspace_create_tet": (_P, [C.c_int, C.c_int64, _P]),
     "hcurl_host_ndspace_elem_face_base": (C.c_int, [_P, _P]),

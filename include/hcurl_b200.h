@@ -282,6 +282,19 @@ int hcurl_host_ndspace_elem_dofs(const hcurl_host_ndspace *s, int32_t *signed_do
 /* dofs on boundary faces and their edges, ascending; returns the count (out may be NULL; room for ndof entries) */
 int64_t hcurl_host_ndspace_boundary_dofs(const hcurl_host_ndspace *s, int32_t *out);
 
+/* ---- host-side setup helper: ExodusII mesh reader (no GPU, no netCDF library needed) ----
+ * What mfem::Mesh(mesh_file) does for the reference's data/*.g / *.gen files (NetCDF classic, CDF-1/2) before the ND
+ * space is built (/root/reference/examples/team7/Main.cpp:152-155): node coordinates, element blocks (TETRA4 / HEX8 /
+ * HEX27; block id = element attribute), side sets (-> boundary faces, side-set id = attribute). */
+typedef struct hcurl_host_exodus hcurl_host_exodus;
+hcurl_host_exodus *hcurl_host_exodus_open(const char *path);
+void hcurl_host_exodus_close(hcurl_host_exodus *x);
+int hcurl_host_exodus_counts(const hcurl_host_exodus *x, int64_t *n_nodes, int64_t *n_elem, int *geom, int *nodes_per_elem,
+                             int64_t *n_side);
+/* xyz [n_nodes][3]; conn [n_elem][nodes_per_elem] 0-based, blocks in file order; attr [n_elem]; bdr [n_side][4|3]
+ * corner nodes of the side-set faces; bdr_attr [n_side].  Any output may be NULL. */
+int hcurl_host_exodus_read(const hcurl_host_exodus *x, double *xyz, int32_t *conn, int32_t *attr, int32_t *bdr, int32_t *bdr_attr);
+
 /* FP64 FMA micro-benchmark used for the roofline co-bound:
  * returns achieved TFLOP/s of dependent-chain-free DFMA on the device. */
 double hcurl_fp64_peak_tflops(hcurl_ctx *ctx);
