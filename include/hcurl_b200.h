@@ -283,8 +283,8 @@ int hcurl_host_ndspace_elem_dofs(const hcurl_host_ndspace *s, int32_t *signed_do
 int64_t hcurl_host_ndspace_boundary_dofs(const hcurl_host_ndspace *s, int32_t *out);
 
 /* ---- host-side setup helper: ExodusII mesh reader (no GPU, no netCDF library needed) ----
- * What mfem::Mesh(mesh_file) does for the reference's data/*.g / *.gen files (NetCDF classic, CDF-1/2) before the ND
- * space is built (/root/reference/examples/team7/Main.cpp:152-155): node coordinates, element blocks (TETRA4 / HEX8 /
+ * What mfem::Mesh(mesh_file) does for the .g and .gen files in the reference's data directory (NetCDF classic,
+ * CDF-1/2) before the ND space is built (/root/reference/examples/team7/Main.cpp:152-155): node coordinates, element blocks (TETRA4 / HEX8 /
  * HEX27; block id = element attribute), side sets (-> boundary faces, side-set id = attribute). */
 typedef struct hcurl_host_exodus hcurl_host_exodus;
 hcurl_host_exodus *hcurl_host_exodus_open(const char *path);
