@@ -76,6 +76,8 @@ struct hcurl_host_ndspace {
   std::vector<int32_t> face_base;   // [n_faces][nfv] vertex order of the first occurrence of every face
   std::vector<int32_t> face_count;  // elements per face (1 = boundary)
   std::vector<int> perm, sign;      // quad orientation tables [8][nfd]
+  // lookup chains (hanging off the smallest vertex) kept for queries by vertex list
+  std::vector<int32_t> e_head, e_next, e_hi, f_head, f_next, f_s1, f_s2;
 };
 
 extern "C" {
@@ -123,6 +125,7 @@ static hcurl_host_ndspace *ndspace_create(bool hex, int order, int64_t n_elem, c
         S->edge_fwd[(size_t)e * nle + le] = a < b;
       }
     S->n_edges = (int64_t)hi.size();
+    S->e_head.swap(head); S->e_next.swap(next); S->e_hi.swap(hi);
   }
   // ---- faces: identified by their three smallest vertices; the first occurrence fixes the base vertex order
   {
@@ -156,6 +159,7 @@ static hcurl_host_ndspace *ndspace_create(bool hex, int order, int64_t n_elem, c
         }
       }
     S->n_faces = (int64_t)s1.size();
+    S->f_head.swap(head); S->f_next.swap(next); S->f_s1.swap(s1); S->f_s2.swap(s2);
   }
   S->face_off = S->n_edges * S->ned;
   S->int_off = S->face_off + S->n_faces * S->nfd;
@@ -248,6 +252,42 @@ int64_t hcurl_host_ndspace_boundary_dofs(const hcurl_host_ndspace *S, int32_t *o
         for (int m = 0; m < S->ned; m++) mark[(size_t)(g + m)] = 1;
       }
     }
+  int64_t n = 0;
+  for (int64_t d = 0; d < S->ndof; d++)
+    if (mark[(size_t)d]) { if (out) out[n] = (int32_t)d; n++; }
+  return n;
+}
+
+/* Dofs on the given faces (n_faces vertex lists of 4 / 3 corner ids each, any order -- e.g. the side-set faces of
+ * hcurl_host_exodus_read) and on their edges, ascending and unique: what BCMap::GetEssentialBdrMarkers ->
+ * GetEssentialTrueDofs selects for a set of boundary attributes
+ * (/root/reference/src/boundary_conditions/boundary_conditions.cpp:32-51).  Returns the count (out may be NULL),
+ * -1 if a face or edge is not part of the mesh. */
+int64_t hcurl_host_ndspace_face_dofs(const hcurl_host_ndspace *S, int64_t n_faces, const int32_t *face_verts, int32_t *out) {
+  std::vector<uint8_t> mark((size_t)S->ndof, 0);
+  const int nfv = S->nfv;
+  const int64_t nv = (int64_t)S->e_head.size();
+  for (int64_t q = 0; q < n_faces; q++) {
+    const int32_t *v = face_verts + q * nfv;
+    for (int k = 0; k < nfv; k++)
+      if (v[k] < 0 || v[k] >= nv) { hcurl::set_error("hcurl_host_ndspace_face_dofs: vertex id out of range"); return -1; }
+    for (int k = 0; k < nfv; k++) {  // edges of the polygon
+      const int32_t a = v[k], b = v[(k + 1) % nfv], lo = std::min(a, b), hi = std::max(a, b);
+      int32_t id = S->e_head[(size_t)lo];
+      while (id >= 0 && S->e_hi[(size_t)id] != hi) id = S->e_next[(size_t)id];
+      if (id < 0) { hcurl::set_error("hcurl_host_ndspace_face_dofs: face %lld has an edge that is not in the mesh", (long long)q); return -1; }
+      for (int m = 0; m < S->ned; m++) mark[(size_t)((int64_t)id * S->ned + m)] = 1;
+    }
+    if (S->nfd) {
+      int32_t s[4];
+      for (int k = 0; k < nfv; k++) s[k] = v[k];
+      std::sort(s, s + nfv);
+      int32_t f = S->f_head[(size_t)s[0]];
+      while (f >= 0 && !(S->f_s1[(size_t)f] == s[1] && S->f_s2[(size_t)f] == s[2])) f = S->f_next[(size_t)f];
+      if (f < 0) { hcurl::set_error("hcurl_host_ndspace_face_dofs: face %lld is not in the mesh", (long long)q); return -1; }
+      for (int m = 0; m < S->nfd; m++) mark[(size_t)(S->face_off + (int64_t)f * S->nfd + m)] = 1;
+    }
+  }
   int64_t n = 0;
   for (int64_t d = 0; d < S->ndof; d++)
     if (mark[(size_t)d]) { if (out) out[n] = (int32_t)d; n++; }

@@ -368,7 +368,7 @@ class NDSpace:
         /root/reference/src/boundary_conditions/boundary_conditions.cpp:32-51)."""
         mesh = self.mesh
         sel = np.isin(mesh.bdr_attr, np.asarray(attrs))
-        b = mesh.bdr[sel]
+        b = np.asarray(mesh.bdr[sel], dtype=np.int64)   # the vertex-triple keys below overflow 32 bits
         nfv = b.shape[1]
         out = []
         # edges of the boundary polygons

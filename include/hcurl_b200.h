@@ -281,6 +281,10 @@ int64_t hcurl_host_ndspace_n_faces(const hcurl_host_ndspace *s);
 int hcurl_host_ndspace_elem_dofs(const hcurl_host_ndspace *s, int32_t *signed_dofs /* [n_elem][nd] */);
 /* dofs on boundary faces and their edges, ascending; returns the count (out may be NULL; room for ndof entries) */
 int64_t hcurl_host_ndspace_boundary_dofs(const hcurl_host_ndspace *s, int32_t *out);
+/* dofs on the given faces ([n_faces][4|3] corner ids, any order: e.g. side-set faces) and their edges -- the essential
+ * dofs BCMap::GetEssentialBdrMarkers selects (/root/reference/src/boundary_conditions/boundary_conditions.cpp:32-51);
+ * ascending; returns the count (out may be NULL), -1 if a face is not part of the mesh */
+int64_t hcurl_host_ndspace_face_dofs(const hcurl_host_ndspace *s, int64_t n_faces, const int32_t *face_verts, int32_t *out);
 
 /* ---- host-side setup helper: ExodusII mesh reader (no GPU, no netCDF library needed) ----
  * What mfem::Mesh(mesh_file) does for the .g and .gen files in the reference's data directory (NetCDF classic,

@@ -117,3 +117,32 @@ def test_tets_match_python_generator(src, p):
     assert np.array_equal(got["face_base"], ref.elem_face_base)
     if src == "team7":
         assert got["ndof"] == 68547
+
+
+@pytest.mark.parametrize("name,p", [("team7", 1), ("cylinder_hex_q2", 2), ("cylinder_hex_q2", 1), ("beam_tet", 2)])
+def test_sideset_dofs_match_python(name, p):
+    """Essential dofs of a set of boundary attributes (side sets of the reference's meshes) as the Python generator's
+    sideset_dofs() selects them."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    if "bdr" not in z.files or z["bdr"].ndim != 2 or len(z["bdr"]) == 0:
+        pytest.skip("fixture has no boundary elements")
+    kind = str(z["kind"])
+    mesh = fespace.Mesh(kind, z["verts"], z["elems"], z["attr"], None, z["bdr"], z["bdr_attr"])
+    ref = fespace.NDSpace(mesh, p)
+    attrs = np.unique(z["bdr_attr"])[:2]
+    want = ref.sideset_dofs(attrs)
+    faces = np.ascontiguousarray(z["bdr"][np.isin(z["bdr_attr"], attrs)], dtype=np.int32)
+    lib = L.lib()
+    ev = np.ascontiguousarray(mesh.elems, dtype=np.int32)
+    create = lib.hcurl_host_ndspace_create_hex if kind == "hex" else lib.hcurl_host_ndspace_create_tet
+    h = L.check_ptr(create(p, len(ev), L.ptr(ev)), "ndspace")
+    n = lib.hcurl_host_ndspace_face_dofs(h, len(faces), L.ptr(faces), None)
+    assert n == len(want)
+    got = np.zeros(n, np.int32)
+    assert lib.hcurl_host_ndspace_face_dofs(h, len(faces), L.ptr(faces), L.ptr(got)) == n
+    assert np.array_equal(got, want)
+    bad = faces[:1].copy()
+    bad[0, 0] = int(ev.max())  # most likely not a face of the mesh
+    if lib.hcurl_host_ndspace_face_dofs(h, 1, L.ptr(bad), None) < 0:
+        assert b"not in the mesh" in lib.hcurl_last_error()
+    lib.hcurl_host_ndspace_destroy(h)
