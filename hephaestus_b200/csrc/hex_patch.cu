@@ -50,16 +50,6 @@ struct ModalTables {
 };
 __constant__ ModalTables cM;
 
-int hex_rot_slot_to_tensor(int p, int slot) {
-  const int p1 = p + 1, nc = p * p1 * p1;
-  const int c = slot / nc, t = slot % nc;
-  int ir[3] = {t % p, (t / p) % p1, t / (p * p1)};  // along axes c, c+1, c+2
-  int idx[3];
-  for (int k = 0; k < 3; k++) idx[(c + k) % 3] = ir[k];
-  const int n0 = (c == 0) ? p : p1, n1 = (c == 1) ? p : p1;
-  return c * nc + idx[0] + n0 * (idx[1] + n1 * idx[2]);
-}
-
 __device__ __forceinline__ int sym6(int i, int j) {  // packed index of the symmetric pair (i,j)
   const int lo = min(i, j), hi = max(i, j);
   return lo * 3 - lo * (lo - 1) / 2 + (hi - lo);
@@ -940,37 +930,18 @@ int hex_patch_build(hcurl_space *sp, const double *elem_xyz, const int32_t *elem
   int FE = 32;  // 32-element patches, 4 CTAs of 96 threads per SM: fastest of 32 / 64 / 128 (profiles/README.md)
   if (const char *s = getenv("HCURL_PATCH_FE")) FE = atoi(s);
   if (FE != 32 && FE != 64 && FE != 128) { set_error("HCURL_PATCH_FE must be 32, 64 or 128"); return 1; }
-  const int nd = sp->nd, p = sp->order, np = nd / 2;
+  const int np = sp->nd / 2;
   const int64_t ne = sp->n_elem;
   if (sp->n_ext() & 1) return 0;
-  std::vector<int> loc, sgn;
-  nd_hex_dof_map(p, loc, sgn);
-  std::vector<int> tens(nd);
-  for (int s = 0; s < nd; s++) tens[s] = hex_rot_slot_to_tensor(p, s);
   std::vector<uint32_t> code((size_t)ne * np);
+  if (hex_p2_pair_codes(ne, elem_ldof, l2e, code.data())) return 0;  // not aligned pairs: no patch path for this space
   std::vector<double> cen((size_t)ne * 3);
-  for (int64_t e = 0; e < ne; e++) {
-    for (int r = 0; r < np; r++) {
-      uint32_t ext[2];
-      bool neg[2];
-      for (int h = 0; h < 2; h++) {
-        const int t = tens[2 * r + h];
-        const int32_t v = elem_ldof[e * nd + loc[t]];
-        const int32_t kk = v >= 0 ? v : -1 - v;
-        neg[h] = (v < 0) != (sgn[t] < 0);
-        ext[h] = l2e ? (uint32_t)l2e[kk] : (uint32_t)kk;
-      }
-      const bool swap = ext[0] > ext[1];
-      const uint32_t lo = swap ? ext[1] : ext[0], hi = swap ? ext[0] : ext[1];
-      if ((lo & 1u) || hi != lo + 1) return 0;  // not an aligned pair: no patch path for this space
-      code[(size_t)e * np + r] = (lo >> 1) | (swap ? PAIR_SWAP : 0u) | (neg[0] ? PAIR_NEG0 : 0u) | (neg[1] ? PAIR_NEG1 : 0u);
-    }
+  for (int64_t e = 0; e < ne; e++)
     for (int d = 0; d < 3; d++) {
       double c = 0.0;
       for (int v = 0; v < 8; v++) c += elem_xyz[(e * 8 + v) * 3 + d];
       cen[(size_t)e * 3 + d] = 0.125 * c;
     }
-  }
   // pairs that take part in the inter-rank exchange: ghosts, and owned pairs other ranks hold as ghosts
   std::vector<uint8_t> xch;
   if (sp->n_nbr > 0) {

@@ -93,6 +93,8 @@ int build_patches(int nd, int64_t n_elem, int FE, int stride, int unit_bytes, in
                   const uint32_t *slot_code, const uint8_t *exchange_units, PatchHost &out);
 // slot s of the rotated per-component layout (hex_patch.cu) -> standard tensor index
 int hex_rot_slot_to_tensor(int p, int slot);
+// dof pairs of an order-2 hex space (patch.cpp); returns 1 when the map is not made of aligned pairs
+int hex_p2_pair_codes(int64_t n_elem, const int32_t *elem_ldof, const int32_t *l2e, uint32_t *code);
 
 struct PatchSet {  // device copy
   int FE = 0;

@@ -416,6 +416,47 @@ int build_patches(int nd, int64_t n_elem, int FE, int stride, int unit_bytes, in
   return 0;
 }
 
+int hex_rot_slot_to_tensor(int p, int slot) {
+  const int p1 = p + 1, nc = p * p1 * p1;
+  const int c = slot / nc, t = slot % nc;
+  int ir[3] = {t % p, (t / p) % p1, t / (p * p1)};  // along axes c, c+1, c+2
+  int idx[3];
+  for (int k = 0; k < 3; k++) idx[(c + k) % 3] = ir[k];
+  const int n0 = (c == 0) ? p : p1, n1 = (c == 1) ? p : p1;
+  return c * nc + idx[0] + n0 * (idx[1] + n1 * idx[2]);
+}
+
+// Pair codes of an order-2 hex space (the units of the patch kernel, hex_patch.cu): in the rotated slot layout the
+// slots 2r, 2r+1 of an element are the two dofs along one line; they must be the doubles 2q, 2q+1 of the (extended)
+// vector, in this order or swapped, each with its own sign.  code[e][r] = q | PAIR_SWAP | PAIR_NEG0 | PAIR_NEG1.
+// Returns 1 (and leaves code partly written) when some slot pair does not have this structure.
+int hex_p2_pair_codes(int64_t n_elem, const int32_t *elem_ldof, const int32_t *l2e, uint32_t *code) {
+  const int p = 2, nd = 54, np = 27;
+  std::vector<int> loc, sgn;
+  nd_hex_dof_map(p, loc, sgn);
+  int tens[54];
+  for (int s = 0; s < nd; s++) tens[s] = hex_rot_slot_to_tensor(p, s);
+  std::atomic<int> bad(0);
+  parallel_for(n_elem, [&](int64_t e) {
+    for (int r = 0; r < np; r++) {
+      uint32_t ext[2];
+      bool neg[2];
+      for (int h = 0; h < 2; h++) {
+        const int t = tens[2 * r + h];
+        const int32_t v = elem_ldof[e * nd + loc[t]];
+        const int32_t kk = v >= 0 ? v : -1 - v;
+        neg[h] = (v < 0) != (sgn[t] < 0);
+        ext[h] = l2e ? (uint32_t)l2e[kk] : (uint32_t)kk;
+      }
+      const bool swap = ext[0] > ext[1];
+      const uint32_t lo = swap ? ext[1] : ext[0], hi = swap ? ext[0] : ext[1];
+      if ((lo & 1u) || hi != lo + 1) { bad.store(1); return; }
+      code[(size_t)e * np + r] = (lo >> 1) | (swap ? PAIR_SWAP : 0u) | (neg[0] ? PAIR_NEG0 : 0u) | (neg[1] ? PAIR_NEG1 : 0u);
+    }
+  });
+  return bad.load();
+}
+
 }  // namespace hcurl
 
 // ---- host-only C entry points (declared in include/hcurl_b200.h): the patch builder can be
@@ -434,6 +475,13 @@ hcurl_host_patches *hcurl_host_patches_create(int nd, int64_t n_elem, int elems_
   return p;
 }
 void hcurl_host_patches_destroy(hcurl_host_patches *p) { delete p; }
+/* order-2 hex space: the 27 dof pairs of every element as the patch kernel uses them (see hex_p2_pair_codes above);
+ * returns 0, or 1 when the map does not consist of aligned pairs (the operator then uses the element-wise kernels) */
+int hcurl_host_hex_p2_pair_codes(int64_t n_elem, const int32_t *elem_ldof, uint32_t *codes) {
+  if (n_elem <= 0 || !elem_ldof || !codes) { hcurl::set_error("hcurl_host_hex_p2_pair_codes: bad arguments"); return 1; }
+  if (hcurl::hex_p2_pair_codes(n_elem, elem_ldof, nullptr, codes)) { hcurl::set_error("the element -> dof map does not consist of aligned dof pairs"); return 1; }
+  return 0;
+}
 int64_t hcurl_host_patches_count(const hcurl_host_patches *p) { return p->h.n_patch; }
 int64_t hcurl_host_patches_boundary_count(const hcurl_host_patches *p) { return p->h.n_boundary; }
 /* total blob size in 32-bit words; largest single patch blob in words */

@@ -244,6 +244,11 @@ int hcurl_dot(hcurl_ctx *ctx, const double *a_dev, const double *b_dev, int64_t 
  *             blob_off [n_patch+1] start of each patch blob in 16-byte units; blob: per patch a
  *             16-word header, the unit list, the 16/32/64-bit slot-entry sections (dof side) and the
  *             per-slot local unit index table (element side); layout in hephaestus_b200/csrc/patch.cpp. */
+/* Order-2 hex spaces: the 27 dof pairs of every element (the 16-byte units of the patch kernel): codes[e][r] = pair
+ * index q (doubles 2q, 2q+1 of the vector) | bit 29 swap | bit 30 sign flip of the second local dof | bit 31 sign
+ * flip of the first.  elem_ldof [n_elem][54] as for hcurl_space_create.  Returns 0, or 1 when the map does not
+ * consist of aligned pairs (such spaces use the element-wise kernels). */
+int hcurl_host_hex_p2_pair_codes(int64_t n_elem, const int32_t *elem_ldof, uint32_t *codes);
 typedef struct hcurl_host_patches hcurl_host_patches;
 hcurl_host_patches *hcurl_host_patches_create(int nd, int64_t n_elem, int elems_per_patch, int slot_stride,
                                               int unit_bytes, int64_t n_dof, const double *centroid,
