@@ -36,6 +36,7 @@
 #include <cstring>
 
 #include "internal.h"
+#include "patch_dev.cuh"
 
 namespace hcurl {
 
@@ -163,92 +164,12 @@ __device__ __forceinline__ void modal_op(const double *Am, const double *Bm, con
 #undef DD
 }
 
-struct PatchArgs {
-  int64_t n_patch;           // patches [k_begin, n_patch) are processed by this launch
-  int64_t k_begin;
-  int dot_add;               // fused dot product: add to *dot_out instead of storing (second / third launch of an apply)
-  const uint32_t *blob_off;  // [n_patch+1] in 16-byte units
-  const uint32_t *blob;      // patch blobs (patch.cpp)
-  const double *edata;       // [n_patch][12][FE] affine geometry factors in patch order
-  const double *x;
-  double *y;
-  double scale;
-  uint32_t blob_cap_bytes;   // shared-memory room reserved for one blob (multiple of 16)
-  uint32_t xs_cap_bytes;     // room for the x staging vector (max patch pairs * 16)
-  // split-blob variant: begin of the slot-offset lists and of the per-slot table of every patch (16-byte units, absolute),
-  // room for one header + pair list, and for one set of lists
-  const uint32_t *part_off;
-  uint32_t d_cap_bytes, l_cap_bytes;
-  // fused <x, y> (PCG's <p, A p>): per-CTA partial sums, arrival counter, result (null = not wanted)
-  double *dot_partial;
-  unsigned int *dot_counter;
-  double *dot_out;
-  // EY position of (slot pair s, element e) is s*(FE+1) + (e ^ swz_row[s] ^ swz_grp[e >> 3]): chosen by patch.cpp so
-  // that the dof side's reads of EY spread over the banks
-  uint8_t swz_row[27], swz_grp[16];
-  unsigned long long *prof;  // null, or 8 counters: cycles of thread 0 per phase summed over patches (scripts/phase_profile.py)
-};
 #define PROF_MARK(i)                                                                         \
   if (PROF && tid == 0) {                                                                    \
     const long long t_now = clock64();                                                       \
     prof_acc[i] += (unsigned long long)(t_now - t_prev);                                     \
     t_prev = t_now;                                                                          \
   }
-
-// orientation of an element slot pair relative to its global pair, carried in bits 13..15 of a lidx entry
-// (PAIR_SWAP / PAIR_NEG1 / PAIR_NEG0 of the slot code >> 16): local = (s0 * g[swap], s1 * g[!swap])
-__device__ __forceinline__ double flip(double v, uint32_t sign_bit31) {
-  return __hiloint2double(__double2hiint(v) ^ (int)sign_bit31, __double2loint(v));
-}
-__device__ __forceinline__ void pair_to_local(const double2 g, const uint32_t l, double &x0, double &x1) {
-  const bool sw = l & 0x2000u;
-  x0 = flip(sw ? g.y : g.x, (l << 16) & 0x80000000u);
-  x1 = flip(sw ? g.x : g.y, (l << 17) & 0x80000000u);
-}
-__device__ __forceinline__ double2 local_to_pair(const double y0, const double y1, const uint32_t l) {
-  const bool sw = l & 0x2000u;
-  const double a = flip(y0, (l << 16) & 0x80000000u), b = flip(y1, (l << 17) & 0x80000000u);
-  return sw ? make_double2(b, a) : make_double2(a, b);
-}
-
-// ---- async copies -----------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *mbar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(mbar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *mbar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(mbar)), "r"(bytes) : "memory");
-}
-// 1-D bulk copy through the TMA engine, completion counted on an mbarrier
-__device__ __forceinline__ void bulk_load(uint64_t *mbar, void *dst, const void *src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
-               "l"(src), "r"(bytes), "r"(smem_addr(mbar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *mbar, uint32_t parity) {
-  const uint32_t mb = smem_addr(mbar);
-  uint32_t done;
-  do {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(done)
-                 : "r"(mb), "r"(parity)
-                 : "memory");
-  } while (!done);
-}
-// 16-byte asynchronous gather global -> shared (LDGSTS, L1 bypassed), no register staging.  (The L1-allocating
-// .ca form was measured 7-9 % slower per apply although ncu counts fewer shared-memory wavefronts for it; staging
-// through registers -- LDG.128 where the gather is issued, STS.128 at the end of the iteration -- 57 % slower.)
-__device__ __forceinline__ void gather16_async(double2 *dst, const double2 *src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
-}
-// fire-and-forget FP64 add (REDG).  Spelled in PTX: once a kernel variant contains fences (the fused dot product's
-// last-CTA reduction) nvcc turns atomicAdd() with an unused result into returning ATOMG, which made that variant
-// 37 % slower.
-__device__ __forceinline__ void red_add(double *p, double v) {
-  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
-}
-__device__ __forceinline__ void gather_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void gather_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // Persistent, software-pipelined patch kernel.  One CTA walks patches k = blockIdx.x, += gridDim.x.
 // While patch i is being computed, the blob of patch i+1 (TMA bulk copy, issued an iteration ago)
@@ -866,6 +787,16 @@ __global__ void patch_flag_kernel(const uint32_t *__restrict__ blob_off, const d
   }
 }
 
+// single-dof units (order 1): one flag per unit
+__global__ void patch_flag8_kernel(const uint32_t *__restrict__ blob_off, const double *__restrict__ flag, uint32_t *__restrict__ blob) {
+  uint32_t *B = blob + (size_t)blob_off[blockIdx.x] * 4;
+  const uint32_t U = B[0];
+  for (uint32_t u = threadIdx.x; u < U; u += blockDim.x) {
+    const uint32_t m = B[PatchHost::HDR + u];
+    if (flag[m & PATCH_IDX] != 0.0) B[PatchHost::HDR + u] = m | PATCH_ESS0;
+  }
+}
+
 unsigned long long *g_patch_prof = nullptr;  // set by hcurl_debug_patch_profile (debug.cu)
 static bool g_modal_set = false;
 static int set_modal_tables() {
@@ -923,7 +854,59 @@ static size_t patch_smem_bytes(int FE, uint32_t max_blob_words, uint32_t max_uni
 // extended vector -- in this order, or swapped when the element sees the line reversed -- each with its
 // own sign.  Checked here for every element slot pair; a map that does not have this structure (or an
 // odd-length vector) simply does not get the patch path.
+// Order-1 spaces (hex_patch_p1.cu): units are single doubles, one thread per element.  Opt-in (HCURL_PATCH_P1=1) until
+// the kernel's device environment has been run on a GPU; affine elements only (the check is done here, on the host).
+static int hex_patch_build_p1(hcurl_space *sp, const double *elem_xyz, const int32_t *elem_ldof, const int32_t *l2e) {
+  const char *on = getenv("HCURL_PATCH_P1");
+  if (!(on && on[0] == '1')) return 0;
+  int FE = 128;
+  if (const char *s = getenv("HCURL_PATCH_FE")) FE = atoi(s);
+  if (FE != 32 && FE != 64 && FE != 128 && FE != 256) { set_error("HCURL_PATCH_FE must be 32, 64, 128 or 256 for order 1"); return 1; }
+  const int64_t ne = sp->n_elem;
+  std::vector<double> cen((size_t)ne * 3);
+  bool affine = true;
+  for (int64_t e = 0; e < ne; e++) {
+    const double *X = elem_xyz + e * 24;  // MFEM corner order: 0 1 2 3 bottom face, 4 5 6 7 top
+    double h2 = 0.0, dev2 = 0.0;
+    for (int d = 0; d < 3; d++) {
+      double c = 0.0;
+      for (int v = 0; v < 8; v++) c += X[v * 3 + d];
+      cen[(size_t)e * 3 + d] = 0.125 * c;
+      const double ex = X[3 + d] - X[d], ey = X[9 + d] - X[d], ez = X[12 + d] - X[d];
+      h2 = std::max(h2, std::max(ex * ex, std::max(ey * ey, ez * ez)));
+      const double pred[8] = {X[d], X[d] + ex, X[d] + ex + ey, X[d] + ey, X[d] + ez, X[d] + ex + ez, X[d] + ex + ey + ez, X[d] + ey + ez};
+      for (int v = 0; v < 8; v++) dev2 = std::max(dev2, (X[v * 3 + d] - pred[v]) * (X[v * 3 + d] - pred[v]));
+    }
+    if (dev2 > 1e-26 * h2) { affine = false; break; }  // same tolerance as fast_affine_kernel (hex_fast.cu)
+  }
+  if (!affine) return 0;
+  std::vector<uint32_t> code((size_t)ne * 12);
+  hex_slot_codes(1, ne, elem_ldof, l2e, code.data());
+  std::vector<uint8_t> xch;
+  if (sp->n_nbr > 0) {
+    xch.assign((size_t)sp->n_ext(), 0);
+    for (int64_t u = sp->n_tdof; u < sp->n_ext(); u++) xch[(size_t)u] = 1;
+    for (int32_t d : sp->own_ext) xch[(size_t)d] = 1;
+  }
+  PatchHost H;
+  if (build_patches(12, ne, FE, FE + 1, 8, sp->n_ext(), cen.data(), code.data(), xch.empty() ? nullptr : xch.data(), H)) return 1;
+  if (H.max_dofs > 8191) return 0;  // 13-bit staging positions
+  HC_CUDA(cudaSetDevice(sp->ctx->device));
+  PatchSet &P = sp->patch;
+  P.FE = FE; P.unit = 8; P.affine = true; P.stride = H.stride; P.n_patch = H.n_patch; P.n_boundary = H.n_boundary;
+  P.blob_words = (int64_t)H.blob.size(); P.max_blob_words = H.max_blob_words; P.max_dofs = H.max_dofs;
+  for (size_t i = 0; i < 27; i++) P.swz_row[i] = i < H.swz_row.size() ? H.swz_row[i] : 0;
+  for (size_t i = 0; i < 16; i++) P.swz_grp[i] = i < H.swz_grp.size() ? H.swz_grp[i] : 0;
+  const uint32_t blob_cap = (H.max_blob_words * 4 + 15u) & ~15u, xs_cap = (H.max_dofs * 8u + 15u) & ~15u;
+  if (patch_p1_smem_bytes(FE, blob_cap, xs_cap) > 227 * 1024) return 0;
+  if (upload(P.d_perm, H.perm) || upload(P.d_blob_off, H.blob_off) || upload(P.d_blob, H.blob) || upload(P.d_shared, H.shared_lines)) return 1;
+  P.n_shared = (int64_t)H.shared_lines.size();
+  sp->has_patches = true;
+  return 0;
+}
+
 int hex_patch_build(hcurl_space *sp, const double *elem_xyz, const int32_t *elem_ldof, const int32_t *l2e) {
+  if (sp->geom == HCURL_GEOM_HEX && sp->order == 1 && sp->geom_order == 1) return hex_patch_build_p1(sp, elem_xyz, elem_ldof, l2e);
   if (sp->geom != HCURL_GEOM_HEX || sp->order != 2 || sp->geom_order != 1) return 0;
   const char *off = getenv("HCURL_NO_PATCH");
   if (off && off[0] == '1') return 0;
@@ -978,10 +961,12 @@ void hex_patch_free(hcurl_space *sp) {
 
 bool hex_patch_eligible(const hcurl_op *op) {
   const hcurl_space *sp = op->sp;
-  if (!(sp->has_patches && op->single_rule && op->qc == 3 && op->coef_layout == HCURL_COEF_PER_ELEM && op->has_alpha &&
+  // the modal operator is exact where the (p+1)-point rule is: that is the rule it stands in for
+  if (!(sp->has_patches && op->single_rule && op->qc == sp->order + 1 && op->coef_layout == HCURL_COEF_PER_ELEM && op->has_alpha &&
         op->has_beta))
     return false;
   if (op->kernel_sel == 1 || op->kernel_sel == 2) return false;
+  if (sp->patch.unit == 8) return sp->patch.affine;  // order 1: classified on the host when the patches were built
   // affine meshes only (modal operator); checked lazily by hex_fast_prepare_space
   if (!sp->fast_ready && hex_fast_prepare_space(const_cast<hcurl_space *>(sp))) return false;
   return sp->all_affine;
@@ -1060,7 +1045,7 @@ int hex_patch_launch(hcurl_op *op, bool constrained, const double *d_x, double *
   hcurl_space *sp = op->sp;
   hcurl_ctx *ctx = op->ctx;
   PatchSet &P = sp->patch;
-  if (set_modal_tables()) return 1;
+  if (P.unit == 16 && set_modal_tables()) return 1;
   const int64_t n_pos = P.n_patch * P.FE;
   if (!op->edataP_valid) {
     if (!op->d_edataP) HC_CUDA(cudaMalloc(&op->d_edataP, sizeof(double) * 12 * n_pos));
@@ -1074,13 +1059,20 @@ int hex_patch_launch(hcurl_op *op, bool constrained, const double *d_x, double *
   if (a.n_patch <= a.k_begin) return 0;
   a.blob = (constrained && op->d_blob_ess) ? op->d_blob_ess : P.d_blob;
   a.blob_cap_bytes = (P.max_blob_words * 4 + 15u) & ~15u;
-  a.xs_cap_bytes = P.max_dofs * 16u;
+  a.xs_cap_bytes = P.unit == 8 ? ((P.max_dofs * 8u + 15u) & ~15u) : P.max_dofs * 16u;
   a.edata = op->d_edataP; a.x = d_x; a.y = d_y; a.scale = scale;
   a.prof = g_patch_prof;
   memcpy(a.swz_row, P.swz_row, sizeof(a.swz_row)); memcpy(a.swz_grp, P.swz_grp, sizeof(a.swz_grp));
   a.dot_out = d_dot; a.dot_partial = ctx->d_partial; a.dot_counter = ctx->d_counter;
   if (d_dot && ctx->n_partial < 8 * ctx->sm_count) { set_error("reduction scratch too small for the patch grid"); return 1; }
   if (a.prof && accumulate) a.prof = nullptr;
+  if (P.unit == 8) {  // order 1
+    a.prof = nullptr; a.part_off = nullptr; a.d_cap_bytes = a.l_cap_bytes = 0;
+    if (hex_patch_p1_launch(op, a, accumulate)) return 1;
+    HC_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+  }
   a.part_off = P.d_part_off;
   a.d_cap_bytes = (P.max_d_words * 4 + 15u) & ~15u;
   a.l_cap_bytes = (P.max_l_words * 4 + 15u) & ~15u;
@@ -1108,12 +1100,27 @@ __global__ void patch_zero_shared_kernel(const int64_t n_lines, const uint32_t *
   if (q < n_pairs) y2[q] = make_double2(0.0, 0.0);
 }
 
+// the same for single-dof units (order 1): sixteen lanes per 128-byte line
+__global__ void patch_zero_shared8_kernel(const int64_t n_lines, const uint32_t *__restrict__ line, double *__restrict__ y, const int64_t n) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_lines * 16) return;
+  const int64_t q = (int64_t)line[t >> 4] * 16 + (t & 15);
+  if (q < n) y[q] = 0.0;
+}
+
 // Private pairs are stored, shared pairs are RED-added by the patch kernel: only the latter need to start from zero.
 // Whole 128-byte lines holding a shared pair are cleared (full-sector writes; private pairs in them are stored later by
 // the kernel anyway) instead of all of y.
 int hex_patch_zero_shared(hcurl_op *op, double *d_y) {
   PatchSet &P = op->sp->patch;
   if (P.n_shared == 0) return 0;
+  if (P.unit == 8) {
+    const int64_t n = P.n_shared * 16;
+    patch_zero_shared8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, op->ctx->stream>>>(P.n_shared, P.d_shared, d_y, op->sp->n_ext());
+    HC_CUDA(cudaGetLastError());
+    op->ctx->launches++;
+    return 0;
+  }
   const int64_t nt = P.n_shared * 8;
   patch_zero_shared_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, op->ctx->stream>>>(P.n_shared, P.d_shared, reinterpret_cast<double2 *>(d_y),
                                                                                      op->sp->n_ext() / 2);
@@ -1130,7 +1137,8 @@ int hex_patch_flag_essential(hcurl_op *op, const double *d_flag) {
   cudaFree(op->d_blob_ess); op->d_blob_ess = nullptr;
   HC_CUDA(cudaMalloc(&op->d_blob_ess, sizeof(uint32_t) * P.blob_words));
   HC_CUDA(cudaMemcpyAsync(op->d_blob_ess, P.d_blob, sizeof(uint32_t) * P.blob_words, cudaMemcpyDeviceToDevice, op->ctx->stream));
-  patch_flag_kernel<<<(unsigned)P.n_patch, 128, 0, op->ctx->stream>>>(P.d_blob_off, d_flag, op->d_blob_ess);
+  if (P.unit == 8) patch_flag8_kernel<<<(unsigned)P.n_patch, 128, 0, op->ctx->stream>>>(P.d_blob_off, d_flag, op->d_blob_ess);
+  else patch_flag_kernel<<<(unsigned)P.n_patch, 128, 0, op->ctx->stream>>>(P.d_blob_off, d_flag, op->d_blob_ess);
   HC_CUDA(cudaGetLastError());
   return 0;
 }

@@ -95,9 +95,13 @@ int build_patches(int nd, int64_t n_elem, int FE, int stride, int unit_bytes, in
 int hex_rot_slot_to_tensor(int p, int slot);
 // dof pairs of an order-2 hex space (patch.cpp); returns 1 when the map is not made of aligned pairs
 int hex_p2_pair_codes(int64_t n_elem, const int32_t *elem_ldof, const int32_t *l2e, uint32_t *code);
+// single-dof slot codes of a hex space of order p in tensor order (component-major, x fastest): extended index | bit 31 = sign flip
+void hex_slot_codes(int p, int64_t n_elem, const int32_t *elem_ldof, const int32_t *l2e, uint32_t *code);
 
 struct PatchSet {  // device copy
   int FE = 0;
+  int unit = 16;                 // bytes per unit of the dof side: 16 = aligned dof pair (order 2), 8 = single dof (order 1)
+  bool affine = false;           // order-1 path: every element is a parallelepiped (checked on the host at build time)
   int64_t n_patch = 0, n_pd = 0, n_boundary = 0;
   int32_t *d_perm = nullptr;
   int stride = 0;
@@ -110,6 +114,33 @@ struct PatchSet {  // device copy
   uint8_t swz_row[27] = {0}, swz_grp[16] = {0};
   uint32_t *d_shared = nullptr;  // 128-byte lines holding RED-added pairs: the only part of y that must be zero before an apply
   int64_t n_shared = 0;
+};
+
+// Kernel arguments of the patch kernels (hex_patch.cu: order 2, 16-byte units; hex_patch_p1.cu: order 1, 8-byte units)
+struct PatchArgs {
+  int64_t n_patch;           // patches [k_begin, n_patch) are processed by this launch
+  int64_t k_begin;
+  int dot_add;               // fused dot product: add to *dot_out instead of storing (second / third launch of an apply)
+  const uint32_t *blob_off;  // [n_patch+1] in 16-byte units
+  const uint32_t *blob;      // patch blobs (patch.cpp)
+  const double *edata;       // [n_patch][12][FE] affine geometry factors in patch order
+  const double *x;
+  double *y;
+  double scale;
+  uint32_t blob_cap_bytes;   // shared-memory room reserved for one blob (multiple of 16)
+  uint32_t xs_cap_bytes;     // room for the x staging vector (max patch pairs * 16)
+  // split-blob variant: begin of the slot-offset lists and of the per-slot table of every patch (16-byte units, absolute),
+  // room for one header + pair list, and for one set of lists
+  const uint32_t *part_off;
+  uint32_t d_cap_bytes, l_cap_bytes;
+  // fused <x, y> (PCG's <p, A p>): per-CTA partial sums, arrival counter, result (null = not wanted)
+  double *dot_partial;
+  unsigned int *dot_counter;
+  double *dot_out;
+  // EY position of (slot pair s, element e) is s*(FE+1) + (e ^ swz_row[s] ^ swz_grp[e >> 3]): chosen by patch.cpp so
+  // that the dof side's reads of EY spread over the banks
+  uint8_t swz_row[27], swz_grp[16];
+  unsigned long long *prof;  // null, or 8 counters: cycles of thread 0 per phase summed over patches (scripts/phase_profile.py)
 };
 
 // ----------------------------------------------------------------- NCCL ----
@@ -232,6 +263,9 @@ int hex_patch_launch(hcurl_op *op, bool constrained, const double *d_x, double *
 int hex_patch_flag_essential(hcurl_op *op, const double *d_flag);
 // zero what the patch kernel accumulates into (instead of clearing all of y)
 int hex_patch_zero_shared(hcurl_op *op, double *d_y);
+// order-1 patch kernel (hex_patch_p1.cu; opt-in with HCURL_PATCH_P1=1 until it has been run on a GPU)
+int hex_patch_p1_launch(hcurl_op *op, const hcurl::PatchArgs &a, bool accumulate);
+size_t patch_p1_smem_bytes(int FE, uint32_t blob_cap_bytes, uint32_t xs_cap_bytes);
 int hex_fast_prepare_space(hcurl_space *sp);
 int tet_build_emat(hcurl_op *op);
 int tet_apply_launch(hcurl_op *op, const uint32_t *d_map, const double *d_x, double *d_y, double scale);

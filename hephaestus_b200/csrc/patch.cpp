@@ -457,6 +457,21 @@ int hex_p2_pair_codes(int64_t n_elem, const int32_t *elem_ldof, const int32_t *l
   return bad.load();
 }
 
+// Single-dof slot codes in tensor order (the 8-byte units of the order-1 patch kernel, hex_patch_p1.cu).
+void hex_slot_codes(int p, int64_t n_elem, const int32_t *elem_ldof, const int32_t *l2e, uint32_t *code) {
+  const int nd = nd_hex_ndof(p);
+  std::vector<int> loc, sgn;
+  nd_hex_dof_map(p, loc, sgn);
+  parallel_for(n_elem, [&](int64_t e) {
+    for (int t = 0; t < nd; t++) {
+      const int32_t v = elem_ldof[e * nd + loc[t]];
+      const int32_t kk = v >= 0 ? v : -1 - v;
+      const bool neg = (v < 0) != (sgn[t] < 0);
+      code[(size_t)e * nd + t] = (l2e ? (uint32_t)l2e[kk] : (uint32_t)kk) | (neg ? 0x80000000u : 0u);
+    }
+  });
+}
+
 }  // namespace hcurl
 
 // ---- host-only C entry points (declared in include/hcurl_b200.h): the patch builder can be
@@ -480,6 +495,11 @@ void hcurl_host_patches_destroy(hcurl_host_patches *p) { delete p; }
 int hcurl_host_hex_p2_pair_codes(int64_t n_elem, const int32_t *elem_ldof, uint32_t *codes) {
   if (n_elem <= 0 || !elem_ldof || !codes) { hcurl::set_error("hcurl_host_hex_p2_pair_codes: bad arguments"); return 1; }
   if (hcurl::hex_p2_pair_codes(n_elem, elem_ldof, nullptr, codes)) { hcurl::set_error("the element -> dof map does not consist of aligned dof pairs"); return 1; }
+  return 0;
+}
+int hcurl_host_hex_slot_codes(int order, int64_t n_elem, const int32_t *elem_ldof, uint32_t *codes) {
+  if (order < 1 || order > 4 || n_elem <= 0 || !elem_ldof || !codes) { hcurl::set_error("hcurl_host_hex_slot_codes: bad arguments"); return 1; }
+  hcurl::hex_slot_codes(order, n_elem, elem_ldof, nullptr, codes);
   return 0;
 }
 int64_t hcurl_host_patches_count(const hcurl_host_patches *p) { return p->h.n_patch; }

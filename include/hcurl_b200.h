@@ -249,6 +249,11 @@ int hcurl_dot(hcurl_ctx *ctx, const double *a_dev, const double *b_dev, int64_t 
  * flip of the first.  elem_ldof [n_elem][54] as for hcurl_space_create.  Returns 0, or 1 when the map does not
  * consist of aligned pairs (such spaces use the element-wise kernels). */
 int hcurl_host_hex_p2_pair_codes(int64_t n_elem, const int32_t *elem_ldof, uint32_t *codes);
+/* Hex spaces of any order 1..4: single-dof slot codes in the kernels' tensor order (component-major, x fastest, the
+ * order of the device map): codes[e][t] = dof index | bit 31 sign flip (MFEM's -1-k encoding of
+ * FiniteElementSpace::GetElementDofs combined with the fixed sign of the local basis function).  The 8-byte units of
+ * the order-1 patch kernel.  elem_ldof [n_elem][nd] as for hcurl_space_create. */
+int hcurl_host_hex_slot_codes(int order, int64_t n_elem, const int32_t *elem_ldof, uint32_t *codes);
 typedef struct hcurl_host_patches hcurl_host_patches;
 hcurl_host_patches *hcurl_host_patches_create(int nd, int64_t n_elem, int elems_per_patch, int slot_stride,
                                               int unit_bytes, int64_t n_dof, const double *centroid,

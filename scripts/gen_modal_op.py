@@ -134,8 +134,85 @@ def emit(p):
                 print("yh[%2d] = fma(G%s%s * %+.17g, xh[%2d], yh[%2d]);" % (i, kind, names[(a, b)], H[i, j], j, i))
 
 
+def _snap(values, rel=1e-13):
+    """magnitudes that differ only by rounding noise become one constant (the mean of the cluster)"""
+    mags = sorted({abs(float(v)) for v in values if abs(v) > 1e-14})
+    rep, cluster = {}, []
+    for m in mags + [None]:
+        if m is not None and (not cluster or m - cluster[0] <= rel * m):
+            cluster.append(m)
+            continue
+        mean = float(np.mean(cluster))
+        if abs(mean - round(mean)) <= rel * mean:
+            mean = float(round(mean))
+        for c in cluster:
+            rep[c] = mean
+        cluster = [m] if m is not None else []
+    return rep
+
+
+def emit_header(p, path):
+    """Complete element operator of order p as one host/device function (tensor-ordered nodal dofs in and out):
+    forward transform, sparse modal operator, backward transform -- straight-line code, every constant a literal.
+    The geometry factors are multiplied once by scale and by each distinct coefficient magnitude, so that every
+    non-zero of the modal operator costs one FMA."""
+    T = transforms(p)
+    n = T.shape[0]
+    names = {(0, 0): 0, (0, 1): 1, (0, 2): 2, (1, 1): 3, (1, 2): 4, (2, 2): 5}
+    Z = np.zeros((3, 3))
+    ops = [(kind, names[ab], modal_operator(p, Z, E) if kind == "M" else modal_operator(p, E, Z)) for kind in ("M", "K") for ab, E in sym_basis()]
+    tsnap = _snap(T.ravel())
+    hsnap = _snap(np.concatenate([H.ravel() for _, _, H in ops]))
+    tname = {m: "t%d" % i for i, m in enumerate(sorted(set(tsnap.values())))}
+    L = []
+    L.append("// GENERATED by scripts/gen_modal_op.py %d --header -- do not edit.  Order-%d Nedelec hex, affine element:" % (p, p))
+    L.append("// y = scale * (K(alpha) + M(beta)) x on the %d tensor-ordered local dofs (component-major, x fastest), applied in the" % n)
+    L.append("// orthonormal Legendre basis; GK[6] = alpha J^T J / det, GM[6] = beta adj adj^T / det (packed 00 01 02 11 12 22).")
+    L.append("// Verified against the oracle's quadrature element matrices by the generator and by tests/test_modal_generated.py.")
+    L.append("#pragma once")
+    L.append("#ifndef HCURL_HD\n#ifdef __CUDACC__\n#define HCURL_HD __host__ __device__ __forceinline__\n#else\n#define HCURL_HD inline\n#endif\n#endif")
+    L.append("HCURL_HD void hcurl_modal_p%d_apply(const double *x, const double *GK, const double *GM, const double scale, double *y) {" % p)
+    for m, nm in sorted(tname.items(), key=lambda kv: kv[1]):
+        L.append("  const double %s = %.17g;" % (nm, m))
+    fac = {}
+    for kind, s, H in ops:
+        for v in np.abs(H[np.abs(H) > 1e-14]):
+            fac.setdefault((kind, s, hsnap[float(v)]), None)
+    for i, key in enumerate(sorted(fac)):
+        kind, s, m = key
+        fac[key] = "g%d" % i
+        L.append("  const double g%d = %sG%s[%d];" % (i, "scale * " if m == 1.0 else "%.17g * scale * " % m, kind, s))
+    L.append("  double xh[%d], yh[%d];" % (n, n))
+
+    def lin(dst, coef, src):
+        terms = [(j, coef[j]) for j in range(n) if abs(coef[j]) > 1e-14]
+        expr = None
+        for j, c in terms:
+            t = "%s%s * %s[%d]" % ("-" if c < 0 else "", tname[tsnap[abs(float(c))]], src, j)
+            expr = t if expr is None else "%s + %s" % (expr, t)
+        L.append("  %s = %s;" % (dst, expr or "0.0"))
+
+    for i in range(n):
+        lin("xh[%d]" % i, T[i], "x")
+    for i in range(n):
+        expr = None
+        for kind, s, H in ops:
+            for j in np.nonzero(np.abs(H[i]) > 1e-14)[0]:
+                g = fac[(kind, s, hsnap[abs(float(H[i, j]))])]
+                t = "%s%s * xh[%d]" % ("-" if H[i, j] < 0 else "", g, j)
+                expr = t if expr is None else "%s + %s" % (expr, t)
+        L.append("  yh[%d] = %s;" % (i, expr or "0.0"))
+    for j in range(n):
+        lin("y[%d]" % j, T[:, j], "yh")
+    L.append("}")
+    with open(path, "w") as f:
+        f.write("\n".join(L) + "\n")
+
+
 if __name__ == "__main__":
     worst = max(check(p) for p in (1, 2, 3))
     assert worst < 1e-12
-    if len(sys.argv) > 1:
+    if len(sys.argv) > 2 and sys.argv[2] == "--header":
+        emit_header(int(sys.argv[1]), sys.argv[3])
+    elif len(sys.argv) > 1:
         emit(int(sys.argv[1]))

@@ -307,3 +307,40 @@ def test_hex_p2_patch_kernel_split_variant(ctx, n, monkeypatch):
         op.Mult(dx, dy)
     ctx.synchronize()
     assert rel_err(dy.download(), oa.constrained_apply(A, ess2, x)) < TOL
+
+
+@pytest.mark.skipif(os.environ.get("HCURL_TEST_PATCH_P1") != "1",
+                    reason="order-1 patch kernel: device environment written after the round-1 GPU budget was spent (the kernel program is "
+                           "checked on host threads, tests/test_patch_p1_emu.py); opt in with HCURL_TEST_PATCH_P1=1")
+@pytest.mark.parametrize("n,fe", [((9, 8, 6), 128), ((5, 4, 3), 32), ((12, 11, 7), 64), ((16, 16, 16), 256)])
+def test_hex_p1_patch_kernel(ctx, n, fe, monkeypatch):
+    """hex_patch_modal_p1_kernel (hex_patch_p1.cu): constrained apply, accumulate, arbitrary essential set, scrambled
+    numbering (sign flips), repeated device-resident applies -- same parity bar as the order-2 patch kernel."""
+    monkeypatch.setenv("HCURL_PATCH_P1", "1")
+    monkeypatch.setenv("HCURL_PATCH_FE", str(fe))
+    m, sp, mo, so = make_pair("hex", n, 1, False, scramble=True)
+    a, b = coefficients(m)
+    gsp = operators.GpuNDSpace(ctx, sp)
+    op = operators.HephGpuOperator(ctx, gsp, 2)
+    op.SetKernel(3)
+    op.SetCoefficients(a, b)
+    essd = sp.boundary_dofs(lambda c: c[:, 0] < 1e-9)
+    op.SetEssentialTrueDofs(essd)
+    x = np.random.default_rng(12345).standard_normal(sp.ndof)
+    A = oa.assemble(so, a, b, q_override=2)
+    assert rel_err(op.Mult(x), oa.constrained_apply(A, essd, x)) < TOL
+    assert op.LastKernel() == 3
+    y0 = np.random.default_rng(1).standard_normal(sp.ndof)
+    assert rel_err(op.MultUnconstrained(x, y0.copy(), scale=-0.5, accumulate=True), y0 - 0.5 * (A @ x)) < TOL
+    ess2 = np.sort(np.random.default_rng(11).choice(sp.ndof, sp.ndof // 5, replace=False)).astype(np.int32)
+    op.SetEssentialTrueDofs(ess2)
+    assert rel_err(op.Mult(x), oa.constrained_apply(A, ess2, x)) < TOL
+    dx, dy = ctx.alloc(sp.ndof).upload(x), ctx.alloc(sp.ndof)
+    for _ in range(3):
+        op.Mult(dx, dy)
+    ctx.synchronize()
+    assert rel_err(dy.download(), oa.constrained_apply(A, ess2, x)) < TOL
+    # the generic sum-factorised kernel agrees (the path order 1 takes without the switch)
+    op.SetKernel(1)
+    assert rel_err(op.Mult(x), oa.constrained_apply(A, ess2, x)) < TOL
+    assert op.LastKernel() == 1

@@ -91,3 +91,29 @@ def test_pcg_reuse_after_coefficient_update(ctx):
         x = s.Mult(rhs)
         xo, it, _, _, _ = opcg.pcg(Ac, rhs, diag=Ac.diagonal(), rtol=s.tol, atol=s.abstol, max_iter=5000)
         assert abs(s.num_iterations - it) <= 2 and rel_err(x, xo) < 1e-6
+
+
+@pytest.mark.skipif(__import__("os").environ.get("HCURL_TEST_PATCH_P1") != "1",
+                    reason="order-1 patch kernel not yet run on a GPU (see tests/test_gpu_apply.py); opt in with HCURL_TEST_PATCH_P1=1")
+def test_pcg_order1_patch_kernel_fused_dot(ctx, monkeypatch):
+    """Jacobi-PCG on affine order-1 hexes through the order-1 patch kernel: <p, A p> comes from the kernel's fused dot
+    product; iteration count and solution as the oracle's hypre-semantics PCG."""
+    monkeypatch.setenv("HCURL_PATCH_P1", "1")
+    m, sp, mo, so = make_pair("hex", (12, 10, 9), 1, False)
+    a, b = coefficients(m)
+    a = a * 0.05
+    gsp = operators.GpuNDSpace(ctx, sp)
+    op = operators.HephGpuOperator(ctx, gsp, 2)
+    op.SetCoefficients(a, b)
+    ess = sp.boundary_dofs()
+    op.SetEssentialTrueDofs(ess)
+    Ac, _ = oa.eliminate(oa.assemble(so, a, b, q_override=2), ess)
+    rhs = Ac @ np.random.default_rng(54321).standard_normal(sp.ndof)
+    s = operators.HephGpuPCG(ctx, tol=1e-9, max_iter=5000)
+    s.SetOperator(op)
+    x = s.Mult(rhs)
+    assert op.LastKernel() == 3
+    xo, it, res, conv, hist = opcg.pcg(Ac, rhs, diag=Ac.diagonal(), rtol=s.tol, atol=s.abstol, max_iter=5000)
+    assert s.converged and conv
+    assert abs(s.num_iterations - it) <= max(2, it // 50), (s.num_iterations, it)
+    assert rel_err(x, xo) < 1e-6
