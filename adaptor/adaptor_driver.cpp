@@ -1,9 +1,12 @@
 // Test driver: builds mock MFEM objects from a dump written by tests/test_adaptor.py, then runs
 // the adaptor exactly as Hephaestus would (operator apply, FormRHS, NewtonSolver-style solve)
 // and writes the results back.  Usage: adaptor_driver <in.bin> <out.bin>
+//        adaptor_driver --tensor-dofs <in.bin> <out.bin>   host only: HephGpuDiscreteInterpolator::TensorDofs of a mock
+//        space (header: nd, ne; arrays: dof_map [nd], elem_dofs [ne][nd]) -> [ne][nd] as doubles
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "mock_mfem.hpp"
@@ -24,11 +27,34 @@ static void wr(FILE * f, const double * p, int64_t n)
   fwrite(p, sizeof(double), (size_t)n, f);
 }
 
+static int tensor_dofs_mode(const char * in, const char * out)
+{
+  FILE * f = fopen(in, "rb");
+  if (!f) return 2;
+  auto hdr = rd<int64_t>(f);
+  auto dm = rd<int32_t>(f), ed = rd<int32_t>(f);
+  fclose(f);
+  mfem::ParMesh mesh;
+  mesh.attr.assign((size_t)hdr[1], 1);
+  mfem::ParFiniteElementSpace fes;
+  fes.mesh = &mesh; fes.nd = (int)hdr[0];
+  fes.elem_dofs.assign(ed.begin(), ed.end());
+  for (int32_t v : dm) fes.fe._dof_map.Append(v);
+  std::vector<int32_t> t;
+  hephaestus::HephGpuDiscreteInterpolator::TensorDofs(fes, t);
+  std::vector<double> d(t.begin(), t.end());
+  FILE * o = fopen(out, "wb");
+  wr(o, d.data(), (int64_t)d.size());
+  fclose(o);
+  return 0;
+}
+
 int main(int argc, char ** argv)
 {
   if (argc < 3) return 2;
   try
   {
+    if (std::string(argv[1]) == "--tensor-dofs" && argc == 4) return tensor_dofs_mode(argv[2], argv[3]);
     FILE * f = fopen(argv[1], "rb");
     if (!f) return 2;
     auto hdr = rd<int64_t>(f);  // kind (5 hex, 4 tet), order, nd, ndofs, quad

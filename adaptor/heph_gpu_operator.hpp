@@ -269,6 +269,65 @@ private:
   hcurl_op * _op{nullptr};
 };
 
+/// Discrete gradient (H1 -> ND) or discrete curl (ND -> RT) on grid functions (L-vectors), hex meshes.
+/// Drop-in for the mfem::ParDiscreteLinearOperator the reference assembles with a GradientInterpolator
+/// (ScalarPotentialSource::BuildGrad, /root/reference/src/sources/scalar_potential_source.cpp:89-97) or a
+/// CurlInterpolator (CurlAuxSolver::Init, /root/reference/src/auxsolvers/curl_aux.cpp:19-23); Mult replaces
+/// _grad->Mult(*_phi, *_grad_phi) (:130) and _curl->Mult(*_u, *_curl_u) (curl_aux.cpp:29).
+/// The library wants element dofs in tensor order: GetElementDofs composed with the element's own
+/// TensorBasisElement::GetDofMap(), so no local ordering convention is restated on this side.
+class HephGpuDiscreteInterpolator : public mfem::Operator
+{
+public:
+  enum Kind { GRADIENT = HCURL_INTERP_GRAD, CURL = HCURL_INTERP_CURL };
+  HephGpuDiscreteInterpolator(HephGpuContext & ctx, Kind kind, mfem::ParFiniteElementSpace & domain,
+                              mfem::ParFiniteElementSpace & range)
+    : mfem::Operator(range.GetVSize(), domain.GetVSize())
+  {
+    // ND_FECollection(p) and H1_FECollection(p) report p; RT_FECollection(p-1) pairs with them
+    const int p = domain.FEColl()->GetOrder();
+    std::vector<int32_t> in, out;
+    TensorDofs(domain, in);
+    TensorDofs(range, out);
+    _it = hcurl_interp_create(ctx.Get(), (int)kind, p, domain.GetParMesh()->GetNE(), in.data(), out.data(),
+                              domain.GetVSize(), range.GetVSize());
+    if (!_it)
+      MFEM_ABORT(std::string("hcurl_interp_create failed: ") + hcurl_last_error());
+  }
+  ~HephGpuDiscreteInterpolator() override { hcurl_interp_destroy(_it); }
+  void Mult(const mfem::Vector & x, mfem::Vector & y) const override
+  {
+    HEPH_GPU_CHECK(hcurl_interp_apply(_it, x.HostRead(), y.HostWrite(), HCURL_HOST));
+  }
+
+  /// [ne][nd] element dofs in tensor order, FiniteElementSpace::GetElementDofs encoding (k or -1-k)
+  static void TensorDofs(const mfem::ParFiniteElementSpace & fes, std::vector<int32_t> & out)
+  {
+    const int ne = fes.GetParMesh()->GetNE();
+    mfem::Array<int> dofs;
+    out.clear();
+    for (int e = 0; e < ne; e++)
+    {
+      const auto * tb = dynamic_cast<const mfem::TensorBasisElement *>(fes.GetFE(e));
+      if (!tb)
+        MFEM_ABORT("HephGpuDiscreteInterpolator: not a tensor-product element (hex meshes only)");
+      const mfem::Array<int> & dm = tb->GetDofMap();
+      fes.GetElementDofs(e, dofs);
+      for (int t = 0; t < dofs.Size(); t++)
+      {
+        const int m = dm.Size() ? dm[t] : t;
+        const int d = dofs[m >= 0 ? m : -1 - m];
+        const int k = d >= 0 ? d : -1 - d;
+        const bool flip = (m < 0) != (d < 0);
+        out.push_back(flip ? -1 - k : k);
+      }
+    }
+  }
+
+private:
+  hcurl_interp * _it{nullptr};
+};
+
 /// Jacobi-preconditioned CG with hypre's PCG semantics, on the device.
 /// Options mirror DefaultJacobiPCGSolver (hephaestus_solvers.hpp:39-42): Tolerance / AbsTolerance
 /// arrive as float, MaxIter as unsigned int, PrintLevel as int.

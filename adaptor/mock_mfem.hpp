@@ -46,6 +46,7 @@ class Operator
 {
 public:
   explicit Operator(int s = 0) : height(s), width(s) {}
+  Operator(int h, int w) : height(h), width(w) {}
   virtual ~Operator() = default;
   int Height() const { return height; }
   int Width() const { return width; }
@@ -197,9 +198,28 @@ public:
   const int * GetGroup(int) const { static int z = 0; return &z; }
 };
 
+// tensor-product elements expose the map lexicographic (tensor) index -> native local index (negative: -1-k, the basis
+// function enters with a sign flip); an empty map means the native order is the tensor order
+class FiniteElement
+{
+public:
+  virtual ~FiniteElement() = default;
+};
+class TensorBasisElement
+{
+public:
+  const Array<int> & GetDofMap() const { return _dof_map; }
+  Array<int> _dof_map;
+};
+class MockTensorElement : public FiniteElement, public TensorBasisElement
+{
+};
+
 class ParFiniteElementSpace
 {
 public:
+  MockTensorElement fe;  // one element type per space
+  const FiniteElement * GetFE(int) const { return &fe; }
   ParMesh * mesh{nullptr};
   FiniteElementCollection * fec{nullptr};
   int nd{0}, ndofs{0};

@@ -66,6 +66,11 @@ SIGNATURES = {
     "hcurl_pcg_solve": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double),
                                   C.POINTER(C.c_int)]),
     "hcurl_pcg_last_loop_ms": (C.c_double, [_P]),
+    "hcurl_interp_create": (_P, [_P, C.c_int, C.c_int, C.c_int64, _P, _P, C.c_int32, C.c_int32]),
+    "hcurl_interp_destroy": (None, [_P]),
+    "hcurl_interp_apply": (C.c_int, [_P, _P, _P, C.c_int]),
+    "hcurl_host_interp_matrix": (C.c_int, [C.c_int, _P]),
+    "hcurl_host_interp_encode": (C.c_int, [C.c_int, C.c_int, C.c_int64, _P, _P, C.c_int32, C.c_int32, _P, _P]),
     "hcurl_device_alloc": (_P, [_P, C.c_int64]),
     "hcurl_device_free": (None, [_P, _P]),
     "hcurl_copy_to_device": (C.c_int, [_P, _P, _P, C.c_int64]),

@@ -269,6 +269,43 @@ def complex_mult(op_re, op_im, xr, xi):
     return yr, yi
 
 
+class HephGpuInterpolator:
+    """Discrete gradient (H1 -> ND) / curl (ND -> RT) on hexes; mirrors mfem::ParDiscreteLinearOperator with a
+    GradientInterpolator / CurlInterpolator as the reference uses them on grid functions
+    (/root/reference/src/auxsolvers/curl_aux.cpp:13-30, /root/reference/src/sources/scalar_potential_source.cpp:89-97)."""
+    GRAD, CURL = 0, 1
+
+    def __init__(self, ctx, kind, order, in_dofs, out_dofs, n_in, n_out):
+        self.ctx = ctx
+        i, o = L.as_i32(in_dofs), L.as_i32(out_dofs)
+        self.n_in, self.n_out = int(n_in), int(n_out)
+        self.h = L.check_ptr(L.lib().hcurl_interp_create(ctx.h, kind, order, i.shape[0], L.ptr(i), L.ptr(o), self.n_in, self.n_out),
+                             "hcurl_interp_create")
+
+    def Mult(self, x, y=None):
+        if isinstance(x, DeviceVector):
+            assert isinstance(y, DeviceVector) and x.n >= self.n_in and y.n >= self.n_out
+            L.check(L.lib().hcurl_interp_apply(self.h, C.c_void_p(x.ptr), C.c_void_p(y.ptr), L.DEVICE), "hcurl_interp_apply")
+            return y
+        x = L.as_f64(x)
+        if x.size != self.n_in:
+            raise L.HcurlError("Mult: x has %d entries, interpolator width is %d" % (x.size, self.n_in))
+        y = np.empty(self.n_out) if y is None else y
+        L.check(L.lib().hcurl_interp_apply(self.h, L.ptr(x), L.ptr(y), L.HOST), "hcurl_interp_apply")
+        return y
+
+    def close(self):
+        if self.h:
+            L.lib().hcurl_interp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class HephGpuPCG:
     """hypre-semantics PCG (+ Jacobi), an ``mfem::Solver``: SetOperator / Mult.
     Defaults are DefaultJacobiPCGSolver's

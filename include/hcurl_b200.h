@@ -36,6 +36,7 @@ typedef struct hcurl_ctx hcurl_ctx;
 typedef struct hcurl_space hcurl_space;
 typedef struct hcurl_op hcurl_op;
 typedef struct hcurl_pcg hcurl_pcg;
+typedef struct hcurl_interp hcurl_interp;
 
 /* element geometry kinds */
 enum { HCURL_GEOM_HEX = 0, HCURL_GEOM_TET = 1 };
@@ -212,6 +213,29 @@ int hcurl_pcg_solve(hcurl_pcg *pcg, const double *b, double *x, int zero_initial
                     int *iters, double *final_rel_res, int *converged);
 /* device time (ms) spent inside the iteration loop of the most recent solve */
 double hcurl_pcg_last_loop_ms(hcurl_pcg *pcg);
+
+/* ---- discrete gradient / curl (hexes, orders 1..4) -------------------------------------------
+ * Replaces: mfem::ParDiscreteLinearOperator + CurlInterpolator of CurlAuxSolver (B = curl A every step,
+ * /root/reference/src/auxsolvers/curl_aux.cpp:13-30) and + GradientInterpolator of ScalarPotentialSource::BuildGrad
+ * (/root/reference/src/sources/scalar_potential_source.cpp:89-97, applied at :130).  Like the reference's, the operator
+ * acts on L-vectors (grid functions) of one rank: y = G x (H1 -> ND) or y = C x (ND -> RT), matrix-free and
+ * geometry-free (the bases are nodal for the pulled-back fields).
+ *   in_dofs  [n_elem][nd_in], out_dofs [n_elem][nd_out]: element dofs in TENSOR order (x fastest, component-major;
+ *            H1 (p+1)^3 | ND component c: p points along c, p+1 along the others | RT component c: p+1 along c, p
+ *            along the others), encoded like FiniteElementSpace::GetElementDofs (k, or -1-k for a sign flip).  From
+ *            MFEM: GetElementDofs composed with TensorBasisElement::GetDofMap() of the element.
+ *   order p: H1_FECollection(p) -> ND_FECollection(p) -> RT_FECollection(p-1). */
+enum { HCURL_INTERP_GRAD = 0, HCURL_INTERP_CURL = 1 };
+hcurl_interp *hcurl_interp_create(hcurl_ctx *ctx, int kind, int order, int64_t n_elem, const int32_t *in_dofs,
+                                  const int32_t *out_dofs, int32_t n_in, int32_t n_out);
+void hcurl_interp_destroy(hcurl_interp *it);
+/* y [n_out] = Interp x [n_in]; where = HCURL_HOST or HCURL_DEVICE */
+int hcurl_interp_apply(hcurl_interp *it, const double *x, double *y, int where);
+/* host-only (no GPU): the 1-D matrix D[i*(p+1)+j] = derivative of the closed basis function j at the open node i, and
+ * the encoded maps (index | bit 31 sign | bit 30 on outputs: another element writes this dof) */
+int hcurl_host_interp_matrix(int order, double *D);
+int hcurl_host_interp_encode(int kind, int order, int64_t n_elem, const int32_t *in_dofs, const int32_t *out_dofs,
+                             int32_t n_in, int32_t n_out, uint32_t *in_map, uint32_t *out_map);
 
 /* ---- vector helpers (device memory owned by the library) --------------------- */
 double *hcurl_device_alloc(hcurl_ctx *ctx, int64_t n_doubles);

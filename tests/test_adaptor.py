@@ -85,6 +85,28 @@ def test_adaptor_without_gpu_aborts_loudly(driver, tmp_path):
     assert "MFEM abort" in r.stderr and "hcurl_ctx_create failed" in r.stderr
 
 
+@pytest.mark.parametrize("p", [1, 2, 3])
+def test_adaptor_tensor_dofs_composition(driver, tmp_path, p):
+    """HephGpuDiscreteInterpolator::TensorDofs (GetElementDofs composed with TensorBasisElement::GetDofMap, signs
+    included) against the library's own composition for ND spaces (hcurl_host_hex_slot_codes) -- host only."""
+    from oracle.nd_hex import NDHex
+    m, sp, mo, so = make_pair("hex", (3, 2, 2), p, False, scramble=True)
+    fe = NDHex(p)
+    dm = np.where(np.asarray(fe.sgn) < 0, -1 - np.asarray(fe.loc), np.asarray(fe.loc))     # MFEM's dof_map encoding
+    sd = np.ascontiguousarray(sp.signed_elem_dofs(), dtype=np.int32)
+    with open(tmp_path / "in.bin", "wb") as f:
+        _arr(f, [sd.shape[1], sd.shape[0]], np.int64)
+        _arr(f, dm, np.int32)
+        _arr(f, sd, np.int32)
+    r = subprocess.run([driver, "--tensor-dofs", str(tmp_path / "in.bin"), str(tmp_path / "out.bin")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = _read(tmp_path / "out.bin")[0].astype(np.int64).reshape(sd.shape)
+    code = np.zeros(sd.shape, np.uint32)
+    L.check(L.lib().hcurl_host_hex_slot_codes(p, sd.shape[0], L.ptr(sd), L.ptr(code)), "slot codes")
+    idx, neg = (code & 0x7FFFFFFF).astype(np.int64), (code >> 31).astype(bool)
+    assert np.array_equal(got, np.where(neg, -1 - idx, idx))
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("kind,n,p,q", [("hex", 4, 2, 0), ("hex", 3, 1, 0), ("hex", 3, 3, 4), ("tet", 3, 1, 0), ("tet", 2, 2, 0)])
 def test_adaptor_end_to_end(driver, tmp_path, kind, n, p, q):
