@@ -1,0 +1,47 @@
+"""First-run harness for GPU code written after the round-1 GPU budget was spent (runs last, cannot mask other tests).
+
+The order-1 patch kernel (hex_patch_p1.cu), the split-blob order-2 variant (hex_patch_split_p2_kernel) and the discrete
+curl / gradient kernel (interp.cu) are verified on the host (tests/test_patch_p1_emu.py, tests/test_interp.py) or
+compile-checked only (split variant), but have never executed on a device.  Their GPU parity tests are opt-in
+(HCURL_TEST_PATCH_P1 / HCURL_TEST_SPLIT / HCURL_TEST_INTERP).  Each test below runs one of those groups in a CHILD process
+with the switch set and a hard time limit -- a kernel that hangs or faults takes the child down, not this run -- and is
+marked xfail(strict=False): XPASS in the summary = the kernel is parity-green on this GPU, XFAIL = it is not yet (the
+child's output is printed).  Neither outcome turns the suite red; the default paths never use these kernels."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def _child(env_switch, args, limit=420):
+    env = dict(os.environ)
+    env[env_switch] = "1"
+    cmd = [sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-p", "no:cacheprovider"] + args
+    try:
+        r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=limit)
+    except subprocess.TimeoutExpired as e:
+        out = (e.stdout or b"").decode(errors="replace") if isinstance(e.stdout, bytes) else (e.stdout or "")
+        pytest.fail("child exceeded %d s (hang?)\n%s" % (limit, out[-3000:]))
+    print(r.stdout[-3000:])
+    print(r.stderr[-2000:])
+    assert r.returncode == 0, "child failed:\n" + r.stdout[-3000:]
+    assert " passed" in r.stdout and "skipped" not in r.stdout.splitlines()[-1], r.stdout[-500:]
+
+
+@pytest.mark.xfail(strict=False, reason="order-1 patch kernel: first execution on a GPU")
+def test_first_run_order1_patch_kernel():
+    _child("HCURL_TEST_PATCH_P1", ["tests/test_gpu_apply.py", "tests/test_gpu_pcg.py", "-k", "p1_patch or order1_patch"])
+
+
+@pytest.mark.xfail(strict=False, reason="discrete curl / gradient kernel: first execution on a GPU")
+def test_first_run_interpolators():
+    _child("HCURL_TEST_INTERP", ["tests/test_interp.py"])
+
+
+@pytest.mark.xfail(strict=False, reason="split-blob order-2 patch kernel variant: first execution on a GPU")
+def test_first_run_split_blob_variant():
+    _child("HCURL_TEST_SPLIT", ["tests/test_gpu_apply.py", "-k", "split"])
