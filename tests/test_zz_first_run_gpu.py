@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
-def _child(env_switch, args, limit=420):
+def _child(env_switch, args, limit=150):
     env = dict(os.environ)
     env[env_switch] = "1"
     cmd = [sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-p", "no:cacheprovider"] + args
