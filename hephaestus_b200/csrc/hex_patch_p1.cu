@@ -26,19 +26,18 @@ struct P1DeviceEnv {
   __device__ __forceinline__ unsigned char *smem() const { return smem_; }
   __device__ __forceinline__ uint64_t *mbar() const { return reinterpret_cast<uint64_t *>(smem_); }
   __device__ __forceinline__ void sync() const { __syncthreads(); }
-  __device__ __forceinline__ void blob_init() const {
-    mbar_init(mbar(), 1);
-    mbar_init(mbar() + 1, 1);
+  __device__ __forceinline__ void bulk_init(int n) const {
+    for (int i = 0; i < n; i++) mbar_init(mbar() + i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __device__ __forceinline__ void blob_request(int b, void *dst, const void *src, uint32_t bytes) const {
+  __device__ __forceinline__ void bulk_request(int b, void *dst, const void *src, uint32_t bytes) const {
     // generic-proxy accesses of the buffer (by all threads, ordered before this point by a CTA barrier) come before
     // the async-proxy write of the bulk copy
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     mbar_expect_tx(mbar() + b, bytes);
     bulk_load(mbar() + b, dst, src, bytes);
   }
-  __device__ __forceinline__ void blob_wait(int b, uint32_t parity) const { mbar_wait(mbar() + b, parity); }
+  __device__ __forceinline__ void bulk_wait(int b, uint32_t parity) const { mbar_wait(mbar() + b, parity); }
   __device__ __forceinline__ void gather8(double *dst, const double *src) const { gather8_async(dst, src); }
   __device__ __forceinline__ void gather_commit() const { hcurl::gather_commit(); }
   __device__ __forceinline__ void gather_wait() const { gather_wait_all(); }

@@ -22,9 +22,9 @@
 //
 // Env provides:
 //   int tid(); int64_t block(), nblocks(); unsigned char *smem(); void sync();
-//   void blob_init();                                                    (thread 0, before the first sync)
-//   void blob_request(int b, void *dst, const void *src, uint32_t bytes) (thread 0)
-//   void blob_wait(int b, uint32_t parity);
+//   void bulk_init(int n);                                               (thread 0, before the first sync: n mbarriers)
+//   void bulk_request(int b, void *dst, const void *src, uint32_t bytes) (thread 0: expect-tx + bulk copy on mbarrier b)
+//   void bulk_wait(int b, uint32_t parity);                              (every thread)
 //   void gather8(double *dst, const double *src); void gather_commit(); void gather_wait();
 //   void red_add(double *p, double v);
 //   uint32_t ldg(const uint32_t *p); double ldg(const double *p);
@@ -58,7 +58,7 @@ HCURL_BODY void hex_patch_p1_body(Env &env, const PatchArgs &a) {
   const int n_it = (int)((a.n_patch - k0 + kstep - 1) / kstep);
 
   auto request = [&](int b, uint32_t o0, uint32_t o1) {
-    env.blob_request(b, blobB + (size_t)b * a.blob_cap_bytes, a.blob + (size_t)o0 * 4, (o1 - o0) * 16u);
+    env.bulk_request(b, blobB + (size_t)b * a.blob_cap_bytes, a.blob + (size_t)o0 * 4, (o1 - o0) * 16u);
   };
   // launch the x gather of the patch whose blob sits in buffer b
   auto gather = [&](int b) {
@@ -73,12 +73,12 @@ HCURL_BODY void hex_patch_p1_body(Env &env, const PatchArgs &a) {
     env.gather_commit();
   };
   if (tid == 0) {
-    env.blob_init();
+    env.bulk_init(2);
     request(0, env.ldg(a.blob_off + k0), env.ldg(a.blob_off + k0 + 1));
     if (n_it > 1) request(1, env.ldg(a.blob_off + k0 + kstep), env.ldg(a.blob_off + k0 + kstep + 1));
   }
   env.sync();  // mbarriers initialised
-  env.blob_wait(0, 0);
+  env.bulk_wait(0, 0);
   gather(0);
   env.gather_wait();
   env.sync();  // Xs of the first patch complete and visible
@@ -120,7 +120,7 @@ HCURL_BODY void hex_patch_p1_body(Env &env, const PatchArgs &a) {
     }
     // ---- start the x gather of the next patch: it lands while this patch is scattered
     if (it + 1 < n_it) {
-      env.blob_wait(b ^ 1, ((it + 1) >> 1) & 1);
+      env.bulk_wait(b ^ 1, ((it + 1) >> 1) & 1);
       gather(b ^ 1);
     }
     if (ok) {

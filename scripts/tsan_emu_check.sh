@@ -6,7 +6,7 @@ set -e
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
 OUT=/tmp/hcurl_tsan
 mkdir -p $OUT
-g++ -std=c++20 -O1 -g -fsanitize=thread -fno-omit-frame-pointer -fPIC -shared -pthread -I$ROOT/hephaestus_b200/csrc -I/usr/local/cuda/include \
+g++ -std=c++20 -O1 -g -fsanitize=thread -fno-omit-frame-pointer -fPIC -shared -pthread -I$ROOT/hephaestus_b200/csrc -I$ROOT/tests/emu -I/usr/local/cuda/include \
   $ROOT/tests/emu/patch_p1_emu.cpp -o $OUT/libp1emu_tsan.so
 cd $ROOT
 LD_PRELOAD=$(gcc -print-file-name=libtsan.so) TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 exitcode=66" HCURL_EMU_LIB=$OUT/libp1emu_tsan.so \

@@ -1,0 +1,157 @@
+// Host execution environment for kernel programs written against an `Env` (hephaestus_b200/csrc/hex_patch_p1_body.h,
+// hex_patch_p2_body.h) -- TEST INFRASTRUCTURE, not part of the product library.  One std::thread per CUDA thread of a
+// CTA, std::barrier for __syncthreads, memcpy for TMA bulk copies and cp.async gathers, compare-and-swap for
+// red.global.add.f64, a per-warp barrier for __all_sync.  CTAs run one after the other; each walks patches
+// block, += nblocks like the persistent kernels.
+//
+// Deliberately pessimistic where the hardware is asynchronous: the destination of an asynchronous copy is poisoned when
+// the copy is issued (it may land at once) and filled at its WAIT (bulk_wait / gather_wait: it may land that late), so a
+// thread that still reads the old content after the request, or the new one before waiting, computes garbage.  The
+// mbarrier protocol is checked: one request per phase, every thread of the CTA waits exactly once per request and on the
+// right parity, bulk-copy alignment rules.  Error flags are returned by run_grid().
+#pragma once
+#include <atomic>
+#include <barrier>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "internal.h"
+
+namespace emu {
+
+static constexpr int MAX_BAR = 4;
+enum { ERR_REARM = 1, ERR_ALIGN = 2, ERR_WAIT_UNARMED = 4, ERR_PARITY = 8, ERR_GATHER_LEFT = 16, ERR_BULK_LEFT = 32 };
+
+struct Pending { void *dst = nullptr; const void *src = nullptr; uint32_t bytes = 0; bool armed = false, landed = false; };
+
+struct WarpShared {
+  std::barrier<> bar;
+  std::atomic<int> flag[3];
+  explicit WarpShared(int n) : bar(n) { for (auto &f : flag) f.store(1); }
+};
+
+struct CtaShared {
+  std::vector<unsigned char> smem;
+  std::barrier<> bar;
+  std::mutex mu[MAX_BAR];
+  Pending bulk[MAX_BAR];   // guarded by mu[b]
+  uint32_t phase[MAX_BAR]; // completed requests per mbarrier, guarded by mu[b]
+  int waiters[MAX_BAR];    // guarded by mu[b]
+  std::vector<std::unique_ptr<WarpShared>> warp;
+  double dot_sum = 0.0;
+  std::vector<double> dot_part;
+  CtaShared(size_t bytes, int nt) : smem(bytes + 16, 0xAB), bar(nt), dot_part((size_t)nt, 0.0) {
+    for (int b = 0; b < MAX_BAR; b++) { phase[b] = 0; waiters[b] = 0; }
+    for (int w = 0; w * 32 < nt; w++) warp.emplace_back(new WarpShared(std::min(32, nt - w * 32)));
+  }
+  unsigned char *base() {  // 16-byte aligned like dynamic shared memory
+    return reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem.data()) + 15) & ~(uintptr_t)15);
+  }
+};
+
+struct HostEnv {
+  CtaShared *cta;
+  int tid_;
+  int64_t block_, nblocks_;
+  int nt_;
+  int *error;
+  const void *tables_;
+  struct Copy { void *dst; const void *src; int bytes; };
+  std::vector<Copy> pend;  // my issued, not yet waited-for gathers
+  unsigned vote_n = 0;
+
+  int tid() const { return tid_; }
+  int64_t block() const { return block_; }
+  int64_t nblocks() const { return nblocks_; }
+  unsigned char *smem() const { return cta->base(); }
+  void sync() { cta->bar.arrive_and_wait(); }
+  template <class T> const T &tables() const { return *static_cast<const T *>(tables_); }
+  void bulk_init(int) {}
+  void bulk_request(int b, void *dst, const void *src, uint32_t bytes) {
+    std::lock_guard<std::mutex> lk(cta->mu[b]);
+    if (cta->bulk[b].armed) *error |= ERR_REARM;  // request on an mbarrier whose previous phase has not been consumed by everyone
+    if (bytes % 16 != 0 || ((uintptr_t)dst & 15) || ((uintptr_t)src & 15)) *error |= ERR_ALIGN;  // cp.async.bulk rules
+    if (bytes) memset(dst, 0xCD, bytes);  // the copy may start at once: whoever still reads the old content gets garbage
+    cta->bulk[b].dst = dst; cta->bulk[b].src = src; cta->bulk[b].bytes = bytes; cta->bulk[b].armed = true; cta->bulk[b].landed = false;
+  }
+  void bulk_wait(int b, uint32_t parity) {
+    std::lock_guard<std::mutex> lk(cta->mu[b]);
+    Pending &q = cta->bulk[b];
+    if (!q.armed) { *error |= ERR_WAIT_UNARMED; return; }
+    if ((cta->phase[b] & 1u) != parity) *error |= ERR_PARITY;          // waiting on the wrong phase of the mbarrier
+    if (!q.landed) { if (q.bytes) memcpy(q.dst, q.src, q.bytes); q.landed = true; }  // ... and it completes as late as allowed
+    if (++cta->waiters[b] == nt_) {  // every thread of the CTA waits exactly once per request
+      cta->waiters[b] = 0;
+      cta->phase[b]++;
+      q.armed = false;
+    }
+  }
+  void gather8(double *dst, const double *src) {
+    *dst = std::numeric_limits<double>::quiet_NaN();  // in flight: readers that do not wait see garbage
+    pend.push_back({dst, src, 8});
+  }
+  void gather16(double2 *dst, const double2 *src) {
+    dst->x = dst->y = std::numeric_limits<double>::quiet_NaN();
+    pend.push_back({dst, src, 16});
+  }
+  void gather_commit() {}
+  void gather_wait() {
+    for (auto &p : pend) memcpy(p.dst, p.src, (size_t)p.bytes);
+    pend.clear();
+  }
+  void red_add(double *p, double v) {
+    std::atomic_ref<double> r(*p);
+    double old = r.load(std::memory_order_relaxed);
+    while (!r.compare_exchange_weak(old, old + v, std::memory_order_relaxed)) {}
+  }
+  bool warp_all(bool pred) {  // __all_sync(0xffffffff, pred)
+    WarpShared &W = *cta->warp[(size_t)(tid_ >> 5)];
+    const unsigned n = vote_n++;
+    if ((tid_ & 31) == 0) W.flag[(n + 1) % 3].store(1);  // slot of the next vote; readers of the previous one use another
+    if (!pred) W.flag[n % 3].store(0);
+    W.bar.arrive_and_wait();
+    return W.flag[n % 3].load() != 0;
+  }
+  uint32_t ldg(const uint32_t *p) const { return *p; }
+  double ldg(const double *p) const { return *p; }
+  double2 ldg(const double2 *p) const { return *p; }
+  void dot_finish(double dacc, const hcurl::PatchArgs &, double *) {
+    cta->dot_part[(size_t)tid_] = dacc;
+    sync();
+    if (tid_ == 0) {
+      double v = 0.0;
+      for (double d : cta->dot_part) v += d;
+      cta->dot_sum = v;
+    }
+  }
+};
+
+// run `grid` CTAs of `nt` threads one after the other; body(env) is the per-thread program
+template <class Body>
+int run_grid(int64_t grid, int nt, size_t smem_bytes, const void *tables, double *dot_total, Body body) {
+  int error = 0;
+  double dot = 0.0;
+  for (int64_t blk = 0; blk < grid; blk++) {
+    CtaShared cta(smem_bytes, nt);
+    std::vector<int> err((size_t)nt, 0);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++)
+      th.emplace_back([&, t]() {
+        HostEnv env{&cta, t, blk, grid, nt, &err[(size_t)t], tables, {}, 0};
+        body(env);
+        if (!env.pend.empty()) err[(size_t)t] |= ERR_GATHER_LEFT;  // gathers never waited for
+      });
+    for (auto &t : th) t.join();
+    for (int e : err) error |= e;
+    for (int b = 0; b < MAX_BAR; b++) if (cta.bulk[b].armed) error |= ERR_BULK_LEFT;  // a requested copy was never consumed
+    dot += cta.dot_sum;
+  }
+  if (dot_total) *dot_total = dot;
+  return error;
+}
+
+}  // namespace emu

@@ -34,7 +34,7 @@ def emu(tmp_path_factory, lib_built):
     if not path:
         path = str(tmp_path_factory.mktemp("emu") / "libp1emu.so")
         cmd = ["g++", "-std=c++20", "-O2", "-fPIC", "-shared", "-pthread", "-I" + os.path.join(ROOT, "hephaestus_b200", "csrc"),
-               "-I/usr/local/cuda/include", os.path.join(ROOT, "tests", "emu", "patch_p1_emu.cpp"), "-o", path]
+               "-I/usr/local/cuda/include", "-I" + os.path.join(ROOT, "tests", "emu"), os.path.join(ROOT, "tests", "emu", "patch_p1_emu.cpp"), "-o", path]
         r = subprocess.run(cmd, capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
     lib = C.CDLL(path)
