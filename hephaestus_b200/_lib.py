@@ -95,6 +95,8 @@ SIGNATURES = {
     "hcurl_host_ndspace_boundary_dofs": (C.c_int64, [_P, _P]),
     "hcurl_host_ndspace_face_dofs": (C.c_int64, [_P, C.c_int64, _P, _P]),
     "hcurl_host_hex_p2_pair_codes": (C.c_int, [C.c_int64, _P, _P]),
+    "hcurl_host_patches_parts": (C.c_int, [_P, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "hcurl_host_modal_tables_p2": (C.c_int, [_P]),
     "hcurl_host_hex_slot_codes": (C.c_int, [C.c_int, C.c_int64, _P, _P]),
     "hcurl_host_patches_create": (_P, [C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int64, _P, _P, _P]),
     "hcurl_host_patches_destroy": (None, [_P]),

@@ -40,15 +40,6 @@
 
 namespace hcurl {
 
-struct ModalTables {
-  // closed basis (Gauss-Lobatto nodes 0, 1/2, 1) -> orthonormal Legendre L0, L1, L2:
-  //   T = [[a0, a1, a0], [-b, 0, b], [c0, c1, c0]]   (symmetry of the nodes)
-  // open basis (2 Gauss-Legendre nodes) -> L0, L1 is [[1/2, 1/2], [-1/2, 1/2]]; the kernel applies
-  // [[1, 1], [-1, 1]] (adds only) and folds the two factors 1/2 (trial and test side) into the
-  // geometry factors.
-  double a0, a1, b, c0, c1;
-  double d1, d2;  // L1' = d1 L0, L2' = d2 L1
-};
 __constant__ ModalTables cM;
 
 __device__ __forceinline__ int sym6(int i, int j) {  // packed index of the symmetric pair (i,j)
@@ -798,11 +789,10 @@ __global__ void patch_flag8_kernel(const uint32_t *__restrict__ blob_off, const 
 }
 
 unsigned long long *g_patch_prof = nullptr;  // set by hcurl_debug_patch_profile (debug.cu)
-static bool g_modal_set = false;
-static int set_modal_tables() {
-  if (g_modal_set) return 0;
-  // orthonormal shifted Legendre on [0,1]: L0 = 1, L1 = sqrt3 (2x-1), L2 = sqrt5 (6x^2-6x+1);
-  // T[m][j] = int_0^1 L_m l_j, by a 5-point Gauss rule (exact)
+// orthonormal shifted Legendre on [0,1]: L0 = 1, L1 = sqrt3 (2x-1), L2 = sqrt5 (6x^2-6x+1);
+// T[m][j] = int_0^1 L_m l_j, by a 5-point Gauss rule (exact).  Host only; returns 1 when the tables do not have the
+// symmetric structure the kernels hard-wire.
+int compute_modal_tables(ModalTables &T) {
   double xq[5], wq[5], gl[2], wl[2], gll[3];
   gauss_legendre01(5, xq, wq);
   gauss_legendre01(2, gl, wl);
@@ -819,17 +809,33 @@ static int set_modal_tables() {
       if (m < 2) for (int i = 0; i < 2; i++) To[m * 2 + i] += wq[q] * L[m] * Bo[q * 2 + i];
     }
   }
-  // the kernel hard-wires the structure of these tables; check it
   const double tol = 1e-14;
   if (fabs(To[0] - 0.5) > tol || fabs(To[1] - 0.5) > tol || fabs(To[2] + 0.5) > tol || fabs(To[3] - 0.5) > tol ||
       fabs(Tc[0] - Tc[2]) > tol || fabs(Tc[3] + Tc[5]) > tol || fabs(Tc[4]) > tol || fabs(Tc[6] - Tc[8]) > tol) {
     set_error("modal tables do not have the expected symmetric structure");
     return 1;
   }
-  ModalTables T;
   T.a0 = 0.5 * (Tc[0] + Tc[2]); T.a1 = Tc[1]; T.b = 0.5 * (Tc[5] - Tc[3]); T.c0 = 0.5 * (Tc[6] + Tc[8]); T.c1 = Tc[7];
   T.d1 = 2.0 * sqrt(3.0);
   T.d2 = 2.0 * sqrt(15.0);
+  return 0;
+}
+
+}  // namespace hcurl
+extern "C" int hcurl_host_modal_tables_p2(double *out7) {
+  hcurl::ModalTables T;
+  if (!out7 || hcurl::compute_modal_tables(T)) return 1;
+  const double v[7] = {T.a0, T.a1, T.b, T.c0, T.c1, T.d1, T.d2};
+  memcpy(out7, v, sizeof(v));
+  return 0;
+}
+namespace hcurl {
+
+static bool g_modal_set = false;
+static int set_modal_tables() {
+  if (g_modal_set) return 0;
+  ModalTables T;
+  if (compute_modal_tables(T)) return 1;
   HC_CUDA(cudaMemcpyToSymbol(cM, &T, sizeof(T)));
   g_modal_set = true;
   return 0;
@@ -939,6 +945,8 @@ int hex_patch_build(hcurl_space *sp, const double *elem_xyz, const int32_t *elem
   HC_CUDA(cudaSetDevice(sp->ctx->device));
   PatchSet &P = sp->patch;
   P.FE = FE; P.stride = H.stride; P.n_patch = H.n_patch; P.n_boundary = H.n_boundary;
+  const char *envk = getenv("HCURL_PATCH_ENV");
+  P.env_kernel = envk && envk[0] == '1' && FE == 32;  // the Env-program restatement of the kernel (hex_patch_p2e.cu), opt-in
   P.split = split; P.max_d_words = H.max_d_words; P.max_l_words = H.max_l_words;
   if (split && upload(P.d_part_off, H.part_off)) return 1;
   P.blob_words = (int64_t)H.blob.size(); P.max_blob_words = H.max_blob_words; P.max_dofs = H.max_dofs;
@@ -1077,6 +1085,13 @@ int hex_patch_launch(hcurl_op *op, bool constrained, const double *d_x, double *
   a.d_cap_bytes = (P.max_d_words * 4 + 15u) & ~15u;
   a.l_cap_bytes = (P.max_l_words * 4 + 15u) & ~15u;
   const size_t smem = P.split ? patch_split_smem_bytes(P.FE, P) : patch_smem_bytes(P.FE, P.max_blob_words, P.max_dofs);
+  if (P.env_kernel) {
+    a.prof = nullptr;
+    if (hex_patch_p2e_launch(op, a, accumulate)) return 1;
+    HC_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+  }
   int rc = 1;
   // 168 registers per thread: 2 CTAs of 192 threads per SM.  (A 3-CTA variant capped at 112 / 104 registers spilled
   // and ran 45 % slower, profiles/README.md.)

@@ -109,12 +109,25 @@ struct PatchSet {  // device copy
   int64_t blob_words = 0;
   uint32_t max_blob_words = 0, max_dofs = 0;
   bool split = false;            // blobs built for the split-blob kernel variant (unpadded rows)
+  bool env_kernel = false;       // launch the Env-program restatement (hex_patch_p2e.cu) instead of hex_patch.cu's kernels
   uint32_t *d_part_off = nullptr;
   uint32_t max_d_words = 0, max_l_words = 0;
   uint8_t swz_row[27] = {0}, swz_grp[16] = {0};
   uint32_t *d_shared = nullptr;  // 128-byte lines holding RED-added pairs: the only part of y that must be zero before an apply
   int64_t n_shared = 0;
 };
+
+// 1-D transform tables of the order-2 modal element operator (hex_patch.cu, hex_patch_p2_body.h)
+struct ModalTables {
+  // closed basis (Gauss-Lobatto nodes 0, 1/2, 1) -> orthonormal Legendre L0, L1, L2:
+  //   T = [[a0, a1, a0], [-b, 0, b], [c0, c1, c0]]   (symmetry of the nodes)
+  // open basis (2 Gauss-Legendre nodes) -> L0, L1 is [[1/2, 1/2], [-1/2, 1/2]]; the kernel applies
+  // [[1, 1], [-1, 1]] (adds only) and folds the two factors 1/2 (trial and test side) into the
+  // geometry factors.
+  double a0, a1, b, c0, c1;
+  double d1, d2;  // L1' = d1 L0, L2' = d2 L1
+};
+int compute_modal_tables(ModalTables &T);
 
 // Kernel arguments of the patch kernels (hex_patch.cu: order 2, 16-byte units; hex_patch_p1.cu: order 1, 8-byte units)
 struct PatchArgs {
@@ -266,6 +279,8 @@ int hex_patch_zero_shared(hcurl_op *op, double *d_y);
 // order-1 patch kernel (hex_patch_p1.cu; opt-in with HCURL_PATCH_P1=1 until it has been run on a GPU)
 int hex_patch_p1_launch(hcurl_op *op, const hcurl::PatchArgs &a, bool accumulate);
 size_t patch_p1_smem_bytes(int FE, uint32_t blob_cap_bytes, uint32_t xs_cap_bytes);
+// order-2 patch kernel restated as an Env program (hex_patch_p2e.cu; opt-in with HCURL_PATCH_ENV=1, FE = 32)
+int hex_patch_p2e_launch(hcurl_op *op, const hcurl::PatchArgs &a, bool accumulate);
 int hex_fast_prepare_space(hcurl_space *sp);
 int tet_build_emat(hcurl_op *op);
 int tet_apply_launch(hcurl_op *op, const uint32_t *d_map, const double *d_x, double *d_y, double scale);

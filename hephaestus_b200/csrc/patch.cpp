@@ -513,6 +513,15 @@ int hcurl_host_patches_swizzle(const hcurl_host_patches *p, uint8_t *row, uint8_
   memcpy(grp, p->h.swz_grp.data(), p->h.swz_grp.size());
   return 0;
 }
+/* the blob of patch k by lifetime (split-blob kernel variant): part_off [2*n_patch] = begin of the slot-offset lists and
+ * of the per-slot table in 16-byte units; largest header + unit list / largest set of lists in 32-bit words */
+int hcurl_host_patches_parts(const hcurl_host_patches *p, uint32_t *part_off, int64_t *max_d_words, int64_t *max_l_words) {
+  const hcurl::PatchHost &h = p->h;
+  if (part_off) memcpy(part_off, h.part_off.data(), sizeof(uint32_t) * h.part_off.size());
+  if (max_d_words) *max_d_words = h.max_d_words;
+  if (max_l_words) *max_l_words = h.max_l_words;
+  return 0;
+}
 int hcurl_host_patches_copy(const hcurl_host_patches *p, int32_t *perm, uint32_t *blob_off, uint32_t *blob) {
   const hcurl::PatchHost &h = p->h;
   if (perm) memcpy(perm, h.perm.data(), sizeof(int32_t) * h.perm.size());

@@ -292,6 +292,12 @@ int64_t hcurl_host_patches_max_dofs(const hcurl_host_patches *p);
 /* E-vector swizzle chosen by the builder: (slot s, position j) sits at unit s*slot_stride + (j ^ row[s] ^ grp[j / NB]),
  * NB = 128 / unit_bytes; row has nd entries, grp ceil(elems_per_patch / NB) */
 int hcurl_host_patches_swizzle(const hcurl_host_patches *p, uint8_t *row, uint8_t *grp);
+/* split-blob kernel variant: begin of the slot-offset lists and of the per-slot table of every patch blob
+ * (part_off [2*n_patch], 16-byte units) and the largest first two parts in 32-bit words */
+int hcurl_host_patches_parts(const hcurl_host_patches *p, uint32_t *part_off, int64_t *max_d_words, int64_t *max_l_words);
+/* the 1-D transform tables of the order-2 modal element operator (a0, a1, b, c0, c1, d1, d2), for the host-side check
+ * of the kernel program (tests/test_patch_p2_emu.py) */
+int hcurl_host_modal_tables_p2(double *out7);
 int hcurl_host_patches_copy(const hcurl_host_patches *p, int32_t *perm, uint32_t *blob_off, uint32_t *blob);
 
 /* ---- host-side setup helper: ND space on a hex or tet mesh (no GPU needed) ------------------

@@ -14,6 +14,9 @@ for cfg in "1 255" "3 85" "4 64"; do set -- $cfg; timeout 200 python bench.py --
 # opt-in variants written without GPU access (round 1): parity first, then their bench lines
 HCURL_TEST_PATCH_P1=1 timeout 300 python -m pytest tests/test_gpu_apply.py tests/test_gpu_pcg.py -x -q -m gpu -k "p1_patch or order1_patch" > gpurun_out/pytest_p1patch_$tag.log 2>&1; tail -3 gpurun_out/pytest_p1patch_$tag.log
 for fe in 64 128 256; do HCURL_PATCH_P1=1 HCURL_PATCH_FE=$fe timeout 200 python bench.py --order 1 --n 255 --steps 20 --no-cpu --no-e2e --pcg-iters 10 > gpurun_out/bench_p1patch_fe${fe}_$tag.json 2>gpurun_out/bench_p1patch_fe${fe}_$tag.err; done
+HCURL_TEST_PATCH_ENV=1 timeout 300 python -m pytest tests/test_gpu_apply.py -x -q -m gpu -k env_program > gpurun_out/pytest_p2env_$tag.log 2>&1; tail -3 gpurun_out/pytest_p2env_$tag.log
+HCURL_PATCH_ENV=1 timeout 200 python bench.py --steps 20 --no-cpu --no-e2e --pcg-iters 10 > gpurun_out/bench_p2env_$tag.json 2>/dev/null
+HCURL_PATCH_ENV=1 HCURL_PATCH_SPLIT=1 timeout 200 python bench.py --steps 20 --no-cpu --no-e2e --pcg-iters 10 > gpurun_out/bench_p2envsplit_$tag.json 2>/dev/null
 HCURL_TEST_INTERP=1 timeout 300 python -m pytest tests/test_interp.py -x -q -m gpu > gpurun_out/pytest_interp_$tag.log 2>&1; tail -3 gpurun_out/pytest_interp_$tag.log
 HCURL_TEST_SPLIT=1 timeout 300 python -m pytest tests/test_gpu_apply.py -x -q -m gpu -k split > gpurun_out/pytest_split_$tag.log 2>&1; tail -3 gpurun_out/pytest_split_$tag.log
 HCURL_PATCH_SPLIT=1 timeout 200 python bench.py --steps 20 --no-cpu --no-e2e --pcg-iters 10 > gpurun_out/bench_p2split_$tag.json 2>/dev/null

@@ -344,3 +344,48 @@ def test_hex_p1_patch_kernel(ctx, n, fe, monkeypatch):
     op.SetKernel(1)
     assert rel_err(op.Mult(x), oa.constrained_apply(A, ess2, x)) < TOL
     assert op.LastKernel() == 1
+
+
+@pytest.mark.skipif(os.environ.get("HCURL_TEST_PATCH_ENV") != "1",
+                    reason="order-2 patch kernel built from the Env program (hex_patch_p2e.cu): verified on host threads "
+                           "(tests/test_patch_p2_emu.py), not yet run on a GPU; opt in with HCURL_TEST_PATCH_ENV=1")
+@pytest.mark.parametrize("split", ["0", "1"])
+@pytest.mark.parametrize("n", [(9, 8, 6), (5, 4, 3)])
+def test_hex_p2_patch_kernel_env_program(ctx, n, split, monkeypatch):
+    """hex_patch_p2e_kernel (plain and split-blob): same parity bar as the default patch kernel."""
+    monkeypatch.setenv("HCURL_PATCH_ENV", "1")
+    monkeypatch.setenv("HCURL_PATCH_SPLIT", split)
+    monkeypatch.setenv("HCURL_PATCH_FE", "32")
+    m, sp, mo, so = make_pair("hex", n, 2, False, scramble=True)
+    a, b = coefficients(m)
+    gsp = operators.GpuNDSpace(ctx, sp)
+    op = operators.HephGpuOperator(ctx, gsp, 3)
+    op.SetKernel(3)
+    op.SetCoefficients(a, b)
+    essd = sp.boundary_dofs(lambda c: c[:, 0] < 1e-9)
+    op.SetEssentialTrueDofs(essd)
+    x = np.random.default_rng(12345).standard_normal(sp.ndof)
+    A = oa.assemble(so, a, b, q_override=3)
+    assert rel_err(op.Mult(x), oa.constrained_apply(A, essd, x)) < TOL
+    assert op.LastKernel() == 3
+    y0 = np.random.default_rng(1).standard_normal(sp.ndof)
+    assert rel_err(op.MultUnconstrained(x, y0.copy(), scale=-0.5, accumulate=True), y0 - 0.5 * (A @ x)) < TOL
+    ess2 = np.sort(np.random.default_rng(11).choice(sp.ndof, sp.ndof // 5, replace=False)).astype(np.int32)
+    op.SetEssentialTrueDofs(ess2)
+    assert rel_err(op.Mult(x), oa.constrained_apply(A, ess2, x)) < TOL
+    dx, dy = ctx.alloc(sp.ndof).upload(x), ctx.alloc(sp.ndof)
+    for _ in range(3):
+        op.Mult(dx, dy)
+    ctx.synchronize()
+    assert rel_err(dy.download(), oa.constrained_apply(A, ess2, x)) < TOL
+    # Jacobi-PCG through it (fused <p, A p>)
+    s = operators.HephGpuPCG(ctx, tol=1e-9, max_iter=3000)
+    op.SetEssentialTrueDofs(sp.boundary_dofs())
+    s.SetOperator(op)
+    rhs = np.random.default_rng(3).standard_normal(sp.ndof)
+    rhs[sp.boundary_dofs()] = 0.0
+    xs = s.Mult(rhs)
+    assert s.converged
+    Ac, _ = oa.eliminate(A, sp.boundary_dofs())
+    r = rhs - Ac @ xs
+    assert np.sqrt((r * r / Ac.diagonal()).sum() / (rhs * rhs / Ac.diagonal()).sum()) < 10 * s.tol

@@ -45,3 +45,8 @@ def test_first_run_interpolators():
 @pytest.mark.xfail(strict=False, reason="split-blob order-2 patch kernel variant: first execution on a GPU")
 def test_first_run_split_blob_variant():
     _child("HCURL_TEST_SPLIT", ["tests/test_gpu_apply.py", "-k", "split"])
+
+
+@pytest.mark.xfail(strict=False, reason="order-2 patch kernel built from the Env program (plain + split-blob): first execution on a GPU")
+def test_first_run_order2_env_program():
+    _child("HCURL_TEST_PATCH_ENV", ["tests/test_gpu_apply.py", "-k", "env_program"])
