@@ -203,6 +203,9 @@ private:
 /// alpha / beta are the coefficient objects the reference's kernels hold:
 /// CurlCurlKernel::_coef (/root/reference/src/kernels/curl_curl_kernel.hpp:22-23) and
 /// VectorFEMassKernel::_coef (/root/reference/src/kernels/vector_fe_mass_kernel.hpp).
+/// quad_pts_per_dim: 0 = MFEM's full-assembly rules (what the reference's integrators use); HCURL_QUAD_AUTO = the
+/// p+1 rule wherever it is exact (all hexes parallelepipeds: equal to MFEM's rules to round-off, and the fast patch
+/// kernels apply), MFEM's rules otherwise -- the recommended setting once validated against MFEM on the target mesh.
 class HephGpuOperator : public mfem::Operator
 {
 public:

@@ -523,6 +523,14 @@ hcurl_op *hcurl_op_create(hcurl_ctx *ctx, hcurl_space *sp, int q) {
   hcurl_op *op = new hcurl_op;
   op->ctx = ctx; op->sp = sp;
   const int p = sp->order;
+  if (q == HCURL_QUAD_AUTO) {  // one p+1 rule where it is exact (all elements parallelepipeds), MFEM's rules otherwise
+    q = 0;
+    if (sp->geom == HCURL_GEOM_HEX && sp->geom_order == 1) {
+      bool affine = false;
+      if (cudaSetDevice(ctx->device) != cudaSuccess || hex_all_affine(sp, &affine)) { delete op; return nullptr; }
+      if (affine) q = p + 1;
+    }
+  }
   if (sp->geom == HCURL_GEOM_HEX) {
     if (q == 0) {
       op->qc = p + 1;
@@ -532,7 +540,7 @@ hcurl_op *hcurl_op_create(hcurl_ctx *ctx, hcurl_space *sp, int q) {
       op->qc = op->qm = q;
       op->single_rule = true;
     } else {
-      set_error("quad_pts_per_dim must be 0, p+1 or p+2 (got %d for p=%d)", q, p);
+      set_error("quad_pts_per_dim must be 0, p+1, p+2 or HCURL_QUAD_AUTO (got %d for p=%d)", q, p);
       delete op;
       return nullptr;
     }

@@ -371,6 +371,22 @@ __global__ void fast_edata_kernel(const int64_t n_elem, const int64_t n_pad, con
     }
 }
 
+// affine classification alone (no dof-major copies): used by hcurl_op_create for HCURL_QUAD_AUTO
+int hex_all_affine(hcurl_space *sp, bool *all_affine) {
+  if (sp->fast_ready) { *all_affine = sp->all_affine; return 0; }
+  hcurl_ctx *ctx = sp->ctx;
+  int *d_bad = nullptr, h_bad = 0;
+  HC_CUDA(cudaMalloc(&d_bad, sizeof(int)));
+  HC_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
+  fast_affine_kernel<<<(unsigned)((sp->n_elem + 255) / 256), 256, 0, ctx->stream>>>(sp->n_elem, sp->d_xyz, 1e-13, d_bad);
+  HC_CUDA(cudaGetLastError());
+  HC_CUDA(cudaMemcpyAsync(&h_bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  HC_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_bad);
+  *all_affine = (h_bad == 0);
+  return 0;
+}
+
 static bool g_tables_set = false;
 
 int hex_fast_prepare_space(hcurl_space *sp) {

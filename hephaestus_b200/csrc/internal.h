@@ -282,6 +282,7 @@ size_t patch_p1_smem_bytes(int FE, uint32_t blob_cap_bytes, uint32_t xs_cap_byte
 // order-2 patch kernel restated as an Env program (hex_patch_p2e.cu; opt-in with HCURL_PATCH_ENV=1, FE = 32)
 int hex_patch_p2e_launch(hcurl_op *op, const hcurl::PatchArgs &a, bool accumulate);
 int hex_fast_prepare_space(hcurl_space *sp);
+int hex_all_affine(hcurl_space *sp, bool *all_affine);
 int tet_build_emat(hcurl_op *op);
 int tet_apply_launch(hcurl_op *op, const uint32_t *d_map, const double *d_x, double *d_y, double scale);
 int tet_diag_launch(hcurl_op *op, double *d_diag);

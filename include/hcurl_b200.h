@@ -142,8 +142,13 @@ int hcurl_space_elem_ndof(const hcurl_space *sp);
  *                    dimension; mass: p+2 on trilinear hexes, p+3 on HEX27;
  *                    exact rules on straight tets), or p+1 / p+2 to force one
  *                    Gauss rule for both terms on hexes (p+1 is exact on
- *                    affine hexes with per-element-constant coefficients).
+ *                    affine hexes with per-element-constant coefficients);
+ *                    HCURL_QUAD_AUTO = the p+1 rule when every element of a
+ *                    trilinear hex mesh is a parallelepiped (there it equals
+ *                    MFEM's rules to round-off and unlocks the patch kernels),
+ *                    MFEM's rules otherwise.
  */
+enum { HCURL_QUAD_MFEM = 0, HCURL_QUAD_AUTO = -1 };
 hcurl_op *hcurl_op_create(hcurl_ctx *ctx, hcurl_space *sp, int quad_pts_per_dim);
 void hcurl_op_destroy(hcurl_op *op);
 /* Kernel selection: 0 = automatic (fastest eligible: patch kernels for order-2 trilinear hexes

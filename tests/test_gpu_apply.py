@@ -389,3 +389,22 @@ def test_hex_p2_patch_kernel_env_program(ctx, n, split, monkeypatch):
     Ac, _ = oa.eliminate(A, sp.boundary_dofs())
     r = rhs - Ac @ xs
     assert np.sqrt((r * r / Ac.diagonal()).sum() / (rhs * rhs / Ac.diagonal()).sum()) < 10 * s.tol
+
+
+@pytest.mark.skipif(os.environ.get("HCURL_TEST_QAUTO") != "1",
+                    reason="HCURL_QUAD_AUTO added after the round-1 GPU budget was spent; opt in with HCURL_TEST_QAUTO=1")
+def test_quad_auto_picks_the_exact_rule_on_affine_meshes(ctx):
+    """HCURL_QUAD_AUTO (-1): p+1 rule (patch kernel) on parallelepiped meshes -- equal to MFEM's rules to round-off --
+    and MFEM's rules (generic kernel) on a perturbed mesh."""
+    for perturb, kernel in ((False, 3), (True, 1)):
+        m, sp, mo, so = make_pair("hex", (5, 4, 3), 2, perturb)
+        a, b = coefficients(m)
+        gsp = operators.GpuNDSpace(ctx, sp)
+        op = operators.HephGpuOperator(ctx, gsp, -1)
+        op.SetCoefficients(a, b)
+        ess = sp.boundary_dofs()
+        op.SetEssentialTrueDofs(ess)
+        x = np.random.default_rng(4).standard_normal(sp.ndof)
+        A = oa.assemble(so, a, b)                       # MFEM's default rules
+        assert rel_err(op.Mult(x), oa.constrained_apply(A, ess, x)) < TOL
+        assert op.LastKernel() == kernel
