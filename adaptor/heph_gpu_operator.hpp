@@ -337,9 +337,12 @@ private:
 class HephGpuPCG : public mfem::Solver
 {
 public:
+  /// chebyshev_order > 0 replaces the Jacobi preconditioner by a Jacobi-scaled Chebyshev polynomial of that order
+  /// (no reference counterpart; the reference's AMS preconditioner is out of scope)
   HephGpuPCG(HephGpuContext & ctx, float tol = 1.0e-9f, float abstol = 1e-16f,
-             unsigned int max_iter = 1000, int print_level = 0)
-    : _ctx(ctx), _tol(tol), _abstol(abstol), _max_iter((int)max_iter), _print_level(print_level)
+             unsigned int max_iter = 1000, int print_level = 0, int chebyshev_order = 0)
+    : _ctx(ctx), _tol(tol), _abstol(abstol), _max_iter((int)max_iter), _print_level(print_level),
+      _cheb_order(chebyshev_order)
   {
     iterative_mode = true; // like mfem::HyprePCG; NewtonSolver::SetSolver sets it to false
   }
@@ -361,10 +364,12 @@ public:
     }
     hcurl_pcg_destroy(_pcg);
     _gop = gop;
-    _pcg = hcurl_pcg_create(_ctx.Get(), gop->Get(), HCURL_PC_JACOBI);
+    _pcg = hcurl_pcg_create(_ctx.Get(), gop->Get(), _cheb_order > 0 ? HCURL_PC_CHEBYSHEV : HCURL_PC_JACOBI);
     if (!_pcg)
       MFEM_ABORT(std::string("hcurl_pcg_create failed: ") + hcurl_last_error());
     HEPH_GPU_CHECK(hcurl_pcg_set(_pcg, _tol, _abstol, _max_iter, _print_level));
+    if (_cheb_order > 0)
+      HEPH_GPU_CHECK(hcurl_pcg_set_chebyshev(_pcg, _cheb_order, 10));
   }
   void Mult(const mfem::Vector & b, mfem::Vector & x) const override
   {
@@ -385,7 +390,7 @@ public:
 private:
   HephGpuContext & _ctx;
   double _tol, _abstol;
-  int _max_iter, _print_level;
+  int _max_iter, _print_level, _cheb_order;
   const HephGpuOperator * _gop{nullptr};
   hcurl_pcg * _pcg{nullptr};
   mutable int _num_iterations{0};

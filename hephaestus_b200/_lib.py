@@ -66,6 +66,8 @@ SIGNATURES = {
     "hcurl_pcg_solve": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double),
                                   C.POINTER(C.c_int)]),
     "hcurl_pcg_last_loop_ms": (C.c_double, [_P]),
+    "hcurl_pcg_set_chebyshev": (C.c_int, [_P, C.c_int, C.c_int]),
+    "hcurl_pcg_lambda_max": (C.c_double, [_P]),
     "hcurl_interp_create": (_P, [_P, C.c_int, C.c_int, C.c_int64, _P, _P, C.c_int32, C.c_int32]),
     "hcurl_interp_destroy": (None, [_P]),
     "hcurl_interp_apply": (C.c_int, [_P, _P, _P, C.c_int]),
@@ -111,7 +113,7 @@ SIGNATURES = {
 
 HEX, TET = 0, 1
 PER_ELEM, PER_QPT = 0, 1
-PC_NONE, PC_JACOBI = 0, 1
+PC_NONE, PC_JACOBI, PC_CHEBYSHEV = 0, 1, 2
 HOST, DEVICE, DEVICE_EXT = 0, 1, 2
 
 

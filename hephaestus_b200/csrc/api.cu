@@ -194,6 +194,60 @@ __global__ void pcg_dir_kernel(const int64_t n, const double *__restrict__ gamma
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     p[i] = s[i] + beta * p[i];
 }
+// ---- Chebyshev preconditioner (HCURL_PC_CHEBYSHEV) ----------------------------------------------------------
+// deterministic pseudo-random start vector of the power method, values in [0.5, 1.5) (oracle/pcg.py: start_vector)
+__global__ void cheb_seed_kernel(const int64_t n, const uint32_t offset, double *__restrict__ v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t h = ((uint32_t)i + offset) * 2654435761u;
+    h ^= h >> 15;
+    h *= 2246822519u;
+    h ^= h >> 13;
+    v[i] = 0.5 + (double)h / 4294967296.0;
+  }
+}
+// out[0] = <v, w>, out[1] = <v, D v>  (D = 1 / dinv)
+__global__ void __launch_bounds__(RED_THREADS)
+cheb_rayleigh_kernel(const int64_t n, const double *__restrict__ v, const double *__restrict__ w, const double *__restrict__ dinv,
+                     double *partial, unsigned int *counter, double *out, const int which) {
+  double s = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    s += which == 0 ? v[i] * w[i] : v[i] * v[i] / dinv[i];
+  block_finish(s, partial, counter, out);
+}
+// v = scale * dinv * w
+__global__ void cheb_scale_kernel(const int64_t n, const double scale, const double *__restrict__ dinv, const double *__restrict__ w,
+                                  double *__restrict__ v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) v[i] = scale * dinv[i] * w[i];
+}
+// res = r; d = inv_theta * dinv * r; z = d
+__global__ void cheb_start_kernel(const int64_t n, const double inv_theta, const double *__restrict__ dinv, const double *__restrict__ r,
+                                  double *__restrict__ res, double *__restrict__ d, double *__restrict__ z) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double ri = r[i], di = inv_theta * dinv[i] * ri;
+    res[i] = ri;
+    d[i] = di;
+    z[i] = di;
+  }
+}
+// res -= t; d = c1 d + c2 dinv res; z += d
+__global__ void cheb_step_kernel(const int64_t n, const double c1, const double c2, const double *__restrict__ dinv,
+                                 const double *__restrict__ t, double *__restrict__ res, double *__restrict__ d, double *__restrict__ z) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double ri = res[i] - t[i], di = c1 * d[i] + c2 * dinv[i] * ri;
+    res[i] = ri;
+    d[i] = di;
+    z[i] += di;
+  }
+}
+// alpha = gamma / <s,p>; x += alpha p; r -= alpha s
+__global__ void pcg_xr_kernel(const int64_t n, const double *__restrict__ gamma, const double *__restrict__ sdotp, const double *__restrict__ p,
+                              const double *__restrict__ s, double *__restrict__ x, double *__restrict__ r) {
+  const double alpha = *gamma / *sdotp;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    x[i] += alpha * p[i];
+    r[i] -= alpha * s[i];
+  }
+}
 __global__ void invert_kernel(const int64_t n, double *__restrict__ d) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) d[i] = 1.0 / d[i];
 }
@@ -750,7 +804,7 @@ double hcurl_op_last_kernel_ms(hcurl_op *op) {
 // ------------------------------------------------------------------------ PCG ----
 hcurl_pcg *hcurl_pcg_create(hcurl_ctx *ctx, hcurl_op *op, int precond) {
   if (!ctx || !op) { set_error("null context or operator"); return nullptr; }
-  if (precond != HCURL_PC_NONE && precond != HCURL_PC_JACOBI) { set_error("unknown preconditioner %d", precond); return nullptr; }
+  if (precond != HCURL_PC_NONE && precond != HCURL_PC_JACOBI && precond != HCURL_PC_CHEBYSHEV) { set_error("unknown preconditioner %d", precond); return nullptr; }
   HC_CUDA_NULL(cudaSetDevice(ctx->device));
   hcurl_pcg *s = new hcurl_pcg;
   s->ctx = ctx; s->op = op; s->precond = precond;
@@ -760,7 +814,13 @@ hcurl_pcg *hcurl_pcg_create(hcurl_ctx *ctx, hcurl_op *op, int precond) {
   HC_CUDA_NULL(cudaMalloc(&s->d_s, bytes));
   HC_CUDA_NULL(cudaMalloc(&s->d_x, bytes));
   HC_CUDA_NULL(cudaMalloc(&s->d_b, bytes));
-  if (precond == HCURL_PC_JACOBI) HC_CUDA_NULL(cudaMalloc(&s->d_dinv, bytes));
+  if (precond == HCURL_PC_JACOBI || precond == HCURL_PC_CHEBYSHEV) HC_CUDA_NULL(cudaMalloc(&s->d_dinv, bytes));
+  if (precond == HCURL_PC_CHEBYSHEV) {
+    HC_CUDA_NULL(cudaMalloc(&s->d_cres, bytes));
+    HC_CUDA_NULL(cudaMalloc(&s->d_cd, bytes));
+    HC_CUDA_NULL(cudaMalloc(&s->d_ct, bytes));
+    HC_CUDA_NULL(cudaMemset(s->d_cd, 0, bytes));
+  }
   HC_CUDA_NULL(cudaEventCreate(&s->ev0));
   HC_CUDA_NULL(cudaEventCreate(&s->ev1));
   return s;
@@ -770,6 +830,7 @@ void hcurl_pcg_destroy(hcurl_pcg *s) {
   cudaSetDevice(s->ctx->device);
   cudaStreamSynchronize(s->ctx->stream);
   cudaFree(s->d_r); cudaFree(s->d_p); cudaFree(s->d_s); cudaFree(s->d_x); cudaFree(s->d_b); cudaFree(s->d_dinv);
+  cudaFree(s->d_cres); cudaFree(s->d_cd); cudaFree(s->d_ct);
   cudaEventDestroy(s->ev0); cudaEventDestroy(s->ev1);
   if (s->ev_red) cudaEventDestroy(s->ev_red);
   delete s;
@@ -780,8 +841,163 @@ int hcurl_pcg_set(hcurl_pcg *s, double rtol, double atol, int max_iter, int prin
 }
 int hcurl_pcg_update(hcurl_pcg *s) { s->diag_valid = false; return 0; }
 
+int hcurl_pcg_set_chebyshev(hcurl_pcg *s, int order, int power_iters) {
+  if (!s || order < 1 || order > 16 || power_iters < 1) { set_error("hcurl_pcg_set_chebyshev: order must be 1..16, power_iters >= 1"); return 1; }
+  s->cheb_order = order; s->cheb_power_iters = power_iters; s->diag_valid = false;
+  return 0;
+}
+double hcurl_pcg_lambda_max(const hcurl_pcg *s) { return s ? s->lambda_max : 0.0; }
+
+// read n doubles of the reduction scratch on the host (stream-ordered)
+static int read_red(hcurl_ctx *ctx, int n) {
+  HC_CUDA(cudaMemcpyAsync(ctx->h_red, ctx->d_red, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  HC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// lambda_max(D^-1 A) by the power method: Rayleigh quotient <v, A v> / <v, D v> (oracle/pcg.py: power_lambda_max)
+static int cheb_estimate(hcurl_pcg *s) {
+  hcurl_ctx *ctx = s->ctx;
+  hcurl_op *op = s->op;
+  const int64_t nt = op->sp->n_tdof;
+  cudaStream_t st = ctx->stream;
+  const int g = red_grid(ctx, nt);
+  double *S = ctx->d_red, *v = s->d_cd, *w = s->d_ct;
+  // distinct streams of the hash on different ranks (the serial case matches the oracle's start vector)
+  cheb_seed_kernel<<<g, RED_THREADS, 0, st>>>(nt, (uint32_t)ctx->rank * 0x9e3779b9u, v);
+  double lam = 0.0;
+  for (int it = 0; it < s->cheb_power_iters; it++) {
+    if (op_apply_ext(op, v, w, true, 1.0, false)) return 1;
+    cheb_rayleigh_kernel<<<g, RED_THREADS, 0, st>>>(nt, v, w, s->d_dinv, ctx->d_partial, ctx->d_counter, S + 0, 0);
+    cheb_rayleigh_kernel<<<g, RED_THREADS, 0, st>>>(nt, v, w, s->d_dinv, ctx->d_partial, ctx->d_counter, S + 1, 1);
+    if (allreduce_sum(ctx, S, 2)) return 1;
+    if (read_red(ctx, 2)) return 1;
+    lam = ctx->h_red[0] / ctx->h_red[1];
+    // v = D^-1 w, normalised in the D inner product: <D^-1 w, w>
+    cheb_scale_kernel<<<g, RED_THREADS, 0, st>>>(nt, 1.0, s->d_dinv, w, v);
+    cheb_rayleigh_kernel<<<g, RED_THREADS, 0, st>>>(nt, v, w, s->d_dinv, ctx->d_partial, ctx->d_counter, S + 0, 0);
+    if (allreduce_sum(ctx, S, 1)) return 1;
+    if (read_red(ctx, 1)) return 1;
+    if (!(ctx->h_red[0] > 0.0)) { set_error("Chebyshev: power method broke down (operator not positive definite?)"); return 1; }
+    cheb_scale_kernel<<<g, RED_THREADS, 0, st>>>(nt, 1.0 / sqrt(ctx->h_red[0]), s->d_dinv, w, v);
+    ctx->launches += 5;
+  }
+  HC_CUDA(cudaGetLastError());
+  if (!(lam > 0.0)) { set_error("Chebyshev: eigenvalue estimate %g is not positive", lam); return 1; }
+  s->lambda_max = lam;
+  return 0;
+}
+
+// z = q(D^-1 A) D^-1 r: three-term Chebyshev iteration from z = 0 on [0.3, 1.2] * lambda_max (oracle/pcg.py: chebyshev)
+static int cheb_apply(hcurl_pcg *s, const double *r, double *z) {
+  hcurl_ctx *ctx = s->ctx;
+  const int64_t nt = s->op->sp->n_tdof;
+  cudaStream_t st = ctx->stream;
+  const int g = red_grid(ctx, nt);
+  const double lo = 0.3 * s->lambda_max, hi = 1.2 * s->lambda_max;
+  const double theta = 0.5 * (hi + lo), delta = 0.5 * (hi - lo), sigma = theta / delta;
+  cheb_start_kernel<<<g, RED_THREADS, 0, st>>>(nt, 1.0 / theta, s->d_dinv, r, s->d_cres, s->d_cd, z);
+  ctx->launches++;
+  double rho = 1.0 / sigma;
+  for (int j = 1; j < s->cheb_order; j++) {
+    if (op_apply_ext(s->op, s->d_cd, s->d_ct, true, 1.0, false)) return 1;
+    const double rho_new = 1.0 / (2.0 * sigma - rho);
+    cheb_step_kernel<<<g, RED_THREADS, 0, st>>>(nt, rho_new * rho, 2.0 * rho_new / delta, s->d_dinv, s->d_ct, s->d_cres, s->d_cd, z);
+    ctx->launches++;
+    rho = rho_new;
+  }
+  HC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// hypre's PCG loop with the Chebyshev polynomial as C; plain sequence, one host read per iteration
+static int pcg_solve_chebyshev(hcurl_pcg *s, const double *b, double *x, int zero_guess, int where, int *iters, double *final_rel,
+                               int *converged) {
+  hcurl_ctx *ctx = s->ctx;
+  hcurl_op *op = s->op;
+  hcurl_space *sp = op->sp;
+  const int64_t nt = sp->n_tdof;
+  cudaStream_t st = ctx->stream;
+  double *S = ctx->d_red;  // S[0]=gamma S[1]=<s,p> S[2]=gamma_new S[3]=bi_prod
+  const int g = red_grid(ctx, nt);
+  if (!s->diag_valid) {
+    if (op_diag_ext(op, s->d_dinv)) return 1;
+    invert_kernel<<<g, RED_THREADS, 0, st>>>(nt, s->d_dinv);
+    if (cheb_estimate(s)) return 1;
+    s->diag_valid = true;
+  }
+  HC_CUDA(cudaMemcpyAsync(s->d_b, b, sizeof(double) * nt, kind_in(where), st));
+  if (zero_guess) HC_CUDA(cudaMemsetAsync(s->d_x, 0, sizeof(double) * sp->n_ext(), st));
+  else HC_CUDA(cudaMemcpyAsync(s->d_x, x, sizeof(double) * nt, kind_in(where), st));
+  // bi_prod = <C b, b>
+  if (cheb_apply(s, s->d_b, s->d_s)) return 1;
+  dot_kernel<<<g, RED_THREADS, 0, st>>>(nt, s->d_s, s->d_b, ctx->d_partial, ctx->d_counter, S + 3);
+  if (allreduce_sum(ctx, S + 3, 1)) return 1;
+  if (read_red(ctx, 4)) return 1;
+  const double bi_prod = ctx->h_red[3];
+  if (!(bi_prod > 0.0)) {
+    HC_CUDA(cudaMemcpyAsync(x, s->d_b, sizeof(double) * nt, kind_out(where), st));
+    HC_CUDA(cudaStreamSynchronize(st));
+    if (converged) *converged = 1;
+    return 0;
+  }
+  const double eps = fmax(s->rtol * s->rtol, s->atol * s->atol / bi_prod);
+  // r = b - A x ; p = C r ; gamma = <r,p>
+  if (!zero_guess) {
+    if (op_apply_ext(op, s->d_x, s->d_r, true, 1.0, false)) return 1;
+    pcg_init_kernel<<<g, RED_THREADS, 0, st>>>(nt, 1, s->d_b, nullptr, s->d_r, s->d_p, ctx->d_partial, ctx->d_counter, S + 0);  // r = b - r
+  } else HC_CUDA(cudaMemcpyAsync(s->d_r, s->d_b, sizeof(double) * nt, cudaMemcpyDeviceToDevice, st));
+  if (cheb_apply(s, s->d_r, s->d_p)) return 1;
+  dot_kernel<<<g, RED_THREADS, 0, st>>>(nt, s->d_r, s->d_p, ctx->d_partial, ctx->d_counter, S + 0);
+  if (allreduce_sum(ctx, S + 0, 1)) return 1;
+  if (read_red(ctx, 4)) return 1;
+  double gamma = ctx->h_red[0];
+  int i = 0, conv = 0;
+  HC_CUDA(cudaEventRecord(s->ev0, st));
+  while (i + 1 <= s->max_iter) {
+    i++;
+    if (op_apply_ext(op, s->d_p, s->d_s, true, 1.0, false)) return 1;
+    dot_kernel<<<g, RED_THREADS, 0, st>>>(nt, s->d_s, s->d_p, ctx->d_partial, ctx->d_counter, S + 1);
+    if (allreduce_sum(ctx, S + 1, 1)) return 1;
+    pcg_xr_kernel<<<g, RED_THREADS, 0, st>>>(nt, S + 0, S + 1, s->d_p, s->d_s, s->d_x, s->d_r);
+    if (cheb_apply(s, s->d_r, s->d_s)) return 1;
+    dot_kernel<<<g, RED_THREADS, 0, st>>>(nt, s->d_r, s->d_s, ctx->d_partial, ctx->d_counter, S + 2);
+    ctx->launches += 3;
+    if (allreduce_sum(ctx, S + 2, 1)) return 1;
+    if (read_red(ctx, 4)) return 1;
+    const double sdotp = ctx->h_red[1], gamma_new = ctx->h_red[2];
+    if (sdotp == 0.0) break;
+    if (s->print_level > 1 && ctx->rank == 0) printf("  hcurl pcg (chebyshev) it %d  rel res %.6e\n", i, sqrt(fabs(gamma_new) / bi_prod));
+    if (gamma_new / bi_prod < eps) { gamma = gamma_new; conv = 1; break; }
+    if (fabs(gamma_new) < 1e-292) { gamma = gamma_new; break; }
+    pcg_dir_kernel<<<g, RED_THREADS, 0, st>>>(nt, S + 2, S + 0, s->d_s, s->d_p);  // p = s + (gamma_new / gamma) p
+    HC_CUDA(cudaMemcpyAsync(S + 0, S + 2, sizeof(double), cudaMemcpyDeviceToDevice, st));
+    ctx->launches++;
+    gamma = gamma_new;
+  }
+  HC_CUDA(cudaEventRecord(s->ev1, st));
+  HC_CUDA(cudaGetLastError());
+  HC_CUDA(cudaMemcpyAsync(x, s->d_x, sizeof(double) * nt, kind_out(where), st));
+  HC_CUDA(cudaStreamSynchronize(st));
+  cudaEventElapsedTime(&s->last_loop_ms, s->ev0, s->ev1);
+  if (iters) *iters = i;
+  if (final_rel) *final_rel = sqrt(fabs(gamma) / bi_prod);
+  if (converged) *converged = conv;
+  if (s->print_level > 0 && ctx->rank == 0)
+    printf("hcurl pcg (chebyshev order %d, lambda_max %.4f): %d iterations, final relative residual %.6e%s\n", s->cheb_order, s->lambda_max, i,
+           sqrt(fabs(gamma) / bi_prod), conv ? "" : " (not converged)");
+  return 0;
+}
+
 int hcurl_pcg_solve(hcurl_pcg *s, const double *b, double *x, int zero_guess, int where, int *iters, double *final_rel,
                     int *converged) {
+  if (s->precond == HCURL_PC_CHEBYSHEV) {
+    HC_CUDA(cudaSetDevice(s->ctx->device));
+    if (iters) *iters = 0;
+    if (final_rel) *final_rel = 0.0;
+    if (converged) *converged = 0;
+    return pcg_solve_chebyshev(s, b, x, zero_guess, where, iters, final_rel, converged);
+  }
   hcurl_ctx *ctx = s->ctx;
   hcurl_op *op = s->op;
   hcurl_space *sp = op->sp;

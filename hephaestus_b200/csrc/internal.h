@@ -254,6 +254,10 @@ struct hcurl_pcg {
   int max_iter = 1000, print_level = 0;
   double *d_dinv = nullptr, *d_r = nullptr, *d_p = nullptr, *d_s = nullptr, *d_x = nullptr, *d_b = nullptr;
   bool diag_valid = false;
+  // Chebyshev preconditioner: polynomial order, power iterations, eigenvalue estimate, work vectors (extended length)
+  int cheb_order = 3, cheb_power_iters = 10;
+  double lambda_max = 0.0;
+  double *d_cres = nullptr, *d_cd = nullptr, *d_ct = nullptr;
   float last_loop_ms = 0.f;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_red = nullptr;
 };

@@ -312,12 +312,14 @@ class HephGpuPCG:
     (/root/reference/src/solvers/hephaestus_solvers.hpp:39-42); tolerances go
     through C `float` like the reference's InputParameters."""
 
-    def __init__(self, ctx, tol=1.0e-9, abstol=1e-16, max_iter=1000, print_level=0, jacobi=True):
+    def __init__(self, ctx, tol=1.0e-9, abstol=1e-16, max_iter=1000, print_level=0, jacobi=True, chebyshev_order=0):
+        """chebyshev_order > 0: Jacobi-scaled Chebyshev polynomial preconditioner of that order (HCURL_PC_CHEBYSHEV)"""
         self.ctx = ctx
+        self.chebyshev_order = int(chebyshev_order)
         self.tol = float(np.float32(tol))
         self.abstol = float(np.float32(abstol))
         self.max_iter, self.print_level = int(max_iter), int(print_level)
-        self.precond = L.PC_JACOBI if jacobi else L.PC_NONE
+        self.precond = L.PC_CHEBYSHEV if self.chebyshev_order > 0 else (L.PC_JACOBI if jacobi else L.PC_NONE)
         self.iterative_mode = False  # NewtonSolver sets this (zero initial guess)
         self.h = None
         self.op = None
@@ -333,6 +335,8 @@ class HephGpuPCG:
         self.op = op
         self.h = L.check_ptr(L.lib().hcurl_pcg_create(self.ctx.h, op.h, self.precond), "hcurl_pcg_create")
         L.check(L.lib().hcurl_pcg_set(self.h, self.tol, self.abstol, self.max_iter, self.print_level), "hcurl_pcg_set")
+        if self.chebyshev_order > 0:
+            L.check(L.lib().hcurl_pcg_set_chebyshev(self.h, self.chebyshev_order, 10), "hcurl_pcg_set_chebyshev")
 
     def Mult(self, b, x=None):
         if self.h is None:
@@ -354,6 +358,9 @@ class HephGpuPCG:
 
     def last_loop_ms(self):
         return L.lib().hcurl_pcg_last_loop_ms(self.h)
+
+    def lambda_max(self):
+        return L.lib().hcurl_pcg_lambda_max(self.h)
 
     def close(self):
         if self.h:

@@ -44,8 +44,9 @@ enum { HCURL_GEOM_HEX = 0, HCURL_GEOM_TET = 1 };
  * (x-fastest tensor order of the operator's rule; curl rule for alpha, mass
  * rule for beta).  PER_QPT is hex-only. */
 enum { HCURL_COEF_PER_ELEM = 0, HCURL_COEF_PER_QPT = 1 };
-/* preconditioners: HCURL_PC_JACOBI reproduces mfem::HypreDiagScale */
-enum { HCURL_PC_NONE = 0, HCURL_PC_JACOBI = 1 };
+/* preconditioners: HCURL_PC_JACOBI reproduces mfem::HypreDiagScale; HCURL_PC_CHEBYSHEV is a Jacobi-scaled Chebyshev
+ * polynomial (no reference counterpart: the device-side stand-in for the AMS preconditioner, which is out of scope) */
+enum { HCURL_PC_NONE = 0, HCURL_PC_JACOBI = 1, HCURL_PC_CHEBYSHEV = 2 };
 /* where a vector argument lives.  HCURL_DEVICE_EXT (apply entry points only): device vectors with room for
  * hcurl_space_ext_size() entries -- the owned true dofs followed by the rank's ghost dofs -- which the
  * library uses in place (the ghost tail of x is overwritten by the shared-dof exchange, that of y is
@@ -216,6 +217,13 @@ int hcurl_pcg_update(hcurl_pcg *pcg);
  * count, final relative residual sqrt(<Cr,r>/<Cb,b>), converged flag. */
 int hcurl_pcg_solve(hcurl_pcg *pcg, const double *b, double *x, int zero_initial_guess, int where,
                     int *iters, double *final_rel_res, int *converged);
+/* HCURL_PC_CHEBYSHEV: z = q(D^-1 A) D^-1 r, q the Chebyshev polynomial of degree order-1 for the interval
+ * [0.3, 1.2] * lambda_max(D^-1 A) (the interval of mfem::OperatorChebyshevSmoother / hypre's Chebyshev smoother),
+ * order-1 operator applies per preconditioner application; lambda_max by power_iters steps of the power method whenever
+ * the operator changes (hcurl_pcg_update).  Defaults: order 3, 10 power iterations. */
+int hcurl_pcg_set_chebyshev(hcurl_pcg *pcg, int order, int power_iters);
+/* the estimate of lambda_max(D^-1 A) used by the most recent solve (0 before the first) */
+double hcurl_pcg_lambda_max(const hcurl_pcg *pcg);
 /* device time (ms) spent inside the iteration loop of the most recent solve */
 double hcurl_pcg_last_loop_ms(hcurl_pcg *pcg);
 

@@ -55,3 +55,8 @@ def test_first_run_order2_env_program():
 @pytest.mark.xfail(strict=False, reason="HCURL_QUAD_AUTO: first execution on a GPU")
 def test_first_run_quad_auto():
     _child("HCURL_TEST_QAUTO", ["tests/test_gpu_apply.py", "-k", "quad_auto"])
+
+
+@pytest.mark.xfail(strict=False, reason="Chebyshev-preconditioned PCG: first execution on a GPU")
+def test_first_run_chebyshev_pcg():
+    _child("HCURL_TEST_CHEBYSHEV", ["tests/test_gpu_pcg.py", "-k", "chebyshev"])
