@@ -143,3 +143,14 @@ def source_field(X, t):
     f[:, 1] = -vs * pi * pi * t * np.sin(pi * x) * np.cos(pi * y) * np.cos(pi * y) * np.sin(pi * z)
     f[:, 2] = -0.5 * vs * pi * pi * t * np.sin(pi * x) * np.sin(2 * pi * y) * np.cos(pi * z)
     return f
+
+
+# ---- TestHFormSource (test_hform_source.cpp:20-50): the H-formulation's manufactured problem --------------------
+def sigma_expr_hform(X, attr=None):
+    """SigmaExpr, test_hform_source.cpp:34-39; the H-formulation uses rho = 1/sigma as the curl-curl coefficient
+    (/root/reference/src/formulations/HCurl/h_formulation.cpp:124-127) and mu = 1 as the mass coefficient (:75-76 of the test)"""
+    return 1.0 / (1.0 + 0.5 * np.cos(np.pi * X[:, 0]) * np.cos(np.pi * X[:, 1]))
+
+
+hdot_exact = adot_exact      # HdotBc / HExactExpr (test_hform_source.cpp:20-32) are AdotBc / AExactExpr of the A-form test
+source_field_hform = source_field  # SourceField (test_hform_source.cpp:41-50): the same expressions

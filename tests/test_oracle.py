@@ -150,6 +150,16 @@ def test_mms_rate_window_of_TestAForm():
     assert 2 - 0.15 < rate[1] < 2 + 1.0, (nd, err, rate)
 
 
+def test_mms_TestHFormSource_is_the_same_discrete_problem():
+    """Second MMS pin of the reference (test_hform_source.cpp:143-220, same mesh / order / dt / window): the
+    H-formulation's alpha = rho = 1/sigma(x) and beta = mu = 1 are the A-form test's alpha = nu = 1/mu(x) and
+    beta = sigma = 1, with the same source, exact solution and essential data -- so the window asserted in
+    test_mms_rate_window_of_TestAForm pins this test too."""
+    X = np.random.default_rng(0).uniform(0, 1, (1000, 3)) * [8.0, 1.0, 1.0]
+    assert np.array_equal(1.0 / mms.sigma_expr_hform(X), 1.0 / mms.mu_expr(X))
+    assert mms.hdot_exact is mms.adot_exact and mms.source_field_hform is mms.source_field
+
+
 def test_mms_rate_hex_orders():
     """Same manufactured problem on hex cubes: rate ~ p (hex orders >= 2 are not pinned by any
     reference test; this is the strongest available check of their discretisation)."""
