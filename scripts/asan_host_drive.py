@@ -55,6 +55,17 @@ for fe, stride in ((32,33),(32,32),(64,65),(128,129)):
     lib.hcurl_host_patches_copy(h, ptr(perm), ptr(off), ptr(blob)); lib.hcurl_host_patches_destroy(h)
 idx = np.where(sd>=0, sd, -1-sd); code8 = np.ascontiguousarray((idx | np.where(sd<0, 0x80000000, 0)).astype(np.uint32))
 h = lib.hcurl_host_patches_create(54, len(sd), 32, 33, 8, sp.ndof, ptr(cen), ptr(code8), None); assert h; lib.hcurl_host_patches_destroy(h)
+# --- split-blob parts, tensor-ordered slot codes (order-1 patch path, 8-byte units)
+lib.hcurl_host_patches_parts.argtypes = [P, P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+lib.hcurl_host_hex_slot_codes.argtypes = [C.c_int, C.c_int64, P, P]
+h = lib.hcurl_host_patches_create(27, len(sd), 32, 32, 16, sp.ndof//2, ptr(cen), ptr(codes), None); assert h
+part = np.zeros(2*lib.hcurl_host_patches_count(h), np.uint32); md, ml = C.c_int64(), C.c_int64()
+assert lib.hcurl_host_patches_parts(h, ptr(part), C.byref(md), C.byref(ml)) == 0 and md.value > 0 and ml.value > 0
+lib.hcurl_host_patches_destroy(h)
+sp1 = fespace.NDSpace(m,1); sd1 = np.ascontiguousarray(sp1.signed_elem_dofs(), dtype=np.int32)
+c1 = np.zeros(sd1.shape, np.uint32); assert lib.hcurl_host_hex_slot_codes(1, len(sd1), ptr(sd1), ptr(c1)) == 0
+for fe in (32, 128, 256):
+    h = lib.hcurl_host_patches_create(12, len(sd1), fe, fe+1, 8, sp1.ndof, ptr(cen), ptr(c1), None); assert h; lib.hcurl_host_patches_destroy(h)
 # --- exodus
 for f in ("team7.g","cylinder-hex-q2.gen","irises.g"):
     path = "/root/reference/data/"+f
