@@ -13,6 +13,10 @@ oracle's readers and committed as compressed fixtures:
   cylinder_hex_q2.npz   data/cylinder-hex-q2.gen 252 HEX27 -- TestHFormRod / TestEBFormRod / TestComplexAFormRod
                                                              (test/integration/test_hform_rod.cpp:40)
   team7.npz             data/team7.g             57 905 tets -- examples/team7/Main.cpp:154, TestComplexTeam7
+  irises.npz            data/irises.g            8 346 HEX8 -- TestComplexIrisWaveguide, the reference's known-answer test
+                                                             for the hex path (test/integration/test_complex_iris_wg.cpp:90,191-195;
+                                                             `python scripts/make_golden.py irises` writes only this one and
+                                                             irises_vectors.npz)
 
 plus `oracle_vectors.npz`: y = A x of the ORACLE on those meshes for fixed seeded inputs.  These are
 regression vectors of the restatement (they pin the oracle against accidental change and let the
@@ -52,8 +56,25 @@ def coef_by_attr(attr, lo, hi):
     return np.array([vals[a] for a in attr])
 
 
+def irises():
+    """mesh fixture + regression vectors of the oracle for the volume operator of the iris-waveguide KAT
+    (K(1/mu0) + M(-omega^2 eps0), ND1) -- the KAT itself is recomputed by tests/test_oracle_iris_kat.py"""
+    from oracle import iris_kat
+    m = om.read_exodus(os.path.join(DATA, "irises.g"))
+    save_mesh("irises", m)
+    s = osp.NDSpace(m, 1)
+    om2 = (2 * np.pi * iris_kat.FREQ) ** 2
+    A = oa.assemble(s, 1.0 / iris_kat.MU0, -om2 * iris_kat.EPS0)
+    x = np.random.default_rng(12345).standard_normal(s.ndof)
+    np.savez_compressed(os.path.join(OUT, "irises_vectors.npz"), irises_p1_y=A @ x, irises_p1_diag=A.diagonal(), irises_p1_ndof=np.array(s.ndof))
+    print("irises", s.ndof, "dofs", A.nnz, "nnz")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if sys.argv[1:] == ["irises"]:
+        return irises()
+    irises()
     meshes = {
         "beam_tet": om.read_mfem_mesh(os.path.join(DATA, "beam-tet.mesh")),
         "cylinder_hex_q2": om.read_exodus(os.path.join(DATA, "cylinder-hex-q2.gen")),

@@ -1,0 +1,75 @@
+"""The reference's known-answer test for the HEX path, reproduced by the oracle: TestComplexIrisWaveguide
+(/root/reference/test/integration/test_complex_iris_wg.cpp:191-195) requires
+
+    max |E_real| = 4896.771 +- 0.001   and   max |E_imag| = 5357.650 +- 0.001
+
+for the ND1 complex E-formulation on data/irises.g (8 346 HEX8, 29 724 dofs) with TE10 waveguide ports.  oracle/iris_kat.py
+restates that problem on top of the oracle's hex element matrices, assembly and essential elimination; the committed
+mesh fixture is tests/golden/irises.npz (scripts/make_golden.py irises).  This pins the oracle's hex ND1 curl-curl and
+mass operators -- and the MFEM conventions it restates for them (basis, Piola maps, quadrature, dof orientation) -- to
+seven significant digits against numbers the reference's own CI asserts."""
+import os
+
+import numpy as np
+import pytest
+
+from hephaestus_b200 import fespace
+from oracle import iris_kat
+from oracle import space as osp
+
+from helpers import GOLDEN, golden_mesh, rel_err
+
+REF_REAL, REF_IMAG, REF_TOL = 4896.771, 5357.650, 0.001
+
+
+@pytest.fixture(scope="module")
+def kat():
+    m, mo = golden_mesh("irises")
+    return m, mo, iris_kat.solve(mo)
+
+
+def test_iris_waveguide_known_answer(kat):
+    m, mo, (er, ei, space, x) = kat
+    assert space.ndof == 29724
+    assert abs(er - REF_REAL) <= REF_TOL, er          # REQUIRE_THAT(norm_r, WithinAbs(4896.771, 0.001))
+    assert abs(ei - REF_IMAG) <= REF_TOL, ei          # REQUIRE_THAT(norm_i, WithinAbs(5357.650, 0.001))
+
+
+def test_iris_waveguide_answer_is_sensitive_to_the_restated_conventions(kat):
+    """the 0.001 window is tight enough to tell MFEM's 2 x 2 load-vector rule from a 3 x 3 one: a restatement that
+    deviates in such a detail does not pass"""
+    m, mo, _ = kat
+    er3, ei3, _, _ = iris_kat.solve(mo, lf_points=3)
+    assert abs(er3 - REF_REAL) > REF_TOL and abs(er3 - REF_REAL) < 0.01
+
+
+def test_product_dof_map_on_the_kat_mesh(kat):
+    m, mo, (_, _, space, _) = kat
+    sp = fespace.NDSpace(m, 1)
+    assert np.array_equal(sp.signed_elem_dofs(), space.signed_elem_dofs())
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("HCURL_TEST_IRIS") != "1",
+                    reason="added after the round-1 GPU budget was spent; opt in with HCURL_TEST_IRIS=1")
+def test_gpu_operator_of_the_kat(ctx, kat):
+    """the volume operator of the known-answer problem, K(1/mu0) + M(-omega^2 eps0) (negative mass coefficient), and the
+    complex block apply with a loss term, through the C ABI against the oracle"""
+    from hephaestus_b200 import operators
+    from oracle import assemble as oa
+    m, mo, (_, _, space, xk) = kat
+    gv = np.load(os.path.join(GOLDEN, "irises_vectors.npz"))
+    sp = fespace.NDSpace(m, 1)
+    gsp = operators.GpuNDSpace(ctx, sp)
+    om2 = (2 * np.pi * iris_kat.FREQ) ** 2
+    ne = m.n_elem
+    op = operators.HephGpuOperator(ctx, gsp, 0)
+    op.SetCoefficients(np.full(ne, 1.0 / iris_kat.MU0), np.full(ne, -om2 * iris_kat.EPS0))
+    x = np.random.default_rng(12345).standard_normal(sp.ndof)
+    y = op.MultUnconstrained(x, np.zeros(sp.ndof), scale=1.0, accumulate=False)
+    assert rel_err(y, gv["irises_p1_y"]) < 1e-12
+    # applied to the KAT's solution the GPU operator gives what the oracle's gives
+    A = oa.assemble(space, 1.0 / iris_kat.MU0, -om2 * iris_kat.EPS0)
+    for part in (xk.real, xk.imag):
+        part = np.ascontiguousarray(part)
+        assert rel_err(op.MultUnconstrained(part, np.zeros(sp.ndof), scale=1.0, accumulate=False), A @ part) < 1e-12
