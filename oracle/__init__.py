@@ -22,13 +22,17 @@ SubmeshBoundary, no pinned SHA; a fork of MFEM ~4.5/4.6 --
 (ibid. :77-104).  Their published algorithms are restated here.
 
 PARITY PINNING STATUS:
-  * pinned by reference-held tests: the curl-curl element-matrix formula
+  * pinned by reference-held tests: the known answer of TestComplexIrisWaveguide
+    for ND1 hexes (/root/reference/test/integration/test_complex_iris_wg.cpp:191-195,
+    reproduced to 7 digits by iris_kat.py), the curl-curl element-matrix formula
     (/root/reference/test/unit/test_nlintegrators.cpp:47-59) and the ND2-tet
-    MMS convergence window of TestAForm
+    MMS convergence windows of TestAForm / TestHFormSource
     (/root/reference/test/integration/test_aform_source.cpp:130-208);
-  * hex order >= 2 operator values and MFEM's global DOF numbering:
-    PARITY UNPINNED (no reference test holds values for them; MFEM cannot be
-    built here).  They are validated by mathematical invariants instead.
+  * hex order >= 2 operator values (same order-generic code as the pinned
+    order 1, no reference test of their own), MFEM's global DOF numbering and
+    the discrete curl / gradient local matrices (interp.py): PARITY UNPINNED
+    (no reference test holds values for them; MFEM cannot be built here).
+    They are validated by mathematical invariants instead.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 --impl reference legs may import this package.  The product package
