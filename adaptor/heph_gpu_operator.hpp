@@ -289,18 +289,42 @@ public:
   {
     // ND_FECollection(p) and H1_FECollection(p) report p; RT_FECollection(p-1) pairs with them
     const int p = domain.FEColl()->GetOrder();
+    mfem::ParMesh * mesh = domain.GetParMesh();
+    const bool tets = mesh->GetNE() > 0 && mesh->GetElementGeometry(0) == mfem::Geometry::TETRAHEDRON;
     std::vector<int32_t> in, out;
-    TensorDofs(domain, in);
-    TensorDofs(range, out);
-    _it = hcurl_interp_create(ctx.Get(), (int)kind, p, domain.GetParMesh()->GetNE(), in.data(), out.data(),
-                              domain.GetVSize(), range.GetVSize());
+    if (tets)
+    { // lowest order only (the TEAM7 configuration): MFEM's own local order, no dof map involved
+      NativeDofs(domain, in);
+      NativeDofs(range, out);
+    }
+    else
+    {
+      TensorDofs(domain, in);
+      TensorDofs(range, out);
+    }
+    _it = hcurl_interp_create_geom(ctx.Get(), tets ? HCURL_GEOM_TET : HCURL_GEOM_HEX, (int)kind, p, mesh->GetNE(), in.data(),
+                                   out.data(), domain.GetVSize(), range.GetVSize());
     if (!_it)
-      MFEM_ABORT(std::string("hcurl_interp_create failed: ") + hcurl_last_error());
+      MFEM_ABORT(std::string("hcurl_interp_create_geom failed: ") + hcurl_last_error());
   }
   ~HephGpuDiscreteInterpolator() override { hcurl_interp_destroy(_it); }
   void Mult(const mfem::Vector & x, mfem::Vector & y) const override
   {
     HEPH_GPU_CHECK(hcurl_interp_apply(_it, x.HostRead(), y.HostWrite(), HCURL_HOST));
+  }
+
+  /// [ne][nd] element dofs exactly as FiniteElementSpace::GetElementDofs returns them
+  static void NativeDofs(const mfem::ParFiniteElementSpace & fes, std::vector<int32_t> & out)
+  {
+    const int ne = fes.GetParMesh()->GetNE();
+    mfem::Array<int> dofs;
+    out.clear();
+    for (int e = 0; e < ne; e++)
+    {
+      fes.GetElementDofs(e, dofs);
+      for (int t = 0; t < dofs.Size(); t++)
+        out.push_back(dofs[t]);
+    }
   }
 
   /// [ne][nd] element dofs in tensor order, FiniteElementSpace::GetElementDofs encoding (k or -1-k)

@@ -69,6 +69,8 @@ SIGNATURES = {
     "hcurl_pcg_set_chebyshev": (C.c_int, [_P, C.c_int, C.c_int]),
     "hcurl_pcg_lambda_max": (C.c_double, [_P]),
     "hcurl_interp_create": (_P, [_P, C.c_int, C.c_int, C.c_int64, _P, _P, C.c_int32, C.c_int32]),
+    "hcurl_interp_create_geom": (_P, [_P, C.c_int, C.c_int, C.c_int, C.c_int64, _P, _P, C.c_int32, C.c_int32]),
+    "hcurl_host_interp_tet_matrix": (C.c_int, [C.c_int, _P]),
     "hcurl_interp_destroy": (None, [_P]),
     "hcurl_interp_apply": (C.c_int, [_P, _P, _P, C.c_int]),
     "hcurl_host_interp_matrix": (C.c_int, [C.c_int, _P]),

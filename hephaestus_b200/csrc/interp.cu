@@ -38,7 +38,33 @@ void interp_matrix(int p, double *D) {
     for (int j = 0; j <= p; j++) D[i * (p + 1) + j] = G[(size_t)i * (p + 1) + j];
 }
 
-int interp_sizes(int kind, int p, int *nd_in, int *nd_out) {
+// tets, order 1: local matrices in MFEM's edge order (0,1),(0,2),(0,3),(1,2),(1,3),(2,3) and face order (1,2,3),(0,3,2),(0,1,3),(0,2,1)
+void interp_tet_matrix(int kind, double *M) {
+  static const int E[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
+  static const double GL[4][3] = {{-1, -1, -1}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}};      // gradients of the barycentric coordinates
+  static const double NK[4][3] = {{1, 1, 1}, {-1, 0, 0}, {0, -1, 0}, {0, 0, -1}};       // RT_TetrahedronElement::nk
+  for (int i = 0; i < 24; i++) M[i] = 0.0;
+  if (kind == HCURL_INTERP_GRAD) {
+    for (int e = 0; e < 6; e++) { M[e * 4 + E[e][0]] = -1.0; M[e * 4 + E[e][1]] = 1.0; }  // phi(b) - phi(a)
+  } else {
+    for (int f = 0; f < 4; f++)
+      for (int e = 0; e < 6; e++) {
+        const double *a = GL[E[e][0]], *b = GL[E[e][1]];  // curl of the Whitney function: 2 grad(l_a) x grad(l_b)
+        const double c[3] = {2 * (a[1] * b[2] - a[2] * b[1]), 2 * (a[2] * b[0] - a[0] * b[2]), 2 * (a[0] * b[1] - a[1] * b[0])};
+        M[f * 6 + e] = NK[f][0] * c[0] + NK[f][1] * c[1] + NK[f][2] * c[2];
+      }
+  }
+}
+
+int interp_sizes(int kind, int p, int *nd_in, int *nd_out, int geom = HCURL_GEOM_HEX) {
+  if (geom == HCURL_GEOM_TET) {
+    if (p != 1) { set_error("tet interpolators: order 1 only (got %d)", p); return 1; }
+    if (kind == HCURL_INTERP_GRAD) { *nd_in = 4; *nd_out = 6; }
+    else if (kind == HCURL_INTERP_CURL) { *nd_in = 6; *nd_out = 4; }
+    else { set_error("unknown interpolator kind %d", kind); return 1; }
+    return 0;
+  }
+  if (geom != HCURL_GEOM_HEX) { set_error("unknown geometry %d", geom); return 1; }
   if (p < 1 || p > 4) { set_error("interpolator order must be 1..4 (got %d)", p); return 1; }
   const int nd_h1 = (p + 1) * (p + 1) * (p + 1), nd_nd = 3 * p * (p + 1) * (p + 1), nd_rt = 3 * p * p * (p + 1);
   if (kind == HCURL_INTERP_GRAD) { *nd_in = nd_h1; *nd_out = nd_nd; }
@@ -73,18 +99,24 @@ extern "C" {
 
 hcurl_interp *hcurl_interp_create(hcurl_ctx *ctx, int kind, int order, int64_t n_elem, const int32_t *in_dofs, const int32_t *out_dofs,
                                   int32_t n_in, int32_t n_out) {
+  return hcurl_interp_create_geom(ctx, HCURL_GEOM_HEX, kind, order, n_elem, in_dofs, out_dofs, n_in, n_out);
+}
+
+hcurl_interp *hcurl_interp_create_geom(hcurl_ctx *ctx, int geom, int kind, int order, int64_t n_elem, const int32_t *in_dofs,
+                                       const int32_t *out_dofs, int32_t n_in, int32_t n_out) {
   if (!ctx || n_elem <= 0 || !in_dofs || !out_dofs || n_in <= 0 || n_out <= 0) { set_error("hcurl_interp_create: bad arguments"); return nullptr; }
   if ((int64_t)n_in > (int64_t)INTERP_IDX || (int64_t)n_out > (int64_t)INTERP_IDX) { set_error("too many dofs for the 30-bit map encoding"); return nullptr; }
   int nd_in = 0, nd_out = 0;
-  if (interp_sizes(kind, order, &nd_in, &nd_out)) return nullptr;
+  if (interp_sizes(kind, order, &nd_in, &nd_out, geom)) return nullptr;
   std::vector<uint32_t> im((size_t)n_elem * nd_in), omap((size_t)n_elem * nd_out);
   if (interp_encode(n_elem, nd_in, nd_out, in_dofs, out_dofs, n_in, n_out, im.data(), omap.data())) return nullptr;
   HC_CUDA_NULL(cudaSetDevice(ctx->device));
   hcurl_interp *it = new hcurl_interp;
   it->ctx = ctx; it->n_in = n_in; it->n_out = n_out;
   memset(&it->a, 0, sizeof(it->a));
-  it->a.kind = kind; it->a.p = order; it->a.n_elem = n_elem; it->a.nd_in = nd_in; it->a.nd_out = nd_out;
-  interp_matrix(order, it->a.D);
+  it->a.kind = kind; it->a.geom = geom == HCURL_GEOM_TET ? 1 : 0; it->a.p = order; it->a.n_elem = n_elem; it->a.nd_in = nd_in; it->a.nd_out = nd_out;
+  if (geom == HCURL_GEOM_TET) interp_tet_matrix(kind, it->a.Mloc);
+  else interp_matrix(order, it->a.D);
   if (!cuda_ok(cudaMalloc(&it->d_in, sizeof(uint32_t) * im.size()), "cudaMalloc") ||
       !cuda_ok(cudaMalloc(&it->d_out, sizeof(uint32_t) * omap.size()), "cudaMalloc") ||
       !cuda_ok(cudaMemcpy(it->d_in, im.data(), sizeof(uint32_t) * im.size(), cudaMemcpyHostToDevice), "cudaMemcpy") ||
@@ -133,6 +165,11 @@ int hcurl_interp_apply(hcurl_interp *it, const double *x, double *y, int where) 
 int hcurl_host_interp_matrix(int order, double *D) {
   if (order < 1 || order > 4 || !D) { set_error("hcurl_host_interp_matrix: bad arguments"); return 1; }
   interp_matrix(order, D);
+  return 0;
+}
+int hcurl_host_interp_tet_matrix(int kind, double *M24) {
+  if ((kind != HCURL_INTERP_GRAD && kind != HCURL_INTERP_CURL) || !M24) { set_error("hcurl_host_interp_tet_matrix: bad arguments"); return 1; }
+  interp_tet_matrix(kind, M24);
   return 0;
 }
 int hcurl_host_interp_encode(int kind, int order, int64_t n_elem, const int32_t *in_dofs, const int32_t *out_dofs, int32_t n_in, int32_t n_out,

@@ -12,7 +12,11 @@
 //   grad:  (G phi)_c (i_c open, others closed)  = sum_j D[i_c][j] phi(.. j ..)
 //   curl:  (C u)_c   (i_c closed, i_a, i_b open) = sum_j D[i_a][j] u_b(.. a: j ..) - sum_j D[i_b][j] u_a(.. b: j ..),
 //          (a, b) = (c+1, c+2) cyclic.
-// Local layouts (all x fastest, component-major): H1 (p+1)^3; ND component c: p points along c, p+1 along the others;
+// Tets (order 1 only: the TEAM7 configuration, ND1 -> RT0 and H1 P1 -> ND1): MFEM's reference tet has the Whitney edge
+// functions (dof = u(midpoint) . (x_b - x_a)) and RT0 face functions with dof = v(centroid) . nk, nk = 2 x area-weighted
+// outward normal [MFEM-upstream: ND_TetrahedronElement::tk, RT_TetrahedronElement::nk = {1,1,1, -1,0,0, 0,-1,0, 0,0,-1}],
+// so the gradient matrix is the edge-vertex incidence (+-1) and the curl matrix the face-edge incidence times 2.
+// Local layouts, hexes (all x fastest, component-major): H1 (p+1)^3; ND component c: p points along c, p+1 along the others;
 // RT component c: p+1 points along c, p along the others.  The element -> dof maps arrive in THIS order (the adaptor
 // converts with MFEM's own TensorBasisElement::GetDofMap()), encoded as index | bit 31 sign flip; bit 30 of an OUTPUT
 // entry = "another element writes this dof" (a dof shared by several elements is written once, by its first element:
@@ -34,6 +38,7 @@ static constexpr uint32_t INTERP_IDX = 0x3fffffffu, INTERP_SKIP = 0x40000000u, I
 
 struct InterpArgs {
   int kind;  // HCURL_INTERP_GRAD (0) or HCURL_INTERP_CURL (1)
+  int geom;  // HCURL_GEOM_HEX (tensor path) or HCURL_GEOM_TET (order 1: the dense local matrix Mloc)
   int p;
   int64_t n_elem;
   int nd_in, nd_out;
@@ -41,7 +46,8 @@ struct InterpArgs {
   const uint32_t *out_map;  // [n_elem][nd_out]
   const double *x;
   double *y;
-  double D[4 * 5];  // [i * (p+1) + j]
+  double D[4 * 5];  // hexes: [i * (p+1) + j]
+  double Mloc[24];  // tets, order 1: [t_out * nd_in + j] (gradient 6 x 4, curl 4 x 6), entries 0, +-1 (gradient), 0, +-2 (curl)
 };
 
 HCURL_HD double interp_in(const InterpArgs &a, const uint32_t *im, int t) {
@@ -66,6 +72,15 @@ HCURL_HD void interp_thread(const InterpArgs &a, int64_t gid) {
   const uint32_t om = a.out_map[gid];
   if (om & INTERP_SKIP) return;
   const uint32_t *im = a.in_map + e * a.nd_in;
+  if (a.geom != 0) {  // tets: lowest order, MFEM's local edge / face order on both sides
+    double v = 0.0;
+    for (int j = 0; j < a.nd_in; j++) {
+      const double m = a.Mloc[t * a.nd_in + j];
+      if (m != 0.0) v += m * interp_in(a, im, j);
+    }
+    a.y[om & INTERP_IDX] = (om & INTERP_NEG) ? -v : v;
+    return;
+  }
   const int per_comp = a.nd_out / 3;
   const int c = t / per_comp;
   int r = t - c * per_comp;

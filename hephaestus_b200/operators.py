@@ -275,12 +275,13 @@ class HephGpuInterpolator:
     (/root/reference/src/auxsolvers/curl_aux.cpp:13-30, /root/reference/src/sources/scalar_potential_source.cpp:89-97)."""
     GRAD, CURL = 0, 1
 
-    def __init__(self, ctx, kind, order, in_dofs, out_dofs, n_in, n_out):
+    def __init__(self, ctx, kind, order, in_dofs, out_dofs, n_in, n_out, geom=L.HEX):
+        """hexes: element dofs in tensor order, orders 1..4; geom=L.TET: order 1, MFEM's local vertex / edge / face order"""
         self.ctx = ctx
         i, o = L.as_i32(in_dofs), L.as_i32(out_dofs)
         self.n_in, self.n_out = int(n_in), int(n_out)
-        self.h = L.check_ptr(L.lib().hcurl_interp_create(ctx.h, kind, order, i.shape[0], L.ptr(i), L.ptr(o), self.n_in, self.n_out),
-                             "hcurl_interp_create")
+        self.h = L.check_ptr(L.lib().hcurl_interp_create_geom(ctx.h, geom, kind, order, i.shape[0], L.ptr(i), L.ptr(o), self.n_in, self.n_out),
+                             "hcurl_interp_create_geom")
 
     def Mult(self, x, y=None):
         if isinstance(x, DeviceVector):

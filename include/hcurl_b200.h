@@ -241,12 +241,18 @@ double hcurl_pcg_last_loop_ms(hcurl_pcg *pcg);
 enum { HCURL_INTERP_GRAD = 0, HCURL_INTERP_CURL = 1 };
 hcurl_interp *hcurl_interp_create(hcurl_ctx *ctx, int kind, int order, int64_t n_elem, const int32_t *in_dofs,
                                   const int32_t *out_dofs, int32_t n_in, int32_t n_out);
+/* the same for a given geometry: HCURL_GEOM_HEX as above; HCURL_GEOM_TET: order 1 only (ND1 -> RT0, H1 P1 -> ND1, the
+ * TEAM7 configuration), element dofs in MFEM's own local order (GetElementDofs as is): 4 vertices / 6 edges / 4 faces */
+hcurl_interp *hcurl_interp_create_geom(hcurl_ctx *ctx, int geom, int kind, int order, int64_t n_elem, const int32_t *in_dofs,
+                                       const int32_t *out_dofs, int32_t n_in, int32_t n_out);
 void hcurl_interp_destroy(hcurl_interp *it);
 /* y [n_out] = Interp x [n_in]; where = HCURL_HOST or HCURL_DEVICE */
 int hcurl_interp_apply(hcurl_interp *it, const double *x, double *y, int where);
 /* host-only (no GPU): the 1-D matrix D[i*(p+1)+j] = derivative of the closed basis function j at the open node i, and
  * the encoded maps (index | bit 31 sign | bit 30 on outputs: another element writes this dof) */
 int hcurl_host_interp_matrix(int order, double *D);
+/* tets, order 1: the local matrix [n_out_local * n_in_local] (gradient 6 x 4, curl 4 x 6), 24 doubles */
+int hcurl_host_interp_tet_matrix(int kind, double *M24);
 int hcurl_host_interp_encode(int kind, int order, int64_t n_elem, const int32_t *in_dofs, const int32_t *out_dofs,
                              int32_t n_in, int32_t n_out, uint32_t *in_map, uint32_t *out_map);
 

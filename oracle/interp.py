@@ -89,9 +89,13 @@ def local_curl_matrix(p):
     return Ct[np.arange(len(nodes)), :, comp]
 
 
-def apply(kind, p, in_dofs, out_dofs, n_out, x):
-    """y = Interp x with signed (-1-k) tensor-ordered element dofs; every element overwrites its output dofs"""
-    M = local_grad_matrix(p) if kind == "grad" else local_curl_matrix(p)
+def apply(kind, p, in_dofs, out_dofs, n_out, x, tet=False):
+    """y = Interp x with signed (-1-k) element dofs (hexes: tensor order; tets: MFEM's local order, order 1); every
+    element overwrites its output dofs"""
+    if tet:
+        M = tet_local_grad_matrix() if kind == "grad" else tet_local_curl_matrix()
+    else:
+        M = local_grad_matrix(p) if kind == "grad" else local_curl_matrix(p)
     ii = np.where(in_dofs >= 0, in_dofs, -1 - in_dofs)
     si = np.where(in_dofs >= 0, 1.0, -1.0)
     oi = np.where(out_dofs >= 0, out_dofs, -1 - out_dofs)
@@ -100,3 +104,25 @@ def apply(kind, p, in_dofs, out_dofs, n_out, x):
     ye = (M @ (si * x[ii]).T).T * so
     y[oi.ravel()] = ye.ravel()
     return y
+
+
+# ---- tets, order 1 (ND1 -> RT0, H1 P1 -> ND1) ---------------------------------------------------------------------
+# [MFEM-upstream] RT_TetrahedronElement::nk: dof_f(v) = v(face centroid) . nk_f on the reference tet, nk = twice the
+# area-weighted outward normal; faces in MFEM's order (1,2,3), (0,3,2), (0,1,3), (0,2,1)
+TET_NK = np.array([[1.0, 1.0, 1.0], [-1.0, 0.0, 0.0], [0.0, -1.0, 0.0], [0.0, 0.0, -1.0]])
+
+
+def tet_local_curl_matrix():
+    """C[f, e] = nk_f . curl(N_e)(centroid of face f), N the oracle's ND1 tet basis (nd_tet.py)"""
+    from .nd_tet import NDTet, TET_FACES, TET_VERTS
+    fe = NDTet(1)
+    cen = np.array([TET_VERTS[list(f)].mean(axis=0) for f in TET_FACES])
+    _, C = fe.shape_and_curl(cen)                                  # (4 points, 6 dofs, 3)
+    return np.einsum("fd,fed->fe", TET_NK, C)
+
+
+def tet_local_grad_matrix():
+    """G[e, v] = tk_e . grad(lambda_v) with tk_e = x_b - x_a (the ND1 dof functional applied to the P1 hat functions)"""
+    from .nd_tet import TET_EDGES, TET_VERTS
+    gl = np.array([[-1.0, -1.0, -1.0], [1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [0.0, 0.0, 1.0]])
+    return np.array([[(TET_VERTS[b] - TET_VERTS[a]) @ gl[v] for v in range(4)] for a, b in TET_EDGES])
