@@ -1,4 +1,5 @@
-"""Domain decomposition of the synthetic structured hex cube across ranks (one per GPU).
+"""Domain decomposition across ranks (one per GPU): the synthetic structured hex cube (BrickProblem, nothing global is
+materialised) and any mesh under a host-supplied element partition (GeneralProblem, at the end of the file).
 
 Stands in for what Hephaestus gets from ``mfem::ParMesh(MPI_COMM_WORLD, mesh)``
 (/root/reference/examples/team7/Main.cpp:155) + ``ParFiniteElementSpace``: element partition,
@@ -272,3 +273,109 @@ def ext_index(local):
     l2e[local.ghost_ldof] = local.n_tdof + np.arange(len(local.ghost_ldof))
     assert np.all(l2e >= 0)
     return l2e
+
+
+# ---- general (unstructured) meshes: host-supplied element partition -------------------------------------------------
+class GeneralProblem:
+    """One rank's share of ANY mesh under a host-supplied element -> rank array ("METIS / host-supplied
+    partition array for unstructured" -- what mfem::ParMesh(comm, mesh, partitioning) + ParFiniteElementSpace produce
+    from METIS output, /root/reference/examples/team7/Main.cpp:155).  Built from the serial space, so every rank uses
+    the serial space's dof orientation and face-dof ordering: a shared dof is the same functional on all ranks
+    (ghost_sign = +1), the lists of a neighbour pair are matched by ascending serial dof number, and the owner of a
+    shared dof is the lowest rank that holds it (MFEM's convention).  Suited to real meshes (team7: 57 905 tets); the
+    synthetic 1e9-dof cubes use BrickProblem, which never materialises anything global.
+
+    attributes: elems (serial element ids of this rank), l2g (local dof -> serial dof), local (LocalSpace),
+    ess_tdofs (true-dof indices of the given serial essential dofs that this rank owns), space (the serial space)."""
+
+    def __init__(self, space, elem_rank, rank, ess_dofs=None):
+        mesh = space.mesh
+        elem_rank = np.asarray(elem_rank)
+        assert elem_rank.shape == (mesh.n_elem,)
+        sd = np.asarray(space.signed_elem_dofs()).astype(np.int64)          # serial dof, -1-k = flipped
+        gd = np.where(sd >= 0, sd, -1 - sd)
+        # lowest rank holding each serial dof, and who else holds it
+        world = int(elem_rank.max()) + 1
+        owner = np.full(space.ndof, world, dtype=np.int64)
+        np.minimum.at(owner, gd.ravel(), np.repeat(elem_rank, gd.shape[1]))
+        self.rank, self.space = rank, space
+        self.elems = np.nonzero(elem_rank == rank)[0]
+        mine = gd[self.elems]
+        self.l2g = np.unique(mine)                                          # ascending serial numbers
+        g2l = -np.ones(space.ndof, dtype=np.int64)
+        g2l[self.l2g] = np.arange(len(self.l2g))
+        loc = g2l[mine]
+        L = LocalSpace()
+        L.elem_xyz = mesh.elem_xyz()[self.elems]
+        L.elem_ldof = np.where(sd[self.elems] >= 0, loc, -1 - loc).astype(np.int32)
+        L.elem_verts = mesh.elems[self.elems].astype(np.int32) if mesh.kind == "tet" else None
+        fb = getattr(space, "elem_face_base", None)
+        L.elem_face_base = np.asarray(fb)[self.elems].astype(np.int32) if (mesh.kind == "tet" and fb is not None and space.p >= 2) else None
+        L.n_ldof = len(self.l2g)
+        owned = owner[self.l2g] == rank
+        ltdof = -np.ones(L.n_ldof, dtype=np.int64)
+        ltdof[owned] = np.arange(int(owned.sum()))
+        L.ldof_ltdof = ltdof.astype(np.int32)
+        L.n_tdof = int(owned.sum())
+        # which other ranks hold my dofs
+        held = {}                                                           # rank q -> serial dofs q holds that I hold too
+        for q in range(world):
+            if q == rank:
+                continue
+            hq = np.zeros(space.ndof, dtype=bool)
+            hq[gd[elem_rank == q].ravel()] = True
+            common = self.l2g[hq[self.l2g]]
+            if len(common):
+                held[q] = common
+        own_off, own_ldof, ghost_off, ghost_ldof = [0], [], [0], []
+        nbrs = []
+        for q in sorted(held):
+            common = held[q]                                                # ascending serial numbers on both sides
+            mine_owned = common[owner[common] == rank]
+            theirs = common[owner[common] == q]
+            if len(mine_owned) == 0 and len(theirs) == 0:
+                continue                                                    # shared only through dofs a third rank owns
+            nbrs.append(q)
+            own_ldof.append(g2l[mine_owned])
+            ghost_ldof.append(g2l[theirs])
+            own_off.append(own_off[-1] + len(mine_owned))
+            ghost_off.append(ghost_off[-1] + len(theirs))
+        cat = lambda xs, dt: np.concatenate(xs).astype(dt) if xs else np.zeros(0, dt)  # noqa: E731
+        L.nbr_rank = np.array(nbrs, dtype=np.int32)
+        L.own_off, L.own_ldof = np.array(own_off, np.int32), cat(own_ldof, np.int32)
+        L.ghost_off, L.ghost_ldof = np.array(ghost_off, np.int32), cat(ghost_ldof, np.int32)
+        L.ghost_sign = np.ones(len(L.ghost_ldof), dtype=np.int8)
+        # every dof I do not own must arrive from exactly one neighbour (its owner)
+        assert len(L.ghost_ldof) == int((~owned).sum()) and len(np.unique(L.ghost_ldof)) == len(L.ghost_ldof)
+        self.local = L
+        if ess_dofs is not None:
+            e = np.asarray(ess_dofs, dtype=np.int64)
+            e = e[g2l[e] >= 0]
+            t = ltdof[g2l[e]]
+            self.ess_tdofs = np.sort(t[t >= 0]).astype(np.int32)
+        else:
+            self.ess_tdofs = np.zeros(0, np.int32)
+
+
+def general_problem(space, elem_rank, rank, ess_dofs=None):
+    return GeneralProblem(space, elem_rank, rank, ess_dofs)
+
+
+def partition_by_coordinate(mesh, world):
+    """A simple host-side element partition for tests and examples (recursive coordinate bisection of the element
+    centroids into `world` parts of near-equal size); production use passes METIS output instead."""
+    cen = mesh.verts[mesh.elems].mean(axis=1)
+    part = np.zeros(mesh.n_elem, dtype=np.int64)
+
+    def split(idx, lo, hi):
+        if hi - lo == 1:
+            part[idx] = lo
+            return
+        mid = (lo + hi) // 2
+        ax = int(np.argmax(cen[idx].max(axis=0) - cen[idx].min(axis=0)))
+        order = idx[np.argsort(cen[idx, ax], kind="stable")]
+        k = len(order) * (mid - lo) // (hi - lo)
+        split(order[:k], lo, mid)
+        split(order[k:], mid, hi)
+    split(np.arange(mesh.n_elem), 0, world)
+    return part

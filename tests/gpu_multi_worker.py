@@ -16,8 +16,49 @@ from helpers import dof_descriptors, match_dofs  # noqa: E402
 from test_partition import coef, serial_problem  # noqa: E402
 
 
+def general_main(ctx, rank, world, name, p):
+    """a reference mesh (committed fixture) under a host-supplied element partition (partition.GeneralProblem): apply and
+    Jacobi-PCG against the serial oracle; local dofs keep the serial orientation, so no sign bookkeeping here"""
+    from hephaestus_b200 import fespace
+    from helpers import coef_by_attr, golden_mesh
+    m, mo = golden_mesh(name)
+    sp, so = fespace.NDSpace(m, p), osp.NDSpace(mo, p)
+    part = partition.partition_by_coordinate(m, world)
+    ess = sp.boundary_dofs()
+    gp = partition.general_problem(sp, part, rank, ess)
+    L = gp.local
+    gsp = operators.GpuNDSpace(ctx, sp, L)
+    op = operators.HephGpuOperator(ctx, gsp, 0)
+    a, b = 0.05 * coef_by_attr(m.attr, 0.5, 2.0), coef_by_attr(m.attr, 1.0, 1.0e3)
+    op.SetCoefficients(a[gp.elems], b[gp.elems])
+    op.SetEssentialTrueDofs(gp.ess_tdofs)
+    A = oa.assemble(so, a, b)
+    own = np.nonzero(L.ldof_ltdof >= 0)[0]
+    own = own[np.argsort(L.ldof_ltdof[own])]
+    g = gp.l2g[own]
+    x_s = np.random.default_rng(5).standard_normal(so.ndof)
+    y_s = oa.constrained_apply(A, ess, x_s)
+    err = np.linalg.norm(op.Mult(x_s[g]) - y_s[g]) / np.linalg.norm(y_s)
+    assert err < 1e-12, ("apply", rank, err)
+    Ac, _ = oa.eliminate(A, ess)
+    b_s = Ac @ np.random.default_rng(54321).standard_normal(so.ndof)
+    solver = operators.HephGpuPCG(ctx, tol=1e-8, max_iter=5000)
+    solver.SetOperator(op)
+    xs = solver.Mult(b_s[g])
+    xo, it_o, _, conv_o, _ = opcg.pcg(Ac, b_s, diag=Ac.diagonal(), rtol=solver.tol, atol=solver.abstol, max_iter=5000)
+    assert solver.converged and conv_o
+    assert abs(solver.num_iterations - it_o) <= max(2, it_o // 100), (solver.num_iterations, it_o)
+    serr = np.linalg.norm(xs - xo[g]) / np.linalg.norm(xo)
+    assert serr < 1e-5, ("solve", rank, serr)
+    print("OK rank %d (%s, %d of %d elements) apply err %.2e iters %d/%d solve err %.2e" % (rank, name, len(gp.elems), m.n_elem, err,
+                                                                                           solver.num_iterations, it_o, serr))
+
+
 def main():
-    rank, world, tmp, n, p, perturbed = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3], int(sys.argv[4]), int(sys.argv[5]), sys.argv[6] == "1"
+    rank, world, tmp = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3]
+    general = sys.argv[4] == "general"
+    if not general:
+        n, p, perturbed = int(sys.argv[4]), int(sys.argv[5]), sys.argv[6] == "1"
     idf = os.path.join(tmp, "nccl_id")
     if rank == 0:
         uid = operators.Context.unique_id()
@@ -31,6 +72,8 @@ def main():
             assert time.time() - t0 < 120
         uid = open(idf, "rb").read()
     ctx = operators.Context(rank, uid, rank, world)
+    if general:
+        return general_main(ctx, rank, world, sys.argv[5], int(sys.argv[6]))
     bp = partition.brick_problem(rank, world, n, p, perturbed)
     L = bp.local
     gsp = operators.GpuNDSpace(ctx, bp.space, L)

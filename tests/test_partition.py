@@ -138,3 +138,62 @@ def test_gloo_world2_exchange(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
     assert all("OK" in o for o in outs), outs
+
+
+# ---- general meshes with a host-supplied element partition (partition.GeneralProblem) -----------------------------------
+def _local_matrix(so, a, b, gp):
+    """the rank's share of the assembled operator in its L-vector numbering (serial dof orientation)"""
+    import scipy.sparse as sps
+    n = so.ndof
+    acc = sps.csr_matrix((n, n))
+    mine = np.zeros(so.mesh.n_elem, bool)
+    mine[gp.elems] = True
+    for e0, e1, A in oa.element_matrices(so, a, b):
+        G = oa.to_global(so, e0, e1, A)
+        sel = mine[e0:e1]
+        if not sel.any():
+            continue
+        d = so.elem_dofs[e0:e1][sel]
+        nd = d.shape[1]
+        acc = acc + sps.coo_matrix((G[sel].ravel(), (np.repeat(d[:, :, None], nd, 2).ravel(), np.repeat(d[:, None, :], nd, 1).ravel())),
+                                   shape=(n, n)).tocsr()
+    return acc[gp.l2g][:, gp.l2g]
+
+
+@pytest.mark.parametrize("kind,n,p,world", [("tet", (3, 2, 2), 1, 3), ("tet", (2, 2, 2), 2, 4), ("hex", (4, 3, 3), 2, 3), ("hex", (3, 3, 2), 1, 5),
+                                            ("tet", (2, 2, 1), 3, 2)])
+def test_general_partition_apply_equals_serial(kind, n, p, world):
+    from helpers import make_pair
+    m, sp, mo, so = make_pair(kind, n, p, True)
+    a, b = coef(np.arange(mo.n_elem) % 2 + 1)
+    A = oa.assemble(so, a, b)
+    part = partition.partition_by_coordinate(m, world)
+    assert len(np.unique(part)) == world and np.bincount(part).max() - np.bincount(part).min() <= 1
+    ess = sp.boundary_dofs()
+    gps = [partition.general_problem(sp, part, r, ess) for r in range(world)]
+    mats = [_local_matrix(so, a, b, g) for g in gps]
+    # every serial dof owned exactly once, by the lowest rank holding it
+    owned = np.concatenate([g.l2g[g.local.ldof_ltdof >= 0] for g in gps])
+    assert np.array_equal(np.sort(owned), np.arange(sp.ndof))
+    x_s = np.random.default_rng(5).standard_normal(sp.ndof)
+    y_s = A @ x_s
+    x_t = []
+    for g in gps:
+        own = g.local.ldof_ltdof >= 0
+        xt = np.zeros(g.local.n_tdof)
+        xt[g.local.ldof_ltdof[own]] = x_s[g.l2g[own]]
+        x_t.append(xt)
+    y_t = emulate_apply(gps, mats, x_t)
+    for g, yt in zip(gps, y_t):
+        own = g.local.ldof_ltdof >= 0
+        assert np.linalg.norm(yt[g.local.ldof_ltdof[own]] - y_s[g.l2g[own]]) <= 1e-12 * np.linalg.norm(y_s)
+    # essential dofs: the union over ranks is the serial set
+    ess_union = np.concatenate([g.l2g[np.nonzero(g.local.ldof_ltdof >= 0)[0][np.argsort(g.local.ldof_ltdof[g.local.ldof_ltdof >= 0])][g.ess_tdofs]]
+                                for g in gps])
+    assert np.array_equal(np.sort(ess_union), np.sort(ess))
+    # local maps only reference local dofs and keep the serial orientation
+    for g in gps:
+        sd = np.asarray(sp.signed_elem_dofs())[g.elems]
+        ld = g.local.elem_ldof
+        assert np.array_equal(ld < 0, sd < 0)
+        assert np.array_equal(g.l2g[np.where(ld >= 0, ld, -1 - ld)], np.where(sd >= 0, sd, -1 - sd))
