@@ -970,8 +970,9 @@ void hex_patch_free(hcurl_space *sp) {
 bool hex_patch_eligible(const hcurl_op *op) {
   const hcurl_space *sp = op->sp;
   // the modal operator is exact where the (p+1)-point rule is: that is the rule it stands in for
-  if (!(sp->has_patches && op->single_rule && op->qc == sp->order + 1 && op->coef_layout == HCURL_COEF_PER_ELEM && op->has_alpha &&
-        op->has_beta))
+  // either term may be absent (statics: curl-curl only; mass solves: mass only): its geometry factors are zero
+  if (!(sp->has_patches && op->single_rule && op->qc == sp->order + 1 && op->coef_layout == HCURL_COEF_PER_ELEM &&
+        (op->has_alpha || op->has_beta)))
     return false;
   if (op->kernel_sel == 1 || op->kernel_sel == 2) return false;
   if (sp->patch.unit == 8) return sp->patch.affine;  // order 1: classified on the host when the patches were built
@@ -1057,8 +1058,8 @@ int hex_patch_launch(hcurl_op *op, bool constrained, const double *d_x, double *
   const int64_t n_pos = P.n_patch * P.FE;
   if (!op->edataP_valid) {
     if (!op->d_edataP) HC_CUDA(cudaMalloc(&op->d_edataP, sizeof(double) * 12 * n_pos));
-    patch_edata_kernel<<<(unsigned)((n_pos + 255) / 256), 256, 0, ctx->stream>>>(n_pos, P.FE, P.d_perm, sp->d_xyz, op->d_alpha, op->d_beta,
-                                                                                op->d_edataP);
+    patch_edata_kernel<<<(unsigned)((n_pos + 255) / 256), 256, 0, ctx->stream>>>(n_pos, P.FE, P.d_perm, sp->d_xyz, op->has_alpha ? op->d_alpha : nullptr,
+                                                                                op->has_beta ? op->d_beta : nullptr, op->d_edataP);
     HC_CUDA(cudaGetLastError());
     op->edataP_valid = true;
   }

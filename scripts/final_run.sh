@@ -20,6 +20,7 @@ HCURL_PATCH_ENV=1 HCURL_PATCH_SPLIT=1 timeout 200 python bench.py --steps 20 --n
 HCURL_TEST_QAUTO=1 timeout 200 python -m pytest tests/test_gpu_apply.py -x -q -m gpu -k quad_auto > gpurun_out/pytest_qauto_$tag.log 2>&1; tail -3 gpurun_out/pytest_qauto_$tag.log
 HCURL_TEST_CHEBYSHEV=1 timeout 300 python -m pytest tests/test_gpu_pcg.py -x -q -m gpu -k chebyshev > gpurun_out/pytest_cheb_$tag.log 2>&1; tail -3 gpurun_out/pytest_cheb_$tag.log
 HCURL_TEST_IRIS=1 timeout 300 python -m pytest tests/test_oracle_iris_kat.py -x -q -m gpu > gpurun_out/pytest_iris_$tag.log 2>&1; tail -3 gpurun_out/pytest_iris_$tag.log
+HCURL_TEST_SINGLE_TERM=1 timeout 200 python -m pytest tests/test_gpu_apply.py -x -q -m gpu -k single_term > gpurun_out/pytest_single_$tag.log 2>&1; tail -3 gpurun_out/pytest_single_$tag.log
 HCURL_TEST_INTERP=1 timeout 300 python -m pytest tests/test_interp.py -x -q -m gpu > gpurun_out/pytest_interp_$tag.log 2>&1; tail -3 gpurun_out/pytest_interp_$tag.log
 HCURL_TEST_SPLIT=1 timeout 300 python -m pytest tests/test_gpu_apply.py -x -q -m gpu -k split > gpurun_out/pytest_split_$tag.log 2>&1; tail -3 gpurun_out/pytest_split_$tag.log
 HCURL_PATCH_SPLIT=1 timeout 200 python bench.py --steps 20 --no-cpu --no-e2e --pcg-iters 10 > gpurun_out/bench_p2split_$tag.json 2>/dev/null
