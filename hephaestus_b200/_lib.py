@@ -99,6 +99,11 @@ SIGNATURES = {
     "hcurl_host_ndspace_boundary_dofs": (C.c_int64, [_P, _P]),
     "hcurl_host_ndspace_face_dofs": (C.c_int64, [_P, C.c_int64, _P, _P]),
     "hcurl_host_hex_p2_pair_codes": (C.c_int, [C.c_int64, _P, _P]),
+    "hcurl_host_partition_create": (_P, [C.c_int64, C.c_int, C.c_int64, _P, _P, C.c_int]),
+    "hcurl_host_partition_destroy": (None, [_P]),
+    "hcurl_host_partition_sizes": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int),
+                                             C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "hcurl_host_partition_copy": (C.c_int, [_P] * 10),
     "hcurl_host_patches_parts": (C.c_int, [_P, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "hcurl_host_modal_tables_p2": (C.c_int, [_P]),
     "hcurl_host_hex_slot_codes": (C.c_int, [C.c_int, C.c_int64, _P, _P]),

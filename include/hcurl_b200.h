@@ -345,6 +345,25 @@ int64_t hcurl_host_ndspace_boundary_dofs(const hcurl_host_ndspace *s, int32_t *o
  * ascending; returns the count (out may be NULL), -1 if a face is not part of the mesh */
 int64_t hcurl_host_ndspace_face_dofs(const hcurl_host_ndspace *s, int64_t n_faces, const int32_t *face_verts, int32_t *out);
 
+/* ---- host-side setup helper: rank-local space under a host-supplied element partition (no GPU needed) ---------
+ * What mfem::ParMesh(comm, mesh, partitioning) + ParFiniteElementSpace derive from METIS output
+ * (/root/reference/examples/team7/Main.cpp:155), for callers without MFEM: from the SERIAL space's signed element -> dof
+ * map (elem_dofs [n_elem][nd], e.g. hcurl_host_ndspace_elem_dofs) and an element -> rank array, the arrays of rank
+ * `rank` that hcurl_space_create() takes.  Every rank keeps the serial orientation of a shared dof (ghost signs +1), the
+ * lowest rank holding a dof owns it, and the two lists of a neighbour pair are in ascending serial dof number.
+ *   copy: elems [n_elem_local] serial element ids; l2g [n_ldof] serial dof of every local dof; elem_ldof
+ *         [n_elem_local][nd] signed local dofs; ldof_ltdof [n_ldof] (-1 = not owned); nbr_rank [n_nbr]; own_off /
+ *         ghost_off [n_nbr+1]; own_ldof [n_own]; ghost_ldof [n_ghost]  (any pointer may be NULL) */
+typedef struct hcurl_host_partition hcurl_host_partition;
+hcurl_host_partition *hcurl_host_partition_create(int64_t n_elem, int nd, int64_t n_dof, const int32_t *elem_dofs,
+                                                  const int32_t *elem_rank, int rank);
+void hcurl_host_partition_destroy(hcurl_host_partition *p);
+int hcurl_host_partition_sizes(const hcurl_host_partition *p, int64_t *n_elem_local, int32_t *n_ldof, int32_t *n_tdof,
+                               int *n_nbr, int32_t *n_own, int32_t *n_ghost);
+int hcurl_host_partition_copy(const hcurl_host_partition *p, int64_t *elems, int32_t *l2g, int32_t *elem_ldof,
+                              int32_t *ldof_ltdof, int32_t *nbr_rank, int32_t *own_off, int32_t *own_ldof,
+                              int32_t *ghost_off, int32_t *ghost_ldof);
+
 /* ---- host-side setup helper: ExodusII mesh reader (no GPU, no netCDF library needed) ----
  * What mfem::Mesh(mesh_file) does for the .g and .gen files in the reference's data directory (NetCDF classic,
  * CDF-1/2) before the ND space is built (/root/reference/examples/team7/Main.cpp:152-155): node coordinates, element blocks (TETRA4 / HEX8 /

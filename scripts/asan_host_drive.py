@@ -66,6 +66,18 @@ sp1 = fespace.NDSpace(m,1); sd1 = np.ascontiguousarray(sp1.signed_elem_dofs(), d
 c1 = np.zeros(sd1.shape, np.uint32); assert lib.hcurl_host_hex_slot_codes(1, len(sd1), ptr(sd1), ptr(c1)) == 0
 for fe in (32, 128, 256):
     h = lib.hcurl_host_patches_create(12, len(sd1), fe, fe+1, 8, sp1.ndof, ptr(cen), ptr(c1), None); assert h; lib.hcurl_host_patches_destroy(h)
+# --- rank-local spaces under an element partition
+lib.hcurl_host_partition_create.restype = P; lib.hcurl_host_partition_create.argtypes = [C.c_int64, C.c_int, C.c_int64, P, P, C.c_int]
+lib.hcurl_host_partition_destroy.argtypes = [P]; lib.hcurl_host_partition_copy.argtypes = [P]*10
+lib.hcurl_host_partition_sizes.argtypes = [P] + [P]*6
+er = np.ascontiguousarray((np.arange(len(sd)) * 7) % 3, dtype=np.int32)
+for r in range(3):
+    h = lib.hcurl_host_partition_create(len(sd), 54, sp.ndof, ptr(sd), ptr(er), r); assert h
+    ne, nl, nt, nn, no, ng = C.c_int64(), C.c_int32(), C.c_int32(), C.c_int(), C.c_int32(), C.c_int32()
+    lib.hcurl_host_partition_sizes(h, C.byref(ne), C.byref(nl), C.byref(nt), C.byref(nn), C.byref(no), C.byref(ng))
+    bufs = [np.zeros(ne.value, np.int64), np.zeros(nl.value, np.int32), np.zeros(ne.value*54, np.int32), np.zeros(nl.value, np.int32), np.zeros(nn.value, np.int32),
+            np.zeros(nn.value+1, np.int32), np.zeros(max(no.value,1), np.int32), np.zeros(nn.value+1, np.int32), np.zeros(max(ng.value,1), np.int32)]
+    lib.hcurl_host_partition_copy(h, *[ptr(b) for b in bufs]); lib.hcurl_host_partition_destroy(h)
 # --- exodus
 for f in ("team7.g","cylinder-hex-q2.gen","irises.g"):
     path = "/root/reference/data/"+f

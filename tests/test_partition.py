@@ -197,3 +197,36 @@ def test_general_partition_apply_equals_serial(kind, n, p, world):
         ld = g.local.elem_ldof
         assert np.array_equal(ld < 0, sd < 0)
         assert np.array_equal(g.l2g[np.where(ld >= 0, ld, -1 - ld)], np.where(sd >= 0, sd, -1 - sd))
+
+
+@pytest.mark.parametrize("kind,n,p,world", [("tet", (3, 2, 2), 2, 4), ("hex", (4, 3, 3), 2, 3), ("hex", (3, 3, 2), 1, 5)])
+def test_cpp_general_partition_equals_python(kind, n, p, world, lib_built):
+    """csrc/partition.cpp (hcurl_host_partition_*) builds the arrays of partition.GeneralProblem"""
+    import ctypes as C
+    from hephaestus_b200 import _lib as L
+    from helpers import make_pair
+    lib = L.lib()
+    m, sp, mo, so = make_pair(kind, n, p, True)
+    part = partition.partition_by_coordinate(m, world)
+    sd = np.ascontiguousarray(sp.signed_elem_dofs(), dtype=np.int32)
+    er = np.ascontiguousarray(part, dtype=np.int32)
+    for r in range(world):
+        g = partition.general_problem(sp, part, r)
+        h = L.check_ptr(lib.hcurl_host_partition_create(len(sd), sd.shape[1], sp.ndof, L.ptr(sd), L.ptr(er), r), "partition")
+        ne, nl, nt, nn, no, ng = C.c_int64(), C.c_int32(), C.c_int32(), C.c_int(), C.c_int32(), C.c_int32()
+        L.check(lib.hcurl_host_partition_sizes(h, C.byref(ne), C.byref(nl), C.byref(nt), C.byref(nn), C.byref(no), C.byref(ng)), "sizes")
+        Lc = g.local
+        assert (ne.value, nl.value, nt.value, nn.value, no.value, ng.value) == (len(g.elems), Lc.n_ldof, Lc.n_tdof, len(Lc.nbr_rank),
+                                                                                   len(Lc.own_ldof), len(Lc.ghost_ldof))
+        elems, l2g = np.zeros(ne.value, np.int64), np.zeros(nl.value, np.int32)
+        eld, lt = np.zeros((ne.value, sd.shape[1]), np.int32), np.zeros(nl.value, np.int32)
+        nbr, oo, go = np.zeros(nn.value, np.int32), np.zeros(nn.value + 1, np.int32), np.zeros(nn.value + 1, np.int32)
+        ol, gl = np.zeros(max(no.value, 1), np.int32), np.zeros(max(ng.value, 1), np.int32)
+        L.check(lib.hcurl_host_partition_copy(h, L.ptr(elems), L.ptr(l2g), L.ptr(eld), L.ptr(lt), L.ptr(nbr), L.ptr(oo), L.ptr(ol), L.ptr(go), L.ptr(gl)), "copy")
+        lib.hcurl_host_partition_destroy(h)
+        assert np.array_equal(elems, g.elems) and np.array_equal(l2g, g.l2g) and np.array_equal(eld, Lc.elem_ldof)
+        assert np.array_equal(lt, Lc.ldof_ltdof) and np.array_equal(nbr, Lc.nbr_rank)
+        assert np.array_equal(oo, Lc.own_off) and np.array_equal(go, Lc.ghost_off)
+        assert np.array_equal(ol[:no.value], Lc.own_ldof) and np.array_equal(gl[:ng.value], Lc.ghost_ldof)
+    assert lib.hcurl_host_partition_create(len(sd), sd.shape[1], 5, L.ptr(sd), L.ptr(er), 0) is None      # dof index out of range
+    assert b"out of range" in lib.hcurl_last_error()
