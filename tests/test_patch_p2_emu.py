@@ -126,6 +126,29 @@ def test_emulated_p2_kernel_matches_oracle(emu2, split, n, grid, scramble):
 
 
 @pytest.mark.parametrize("split", [False, True])
+def test_emulated_p2_kernel_overflow_slots(emu2, split):
+    """star meshes (six rhombic prisms around an edge, stacked): pairs with more than four element slots in one patch go
+    through the overflow list and are RED-added"""
+    m, mo = affine_pair("star", (6,))
+    sp, so = fespace.NDSpace(m, 2), osp.NDSpace(mo, 2)
+    if sp.ndof % 2:
+        pytest.skip("odd number of dofs: no pair structure")
+    alpha, beta = coefficients(mo)
+    A = oa.assemble(so, alpha, beta, q_override=3).tocsr()
+    P = build_patches(sp, m, split)
+    n_ovf = sum(int(P["blob"][int(o) * 4 + 7]) for o in P["off"][:-1])
+    assert n_ovf > 0
+    edata = geometry_factors(m, P["perm"], FE, alpha, beta)
+    x = np.random.default_rng(4).standard_normal(sp.ndof)
+    sh = shared_mask(P["off"], P["blob"], sp.ndof)
+    y = np.where(sh, 0.0, 1e30)
+    dot = run_emu(emu2, P, edata, x, y, grid=2, dot=True)
+    ref = A @ x
+    assert np.abs(y - ref).max() <= 1e-12 * np.abs(ref).max()
+    assert abs(dot - x @ ref) <= 1e-12 * abs(x @ ref)
+
+
+@pytest.mark.parametrize("split", [False, True])
 def test_emulated_p2_kernel_essential_dofs(emu2, split):
     m, mo = affine_pair("hex", (5, 4, 3), seed=9)
     sp, so = fespace.NDSpace(m, 2), osp.NDSpace(mo, 2)
