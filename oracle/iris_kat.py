@@ -113,9 +113,12 @@ def face_terms(space, elems, lface, npts, coef=None, func=None):
     return M, b
 
 
-def solve(mesh, lf_points=2):
-    """Returns (max |E_real|, max |E_imag|, space, x) -- the two numbers of test_complex_iris_wg.cpp:191-195."""
-    space = osp.NDSpace(mesh, 1)
+def solve(mesh, lf_points=None, p=1):
+    """Returns (max |E_real|, max |E_imag|, space, x) -- the two numbers of test_complex_iris_wg.cpp:191-195 for p = 1
+    (the reference's ND_3D_P1); p > 1 runs the same problem at a higher order with MFEM's order-dependent rules (a
+    consistency check of the higher-order hex operator on a real mesh: the answer must stay close)."""
+    lf_points = lf_points if lf_points is not None else (2 * p) // 2 + 1     # order 2p + 0
+    space = osp.NDSpace(mesh, p)
     topo = space.topo
     port = Port()
     n = space.ndof
@@ -129,7 +132,7 @@ def solve(mesh, lf_points=2):
             if not sel.any():
                 continue
             el = fel[sel, 0]
-            M, vr = face_terms(space, el, lf, 2, coef=port.kz / MU0, func=port.u_real if attr == 2 else None)
+            M, vr = face_terms(space, el, lf, p + 1, coef=port.kz / MU0, func=None)   # exact on planar rectangular faces
             s = space.elem_sign[el].astype(float)
             d = space.elem_dofs[el]
             G = M * s[:, :, None] * s[:, None, :]
@@ -149,8 +152,8 @@ def solve(mesh, lf_points=2):
     Z = (Ar + 1j * Ai).tocsr()[idx][:, idx].tocsc()
     x = np.zeros(n, complex)
     x[idx] = spla.splu(Z).solve((br + 1j * bi)[idx])
-    # ComputeMaxError against zero: Gauss points of order 2*1 + 3 = 5 -> 3 per direction
-    g, _ = gauss_legendre(3)
+    # ComputeMaxError against zero: Gauss points of order 2*p + 3 (p = 1: 5 -> 3 per direction)
+    g, _ = gauss_legendre((2 * p + 3) // 2 + 1)
     pts = np.array([[a, b, c] for c in g for b in g for a in g])
     V, _ = space.fe.shape_and_curl(pts)
     J, _ = oa.hex8_jacobians(mesh.elem_coords(), pts)
