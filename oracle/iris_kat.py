@@ -25,7 +25,6 @@ import scipy.sparse.linalg as spla
 
 from . import assemble as oa
 from . import space as osp
-from .nd_hex import HEX_FACES
 from .quadrature import gauss_legendre
 
 EPS0 = 8.8541878176e-12

@@ -15,7 +15,6 @@ import pytest
 
 from hephaestus_b200 import fespace
 from oracle import iris_kat
-from oracle import space as osp
 
 from helpers import GOLDEN, golden_mesh, rel_err
 
