@@ -947,6 +947,9 @@ int hex_patch_build(hcurl_space *sp, const double *elem_xyz, const int32_t *elem
   P.FE = FE; P.stride = H.stride; P.n_patch = H.n_patch; P.n_boundary = H.n_boundary;
   const char *envk = getenv("HCURL_PATCH_ENV");
   P.env_kernel = envk && envk[0] == '1' && FE == 32;  // the Env-program restatement of the kernel (hex_patch_p2e.cu), opt-in
+  const char *halfk = getenv("HCURL_PATCH_HALF");
+  P.half_kernel = halfk && (halfk[0] == '1' || halfk[0] == '2') && FE == 32 && !split;  // two threads per element component, opt-in
+  P.half_regs = (halfk && halfk[0] == '2') ? 80 : 96;
   P.split = split; P.max_d_words = H.max_d_words; P.max_l_words = H.max_l_words;
   if (split && upload(P.d_part_off, H.part_off)) return 1;
   P.blob_words = (int64_t)H.blob.size(); P.max_blob_words = H.max_blob_words; P.max_dofs = H.max_dofs;
@@ -1086,7 +1089,7 @@ int hex_patch_launch(hcurl_op *op, bool constrained, const double *d_x, double *
   a.d_cap_bytes = (P.max_d_words * 4 + 15u) & ~15u;
   a.l_cap_bytes = (P.max_l_words * 4 + 15u) & ~15u;
   const size_t smem = P.split ? patch_split_smem_bytes(P.FE, P) : patch_smem_bytes(P.FE, P.max_blob_words, P.max_dofs);
-  if (P.env_kernel) {
+  if (P.env_kernel || P.half_kernel) {
     a.prof = nullptr;
     if (hex_patch_p2e_launch(op, a, accumulate)) return 1;
     HC_CUDA(cudaGetLastError());

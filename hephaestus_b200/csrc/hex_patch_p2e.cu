@@ -9,6 +9,7 @@
 #include "internal.h"
 #include "patch_dev.cuh"
 #include "hex_patch_p2_body.h"
+#include "hex_patch_p2h_body.h"
 
 namespace hcurl {
 
@@ -38,6 +39,7 @@ struct P2DeviceEnv {
   __device__ __forceinline__ void gather_wait() const { gather_wait_all(); }
   __device__ __forceinline__ void red_add(double *p, double v) const { hcurl::red_add(p, v); }
   __device__ __forceinline__ bool warp_all(bool pred) const { return __all_sync(0xffffffffu, pred); }
+  __device__ __forceinline__ double shfl_xor(double v, int lane_mask) const { return __shfl_xor_sync(0xffffffffu, v, lane_mask); }
   __device__ __forceinline__ uint32_t ldg(const uint32_t *p) const { return __ldg(p); }
   __device__ __forceinline__ double ldg(const double *p) const { return __ldg(p); }
   __device__ __forceinline__ double2 ldg(const double2 *p) const { return __ldg(p); }
@@ -70,6 +72,45 @@ __global__ void __maxnreg__(SPLIT ? 128 : 168) hex_patch_p2e_kernel(const PatchA
   extern __shared__ __align__(16) unsigned char smem_p2e[];
   P2DeviceEnv env{smem_p2e};
   hex_patch_p2_body<P2DeviceEnv, FE, ACC, DOT, SPLIT>(env, a);
+}
+
+// two threads per element component (hex_patch_p2h_body.h): 6 FE threads per CTA, same shared memory as the plain kernel
+// REGS: 96 (4 bytes of spills; 3 CTAs = 18 warps per SM) or 80 (76 bytes of spills; 4 CTAs = 24 warps per SM); natural need 116
+template <int FE, bool ACC, bool DOT, int REGS>
+__global__ void __maxnreg__(REGS) hex_patch_p2h_kernel(const PatchArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_p2h[];
+  P2DeviceEnv env{smem_p2h};
+  hex_patch_p2h_body<P2DeviceEnv, FE, ACC, DOT>(env, a);
+}
+
+template <int FE, int REGS>
+static int launch_p2h(const PatchArgs &a, int64_t n_run, int sm_count, int n_partial, size_t smem, bool acc, cudaStream_t st) {
+  auto k0 = hex_patch_p2h_kernel<FE, false, false, REGS>;
+  auto k1 = hex_patch_p2h_kernel<FE, true, false, REGS>;
+  auto kd = hex_patch_p2h_kernel<FE, false, true, REGS>;
+  static size_t attr = 0;
+  static int per_sm = 0;
+  if (attr < smem) {
+    HC_CUDA(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HC_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HC_CUDA(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HC_CUDA(cudaFuncSetAttribute(k0, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    HC_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    HC_CUDA(cudaFuncSetAttribute(kd, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    HC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kd, 6 * FE, smem));
+    if (per_sm < 1) { set_error("patch kernel does not fit on an SM (%zu bytes of shared memory)", smem); return 1; }
+    attr = smem;
+  }
+  int64_t grid = (int64_t)per_sm * sm_count;
+  if (const char *s = getenv("HCURL_PATCH_CTAS_PER_SM")) { const int v = atoi(s); if (v >= 1 && v <= per_sm) grid = (int64_t)v * sm_count; }
+  if (grid > n_run) grid = n_run;
+  if (a.dot_out) {
+    if (acc) { set_error("patch kernel: fused dot product is not available with accumulation"); return 1; }
+    if (grid > n_partial) grid = n_partial;
+    kd<<<(unsigned)grid, 6 * FE, smem, st>>>(a);
+  } else if (acc) k1<<<(unsigned)grid, 6 * FE, smem, st>>>(a);
+  else k0<<<(unsigned)grid, 6 * FE, smem, st>>>(a);
+  return 0;
 }
 
 template <int FE, bool SPLIT>
@@ -119,6 +160,11 @@ int hex_patch_p2e_launch(hcurl_op *op, const PatchArgs &a, bool accumulate) {
   const size_t smem = P.split ? 32 + 2 * (size_t)a.d_cap_bytes + a.l_cap_bytes + T_CAP + a.xs_cap_bytes + 2 * (size_t)27 * FE * 16
                               : 16 + 2 * (size_t)a.blob_cap_bytes + a.xs_cap_bytes + 2 * (size_t)27 * (FE + 1) * 16;
   const int64_t n_run = a.n_patch - a.k_begin;
+  if (P.half_kernel) {
+    if (P.split) { set_error("the two-threads-per-component kernel uses the plain blob layout (unset HCURL_PATCH_SPLIT)"); return 1; }
+    if (P.half_regs == 80) return launch_p2h<FE, 80>(a, n_run, ctx->sm_count, ctx->n_partial, smem, accumulate, ctx->stream);
+    return launch_p2h<FE, 96>(a, n_run, ctx->sm_count, ctx->n_partial, smem, accumulate, ctx->stream);
+  }
   if (P.split) return launch_p2e<FE, true>(a, n_run, ctx->sm_count, ctx->n_partial, smem, accumulate, ctx->stream);
   return launch_p2e<FE, false>(a, n_run, ctx->sm_count, ctx->n_partial, smem, accumulate, ctx->stream);
 }

@@ -110,6 +110,8 @@ struct PatchSet {  // device copy
   uint32_t max_blob_words = 0, max_dofs = 0;
   bool split = false;            // blobs built for the split-blob kernel variant (unpadded rows)
   bool env_kernel = false;       // launch the Env-program restatement (hex_patch_p2e.cu) instead of hex_patch.cu's kernels
+  bool half_kernel = false;      // launch the two-threads-per-component Env program (hex_patch_p2h_body.h)
+  int half_regs = 96;            // its register cap: 96 (HCURL_PATCH_HALF=1) or 80 (HCURL_PATCH_HALF=2)
   uint32_t *d_part_off = nullptr;
   uint32_t max_d_words = 0, max_l_words = 0;
   uint8_t swz_row[27] = {0}, swz_grp[16] = {0};

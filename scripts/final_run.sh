@@ -17,6 +17,8 @@ for fe in 64 128 256; do HCURL_PATCH_P1=1 HCURL_PATCH_FE=$fe timeout 200 python 
 HCURL_TEST_PATCH_ENV=1 timeout 300 python -m pytest tests/test_gpu_apply.py -x -q -m gpu -k env_program > gpurun_out/pytest_p2env_$tag.log 2>&1; tail -3 gpurun_out/pytest_p2env_$tag.log
 HCURL_PATCH_ENV=1 timeout 200 python bench.py --steps 20 --no-cpu --no-e2e --pcg-iters 10 > gpurun_out/bench_p2env_$tag.json 2>/dev/null
 HCURL_PATCH_ENV=1 HCURL_PATCH_SPLIT=1 timeout 200 python bench.py --steps 20 --no-cpu --no-e2e --pcg-iters 10 > gpurun_out/bench_p2envsplit_$tag.json 2>/dev/null
+HCURL_TEST_PATCH_HALF=1 timeout 300 python -m pytest tests/test_gpu_apply.py -x -q -m gpu -k half_program > gpurun_out/pytest_p2half_$tag.log 2>&1; tail -3 gpurun_out/pytest_p2half_$tag.log
+for hv in 1 2; do HCURL_PATCH_HALF=$hv timeout 200 python bench.py --steps 20 --no-cpu --no-e2e --pcg-iters 10 > gpurun_out/bench_p2half${hv}_$tag.json 2>/dev/null; done
 HCURL_TEST_QAUTO=1 timeout 200 python -m pytest tests/test_gpu_apply.py -x -q -m gpu -k quad_auto > gpurun_out/pytest_qauto_$tag.log 2>&1; tail -3 gpurun_out/pytest_qauto_$tag.log
 HCURL_TEST_CHEBYSHEV=1 timeout 300 python -m pytest tests/test_gpu_pcg.py -x -q -m gpu -k chebyshev > gpurun_out/pytest_cheb_$tag.log 2>&1; tail -3 gpurun_out/pytest_cheb_$tag.log
 HCURL_TEST_IRIS=1 timeout 300 python -m pytest tests/test_oracle_iris_kat.py -x -q -m gpu > gpurun_out/pytest_iris_$tag.log 2>&1; tail -3 gpurun_out/pytest_iris_$tag.log

@@ -31,6 +31,7 @@ struct Pending { void *dst = nullptr; const void *src = nullptr; uint32_t bytes 
 struct WarpShared {
   std::barrier<> bar;
   std::atomic<int> flag[3];
+  double xch[3][32];  // shuffle scratch, rotating like the vote flags
   explicit WarpShared(int n) : bar(n) { for (auto &f : flag) f.store(1); }
 };
 
@@ -62,7 +63,7 @@ struct HostEnv {
   const void *tables_;
   struct Copy { void *dst; const void *src; int bytes; };
   std::vector<Copy> pend;  // my issued, not yet waited-for gathers
-  unsigned vote_n = 0;
+  unsigned vote_n = 0, shfl_n = 0;
 
   int tid() const { return tid_; }
   int64_t block() const { return block_; }
@@ -116,6 +117,13 @@ struct HostEnv {
     W.bar.arrive_and_wait();
     return W.flag[n % 3].load() != 0;
   }
+  double shfl_xor(double v, int lane_mask) {  // __shfl_xor_sync(0xffffffff, v, lane_mask): every thread of the warp calls it
+    WarpShared &W = *cta->warp[(size_t)(tid_ >> 5)];
+    const unsigned n = shfl_n++ % 3;
+    W.xch[n][tid_ & 31] = v;
+    W.bar.arrive_and_wait();
+    return W.xch[n][(tid_ & 31) ^ lane_mask];
+  }
   uint32_t ldg(const uint32_t *p) const { return *p; }
   double ldg(const double *p) const { return *p; }
   double2 ldg(const double2 *p) const { return *p; }
@@ -141,7 +149,7 @@ int run_grid(int64_t grid, int nt, size_t smem_bytes, const void *tables, double
     std::vector<std::thread> th;
     for (int t = 0; t < nt; t++)
       th.emplace_back([&, t]() {
-        HostEnv env{&cta, t, blk, grid, nt, &err[(size_t)t], tables, {}, 0};
+        HostEnv env{&cta, t, blk, grid, nt, &err[(size_t)t], tables, {}, 0, 0};
         body(env);
         if (!env.pend.empty()) err[(size_t)t] |= ERR_GATHER_LEFT;  // gathers never waited for
       });

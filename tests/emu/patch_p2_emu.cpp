@@ -2,6 +2,7 @@
 // on the host environment of host_env.h -- TEST INFRASTRUCTURE, see tests/test_patch_p2_emu.py.
 #include "host_env.h"
 #include "hex_patch_p2_body.h"
+#include "hex_patch_p2h_body.h"
 
 namespace {
 template <int FE, bool ACC, bool DOT, bool SPLIT>
@@ -9,6 +10,14 @@ int run(const hcurl::PatchArgs &a, int64_t grid, size_t smem_bytes, const hcurl:
   double dot = 0.0;
   const int err = emu::run_grid(grid, 3 * FE, smem_bytes, &T, &dot,
                                 [&](emu::HostEnv &env) { hcurl::hex_patch_p2_body<emu::HostEnv, FE, ACC, DOT, SPLIT>(env, a); });
+  if (DOT && a.dot_out) *a.dot_out = a.dot_add ? *a.dot_out + dot : dot;
+  return err;
+}
+template <int FE, bool ACC, bool DOT>
+int run_half(const hcurl::PatchArgs &a, int64_t grid, size_t smem_bytes, const hcurl::ModalTables &T) {
+  double dot = 0.0;
+  const int err = emu::run_grid(grid, 6 * FE, smem_bytes, &T, &dot,
+                                [&](emu::HostEnv &env) { hcurl::hex_patch_p2h_body<emu::HostEnv, FE, ACC, DOT>(env, a); });
   if (DOT && a.dot_out) *a.dot_out = a.dot_add ? *a.dot_out + dot : dot;
   return err;
 }
@@ -29,10 +38,14 @@ extern "C" int emu_patch_p2_apply(int split, int accumulate, int64_t n_patch, in
   hcurl::ModalTables T;
   T.a0 = tables7[0]; T.a1 = tables7[1]; T.b = tables7[2]; T.c0 = tables7[3]; T.c1 = tables7[4]; T.d1 = tables7[5]; T.d2 = tables7[6];
   constexpr size_t T_CAP = (27 * FE * 2 + 15) & ~15;
-  const size_t smem = split ? 32 + 2 * (size_t)d_cap_bytes + l_cap_bytes + T_CAP + xs_cap_bytes + 2 * (size_t)27 * FE * 16
+  const size_t smem = split == 1 ? 32 + 2 * (size_t)d_cap_bytes + l_cap_bytes + T_CAP + xs_cap_bytes + 2 * (size_t)27 * FE * 16
                             : 16 + 2 * (size_t)blob_cap_bytes + xs_cap_bytes + 2 * (size_t)27 * (FE + 1) * 16;
   if (grid > n_patch - k_begin) grid = n_patch - k_begin;
   if (grid < 1) return 0;
+  if (split == 2) {  // two threads per element component (hex_patch_p2h_body.h), plain blob layout
+    if (dot_out) return accumulate ? -1 : run_half<FE, false, true>(a, grid, smem, T);
+    return accumulate ? run_half<FE, true, false>(a, grid, smem, T) : run_half<FE, false, false>(a, grid, smem, T);
+  }
   if (dot_out) {
     if (accumulate) return -1;
     return split ? run<FE, false, true, true>(a, grid, smem, T) : run<FE, false, true, false>(a, grid, smem, T);

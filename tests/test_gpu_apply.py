@@ -356,6 +356,23 @@ def test_hex_p2_patch_kernel_env_program(ctx, n, split, monkeypatch):
     monkeypatch.setenv("HCURL_PATCH_ENV", "1")
     monkeypatch.setenv("HCURL_PATCH_SPLIT", split)
     monkeypatch.setenv("HCURL_PATCH_FE", "32")
+    _p2_patch_variant_parity(ctx, n)
+
+
+@pytest.mark.skipif(os.environ.get("HCURL_TEST_PATCH_HALF") != "1",
+                    reason="two-threads-per-component order-2 patch kernel (hex_patch_p2h_body.h): verified on host threads "
+                           "(tests/test_patch_p2_emu.py), not yet run on a GPU; opt in with HCURL_TEST_PATCH_HALF=1")
+@pytest.mark.parametrize("regs", ["1", "2"])
+@pytest.mark.parametrize("n", [(9, 8, 6), (5, 4, 3)])
+def test_hex_p2_patch_kernel_half_program(ctx, n, regs, monkeypatch):
+    """hex_patch_p2h_kernel at 96 (HCURL_PATCH_HALF=1) and 80 (=2) registers: same parity bar as the default patch kernel."""
+    monkeypatch.setenv("HCURL_PATCH_HALF", regs)
+    monkeypatch.setenv("HCURL_PATCH_SPLIT", "0")
+    monkeypatch.setenv("HCURL_PATCH_FE", "32")
+    _p2_patch_variant_parity(ctx, n)
+
+
+def _p2_patch_variant_parity(ctx, n):
     m, sp, mo, so = make_pair("hex", n, 2, False, scramble=True)
     a, b = coefficients(m)
     gsp = operators.GpuNDSpace(ctx, sp)

@@ -41,7 +41,9 @@ def emu2(tmp_path_factory, lib_built):
 
 
 def build_patches(sp, mesh, split):
+    """split: False = plain blobs, True = split-blob layout, "half" = plain blobs for the two-threads-per-component program"""
     lib = L.lib()
+    half, split = split == "half", split is True
     sd = np.ascontiguousarray(sp.signed_elem_dofs(), dtype=np.int32)
     ne = sd.shape[0]
     assert sd.shape[1] == 54 and sp.ndof % 2 == 0
@@ -63,7 +65,7 @@ def build_patches(sp, mesh, split):
     lib.hcurl_host_patches_destroy(h)
     T = np.zeros(7)
     L.check(lib.hcurl_host_modal_tables_p2(L.ptr(T)), "tables")
-    return dict(perm=perm, off=off, blob=blob, row=row, grp=grp, part=part, caps=caps, T=T, split=split)
+    return dict(perm=perm, off=off, blob=blob, row=row, grp=grp, part=part, caps=caps, T=T, split=2 if half else int(split))
 
 
 def run_emu(emu2, P, edata, x, y, scale=1.0, accumulate=False, grid=2, dot=False, blob=None, k_begin=0, k_end=None):
@@ -89,7 +91,7 @@ def shared_mask(off, blob, ndof):
 
 # (6,6,5) = 180 elements -> 6 patches: with grid 1 / 2 the double-buffered pipeline wraps around; scrambled vertex
 # numbering makes pairs swapped / sign-flipped (the non-plain path), the unscrambled cube exercises the plain path
-@pytest.mark.parametrize("split", [False, True])
+@pytest.mark.parametrize("split", [False, True, "half"])
 @pytest.mark.parametrize("n,grid,scramble", [((6, 6, 5), 1, True), ((6, 6, 5), 2, False), ((4, 4, 4), 3, True), ((3, 2, 2), 1, True)])
 def test_emulated_p2_kernel_matches_oracle(emu2, split, n, grid, scramble):
     m, mo = affine_pair("hex", n)
@@ -125,7 +127,7 @@ def test_emulated_p2_kernel_matches_oracle(emu2, split, n, grid, scramble):
         assert np.abs(y3 - ref).max() <= 1e-12 * np.abs(ref).max()
 
 
-@pytest.mark.parametrize("split", [False, True])
+@pytest.mark.parametrize("split", [False, True, "half"])
 def test_emulated_p2_kernel_overflow_slots(emu2, split):
     """star meshes (six rhombic prisms around an edge, stacked): pairs with more than four element slots in one patch go
     through the overflow list and are RED-added"""
@@ -148,7 +150,7 @@ def test_emulated_p2_kernel_overflow_slots(emu2, split):
     assert abs(dot - x @ ref) <= 1e-12 * abs(x @ ref)
 
 
-@pytest.mark.parametrize("split", [False, True])
+@pytest.mark.parametrize("split", [False, True, "half"])
 def test_emulated_p2_kernel_essential_dofs(emu2, split):
     m, mo = affine_pair("hex", (5, 4, 3), seed=9)
     sp, so = fespace.NDSpace(m, 2), osp.NDSpace(mo, 2)
