@@ -1,0 +1,121 @@
+"""Size-independent properties of the BASELINE workload (structured cube, order 2, two attributes split at x = 1/2).
+
+At the bench size (n = 128: 2 097 152 hexes, 50 725 632 dofs) the oracle's assembled matrix is out of reach, so parity
+at that size goes through properties whose right answer is known without it:
+  * closed-form energies: the order-2 ND space holds every linear field, the nodal interpolant reproduces it and the
+    (p+1)-point rule integrates the products exactly on parallelepipeds, so for u = w x r / 2 + c
+        x_u^T A x_u = sum_attr alpha_attr |w|^2 vol_attr + sum_attr beta_attr int_attr |u|^2      (closed form below)
+  * symmetry  <A x, y> = <x, A y>,  linearity  A(2 x - 3 y) = 2 A x - 3 A y,  identity rows on essential dofs
+  * two independent kernels (patch kernel, generic sum-factorised kernel) agree.
+The CPU test pins the closed forms and the interpolation helper against the oracle at a size it assembles in seconds;
+the GPU test applies them to the CUDA operator at the full size through the C ABI (host buffers)."""
+import numpy as np
+import pytest
+
+from hephaestus_b200 import fespace
+
+from helpers import interpolate_affine_hex
+
+W = np.array([0.3, -0.7, 1.1])   # curl of the test field
+C0 = np.array([0.5, 0.25, -1.0])  # its constant part
+NU = {1: 1.0, 2: 2.0}             # alpha per attribute (x < 1/2 -> 1, else 2)
+SIGMA = {1: 1.0, 2: 3.0}          # beta per attribute
+TOL_ENERGY = 1e-10                # closed forms: summation round-off over 5e7 dofs, not a parity tolerance
+TOL = 1e-12                       # parity bar (BASELINE.json north_star)
+
+
+SKEW = 0.5 * np.array([[0, -W[2], W[1]], [W[2], 0, -W[0]], [-W[1], W[0], 0]])  # u = SKEW r + C0 = w x r / 2 + C0
+
+
+def field(X):
+    return X @ SKEW.T + C0
+
+
+def _box_moments(x0, x1):
+    """int over [x0,x1] x [0,1]^2 of 1, r, r r^T"""
+    lo, hi = np.array([x0, 0.0, 0.0]), np.array([x1, 1.0, 1.0])
+    vol = np.prod(hi - lo)
+    m1 = vol * 0.5 * (lo + hi)
+    m2 = np.outer(m1, m1) / vol
+    m2[np.diag_indices(3)] = vol * (hi ** 3 - lo ** 3) / (3.0 * (hi - lo))
+    return vol, m1, m2
+
+
+def energy_closed_form(alpha=NU, beta=SIGMA):
+    """int alpha |curl u|^2 + beta |u|^2 for u = field, attributes split at x = 1/2 of the unit cube.
+    u = S r + c with S = [w]_x / 2:  |u|^2 = tr(S^T S r r^T) + 2 c^T S r + |c|^2"""
+    S = SKEW
+    e = 0.0
+    for attr, (x0, x1) in ((1, (0.0, 0.5)), (2, (0.5, 1.0))):
+        vol, m1, m2 = _box_moments(x0, x1)
+        e += alpha[attr] * (W @ W) * vol
+        e += beta[attr] * (np.trace(S.T @ S @ m2) + 2.0 * C0 @ S @ m1 + (C0 @ C0) * vol)
+    return e
+
+
+def coefficient_arrays(mesh):
+    return (np.where(mesh.attr == 1, NU[1], NU[2]).astype(float), np.where(mesh.attr == 1, SIGMA[1], SIGMA[2]).astype(float))
+
+
+def test_closed_form_energy_matches_oracle():
+    """the closed form and the chunked interpolation helper, against the oracle's matrix and its own projection"""
+    from oracle import assemble as oa
+    from oracle import mesh as om
+    from oracle import space as osp
+    n = 4
+    m, mo = fespace.cartesian_hex_mesh(n, n, n), om.cartesian_hex(n, n, n)
+    assert set(np.unique(m.attr)) == {1, 2}
+    sp, so = fespace.NDSpace(m, 2), osp.NDSpace(mo, 2)
+    x = interpolate_affine_hex(sp, field, chunk=7)
+    assert np.abs(x - oa.project_tangential(so, field)).max() < 1e-14
+    a, b = coefficient_arrays(m)
+    A = oa.assemble(so, a, b, q_override=3)
+    assert abs(x @ (A @ x) - energy_closed_form()) < 1e-12 * energy_closed_form()
+    # and with MFEM's own rules (curl-curl p+1, mass p+2 points): the same on parallelepipeds
+    A0 = oa.assemble(so, a, b)
+    assert abs(x @ (A0 @ x) - energy_closed_form()) < 1e-12 * energy_closed_form()
+
+
+@pytest.mark.gpu
+def test_full_size_operator_properties(ctx):
+    """BASELINE configs: n = 128 cube, order 2, 50.7 M dofs -- the size bench.py's number is quoted on."""
+    from hephaestus_b200 import operators
+    n = 128
+    mesh = fespace.cartesian_hex_mesh(n, n, n)
+    sp = fespace.NativeNDSpace(mesh, 2)
+    assert sp.ndof == 50725632
+    gsp = operators.GpuNDSpace(ctx, sp)
+    a, b = coefficient_arrays(mesh)
+    ops = {}
+    for which in (0, 1):  # automatic (patch kernel on this mesh) and the generic kernel
+        op = operators.HephGpuOperator(ctx, gsp, 3)
+        op.SetKernel(which)
+        op.SetCoefficients(a, b)
+        ops[which] = op
+    op = ops[0]
+    # closed-form energy, unconstrained operator
+    xu = interpolate_affine_hex(sp, field)
+    e_ref = energy_closed_form()
+    yu = op.MultUnconstrained(xu)
+    assert abs(xu @ yu - e_ref) < TOL_ENERGY * e_ref, (xu @ yu, e_ref)
+    yg = ops[1].MultUnconstrained(xu)
+    assert abs(xu @ yg - e_ref) < TOL_ENERGY * e_ref, (xu @ yg, e_ref)
+    # constrained operator (all six faces essential, as in the bench): symmetry, linearity, identity rows, two kernels
+    ess = sp.boundary_dofs()
+    for o in ops.values():
+        o.SetEssentialTrueDofs(ess)
+    rng = np.random.default_rng(12345)
+    x, y = rng.standard_normal(sp.ndof), rng.standard_normal(sp.ndof)
+    Ax, Ay = op.Mult(x), op.Mult(y)
+    assert op.LastKernel() == 3
+    assert np.array_equal(Ax[ess], x[ess])
+    nx, ny, nAx, nAy = (np.linalg.norm(v) for v in (x, y, Ax, Ay))
+    assert abs(Ax @ y - x @ Ay) < TOL * max(nAx * ny, nx * nAy)
+    Az = op.Mult(2.0 * x - 3.0 * y)
+    assert np.linalg.norm(Az - (2.0 * Ax - 3.0 * Ay)) < TOL * np.linalg.norm(Az)
+    assert x @ Ax > 0.0
+    Gx = ops[1].Mult(x)
+    assert ops[1].LastKernel() == 1
+    assert np.linalg.norm(Gx - Ax) < TOL * np.linalg.norm(Ax)
+    for o in ops.values():
+        o.close()
