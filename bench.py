@@ -338,8 +338,11 @@ def main():
     abytes = algorithmic_bytes(n_tdof, n_elem_local, nd) if args.geom == "hex" else algorithmic_bytes_tet(n_tdof, n_elem_local, nd)
     achieved = abytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
     fp64 = ctx.fp64_peak_tflops()
+    # opt-in kernel variants are named in the line; the recorded ncu traffic is the default kernel's only
+    switches = {k: v for k, v in sorted(os.environ.items()) if k.startswith("HCURL_PATCH_") or k in ("HCURL_NO_PATCH", "HCURL_OVERLAP")}
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": measured_traffic(p, n, op.LastKernel()) if world == 1 and not args.perturbed and args.quad == "fast" else None,
+                "traffic": measured_traffic(p, n, op.LastKernel()) if world == 1 and not args.perturbed and args.quad == "fast" and not switches else None,
+                "switches": switches or None,
                 "peak_kind": "of " + peak_kind,
                 "kernel": "tet batched packed-symmetric element-matrix kernel (order %d)" % p if args.geom == "tet" else
                 "hex element kernel (order %d; %s)" % (
