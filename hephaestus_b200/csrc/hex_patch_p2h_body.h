@@ -92,20 +92,21 @@ HCURL_BODY void hex_patch_p2h_body(Env &env, const PatchArgs &a) {
     const bool ok = (uint32_t)el < B[13];
     // ---- pull (both halves read the pairs: broadcast), open-direction butterfly for my mode, closed transforms
     double A9[9];  // Am(h, m1, m2) at r = m1 + 3 m2
-    uint32_t lx[9];
+    // per-slot table entries (staging position | swap / sign flags): read here for the pull and AGAIN at the result
+    // store of the non-plain path instead of being kept in nine registers across the element operator
+    const uint16_t *lidx = reinterpret_cast<const uint16_t *>(B + B[12]) + (c * 9) * FE + el;
     uint32_t fl = 0;
     if (ok) {
-      const uint16_t *lidx = reinterpret_cast<const uint16_t *>(B + B[12]) + (c * 9) * FE + el;
 #pragma unroll
-      for (int r = 0; r < 9; r++) { lx[r] = lidx[r * FE]; fl |= lx[r]; }
-    } else {
-#pragma unroll
-      for (int r = 0; r < 9; r++) lx[r] = 0;
+      for (int r = 0; r < 9; r++) fl |= lidx[r * FE];
     }
     // warp-uniform: no element of this warp sees a pair swapped or sign-flipped (consistently oriented meshes)
     const bool plain = env.warp_all((fl & 0xe000u) == 0u);
     if (ok) {
       double ah[9], bh[9];
+      uint32_t lx[9];
+#pragma unroll
+      for (int r = 0; r < 9; r++) lx[r] = lidx[r * FE];
       if (plain) {
 #pragma unroll
         for (int r = 0; r < 9; r++) { const double2 v = Xs[lx[r]]; ah[r] = h ? v.y - v.x : v.x + v.y; }
@@ -225,7 +226,7 @@ HCURL_BODY void hex_patch_p2h_body(Env &env, const PatchArgs &a) {
           double *dst = Eown + ((size_t)r * ST + (elx ^ a.swz_row[c * 9 + r])) * 2;
           if (plain) dst[h] = yl;
           else {
-            const uint32_t l = lx[r];
+            const uint32_t l = lidx[r * FE];
             const int slot = h ^ (int)((l >> 13) & 1u);             // pair swapped: local dof h sits in the other slot
             const uint32_t neg = h ? (l << 17) & 0x80000000u : (l << 16) & 0x80000000u;  // PAIR_NEG1 / PAIR_NEG0
             dst[slot] = p2_flip(yl, neg);
