@@ -251,13 +251,15 @@ HCURL_BODY void hex_patch_p2_body(Env &env, const PatchArgs &a) {
     const bool ok = (uint32_t)el < B[13];
     // ---- pull the element inputs through the per-slot table, forward transform
     double Am[18];
-    uint32_t lx[9];
     uint32_t fl = 0;
+    // swap / sign flags of my nine slots, three bits each: all the result store needs of the per-slot table (which, SPLIT,
+    // is gone by then) -- one register across the element operator instead of the nine table entries
+    uint32_t fpk = 0;
     if (SPLIT) env.bulk_wait(3, it & 1);  // per-slot table of this patch
+    const uint16_t *lidx = (SPLIT ? reinterpret_cast<const uint16_t *>(tabB) : reinterpret_cast<const uint16_t *>(B + B[12])) + (c * 9) * FE + el;
     if (ok) {
-      const uint16_t *lidx = (SPLIT ? reinterpret_cast<const uint16_t *>(tabB) : reinterpret_cast<const uint16_t *>(B + B[12])) + (c * 9) * FE + el;
 #pragma unroll
-      for (int r = 0; r < 9; r++) { lx[r] = lidx[r * FE]; fl |= lx[r]; }
+      for (int r = 0; r < 9; r++) fl |= lidx[r * FE];
     }
     // warp-uniform: no element of this warp sees a pair swapped or sign-flipped (consistently oriented meshes)
     const bool plain = env.warp_all((fl & 0xe000u) == 0u);
@@ -265,10 +267,14 @@ HCURL_BODY void hex_patch_p2_body(Env &env, const PatchArgs &a) {
       double X[18];
       if (plain) {
 #pragma unroll
-        for (int r = 0; r < 9; r++) { const double2 v = Xs[lx[r]]; X[2 * r] = v.x; X[2 * r + 1] = v.y; }
+        for (int r = 0; r < 9; r++) { const double2 v = Xs[lidx[r * FE]]; X[2 * r] = v.x; X[2 * r + 1] = v.y; }
       } else {
 #pragma unroll
-        for (int r = 0; r < 9; r++) p2_pair_to_local(Xs[lx[r] & 0x1fffu], lx[r], X[2 * r], X[2 * r + 1]);
+        for (int r = 0; r < 9; r++) {
+          const uint32_t l = lidx[r * FE];
+          p2_pair_to_local(Xs[l & 0x1fffu], l, X[2 * r], X[2 * r + 1]);
+          fpk |= ((l >> 13) & 7u) << (3 * r);
+        }
       }
       p2_modal_fwd(M, X, Am);
       double2 *Eown = E2 + (c * 9) * ST + el;
@@ -323,7 +329,7 @@ HCURL_BODY void hex_patch_p2_body(Env &env, const PatchArgs &a) {
         for (int r = 0; r < 9; r++) Eown[r * ST + (elx ^ a.swz_row[c * 9 + r])] = make_double2(Y[2 * r], Y[2 * r + 1]);
       } else {
 #pragma unroll
-        for (int r = 0; r < 9; r++) Eown[r * ST + (elx ^ a.swz_row[c * 9 + r])] = p2_local_to_pair(Y[2 * r], Y[2 * r + 1], lx[r]);
+        for (int r = 0; r < 9; r++) Eown[r * ST + (elx ^ a.swz_row[c * 9 + r])] = p2_local_to_pair(Y[2 * r], Y[2 * r + 1], ((fpk >> (3 * r)) & 7u) << 13);
       }
     }
     env.sync();  // element results visible; everyone has read the modal coefficients
