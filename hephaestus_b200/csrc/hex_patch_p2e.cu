@@ -75,7 +75,7 @@ __global__ void __maxnreg__(SPLIT ? 128 : 168) hex_patch_p2e_kernel(const PatchA
 }
 
 // two threads per element component (hex_patch_p2h_body.h): 6 FE threads per CTA, same shared memory as the plain kernel
-// REGS: 96 (no spills; 3 CTAs = 18 warps per SM) or 80 (32-56 bytes of stack; 4 CTAs = 24 warps per SM); natural need 116
+// REGS: 96 (no spills; 3 CTAs = 18 warps per SM) or 80 (32-48 bytes of stack; 4 CTAs = 24 warps per SM); natural need 116
 template <int FE, bool ACC, bool DOT, int REGS>
 __global__ void __maxnreg__(REGS) hex_patch_p2h_kernel(const PatchArgs a) {
   extern __shared__ __align__(16) unsigned char smem_p2h[];

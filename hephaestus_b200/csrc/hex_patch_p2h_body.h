@@ -132,45 +132,59 @@ HCURL_BODY void hex_patch_p2h_body(Env &env, const PatchArgs &a) {
       const double2 *E1 = E2 + (c1 * 9) * ST + el, *E2c = E2 + (c2 * 9) * ST + el;
       // rows m0 = h ("lo") and m0 = h + 1 ("hi") of the other components' coefficients, in my frame:
       //   Bm(m0, m1 in {0,1}, m2): pair at row m2 + 3 m0 of component c+1;  Cm(m0, m1, m2 in {0,1}): pair at row m0 + 3 m1 of c+2
-      double Bl[2][3], Bh[2][3], Cl[3][2], Ch[3][2];
-#pragma unroll
-      for (int m2 = 0; m2 < 3; m2++) {
-        const double2 v = E1[(m2 + 3 * h) * ST], w = E1[(m2 + 3 * (h + 1)) * ST];
-        Bl[0][m2] = v.x; Bl[1][m2] = v.y;
-        Bh[0][m2] = w.x; Bh[1][m2] = w.y;
-      }
-#pragma unroll
-      for (int m1 = 0; m1 < 3; m1++) {
-        const double2 v = E2c[(h + 3 * m1) * ST], w = E2c[(h + 1 + 3 * m1) * ST];
-        Cl[m1][0] = v.x; Cl[m1][1] = v.y;
-        Ch[m1][0] = w.x; Ch[m1][1] = w.y;
-      }
       const double sc = 0.25 * a.scale;
       K11 *= sc; K10 *= sc; K12 *= sc; K22 *= sc; K20 *= sc; M00 *= sc; M01 *= sc; M02 *= sc;
       const double K21 = K12;
 #define P2H_DD(n) ((n) == 1 ? d1 : d2)
 #define P2H_A(m1, m2) A9[(m1) + 3 * (m2)]
-      double r0[2][2], r1[3][2], r2[2][3];
+      // ordered for short live ranges: the "lo" rows feed the mass terms and r0 and die; then one "hi" block at a time
+      double Yh[9], r0[2][2], r1[3][2], r2[2][3];
+      {
+        double Bl[2][3], Cl[3][2];
 #pragma unroll
-      for (int m1 = 0; m1 < 2; m1++)
+        for (int m2 = 0; m2 < 3; m2++) { const double2 v = E1[(m2 + 3 * h) * ST]; Bl[0][m2] = v.x; Bl[1][m2] = v.y; }
 #pragma unroll
-        for (int m2 = 0; m2 < 2; m2++) r0[m1][m2] = fma(P2H_DD(m1 + 1), Cl[m1 + 1][m2], -P2H_DD(m2 + 1) * Bl[m1][m2 + 1]);
+        for (int m1 = 0; m1 < 3; m1++) { const double2 v = E2c[(h + 3 * m1) * ST]; Cl[m1][0] = v.x; Cl[m1][1] = v.y; }
 #pragma unroll
-      for (int m1 = 0; m1 < 3; m1++)
+        for (int n2 = 0; n2 < 3; n2++)
 #pragma unroll
-        for (int m2 = 0; m2 < 2; m2++) r1[m1][m2] = fma(P2H_DD(m2 + 1), P2H_A(m1, m2 + 1), -dh * Ch[m1][m2]);
+          for (int n1 = 0; n1 < 3; n1++) {
+            double v = M00 * P2H_A(n1, n2);
+            if (n1 < 2) v = fma(M01, Bl[n1][n2], v);
+            if (n2 < 2) v = fma(M02, Cl[n1][n2], v);
+            Yh[n1 + 3 * n2] = v;
+          }
 #pragma unroll
-      for (int m1 = 0; m1 < 2; m1++)
+        for (int m1 = 0; m1 < 2; m1++)
 #pragma unroll
-        for (int m2 = 0; m2 < 3; m2++) r2[m1][m2] = fma(dh, Bh[m1][m2], -P2H_DD(m1 + 1) * P2H_A(m1 + 1, m2));
-      double w1[3][2], w2[2][3];
+          for (int m2 = 0; m2 < 2; m2++) r0[m1][m2] = fma(P2H_DD(m1 + 1), Cl[m1 + 1][m2], -P2H_DD(m2 + 1) * Bl[m1][m2 + 1]);
+      }
+      {
+        double Ch[3][2];
+#pragma unroll
+        for (int m1 = 0; m1 < 3; m1++) { const double2 w = E2c[(h + 1 + 3 * m1) * ST]; Ch[m1][0] = w.x; Ch[m1][1] = w.y; }
+#pragma unroll
+        for (int m1 = 0; m1 < 3; m1++)
+#pragma unroll
+          for (int m2 = 0; m2 < 2; m2++) r1[m1][m2] = fma(P2H_DD(m2 + 1), P2H_A(m1, m2 + 1), -dh * Ch[m1][m2]);
+      }
+      {
+        double Bh[2][3];
+#pragma unroll
+        for (int m2 = 0; m2 < 3; m2++) { const double2 w = E1[(m2 + 3 * (h + 1)) * ST]; Bh[0][m2] = w.x; Bh[1][m2] = w.y; }
+#pragma unroll
+        for (int m1 = 0; m1 < 2; m1++)
+#pragma unroll
+          for (int m2 = 0; m2 < 3; m2++) r2[m1][m2] = fma(dh, Bh[m1][m2], -P2H_DD(m1 + 1) * P2H_A(m1 + 1, m2));
+      }
+      // Yh += D^T (K r): w1 = K11 r1 + K10 r0 + K12 r2, w2 = K22 r2 + K20 r0 + K21 r1 (same operation order as before)
 #pragma unroll
       for (int m1 = 0; m1 < 3; m1++)
 #pragma unroll
         for (int m2 = 0; m2 < 2; m2++) {
           double v = K11 * r1[m1][m2];
           if (m1 < 2) v = fma(K12, r2[m1][m2], fma(K10, r0[m1][m2], v));
-          w1[m1][m2] = v;
+          Yh[m1 + 3 * (m2 + 1)] = fma(P2H_DD(m2 + 1), v, Yh[m1 + 3 * (m2 + 1)]);
         }
 #pragma unroll
       for (int m1 = 0; m1 < 2; m1++)
@@ -178,19 +192,7 @@ HCURL_BODY void hex_patch_p2h_body(Env &env, const PatchArgs &a) {
         for (int m2 = 0; m2 < 3; m2++) {
           double v = K22 * r2[m1][m2];
           if (m2 < 2) v = fma(K21, r1[m1][m2], fma(K20, r0[m1][m2], v));
-          w2[m1][m2] = v;
-        }
-      double Yh[9];
-#pragma unroll
-      for (int n2 = 0; n2 < 3; n2++)
-#pragma unroll
-        for (int n1 = 0; n1 < 3; n1++) {
-          double v = M00 * P2H_A(n1, n2);
-          if (n1 < 2) v = fma(M01, Bl[n1][n2], v);
-          if (n2 < 2) v = fma(M02, Cl[n1][n2], v);
-          if (n2 >= 1) v = fma(P2H_DD(n2), w1[n1][n2 - 1], v);
-          if (n1 >= 1) v = fma(-P2H_DD(n1), w2[n1 - 1][n2], v);
-          Yh[n1 + 3 * n2] = v;
+          Yh[(m1 + 1) + 3 * m2] = fma(-P2H_DD(m1 + 1), v, Yh[(m1 + 1) + 3 * m2]);
         }
 #undef P2H_DD
 #undef P2H_A
