@@ -6,7 +6,7 @@ tag=${1:-r2a}
 mkdir -p gpurun_out
 run_tests() {  # name, env switch, pytest args...
   local name=$1 sw=$2; shift 2
-  env $sw=1 timeout 240 python -m pytest -x -q -m gpu -p no:cacheprovider "$@" > gpurun_out/pytest_${name}_$tag.log 2>&1
+  env $sw=1 timeout 400 python -m pytest -x -q -m gpu -p no:cacheprovider "$@" > gpurun_out/pytest_${name}_$tag.log 2>&1
   echo "$name: $(tail -1 gpurun_out/pytest_${name}_$tag.log)"
 }
 run_tests default HCURL_NONE tests/test_gpu_apply.py tests/test_gpu_pcg.py tests/test_zy_fullsize_properties.py
