@@ -47,7 +47,9 @@ def _run_child(env_switch, args, limit):
         pytest.fail("child exceeded %d s (hang?)\n%s" % (limit, out[-3000:]))
     print(r.stdout[-3000:])
     print(r.stderr[-2000:])
-    assert r.returncode == 0, "child failed:\n" + r.stdout[-3000:]
+    if r.returncode != 0:
+        key = [ln.strip() for ln in r.stdout.splitlines() if ln.startswith(("E  ", "FAILED", "ERROR")) or "Error" in ln][:6]
+        pytest.fail("child failed:\n" + r.stdout[-3000:] + "\nKEY LINES:\n" + "\n".join(ln[:200] for ln in key), pytrace=False)
     assert " passed" in r.stdout and "skipped" not in r.stdout.splitlines()[-1], r.stdout[-500:]
 
 
