@@ -3,7 +3,7 @@
 # full capture of the dominant kernel, phase profile, sweep over the other orders.  Outputs under gpurun_out/.
 tag=${1:-r1}
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu_$tag.log 2>&1; tail -3 gpurun_out/pytest_gpu_$tag.log
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu_$tag.log 2>&1; tail -3 gpurun_out/pytest_gpu_$tag.log
 timeout 400 python bench.py > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err; tail -c 300 gpurun_out/bench_$tag.err
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$tag.json 2> gpurun_out/bench_ref_$tag.err; tail -c 300 gpurun_out/bench_ref_$tag.err
 BENCH="python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e --pcg-iters 3"
