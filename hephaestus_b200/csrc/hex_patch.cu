@@ -950,6 +950,13 @@ int hex_patch_build(hcurl_space *sp, const double *elem_xyz, const int32_t *elem
   const char *halfk = getenv("HCURL_PATCH_HALF");
   P.half_kernel = halfk && (halfk[0] == '1' || halfk[0] == '2') && FE == 32 && !split;  // two threads per element component, opt-in
   P.half_regs = (halfk && halfk[0] == '2') ? 80 : 96;
+  for (size_t i = 0; i < code.size() && !P.general_orient; i++) {
+    const uint32_t f = code[i] >> 29;
+    P.general_orient = f != 0u && f != 7u;
+  }
+  if (const char *s = getenv("HCURL_PATCH_GENERAL")) P.general_orient = P.general_orient || s[0] == '1';  // tests
+  const char *sglk = getenv("HCURL_PATCH_SINGLE");
+  P.single_kernel = sglk && sglk[0] == '1' && (FE == 32 || FE == 64) && !split;  // one thread per element, opt-in
   P.split = split; P.max_d_words = H.max_d_words; P.max_l_words = H.max_l_words;
   if (split && upload(P.d_part_off, H.part_off)) return 1;
   P.blob_words = (int64_t)H.blob.size(); P.max_blob_words = H.max_blob_words; P.max_dofs = H.max_dofs;
@@ -1089,7 +1096,7 @@ int hex_patch_launch(hcurl_op *op, bool constrained, const double *d_x, double *
   a.d_cap_bytes = (P.max_d_words * 4 + 15u) & ~15u;
   a.l_cap_bytes = (P.max_l_words * 4 + 15u) & ~15u;
   const size_t smem = P.split ? patch_split_smem_bytes(P.FE, P) : patch_smem_bytes(P.FE, P.max_blob_words, P.max_dofs);
-  if (P.env_kernel || P.half_kernel) {
+  if (P.env_kernel || P.half_kernel || P.single_kernel) {
     a.prof = nullptr;
     if (hex_patch_p2e_launch(op, a, accumulate)) return 1;
     HC_CUDA(cudaGetLastError());

@@ -10,6 +10,7 @@
 #include "patch_dev.cuh"
 #include "hex_patch_p2_body.h"
 #include "hex_patch_p2h_body.h"
+#include "hex_patch_p2s_body.h"
 
 namespace hcurl {
 
@@ -83,6 +84,44 @@ __global__ void __maxnreg__(REGS) hex_patch_p2h_kernel(const PatchArgs a) {
   hex_patch_p2h_body<P2DeviceEnv, FE, ACC, DOT>(env, a);
 }
 
+// one thread per element (hex_patch_p2s_body.h): FE threads per CTA, no exchange buffer
+template <int FE, bool ACC, bool DOT, bool GENERAL>
+__global__ void __launch_bounds__(FE, 1) hex_patch_p2s_kernel(const PatchArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_p2s[];
+  P2DeviceEnv env{smem_p2s};
+  hex_patch_p2s_body<P2DeviceEnv, FE, ACC, DOT, GENERAL>(env, a);
+}
+
+template <int FE, bool GENERAL>
+static int launch_p2s(const PatchArgs &a, int64_t n_run, int sm_count, int n_partial, size_t smem, bool acc, cudaStream_t st) {
+  auto k0 = hex_patch_p2s_kernel<FE, false, false, GENERAL>;
+  auto k1 = hex_patch_p2s_kernel<FE, true, false, GENERAL>;
+  auto kd = hex_patch_p2s_kernel<FE, false, true, GENERAL>;
+  static size_t attr = 0;
+  static int per_sm = 0;
+  if (attr < smem) {
+    HC_CUDA(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HC_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HC_CUDA(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HC_CUDA(cudaFuncSetAttribute(k0, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    HC_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    HC_CUDA(cudaFuncSetAttribute(kd, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    HC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kd, FE, smem));
+    if (per_sm < 1) { set_error("patch kernel does not fit on an SM (%zu bytes of shared memory)", smem); return 1; }
+    attr = smem;
+  }
+  int64_t grid = (int64_t)per_sm * sm_count;
+  if (const char *s = getenv("HCURL_PATCH_CTAS_PER_SM")) { const int v = atoi(s); if (v >= 1 && v <= per_sm) grid = (int64_t)v * sm_count; }
+  if (grid > n_run) grid = n_run;
+  if (a.dot_out) {
+    if (acc) { set_error("patch kernel: fused dot product is not available with accumulation"); return 1; }
+    if (grid > n_partial) grid = n_partial;
+    kd<<<(unsigned)grid, FE, smem, st>>>(a);
+  } else if (acc) k1<<<(unsigned)grid, FE, smem, st>>>(a);
+  else k0<<<(unsigned)grid, FE, smem, st>>>(a);
+  return 0;
+}
+
 template <int FE, int REGS>
 static int launch_p2h(const PatchArgs &a, int64_t n_run, int sm_count, int n_partial, size_t smem, bool acc, cudaStream_t st) {
   auto k0 = hex_patch_p2h_kernel<FE, false, false, REGS>;
@@ -148,7 +187,7 @@ static bool g_modal2_set = false;
 int hex_patch_p2e_launch(hcurl_op *op, const PatchArgs &a, bool accumulate) {
   hcurl_ctx *ctx = op->ctx;
   const PatchSet &P = op->sp->patch;
-  if (P.FE != 32) { set_error("Env patch kernel: FE must be 32"); return 1; }
+  if (P.FE != 32 && !(P.single_kernel && P.FE == 64)) { set_error("Env patch kernel: FE must be 32"); return 1; }
   if (!g_modal2_set) {
     ModalTables T;
     if (compute_modal_tables(T)) return 1;
@@ -160,6 +199,16 @@ int hex_patch_p2e_launch(hcurl_op *op, const PatchArgs &a, bool accumulate) {
   const size_t smem = P.split ? 32 + 2 * (size_t)a.d_cap_bytes + a.l_cap_bytes + T_CAP + a.xs_cap_bytes + 2 * (size_t)27 * FE * 16
                               : 16 + 2 * (size_t)a.blob_cap_bytes + a.xs_cap_bytes + 2 * (size_t)27 * (FE + 1) * 16;
   const int64_t n_run = a.n_patch - a.k_begin;
+  if (P.single_kernel) {
+    if (P.split) { set_error("the one-thread-per-element kernel uses the plain blob layout (unset HCURL_PATCH_SPLIT)"); return 1; }
+    const size_t sm1 = 16 + 2 * (size_t)a.blob_cap_bytes + a.xs_cap_bytes + (size_t)27 * (P.FE + 1) * 16;
+    if (P.general_orient) {
+      if (P.FE == 64) return launch_p2s<64, true>(a, n_run, ctx->sm_count, ctx->n_partial, sm1, accumulate, ctx->stream);
+      return launch_p2s<32, true>(a, n_run, ctx->sm_count, ctx->n_partial, sm1, accumulate, ctx->stream);
+    }
+    if (P.FE == 64) return launch_p2s<64, false>(a, n_run, ctx->sm_count, ctx->n_partial, sm1, accumulate, ctx->stream);
+    return launch_p2s<32, false>(a, n_run, ctx->sm_count, ctx->n_partial, sm1, accumulate, ctx->stream);
+  }
   if (P.half_kernel) {
     if (P.split) { set_error("the two-threads-per-component kernel uses the plain blob layout (unset HCURL_PATCH_SPLIT)"); return 1; }
     if (P.half_regs == 80) return launch_p2h<FE, 80>(a, n_run, ctx->sm_count, ctx->n_partial, smem, accumulate, ctx->stream);

@@ -111,6 +111,8 @@ struct PatchSet {  // device copy
   bool split = false;            // blobs built for the split-blob kernel variant (unpadded rows)
   bool env_kernel = false;       // launch the Env-program restatement (hex_patch_p2e.cu) instead of hex_patch.cu's kernels
   bool half_kernel = false;      // launch the two-threads-per-component Env program (hex_patch_p2h_body.h)
+  bool general_orient = false;   // some element slot pair is flagged other than "reversed line" (all three bits): general kernels
+  bool single_kernel = false;    // launch the one-thread-per-element Env program (hex_patch_p2s_body.h)
   int half_regs = 96;            // its register cap: 96 (HCURL_PATCH_HALF=1) or 80 (HCURL_PATCH_HALF=2)
   uint32_t *d_part_off = nullptr;
   uint32_t max_d_words = 0, max_l_words = 0;

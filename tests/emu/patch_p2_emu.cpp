@@ -3,6 +3,7 @@
 #include "host_env.h"
 #include "hex_patch_p2_body.h"
 #include "hex_patch_p2h_body.h"
+#include "hex_patch_p2s_body.h"
 
 namespace {
 template <int FE, bool ACC, bool DOT, bool SPLIT>
@@ -20,6 +21,20 @@ int run_half(const hcurl::PatchArgs &a, int64_t grid, size_t smem_bytes, const h
                                 [&](emu::HostEnv &env) { hcurl::hex_patch_p2h_body<emu::HostEnv, FE, ACC, DOT>(env, a); });
   if (DOT && a.dot_out) *a.dot_out = a.dot_add ? *a.dot_out + dot : dot;
   return err;
+}
+template <int FE, bool ACC, bool DOT, bool GENERAL>
+int run_single(const hcurl::PatchArgs &a, int64_t grid, size_t smem_bytes, const hcurl::ModalTables &T) {
+  double dot = 0.0;
+  const int err = emu::run_grid(grid, FE, smem_bytes, &T, &dot,
+                                [&](emu::HostEnv &env) { hcurl::hex_patch_p2s_body<emu::HostEnv, FE, ACC, DOT, GENERAL>(env, a); });
+  if (DOT && a.dot_out) *a.dot_out = a.dot_add ? *a.dot_out + dot : dot;
+  return err;
+}
+template <int FE, bool GENERAL>
+int run_single_fe(const hcurl::PatchArgs &a, int64_t grid, const hcurl::ModalTables &T, bool accumulate) {
+  const size_t smem = 16 + 2 * (size_t)a.blob_cap_bytes + a.xs_cap_bytes + (size_t)27 * (FE + 1) * 16;
+  if (a.dot_out) return accumulate ? -1 : run_single<FE, false, true, GENERAL>(a, grid, smem, T);
+  return accumulate ? run_single<FE, true, false, GENERAL>(a, grid, smem, T) : run_single<FE, false, false, GENERAL>(a, grid, smem, T);
 }
 }  // namespace
 
@@ -42,6 +57,10 @@ extern "C" int emu_patch_p2_apply(int split, int accumulate, int64_t n_patch, in
                             : 16 + 2 * (size_t)blob_cap_bytes + xs_cap_bytes + 2 * (size_t)27 * (FE + 1) * 16;
   if (grid > n_patch - k_begin) grid = n_patch - k_begin;
   if (grid < 1) return 0;
+  // one thread per element (hex_patch_p2s_body.h): reversed-line orientation flags only (3, 4) / general flags (5)
+  if (split == 3) return run_single_fe<32, false>(a, grid, T, accumulate != 0);
+  if (split == 4) return run_single_fe<64, false>(a, grid, T, accumulate != 0);
+  if (split == 5) return run_single_fe<32, true>(a, grid, T, accumulate != 0);
   if (split == 2) {  // two threads per element component (hex_patch_p2h_body.h), plain blob layout
     if (dot_out) return accumulate ? -1 : run_half<FE, false, true>(a, grid, smem, T);
     return accumulate ? run_half<FE, true, false>(a, grid, smem, T) : run_half<FE, false, false>(a, grid, smem, T);

@@ -372,6 +372,19 @@ def test_hex_p2_patch_kernel_half_program(ctx, n, regs, monkeypatch):
     _p2_patch_variant_parity(ctx, n)
 
 
+@pytest.mark.parametrize("general", ["0", "1"])
+@pytest.mark.parametrize("fe", ["32", "64"])
+@pytest.mark.parametrize("n", [(9, 8, 6), (5, 4, 3)])
+def test_hex_p2_patch_kernel_single_program(ctx, n, fe, general, monkeypatch):
+    """hex_patch_p2s_kernel (one thread per element, 32- / 64-element patches; reversed-line and general orientation
+    handling): same parity bar as the other patch kernels."""
+    monkeypatch.setenv("HCURL_PATCH_SINGLE", "1")
+    monkeypatch.setenv("HCURL_PATCH_GENERAL", general)
+    monkeypatch.setenv("HCURL_PATCH_SPLIT", "0")
+    monkeypatch.setenv("HCURL_PATCH_FE", fe)
+    _p2_patch_variant_parity(ctx, n)
+
+
 def _p2_patch_variant_parity(ctx, n):
     m, sp, mo, so = make_pair("hex", n, 2, False, scramble=True)
     a, b = coefficients(m)

@@ -40,15 +40,22 @@ def emu2(tmp_path_factory, lib_built):
     return lib
 
 
+VARIANT = {"half": 2, "single": 3, "single64": 4, "single_general": 5}
+
+
 def build_patches(sp, mesh, split):
-    """split: False = plain blobs, True = split-blob layout, "half" = plain blobs for the two-threads-per-component program"""
+    """split: False = plain blobs, True = split-blob layout, "half" / "single" / "single64" = plain blobs for the
+    two-threads-per-component program / the one-thread-per-element program with 32- / 64-element patches"""
     lib = L.lib()
-    half, split = split == "half", split is True
+    variant, split = VARIANT.get(split, 0), split is True
+    FE = 64 if variant == 4 else 32
     sd = np.ascontiguousarray(sp.signed_elem_dofs(), dtype=np.int32)
     ne = sd.shape[0]
     assert sd.shape[1] == 54 and sp.ndof % 2 == 0
     code = np.zeros((ne, 27), np.uint32)
     L.check(lib.hcurl_host_hex_p2_pair_codes(ne, L.ptr(sd), L.ptr(code)), "pair codes")
+    if variant in (3, 4):  # the reversed-line kernels: MFEM-convention maps flag a slot pair with all three bits or none
+        assert np.all(np.isin(code >> 29, (0, 7)))
     cen = np.ascontiguousarray(mesh.verts[mesh.elems].mean(axis=1))
     h = L.check_ptr(lib.hcurl_host_patches_create(27, ne, FE, FE if split else FE + 1, 16, sp.ndof // 2, L.ptr(cen), L.ptr(code), None), "patches")
     npatch = lib.hcurl_host_patches_count(h)
@@ -65,7 +72,7 @@ def build_patches(sp, mesh, split):
     lib.hcurl_host_patches_destroy(h)
     T = np.zeros(7)
     L.check(lib.hcurl_host_modal_tables_p2(L.ptr(T)), "tables")
-    return dict(perm=perm, off=off, blob=blob, row=row, grp=grp, part=part, caps=caps, T=T, split=2 if half else int(split))
+    return dict(perm=perm, off=off, blob=blob, row=row, grp=grp, part=part, caps=caps, T=T, split=variant or int(split), FE=FE)
 
 
 def run_emu(emu2, P, edata, x, y, scale=1.0, accumulate=False, grid=2, dot=False, blob=None, k_begin=0, k_end=None):
@@ -91,7 +98,7 @@ def shared_mask(off, blob, ndof):
 
 # (6,6,5) = 180 elements -> 6 patches: with grid 1 / 2 the double-buffered pipeline wraps around; scrambled vertex
 # numbering makes pairs swapped / sign-flipped (the non-plain path), the unscrambled cube exercises the plain path
-@pytest.mark.parametrize("split", [False, True, "half"])
+@pytest.mark.parametrize("split", [False, True, "half", "single", "single64", "single_general"])
 @pytest.mark.parametrize("n,grid,scramble", [((6, 6, 5), 1, True), ((6, 6, 5), 2, False), ((4, 4, 4), 3, True), ((3, 2, 2), 1, True)])
 def test_emulated_p2_kernel_matches_oracle(emu2, split, n, grid, scramble):
     m, mo = affine_pair("hex", n)
@@ -106,7 +113,7 @@ def test_emulated_p2_kernel_matches_oracle(emu2, split, n, grid, scramble):
     alpha, beta = coefficients(mo)
     A = oa.assemble(so, alpha, beta, q_override=3).tocsr()
     P = build_patches(sp, m, split)
-    edata = geometry_factors(m, P["perm"], FE, alpha, beta)
+    edata = geometry_factors(m, P["perm"], P["FE"], alpha, beta)
     rng = np.random.default_rng(8)
     x = rng.standard_normal(sp.ndof)
     sh = shared_mask(P["off"], P["blob"], sp.ndof)
@@ -127,7 +134,7 @@ def test_emulated_p2_kernel_matches_oracle(emu2, split, n, grid, scramble):
         assert np.abs(y3 - ref).max() <= 1e-12 * np.abs(ref).max()
 
 
-@pytest.mark.parametrize("split", [False, True, "half"])
+@pytest.mark.parametrize("split", [False, True, "half", "single", "single64", "single_general"])
 def test_emulated_p2_kernel_overflow_slots(emu2, split):
     """star meshes (six rhombic prisms around an edge, stacked): pairs with more than four element slots in one patch go
     through the overflow list and are RED-added"""
@@ -140,7 +147,7 @@ def test_emulated_p2_kernel_overflow_slots(emu2, split):
     P = build_patches(sp, m, split)
     n_ovf = sum(int(P["blob"][int(o) * 4 + 7]) for o in P["off"][:-1])
     assert n_ovf > 0
-    edata = geometry_factors(m, P["perm"], FE, alpha, beta)
+    edata = geometry_factors(m, P["perm"], P["FE"], alpha, beta)
     x = np.random.default_rng(4).standard_normal(sp.ndof)
     sh = shared_mask(P["off"], P["blob"], sp.ndof)
     y = np.where(sh, 0.0, 1e30)
@@ -150,7 +157,7 @@ def test_emulated_p2_kernel_overflow_slots(emu2, split):
     assert abs(dot - x @ ref) <= 1e-12 * abs(x @ ref)
 
 
-@pytest.mark.parametrize("split", [False, True, "half"])
+@pytest.mark.parametrize("split", [False, True, "half", "single", "single64", "single_general"])
 def test_emulated_p2_kernel_essential_dofs(emu2, split):
     m, mo = affine_pair("hex", (5, 4, 3), seed=9)
     sp, so = fespace.NDSpace(m, 2), osp.NDSpace(mo, 2)
@@ -169,7 +176,7 @@ def test_emulated_p2_kernel_essential_dofs(emu2, split):
         q = (w & IDX).astype(np.int64)
         w[flag[2 * q]] |= ESS0
         w[flag[2 * q + 1]] |= ESS1
-    edata = geometry_factors(m, P["perm"], FE, alpha, beta)
+    edata = geometry_factors(m, P["perm"], P["FE"], alpha, beta)
     x = np.random.default_rng(2).standard_normal(sp.ndof)
     sh = shared_mask(P["off"], P["blob"], sp.ndof)
     y = np.where(sh, 0.0, 1e30)
