@@ -346,7 +346,8 @@ def main():
                 "peak_kind": "of " + peak_kind,
                 "kernel": "tet batched packed-symmetric element-matrix kernel (order %d)" % p if args.geom == "tet" else
                 "hex element kernel (order %d; %s)" % (
-                    p, {1: "generic sum-factorised", 2: "element-wise register-blocked", 3: "patch, modal, persistent"}.get(op.LastKernel(), "?")),
+                    p, {1: "generic sum-factorised", 2: "element-wise register-blocked",
+                        3: "patch pipeline: one thread per element, modal operator, persistent, zero-ahead watermark"}.get(op.LastKernel(), "?")),
                 "kernel_ms": kern_ms, "kernel_launches_timed": kern_n, "algorithmic_bytes_per_launch": abytes,
                 "bytes_per_dof": abytes / n_tdof, "kernel_share_of_step": kern_ms / ms_step if ms_step > 0 else None,
                 "fp64_fma_peak_tflops_measured": fp64}

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libhcurl_b200.so")
+LIB_PATH = os.environ.get("HCURL_LIB_PATH") or os.path.join(_HERE, "lib", "libhcurl_b200.so")  # override: diagnostic builds only
 
 
 class HcurlError(RuntimeError):
@@ -104,7 +104,8 @@ SIGNATURES = {
     "hcurl_host_partition_sizes": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int),
                                              C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "hcurl_host_partition_copy": (C.c_int, [_P] * 10),
-    "hcurl_host_patches_parts": (C.c_int, [_P, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "hcurl_host_patches_parts": (C.c_int, [_P, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "hcurl_host_patches_owned": (C.c_int64, [_P, _P, _P]),
     "hcurl_host_modal_tables_p2": (C.c_int, [_P]),
     "hcurl_host_hex_slot_codes": (C.c_int, [C.c_int, C.c_int64, _P, _P]),
     "hcurl_host_patches_create": (_P, [C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int64, _P, _P, _P]),

@@ -278,62 +278,28 @@ int op_apply_ext(hcurl_op *op, double *d_x, double *d_y, bool constrained, doubl
   hcurl_space *sp = op->sp;
   hcurl_ctx *ctx = op->ctx;
   const int64_t next = sp->n_ext();
-  // the patch kernel stores every private pair itself: only what it accumulates into must be cleared (plus, on
-  // several GPUs, the ghost tail that the reduction sends back); the other kernels RED-add everything
+  // the patch kernel writes every dof the elements touch (owner stores, the others add after it) and the identity on
+  // the essential dofs: nothing to clear, nothing to fix up; the other kernels RED-add everything
   const bool patch_path = hex_patch_eligible(op) && (((uintptr_t)d_x | (uintptr_t)d_y) & 15) == 0;
   const bool fuse_dot = patch_path && d_dot && !accumulate;
   if (dot_done) *dot_done = fuse_dot;
-  // Several GPUs, patch path: the patches that touch exchanged pairs come first in the patch order (patch.cpp), so the
-  // apply CAN run as   [x: owner -> ghosts] || interior patches (1st part)  ->  boundary patches  ->
-  // [y: ghosts -> owner] || interior patches (2nd part), the two exchanges on the communication stream.
-  // Measured on 2 B200s (128^3 bricks): 0.616 ms per apply against 0.578 ms for the plain sequence -- three launches
-  // of a persistent kernel cost more in fill/drain (1024 boundary patches on 592 CTAs) than the 2 x 30 us of exchange
-  // they hide, and NCCL's copy kernels wait for SM resources the persistent CTAs hold.  Off unless HCURL_OVERLAP=1.
-  static const bool want_overlap = [] { const char *e = getenv("HCURL_OVERLAP"); return e && e[0] == '1'; }();
-  const PatchSet &P = sp->patch;
-  const bool overlap = want_overlap && patch_path && sp->n_nbr > 0 && ctx->comm_stream && P.n_boundary > 0 && P.n_boundary < P.n_patch;
-  if (overlap) {
-    HC_CUDA(cudaEventRecord(ctx->ev_x[0], ctx->stream));            // x is final on the main stream
-    HC_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_x[0], 0));
-    if (exchange_broadcast(sp, d_x, ctx->comm_stream)) return 1;
-    HC_CUDA(cudaEventRecord(ctx->ev_x[1], ctx->comm_stream));
-  } else if (exchange_broadcast(sp, d_x)) return 1;
-  if (!accumulate && patch_path) {
-    if (hex_patch_zero_shared(op, d_y)) return 1;
-    if (sp->n_ghost) HC_CUDA(cudaMemsetAsync(d_y + sp->n_tdof, 0, sizeof(double) * sp->n_ghost, ctx->stream));
-  } else if (!accumulate) HC_CUDA(cudaMemsetAsync(d_y, 0, sizeof(double) * next, ctx->stream));
-  else if (sp->n_ghost) HC_CUDA(cudaMemsetAsync(d_y + sp->n_tdof, 0, sizeof(double) * sp->n_ghost, ctx->stream));
+  if (exchange_broadcast(sp, d_x)) return 1;
+  if (!patch_path) {
+    if (!accumulate) HC_CUDA(cudaMemsetAsync(d_y, 0, sizeof(double) * next, ctx->stream));
+    else if (sp->n_ghost) HC_CUDA(cudaMemsetAsync(d_y + sp->n_tdof, 0, sizeof(double) * sp->n_ghost, ctx->stream));
+  }
   const uint32_t *map = (constrained && op->d_map_ess) ? op->d_map_ess : sp->d_map;
   cudaEvent_t e0 = op->ev0, e1 = op->ev1;
   if (op->ring_ok) { e0 = op->ring0[op->ring_n % hcurl_op::RING]; e1 = op->ring1[op->ring_n % hcurl_op::RING]; op->ring_n++; op->ev0 = e0; op->ev1 = e1; }
   if (op->timed) HC_CUDA(cudaEventRecord(e0, ctx->stream));
   int rc;
-  if (overlap) {
-    op->last_kernel = 3;
-    // a quarter of the interior patches covers the x exchange, the rest the y exchange
-    const int64_t nb = P.n_boundary, mid = nb + (P.n_patch - nb) / 4;
-    double *dd = fuse_dot ? d_dot : nullptr;
-    rc = hex_patch_launch(op, constrained, d_x, d_y, scale, accumulate, dd, nb, mid, false);
-    if (rc) return rc;
-    HC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_x[1], 0));     // ghosts of x have arrived
-    rc = hex_patch_launch(op, constrained, d_x, d_y, scale, accumulate, dd, 0, nb, true);
-    if (rc) return rc;
-    HC_CUDA(cudaEventRecord(ctx->ev_x[2], ctx->stream));            // every exchanged pair of y is final locally
-    HC_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_x[2], 0));
-    if (exchange_reduce(sp, d_y, true, ctx->comm_stream)) return 1;
-    HC_CUDA(cudaEventRecord(ctx->ev_x[3], ctx->comm_stream));
-    rc = hex_patch_launch(op, constrained, d_x, d_y, scale, accumulate, dd, mid, P.n_patch, true);
-    if (rc) return rc;
-    HC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_x[3], 0));
-    if (op->timed) HC_CUDA(cudaEventRecord(e1, ctx->stream));
-  } else {
-    if (patch_path) { op->last_kernel = 3; rc = hex_patch_launch(op, constrained, d_x, d_y, scale, accumulate, fuse_dot ? d_dot : nullptr); }
-    else if (hex_fast_eligible(op)) { op->last_kernel = 2; rc = hex_fast_launch(op, constrained, d_x, d_y, scale); }
-    else { op->last_kernel = 1; rc = (sp->geom == HCURL_GEOM_HEX) ? hex_apply_launch(op, map, d_x, d_y, scale) : tet_apply_launch(op, map, d_x, d_y, scale); }
-    if (rc) return rc;
-    if (op->timed) HC_CUDA(cudaEventRecord(e1, ctx->stream));
-    if (exchange_reduce(sp, d_y)) return 1;
-  }
+  if (patch_path) { op->last_kernel = 3; rc = hex_patch_launch(op, constrained, d_x, d_y, scale, accumulate, fuse_dot ? d_dot : nullptr); }
+  else if (hex_fast_eligible(op)) { op->last_kernel = 2; rc = hex_fast_launch(op, constrained, d_x, d_y, scale); }
+  else { op->last_kernel = 1; rc = (sp->geom == HCURL_GEOM_HEX) ? hex_apply_launch(op, map, d_x, d_y, scale) : tet_apply_launch(op, map, d_x, d_y, scale); }
+  if (rc) return rc;
+  if (op->timed) HC_CUDA(cudaEventRecord(e1, ctx->stream));
+  if (exchange_reduce(sp, d_y)) return 1;
+  if (patch_path && sp->n_nbr == 0) return 0;  // essential rows were written by the kernel
   if (constrained && op->n_ess > 0) {
     if (fuse_dot) {  // essential rows are identity: y = x there, and <x, y> gains x^2
       int g = (op->n_ess + RED_THREADS * 4 - 1) / (RED_THREADS * 4);
@@ -402,6 +368,9 @@ hcurl_ctx *hcurl_ctx_create(int device, const void *uid, int rank, int nranks) {
   HC_CUDA_NULL(cudaMalloc(&ctx->d_partial, sizeof(double) * ctx->n_partial));
   HC_CUDA_NULL(cudaEventCreate(&ctx->mark[0]));
   HC_CUDA_NULL(cudaEventCreate(&ctx->mark[1]));
+  int coop = 0;
+  HC_CUDA_NULL(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+  ctx->coop_ok = coop != 0;
   if (comm_init(ctx, uid)) { delete ctx; return nullptr; }
   if (ctx->nranks > 1) {  // second stream + hand-off events: the shared-dof exchange overlaps with interior patches
     HC_CUDA_NULL(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));

@@ -70,26 +70,8 @@ __global__ void dmma_kernel(double *out, int iters, int mode) {
 }  // namespace hcurl
 
 using namespace hcurl;
-namespace hcurl { extern unsigned long long *g_patch_prof; }
 
 extern "C" {
-
-// Phase profile of the patch kernel: enable (allocates 8 device counters), run applies, then read.
-// out[i] = cycles thread 0 spent in phase i summed over all CTAs since enable.
-int hcurl_debug_patch_profile(hcurl_ctx *ctx, int enable, unsigned long long *out8) {
-  cudaSetDevice(ctx->device);
-  if (enable) {
-    if (!g_patch_prof) cudaMalloc(&g_patch_prof, 8 * sizeof(unsigned long long));
-    cudaMemset(g_patch_prof, 0, 8 * sizeof(unsigned long long));
-    return 0;
-  }
-  if (!g_patch_prof) return 1;
-  cudaStreamSynchronize(ctx->stream);
-  cudaMemcpy(out8, g_patch_prof, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-  cudaFree(g_patch_prof);
-  g_patch_prof = nullptr;
-  return 0;
-}
 
 // returns ms per launch (best of reps); mode 0 gather only, 1 gather+RED scatter, 2 flagged dofs as plain stores
 double hcurl_debug_gather_scatter_ms(hcurl_op *op, int mode, int reps) {

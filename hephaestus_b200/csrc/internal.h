@@ -26,12 +26,15 @@ bool cuda_ok(cudaError_t e, const char *what);
 static constexpr uint32_t MAP_IDX = 0x3fffffffu;
 static constexpr uint32_t MAP_ESS = 0x40000000u;
 static constexpr uint32_t MAP_NEG = 0x80000000u;
-// patch blobs (patch.cpp): unit index in bits 0..28, bits 29/30 essential flags of the unit's first /
-// second double, bit 31 marks units shared with other patches.  Slot codes handed to build_patches
-// carry orientation flags in bits 29..31 instead.
-static constexpr uint32_t PATCH_IDX = 0x1fffffffu;
+// patch blobs (patch.cpp): unit index in bits 0..27, bit 28 marks the shared units this patch OWNS (it is the
+// lowest-numbered patch touching them: it pre-fills them), bits 29/30 essential flags of the unit's first / second
+// double, bit 31 marks units shared with other patches.  Slot codes handed to build_patches carry a 29-bit unit index
+// and orientation flags in bits 29..31 instead.
+static constexpr uint32_t PATCH_IDX = 0x0fffffffu;
+static constexpr uint32_t PATCH_OWNED = 0x10000000u;
 static constexpr uint32_t PATCH_ESS0 = 0x20000000u, PATCH_ESS1 = 0x40000000u;
 static constexpr uint32_t PATCH_SHARED = 0x80000000u;
+static constexpr uint32_t SLOT_IDX = 0x1fffffffu;  // unit index of a slot code
 static constexpr uint32_t PAIR_SWAP = 0x20000000u, PAIR_NEG1 = 0x40000000u, PAIR_NEG0 = 0x80000000u;
 
 // ---------------------------------------------------------------- basis ----
@@ -74,20 +77,21 @@ struct PatchHost {
   int FE = 0, stride = 0, nd = 0;
   int64_t n_patch = 0;
   int64_t n_boundary = 0;         // patches [0, n_boundary) touch units of the inter-rank exchange
-  static constexpr int HDR = 16;  // header words per patch blob
+  static constexpr int HDR = 32;  // header words per patch blob
   std::vector<int32_t> perm;      // [n_patch*FE] element at each patch position, -1 = padding
   std::vector<uint32_t> blob_off; // [n_patch+1] start of each patch blob in 16-byte units
   std::vector<uint32_t> blob;     // see patch.cpp for the layout
   uint32_t max_blob_words = 0;
-  uint32_t max_dofs = 0;          // largest number of unique dofs of one patch
+  uint32_t max_dofs = 0;          // largest number of unique units of one patch
   // the blob of patch k by lifetime: [blob_off[k], part_off[2k]) header + unit list, [part_off[2k], part_off[2k+1])
-  // slot-offset lists, [part_off[2k+1], blob_off[k+1]) per-slot table (16-byte units); largest first two parts in words
+  // slot-offset / overflow / dependency lists, [part_off[2k+1], blob_off[k+1]) per-slot table (16-byte units); largest
+  // parts in words
   std::vector<uint32_t> part_off;
-  uint32_t max_d_words = 0, max_l_words = 0;
+  uint32_t max_d_words = 0, max_l_words = 0, max_t_words = 0;
   // E-vector swizzle: slot s of patch position j sits at unit s*stride + (j ^ swz_row[s] ^ swz_grp[j / NB]), NB = 128 /
   // unit_bytes (values < NB, so positions stay inside their aligned run of NB: the element side remains conflict-free)
   std::vector<uint8_t> swz_row, swz_grp;
-  std::vector<uint32_t> shared_lines;  // 128-byte lines of the vector holding a unit touched by more than one patch (RED-added)
+  std::vector<uint32_t> own_off, own_idx;  // the shared units each patch owns: [n_patch+1] offsets into own_idx
 };
 int build_patches(int nd, int64_t n_elem, int FE, int stride, int unit_bytes, int64_t n_ext, const double *centroid,
                   const uint32_t *slot_code, const uint8_t *exchange_units, PatchHost &out);
@@ -101,24 +105,20 @@ void hex_slot_codes(int p, int64_t n_elem, const int32_t *elem_ldof, const int32
 struct PatchSet {  // device copy
   int FE = 0;
   int unit = 16;                 // bytes per unit of the dof side: 16 = aligned dof pair (order 2), 8 = single dof (order 1)
-  bool affine = false;           // order-1 path: every element is a parallelepiped (checked on the host at build time)
-  int64_t n_patch = 0, n_pd = 0, n_boundary = 0;
+  int64_t n_patch = 0, n_boundary = 0;
   int32_t *d_perm = nullptr;
   int stride = 0;
-  uint32_t *d_blob_off = nullptr, *d_blob = nullptr;
+  uint32_t *d_blob_off = nullptr, *d_part_off = nullptr, *d_blob = nullptr;
   int64_t blob_words = 0;
-  uint32_t max_blob_words = 0, max_dofs = 0;
-  bool split = false;            // blobs built for the split-blob kernel variant (unpadded rows)
-  bool env_kernel = false;       // launch the Env-program restatement (hex_patch_p2e.cu) instead of hex_patch.cu's kernels
-  bool half_kernel = false;      // launch the two-threads-per-component Env program (hex_patch_p2h_body.h)
-  bool general_orient = false;   // some element slot pair is flagged other than "reversed line" (all three bits): general kernels
-  bool single_kernel = false;    // launch the one-thread-per-element Env program (hex_patch_p2s_body.h)
-  int half_regs = 96;            // its register cap: 96 (HCURL_PATCH_HALF=1) or 80 (HCURL_PATCH_HALF=2)
-  uint32_t *d_part_off = nullptr;
-  uint32_t max_d_words = 0, max_l_words = 0;
+  uint32_t max_d_words = 0, max_l_words = 0, max_t_words = 0, max_dofs = 0;
+  bool general_orient = false;   // order 2: some element slot pair is flagged other than "reversed line" (all three bits)
   uint8_t swz_row[27] = {0}, swz_grp[16] = {0};
-  uint32_t *d_shared = nullptr;  // 128-byte lines holding RED-added pairs: the only part of y that must be zero before an apply
-  int64_t n_shared = 0;
+  uint32_t *d_own_off = nullptr, *d_own_idx = nullptr;  // owned shared units per patch (zeroed ahead of the sums)
+  // split-phase watermark of the zeroing (patch_pipeline.h): one arrival counter per batch of pipeline iterations,
+  // never reset: every launch adds its grid size to each, `arrivals` is the running total
+  uint32_t *d_count = nullptr;
+  int64_t n_count = 0;
+  uint32_t arrivals = 0;
 };
 
 // 1-D transform tables of the order-2 modal element operator (hex_patch.cu, hex_patch_p2_body.h)
@@ -133,31 +133,32 @@ struct ModalTables {
 };
 int compute_modal_tables(ModalTables &T);
 
-// Kernel arguments of the patch kernels (hex_patch.cu: order 2, 16-byte units; hex_patch_p1.cu: order 1, 8-byte units)
+// Kernel arguments of the patch kernels (patch_pipeline.h; order 2: 16-byte units, order 1: 8-byte units)
 struct PatchArgs {
   int64_t n_patch;           // patches [k_begin, n_patch) are processed by this launch
-  int64_t k_begin;
-  int dot_add;               // fused dot product: add to *dot_out instead of storing (second / third launch of an apply)
+  int64_t k_begin;           // (0 unless accumulating: the zeroing watermark counts whole launches)
+  int dot_add;               // fused dot product: add to *dot_out instead of storing
+  int ess_identity;          // 1: essential dofs get y = x (and x^2 enters the fused dot); 0: they get 0 (several ranks: the caller writes the rows after the exchange)
   const uint32_t *blob_off;  // [n_patch+1] in 16-byte units
+  const uint32_t *part_off;  // [2 n_patch] begin of the lists and of the per-slot table of every patch (16-byte units, absolute)
   const uint32_t *blob;      // patch blobs (patch.cpp)
   const double *edata;       // [n_patch][12][FE] affine geometry factors in patch order
   const double *x;
   double *y;
   double scale;
-  uint32_t blob_cap_bytes;   // shared-memory room reserved for one blob (multiple of 16)
-  uint32_t xs_cap_bytes;     // room for the x staging vector (max patch pairs * 16)
-  // split-blob variant: begin of the slot-offset lists and of the per-slot table of every patch (16-byte units, absolute),
-  // room for one header + pair list, and for one set of lists
-  const uint32_t *part_off;
-  uint32_t d_cap_bytes, l_cap_bytes;
+  uint32_t d_cap_bytes, l_cap_bytes, t_cap_bytes;  // shared-memory room for one header + unit list / set of lists / table (multiples of 16)
+  uint32_t xs_cap_bytes;     // room for the x staging vector
+  const uint32_t *own_off, *own_idx;  // the shared units each patch owns
+  uint32_t *count;           // arrival counters of the zeroing batches
+  uint32_t count_target;     // value every counter reaches when all CTAs of this launch have arrived
   // fused <x, y> (PCG's <p, A p>): per-CTA partial sums, arrival counter, result (null = not wanted)
   double *dot_partial;
   unsigned int *dot_counter;
   double *dot_out;
-  // EY position of (slot pair s, element e) is s*(FE+1) + (e ^ swz_row[s] ^ swz_grp[e >> 3]): chosen by patch.cpp so
+  // EY position of (slot row s, element e) is s*(FE+1) + (e ^ swz_row[s] ^ swz_grp[e / NB]): chosen by patch.cpp so
   // that the dof side's reads of EY spread over the banks
   uint8_t swz_row[27], swz_grp[16];
-  unsigned long long *prof;  // null, or 8 counters: cycles of thread 0 per phase summed over patches (scripts/phase_profile.py)
+  ModalTables modal;         // order 2: 1-D transform tables (kernel parameters live in the constant bank)
 };
 
 // ----------------------------------------------------------------- NCCL ----
@@ -180,6 +181,11 @@ struct hcurl_ctx {
   cudaEvent_t mark[2] = {nullptr, nullptr};
   cudaEvent_t ev_x[4] = {nullptr, nullptr, nullptr, nullptr};  // main <-> comm stream hand-offs of an overlapped apply
   int64_t launches = 0;
+  // per-context (= per-device) launch state of the patch kernels: shared memory opted into / CTAs per SM, by variant
+  static constexpr int N_KVAR = 16;
+  size_t kattr_smem[N_KVAR] = {0};
+  int kattr_per_sm[N_KVAR] = {0};
+  bool coop_ok = false;
 };
 
 struct hcurl_space {
@@ -275,20 +281,15 @@ int hex_fast_launch(hcurl_op *op, bool constrained, const double *d_x, double *d
 int hex_patch_build(hcurl_space *sp, const double *elem_xyz, const int32_t *elem_ldof, const int32_t *l2e);
 void hex_patch_free(hcurl_space *sp);
 bool hex_patch_eligible(const hcurl_op *op);
-// y (+)= scale * A x through the patch path; when !accumulate every dof of y is written
-// (private dofs) or must have been zeroed by the caller (shared dofs)
-// d_dot (optional, device): receives <x, y_elements> = sum over elements of x_e^T A_e x_e, computed inside the kernel
-// [k_begin, k_end): the patches to process (k_end < 0: all); dot_add: add to *d_dot instead of storing
+// y (+)= scale * A x through the patch path: every dof of y the space's elements touch is written (nothing has to be
+// cleared before), essential dofs get y = x when `constrained`
+// d_dot (optional, device): receives <x, y> over this rank's elements and owned essential dofs, computed inside the kernel
 int hex_patch_launch(hcurl_op *op, bool constrained, const double *d_x, double *d_y, double scale, bool accumulate,
-                     double *d_dot = nullptr, int64_t k_begin = 0, int64_t k_end = -1, bool dot_add = false);
+                     double *d_dot = nullptr);
 int hex_patch_flag_essential(hcurl_op *op, const double *d_flag);
-// zero what the patch kernel accumulates into (instead of clearing all of y)
-int hex_patch_zero_shared(hcurl_op *op, double *d_y);
-// order-1 patch kernel (hex_patch_p1.cu; opt-in with HCURL_PATCH_P1=1 until it has been run on a GPU)
-int hex_patch_p1_launch(hcurl_op *op, const hcurl::PatchArgs &a, bool accumulate);
-size_t patch_p1_smem_bytes(int FE, uint32_t blob_cap_bytes, uint32_t xs_cap_bytes);
-// order-2 patch kernel restated as an Env program (hex_patch_p2e.cu; opt-in with HCURL_PATCH_ENV=1, FE = 32)
-int hex_patch_p2e_launch(hcurl_op *op, const hcurl::PatchArgs &a, bool accumulate);
+// the patch kernels (hex_patch_kernels.cu): device environment of patch_pipeline.h, cooperative launch
+int hex_patch_kernel_launch(hcurl_op *op, const hcurl::PatchArgs &a, bool accumulate);
+size_t patch_smem_bytes(int unit, int FE, uint32_t d_cap, uint32_t l_cap, uint32_t t_cap, uint32_t xs_cap);
 int hex_fast_prepare_space(hcurl_space *sp);
 int hex_all_affine(hcurl_space *sp, bool *all_affine);
 int tet_build_emat(hcurl_op *op);

@@ -27,20 +27,34 @@
 // unit_bytes).  Orientation flags (sign flips, pair swap) are applied on the element side (lidx bits
 // 13..15, for the gather and for the scatter), so the dof side only sums.
 //
-// Blob layout in 32-bit words, every section starting on a 16-byte boundary:
-//   [0] U  [1] n1  [2] n2  [3] n4      number of patch units, and of 1- / 2- / 3..4-slot units
-//   [4] nP1 [5] nP2 [6] nP4            number of private units in each width section (informational)
-//   [7] n_ovf  [8..11] word offsets of the e16 / e32 / e64 / ovf sections
-//   [12] word offset of lidx  [13] number of real (non-padding) elements of the patch  [14..15] 0
-//   [16 ..] dof[U]   global unit index (bits 0..28) | PATCH_SHARED (bit 31) when other patches also
-//            touch the unit, i.e. its sum must be RED-added; bits 29, 30 are the essential flags the
-//            operator ORs in (hex_patch.cu)
-//   e16[n1], e32[n2], e64[n4]  per unit 1 / 2 / 4 entries of 16 bits: BYTE offset of the slot in the
-//            E-vector; 0xffff = unused (a 3-slot unit in the 64-bit section)
-//   ovf[n_ovf]  (u << 16 | byte offset) for the slots beyond four (edge valence > 4 inside one patch,
-//            only on unstructured meshes); such units are classed shared, overflow is RED-added.
-//   lidx[nd][FE] 16 bits per element slot: Xs position u of the slot's unit (bits 0..12) | the slot
-//            code's flag bits 29..31 (bits 13..15); the element side PULLS its inputs through this table.
+// Ownership instead of a zero-filling pass: a unit touched by several patches is OWNED by the lowest-numbered of them.
+// The CTA that will process the owner ZEROES it a batch of pipeline iterations ahead (own_off / own_idx: the owned
+// shared units of every patch) and the kernel keeps a split-phase watermark over these batches; every patch touching
+// the unit RED-adds its sum once the watermark has passed (patch_pipeline.h) -- so y never has to be cleared before an
+// apply and the zeros are still in L2 when the adds arrive.
+// The units of a patch are ordered private first (plain stores), shared second (REDs), each group by slot count.
+//
+// Blob layout in 32-bit words: three PARTS by lifetime in the kernel's pipeline, each starting on a 16-byte boundary,
+// located by blob_off[k] (16-byte units) and part_off[2k], part_off[2k+1]:
+//  part D  [blob_off[k], part_off[2k])      header (HDR = 32 words) + unit words; double-buffered by the kernels
+//  part L  [part_off[2k], part_off[2k+1])   slot-offset lists, overflow list, dependency list (needed while summing)
+//  part T  [part_off[2k+1], blob_off[k+1])  per-slot table (needed while the element side pulls / writes results)
+// Header:
+//   [0] U  number of patch units   [1] number of real (non-padding) elements   [2] n_ovf   [3] 0
+//   [4..6]  n1a n2a n4a  private units (stored), with 1 / 2 / 3..4 element slots
+//   [7..9]  n1b n2b n4b  shared units (RED-added); those with PATCH_OWNED are zeroed ahead by this patch's CTA
+//   [10..15] word offsets, relative to the start of part L, of the lists e16a e32a e64a e16b e32b e64b
+//   [16] offset of ovf (part L)   [17] 0   [18] words of part D   [19] words of part L
+//   [20] 1 when a unit of the patch carries an essential flag (set together with the flags, hex_patch.cu)   [21..31] 0
+// Part D:  dof[U]  global unit index (bits 0..27) | PATCH_OWNED (bit 28) | PATCH_SHARED (bit 31) when other patches also
+//          touch the unit; bits 29, 30 are the essential flags the operator ORs in (hex_patch.cu).  Order: the six
+//          classes above.
+// Part L:  e16[n1], e32[n2], e64[n4] per class: per unit 1 / 2 / 4 entries of 16 bits: BYTE offset of the slot in the
+//          E-vector; 0xffff = unused (a 3-slot unit in a 64-bit section)
+//          ovf[n_ovf]  (u << 16 | byte offset) for the slots beyond four (edge valence > 4 inside one patch, only on
+//          unstructured meshes); such units are classed shared (zeroed ahead, every slot sum RED-added).
+// Part T:  lidx[nd][FE] 16 bits per element slot: Xs position u of the slot's unit (bits 0..12) | the slot
+//          code's flag bits 29..31 (bits 13..15); the element side PULLS its inputs through this table.
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -90,7 +104,7 @@ int build_patches(int nd, int64_t n_elem, int FE, int stride, int unit_bytes, in
   if (stride < FE) { set_error("slot stride must be >= elements per patch"); return 1; }
   if (unit_bytes != 8 && unit_bytes != 16) { set_error("unit size must be 8 or 16 bytes"); return 1; }
   if ((int64_t)stride * nd * unit_bytes > 65534 || (int64_t)FE * nd > 8191) { set_error("patch too large for the 16-bit slot encoding"); return 1; }
-  if (n_ext > (int64_t)PATCH_IDX + 1) { set_error("too many units for the patch dof words"); return 1; }
+  if (n_ext > (int64_t)PATCH_IDX + 1) { set_error("too many units for the patch unit words"); return 1; }
   const int64_t n_patch = (n_elem + FE - 1) / FE;
   out.FE = FE; out.stride = stride; out.nd = nd; out.n_patch = n_patch;
   // ---- Morton order of the centroids
@@ -130,7 +144,7 @@ int build_patches(int nd, int64_t n_elem, int FE, int stride, int unit_bytes, in
         const int32_t e = out.perm[(size_t)k * FE + j];
         if (e < 0) continue;
         for (int s = 0; s < nd; s++)
-          if (exchange_units[slot_code[(size_t)e * nd + s] & PATCH_IDX]) { bdr[(size_t)k] = 1; break; }
+          if (exchange_units[slot_code[(size_t)e * nd + s] & SLOT_IDX]) { bdr[(size_t)k] = 1; break; }
       }
     });
     std::vector<int32_t> perm2((size_t)n_patch * FE, -1);
@@ -161,7 +175,7 @@ int build_patches(int nd, int64_t n_elem, int FE, int stride, int unit_bytes, in
       for (int s = 0; s < nd; s++) {
         const uint32_t code = slot_code[(size_t)e * nd + s];
         const uint16_t sl = (uint16_t)((s * stride + j) * unit_bytes);
-        ent.push_back({code & PATCH_IDX, sl, (uint16_t)((uint32_t)(s * FE + j) | ((code >> 29) << 13))});
+        ent.push_back({code & SLOT_IDX, sl, (uint16_t)((uint32_t)(s * FE + j) | ((code >> 29) << 13))});
       }
     }
     std::sort(ent.begin(), ent.end(), [](const Ent &a, const Ent &b) { return a.dof < b.dof || (a.dof == b.dof && a.slot < b.slot); });
@@ -175,8 +189,7 @@ int build_patches(int nd, int64_t n_elem, int FE, int stride, int unit_bytes, in
     }
     us.push_back((uint16_t)ent.size());
   });
-  // ---- which dofs are private to one patch; dofs with more than four slots in a patch are
-  // treated as shared everywhere (their overflow slots are RED-added separately)
+  // ---- owner of every unit = the lowest-numbered patch touching it; multi = touched by more than one patch
   std::vector<int32_t> owner((size_t)n_ext, -1);
   std::vector<uint8_t> multi((size_t)n_ext, 0);
   for (int64_t k = 0; k < n_patch; k++) {
@@ -186,119 +199,130 @@ int build_patches(int nd, int64_t n_elem, int FE, int stride, int unit_bytes, in
       const uint32_t d = ud[i];
       if (owner[d] < 0) owner[d] = (int32_t)k;
       else if (owner[d] != (int32_t)k) multi[d] = 1;
-      if (us[i + 1] - us[i] > 4) multi[d] = 1;
+      if (us[i + 1] - us[i] > 4) multi[d] = 1;  // overflow slots are RED-added: the unit must be pre-filled
     }
   }
-  owner.clear(); owner.shrink_to_fit();
-  // 128-byte lines of the vector that hold at least one shared unit (ascending)
-  out.shared_lines.clear();
-  {
-    const int64_t per_line = 128 / unit_bytes;
-    for (int64_t l = 0; l * per_line < n_ext; l++) {
-      bool any = false;
-      for (int64_t d = l * per_line; d < std::min(n_ext, (l + 1) * per_line); d++) any |= multi[(size_t)d] != 0;
-      if (any) out.shared_lines.push_back((uint32_t)l);
-    }
-  }
-  // ---- emit one blob per patch
+  // class of unit i of patch k: (shared ? 3 : 0) + width
   auto width_of = [](int nslot) { return nslot <= 1 ? 0 : (nslot == 2 ? 1 : 2); };
+  auto class_of = [&](int64_t k, size_t i) {
+    const auto &us = ustart[(size_t)k];
+    return (multi[udof[(size_t)k][i]] ? 3 : 0) + width_of(us[i + 1] - us[i]);
+  };
   auto align4 = [](uint32_t w) { return (w + 3u) & ~3u; };  // words -> 16-byte boundary
+  constexpr uint32_t HDR = PatchHost::HDR;
   const uint32_t lidx_words = align4((uint32_t)(per + 1) / 2);
+  // the owned shared units of every patch, ascending (zeroed ahead of the sums by the CTA that processes the patch)
+  out.own_off.assign((size_t)n_patch + 1, 0);
+  for (int64_t k = 0; k < n_patch; k++) {
+    uint32_t n = 0;
+    for (uint32_t d : udof[(size_t)k]) n += multi[d] && owner[d] == (int32_t)k;
+    out.own_off[(size_t)k + 1] = out.own_off[(size_t)k] + n;
+  }
+  out.own_idx.assign((size_t)out.own_off[(size_t)n_patch], 0);
+  parallel_for(n_patch, [&](int64_t k) {
+    uint32_t *o = out.own_idx.data() + out.own_off[(size_t)k];
+    for (uint32_t d : udof[(size_t)k]) if (multi[d] && owner[d] == (int32_t)k) *o++ = d;
+  });
   out.blob_off.assign((size_t)n_patch + 1, 0);
   out.max_blob_words = 0;
   out.max_dofs = 0;
   out.max_d_words = out.max_l_words = 0;
+  out.max_t_words = lidx_words;
   out.part_off.assign((size_t)n_patch * 2, 0);
-  for (int64_t k = 0; k < n_patch; k++) {
+  struct Sizes { uint32_t n[6], nov, wd, wl; };
+  auto sizes_of = [&](int64_t k) {
     const auto &ud = udof[(size_t)k];
     const auto &us = ustart[(size_t)k];
-    uint32_t n[3] = {0, 0, 0}, nov = 0;
+    Sizes z = {{0, 0, 0, 0, 0, 0}, 0, 0, 0};
     for (size_t i = 0; i < ud.size(); i++) {
-      const int ns = us[i + 1] - us[i];
-      n[width_of(ns)]++;
-      if (ns > 4) nov += ns - 4;
+      z.n[class_of(k, i)]++;
+      if (us[i + 1] - us[i] > 4) z.nov += us[i + 1] - us[i] - 4;
     }
-    const uint32_t w = PatchHost::HDR + align4((uint32_t)ud.size()) + align4((n[0] + 1) / 2) + align4(n[1]) + align4(2 * n[2]) +
-                       align4(nov) + lidx_words;
+    z.wd = HDR + align4((uint32_t)ud.size());
+    z.wl = 0;
+    for (int ph = 0; ph < 2; ph++) z.wl += align4((z.n[3 * ph] + 1) / 2) + align4(z.n[3 * ph + 1]) + align4(2 * z.n[3 * ph + 2]);
+    z.wl += align4(z.nov);
+    return z;
+  };
+  for (int64_t k = 0; k < n_patch; k++) {
+    const Sizes z = sizes_of(k);
+    const uint32_t w = z.wd + z.wl + lidx_words;
     out.blob_off[(size_t)k + 1] = out.blob_off[(size_t)k] + w / 4;
-    // parts by lifetime: [header + unit list | slot-offset lists | per-slot table]
-    const uint32_t wd = PatchHost::HDR + align4((uint32_t)ud.size()), wl = w - wd - lidx_words;
-    out.part_off[(size_t)k * 2] = out.blob_off[(size_t)k] + wd / 4;
-    out.part_off[(size_t)k * 2 + 1] = out.blob_off[(size_t)k] + (wd + wl) / 4;
-    out.max_d_words = std::max(out.max_d_words, wd);
-    out.max_l_words = std::max(out.max_l_words, wl);
+    out.part_off[(size_t)k * 2] = out.blob_off[(size_t)k] + z.wd / 4;
+    out.part_off[(size_t)k * 2 + 1] = out.blob_off[(size_t)k] + (z.wd + z.wl) / 4;
+    out.max_d_words = std::max(out.max_d_words, z.wd);
+    out.max_l_words = std::max(out.max_l_words, z.wl);
     out.max_blob_words = std::max(out.max_blob_words, w);
-    out.max_dofs = std::max(out.max_dofs, (uint32_t)ud.size());
+    out.max_dofs = std::max(out.max_dofs, (uint32_t)udof[(size_t)k].size());
   }
-  // position -> index into ud, for patch k (n1 / n2: sizes of the 1- and 2-slot classes)
-  auto make_order = [&](int64_t k, uint32_t n1, uint32_t n2, std::vector<uint32_t> &order) {
+  // position -> index into ud, for patch k: the six classes in order, each in ascending global index (consecutive lanes
+  // gather / store consecutive addresses) up to a bank-spreading permutation: the position of a unit is also its place in
+  // the staging vector Xs, so its shared-memory bank on the element side (the pull through lidx) is position mod NB, NB =
+  // 128 / unit_bytes lanes being served per wavefront.  Sorted order makes the pull 4.4-way bank conflicted on structured
+  // meshes (strided dof numbering), so inside every aligned run of NB positions the units are PERMUTED to spread, for each
+  // (slot, NB consecutive elements) access group, the units it reads over distinct banks.  A warp of the dof side still
+  // touches the same 32 units, i.e. the same global sectors.
+  auto make_order = [&](int64_t k, std::vector<uint32_t> &order, uint32_t *cls_end) {
     const auto &ud = udof[(size_t)k];
     const auto &us = ustart[(size_t)k];
     const auto &sj = usj[(size_t)k];
-    const uint32_t U = (uint32_t)ud.size();
     order.clear();
-    order.reserve(U);
-    for (int w = 0; w < 3; w++)
+    order.reserve(ud.size());
+    for (int w = 0; w < 6; w++) {
       for (size_t i = 0; i < ud.size(); i++)
-        if (width_of(us[i + 1] - us[i]) == w) order.push_back((uint32_t)i);
-    {
-      const int NB = 128 / unit_bytes, HG = (FE + NB - 1) / NB;
-      std::vector<uint8_t> cnt((size_t)nd * HG * 16, 0);
-      auto groups_of = [&](uint32_t i, int *g) {  // distinct access groups reading dof i
-        int n = 0;
-        for (int q = us[i]; q < us[i + 1] && n < 8; q++) {
-          const int v = sj[q] & 0x1fff, gid = (v / FE) * HG + (v % FE) / NB;
-          bool dup = false;
-          for (int t = 0; t < n; t++) dup |= g[t] == gid;
-          if (!dup) g[n++] = gid;
-        }
-        return n;
-      };
-      auto add = [&](uint32_t i, int bank, int v) {
-        int g[8];
-        const int n = groups_of(i, g);
-        for (int t = 0; t < n; t++) cnt[(size_t)g[t] * 16 + bank] = (uint8_t)(cnt[(size_t)g[t] * 16 + bank] + v);
-      };
-      const uint32_t cls_end[3] = {n1, n1 + n2, U};
-      for (int pass = 0; pass < 2; pass++) {
-        uint32_t p0 = 0;
-        for (int w = 0; w < 3; w++)
-          while (p0 < cls_end[w]) {
-            const uint32_t p1 = std::min(cls_end[w], (p0 / NB + 1) * NB);
-            const int m = (int)(p1 - p0);
-            uint32_t ds[16];
-            for (int t = 0; t < m; t++) ds[t] = order[p0 + t];
-            if (pass > 0) for (int t = 0; t < m; t++) add(ds[t], (int)((p0 + t) % NB), -1);
-            bool used[16] = {false};
-            // dofs read by more groups first
-            std::stable_sort(ds, ds + m, [&](uint32_t a, uint32_t b) { return us[a + 1] - us[a] > us[b + 1] - us[b]; });
-            for (int t = 0; t < m; t++) {
-              int g[8];
-              const int n = groups_of(ds[t], g);
-              int best = -1, best_cost = 1 << 30;
-              for (int q = 0; q < m; q++) {
-                if (used[q]) continue;
-                const int bank = (int)((p0 + q) % NB);
-                int c = 0;
-                for (int r = 0; r < n; r++) c += 2 * cnt[(size_t)g[r] * 16 + bank] + 1;
-                if (c < best_cost) { best_cost = c; best = q; }
-              }
-              used[best] = true;
-              order[p0 + best] = ds[t];
-              add(ds[t], (int)((p0 + best) % NB), +1);
-            }
-            p0 = p1;
-          }
+        if (class_of(k, i) == w) order.push_back((uint32_t)i);
+      cls_end[w] = (uint32_t)order.size();
+    }
+    const int NB = 128 / unit_bytes, HG = (FE + NB - 1) / NB;
+    std::vector<uint8_t> cnt((size_t)nd * HG * 16, 0);
+    auto groups_of = [&](uint32_t i, int *g) {  // distinct access groups reading dof i
+      int n = 0;
+      for (int q = us[i]; q < us[i + 1] && n < 8; q++) {
+        const int v = sj[q] & 0x1fff, gid = (v / FE) * HG + (v % FE) / NB;
+        bool dup = false;
+        for (int t = 0; t < n; t++) dup |= g[t] == gid;
+        if (!dup) g[n++] = gid;
       }
+      return n;
+    };
+    auto add = [&](uint32_t i, int bank, int v) {
+      int g[8];
+      const int n = groups_of(i, g);
+      for (int t = 0; t < n; t++) cnt[(size_t)g[t] * 16 + bank] = (uint8_t)(cnt[(size_t)g[t] * 16 + bank] + v);
+    };
+    for (int pass = 0; pass < 2; pass++) {
+      uint32_t p0 = 0;
+      for (int w = 0; w < 6; w++)
+        while (p0 < cls_end[w]) {
+          const uint32_t p1 = std::min(cls_end[w], (p0 / NB + 1) * NB);
+          const int m = (int)(p1 - p0);
+          uint32_t ds[16];
+          for (int t = 0; t < m; t++) ds[t] = order[p0 + t];
+          if (pass > 0) for (int t = 0; t < m; t++) add(ds[t], (int)((p0 + t) % NB), -1);
+          bool used[16] = {false};
+          // dofs read by more groups first
+          std::stable_sort(ds, ds + m, [&](uint32_t a, uint32_t b) { return us[a + 1] - us[a] > us[b + 1] - us[b]; });
+          for (int t = 0; t < m; t++) {
+            int g[8];
+            const int n = groups_of(ds[t], g);
+            int best = -1, best_cost = 1 << 30;
+            for (int q = 0; q < m; q++) {
+              if (used[q]) continue;
+              const int bank = (int)((p0 + q) % NB);
+              int c = 0;
+              for (int r = 0; r < n; r++) c += 2 * cnt[(size_t)g[r] * 16 + bank] + 1;
+              if (c < best_cost) { best_cost = c; best = q; }
+            }
+            used[best] = true;
+            order[p0 + best] = ds[t];
+            add(ds[t], (int)((p0 + best) % NB), +1);
+          }
+          p0 = p1;
+        }
     }
   };
-  auto class_sizes = [&](int64_t k, uint32_t *n) {
-    const auto &us = ustart[(size_t)k];
-    n[0] = n[1] = n[2] = 0;
-    for (size_t i = 0; i + 1 < us.size(); i++) n[width_of(us[i + 1] - us[i])]++;
-  };
   // ---- swizzle of the E-vector positions (see PatchHost::swz_row): coordinate descent on the bank conflicts of the
-  // dof side's slot reads -- lanes = NB consecutive units of a width class, one read per slot rank -- over a sample
+  // dof side's slot reads -- lanes = NB consecutive units of a class, one read per slot rank -- over a sample
   // of patches.  Structured meshes number dofs in strides that make neighbouring units hit the same bank (2.8
   // wavefronts per read measured); one global swizzle removes about half of the excess.
   {
@@ -313,15 +337,13 @@ int build_patches(int nd, int64_t n_elem, int FE, int stride, int unit_bytes, in
       const int64_t k = q * n_patch / n_sample;
       const auto &us = ustart[(size_t)k];
       const auto &sj = usj[(size_t)k];
-      uint32_t n[3];
-      class_sizes(k, n);
-      make_order(k, n[0], n[1], order);
-      const uint32_t base[4] = {0, n[0], n[0] + n[1], n[0] + n[1] + n[2]};
-      for (int w = 0; w < 3; w++)
-        for (uint32_t p0 = base[w]; p0 < base[w + 1]; p0 += NB)
-          for (int kk = 0; kk < (w == 0 ? 1 : (w == 1 ? 2 : 4)); kk++) {
+      uint32_t cls_end[6];
+      make_order(k, order, cls_end);
+      for (int w = 0; w < 6; w++)
+        for (uint32_t p0 = w ? cls_end[w - 1] : 0; p0 < cls_end[w]; p0 += NB)
+          for (int kk = 0; kk < (w % 3 == 0 ? 1 : (w % 3 == 1 ? 2 : 4)); kk++) {
             std::vector<Acc> acc;
-            for (uint32_t ul = p0; ul < std::min(base[w + 1], p0 + NB); ul++) {
+            for (uint32_t ul = p0; ul < std::min(cls_end[w], p0 + NB); ul++) {
               const uint32_t i = order[ul];
               if (us[i] + kk < us[i + 1]) { const int v = sj[us[i] + kk] & 0x1fff; acc.push_back({(uint16_t)(v / FE), (uint16_t)(v % FE)}); }
             }
@@ -359,57 +381,46 @@ int build_patches(int nd, int64_t n_elem, int FE, int stride, int unit_bytes, in
     const auto &us = ustart[(size_t)k];
     const auto &sj = usj[(size_t)k];
     uint32_t *B = out.blob.data() + (size_t)out.blob_off[(size_t)k] * 4;
-    // group sizes: [width][private|shared]
-    uint32_t cnt[3][2] = {{0, 0}, {0, 0}, {0, 0}}, nov = 0;
-    for (size_t i = 0; i < ud.size(); i++) {
-      const int ns = us[i + 1] - us[i];
-      cnt[width_of(ns)][multi[ud[i]] ? 1 : 0]++;
-      if (ns > 4) nov += ns - 4;
+    const Sizes z = sizes_of(k);
+    const uint32_t U = (uint32_t)ud.size();
+    uint32_t oL[6], o = 0;  // list offsets relative to part L
+    for (int w = 0; w < 6; w++) {
+      oL[w] = o;
+      o += w % 3 == 0 ? align4((z.n[w] + 1) / 2) : (w % 3 == 1 ? align4(z.n[w]) : align4(2 * z.n[w]));
     }
-    const uint32_t U = (uint32_t)ud.size(), n1 = cnt[0][0] + cnt[0][1], n2 = cnt[1][0] + cnt[1][1], n4 = cnt[2][0] + cnt[2][1];
-    const uint32_t o16 = PatchHost::HDR + align4(U), o32 = o16 + align4((n1 + 1) / 2), o64 = o32 + align4(n2), oov = o64 + align4(2 * n4);
-    const uint32_t olx = oov + align4(nov);
+    const uint32_t oov = o;
     uint32_t n_real = 0;
     for (int j = 0; j < FE; j++) n_real += out.perm[(size_t)k * FE + j] >= 0;
-    B[0] = U; B[1] = n1; B[2] = n2; B[3] = n4; B[4] = cnt[0][0]; B[5] = cnt[1][0]; B[6] = cnt[2][0]; B[7] = nov;
-    B[8] = o16; B[9] = o32; B[10] = o64; B[11] = oov; B[12] = olx; B[13] = n_real;
-    uint32_t *pd = B + PatchHost::HDR;
-    uint16_t *p16 = (uint16_t *)(B + o16);
-    uint32_t *p32 = B + o32;
-    uint64_t *p64 = (uint64_t *)(B + o64);
-    uint32_t *po = B + oov;
-    uint16_t *plx = (uint16_t *)(B + olx);
-    // order inside each width class: ascending global index (consecutive lanes gather / store
-    // consecutive addresses); private and shared units are told apart by the PATCH_SHARED bit of the
-    // dof word.  The position of a unit in this order is also its place in the staging vector Xs, so
-    // its shared-memory bank on the element side (the pull through lidx) is position mod NB, NB =
-    // 128 / unit_bytes lanes being served per wavefront.  Sorted order makes the pull 4.4-way bank
-    // conflicted on structured meshes (strided dof numbering), so inside every aligned run of NB
-    // positions the units are PERMUTED to spread, for each (slot, NB consecutive elements) access
-    // group, the units it reads over distinct banks.  A warp of the dof side still touches the same
-    // 32 units, i.e. the same global sectors.
+    B[0] = U; B[1] = n_real; B[2] = z.nov;
+    for (int w = 0; w < 6; w++) { B[4 + w] = z.n[w]; B[10 + w] = oL[w]; }
+    B[16] = oov; B[18] = z.wd; B[19] = z.wl;
+    uint32_t *pd = B + HDR;
+    uint32_t *Lp = B + z.wd;
+    uint32_t *po = Lp + oov;
+    uint16_t *plx = (uint16_t *)(Lp + z.wl);
     std::vector<uint32_t> order;  // position -> index into ud
-    make_order(k, n1, n2, order);
-    const uint32_t base[3] = {0, n1, n1 + n2};
+    uint32_t cls_end[6];
+    make_order(k, order, cls_end);
     for (uint32_t ul = 0; ul < U; ul++) {
       const uint32_t i = order[ul];
-      const int ns = us[i + 1] - us[i], w = width_of(ns);
-      const uint32_t r = ul - base[w];  // index inside the width section
-      pd[ul] = ud[i] | (multi[ud[i]] ? PATCH_SHARED : 0u);
+      const int ns = us[i + 1] - us[i], w = class_of(k, i);
+      const uint32_t r = ul - (w ? cls_end[w - 1] : 0);  // index inside the class
+      pd[ul] = ud[i] | (multi[ud[i]] ? PATCH_SHARED | (owner[ud[i]] == (int32_t)k ? PATCH_OWNED : 0u) : 0u);
       for (int j = 0; j < ns; j++) plx[sj[us[i] + j] & 0x1fffu] = (uint16_t)(ul | (sj[us[i] + j] & 0xe000u));
       auto off = [&](int q) {  // byte offset of the slot in the (swizzled) E-vector
         const int v = sj[q] & 0x1fff, ss = v / FE, jj = v % FE;
         return (uint32_t)((ss * stride + (jj ^ out.swz_row[(size_t)ss] ^ out.swz_grp[(size_t)(jj / (128 / unit_bytes))])) * unit_bytes);
       };
-      if (w == 0) p16[r] = (uint16_t)off(us[i]);
-      else if (w == 1) p32[r] = off(us[i]) | (off(us[i] + 1) << 16);
+      if (w % 3 == 0) ((uint16_t *)(Lp + oL[w]))[r] = (uint16_t)off(us[i]);
+      else if (w % 3 == 1) (Lp + oL[w])[r] = off(us[i]) | (off(us[i] + 1) << 16);
       else {
         uint64_t v = ~0ULL;
         for (int j = 0; j < ns; j++) {
           if (j < 4) v = (v & ~(0xffffULL << (16 * j))) | ((uint64_t)off(us[i] + j) << (16 * j));
           else *po++ = (ul << 16) | off(us[i] + j);
         }
-        p64[r] = v;
+        (Lp + oL[w])[2 * r] = (uint32_t)v;
+        (Lp + oL[w])[2 * r + 1] = (uint32_t)(v >> 32);
       }
     }
   });
@@ -484,7 +495,7 @@ hcurl_host_patches *hcurl_host_patches_create(int nd, int64_t n_elem, int elems_
                                               const uint8_t *exchange_units) {
   if (nd <= 0 || n_elem <= 0 || !centroid || !slot_code) { hcurl::set_error("hcurl_host_patches_create: bad arguments"); return nullptr; }
   for (int64_t i = 0; i < n_elem * nd; i++)
-    if ((int64_t)(slot_code[i] & hcurl::PATCH_IDX) >= n_dof) { hcurl::set_error("hcurl_host_patches_create: dof index out of range"); return nullptr; }
+    if ((int64_t)(slot_code[i] & hcurl::SLOT_IDX) >= n_dof) { hcurl::set_error("hcurl_host_patches_create: dof index out of range"); return nullptr; }
   hcurl_host_patches *p = new hcurl_host_patches;
   if (hcurl::build_patches(nd, n_elem, elems_per_patch, slot_stride, unit_bytes, n_dof, centroid, slot_code, exchange_units, p->h)) { delete p; return nullptr; }
   return p;
@@ -513,14 +524,23 @@ int hcurl_host_patches_swizzle(const hcurl_host_patches *p, uint8_t *row, uint8_
   memcpy(grp, p->h.swz_grp.data(), p->h.swz_grp.size());
   return 0;
 }
-/* the blob of patch k by lifetime (split-blob kernel variant): part_off [2*n_patch] = begin of the slot-offset lists and
- * of the per-slot table in 16-byte units; largest header + unit list / largest set of lists in 32-bit words */
-int hcurl_host_patches_parts(const hcurl_host_patches *p, uint32_t *part_off, int64_t *max_d_words, int64_t *max_l_words) {
+/* the blob of patch k by lifetime: part_off [2*n_patch] = begin of the lists and of the per-slot table in 16-byte
+ * units; largest header + unit list / set of lists / table in 32-bit words */
+int hcurl_host_patches_parts(const hcurl_host_patches *p, uint32_t *part_off, int64_t *max_d_words, int64_t *max_l_words, int64_t *max_t_words) {
   const hcurl::PatchHost &h = p->h;
   if (part_off) memcpy(part_off, h.part_off.data(), sizeof(uint32_t) * h.part_off.size());
   if (max_d_words) *max_d_words = h.max_d_words;
   if (max_l_words) *max_l_words = h.max_l_words;
+  if (max_t_words) *max_t_words = h.max_t_words;
   return 0;
+}
+/* the shared units every patch owns (it is the lowest-numbered patch touching them): own_off [n_patch+1], own_idx
+ * [own_off[n_patch]]; a null own_idx only returns the offsets */
+int64_t hcurl_host_patches_owned(const hcurl_host_patches *p, uint32_t *own_off, uint32_t *own_idx) {
+  const hcurl::PatchHost &h = p->h;
+  if (own_off) memcpy(own_off, h.own_off.data(), sizeof(uint32_t) * h.own_off.size());
+  if (own_idx) memcpy(own_idx, h.own_idx.data(), sizeof(uint32_t) * h.own_idx.size());
+  return (int64_t)h.own_idx.size();
 }
 int hcurl_host_patches_copy(const hcurl_host_patches *p, int32_t *perm, uint32_t *blob_off, uint32_t *blob) {
   const hcurl::PatchHost &h = p->h;

@@ -281,12 +281,12 @@ int hcurl_dot(hcurl_ctx *ctx, const double *a_dev, const double *b_dev, int64_t 
  *  slot_stride  >= elems_per_patch: E-vector index (in units) of (slot s, patch position j) = s*slot_stride + j',
  *             j' = j up to the bank swizzle reported by hcurl_host_patches_swizzle()
  *  exchange_units  NULL, or one flag per unit: patches touching a flagged unit (ghosts, units other ranks hold as
- *             ghosts) are placed first -- hcurl_host_patches_boundary_count() of them -- so that an apply can overlap the
- *             inter-rank exchange with the remaining patches
+ *             ghosts) are placed first -- hcurl_host_patches_boundary_count() of them
  *  outputs    perm [n_patch*epp] element at each patch position (-1 padding);
  *             blob_off [n_patch+1] start of each patch blob in 16-byte units; blob: per patch a
- *             16-word header, the unit list, the 16/32/64-bit slot-entry sections (dof side) and the
- *             per-slot local unit index table (element side); layout in hephaestus_b200/csrc/patch.cpp. */
+ *             32-word header + the unit list (units the patch owns and stores first, units it adds to second), the
+ *             16/32/64-bit slot-entry lists + overflow list (dof side) and the per-slot local unit
+ *             index table (element side); layout in hephaestus_b200/csrc/patch.cpp. */
 /* Order-2 hex spaces: the 27 dof pairs of every element (the 16-byte units of the patch kernel): codes[e][r] = pair
  * index q (doubles 2q, 2q+1 of the vector) | bit 29 swap | bit 30 sign flip of the second local dof | bit 31 sign
  * flip of the first.  elem_ldof [n_elem][54] as for hcurl_space_create.  Returns 0, or 1 when the map does not
@@ -311,13 +311,17 @@ int64_t hcurl_host_patches_max_dofs(const hcurl_host_patches *p);
 /* E-vector swizzle chosen by the builder: (slot s, position j) sits at unit s*slot_stride + (j ^ row[s] ^ grp[j / NB]),
  * NB = 128 / unit_bytes; row has nd entries, grp ceil(elems_per_patch / NB) */
 int hcurl_host_patches_swizzle(const hcurl_host_patches *p, uint8_t *row, uint8_t *grp);
-/* split-blob kernel variant: begin of the slot-offset lists and of the per-slot table of every patch blob
- * (part_off [2*n_patch], 16-byte units) and the largest first two parts in 32-bit words */
-int hcurl_host_patches_parts(const hcurl_host_patches *p, uint32_t *part_off, int64_t *max_d_words, int64_t *max_l_words);
+/* the three parts of every patch blob by lifetime in the kernel's pipeline: begin of the lists and of the per-slot
+ * table (part_off [2*n_patch], 16-byte units) and the largest parts in 32-bit words */
+int hcurl_host_patches_parts(const hcurl_host_patches *p, uint32_t *part_off, int64_t *max_d_words, int64_t *max_l_words,
+                             int64_t *max_t_words);
 /* the 1-D transform tables of the order-2 modal element operator (a0, a1, b, c0, c1, d1, d2), for the host-side check
  * of the kernel program (tests/test_patch_p2_emu.py) */
 int hcurl_host_modal_tables_p2(double *out7);
 int hcurl_host_patches_copy(const hcurl_host_patches *p, int32_t *perm, uint32_t *blob_off, uint32_t *blob);
+/* the shared units every patch owns (the lowest-numbered patch touching a unit owns it; the kernel zeroes them ahead of
+ * the sums instead of clearing y): own_off [n_patch+1], own_idx [returned count]; null pointers are skipped */
+int64_t hcurl_host_patches_owned(const hcurl_host_patches *p, uint32_t *own_off, uint32_t *own_idx);
 
 /* ---- host-side setup helper: ND space on a hex or tet mesh (no GPU needed) ------------------
  * What mfem::ParFiniteElementSpace hands the assembly once ProblemBuilder::AddFESpace("ND_3D_P<p>") has run

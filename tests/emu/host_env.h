@@ -1,8 +1,9 @@
-// Host execution environment for kernel programs written against an `Env` (hephaestus_b200/csrc/hex_patch_p1_body.h,
-// hex_patch_p2_body.h) -- TEST INFRASTRUCTURE, not part of the product library.  One std::thread per CUDA thread of a
+// Host execution environment for kernel programs written against an `Env` (hephaestus_b200/csrc/patch_pipeline.h,
+// interp_body.h) -- TEST INFRASTRUCTURE, not part of the product library.  One std::thread per CUDA thread of a
 // CTA, std::barrier for __syncthreads, memcpy for TMA bulk copies and cp.async gathers, compare-and-swap for
-// red.global.add.f64, a per-warp barrier for __all_sync.  CTAs run one after the other; each walks patches
-// block, += nblocks like the persistent kernels.
+// red.global.add.f64, release / acquire atomics for the arrival counters, a per-warp barrier for __all_sync.  All CTAs of
+// the grid run CONCURRENTLY (the patch pipeline waits on flags of other CTAs, like the cooperative launch on the
+// device); each walks patches block, += nblocks like the persistent kernels.
 //
 // Deliberately pessimistic where the hardware is asynchronous: the destination of an asynchronous copy is poisoned when
 // the copy is issued (it may land at once) and filled at its WAIT (bulk_wait / gather_wait: it may land that late), so a
@@ -124,6 +125,9 @@ struct HostEnv {
     W.bar.arrive_and_wait();
     return W.xch[n][(tid_ & 31) ^ lane_mask];
   }
+  void arrive(uint32_t *p) { std::atomic_ref<uint32_t>(*p).fetch_add(1u, std::memory_order_release); }
+  uint32_t counter_acquire(const uint32_t *p) { return std::atomic_ref<uint32_t>(*const_cast<uint32_t *>(p)).load(std::memory_order_acquire); }
+  void backoff(unsigned) { std::this_thread::yield(); }
   uint32_t ldg(const uint32_t *p) const { return *p; }
   double ldg(const double *p) const { return *p; }
   double2 ldg(const double2 *p) const { return *p; }
@@ -138,25 +142,27 @@ struct HostEnv {
   }
 };
 
-// run `grid` CTAs of `nt` threads one after the other; body(env) is the per-thread program
+// run `grid` CTAs of `nt` threads, all at the same time; body(env) is the per-thread program
 template <class Body>
 int run_grid(int64_t grid, int nt, size_t smem_bytes, const void *tables, double *dot_total, Body body) {
+  std::vector<std::unique_ptr<CtaShared>> ctas;
+  for (int64_t blk = 0; blk < grid; blk++) ctas.emplace_back(new CtaShared(smem_bytes, nt));
+  std::vector<int> err((size_t)(grid * nt), 0);
+  std::vector<std::thread> th;
+  for (int64_t blk = 0; blk < grid; blk++)
+    for (int t = 0; t < nt; t++)
+      th.emplace_back([&, blk, t]() {
+        HostEnv env{ctas[(size_t)blk].get(), t, blk, grid, nt, &err[(size_t)(blk * nt + t)], tables, {}, 0, 0};
+        body(env);
+        if (!env.pend.empty()) err[(size_t)(blk * nt + t)] |= ERR_GATHER_LEFT;  // gathers never waited for
+      });
+  for (auto &t : th) t.join();
   int error = 0;
   double dot = 0.0;
-  for (int64_t blk = 0; blk < grid; blk++) {
-    CtaShared cta(smem_bytes, nt);
-    std::vector<int> err((size_t)nt, 0);
-    std::vector<std::thread> th;
-    for (int t = 0; t < nt; t++)
-      th.emplace_back([&, t]() {
-        HostEnv env{&cta, t, blk, grid, nt, &err[(size_t)t], tables, {}, 0, 0};
-        body(env);
-        if (!env.pend.empty()) err[(size_t)t] |= ERR_GATHER_LEFT;  // gathers never waited for
-      });
-    for (auto &t : th) t.join();
-    for (int e : err) error |= e;
-    for (int b = 0; b < MAX_BAR; b++) if (cta.bulk[b].armed) error |= ERR_BULK_LEFT;  // a requested copy was never consumed
-    dot += cta.dot_sum;
+  for (int e : err) error |= e;
+  for (auto &c : ctas) {
+    for (int b = 0; b < MAX_BAR; b++) if (c->bulk[b].armed) error |= ERR_BULK_LEFT;  // a requested copy was never consumed
+    dot += c->dot_sum;
   }
   if (dot_total) *dot_total = dot;
   return error;

@@ -212,9 +212,9 @@ def test_hex_p2_fast_paths_match_generic_and_oracle(ctx, perturb, n):
     assert rel_err(op.Mult(x), oa.constrained_apply(A2, essd, x)) < TOL
 
 
-@pytest.mark.parametrize("fe", [32, 64, 128])
+@pytest.mark.parametrize("fe", [32, 64])
 def test_hex_p2_patch_kernel_patch_sizes(ctx, fe, monkeypatch):
-    """Patch kernel with 32 / 64 / 128 elements per patch on a mesh with several patches,
+    """Patch kernel with 32 / 64 elements per patch on a mesh with several patches,
     a skewed (non axis-aligned) affine geometry and a device-resident repeat (determinism of the
     private-dof stores, RED only on patch-boundary dofs)."""
     monkeypatch.setenv("HCURL_PATCH_FE", str(fe))
@@ -277,46 +277,10 @@ def test_hex_p2_unstructured_affine_valence6(ctx, which, monkeypatch):
     assert op.LastKernel() == which
 
 
-@pytest.mark.skipif(os.environ.get("HCURL_TEST_SPLIT") != "1",
-                    reason="split-blob kernel variant: written after the round-1 GPU budget was spent; opt in with HCURL_TEST_SPLIT=1")
-@pytest.mark.parametrize("n", [(9, 8, 6), (5, 4, 3)])
-def test_hex_p2_patch_kernel_split_variant(ctx, n, monkeypatch):
-    """hex_patch_split_p2_kernel (blob split by lifetime, unpadded rows, 5 CTAs/SM): same parity bar as the default
-    patch kernel -- constrained apply, accumulate, arbitrary essential set, scrambled numbering (orientation flags)."""
-    monkeypatch.setenv("HCURL_PATCH_SPLIT", "1")
-    monkeypatch.setenv("HCURL_PATCH_FE", "32")
-    m, sp, mo, so = make_pair("hex", n, 2, False, scramble=True)
-    a, b = coefficients(m)
-    gsp = operators.GpuNDSpace(ctx, sp)
-    op = operators.HephGpuOperator(ctx, gsp, 3)
-    op.SetKernel(3)
-    op.SetCoefficients(a, b)
-    essd = sp.boundary_dofs(lambda c: c[:, 0] < 1e-9)
-    op.SetEssentialTrueDofs(essd)
-    x = np.random.default_rng(12345).standard_normal(sp.ndof)
-    A = oa.assemble(so, a, b, q_override=3)
-    assert rel_err(op.Mult(x), oa.constrained_apply(A, essd, x)) < TOL
-    assert op.LastKernel() == 3
-    y0 = np.random.default_rng(1).standard_normal(sp.ndof)
-    assert rel_err(op.MultUnconstrained(x, y0.copy(), scale=-0.5, accumulate=True), y0 - 0.5 * (A @ x)) < TOL
-    ess2 = np.sort(np.random.default_rng(11).choice(sp.ndof, sp.ndof // 5, replace=False)).astype(np.int32)
-    op.SetEssentialTrueDofs(ess2)
-    assert rel_err(op.Mult(x), oa.constrained_apply(A, ess2, x)) < TOL
-    dx, dy = ctx.alloc(sp.ndof).upload(x), ctx.alloc(sp.ndof)
-    for _ in range(3):
-        op.Mult(dx, dy)
-    ctx.synchronize()
-    assert rel_err(dy.download(), oa.constrained_apply(A, ess2, x)) < TOL
-
-
-@pytest.mark.skipif(os.environ.get("HCURL_TEST_PATCH_P1") != "1",
-                    reason="order-1 patch kernel: device environment written after the round-1 GPU budget was spent (the kernel program is "
-                           "checked on host threads, tests/test_patch_p1_emu.py); opt in with HCURL_TEST_PATCH_P1=1")
 @pytest.mark.parametrize("n,fe", [((9, 8, 6), 128), ((5, 4, 3), 32), ((12, 11, 7), 64), ((16, 16, 16), 256)])
 def test_hex_p1_patch_kernel(ctx, n, fe, monkeypatch):
-    """hex_patch_modal_p1_kernel (hex_patch_p1.cu): constrained apply, accumulate, arbitrary essential set, scrambled
+    """hex_patch_p1_kernel (patch_pipeline.h + hex_patch_p1_elem.h): constrained apply, accumulate, arbitrary essential set, scrambled
     numbering (sign flips), repeated device-resident applies -- same parity bar as the order-2 patch kernel."""
-    monkeypatch.setenv("HCURL_PATCH_P1", "1")
     monkeypatch.setenv("HCURL_PATCH_FE", str(fe))
     m, sp, mo, so = make_pair("hex", n, 1, False, scramble=True)
     a, b = coefficients(m)
@@ -340,47 +304,19 @@ def test_hex_p1_patch_kernel(ctx, n, fe, monkeypatch):
         op.Mult(dx, dy)
     ctx.synchronize()
     assert rel_err(dy.download(), oa.constrained_apply(A, ess2, x)) < TOL
-    # the generic sum-factorised kernel agrees (the path order 1 takes without the switch)
+    # the generic sum-factorised kernel agrees (the path non-affine order-1 meshes take)
     op.SetKernel(1)
     assert rel_err(op.Mult(x), oa.constrained_apply(A, ess2, x)) < TOL
     assert op.LastKernel() == 1
 
 
-@pytest.mark.skipif(os.environ.get("HCURL_TEST_PATCH_ENV") != "1",
-                    reason="order-2 patch kernel built from the Env program (hex_patch_p2e.cu): verified on host threads "
-                           "(tests/test_patch_p2_emu.py), not yet run on a GPU; opt in with HCURL_TEST_PATCH_ENV=1")
-@pytest.mark.parametrize("split", ["0", "1"])
-@pytest.mark.parametrize("n", [(9, 8, 6), (5, 4, 3)])
-def test_hex_p2_patch_kernel_env_program(ctx, n, split, monkeypatch):
-    """hex_patch_p2e_kernel (plain and split-blob): same parity bar as the default patch kernel."""
-    monkeypatch.setenv("HCURL_PATCH_ENV", "1")
-    monkeypatch.setenv("HCURL_PATCH_SPLIT", split)
-    monkeypatch.setenv("HCURL_PATCH_FE", "32")
-    _p2_patch_variant_parity(ctx, n)
-
-
-@pytest.mark.skipif(os.environ.get("HCURL_TEST_PATCH_HALF") != "1",
-                    reason="two-threads-per-component order-2 patch kernel (hex_patch_p2h_body.h): verified on host threads "
-                           "(tests/test_patch_p2_emu.py), not yet run on a GPU; opt in with HCURL_TEST_PATCH_HALF=1")
-@pytest.mark.parametrize("regs", ["1", "2"])
-@pytest.mark.parametrize("n", [(9, 8, 6), (5, 4, 3)])
-def test_hex_p2_patch_kernel_half_program(ctx, n, regs, monkeypatch):
-    """hex_patch_p2h_kernel at 96 (HCURL_PATCH_HALF=1) and 80 (=2) registers: same parity bar as the default patch kernel."""
-    monkeypatch.setenv("HCURL_PATCH_HALF", regs)
-    monkeypatch.setenv("HCURL_PATCH_SPLIT", "0")
-    monkeypatch.setenv("HCURL_PATCH_FE", "32")
-    _p2_patch_variant_parity(ctx, n)
-
-
 @pytest.mark.parametrize("general", ["0", "1"])
 @pytest.mark.parametrize("fe", ["32", "64"])
 @pytest.mark.parametrize("n", [(9, 8, 6), (5, 4, 3)])
-def test_hex_p2_patch_kernel_single_program(ctx, n, fe, general, monkeypatch):
-    """hex_patch_p2s_kernel (one thread per element, 32- / 64-element patches; reversed-line and general orientation
-    handling): same parity bar as the other patch kernels."""
-    monkeypatch.setenv("HCURL_PATCH_SINGLE", "1")
+def test_hex_p2_patch_kernel_variants(ctx, n, fe, general, monkeypatch):
+    """hex_patch_p2_kernel with 32- / 64-element patches, reversed-line and general orientation handling, on a scrambled
+    vertex numbering (reversed lines)."""
     monkeypatch.setenv("HCURL_PATCH_GENERAL", general)
-    monkeypatch.setenv("HCURL_PATCH_SPLIT", "0")
     monkeypatch.setenv("HCURL_PATCH_FE", fe)
     _p2_patch_variant_parity(ctx, n)
 
@@ -421,8 +357,6 @@ def _p2_patch_variant_parity(ctx, n):
     assert np.sqrt((r * r / Ac.diagonal()).sum() / (rhs * rhs / Ac.diagonal()).sum()) < 10 * s.tol
 
 
-@pytest.mark.skipif(os.environ.get("HCURL_TEST_QAUTO") != "1",
-                    reason="HCURL_QUAD_AUTO added after the round-1 GPU budget was spent; opt in with HCURL_TEST_QAUTO=1")
 def test_quad_auto_picks_the_exact_rule_on_affine_meshes(ctx):
     """HCURL_QUAD_AUTO (-1): p+1 rule (patch kernel) on parallelepiped meshes -- equal to MFEM's rules to round-off --
     and MFEM's rules (generic kernel) on a perturbed mesh."""
@@ -440,8 +374,6 @@ def test_quad_auto_picks_the_exact_rule_on_affine_meshes(ctx):
         assert op.LastKernel() == kernel
 
 
-@pytest.mark.skipif(os.environ.get("HCURL_TEST_SINGLE_TERM") != "1",
-                    reason="patch path for single-term operators enabled after the round-1 GPU budget was spent; opt in with HCURL_TEST_SINGLE_TERM=1")
 @pytest.mark.parametrize("which", ["curl", "mass"])
 def test_patch_kernel_single_term_operators(ctx, which):
     """statics (curl-curl only, statics_formulation.cpp:131-161) and mass solves (mass only,

@@ -36,9 +36,6 @@ def test_two_gpu_apply_and_pcg(tmp_path, lib_built, n, p, perturbed):
     assert all("OK" in o for o in outs), outs
 
 
-@pytest.mark.skipif(os.environ.get("HCURL_TEST_GENERAL_PART") != "1",
-                    reason="general (unstructured) partition added after the round-1 GPU budget was spent (CPU-emulated in "
-                           "tests/test_partition.py); opt in with HCURL_TEST_GENERAL_PART=1 on >= 2 GPUs")
 @pytest.mark.parametrize("name,p", [("team7", 1), ("cylinder_hex_q2", 2), ("beam_tet", 3)])
 def test_two_gpu_reference_meshes_general_partition(tmp_path, lib_built, name, p):
     """the reference's own meshes split across 2 GPUs by a host-supplied element partition (TEAM7 runs with mpirun -n 4 in

@@ -93,12 +93,9 @@ def test_pcg_reuse_after_coefficient_update(ctx):
         assert abs(s.num_iterations - it) <= 2 and rel_err(x, xo) < 1e-6
 
 
-@pytest.mark.skipif(__import__("os").environ.get("HCURL_TEST_PATCH_P1") != "1",
-                    reason="order-1 patch kernel not yet run on a GPU (see tests/test_gpu_apply.py); opt in with HCURL_TEST_PATCH_P1=1")
 def test_pcg_order1_patch_kernel_fused_dot(ctx, monkeypatch):
     """Jacobi-PCG on affine order-1 hexes through the order-1 patch kernel: <p, A p> comes from the kernel's fused dot
     product; iteration count and solution as the oracle's hypre-semantics PCG."""
-    monkeypatch.setenv("HCURL_PATCH_P1", "1")
     m, sp, mo, so = make_pair("hex", (12, 10, 9), 1, False)
     a, b = coefficients(m)
     a = a * 0.05
@@ -119,8 +116,6 @@ def test_pcg_order1_patch_kernel_fused_dot(ctx, monkeypatch):
     assert rel_err(x, xo) < 1e-6
 
 
-@pytest.mark.skipif(__import__("os").environ.get("HCURL_TEST_CHEBYSHEV") != "1",
-                    reason="Chebyshev preconditioner added after the round-1 GPU budget was spent; opt in with HCURL_TEST_CHEBYSHEV=1")
 @pytest.mark.parametrize("kind,n,p,order", [("hex", 6, 2, 3), ("hex", 8, 1, 2), ("tet", 3, 2, 4), ("hex", 6, 2, 1)])
 def test_pcg_chebyshev_matches_oracle(ctx, kind, n, p, order):
     """HCURL_PC_CHEBYSHEV against the oracle's restatement (oracle/pcg.py: power_lambda_max, chebyshev): eigenvalue

@@ -30,6 +30,19 @@ def build(space, fe, slot_code, centroid, stride=None, unit=8, n_units=None, exc
     L.check(lib.hcurl_host_patches_copy(h, L.ptr(perm), L.ptr(off), L.ptr(blob)), "copy")
     assert lib.hcurl_host_patches_max_blob_words(h) == int(np.diff(off.astype(np.int64)).max()) * 4
     assert lib.hcurl_host_patches_max_dofs(h) == max(int(blob[int(o) * 4]) for o in off[:-1])
+    part = np.zeros(2 * npatch, np.uint32)
+    md, ml, mt = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+    L.check(lib.hcurl_host_patches_parts(h, L.ptr(part), C.byref(md), C.byref(ml), C.byref(mt)), "parts")
+    part = part.astype(np.int64).reshape(npatch, 2)
+    assert np.all(off[:-1] < part[:, 0]) and np.all(part[:, 0] <= part[:, 1]) and np.all(part[:, 1] < off[1:])
+    assert md.value == int((part[:, 0] - off[:-1].astype(np.int64)).max()) * 4 and ml.value == int((part[:, 1] - part[:, 0]).max()) * 4
+    assert mt.value == int((off[1:].astype(np.int64) - part[:, 1]).max()) * 4
+    SWIZZLE["part"] = part
+    own_off = np.zeros(npatch + 1, np.uint32)
+    n_own = lib.hcurl_host_patches_owned(h, L.ptr(own_off), None)
+    own_idx = np.zeros(max(n_own, 1), np.uint32)
+    assert lib.hcurl_host_patches_owned(h, None, L.ptr(own_idx)) == n_own == int(own_off[-1])
+    SWIZZLE["owned"] = (own_off.astype(np.int64), own_idx.astype(np.int64))
     nb = 128 // unit
     row, grp = np.zeros(nd, np.uint8), np.zeros((fe + nb - 1) // nb, np.uint8)
     L.check(lib.hcurl_host_patches_swizzle(h, L.ptr(row), L.ptr(grp)), "swizzle")
@@ -39,33 +52,56 @@ def build(space, fe, slot_code, centroid, stride=None, unit=8, n_units=None, exc
     return perm, off.astype(np.int64), blob, stride
 
 
-SHARED = 0x80000000
+SHARED, OWNED = 0x80000000, 0x10000000
+
+
+HDR = 32
 
 
 def decode_patch(k, off, blob, nd=None, fe=None):
     """Blob of patch k (layout: hephaestus_b200/csrc/patch.cpp) ->
-    (dof ids (U,), [(first u, dof ids, private?, E byte offsets (n, W))] per width class, overflow words
+    (unit ids (U,), [(first u, unit ids, None for private units | owned-by-this-patch mask for shared ones, E byte offsets
+     (n, W))] per class -- private with 1 / 2 / 3..4 slots, then shared with 1 / 2 / 3..4 slots --, overflow words,
+     dependency patches
      [, lidx (nd, fe), number of real elements -- when nd and fe are given])."""
     B = blob[off[k] * 4:off[k + 1] * 4]
-    U, n1, n2, n4, nP1, nP2, nP4, nov, o16, o32, o64, oov, olx, n_real = [int(v) for v in B[:14]]
-    assert np.all(B[14:16] == 0) and U == n1 + n2 + n4
-    assert o16 % 4 == 0 and o32 % 4 == 0 and o64 % 4 == 0 and oov % 4 == 0 and olx % 4 == 0 and len(B) % 4 == 0
-    word = B[16:16 + U].astype(np.int64)
+    U, n_real, nov = [int(v) for v in B[:3]]
+    assert B[3] == 0 and B[17] == 0
+    n = [int(v) for v in B[4:10]]
+    oL = [int(v) for v in B[10:16]]
+    oov, wd, wl = int(B[16]), int(B[18]), int(B[19])
+    assert np.all(B[20:HDR] == 0) and U == sum(n)
+    pd0, pt0 = SWIZZLE["part"][k]
+    assert wd == (pd0 - off[k]) * 4 and wl == (pt0 - pd0) * 4 and wd >= HDR + U
+    assert all(o % 4 == 0 for o in oL + [oov]) and len(B) % 4 == 0
+    word = B[HDR:HDR + U].astype(np.int64)
     assert np.all(word & 0x60000000 == 0)                        # essential flags are set by the operator
-    dof, priv = word & 0x1FFFFFFF, (word & SHARED) == 0
+    assert np.all(((word & OWNED) == 0) | ((word & SHARED) != 0))   # only shared units have an owner flag
+    dof, multi, owned = word & 0x0FFFFFFF, (word & SHARED) != 0, (word & OWNED) != 0
+    Lw = B[wd:wd + wl]
     sh = 16 * np.arange(4, dtype=np.uint64)
-    e16 = B[o16:o16 + (n1 + 1) // 2].view(np.uint16)[:n1].astype(np.int64)[:, None]
-    e32 = (B[o32:o32 + n2, None].astype(np.uint64) >> sh[None, :2]).astype(np.int64) & 0xFFFF
-    e64 = (B[o64:o64 + 2 * n4].view(np.uint64)[:, None] >> sh[None]).astype(np.int64) & 0xFFFF
-    groups = [(0, dof[:n1], priv[:n1], e16), (n1, dof[n1:n1 + n2], priv[n1:n1 + n2], e32),
-              (n1 + n2, dof[n1 + n2:], priv[n1 + n2:], e64)]
-    assert [int(g[2].sum()) for g in groups] == [nP1, nP2, nP4]
-    ov = B[oov:oov + nov].astype(np.int64)
+    groups, u0 = [], 0
+    for c in range(6):
+        w, cnt, o = c % 3, n[c], oL[c]
+        if w == 0:
+            ent = Lw[o:o + (cnt + 1) // 2].view(np.uint16)[:cnt].astype(np.int64)[:, None]
+        elif w == 1:
+            ent = (Lw[o:o + cnt, None].astype(np.uint64) >> sh[None, :2]).astype(np.int64) & 0xFFFF
+        else:
+            ent = (Lw[o:o + 2 * cnt].view(np.uint64)[:, None] >> sh[None]).astype(np.int64) & 0xFFFF
+        groups.append((u0, dof[u0:u0 + cnt], None if c < 3 else owned[u0:u0 + cnt], ent))
+        assert np.all(multi[u0:u0 + cnt] == (c >= 3))
+        u0 += cnt
+    ov = Lw[oov:oov + nov].astype(np.int64)
+    oo, oi = SWIZZLE["owned"]
+    deps = oi[oo[k]:oo[k + 1]]                 # the shared units this patch owns (zeroed ahead of the sums by its CTA)
+    assert np.all(np.diff(deps) > 0) and np.array_equal(deps, np.sort(dof[owned]))
     if nd is None:
-        return dof, groups, ov
-    lidx = B[olx:olx + (nd * fe + 1) // 2].view(np.uint16)[:nd * fe].astype(np.int64).reshape(nd, fe)
-    assert olx + (nd * fe + 1) // 2 <= len(B)
-    return dof, groups, ov, lidx, n_real
+        return dof, groups, ov, deps
+    T = B[wd + wl:]
+    lidx = T[:(nd * fe + 1) // 2].view(np.uint16)[:nd * fe].astype(np.int64).reshape(nd, fe)
+    assert (nd * fe + 1) // 2 <= len(T)
+    return dof, groups, ov, deps, lidx, n_real
 
 
 SWIZZLE = {}   # bank swizzle of the most recent build(): row[s], grp[j // nb]
@@ -117,8 +153,9 @@ def test_patch_lists_reproduce_gather_and_scatter(kind, n, p, fe, perturb):
     ye = rng.standard_normal((ne, nd))
     y_ref = np.zeros(sp.ndof)
     np.add.at(y_ref, idx.ravel(), (sgn * ye).ravel())
-    y = np.zeros(sp.ndof)
+    y = np.full(sp.ndof, 1e30)                  # nothing is cleared: the owner's store comes first
     touched = np.zeros(sp.ndof, np.int64)
+    filled_by = np.full(sp.ndof, -1)
     elem_patch = np.empty(ne, np.int64)
     elem_patch[perm[perm >= 0]] = np.nonzero(perm >= 0)[0] // fe
     pmin = np.full(sp.ndof, 1 << 40)
@@ -127,7 +164,7 @@ def test_patch_lists_reproduce_gather_and_scatter(kind, n, p, fe, perturb):
     np.maximum.at(pmax, idx.ravel(), np.repeat(elem_patch, nd))
     sl = np.arange(nd)
     for k in range(npatch):
-        pd_all, groups, ov, lidx, n_real_blob = decode_patch(k, off, blob, nd, fe)
+        pd_all, groups, ov, deps, lidx, n_real_blob = decode_patch(k, off, blob, nd, fe)
         el = perm[k * fe:(k + 1) * fe]
         n_real = int((el >= 0).sum())
         assert n_real == n_real_blob
@@ -145,7 +182,7 @@ def test_patch_lists_reproduce_gather_and_scatter(kind, n, p, fe, perturb):
         for j in range(n_real):
             Ey[e_index(sl, j, st)] = np.where(neg_l[:, j], -ye[el[j]], ye[el[j]])
         n_slots = 0
-        for u0, pd, priv, ent in groups:
+        for u0, pd, own, ent in groups:
             # ascending global index up to the bank-spreading permutation inside aligned runs of 16 positions
             run = (u0 + np.arange(len(pd))) // 16
             srt = np.sort(pd)
@@ -161,21 +198,28 @@ def test_patch_lists_reproduce_gather_and_scatter(kind, n, p, fe, perturb):
                 assert used[:, :3].all()                         # only the 4th entry may be unused
             assert np.all(ent[used] % 8 == 0)
             n_slots += int(used.sum())
-            assert np.all(pmin[pd[priv]] == pmax[pd[priv]]) and np.all(touched[pd[priv]] == 0)
-            if kind == "hex":
-                assert np.all(pmin[pd[~priv]] != pmax[pd[~priv]])
+            # private units are stored; the owner of a shared unit is the lowest-numbered patch touching it: its CTA zeroes
+            # the unit ahead of time, every patch (the owner included) adds once the zeroing watermark has passed
+            if own is None:
+                assert np.all(pmin[pd] == k) and np.all(pmax[pd] == k) and np.all(touched[pd] == 0)
+            else:
+                assert np.array_equal(own, pmin[pd] == k)
+                y[pd[own]] = 0.0
+                filled_by[pd[own]] = k
+                assert np.all(filled_by[pd] == pmin[pd])
+
             for u in range(len(pd)):
                 v = np.sum(Ey[ent[u][used[u]] // 8])
-                if priv[u]:
+                if own is None:
                     y[pd[u]] = v
                 else:
                     y[pd[u]] += v
                 touched[pd[u]] += 1
         assert n_slots + len(ov) == n_real * nd
-        u_ov = ov >> 16
-        assert np.all(u_ov >= groups[2][0]) and not np.any(groups[2][2][u_ov - groups[2][0]])   # overflow: shared 3..4-slot dofs
-        for w in ov:
-            y[pd_all[w >> 16]] += Ey[(w & 0xFFFF) // 8]
+        for w in ov:                                             # overflow slots: units with more than four slots are classed shared
+            u = w >> 16
+            assert groups[5][0] <= u < groups[5][0] + len(groups[5][1])
+            y[pd_all[u]] += Ey[(w & 0xFFFF) // 8]
     assert np.all(touched >= 1)
     np.testing.assert_allclose(y, y_ref, rtol=0, atol=1e-13)
 
@@ -190,9 +234,9 @@ def test_structured_cube_patches_are_blocks():
         np.testing.assert_allclose(ext, 3.0 / 8, atol=1e-12)
         # 4x4x4 block of order-2 hexes: 1944 unique dofs, 1176 of them interior to the block
         # (here blocks touch the domain boundary, which only adds private dofs)
-        pd, groups, ov = decode_patch(k, off, blob)
+        pd, groups, ov, deps = decode_patch(k, off, blob)
         assert len(pd) == 1944
-        assert sum(int(g[2].sum()) for g in groups) >= 1176
+        assert sum(len(g[1]) for g in groups[:3]) >= 1176
 
 
 def test_bad_arguments_are_reported():
@@ -226,7 +270,7 @@ def test_pair_units_with_orientation_flags(n, fe, padded):
     flags = rng.integers(0, 8, size=idx.shape).astype(np.uint32) << 29
     code = np.ascontiguousarray((idx.astype(np.uint32) | flags).astype(np.uint32))
     cen = np.ascontiguousarray(m.verts[m.elems].mean(axis=1))
-    perm, off, blob, st = build(sp, fe, code, cen, stride=None if padded else fe, unit=16, n_units=n_units)   # unpadded rows: split-blob kernel
+    perm, off, blob, st = build(sp, fe, code, cen, stride=None if padded else fe, unit=16, n_units=n_units)   # any slot stride >= elements per patch
     x = rng.standard_normal((n_units, 2))
     ye = rng.standard_normal((ne, npair, 2))
     sw, n1, n0 = (flags & SWAP) != 0, (flags & NEG1) != 0, (flags & NEG0) != 0
@@ -237,10 +281,10 @@ def test_pair_units_with_orientation_flags(n, fe, padded):
     contrib = np.stack([np.where(sw, s1 * ye[..., 1], s0 * ye[..., 0]), np.where(sw, s0 * ye[..., 0], s1 * ye[..., 1])], axis=-1)
     y_ref = np.zeros((n_units, 2))
     np.add.at(y_ref, idx.ravel(), contrib.reshape(-1, 2))
-    y = np.zeros((n_units, 2))
+    y = np.full((n_units, 2), 1e30)
     sl = np.arange(npair)
     for k in range(len(off) - 1):
-        pd_all, groups, ov, lidx, n_real = decode_patch(k, off, blob, npair, fe)
+        pd_all, groups, ov, deps, lidx, n_real = decode_patch(k, off, blob, npair, fe)
         el = perm[k * fe:(k + 1) * fe]
         Xs = x[pd_all]
         pos = lidx & 0x1FFF
@@ -254,11 +298,14 @@ def test_pair_units_with_orientation_flags(n, fe, padded):
             b0 = np.where(ln0[:, j], -1.0, 1.0) * ye[el[j], :, 0]
             b1 = np.where(ln1[:, j], -1.0, 1.0) * ye[el[j], :, 1]
             Ey[e_index(sl, j, st)] = np.where(lsw[:, j, None], np.stack([b1, b0], -1), np.stack([b0, b1], -1))
-        for u0, pd, priv, ent in groups:
+        for u0, pd, own, ent in groups:
             used = ent != 0xFFFF
             assert np.all(ent[used] % 16 == 0)
+            if own is not None:
+                y[pd[own]] = 0.0
             for u in range(len(pd)):
-                y[pd[u]] += Ey[ent[u][used[u]] // 16].sum(axis=0)
+                v = Ey[ent[u][used[u]] // 16].sum(axis=0)
+                y[pd[u]] = v if own is None else y[pd[u]] + v
         for w in ov:
             y[pd_all[w >> 16]] += Ey[(w & 0xFFFF) // 16]
     np.testing.assert_allclose(y, y_ref, rtol=0, atol=1e-13)

@@ -241,8 +241,6 @@ def test_bad_arguments_are_reported(lib_built):
 
 # ---- GPU (opt-in until run on a B200) -------------------------------------------------------------------------------------
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("HCURL_TEST_INTERP") != "1",
-                    reason="interpolator kernel written after the round-1 GPU budget was spent; opt in with HCURL_TEST_INTERP=1")
 @pytest.mark.parametrize("p,n", [(1, (9, 7, 5)), (2, (5, 4, 3)), (3, (3, 2, 2)), (4, (2, 2, 1))])
 def test_gpu_interpolators_match_oracle(ctx, p, n):
     from hephaestus_b200 import operators
@@ -270,8 +268,6 @@ def test_gpu_interpolators_match_oracle(ctx, p, n):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("HCURL_TEST_INTERP") != "1",
-                    reason="interpolator kernel written after the round-1 GPU budget was spent; opt in with HCURL_TEST_INTERP=1")
 def test_gpu_tet_order1_interpolators_match_oracle(ctx):
     from hephaestus_b200 import operators
     mo, h1, nd, rt, (nv, nn, nf) = tet_spaces((3, 3, 2))

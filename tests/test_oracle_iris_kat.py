@@ -49,8 +49,6 @@ def test_product_dof_map_on_the_kat_mesh(kat):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("HCURL_TEST_IRIS") != "1",
-                    reason="added after the round-1 GPU budget was spent; opt in with HCURL_TEST_IRIS=1")
 def test_gpu_operator_of_the_kat(ctx, kat):
     """the volume operator of the known-answer problem, K(1/mu0) + M(-omega^2 eps0) (negative mass coefficient), and the
     complex block apply with a loss term, through the C ABI against the oracle"""
