@@ -38,7 +38,8 @@ def parse():
     ap.add_argument("--perturbed", action="store_true", help="trilinearly perturbed mesh variant (general geometry)")
     ap.add_argument("--quad", default="fast", choices=["fast", "mfem"])
     ap.add_argument("--pcg-iters", type=int, default=50)
-    ap.add_argument("--cpu-n", type=int, default=24, help="cube size of the bounded CPU sample")
+    ap.add_argument("--cpu-n", type=int, default=0, help="cube size of the bounded CPU sample (0: 32 for the cpu_baseline leg, "
+                    "as large as host memory allows -- 64 -- for --impl reference)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -60,9 +61,9 @@ def peaks():
 
 def measured_traffic(order, n, kernel_id):
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this command
-    (profiles/r1_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum), or None when no capture exists for
+    (profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum), or None when no capture exists for
     the configuration being run."""
-    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    path = os.path.join(ROOT, "profiles", "traffic.json")
     if not os.path.exists(path):
         return None
     with open(path) as f:
@@ -130,36 +131,77 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def cpu_sample(n, p, steps, warmup, pcg_iters, threads=None):
-    """The reference's algorithm on the host: assembled CSR SpMV + Jacobi-PCG (oracle port)."""
+def host_threads():
+    """all host cores, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1 to every rank)"""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_sample(n, p, steps, warmup, pcg_iters, threads=None, extra_threads=()):
+    """The reference's algorithm on the host: element matrices -> assembled CSR (blf->Assemble + FormLinearSystem
+    elimination) -> SpMV + Jacobi-PCG with hypre's semantics (oracle port, C + OpenMP)."""
     from oracle import assemble as oa
     from oracle import csr as ocsr
     from oracle import mesh as om
     from oracle import space as osp
+    t0 = time.perf_counter()
+    ocsr.lib().csr_set_threads(threads or host_threads())
     mesh = om.cartesian_hex(n, n, n)
     space = osp.NDSpace(mesh, p)
     alpha, beta = coefficients(mesh.attr)
-    A = oa.assemble(space, alpha, beta, q_override=p + 1)
     ess = space.boundary_dofs()
-    Ac, _ = oa.eliminate(A, ess)
-    op = ocsr.CsrOperator(Ac)
-    if threads:
-        ocsr.lib().csr_set_threads(threads)
+    # the structured cube has one element matrix per attribute: computed by the oracle's quadrature code on a
+    # representative element of each, scattered by the C assembly
+    reps = [int(np.nonzero(mesh.attr == a)[0][0]) for a in (1, 2)]
+    sub = om.Mesh("hex", mesh.verts, mesh.elems[reps], mesh.attr[reps])
+    ssp = osp.NDSpace(sub, p)
+    (_, _, Ae), = list(oa.element_matrices(ssp, alpha[reps], beta[reps], q_override=p + 1))
+    sd = np.where(space.elem_sign > 0, space.elem_dofs, -1 - space.elem_dofs)
+    op = ocsr.CsrOperator.from_element_matrices(space.ndof, sd, mesh.attr - 1, Ae, ess)
+    t_setup = time.perf_counter() - t0
     cores = ocsr.lib().csr_num_threads()
     x = np.random.default_rng(12345).standard_normal(space.ndof)
     y = np.empty_like(x)
-    for _ in range(warmup):
-        op.spmv(x, y)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        op.spmv(x, y)
-    t_apply = (time.perf_counter() - t0) / steps
-    b = Ac @ np.random.default_rng(54321).standard_normal(space.ndof)
-    dinv = 1.0 / Ac.diagonal()
-    t0 = time.perf_counter()
+
+    def time_apply():
+        for _ in range(warmup):
+            op.spmv(x, y)
+        t1 = time.perf_counter()
+        for _ in range(steps):
+            op.spmv(x, y)
+        return (time.perf_counter() - t1) / steps
+
+    t_apply = time_apply()
+    xs = np.random.default_rng(54321).standard_normal(space.ndof)
+    b = np.empty_like(xs)
+    op.spmv(xs, b)
+    dinv = 1.0 / op.diagonal()
+    t1 = time.perf_counter()
     _, it, _, _ = op.pcg(b, dinv, rtol=0.0, atol=0.0, max_iter=pcg_iters)
-    t_pcg = (time.perf_counter() - t0) / max(it, 1)
-    return {"n_dof": int(space.ndof), "nnz": int(op.nnz), "cores": int(cores), "apply_s": t_apply, "pcg_iter_s": t_pcg}
+    t_pcg = (time.perf_counter() - t1) / max(it, 1)
+    other = {}
+    for nt in extra_threads:  # e.g. 4: the reference README's `mpirun -n 4`
+        if nt < cores:
+            ocsr.lib().csr_set_threads(nt)
+            other[int(nt)] = space.ndof / time_apply() / 1e9
+    ocsr.lib().csr_set_threads(cores)
+    return {"n_dof": int(space.ndof), "nnz": int(op.nnz), "cores": int(cores), "apply_s": t_apply, "pcg_iter_s": t_pcg,
+            "setup_s": t_setup, "gdofs_by_threads": other}
+
+
+def reference_sample_n(args):
+    """cube size of the reference arm's sample: as close to the GPU workload as host memory allows (the assembled CSR of
+    the n = 128 workload would need about 55 GB; n = 64 -- 6.4 M DOFs, about 7 GB -- is the default where it fits)"""
+    if args.cpu_n:
+        return args.cpu_n
+    try:
+        mem_gb = os.sysconf("SC_PAGE_SIZE") * os.sysconf("SC_PHYS_PAGES") / 2 ** 30
+    except (ValueError, OSError):
+        mem_gb = 16.0
+    want = 64 if args.order <= 2 else 32
+    return min(args.n, want if mem_gb >= 48 else (48 if mem_gb >= 24 else 32))
 
 
 def run_reference(args, rank, world):
@@ -167,17 +209,19 @@ def run_reference(args, rank, world):
     cannot be built in this image), all host threads, bounded sample of the same workload."""
     if rank != 0:
         return
-    s = cpu_sample(args.cpu_n, args.order, args.steps, max(args.warmup, 3), args.pcg_iters)
+    n = reference_sample_n(args)
+    s = cpu_sample(n, args.order, args.steps, max(args.warmup, 3), args.pcg_iters, extra_threads=(4,))
     gdofs = s["n_dof"] / s["apply_s"] / 1e9
-    sample = "structured hex cube n=%d order %d (%d DOFs, %d nnz): assembled CSR SpMV, all host threads" % (
-        args.cpu_n, args.order, s["n_dof"], s["nnz"])
+    sample = "structured hex cube n=%d order %d (%d DOFs, %d nnz, %.1f GB CSR): assembled CSR SpMV, %d host threads (setup %.0f s)" % (
+        n, args.order, s["n_dof"], s["nnz"], s["nnz"] * 12 / 1e9, s["cores"], s["setup_s"])
     line = {
         "impl": "reference", "metric": "hcurl_apply_gdofs", "value": gdofs, "unit": "GDOF/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": s["apply_s"] * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, args.cpu_n, s["n_dof"], bounded=True),
+        "config": workload_config(args, n, s["n_dof"], bounded=True),
         "cpu_baseline": {"value": gdofs, "unit": "GDOF/s", "cores": s["cores"], "kind": "port", "sample": sample,
-                         "pcg_iters_per_s": 1.0 / s["pcg_iter_s"]},
+                         "pcg_iters_per_s": 1.0 / s["pcg_iter_s"],
+                         "gdofs_4_threads": s["gdofs_by_threads"].get(4), "same_order_of_size": bool(s["n_dof"] >= 5e6)},
         "e2e": {"value": gdofs, "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -350,6 +394,7 @@ def main():
                         3: "patch pipeline: one thread per element, modal operator, persistent, zero-ahead watermark"}.get(op.LastKernel(), "?")),
                 "kernel_ms": kern_ms, "kernel_launches_timed": kern_n, "algorithmic_bytes_per_launch": abytes,
                 "bytes_per_dof": abytes / n_tdof, "kernel_share_of_step": kern_ms / ms_step if ms_step > 0 else None,
+                "step_frac": abytes / (ms_step * 1e-3) / 1e9 / peak if ms_step > 0 else None,
                 "fp64_fma_peak_tflops_measured": fp64}
 
     if rank != 0:
@@ -371,11 +416,12 @@ def main():
                        "note": "hcurl_pcg_solve(HCURL_HOST): pinned b -> device, whole Krylov loop on the device, x -> host"}
         except Exception as exc:  # a reporting extra: never lose the bench line over it
             pcg_e2e = {"error": str(exc)}
-    if world == 1 and not args.no_cpu:
-        s = cpu_sample(args.cpu_n, p, 10, 3, 20)
+    if not args.no_cpu and args.geom == "hex" and not args.perturbed:
+        cn = args.cpu_n or (32 if p <= 2 else 16)
+        s = cpu_sample(cn, p, 10, 3, 20)
         cpu = {"value": s["n_dof"] / s["apply_s"] / 1e9, "unit": "GDOF/s", "cores": s["cores"], "kind": "port",
                "sample": "structured hex cube n=%d order %d (%d DOFs, %d nnz): assembled CSR SpMV (hypre-style row "
-                         "blocks, OpenMP), 10 timed applies" % (args.cpu_n, p, s["n_dof"], s["nnz"]),
+                         "blocks, OpenMP), 10 timed applies" % (cn, p, s["n_dof"], s["nnz"]),
                "pcg_iters_per_s": 1.0 / s["pcg_iter_s"]}
     line = {
         "metric": "hcurl_apply_gdofs", "value": value, "unit": "GDOF/s", "n_gpus": world, "steps": args.steps,

@@ -23,12 +23,16 @@ def lib():
         L.csr_pcg.restype = C.c_int
         L.csr_pcg.argtypes = [C.c_int64] + [C.c_void_p] * 6 + [C.c_double, C.c_double, C.c_int, C.POINTER(C.c_double),
                                                                C.POINTER(C.c_int)]
+        L.csr_assemble.restype = C.c_int
+        L.csr_assemble.argtypes = [C.c_int64, C.c_int64, C.c_int] + [C.c_void_p] * 7
         _LIB = L
     return _LIB
 
 
 class CsrOperator:
-    def __init__(self, A):
+    def __init__(self, A=None):
+        if A is None:
+            return
         A = A.tocsr()
         A.sort_indices()
         self.n = A.shape[0]
@@ -36,6 +40,39 @@ class CsrOperator:
         self.col = np.ascontiguousarray(A.indices, dtype=np.int32)
         self.val = np.ascontiguousarray(A.data, dtype=np.float64)
         self.nnz = len(self.val)
+
+    @classmethod
+    def from_element_matrices(cls, n, signed_elem_dofs, mat_id, elmat, ess=None):
+        """blf->Assemble() + FormLinearSystem elimination in C (csr_assemble): signed_elem_dofs (ne, nd) in MFEM's
+        -1-k encoding, mat_id (ne,) into elmat (nmat, nd, nd) local element matrices, ess = essential dof indices."""
+        self = cls()
+        sd = np.ascontiguousarray(signed_elem_dofs, dtype=np.int32)
+        ne, nd = sd.shape
+        mid = np.ascontiguousarray(mat_id, dtype=np.int32)
+        em = np.ascontiguousarray(elmat, dtype=np.float64)
+        assert em.shape[1:] == (nd, nd) and mid.max() < em.shape[0]
+        flag = None
+        if ess is not None:
+            flag = np.zeros(n, np.uint8)
+            flag[np.asarray(ess, dtype=np.int64)] = 1
+        self.n = int(n)
+        self.rowptr = np.zeros(n + 1, np.int64)
+        p = self._p
+        if lib().csr_assemble(n, ne, nd, p(sd), p(mid), p(em), p(flag), p(self.rowptr), None, None):
+            raise MemoryError("csr_assemble (count)")
+        self.nnz = int(self.rowptr[-1])
+        self.col = np.empty(self.nnz, np.int32)
+        self.val = np.empty(self.nnz, np.float64)
+        if lib().csr_assemble(n, ne, nd, p(sd), p(mid), p(em), p(flag), p(self.rowptr), p(self.col), p(self.val)):
+            raise MemoryError("csr_assemble (fill)")
+        return self
+
+    def diagonal(self):
+        d = np.zeros(self.n)
+        rows = np.repeat(np.arange(self.n), np.diff(self.rowptr))
+        m = rows == self.col
+        d[rows[m]] = self.val[m]
+        return d
 
     def _p(self, a):
         return a.ctypes.data_as(C.c_void_p) if a is not None else None

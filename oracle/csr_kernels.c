@@ -79,3 +79,75 @@ int csr_pcg(int64_t n, const int64_t *rowptr, const int32_t *col, const double *
   free(r); free(p); free(s);
   return it;
 }
+
+/* ---- assembly ------------------------------------------------------------------------------------------------
+ * What blf->Assemble() (/root/reference/src/equation_systems/equation_system.cpp:345) followed by the essential-row /
+ * column elimination of FormLinearSystem (ibid. :132-190, diagonal policy ONE) produce, from element matrices:
+ *   elem_dof [ne][nd]   signed MFEM encoding of FiniteElementSpace::GetElementDofs (k, or -1-k = flipped)
+ *   mat_id  [ne]        which of the nmat local element matrices elmat [nmat][nd][nd] the element uses (elements of
+ *                       a structured mesh share the matrix of their attribute)
+ *   ess     [n]         1 = essential dof (row and column replaced by the identity), may be NULL
+ * Row-wise: every row gathers the contributions of the elements touching it, sorts them by column and merges
+ * duplicates (fixed order: the result does not depend on the thread count).  Pass 1 (col == NULL) only counts:
+ * rowptr [n+1] is written; pass 2 fills col / val. */
+typedef struct { int32_t c; double v; } entry_t;
+static int cmp_entry(const void *a, const void *b) {
+  const int32_t x = ((const entry_t *)a)->c, y = ((const entry_t *)b)->c;
+  return (x > y) - (x < y);
+}
+int csr_assemble(int64_t n, int64_t ne, int nd, const int32_t *elem_dof, const int32_t *mat_id, const double *elmat,
+                 const uint8_t *ess, int64_t *rowptr, int32_t *col, double *val) {
+  /* dof -> (element, local index) adjacency */
+  int64_t *aoff = calloc((size_t)n + 2, sizeof(int64_t));
+  if (!aoff) return 1;
+  for (int64_t i = 0; i < ne * nd; i++) { const int32_t d = elem_dof[i]; aoff[(d >= 0 ? d : -1 - d) + 2]++; }
+  for (int64_t i = 0; i < n; i++) aoff[i + 2] += aoff[i + 1];
+  int64_t *adj = malloc(sizeof(int64_t) * (size_t)(ne * nd));
+  if (!adj) { free(aoff); return 1; }
+  for (int64_t i = 0; i < ne * nd; i++) { const int32_t d = elem_dof[i]; adj[aoff[(d >= 0 ? d : -1 - d) + 1]++] = i; }
+  int64_t maxadj = 0;
+  for (int64_t i = 0; i < n; i++) if (aoff[i + 1] - aoff[i] > maxadj) maxadj = aoff[i + 1] - aoff[i];
+  const int fill = col != NULL;
+  if (!fill) rowptr[0] = 0;
+  int fail = 0;
+#pragma omp parallel
+  {
+    entry_t *buf = malloc(sizeof(entry_t) * (size_t)(maxadj * nd + 1));
+    if (!buf) {
+#pragma omp atomic write
+      fail = 1;
+    }
+#pragma omp for schedule(dynamic, 1024)
+    for (int64_t i = 0; i < n; i++) {
+      if (!buf) continue;
+      int64_t m = 0;
+      if (ess && ess[i]) { buf[m].c = (int32_t)i; buf[m++].v = 1.0; }
+      else
+        for (int64_t q = aoff[i]; q < aoff[i + 1]; q++) {
+          const int64_t e = adj[q] / nd;
+          const int li = (int)(adj[q] % nd);
+          const double si = elem_dof[e * nd + li] < 0 ? -1.0 : 1.0;
+          const double *M = elmat + ((int64_t)mat_id[e] * nd + li) * nd;
+          for (int lj = 0; lj < nd; lj++) {
+            const int32_t d = elem_dof[e * nd + lj], cj = d >= 0 ? d : -1 - d;
+            if (ess && ess[cj]) continue;
+            buf[m].c = cj;
+            buf[m++].v = (d < 0 ? -si : si) * M[lj];
+          }
+        }
+      qsort(buf, (size_t)m, sizeof(entry_t), cmp_entry);
+      int64_t u = 0;
+      for (int64_t k = 0; k < m; k++) {
+        if (u > 0 && buf[u - 1].c == buf[k].c) buf[u - 1].v += buf[k].v;
+        else buf[u++] = buf[k];
+      }
+      if (!fill) rowptr[i + 1] = u;
+      else
+        for (int64_t k = 0; k < u; k++) { col[rowptr[i] + k] = buf[k].c; val[rowptr[i] + k] = buf[k].v; }
+    }
+    free(buf);
+  }
+  if (!fill && !fail) for (int64_t i = 0; i < n; i++) rowptr[i + 1] += rowptr[i];
+  free(adj); free(aoff);
+  return fail;
+}
