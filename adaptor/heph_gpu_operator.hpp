@@ -18,6 +18,7 @@
 // against the mock only -- see DESIGN.md "unverified against real MFEM").
 #pragma once
 #include <cstdint>
+#include <algorithm>
 #include <map>
 #include <memory>
 #include <string>
@@ -140,45 +141,62 @@ public:
     std::vector<int8_t> ghost_sign;
     if (fes.GetNRanks() > 1)
     {
-      // group g is a set of ranks sharing some ldofs; its master owns them.  For every
-      // neighbour r: dofs I own that r also holds, and dofs r owns that I hold -- both sides
-      // enumerate a group's dofs in the same (group, local-in-group) order.
+#ifndef HEPH_GPU_ALLOW_UNVERIFIED_MULTIRANK
+      // This branch has only ever been compiled against the mock (MFEM is not installable in the build container).  The
+      // lists below follow MFEM's GroupCommunicator conventions as documented, but until they have been checked against
+      // a real ParFiniteElementSpace a silent mis-pairing of shared dofs is worse than an abort.  The library's own
+      // multi-GPU path (hcurl_host_partition_*, tests/test_gpu_multi.py) does not go through here.
+      MFEM_ABORT("HephGpuSpace: several MPI ranks need -DHEPH_GPU_ALLOW_UNVERIFIED_MULTIRANK (unverified against MFEM)");
+#endif
+      // A group g is a set of ranks sharing some ldofs; its master owns them.  GroupCommunicator::GroupLDofTable() lists
+      // the ldofs of every group in the order BOTH sides agree on (shared edges, then triangles, then quadrilaterals of
+      // the group; an entry -1-k marks a dof this rank sees with the opposite orientation).  Local group ids differ
+      // between ranks, so the groups of a neighbour are ordered by a rank-independent key: (master rank, the master's
+      // own id of the group, GroupTopology::GetGroupMasterGroup).
       mfem::GroupTopology & gt = fes.GetGroupTopo();
+      const mfem::Table & gl = fes.GroupComm().GroupLDofTable();
       const int me = fes.GetMyRank();
-      std::map<int, std::vector<int32_t>> own_by, ghost_by;
-      mfem::Array<int> gdofs;
+      struct Seg { int master, master_group, g; };
+      std::map<int, std::vector<Seg>> segs; // neighbour rank -> groups shared with it
       for (int g = 1; g < gt.NGroups(); g++)
       {
-        fes.GetSharedDofs(g, gdofs); // ldofs of group g (edges, faces of the group in order)
         const int master = gt.GetNeighborRank(gt.GetGroupMaster(g));
-        for (int k = 0; k < gdofs.Size(); k++)
+        const Seg sg{master, gt.GetGroupMasterGroup(g), g};
+        if (master == me)
         {
-          const int ld = gdofs[k] >= 0 ? gdofs[k] : -1 - gdofs[k];
-          if (master == me)
-          {
-            const int * gr = gt.GetGroup(g);
-            for (int m = 0; m < gt.GetGroupSize(g); m++)
-              if (gt.GetNeighborRank(gr[m]) != me)
-                own_by[gt.GetNeighborRank(gr[m])].push_back(ld);
-          }
-          else
-            ghost_by[master].push_back(ld);
+          const int * gr = gt.GetGroup(g);
+          for (int m = 0; m < gt.GetGroupSize(g); m++)
+            if (gt.GetNeighborRank(gr[m]) != me)
+              segs[gt.GetNeighborRank(gr[m])].push_back(sg);
         }
+        else
+          segs[master].push_back(sg);
       }
-      std::map<int, int> ranks;
-      for (auto & kv : own_by) ranks[kv.first] = 1;
-      for (auto & kv : ghost_by) ranks[kv.first] = 1;
-      for (auto & kv : ranks)
+      for (auto & kv : segs)
       {
+        std::sort(kv.second.begin(), kv.second.end(), [](const Seg & a, const Seg & b)
+                  { return a.master != b.master ? a.master < b.master : a.master_group < b.master_group; });
         nbr.push_back(kv.first);
-        for (int32_t d : own_by[kv.first]) own_ldof.push_back(d);
-        for (int32_t d : ghost_by[kv.first]) { ghost_ldof.push_back(d); ghost_sign.push_back(1); }
+        for (const Seg & sg : kv.second)
+        {
+          const int * row = gl.GetRow(sg.g);
+          for (int k = 0; k < gl.RowSize(sg.g); k++)
+          {
+            const int ld = row[k] >= 0 ? row[k] : -1 - row[k];
+            if (sg.master == me)
+              own_ldof.push_back(ld);
+            else
+            {
+              ghost_ldof.push_back(ld);
+              // the master's value enters with the relative orientation of the two ranks' copies; the master's own
+              // entry is non-negative by MFEM's convention, so the sign of this rank's entry is that orientation
+              ghost_sign.push_back(row[k] >= 0 ? 1 : -1);
+            }
+          }
+        }
         own_off.push_back((int32_t)own_ldof.size());
         ghost_off.push_back((int32_t)ghost_ldof.size());
       }
-      // MFEM stores the relative orientation of a shared ND dof in the sign of the group's ldof
-      // entries (ParFiniteElementSpace::GetSharedEdgeDofs ...); element maps already carry it, so
-      // ghost values are exchanged unsigned (ghost_sign = +1) -- see DESIGN.md for the caveat.
     }
     _space = hcurl_space_create(ctx.Get(), tet ? HCURL_GEOM_TET : HCURL_GEOM_HEX, geom_order, order, ne,
                                 xyz.data(), ldof.data(), ev.empty() ? nullptr : ev.data(),
@@ -203,47 +221,109 @@ private:
 /// alpha / beta are the coefficient objects the reference's kernels hold:
 /// CurlCurlKernel::_coef (/root/reference/src/kernels/curl_curl_kernel.hpp:22-23) and
 /// VectorFEMassKernel::_coef (/root/reference/src/kernels/vector_fe_mass_kernel.hpp).
-/// quad_pts_per_dim: 0 = MFEM's full-assembly rules (what the reference's integrators use); HCURL_QUAD_AUTO = the
-/// p+1 rule wherever it is exact (all hexes parallelepipeds: equal to MFEM's rules to round-off, and the fast patch
-/// kernels apply), MFEM's rules otherwise -- the recommended setting once validated against MFEM on the target mesh.
+/// quad_pts_per_dim: HCURL_QUAD_AUTO (default) = the p+1 rule wherever it is exact (all hexes parallelepipeds with
+/// per-element coefficients: equal to MFEM's full-assembly rules to round-off -- tests/test_gpu_apply.py::
+/// test_quad_auto_picks_the_exact_rule_on_affine_meshes -- and the patch kernels apply), MFEM's rules otherwise;
+/// 0 = MFEM's full-assembly rules everywhere.
 class HephGpuOperator : public mfem::Operator
 {
 public:
+  /// How alpha / beta are sampled: once per element at its centre (PWCoefficient / ConstantCoefficient and
+  /// TransformedCoefficients of those -- TEAM7, TEAM4, the rod and coil examples), or at every quadrature point of the
+  /// integrators' rules (FunctionCoefficients, as in the reference's MMS tests,
+  /// /root/reference/test/integration/test_aform_source.cpp:32-37).  PER_QUAD_POINT keeps MFEM's rules (the patch
+  /// kernels need per-element coefficients).
+  enum Sampling { PER_ELEMENT = 0, PER_QUAD_POINT = 1 };
+
   HephGpuOperator(HephGpuContext & ctx, HephGpuSpace & space, mfem::Coefficient * alpha,
                   mfem::Coefficient * beta, const mfem::Array<int> & ess_tdof_list,
-                  int quad_pts_per_dim = 0)
-    : mfem::Operator(space.FESpace().GetTrueVSize()), _space(space), _alpha(alpha), _beta(beta)
+                  int quad_pts_per_dim = HCURL_QUAD_AUTO, Sampling sampling = PER_ELEMENT)
+    : mfem::Operator(space.FESpace().GetTrueVSize()), _space(space), _alpha(alpha), _beta(beta), _sampling(sampling)
   {
-    _op = hcurl_op_create(ctx.Get(), space.Get(), quad_pts_per_dim);
+    _op = hcurl_op_create(ctx.Get(), space.Get(), sampling == PER_QUAD_POINT ? 0 : quad_pts_per_dim);
     if (!_op)
       MFEM_ABORT(std::string("hcurl_op_create failed: ") + hcurl_last_error());
     UpdateCoefficients();
+    SetEssentialTrueDofs(ess_tdof_list);
+  }
+  ~HephGpuOperator() override { hcurl_op_destroy(_op); }
+
+  /// EquationSystem::_ess_tdof_lists (equation_system.hpp:94): rows / columns -> identity
+  void SetEssentialTrueDofs(const mfem::Array<int> & ess_tdof_list)
+  {
     std::vector<int32_t> ess(ess_tdof_list.Size());
     for (int i = 0; i < ess_tdof_list.Size(); i++)
       ess[i] = ess_tdof_list[i];
     HEPH_GPU_CHECK(hcurl_op_set_essential_tdofs(_op, ess.data(), (int32_t)ess.size()));
   }
-  ~HephGpuOperator() override { hcurl_op_destroy(_op); }
 
   /// Re-sample alpha / beta (Coefficients::SetTime, dt change:
   /// /root/reference/src/problem_operators/time_domain_equation_system_problem_operator.cpp:43,
   /// /root/reference/src/equation_systems/equation_system.cpp:413-426).  Values only, no rebuild.
-  /// Piecewise-constant coefficients (PWCoefficient / ConstantCoefficient / TransformedCoefficient
-  /// of those) are sampled once per element at the element centre.
   void UpdateCoefficients()
   {
     mfem::ParMesh * mesh = _space.FESpace().GetParMesh();
     const int ne = mesh->GetNE();
-    std::vector<double> a(_alpha ? ne : 0), b(_beta ? ne : 0);
+    if (_sampling == PER_ELEMENT)
+    {
+      std::vector<double> a(_alpha ? ne : 0), b(_beta ? ne : 0);
+      for (int e = 0; e < ne; e++)
+      {
+        mfem::ElementTransformation * T = mesh->GetElementTransformation(e);
+        const mfem::IntegrationPoint & ip = mfem::Geometries.GetCenter(mesh->GetElementGeometry(e));
+        T->SetIntPoint(&ip);
+        if (_alpha) a[e] = _alpha->Eval(*T, ip);
+        if (_beta) b[e] = _beta->Eval(*T, ip);
+      }
+      HEPH_GPU_CHECK(hcurl_op_set_coefficients(_op, HCURL_COEF_PER_ELEM, _alpha ? a.data() : nullptr,
+                                               _beta ? b.data() : nullptr, HCURL_HOST));
+      return;
+    }
+    // the rules MFEM's integrators pick on these elements: CurlCurlIntegrator order 2p-2 (simplices) /
+    // 2p (tensor elements), VectorFEMassIntegrator order OrderW + 2p; hex rules are tensor rules, x fastest, which is
+    // the library's order; tet rules are handed to the library point by point
+    const int geom = mesh->GetElementGeometry(0);
+    const int p = _space.FESpace().FEColl()->GetOrder();
+    mfem::ElementTransformation * T0 = mesh->GetElementTransformation(0);
+    const bool tet = geom == mfem::Geometry::TETRAHEDRON;
+    const mfem::IntegrationRule & irc = mfem::IntRules.Get(geom, tet ? 2 * p - 2 : 2 * p);
+    const mfem::IntegrationRule & irm = mfem::IntRules.Get(geom, T0->OrderW() + 2 * p);
+    if (tet)
+    {
+      auto flat = [](const mfem::IntegrationRule & ir, std::vector<double> & pts, std::vector<double> & w)
+      {
+        for (int q = 0; q < ir.GetNPoints(); q++)
+        {
+          const mfem::IntegrationPoint & ip = ir.IntPoint(q);
+          pts.push_back(ip.x); pts.push_back(ip.y); pts.push_back(ip.z);
+          w.push_back(ip.weight);
+        }
+      };
+      std::vector<double> pc, wc, pm, wm;
+      flat(irc, pc, wc);
+      flat(irm, pm, wm);
+      HEPH_GPU_CHECK(hcurl_op_set_tet_rules(_op, (int)wc.size(), pc.data(), wc.data(), (int)wm.size(), pm.data(), wm.data()));
+    }
+    if (irc.GetNPoints() != hcurl_op_qpts_curl(_op) || irm.GetNPoints() != hcurl_op_qpts_mass(_op))
+      MFEM_ABORT("HephGpuOperator: MFEM's integration rules differ from the library's (curl / mass points per element)");
+    std::vector<double> a(_alpha ? (size_t)ne * irc.GetNPoints() : 0), b(_beta ? (size_t)ne * irm.GetNPoints() : 0);
     for (int e = 0; e < ne; e++)
     {
       mfem::ElementTransformation * T = mesh->GetElementTransformation(e);
-      const mfem::IntegrationPoint & ip = mfem::Geometries.GetCenter(mesh->GetElementGeometry(e));
-      T->SetIntPoint(&ip);
-      if (_alpha) a[e] = _alpha->Eval(*T, ip);
-      if (_beta) b[e] = _beta->Eval(*T, ip);
+      if (_alpha)
+        for (int q = 0; q < irc.GetNPoints(); q++)
+        {
+          T->SetIntPoint(&irc.IntPoint(q));
+          a[(size_t)e * irc.GetNPoints() + q] = _alpha->Eval(*T, irc.IntPoint(q));
+        }
+      if (_beta)
+        for (int q = 0; q < irm.GetNPoints(); q++)
+        {
+          T->SetIntPoint(&irm.IntPoint(q));
+          b[(size_t)e * irm.GetNPoints() + q] = _beta->Eval(*T, irm.IntPoint(q));
+        }
     }
-    HEPH_GPU_CHECK(hcurl_op_set_coefficients(_op, HCURL_COEF_PER_ELEM, _alpha ? a.data() : nullptr,
+    HEPH_GPU_CHECK(hcurl_op_set_coefficients(_op, HCURL_COEF_PER_QPT, _alpha ? a.data() : nullptr,
                                              _beta ? b.data() : nullptr, HCURL_HOST));
   }
 
@@ -269,6 +349,7 @@ private:
   HephGpuSpace & _space;
   mfem::Coefficient * _alpha;
   mfem::Coefficient * _beta;
+  Sampling _sampling;
   hcurl_op * _op{nullptr};
 };
 

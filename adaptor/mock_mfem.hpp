@@ -65,9 +65,24 @@ public:
 
 struct IntegrationPoint
 {
-  double x{0}, y{0}, z{0};
+  double x{0}, y{0}, z{0}, weight{0};
   void Set3(double a, double b, double c) { x = a; y = b; z = c; }
 };
+class IntegrationRule
+{
+public:
+  int GetNPoints() const { return (int)_p.size(); }
+  const IntegrationPoint & IntPoint(int i) const { return _p[(size_t)i]; }
+  std::vector<IntegrationPoint> _p;
+};
+/// MFEM's quadrature tables are not restated in the mock: per-quadrature-point sampling is compiled, not run, here
+/// (the library side of it is exercised through the C ABI by tests/test_gpu_timestep.py)
+class IntegrationRules
+{
+public:
+  const IntegrationRule & Get(int, int) { MFEM_ABORT("mock MFEM has no integration rule tables"); }
+};
+static IntegrationRules IntRules;
 
 struct Geometry
 {
@@ -90,6 +105,7 @@ public:
   const std::vector<double> * xyz{nullptr};  // 8 or 4 corner nodes of the element
   int nv{8};
   void SetIntPoint(const IntegrationPoint * p) { ip = p; }
+  int OrderW() const { return nv == 4 ? 0 : 2; }  // straight tets / trilinear hexes
   void Transform(const IntegrationPoint & p, Vector & x) const
   {
     x.SetSize(3);
@@ -188,10 +204,23 @@ private:
   std::vector<double> _xyz;
 };
 
+class Table
+{
+public:
+  int RowSize(int) const { return 0; }
+  const int * GetRow(int) const { return nullptr; }
+};
+class GroupCommunicator
+{
+public:
+  const Table & GroupLDofTable() const { return _t; }
+  Table _t;
+};
 class GroupTopology
 {
 public:
   int NGroups() const { return 1; }  // serial mock: only the local group
+  int GetGroupMasterGroup(int) const { return 0; }
   int GetGroupMaster(int) const { return 0; }
   int GetNeighborRank(int) const { return 0; }
   int GetGroupSize(int) const { return 1; }
@@ -237,10 +266,11 @@ public:
   int GetNRanks() const { return 1; }
   int GetMyRank() const { return 0; }
   GroupTopology & GetGroupTopo() { return _gt; }
-  void GetSharedDofs(int, Array<int> & d) const { d.SetSize(0); }
+  GroupCommunicator & GroupComm() { return _gc; }
 
 private:
   GroupTopology _gt;
+  GroupCommunicator _gc;
 };
 
 } // namespace mfem

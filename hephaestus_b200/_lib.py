@@ -47,6 +47,7 @@ SIGNATURES = {
     "hcurl_op_destroy": (None, [_P]),
     "hcurl_op_set_kernel": (C.c_int, [_P, C.c_int]),
     "hcurl_op_last_kernel": (C.c_int, [_P]),
+    "hcurl_op_set_tet_rules": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, _P, _P]),
     "hcurl_op_qpts_curl": (C.c_int, [_P]),
     "hcurl_op_qpts_mass": (C.c_int, [_P]),
     "hcurl_op_set_coefficients": (C.c_int, [_P, C.c_int, _P, _P, C.c_int]),

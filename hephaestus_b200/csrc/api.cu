@@ -161,7 +161,8 @@ __global__ void __launch_bounds__(RED_THREADS)
 pcg_update_kernel(const int64_t n, const double *__restrict__ gamma, const double *__restrict__ sdotp, const double *__restrict__ dinv,
                   const double *__restrict__ p, double *__restrict__ x, double *__restrict__ r, double *__restrict__ s,
                   double *partial, unsigned int *counter, double *out) {
-  const double alpha = *gamma / *sdotp;
+  // <s, p> = 0 (exact initial guess: r = p = 0): hypre breaks before the update and returns x unchanged
+  const double alpha = *sdotp != 0.0 ? *gamma / *sdotp : 0.0;
   double acc0 = 0.0, acc1 = 0.0;
   const int64_t n2 = n >> 1;
   const double2 *p2 = reinterpret_cast<const double2 *>(p), *d2 = reinterpret_cast<const double2 *>(dinv);
@@ -242,7 +243,7 @@ __global__ void cheb_step_kernel(const int64_t n, const double c1, const double 
 // alpha = gamma / <s,p>; x += alpha p; r -= alpha s
 __global__ void pcg_xr_kernel(const int64_t n, const double *__restrict__ gamma, const double *__restrict__ sdotp, const double *__restrict__ p,
                               const double *__restrict__ s, double *__restrict__ x, double *__restrict__ r) {
-  const double alpha = *gamma / *sdotp;
+  const double alpha = *sdotp != 0.0 ? *gamma / *sdotp : 0.0;  // breakdown: leave x, r unchanged (as hypre does)
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     x[i] += alpha * p[i];
     r[i] -= alpha * s[i];
@@ -352,6 +353,13 @@ hcurl_ctx *hcurl_ctx_create(int device, const void *uid, int rank, int nranks) {
     return nullptr;
   }
   if (device < 0 || device >= ndev) { set_error("invalid device %d (have %d)", device, ndev); return nullptr; }
+  // one process per GPU: constant-memory tables and cached device buffers of the kernels are per process
+  static int first_device = -1;
+  if (first_device >= 0 && device != first_device) {
+    set_error("this process already uses CUDA device %d: one process per GPU (requested %d)", first_device, device);
+    return nullptr;
+  }
+  first_device = device;
   HC_CUDA_NULL(cudaSetDevice(device));
   hcurl_ctx *ctx = new hcurl_ctx;
   ctx->device = device; ctx->rank = rank; ctx->nranks = nranks < 1 ? 1 : nranks;
@@ -435,7 +443,22 @@ hcurl_space *hcurl_space_create(hcurl_ctx *ctx, int geom, int geom_order, int or
   sp->n_elem_pad = (n_elem + 31) / 32 * 32;
   // ---- parallel layout
   std::vector<int32_t> l2e;
+  if (n_nbr > 0 && (ctx->nranks <= 1 || !ldof_ltdof || !nbr_rank || !own_off || !ghost_off)) {
+    set_error("neighbour lists given (n_nbr = %d) but the context has one rank / the parallel layout is incomplete", n_nbr);
+    delete sp;
+    return nullptr;
+  }
   if (ldof_ltdof) {
+    for (int q = 0; q < n_nbr; q++)
+      if (nbr_rank[q] < 0 || nbr_rank[q] >= ctx->nranks || nbr_rank[q] == ctx->rank || own_off[q + 1] < own_off[q] || ghost_off[q + 1] < ghost_off[q]) {
+        set_error("bad neighbour entry %d (rank %d of %d)", q, nbr_rank[q], ctx->nranks);
+        delete sp;
+        return nullptr;
+      }
+    for (int32_t i = 0; n_nbr > 0 && i < own_off[n_nbr]; i++)
+      if (own_ldof[i] < 0 || own_ldof[i] >= n_ldof) { set_error("own_ldof[%d] out of range", i); delete sp; return nullptr; }
+    for (int32_t i = 0; n_nbr > 0 && i < ghost_off[n_nbr]; i++)
+      if (ghost_ldof[i] < 0 || ghost_ldof[i] >= n_ldof) { set_error("ghost_ldof[%d] out of range", i); delete sp; return nullptr; }
     sp->n_tdof = n_tdof;
     sp->n_nbr = n_nbr;
     sp->nbr_rank.assign(nbr_rank, nbr_rank + n_nbr);
@@ -452,14 +475,14 @@ hcurl_space *hcurl_space_create(hcurl_ctx *ctx, int geom, int geom_order, int or
       std::vector<int32_t> own_ext(n_own);
       for (int32_t i = 0; i < n_own; i++) own_ext[i] = l2e[own_ldof[i]];
       HC_CUDA_NULL(cudaMalloc(&sp->d_own_idx, sizeof(int32_t) * n_own));
-      HC_CUDA_NULL(cudaMemcpy(sp->d_own_idx, own_ext.data(), sizeof(int32_t) * n_own, cudaMemcpyHostToDevice));
+      HC_CUDA_NULL(h2d_sync(ctx, sp->d_own_idx, own_ext.data(), sizeof(int32_t) * n_own));
       sp->own_ext = own_ext;
       HC_CUDA_NULL(cudaMalloc(&sp->d_sendbuf, sizeof(double) * n_own));
       HC_CUDA_NULL(cudaMalloc(&sp->d_recvbuf, sizeof(double) * n_own));
     }
     if (ghost_sign && sp->n_ghost > 0) {
       HC_CUDA_NULL(cudaMalloc(&sp->d_ghost_sign, sp->n_ghost));
-      HC_CUDA_NULL(cudaMemcpy(sp->d_ghost_sign, ghost_sign, sp->n_ghost, cudaMemcpyHostToDevice));
+      HC_CUDA_NULL(h2d_sync(ctx, sp->d_ghost_sign, ghost_sign, sp->n_ghost));
     }
     sp->ldof_to_ext = l2e;
   } else {
@@ -471,19 +494,19 @@ hcurl_space *hcurl_space_create(hcurl_ctx *ctx, int geom, int geom_order, int or
   if (hex && geom_order == 1) {
     double *tmp = nullptr;
     HC_CUDA_NULL(cudaMalloc(&tmp, sizeof(double) * nxyz));
-    HC_CUDA_NULL(cudaMemcpy(tmp, elem_xyz, sizeof(double) * nxyz, cudaMemcpyHostToDevice));
+    HC_CUDA_NULL(h2d_sync(ctx, tmp, elem_xyz, sizeof(double) * nxyz));
     permute_xyz_kernel<<<(unsigned)((nxyz + 255) / 256), 256, 0, ctx->stream>>>(n_elem, tmp, sp->d_xyz);
     HC_CUDA_NULL(cudaStreamSynchronize(ctx->stream));
     cudaFree(tmp);
   } else {
-    HC_CUDA_NULL(cudaMemcpy(sp->d_xyz, elem_xyz, sizeof(double) * nxyz, cudaMemcpyHostToDevice));
+    HC_CUDA_NULL(h2d_sync(ctx, sp->d_xyz, elem_xyz, sizeof(double) * nxyz));
   }
   // ---- element -> dof map
   {
     const size_t nmap = (size_t)n_elem * sp->nd;
     int32_t *d_ldof = nullptr;
     HC_CUDA_NULL(cudaMalloc(&d_ldof, sizeof(int32_t) * nmap));
-    HC_CUDA_NULL(cudaMemcpy(d_ldof, elem_ldof, sizeof(int32_t) * nmap, cudaMemcpyHostToDevice));
+    HC_CUDA_NULL(h2d_sync(ctx, d_ldof, elem_ldof, sizeof(int32_t) * nmap));
     int *d_loc = nullptr, *d_sgn = nullptr;
     int32_t *d_l2e = nullptr;
     if (hex) {
@@ -491,12 +514,12 @@ hcurl_space *hcurl_space_create(hcurl_ctx *ctx, int geom, int geom_order, int or
       nd_hex_dof_map(order, loc, sgn);
       HC_CUDA_NULL(cudaMalloc(&d_loc, sizeof(int) * sp->nd));
       HC_CUDA_NULL(cudaMalloc(&d_sgn, sizeof(int) * sp->nd));
-      HC_CUDA_NULL(cudaMemcpy(d_loc, loc.data(), sizeof(int) * sp->nd, cudaMemcpyHostToDevice));
-      HC_CUDA_NULL(cudaMemcpy(d_sgn, sgn.data(), sizeof(int) * sp->nd, cudaMemcpyHostToDevice));
+      HC_CUDA_NULL(h2d_sync(ctx, d_loc, loc.data(), sizeof(int) * sp->nd));
+      HC_CUDA_NULL(h2d_sync(ctx, d_sgn, sgn.data(), sizeof(int) * sp->nd));
     }
     if (!l2e.empty()) {
       HC_CUDA_NULL(cudaMalloc(&d_l2e, sizeof(int32_t) * n_ldof));
-      HC_CUDA_NULL(cudaMemcpy(d_l2e, l2e.data(), sizeof(int32_t) * n_ldof, cudaMemcpyHostToDevice));
+      HC_CUDA_NULL(h2d_sync(ctx, d_l2e, l2e.data(), sizeof(int32_t) * n_ldof));
     }
     const size_t nout = hex ? nmap : (size_t)sp->nd * sp->n_elem_pad;
     HC_CUDA_NULL(cudaMalloc(&sp->d_map, sizeof(uint32_t) * nout));
@@ -521,7 +544,7 @@ hcurl_space *hcurl_space_create(hcurl_ctx *ctx, int geom, int geom_order, int or
         tri_face_transform(order, lv, elem_face_base + (e * 4 + f) * 3, &R[((size_t)e * 4 + f) * sp->nf * sp->nf]);
       }
     HC_CUDA_NULL(cudaMalloc(&sp->d_faceR, sizeof(double) * R.size()));
-    HC_CUDA_NULL(cudaMemcpy(sp->d_faceR, R.data(), sizeof(double) * R.size(), cudaMemcpyHostToDevice));
+    HC_CUDA_NULL(h2d_sync(ctx, sp->d_faceR, R.data(), sizeof(double) * R.size()));
   }
   return sp;
 }
@@ -585,7 +608,7 @@ void hcurl_op_destroy(hcurl_op *op) {
   cudaStreamSynchronize(op->ctx->stream);
   cudaFree(op->d_alpha); cudaFree(op->d_beta); cudaFree(op->d_map_ess); cudaFree(op->d_ess);
   cudaFree(op->d_edata); cudaFree(op->d_mapT_ess); cudaFree(op->d_edataP); cudaFree(op->d_blob_ess);
-  cudaFree(op->d_emat); cudaFree(op->d_xin); cudaFree(op->d_yout); cudaFree(op->d_tmp);
+  cudaFree(op->d_emat); cudaFree(op->d_xin); cudaFree(op->d_yout); cudaFree(op->d_tmp); cudaFree(op->d_refq_k); cudaFree(op->d_refq_m);
   for (int i = 0; i < hcurl_op::RING; i++) { cudaEventDestroy(op->ring0[i]); cudaEventDestroy(op->ring1[i]); }
   delete op;
 }
@@ -596,13 +619,27 @@ int hcurl_op_set_kernel(hcurl_op *op, int which) {
   return 0;
 }
 int hcurl_op_last_kernel(const hcurl_op *op) { return op->last_kernel; }
-int hcurl_op_qpts_curl(const hcurl_op *op) { return op->sp->geom == HCURL_GEOM_HEX ? op->qc * op->qc * op->qc : 1; }
-int hcurl_op_qpts_mass(const hcurl_op *op) { return op->sp->geom == HCURL_GEOM_HEX ? op->qm * op->qm * op->qm : 1; }
+int hcurl_op_qpts_curl(const hcurl_op *op) { return op->sp->geom == HCURL_GEOM_HEX ? op->qc * op->qc * op->qc : op->tet_nqc; }
+int hcurl_op_qpts_mass(const hcurl_op *op) { return op->sp->geom == HCURL_GEOM_HEX ? op->qm * op->qm * op->qm : op->tet_nqm; }
+
+int hcurl_op_set_tet_rules(hcurl_op *op, int nq_curl, const double *pts_curl, const double *w_curl, int nq_mass,
+                           const double *pts_mass, const double *w_mass) {
+  if (!op || op->sp->geom != HCURL_GEOM_TET) { set_error("hcurl_op_set_tet_rules: not a tet operator"); return 1; }
+  if (nq_curl < 1 || nq_mass < 1 || nq_curl > 64 || nq_mass > 64 || !pts_curl || !w_curl || !pts_mass || !w_mass) {
+    set_error("hcurl_op_set_tet_rules: rules of 1..64 points needed");
+    return 1;
+  }
+  HC_CUDA(cudaSetDevice(op->ctx->device));
+  return tet_set_rules(op, nq_curl, pts_curl, w_curl, nq_mass, pts_mass, w_mass);
+}
 
 int hcurl_op_set_coefficients(hcurl_op *op, int layout, const double *alpha, const double *beta, int where) {
   hcurl_space *sp = op->sp;
   HC_CUDA(cudaSetDevice(op->ctx->device));
-  if (layout == HCURL_COEF_PER_QPT && sp->geom != HCURL_GEOM_HEX) { set_error("PER_QPT coefficients are hex-only"); return 1; }
+  if (layout == HCURL_COEF_PER_QPT && sp->geom != HCURL_GEOM_HEX && (op->tet_nqc < 1 || op->tet_nqm < 1)) {
+    set_error("PER_QPT coefficients on tets need the quadrature rules first (hcurl_op_set_tet_rules)");
+    return 1;
+  }
   if (layout != HCURL_COEF_PER_ELEM && layout != HCURL_COEF_PER_QPT) { set_error("bad coefficient layout %d", layout); return 1; }
   op->coef_layout = layout;
   const int64_t na = sp->n_elem * (layout == HCURL_COEF_PER_QPT ? hcurl_op_qpts_curl(op) : 1);

@@ -232,9 +232,9 @@ const int TE[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
 const int TF[4][3] = {{1, 2, 3}, {0, 3, 2}, {0, 1, 3}, {0, 2, 1}};
 }  // namespace
 
-void build_tet_ref(int p, TetRef &r) {
+// shape functions and curls of ND_p on the reference tet as polynomials (MFEM's nodal basis: see below)
+static void tet_shape_polys(int p, std::vector<VecPoly> &shp, std::vector<VecPoly> &crl) {
   const int nd = nd_tet_ndof(p);
-  r.p = p; r.nd = nd; r.npk = nd * (nd + 1) / 2;
   // raw basis of ND_p: P_{p-1}^3 (+) m*(y,-x,0), m*(z,0,-x), [a==0] m*(0,z,-y), m hom. deg p-1
   std::vector<VecPoly> raw;
   for (int deg = 0; deg < p; deg++)
@@ -307,7 +307,8 @@ void build_tet_ref(int p, TetRef &r) {
     }
   }
   // shape_m = sum_n Vi[n][m] raw_n
-  std::vector<VecPoly> shp(nd), crl(nd);
+  shp.assign(nd, VecPoly());
+  crl.assign(nd, VecPoly());
   for (int m = 0; m < nd; m++) {
     for (int n = 0; n < nd; n++)
       for (int d = 0; d < 3; d++) shp[m].v[d].axpy(Vi[n * nd + m], raw[n].v[d]);
@@ -318,6 +319,13 @@ void build_tet_ref(int p, TetRef &r) {
       crl[m].v[d].axpy(-1.0, shp[m].v[d1].deriv(d2));
     }
   }
+}
+
+void build_tet_ref(int p, TetRef &r) {
+  const int nd = nd_tet_ndof(p);
+  r.p = p; r.nd = nd; r.npk = nd * (nd + 1) / 2;
+  std::vector<VecPoly> shp, crl;
+  tet_shape_polys(p, shp, crl);
   r.Mref.assign(6 * r.npk, 0.0);
   r.Kref.assign(6 * r.npk, 0.0);
   int pr = 0;
@@ -333,6 +341,33 @@ void build_tet_ref(int p, TetRef &r) {
           r.Kref[pr * r.npk + k] = c;
         }
     }
+}
+
+// Quadrature-point reference matrices for coefficients that vary inside an element: for every point q of the caller's
+// rule (pts [nq][3], w [nq]) and every pair (a,b) as in TetRef, w_q * (f_i^a f_j^b [+ f_i^b f_j^a]) packed upper; f =
+// shape functions (curl = false) or their curls (curl = true).  out [nq][6][npk].
+void build_tet_ref_q(int p, bool curl, int nq, const double *pts, const double *w, std::vector<double> &out) {
+  const int nd = nd_tet_ndof(p), npk = nd * (nd + 1) / 2;
+  std::vector<VecPoly> shp, crl;
+  tet_shape_polys(p, shp, crl);
+  const std::vector<VecPoly> &F = curl ? crl : shp;
+  out.assign((size_t)nq * 6 * npk, 0.0);
+  std::vector<double> val((size_t)nd * 3);
+  for (int q = 0; q < nq; q++) {
+    for (int i = 0; i < nd; i++)
+      for (int d = 0; d < 3; d++) val[(size_t)i * 3 + d] = F[i].v[d].eval(pts + 3 * q);
+    int pr = 0;
+    for (int a = 0; a < 3; a++)
+      for (int b = a; b < 3; b++, pr++) {
+        int k = 0;
+        for (int i = 0; i < nd; i++)
+          for (int j = i; j < nd; j++, k++) {
+            double m = val[(size_t)i * 3 + a] * val[(size_t)j * 3 + b];
+            if (a != b) m += val[(size_t)i * 3 + b] * val[(size_t)j * 3 + a];
+            out[((size_t)q * 6 + pr) * npk + k] = w[q] * m;
+          }
+      }
+  }
 }
 
 void tri_face_transform(int p, const int32_t *lv, const int32_t *bv, double *R) {

@@ -68,6 +68,7 @@ struct TetRef {
   std::vector<double> Mref, Kref;
 };
 void build_tet_ref(int p, TetRef &r);
+void build_tet_ref_q(int p, bool curl, int nq, const double *pts, const double *w, std::vector<double> &out);
 // triangle-face dof transformation: R (nf x nf, row-major), x_local = R x_base
 void tri_face_transform(int p, const int32_t *local_verts, const int32_t *base_verts, double *R);
 
@@ -236,6 +237,9 @@ struct hcurl_op {
   // tets: packed element matrices [npk][n_elem_pad]
   double *d_emat = nullptr;
   bool emat_valid = false;
+  // tets, PER_QPT coefficients: the caller's quadrature rules (hcurl_op_set_tet_rules) as per-point reference matrices
+  int tet_nqc = 0, tet_nqm = 0;
+  double *d_refq_k = nullptr, *d_refq_m = nullptr;  // [nq][6][npk]
   // fast order-2 hex path: per-element affine data [12][n_pad], dof-major essential map
   double *d_edata = nullptr;
   bool edata_valid = false;
@@ -273,6 +277,12 @@ struct hcurl_pcg {
 };
 
 namespace hcurl {
+// Set-up upload from pageable host memory, ordered with the context's (non-blocking) stream: the kernels that consume
+// the buffer are launched on that stream, which has no implicit ordering with the legacy default stream.
+inline cudaError_t h2d_sync(hcurl_ctx *ctx, void *dst, const void *src, size_t bytes) {
+  cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+  return e != cudaSuccess ? e : cudaStreamSynchronize(ctx->stream);
+}
 // kernels / drivers implemented in the .cu files (all enqueue on ctx->stream)
 int hex_apply_launch(hcurl_op *op, const uint32_t *d_map, const double *d_x, double *d_y, double scale);
 int hex_diag_launch(hcurl_op *op, double *d_diag);
@@ -293,6 +303,7 @@ size_t patch_smem_bytes(int unit, int FE, uint32_t d_cap, uint32_t l_cap, uint32
 int hex_fast_prepare_space(hcurl_space *sp);
 int hex_all_affine(hcurl_space *sp, bool *all_affine);
 int tet_build_emat(hcurl_op *op);
+int tet_set_rules(hcurl_op *op, int nqc, const double *pc, const double *wc, int nqm, const double *pm, const double *wm);
 int tet_apply_launch(hcurl_op *op, const uint32_t *d_map, const double *d_x, double *d_y, double scale);
 int tet_diag_launch(hcurl_op *op, double *d_diag);
 // exchange (comm.cu): broadcast owner->ghost on x_ext, reduce ghost->owner on y_ext

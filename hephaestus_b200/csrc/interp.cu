@@ -119,8 +119,8 @@ hcurl_interp *hcurl_interp_create_geom(hcurl_ctx *ctx, int geom, int kind, int o
   else interp_matrix(order, it->a.D);
   if (!cuda_ok(cudaMalloc(&it->d_in, sizeof(uint32_t) * im.size()), "cudaMalloc") ||
       !cuda_ok(cudaMalloc(&it->d_out, sizeof(uint32_t) * omap.size()), "cudaMalloc") ||
-      !cuda_ok(cudaMemcpy(it->d_in, im.data(), sizeof(uint32_t) * im.size(), cudaMemcpyHostToDevice), "cudaMemcpy") ||
-      !cuda_ok(cudaMemcpy(it->d_out, omap.data(), sizeof(uint32_t) * omap.size(), cudaMemcpyHostToDevice), "cudaMemcpy")) {
+      !cuda_ok(h2d_sync(ctx, it->d_in, im.data(), sizeof(uint32_t) * im.size()), "cudaMemcpy") ||
+      !cuda_ok(h2d_sync(ctx, it->d_out, omap.data(), sizeof(uint32_t) * omap.size()), "cudaMemcpy")) {
     cudaFree(it->d_in); cudaFree(it->d_out);
     delete it;
     return nullptr;

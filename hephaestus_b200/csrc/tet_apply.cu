@@ -86,11 +86,14 @@ __device__ __forceinline__ int packed_index(int nd, int i, int j) {  // i <= j
 }
 
 // one thread per (packed entry, element); ref = [Mref(6*npk) | Kref(6*npk)]
+// nqc / nqm > 0: coefficients per quadrature point of the caller's rules (alpha [n_elem][nqc], beta [n_elem][nqm]) with
+// the per-point reference matrices refq_k / refq_m [nq][6][npk] instead of the exactly integrated ones
 __global__ void tet_emat_kernel(const int p, const int nd, const int npk, const int nf, const int64_t n_elem,
                                 const int64_t n_pad, const double *__restrict__ xyz,
                                 const double *__restrict__ ref, const double *__restrict__ faceR,
                                 const double *__restrict__ alpha, const double *__restrict__ beta,
-                                double *__restrict__ emat) {
+                                double *__restrict__ emat, const int nqc, const int nqm,
+                                const double *__restrict__ refq_k, const double *__restrict__ refq_m) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int k = blockIdx.y;
   if (e >= n_elem) return;
@@ -109,7 +112,8 @@ __global__ void tet_emat_kernel(const int p, const int nd, const int npk, const 
   const double det = J[0][0] * a0[0] + J[1][0] * a0[1] + J[2][0] * a0[2];
   const double *ar[3] = {a0, a1, a2};
   double gm[6], gk[6];
-  const double al = alpha ? alpha[e] : 0.0, be = beta ? beta[e] : 0.0;
+  const bool perq = nqc > 0 || nqm > 0;
+  const double al = perq ? 1.0 : (alpha ? alpha[e] : 0.0), be = perq ? 1.0 : (beta ? beta[e] : 0.0);
   int s = 0;
   for (int a = 0; a < 3; a++)
     for (int b = a; b < 3; b++, s++) {
@@ -121,7 +125,22 @@ __global__ void tet_emat_kernel(const int p, const int nd, const int npk, const 
     if (r > c) { int t = r; r = c; c = t; }
     const int kk = packed_index(nd, r, c);
     double v = 0.0;
-    for (int q = 0; q < 6; q++) v += gm[q] * ref[q * npk + kk] + gk[q] * ref[(6 + q) * npk + kk];
+    if (!perq) {
+      for (int q = 0; q < 6; q++) v += gm[q] * ref[q * npk + kk] + gk[q] * ref[(6 + q) * npk + kk];
+      return v;
+    }
+    if (beta)
+      for (int q = 0; q < nqm; q++) {
+        double t = 0.0;
+        for (int s2 = 0; s2 < 6; s2++) t += gm[s2] * refq_m[((int64_t)q * 6 + s2) * npk + kk];
+        v += beta[e * nqm + q] * t;
+      }
+    if (alpha)
+      for (int q = 0; q < nqc; q++) {
+        double t = 0.0;
+        for (int s2 = 0; s2 < 6; s2++) t += gk[s2] * refq_k[((int64_t)q * 6 + s2) * npk + kk];
+        v += alpha[e * nqc + q] * t;
+      }
     return v;
   };
   const int fbeg = 6 * p, fend = 6 * p + 4 * nf;
@@ -173,15 +192,34 @@ int tet_build_emat(hcurl_op *op) {
     std::vector<double> h(12 * npk);
     for (int i = 0; i < 6 * npk; i++) { h[i] = r.Mref[i]; h[6 * npk + i] = r.Kref[i]; }
     HC_CUDA(cudaMalloc(&g_ref_dev[p], sizeof(double) * h.size()));
-    HC_CUDA(cudaMemcpy(g_ref_dev[p], h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice));
+    HC_CUDA(h2d_sync(op->ctx, g_ref_dev[p], h.data(), sizeof(double) * h.size()));
   }
   if (!op->d_emat) HC_CUDA(cudaMalloc(&op->d_emat, sizeof(double) * (size_t)npk * sp->n_elem_pad));
   dim3 grid((unsigned)((sp->n_elem + 127) / 128), npk);
   tet_emat_kernel<<<grid, 128, 0, op->ctx->stream>>>(p, nd, npk, sp->nf, sp->n_elem, sp->n_elem_pad, sp->d_xyz, g_ref_dev[p],
                                                     sp->d_faceR, op->has_alpha ? op->d_alpha : nullptr,
-                                                    op->has_beta ? op->d_beta : nullptr, op->d_emat);
+                                                    op->has_beta ? op->d_beta : nullptr, op->d_emat,
+                                                    op->coef_layout == HCURL_COEF_PER_QPT ? op->tet_nqc : 0,
+                                                    op->coef_layout == HCURL_COEF_PER_QPT ? op->tet_nqm : 0, op->d_refq_k, op->d_refq_m);
   HC_CUDA(cudaGetLastError());
   op->emat_valid = true;
+  return 0;
+}
+
+// the caller's quadrature rules for PER_QPT coefficients (hcurl_op_set_tet_rules)
+int tet_set_rules(hcurl_op *op, int nqc, const double *pc, const double *wc, int nqm, const double *pm, const double *wm) {
+  const int p = op->sp->order;
+  std::vector<double> h;
+  cudaFree(op->d_refq_k); cudaFree(op->d_refq_m);
+  op->d_refq_k = op->d_refq_m = nullptr;
+  build_tet_ref_q(p, true, nqc, pc, wc, h);
+  HC_CUDA(cudaMalloc(&op->d_refq_k, sizeof(double) * (h.size() ? h.size() : 1)));
+  HC_CUDA(h2d_sync(op->ctx, op->d_refq_k, h.data(), sizeof(double) * h.size()));
+  build_tet_ref_q(p, false, nqm, pm, wm, h);
+  HC_CUDA(cudaMalloc(&op->d_refq_m, sizeof(double) * (h.size() ? h.size() : 1)));
+  HC_CUDA(h2d_sync(op->ctx, op->d_refq_m, h.data(), sizeof(double) * h.size()));
+  op->tet_nqc = nqc; op->tet_nqm = nqm;
+  op->emat_valid = false;
   return 0;
 }
 

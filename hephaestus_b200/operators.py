@@ -177,6 +177,14 @@ class HephGpuOperator:
 
     Width = Height
 
+    def SetTetRules(self, pts_curl, w_curl, pts_mass, w_mass):
+        """Tets, coefficients varying inside an element: the quadrature rules MFEM's integrators use (IntRules of order
+        2p-2 for the curl-curl term, 2p for the mass term), after which SetCoefficients(layout=PER_QPT) takes values per
+        rule point."""
+        pc, wc, pm, wm = (L.as_f64(np.ascontiguousarray(v)) for v in (pts_curl, w_curl, pts_mass, w_mass))
+        L.check(L.lib().hcurl_op_set_tet_rules(self.h, len(wc), L.ptr(pc), L.ptr(wc), len(wm), L.ptr(pm), L.ptr(wm)), "hcurl_op_set_tet_rules")
+        self.qpts_curl, self.qpts_mass = len(wc), len(wm)
+
     def SetCoefficients(self, alpha=None, beta=None, layout=L.PER_ELEM):
         a = L.as_f64(alpha) if alpha is not None else None
         b = L.as_f64(beta) if beta is not None else None

@@ -40,9 +40,8 @@ typedef struct hcurl_interp hcurl_interp;
 
 /* element geometry kinds */
 enum { HCURL_GEOM_HEX = 0, HCURL_GEOM_TET = 1 };
-/* coefficient layouts: one value per element, or one per quadrature point
- * (x-fastest tensor order of the operator's rule; curl rule for alpha, mass
- * rule for beta).  PER_QPT is hex-only. */
+/* coefficient layouts: one value per element, or one per quadrature point (curl rule for alpha, mass rule for beta;
+ * hexes: x-fastest tensor order of the operator's rule; tets: the caller's rules, hcurl_op_set_tet_rules). */
 enum { HCURL_COEF_PER_ELEM = 0, HCURL_COEF_PER_QPT = 1 };
 /* preconditioners: HCURL_PC_JACOBI reproduces mfem::HypreDiagScale; HCURL_PC_CHEBYSHEV is a Jacobi-scaled Chebyshev
  * polynomial (no reference counterpart: the device-side stand-in for the AMS preconditioner, which is out of scope) */
@@ -159,6 +158,15 @@ void hcurl_op_destroy(hcurl_op *op);
 int hcurl_op_set_kernel(hcurl_op *op, int which);
 /* which kernel the most recent apply launched (1, 2, 3 as above; 0 = none yet) */
 int hcurl_op_last_kernel(const hcurl_op *op);
+/* Tets with coefficients that vary inside an element (mfem::FunctionCoefficient, as in the reference's MMS tests,
+ * /root/reference/test/integration/test_aform_source.cpp:32-37): the caller hands over the quadrature rules MFEM's
+ * integrators use on the element -- IntRules.Get(Geometry::TETRAHEDRON, 2p-2) for CurlCurlIntegrator, order 2p for
+ * VectorFEMassIntegrator -- so that MFEM's simplex tables are not restated in the library; then PER_QPT
+ * values alpha [n_elem][nq_curl], beta [n_elem][nq_mass] through hcurl_op_set_coefficients.  pts [nq][3] reference
+ * coordinates, w [nq] weights (sum 1/6).  The element matrices are rebuilt on the device from per-point reference
+ * matrices whenever the coefficients change. */
+int hcurl_op_set_tet_rules(hcurl_op *op, int nq_curl, const double *pts_curl, const double *w_curl, int nq_mass,
+                           const double *pts_mass, const double *w_mass);
 /* Number of coefficient values expected per element for PER_QPT layout. */
 int hcurl_op_qpts_curl(const hcurl_op *op);
 int hcurl_op_qpts_mass(const hcurl_op *op);

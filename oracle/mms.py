@@ -16,7 +16,7 @@ test_hform_source.cpp:20-50,143-220 is the same with a variable sigma):
 """
 import numpy as np
 
-from .assemble import hex8_jacobians, hex_tensor_rule, tet_jacobians
+from .assemble import hex8_jacobians, hex27_jacobians, hex27_ref_coords, hex_tensor_rule, tet_jacobians
 from .mesh import Mesh
 from .quadrature import tet_rule
 
@@ -28,9 +28,11 @@ def _rule_and_jac(space, degree):
         pts, wts = tet_rule(degree)
         J, xq = tet_jacobians(X, pts)
     else:
-        assert mesh.geom_nodes is None
         pts, wts = hex_tensor_rule(degree // 2 + 1)
-        J, xq = hex8_jacobians(X, pts)
+        if mesh.geom_nodes is not None:  # HEX27 geometry (cylinder-hex-q2.gen)
+            J, xq = hex27_jacobians(mesh.geom_nodes, hex27_ref_coords(mesh.geom_nodes), pts)
+        else:
+            J, xq = hex8_jacobians(X, pts)
     return pts, wts, J, xq
 
 

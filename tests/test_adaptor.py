@@ -126,3 +126,82 @@ def test_adaptor_end_to_end(driver, tmp_path, kind, n, p, q):
     assert info[2] == 1.0 and conv_o
     assert abs(info[0] - it_o) <= 2
     assert rel_err(sol, xo) < 1e-6
+
+
+# ---- the GPU equation system (adaptor/gpu_curlcurl_equation_system.hpp) through the reference's per-step call sequence --------
+@pytest.fixture(scope="module")
+def timestep_driver(lib_built, tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("adaptor_ts") / "timestep_driver")
+    libdir = os.path.dirname(L.LIB_PATH)
+    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "adaptor", "timestep_driver.cpp"), "-o", exe, "-L" + libdir, "-lhcurl_b200", "-Wl,-rpath," + libdir]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def _timestep_case(kind, n, p, nsteps, dt):
+    m, sp, mo, so = make_pair(kind, n, p, False)
+    nu_attr, sigma_attr = np.array([1.0, 2.0]), np.array([1.0, 1.0e3])
+    ess = sp.boundary_dofs()
+    rng = np.random.default_rng(21)
+    loads = rng.standard_normal((nsteps, sp.ndof))
+    kbc = np.zeros((nsteps, sp.ndof))
+    kbc[:, ess] = rng.standard_normal((nsteps, len(ess)))
+    return m, sp, mo, so, nu_attr, sigma_attr, ess, loads, kbc
+
+
+def _dump_timestep(path, kind, p, m, sp, nu_attr, sigma_attr, ess, loads, kbc, dt):
+    with open(path, "wb") as f:
+        _arr(f, [5 if kind == "hex" else 4, p, sp.nd, sp.ndof, loads.shape[0]], np.int64)
+        _arr(f, [dt], np.float64)
+        _arr(f, m.verts, np.float64)
+        _arr(f, m.elems, np.int32)
+        _arr(f, m.attr, np.int32)
+        _arr(f, sp.el_faces if kind == "tet" else [], np.int32)
+        _arr(f, sp.face_verts if kind == "tet" else [], np.int32)
+        _arr(f, sp.signed_elem_dofs(), np.int32)
+        _arr(f, nu_attr, np.float64)
+        _arr(f, sigma_attr, np.float64)
+        _arr(f, ess, np.int32)
+        _arr(f, loads, np.float64)
+        _arr(f, kbc, np.float64)
+
+
+def test_gpu_equation_system_compiles_and_fails_loudly_without_a_gpu(timestep_driver, tmp_path):
+    """the glue a maintainer adds compiles (-Wall -Werror) against the mock of the reference's EquationSystem hierarchy;
+    on a box without CUDA its first device call is an MFEM_ABORT -- no CPU fallback"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    m, sp, mo, so, nu, sg, ess, loads, kbc = _timestep_case("hex", 2, 1, 1, 0.05)
+    _dump_timestep(tmp_path / "in.bin", "hex", 1, m, sp, nu, sg, ess, loads, kbc, 0.05)
+    r = subprocess.run([timestep_driver, str(tmp_path / "in.bin"), str(tmp_path / "out.bin")], capture_output=True, text=True)
+    assert r.returncode == 1 and "MFEM abort" in r.stderr and "hcurl_ctx_create failed" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,n,p", [("hex", 4, 2), ("hex", 5, 1), ("tet", 3, 1), ("tet", 2, 2)])
+def test_time_steps_through_the_gpu_equation_system(timestep_driver, tmp_path, kind, n, p):
+    """three backward-Euler steps of the A-formulation driven exactly as
+    TimeDomainEquationSystemProblemOperator::ImplicitSolve drives them (SetTimeStep, UpdateEquationSystem, BuildJacobian,
+    NewtonSolver with the GPU PCG, RecoverFEMSolution) against the oracle: b_n = load_n - K(nu) u_n, A = M(sigma) + K(dt nu),
+    essential data on k = du/dt, u += dt k.  Affine hexes take the patch kernels (HCURL_QUAD_AUTO)."""
+    from oracle import assemble as oa, pcg as opcg
+    dt, nsteps = 0.05, 3
+    m, sp, mo, so, nu_attr, sg_attr, ess, loads, kbc = _timestep_case(kind, n, p, nsteps, dt)
+    _dump_timestep(tmp_path / "in.bin", kind, p, m, sp, nu_attr, sg_attr, ess, loads, kbc, dt)
+    r = subprocess.run([timestep_driver, str(tmp_path / "in.bin"), str(tmp_path / "out.bin")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    u_gpu, k_gpu, iters = _read(tmp_path / "out.bin")
+    nu, sg = nu_attr[mo.attr - 1], sg_attr[mo.attr - 1]
+    A = oa.assemble(so, dt * nu, sg)
+    K = oa.assemble(so, nu, None)
+    u = np.zeros(sp.ndof)
+    tol = float(np.float32(1e-12))
+    for s in range(nsteps):
+        Ac, B = oa.eliminate(A, ess, kbc[s], loads[s] - K @ u)
+        k, it_o, _, conv, _ = opcg.pcg(Ac, B, diag=Ac.diagonal(), rtol=tol, atol=0.0, max_iter=5000)
+        assert conv and abs(iters[s] - it_o) <= 2, (s, iters[s], it_o)
+        u += dt * k
+    assert rel_err(k_gpu, k) < 1e-8 and rel_err(u_gpu, u) < 1e-8
