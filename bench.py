@@ -391,7 +391,10 @@ def main():
                 "kernel": "tet batched packed-symmetric element-matrix kernel (order %d)" % p if args.geom == "tet" else
                 "hex element kernel (order %d; %s)" % (
                     p, {1: "generic sum-factorised", 2: "element-wise register-blocked",
-                        3: "patch pipeline: one thread per element, modal operator, persistent, zero-ahead watermark"}.get(op.LastKernel(), "?")),
+                        3: ("patch kernel, warp-specialised streams: 2 element warps (one thread per element, modal operator) + 4 dof warps per "
+                            "64-element patch, setmaxnreg, mbarrier rings, persistent, zero-ahead watermark"
+                            if p == 2 and os.environ.get("HCURL_PATCH_STREAM", "1") != "0" and os.environ.get("HCURL_PATCH_FE", "64") == "64" else
+                            "patch pipeline: one thread per element, modal operator, persistent, zero-ahead watermark")}.get(op.LastKernel(), "?")),
                 "kernel_ms": kern_ms, "kernel_launches_timed": kern_n, "algorithmic_bytes_per_launch": abytes,
                 "bytes_per_dof": abytes / n_tdof, "kernel_share_of_step": kern_ms / ms_step if ms_step > 0 else None,
                 "step_frac": abytes / (ms_step * 1e-3) / 1e9 / peak if ms_step > 0 else None,
@@ -429,7 +432,7 @@ def main():
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, n, n_dof_global),
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        "pcg": {"iters_per_s": 1e3 / pcg_iter_ms, "ms_per_iter": pcg_iter_ms, "iters": solver.num_iterations,
+        "pcg": {"iters_per_s": 1e3 / pcg_iter_ms if pcg_iter_ms > 0 else 0.0, "ms_per_iter": pcg_iter_ms, "iters": solver.num_iterations,
                 "precond": "jacobi", "gdofs": n_dof_global / (pcg_iter_ms * 1e-3) / 1e9,
                 "final_rel_res": solver.final_rel_res, "e2e": pcg_e2e},
         "setup_s": t_setup,

@@ -166,10 +166,15 @@ int hex_patch_build(hcurl_space *sp, const double *elem_xyz, const int32_t *elem
   const char *off = getenv("HCURL_NO_PATCH");
   if (off && off[0] == '1') return 0;
   const bool p2 = sp->order == 2;
-  // elements per patch.  Order 2: one warp per patch (the kernel's occupancy is bounded by shared memory per patch, and
-  // 32- / 64-element patches measured within 2 % of each other); order 1: 128 (fastest of 64 / 128 / 256)
-  int FE = p2 ? 32 : 128;
-  if (const char *s = getenv("HCURL_PATCH_FE")) FE = atoi(s);
+  // Elements per patch and kernel.  Order 2: 64-element patches through the warp-specialised kernel (patch_stream.h)
+  // when its two streams fit into one CTA's shared memory, else 32-element patches through the single-warp pipeline
+  // (patch_pipeline.h; irregular meshes have longer unit lists).  Order 1: 128 (fastest of 64 / 128 / 256).
+  // HCURL_PATCH_FE fixes the patch size, HCURL_PATCH_STREAM=0 the single-warp pipeline (measurements, tests).
+  int FE = p2 ? 64 : 128;
+  bool fe_fixed = false, want_stream = p2;
+  if (const char *s = getenv("HCURL_PATCH_STREAM")) want_stream = p2 && atoi(s) != 0;
+  if (p2 && !want_stream) FE = 32;
+  if (const char *s = getenv("HCURL_PATCH_FE")) { FE = atoi(s); fe_fixed = true; }
   if (p2 ? (FE != 32 && FE != 64) : (FE != 32 && FE != 64 && FE != 128 && FE != 256)) {
     set_error(p2 ? "HCURL_PATCH_FE must be 32 or 64 for order 2" : "HCURL_PATCH_FE must be 32, 64, 128 or 256 for order 1");
     return 1;
@@ -201,6 +206,17 @@ int hex_patch_build(hcurl_space *sp, const double *elem_xyz, const int32_t *elem
   }
   PatchHost H;
   if (build_patches(nu, ne, FE, FE + 1, unit, n_units, cen.data(), code.data(), xch.empty() ? nullptr : xch.data(), H)) return 1;
+  if (p2 && FE == 64 && want_stream) {
+    int optin = 0;
+    HC_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, sp->ctx->device));
+    const size_t need = 2 * patch_stream_smem_bytes(64, H.max_d_words * 4, H.max_l_words * 4, H.max_t_words * 4, (H.max_dofs * 16u + 15u) & ~15u) + 1024;
+    P.stream = sp->ctx->coop_ok && H.max_dofs <= 8191 && need <= (size_t)optin;
+    if (!P.stream && !fe_fixed) {  // the single-warp pipeline is fastest with 32-element patches
+      FE = 32;
+      H = PatchHost();
+      if (build_patches(nu, ne, FE, FE + 1, unit, n_units, cen.data(), code.data(), xch.empty() ? nullptr : xch.data(), H)) return 1;
+    }
+  }
   if (H.max_dofs > 8191) return 0;  // 13-bit staging positions
   P.FE = FE; P.unit = unit; P.stride = H.stride; P.n_patch = H.n_patch; P.n_boundary = H.n_boundary;
   P.blob_words = (int64_t)H.blob.size(); P.max_d_words = H.max_d_words; P.max_l_words = H.max_l_words; P.max_t_words = H.max_t_words;

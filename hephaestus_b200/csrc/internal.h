@@ -113,6 +113,7 @@ struct PatchSet {  // device copy
   int64_t blob_words = 0;
   uint32_t max_d_words = 0, max_l_words = 0, max_t_words = 0, max_dofs = 0;
   bool general_orient = false;   // order 2: some element slot pair is flagged other than "reversed line" (all three bits)
+  bool stream = false;           // order 2, 64-element patches: the warp-specialised kernel (patch_stream.h)
   uint8_t swz_row[27] = {0}, swz_grp[16] = {0};
   uint32_t *d_own_off = nullptr, *d_own_idx = nullptr;  // owned shared units per patch (zeroed ahead of the sums)
   // split-phase watermark of the zeroing (patch_pipeline.h): one arrival counter per batch of pipeline iterations,
@@ -187,6 +188,7 @@ struct hcurl_ctx {
   size_t kattr_smem[N_KVAR] = {0};
   int kattr_per_sm[N_KVAR] = {0};
   bool coop_ok = false;
+  int max_smem_optin = -1;  // cudaDevAttrMaxSharedMemoryPerBlockOptin, queried on first use
 };
 
 struct hcurl_space {
@@ -300,6 +302,7 @@ int hex_patch_flag_essential(hcurl_op *op, const double *d_flag);
 // the patch kernels (hex_patch_kernels.cu): device environment of patch_pipeline.h, cooperative launch
 int hex_patch_kernel_launch(hcurl_op *op, const hcurl::PatchArgs &a, bool accumulate);
 size_t patch_smem_bytes(int unit, int FE, uint32_t d_cap, uint32_t l_cap, uint32_t t_cap, uint32_t xs_cap);
+size_t patch_stream_smem_bytes(int FE, uint32_t d_cap, uint32_t l_cap, uint32_t t_cap, uint32_t xs_cap);
 int hex_fast_prepare_space(hcurl_space *sp);
 int hex_all_affine(hcurl_space *sp, bool *all_affine);
 int tet_build_emat(hcurl_op *op);

@@ -62,6 +62,11 @@ namespace hcurl {
 #ifndef HCURL_SUMS_UNROLL
 #define HCURL_SUMS_UNROLL 1  // measured: 0.504 ms against 0.546 with 2 (instruction count and code size beat loads in flight)
 #endif
+#ifdef HCURL_PHASE_PROFILE  // diagnostic builds only (scripts/phase_profile.sh): clock64 deltas of thread 0 per pipeline phase
+#define HCURL_MARK(k) env.mark(k)
+#else
+#define HCURL_MARK(k) ((void)0)
+#endif
 #define HCURL_PRAGMA_(x) _Pragma(#x)
 #define HCURL_UNROLL(n) HCURL_PRAGMA_(unroll n)
 
@@ -251,12 +256,22 @@ HCURL_BODY void patch_pipeline(Env &env, const PatchArgs &a) {
   constexpr int ZB = HCURL_ZERO_BATCH, ZU = 6;  // iterations per batch; zero indices a thread keeps in flight across the pull
   const int NB = (int)(((a.n_patch - a.k_begin + kstep - 1) / kstep + ZB - 1) / ZB);
   T *yu = reinterpret_cast<T *>(a.y);
-  auto zero_patch = [&](int j) {  // plain stores of zeros to the shared units my patch of iteration j owns (prologue)
-    if (j >= n_it) return;
-    const int64_t p = k0 + (int64_t)j * kstep;
-    const uint32_t u1 = env.ldg(a.own_off + p + 1);
-    for (uint32_t u = env.ldg(a.own_off + p) + tid; u < u1; u += NT) yu[env.ldg(a.own_idx + u)] = Unit::zero();
-  };
+  // prologue: the extents of the 2 ZB owned lists are loaded by 4 ZB threads at once and handed over through shared memory
+  // (EY is still unused), so that the index loads of all patches are independent
+  auto zero_prologue = [&]() {
+    constexpr int NJ = 2 * ZB;
+    uint32_t *ext = reinterpret_cast<uint32_t *>(EY);  // [2 NJ]
+    for (int j = tid; j < 2 * NJ; j += NT) {
+      const int jj = j >> 1;
+      ext[j] = jj < n_it ? env.ldg(a.own_off + k0 + (int64_t)jj * kstep + (j & 1)) : 0u;
+    }
+    env.sync();
+#pragma unroll 4
+    for (int j = 0; j < NJ; j++) {
+      const uint32_t u1 = ext[2 * j + 1];
+      for (uint32_t u = ext[2 * j] + tid; u < u1; u += NT) yu[env.ldg(a.own_idx + u)] = Unit::zero();
+    }
+  };  // (EY is first written behind the barrier that follows)
   // extent of the owned list zeroed in the coming iteration, loaded an iteration ahead (the index loads depend on it)
   uint32_t zn0 = 0, zn1 = 0;
   if (!ACC && 2 * ZB < n_it) { zn0 = env.ldg(a.own_off + k0 + (int64_t)(2 * ZB) * kstep); zn1 = env.ldg(a.own_off + k0 + (int64_t)(2 * ZB) * kstep + 1); }
@@ -273,8 +288,7 @@ HCURL_BODY void patch_pipeline(Env &env, const PatchArgs &a) {
   env.sync();  // mbarriers initialised
   env.bulk_wait(0, 0);
   gather(0);
-  if (!ACC)
-    for (int j = 0; j < 2 * ZB; j++) zero_patch(j);
+  if (!ACC) zero_prologue();
   env.gather_wait();
   env.sync();  // Xs of the first patch complete and visible; the zeros of batches 0, 1 issued by every thread
   if (!ACC) {
@@ -288,12 +302,7 @@ HCURL_BODY void patch_pipeline(Env &env, const PatchArgs &a) {
     const uint32_t *B = reinterpret_cast<const uint32_t *>(bufD + (size_t)b * a.d_cap_bytes);
     const uint32_t *Lw = reinterpret_cast<const uint32_t *>(bufL);
     const uint16_t *lidx = reinterpret_cast<const uint16_t *>(bufT) + el;
-    // thread 0: extents of the parts requested during this iteration (loaded now, used an operator later)
-    uint32_t nL = 0, nT = 0, nE = 0, qD = 0, qL = 0;
-    if (tid == 0) {
-      if (it + 1 < n_it) { nL = env.ldg(a.part_off + 2 * (k + kstep)); nT = env.ldg(a.part_off + 2 * (k + kstep) + 1); nE = env.ldg(a.blob_off + k + kstep + 1); }
-      if (it + 2 < n_it) { qD = env.ldg(a.blob_off + k + 2 * kstep); qL = env.ldg(a.part_off + 2 * (k + 2 * kstep)); }
-    }
+    uint32_t nL = 0, nT = 0, nE = 0, qD = 0, qL = 0;  // thread 0: extents of the parts requested during this iteration
     // zeroing ahead: the owned shared units of my patch of iteration it + 2 ZB (indices loaded now, zeros stored after the pull)
     uint32_t zu[ZU];
     const uint32_t z0 = zn0 + tid, z1 = zn1;
@@ -304,16 +313,17 @@ HCURL_BODY void patch_pipeline(Env &env, const PatchArgs &a) {
       if (it + 1 + 2 * ZB < n_it) { const int64_t pz = k + (int64_t)(2 * ZB + 1) * kstep; zn0 = env.ldg(a.own_off + pz); zn1 = env.ldg(a.own_off + pz + 1); }
     }
     Elem e;
+    HCURL_MARK(0);
     e.geometry(env, a, k, el);  // issued now, consumed by the operator
     const bool ok = (uint32_t)el < B[1];
     env.bulk_wait(3, it & 1);  // per-slot table of this patch
+    HCURL_MARK(1);
     if (ok) e.pull(env, a, Xs, lidx);
+    HCURL_MARK(2);
     env.sync();  // Xs free
-    // ---- the x gather of the next patch lands behind the element operator
-    if (it + 1 < n_it) {
-      env.bulk_wait(b ^ 1, ((it + 1) >> 1) & 1);
-      gather(b ^ 1);
-    }
+    HCURL_MARK(3);
+    // the release fence of an arrival waits for the thread's outstanding memory operations: fewer here than behind the
+    // gather (there it cost 2 % of the kernel)
     if (!ACC) {
       if (it % ZB == 0) {  // first iteration of batch m: arrive for batch m+1 (its zeros were written during batch m-1)
         const int m = it / ZB;
@@ -323,41 +333,66 @@ HCURL_BODY void patch_pipeline(Env &env, const PatchArgs &a) {
         }
         passed = false;
       }
+    }
+    // ---- the x gather of the next patch lands behind the element operator
+    if (it + 1 < n_it) {
+      env.bulk_wait(b ^ 1, ((it + 1) >> 1) & 1);
+      HCURL_MARK(4);
+      gather(b ^ 1);
+    }
+    HCURL_MARK(5);
+    if (!ACC) {
       if (z0 < z1) {
 #pragma unroll
         for (int i = 0; i < ZU; i++) if (zu[i] != 0xffffffffu) yu[zu[i]] = Unit::zero();
         for (uint32_t u = z0 + ZU * NT; u < z1; u += NT) yu[env.ldg(a.own_idx + u)] = Unit::zero();  // (patches owning more than ZU NT units)
       }
     }
+    HCURL_MARK(6);
     if (ok) {
       const double d = e.template apply<DOT>(env, a);
       if (DOT) dacc += d;
-      e.store(env, a, EY, lidx, el);
     }
+    HCURL_MARK(7);
+    // thread 0: extents of the parts requested below, loaded HERE (the operator's registers are free again, the result
+    // store hides the latency): at the top of the iteration these loads sat in front of the first use of zn0 and made it
+    // wait a full global-memory latency per iteration (shared scoreboard; 4 % of the kernel in the ncu source view)
+    if (tid == 0) {
+      if (it + 1 < n_it) { nL = env.ldg(a.part_off + 2 * (k + kstep)); nT = env.ldg(a.part_off + 2 * (k + kstep) + 1); nE = env.ldg(a.blob_off + k + kstep + 1); }
+      if (it + 2 < n_it) { qD = env.ldg(a.blob_off + k + 2 * kstep); qL = env.ldg(a.part_off + 2 * (k + 2 * kstep)); }
+    }
+    if (ok) e.store(env, a, EY, lidx, el);
+    HCURL_MARK(8);
     env.sync();  // element results visible; the per-slot table is free
     if (tid == 0 && it + 1 < n_it) request_t(nT, nE);
     env.bulk_wait(2, it & 1);  // slot-offset lists of this patch
+    HCURL_MARK(9);
     const bool essp = B[20] != 0;
     if (essp) {
       const double d = patch_unit_sums<Env, Unit, NT, ACC, DOT, 0, true>(env, a, B, Lw, Eb, tid);
       if (DOT) dacc += d;
     } else patch_unit_sums<Env, Unit, NT, ACC, false, 0, false>(env, a, B, Lw, Eb, tid);
+    HCURL_MARK(10);
     if (B[7] + B[8] + B[9] + B[2]) {
       if (!passed) {  // every CTA has arrived for this batch: all zeros under the shared units of its patches are visible
         for (unsigned ns = 0; (int32_t)(env.counter_acquire(a.count + it / ZB) - a.count_target) < 0; ns++) env.backoff(ns);
         passed = true;
       }
+      HCURL_MARK(11);
       if (essp) {
         const double d = patch_unit_sums<Env, Unit, NT, ACC, DOT, 1, true>(env, a, B, Lw, Eb, tid);
         if (DOT) dacc += d;
       } else patch_unit_sums<Env, Unit, NT, ACC, false, 1, false>(env, a, B, Lw, Eb, tid);
     }
+    HCURL_MARK(12);
     env.gather_wait();
+    HCURL_MARK(13);
     env.sync();  // buffer b, the lists and EY are free; Xs of the next patch complete and visible
     if (tid == 0) {
       if (it + 1 < n_it) request_l(nL, nT);
       if (it + 2 < n_it) request_d(b, qD, qL);
     }
+    HCURL_MARK(14);
   }
   if (!ACC && tid == 0) for (int m = arrived; m < NB; m++) env.arrive(a.count + m);  // (zeros of these batches: none of mine left)
   if (DOT) env.dot_finish(dacc, a, reinterpret_cast<double *>(EY));

@@ -24,10 +24,10 @@
 
 namespace emu {
 
-static constexpr int MAX_BAR = 4;
-enum { ERR_REARM = 1, ERR_ALIGN = 2, ERR_WAIT_UNARMED = 4, ERR_PARITY = 8, ERR_GATHER_LEFT = 16, ERR_BULK_LEFT = 32 };
+static constexpr int MAX_BAR = 7, MAX_FLAG = 8;
+enum { ERR_REARM = 1, ERR_ALIGN = 2, ERR_WAIT_UNARMED = 4, ERR_PARITY = 8, ERR_GATHER_LEFT = 16, ERR_BULK_LEFT = 32, ERR_FLAG_AHEAD = 64 };
 
-struct Pending { void *dst = nullptr; const void *src = nullptr; uint32_t bytes = 0; bool armed = false, landed = false; };
+struct Pending { void *dst = nullptr; const void *src = nullptr; uint32_t bytes = 0; bool armed = false, landed = false; int nwait = 0; };
 
 struct WarpShared {
   std::barrier<> bar;
@@ -44,10 +44,16 @@ struct CtaShared {
   uint32_t phase[MAX_BAR]; // completed requests per mbarrier, guarded by mu[b]
   int waiters[MAX_BAR];    // guarded by mu[b]
   std::vector<std::unique_ptr<WarpShared>> warp;
+  std::unique_ptr<std::barrier<>> group, elem;  // the dof group / the element warps of a stream (patch_stream.h): threads [n_elem, nt) / [0, n_elem)
+  int n_elem = 32;
+  std::atomic<uint32_t> flag[MAX_FLAG];   // signals so far
   double dot_sum = 0.0;
   std::vector<double> dot_part;
+  void set_stream(int ne, int nt) { n_elem = ne; elem.reset(new std::barrier<>(ne)); group.reset(new std::barrier<>(nt - ne)); }
   CtaShared(size_t bytes, int nt) : smem(bytes + 16, 0xAB), bar(nt), dot_part((size_t)nt, 0.0) {
     for (int b = 0; b < MAX_BAR; b++) { phase[b] = 0; waiters[b] = 0; }
+    for (auto &f : flag) f.store(0);
+
     for (int w = 0; w * 32 < nt; w++) warp.emplace_back(new WarpShared(std::min(32, nt - w * 32)));
   }
   unsigned char *base() {  // 16-byte aligned like dynamic shared memory
@@ -62,9 +68,11 @@ struct HostEnv {
   int nt_;
   int *error;
   const void *tables_;
-  struct Copy { void *dst; const void *src; int bytes; };
+  struct Copy { void *dst; const void *src; int bytes; unsigned grp; };
   std::vector<Copy> pend;  // my issued, not yet waited-for gathers
   unsigned vote_n = 0, shfl_n = 0;
+  bool wait_may_precede_request = false;  // set by role(): the stream program
+  unsigned commits = 0;  // committed gather groups
 
   int tid() const { return tid_; }
   int64_t block() const { return block_; }
@@ -73,20 +81,31 @@ struct HostEnv {
   void sync() { cta->bar.arrive_and_wait(); }
   template <class T> const T &tables() const { return *static_cast<const T *>(tables_); }
   void bulk_init(int) {}
-  void bulk_request(int b, void *dst, const void *src, uint32_t bytes) {
+  void bulk_request(int b, void *dst, const void *src, uint32_t bytes) { bulk_request_w(b, dst, src, bytes, nt_); }
+  void bulk_request_w(int b, void *dst, const void *src, uint32_t bytes, int nwait) {  // nwait threads will wait for this request
     std::lock_guard<std::mutex> lk(cta->mu[b]);
     if (cta->bulk[b].armed) *error |= ERR_REARM;  // request on an mbarrier whose previous phase has not been consumed by everyone
     if (bytes % 16 != 0 || ((uintptr_t)dst & 15) || ((uintptr_t)src & 15)) *error |= ERR_ALIGN;  // cp.async.bulk rules
     if (bytes) memset(dst, 0xCD, bytes);  // the copy may start at once: whoever still reads the old content gets garbage
     cta->bulk[b].dst = dst; cta->bulk[b].src = src; cta->bulk[b].bytes = bytes; cta->bulk[b].armed = true; cta->bulk[b].landed = false;
+    cta->bulk[b].nwait = nwait;
   }
   void bulk_wait(int b, uint32_t parity) {
+    // a wait may come before its request (warp-specialised streams: the requesting thread runs on its own); on the
+    // device the mbarrier phase is simply incomplete until then.  A wait whose request never comes hangs here as it would there.
+    for (unsigned tries = 0;; tries++) {
+      {
+        std::lock_guard<std::mutex> lk(cta->mu[b]);
+        if (cta->bulk[b].armed) break;
+      }
+      if (!wait_may_precede_request) { *error |= ERR_WAIT_UNARMED; return; }
+      std::this_thread::yield();
+    }
     std::lock_guard<std::mutex> lk(cta->mu[b]);
     Pending &q = cta->bulk[b];
-    if (!q.armed) { *error |= ERR_WAIT_UNARMED; return; }
     if ((cta->phase[b] & 1u) != parity) *error |= ERR_PARITY;          // waiting on the wrong phase of the mbarrier
     if (!q.landed) { if (q.bytes) memcpy(q.dst, q.src, q.bytes); q.landed = true; }  // ... and it completes as late as allowed
-    if (++cta->waiters[b] == nt_) {  // every thread of the CTA waits exactly once per request
+    if (++cta->waiters[b] == q.nwait) {  // every thread concerned waits exactly once per request
       cta->waiters[b] = 0;
       cta->phase[b]++;
       q.armed = false;
@@ -94,16 +113,24 @@ struct HostEnv {
   }
   void gather8(double *dst, const double *src) {
     *dst = std::numeric_limits<double>::quiet_NaN();  // in flight: readers that do not wait see garbage
-    pend.push_back({dst, src, 8});
+    pend.push_back({dst, src, 8, commits});
   }
   void gather16(double2 *dst, const double2 *src) {
     dst->x = dst->y = std::numeric_limits<double>::quiet_NaN();
-    pend.push_back({dst, src, 16});
+    pend.push_back({dst, src, 16, commits});
   }
-  void gather_commit() {}
+  void gather_commit() { commits++; }
   void gather_wait() {
     for (auto &p : pend) memcpy(p.dst, p.src, (size_t)p.bytes);
     pend.clear();
+  }
+  void gather_wait_prev() {  // cp.async.wait_group 1: every committed group but the latest has landed
+    std::vector<Copy> keep;
+    for (auto &p : pend) {
+      if (p.grp + 1 < commits) memcpy(p.dst, p.src, (size_t)p.bytes);
+      else keep.push_back(p);
+    }
+    pend.swap(keep);
   }
   void red_add(double *p, double v) {
     std::atomic_ref<double> r(*p);
@@ -125,6 +152,21 @@ struct HostEnv {
     W.bar.arrive_and_wait();
     return W.xch[n][(tid_ & 31) ^ lane_mask];
   }
+  // ---- warp-specialised streams (patch_stream.h)
+  void role(bool) { wait_may_precede_request = true; }
+  void group_sync() { cta->group->arrive_and_wait(); }
+  void warp_sync() { cta->warp[(size_t)(tid_ >> 5)]->bar.arrive_and_wait(); }
+  void elem_sync() { cta->elem->arrive_and_wait(); }
+  void flag_init(int f) { cta->flag[f].store(0); }
+  void flag_signal(int f) { cta->flag[f].fetch_add(1u, std::memory_order_release); }
+  void flag_wait(int f, uint32_t n) {
+    for (;;) {
+      const uint32_t c = cta->flag[f].load(std::memory_order_acquire);
+      if (c > n + 1) *error |= ERR_FLAG_AHEAD;  // the device's one-bit phase parity could not tell this signal from an older one
+      if (c >= n + 1) return;
+      std::this_thread::yield();
+    }
+  }
   void arrive(uint32_t *p) { std::atomic_ref<uint32_t>(*p).fetch_add(1u, std::memory_order_release); }
   uint32_t counter_acquire(const uint32_t *p) { return std::atomic_ref<uint32_t>(*const_cast<uint32_t *>(p)).load(std::memory_order_acquire); }
   void backoff(unsigned) { std::this_thread::yield(); }
@@ -144,9 +186,12 @@ struct HostEnv {
 
 // run `grid` CTAs of `nt` threads, all at the same time; body(env) is the per-thread program
 template <class Body>
-int run_grid(int64_t grid, int nt, size_t smem_bytes, const void *tables, double *dot_total, Body body) {
+int run_grid(int64_t grid, int nt, size_t smem_bytes, const void *tables, double *dot_total, Body body, int stream_elem_threads = 0) {
   std::vector<std::unique_ptr<CtaShared>> ctas;
-  for (int64_t blk = 0; blk < grid; blk++) ctas.emplace_back(new CtaShared(smem_bytes, nt));
+  for (int64_t blk = 0; blk < grid; blk++) {
+    ctas.emplace_back(new CtaShared(smem_bytes, nt));
+    if (stream_elem_threads) ctas.back()->set_stream(stream_elem_threads, nt);
+  }
   std::vector<int> err((size_t)(grid * nt), 0);
   std::vector<std::thread> th;
   for (int64_t blk = 0; blk < grid; blk++)

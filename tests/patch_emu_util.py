@@ -141,15 +141,16 @@ def flag_essential(P, flag):
 
 
 def run_emu(emu, P, edata, x, y, scale=1.0, accumulate=False, grid=2, dot=False, blob=None, k_begin=0, k_end=None, general=None,
-            ess_identity=True):
+            ess_identity=True, stream=False):
+    """stream = True: the warp-specialised program (patch_stream.h); `grid` then counts streams of 32 + 64 threads"""
     d = np.zeros(1)
     blob = P["blob"] if blob is None else blob
     npatch = len(P["off"]) - 1 if k_end is None else k_end
     c = P["caps"]
     g = P["general"] if general is None else general
     if not accumulate:   # every arrival counter receives one arrival per CTA of the launch (what the launcher accounts for)
-        P["arrivals"] += min(grid, npatch - k_begin)
-    rc = emu.emu_patch_apply(P["order"], P["FE"], int(g), int(accumulate), npatch, k_begin, grid, L.ptr(P["off"]), L.ptr(P["part"]),
+        P["arrivals"] += grid if stream else min(grid, npatch - k_begin)   # (idle streams arrive too)
+    rc = emu.emu_patch_apply(P["order"], -P["FE"] if stream else P["FE"], int(g), int(accumulate), npatch, k_begin, grid, L.ptr(P["off"]), L.ptr(P["part"]),
                              L.ptr(blob), L.ptr(edata), L.ptr(x), L.ptr(y), scale, c["d"], c["l"], c["t"], c["xs"], L.ptr(P["row"]),
                              L.ptr(P["grp"]), P["n_grp"], L.ptr(P["T"]), L.ptr(P["own_off"]), L.ptr(P["own_idx"]), L.ptr(P["count"]), P["arrivals"], int(ess_identity),
                              L.ptr(d) if dot else None)

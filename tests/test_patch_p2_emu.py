@@ -18,7 +18,7 @@ def emu(tmp_path_factory, lib_built):
     return build_emu_lib(tmp_path_factory)
 
 
-VARIANTS = [(32, False), (64, False), (32, True)]   # (elements per patch, general orientation handling)
+VARIANTS = [(32, False), (64, False), (32, True), (-32, False), (-32, True), (-64, False), (-64, True)]   # (elements per patch, general orientation handling); negative: the warp-specialised stream program (patch_stream.h)
 
 
 # (6,6,5) = 180 elements -> 6 patches of 32: with grid 1 / 2 the pipeline wraps around; scrambled vertex numbering makes
@@ -37,19 +37,22 @@ def test_emulated_p2_kernel_matches_oracle(emu, fe, general, n, grid, scramble):
     assert np.array_equal(sp.signed_elem_dofs(), np.where(so.elem_sign > 0, so.elem_dofs, -1 - so.elem_dofs))
     alpha, beta = coefficients(mo)
     A = oa.assemble(so, alpha, beta, q_override=3).tocsr()
+    stream, fe = fe < 0, abs(fe)
+    if stream:
+        grid = {1: 1, 2: 3, 3: 8}[grid]   # streams; 8 > the 2 patches of the (4, 4, 4) case: idle streams
     P = build_patches(sp, m, 2, fe)
     assert not P["general"]
     edata = geometry_factors(m, P["perm"], fe, alpha, beta)
     rng = np.random.default_rng(8)
     x = rng.standard_normal(sp.ndof)
     y = np.full(sp.ndof, 1e30)   # nothing is cleared before an apply
-    dot = run_emu(emu, P, edata, x, y, grid=grid, dot=True, general=general)
+    dot = run_emu(emu, P, edata, x, y, grid=grid, dot=True, general=general, stream=stream)
     ref = A @ x
     assert np.abs(y - ref).max() <= 1e-12 * np.abs(ref).max()
     assert abs(dot - x @ ref) <= 1e-12 * abs(x @ ref)
     y2 = rng.standard_normal(sp.ndof)
     y2_0 = y2.copy()
-    run_emu(emu, P, edata, x, y2, scale=-0.37, accumulate=True, grid=grid, general=general)
+    run_emu(emu, P, edata, x, y2, scale=-0.37, accumulate=True, grid=grid, general=general, stream=stream)
     assert np.abs(y2 - (y2_0 - 0.37 * ref)).max() <= 1e-12 * np.abs(ref).max()
 
 
@@ -63,12 +66,13 @@ def test_emulated_p2_kernel_overflow_slots(emu, fe, general):
         pytest.skip("odd number of dofs: no pair structure")
     alpha, beta = coefficients(mo)
     A = oa.assemble(so, alpha, beta, q_override=3).tocsr()
+    stream, fe = fe < 0, abs(fe)
     P = build_patches(sp, m, 2, fe)
     assert sum(int(header(P, k)[2]) for k in range(len(P["off"]) - 1)) > 0
     edata = geometry_factors(m, P["perm"], fe, alpha, beta)
     x = np.random.default_rng(4).standard_normal(sp.ndof)
     y = np.full(sp.ndof, 1e30)
-    dot = run_emu(emu, P, edata, x, y, grid=2, dot=True, general=general or P["general"])
+    dot = run_emu(emu, P, edata, x, y, grid=2, dot=True, general=general or P["general"], stream=stream)
     ref = A @ x
     assert np.abs(y - ref).max() <= 1e-12 * np.abs(ref).max()
     assert abs(dot - x @ ref) <= 1e-12 * abs(x @ ref)
@@ -84,12 +88,13 @@ def test_emulated_p2_kernel_essential_dofs(emu, fe, general):
     ess = np.sort(np.random.default_rng(11).choice(sp.ndof, sp.ndof // 4, replace=False))
     flag = np.zeros(sp.ndof, bool)
     flag[ess] = True
+    stream, fe = fe < 0, abs(fe)
     P = build_patches(sp, m, 2, fe)
     blob_ess = flag_essential(P, flag)
     edata = geometry_factors(m, P["perm"], fe, alpha, beta)
     x = np.random.default_rng(2).standard_normal(sp.ndof)
     y = np.full(sp.ndof, 1e30)
-    dot = run_emu(emu, P, edata, x, y, grid=2, dot=True, blob=blob_ess, general=general)
+    dot = run_emu(emu, P, edata, x, y, grid=2, dot=True, blob=blob_ess, general=general, stream=stream)
     ref = oa.constrained_apply(A, ess, x)
     assert np.abs(y - ref).max() <= 1e-12 * np.abs(ref).max()
     assert np.array_equal(y[ess], x[ess])
@@ -97,7 +102,7 @@ def test_emulated_p2_kernel_essential_dofs(emu, fe, general):
     # accumulating constrained apply: free dofs accumulate, essential rows are still the identity
     y2 = np.random.default_rng(3).standard_normal(sp.ndof)
     y2_0 = y2.copy()
-    run_emu(emu, P, edata, x, y2, scale=2.0, accumulate=True, grid=2, blob=blob_ess, general=general)
+    run_emu(emu, P, edata, x, y2, scale=2.0, accumulate=True, grid=2, blob=blob_ess, general=general, stream=stream)
     xz = x.copy()
     xz[ess] = 0.0
     exp = y2_0 + 2.0 * (A @ xz)
@@ -105,7 +110,7 @@ def test_emulated_p2_kernel_essential_dofs(emu, fe, general):
     assert np.abs(y2 - exp).max() <= 1e-12 * np.abs(ref).max()
     # several ranks: essential rows are left to the caller (zeros)
     y = np.full(sp.ndof, 1e30)
-    run_emu(emu, P, edata, x, y, grid=2, blob=blob_ess, general=general, ess_identity=False)
+    run_emu(emu, P, edata, x, y, grid=2, blob=blob_ess, general=general, ess_identity=False, stream=stream)
     ref0 = ref.copy()
     ref0[ess] = 0.0
     assert np.abs(y - ref0).max() <= 1e-12 * np.abs(ref).max() and np.all(y[ess] == 0.0)

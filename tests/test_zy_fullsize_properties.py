@@ -89,7 +89,7 @@ def test_full_size_operator_properties(ctx, p, n, ndof):
     gsp = operators.GpuNDSpace(ctx, sp)
     a, b = coefficient_arrays(mesh)
     ops = {}
-    for which in (0, 1) if p == 2 else (0,):  # automatic (order 2: patch kernel on this mesh) and the generic kernel
+    for which in (0, 1) if p <= 2 else (0,):  # automatic (orders 1, 2: patch kernel on this mesh) and the generic kernel
         op = operators.HephGpuOperator(ctx, gsp, p + 1)
         op.SetKernel(which)
         op.SetCoefficients(a, b)
@@ -109,14 +109,14 @@ def test_full_size_operator_properties(ctx, p, n, ndof):
     rng = np.random.default_rng(12345)
     x, y = rng.standard_normal(sp.ndof), rng.standard_normal(sp.ndof)
     Ax, Ay = op.Mult(x), op.Mult(y)
-    assert op.LastKernel() == (3 if p == 2 else 1)
+    assert op.LastKernel() == (3 if p <= 2 else 1)
     assert np.array_equal(Ax[ess], x[ess])
     nx, ny, nAx, nAy = (np.linalg.norm(v) for v in (x, y, Ax, Ay))
     assert abs(Ax @ y - x @ Ay) < TOL * max(nAx * ny, nx * nAy)
     Az = op.Mult(2.0 * x - 3.0 * y)
     assert np.linalg.norm(Az - (2.0 * Ax - 3.0 * Ay)) < TOL * np.linalg.norm(Az)
     assert x @ Ax > 0.0
-    if p == 2:  # two independent kernels
+    if p <= 2:  # two independent kernels
         Gx = ops[1].Mult(x)
         assert ops[1].LastKernel() == 1
         assert np.linalg.norm(Gx - Ax) < TOL * np.linalg.norm(Ax)
