@@ -4,6 +4,7 @@
 //        adaptor_driver --tensor-dofs <in.bin> <out.bin>   host only: HephGpuDiscreteInterpolator::TensorDofs of a mock
 //        space (header: nd, ne; arrays: dof_map [nd], elem_dofs [ne][nd]) -> [ne][nd] as doubles
 #include <cstdint>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -84,6 +85,15 @@ int main(int argc, char ** argv)
     mfem::Vector X(fes.ndofs), Y(fes.ndofs), XBC(fes.ndofs), B(fes.ndofs), RHS(fes.ndofs), SOL(fes.ndofs);
     X._d = x; XBC._d = xbc; B._d = b;
     A.Mult(X, Y);                      // EquationSystem::Mult
+    {                                  // mfem::Operator::ArrayMult: pipelined batch, same results
+      mfem::Vector Y2(fes.ndofs), Y3(fes.ndofs), Y4(fes.ndofs);
+      std::vector<const mfem::Vector *> XS{&X, &XBC, &X};
+      std::vector<mfem::Vector *> YS{&Y2, &Y3, &Y4};
+      A.ArrayMult(XS, YS);
+      double d = 0.0, nrm = 0.0;
+      for (int i = 0; i < fes.ndofs; i++) { d = std::max(d, std::fabs(Y2._d[(size_t)i] - Y._d[(size_t)i])); d = std::max(d, std::fabs(Y4._d[(size_t)i] - Y._d[(size_t)i])); nrm = std::max(nrm, std::fabs(Y._d[(size_t)i])); }
+      if (!(d <= 1e-12 * nrm)) { fprintf(stderr, "ArrayMult differs from Mult: %g (scale %g)\n", d, nrm); return 4; }
+    }
     A.FormRHS(XBC, B, RHS);            // FormLinearSystem right-hand side
     hephaestus::HephGpuPCG pcg(ctx, 1e-9f, 1e-16f, 2000u, 0);
     pcg.iterative_mode = false;        // NewtonSolver::SetSolver

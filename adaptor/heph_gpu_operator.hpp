@@ -332,6 +332,24 @@ public:
   {
     HEPH_GPU_CHECK(hcurl_op_apply(_op, x.HostRead(), y.HostWrite(), HCURL_HOST));
   }
+  /// Y_j = A X_j (mfem::Operator::ArrayMult; with MFEM proper the arguments are mfem::Array<const Vector *> /
+  /// mfem::Array<Vector *> -- same body): uploads, applies and downloads of consecutive vectors overlap
+  template <class ConstVecPtrArray, class VecPtrArray>
+  void ArrayMultT(const ConstVecPtrArray & X, VecPtrArray & Y, int n) const
+  {
+    std::vector<const double *> px((size_t)n);
+    std::vector<double *> py((size_t)n);
+    for (int j = 0; j < n; j++)
+    {
+      px[(size_t)j] = X[j]->HostRead();
+      py[(size_t)j] = Y[j]->HostWrite();
+    }
+    HEPH_GPU_CHECK(hcurl_op_apply_batch(_op, n, px.data(), py.data(), HCURL_HOST));
+  }
+  void ArrayMult(const std::vector<const mfem::Vector *> & X, std::vector<mfem::Vector *> & Y) const override
+  {
+    ArrayMultT(X, Y, (int)X.size());
+  }
   /// B = b - A x_bc|ess, B[ess] = x_bc[ess]: the right-hand side FormLinearSystem produces
   void FormRHS(const mfem::Vector & x_bc, const mfem::Vector & b, mfem::Vector & B) const
   {

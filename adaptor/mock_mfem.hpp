@@ -51,6 +51,12 @@ public:
   int Height() const { return height; }
   int Width() const { return width; }
   virtual void Mult(const Vector & x, Vector & y) const = 0;
+  /// mfem::Operator::ArrayMult: operator application on a set of vectors (default: one Mult each)
+  virtual void ArrayMult(const std::vector<const Vector *> & X, std::vector<Vector *> & Y) const
+  {
+    for (size_t i = 0; i < X.size(); i++)
+      Mult(*X[i], *Y[i]);
+  }
 
 protected:
   int height, width;

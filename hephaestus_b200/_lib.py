@@ -45,6 +45,7 @@ SIGNATURES = {
     "hcurl_space_elem_ndof": (C.c_int, [_P]),
     "hcurl_op_create": (_P, [_P, _P, C.c_int]),
     "hcurl_op_destroy": (None, [_P]),
+    "hcurl_op_apply_batch": (C.c_int, [_P, C.c_int, _P, _P, C.c_int]),
     "hcurl_op_set_kernel": (C.c_int, [_P, C.c_int]),
     "hcurl_op_last_kernel": (C.c_int, [_P]),
     "hcurl_op_set_tet_rules": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, _P, _P]),
@@ -67,6 +68,7 @@ SIGNATURES = {
     "hcurl_pcg_solve": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double),
                                   C.POINTER(C.c_int)]),
     "hcurl_pcg_last_loop_ms": (C.c_double, [_P]),
+    "hcurl_pcg_last_used_graph": (C.c_int, [_P]),
     "hcurl_pcg_set_chebyshev": (C.c_int, [_P, C.c_int, C.c_int]),
     "hcurl_pcg_lambda_max": (C.c_double, [_P]),
     "hcurl_interp_create": (_P, [_P, C.c_int, C.c_int, C.c_int64, _P, _P, C.c_int32, C.c_int32]),

@@ -195,6 +195,24 @@ __global__ void pcg_dir_kernel(const int64_t n, const double *__restrict__ gamma
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     p[i] = s[i] + beta * p[i];
 }
+// End of one iteration of the graph-captured loop (pcg_graph_build): hypre's stopping tests on the device, in the order
+// of the host loop below -- <s, p> = 0: stop, x unchanged; gamma_new / bi_prod < eps: converged; |gamma_new| < 1e-292:
+// stop; iteration limit -- and the value of the WHILE node's condition.  S[0] gamma, S[1] <s,p>, S[2] gamma_new,
+// S[3] bi_prod, S[4] eps; state[0] iterations done, [1] converged, [2] limit.
+__global__ void pcg_check_kernel(double *S, int *state, cudaGraphConditionalHandle handle) {
+  const double sdotp = S[1], gamma_new = S[2];
+  const int it = state[0] + 1;
+  state[0] = it;
+  bool stop = false;
+  if (sdotp == 0.0) stop = true;
+  else {
+    S[0] = gamma_new;
+    if (gamma_new / S[3] < S[4]) { state[1] = 1; stop = true; }
+    else if (fabs(gamma_new) < 1e-292) stop = true;
+  }
+  if (it >= state[2]) stop = true;
+  cudaGraphSetConditional(handle, stop ? 0u : 1u);
+}
 // ---- Chebyshev preconditioner (HCURL_PC_CHEBYSHEV) ----------------------------------------------------------
 // deterministic pseudo-random start vector of the power method, values in [0.5, 1.5) (oracle/pcg.py: start_vector)
 __global__ void cheb_seed_kernel(const int64_t n, const uint32_t offset, double *__restrict__ v) {
@@ -392,6 +410,8 @@ void hcurl_ctx_destroy(hcurl_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->comm_stream) { cudaStreamSynchronize(ctx->comm_stream); cudaStreamDestroy(ctx->comm_stream); }
+  if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+  if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
   for (int i = 0; i < 4; i++) if (ctx->ev_x[i]) cudaEventDestroy(ctx->ev_x[i]);
   comm_destroy(ctx);
   cudaFree(ctx->d_red); cudaFreeHost(ctx->h_red); cudaFree(ctx->d_counter); cudaFree(ctx->d_partial);
@@ -608,7 +628,9 @@ void hcurl_op_destroy(hcurl_op *op) {
   cudaStreamSynchronize(op->ctx->stream);
   cudaFree(op->d_alpha); cudaFree(op->d_beta); cudaFree(op->d_map_ess); cudaFree(op->d_ess);
   cudaFree(op->d_edata); cudaFree(op->d_mapT_ess); cudaFree(op->d_edataP); cudaFree(op->d_blob_ess);
-  cudaFree(op->d_emat); cudaFree(op->d_xin); cudaFree(op->d_yout); cudaFree(op->d_tmp); cudaFree(op->d_refq_k); cudaFree(op->d_refq_m);
+  cudaFree(op->d_emat); cudaFree(op->d_xin); cudaFree(op->d_yout); cudaFree(op->d_xin2); cudaFree(op->d_yout2); cudaFree(op->d_tmp);
+  for (int i = 0; i < 2; i++) { if (op->ev_h2d[i]) cudaEventDestroy(op->ev_h2d[i]); if (op->ev_run[i]) cudaEventDestroy(op->ev_run[i]); if (op->ev_d2h[i]) cudaEventDestroy(op->ev_d2h[i]); }
+  cudaFree(op->d_refq_k); cudaFree(op->d_refq_m);
   for (int i = 0; i < hcurl_op::RING; i++) { cudaEventDestroy(op->ring0[i]); cudaEventDestroy(op->ring1[i]); }
   delete op;
 }
@@ -616,6 +638,7 @@ int hcurl_op_set_kernel(hcurl_op *op, int which) {
   if (which < 0 || which > 3) { set_error("kernel selector must be 0 (auto), 1 (generic), 2 (element-wise fast) or 3 (patch)"); return 1; }
   op->force_generic = which == 1;
   op->kernel_sel = which;
+  op->generation++;
   return 0;
 }
 int hcurl_op_last_kernel(const hcurl_op *op) { return op->last_kernel; }
@@ -635,6 +658,7 @@ int hcurl_op_set_tet_rules(hcurl_op *op, int nq_curl, const double *pts_curl, co
 
 int hcurl_op_set_coefficients(hcurl_op *op, int layout, const double *alpha, const double *beta, int where) {
   hcurl_space *sp = op->sp;
+  op->generation++;
   HC_CUDA(cudaSetDevice(op->ctx->device));
   if (layout == HCURL_COEF_PER_QPT && sp->geom != HCURL_GEOM_HEX && (op->tet_nqc < 1 || op->tet_nqm < 1)) {
     set_error("PER_QPT coefficients on tets need the quadrature rules first (hcurl_op_set_tet_rules)");
@@ -663,6 +687,7 @@ int hcurl_op_set_coefficients(hcurl_op *op, int layout, const double *alpha, con
 
 int hcurl_op_set_essential_tdofs(hcurl_op *op, const int32_t *ess, int32_t n_ess) {
   hcurl_space *sp = op->sp;
+  op->generation++;
   hcurl_ctx *ctx = op->ctx;
   HC_CUDA(cudaSetDevice(ctx->device));
   for (int32_t i = 0; i < n_ess; i++)
@@ -718,6 +743,52 @@ int hcurl_op_apply_unconstrained(hcurl_op *op, const double *x, double *y, doubl
   return apply_common(op, x, y, where, false, scale, accumulate);
 }
 
+// y_j = A x_j for a batch of vectors (mfem::Operator::ArrayMult, which EquationSystem inherits and MFEM's block / multi-
+// vector callers use).  With HOST buffers the three stages of consecutive vectors run concurrently on three streams --
+// x_{j+1} host -> device  |  apply of x_j  |  y_{j-1} device -> host -- through two staging pairs, so that both directions
+// of the PCIe link are busy at once (a single host-buffer apply is one direction at a time: 2 x 406 MB at ~54 GB/s for the
+// bench vector, against 0.44 ms of compute).  Pinned host buffers are needed for the copies to be asynchronous.
+int hcurl_op_apply_batch(hcurl_op *op, int n, const double *const *x, double *const *y, int where) {
+  hcurl_space *sp = op->sp;
+  hcurl_ctx *ctx = op->ctx;
+  if (n < 0 || (n > 0 && (!x || !y))) { set_error("hcurl_op_apply_batch: bad arguments"); return 1; }
+  if (where != HCURL_HOST) {
+    for (int j = 0; j < n; j++) if (apply_common(op, x[j], y[j], where, true, 1.0, 0)) return 1;
+    return 0;
+  }
+  HC_CUDA(cudaSetDevice(ctx->device));
+  if (!op->has_alpha && !op->has_beta) { set_error("operator has no coefficients set"); return 1; }
+  if (ensure_work(op)) return 1;
+  const size_t bytes_ext = sizeof(double) * (size_t)sp->n_ext(), bytes = sizeof(double) * (size_t)sp->n_tdof;
+  if (!op->d_xin2) HC_CUDA(cudaMalloc(&op->d_xin2, bytes_ext));
+  if (!op->d_yout2) HC_CUDA(cudaMalloc(&op->d_yout2, bytes_ext));
+  if (!ctx->h2d_stream) HC_CUDA(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+  if (!ctx->d2h_stream) HC_CUDA(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; i++) {
+    if (!op->ev_h2d[i]) HC_CUDA(cudaEventCreateWithFlags(&op->ev_h2d[i], cudaEventDisableTiming));
+    if (!op->ev_run[i]) HC_CUDA(cudaEventCreateWithFlags(&op->ev_run[i], cudaEventDisableTiming));
+    if (!op->ev_d2h[i]) HC_CUDA(cudaEventCreateWithFlags(&op->ev_d2h[i], cudaEventDisableTiming));
+  }
+  double *xin[2] = {op->d_xin, op->d_xin2}, *yout[2] = {op->d_yout, op->d_yout2};
+  HC_CUDA(cudaStreamSynchronize(ctx->stream));  // earlier work on the staging buffers
+  for (int j = 0; j < n; j++) {
+    const int b = j & 1;
+    if (j >= 2) HC_CUDA(cudaStreamWaitEvent(ctx->h2d_stream, op->ev_run[b], 0));   // the apply of x_{j-2} has read its staging copy
+    HC_CUDA(cudaMemcpyAsync(xin[b], x[j], bytes, cudaMemcpyHostToDevice, ctx->h2d_stream));
+    HC_CUDA(cudaEventRecord(op->ev_h2d[b], ctx->h2d_stream));
+    HC_CUDA(cudaStreamWaitEvent(ctx->stream, op->ev_h2d[b], 0));
+    if (j >= 2) HC_CUDA(cudaStreamWaitEvent(ctx->stream, op->ev_d2h[b], 0));       // y_{j-2} has left its staging copy
+    if (op_apply_ext(op, xin[b], yout[b], true, 1.0, false)) return 1;
+    HC_CUDA(cudaEventRecord(op->ev_run[b], ctx->stream));
+    HC_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, op->ev_run[b], 0));
+    HC_CUDA(cudaMemcpyAsync(y[j], yout[b], bytes, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    HC_CUDA(cudaEventRecord(op->ev_d2h[b], ctx->d2h_stream));
+  }
+  HC_CUDA(cudaStreamSynchronize(ctx->d2h_stream));
+  HC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
 int hcurl_op_apply_complex(hcurl_op *op_re, hcurl_op *op_im, const double *xr, const double *xi, double *yr, double *yi, int where) {
   if (op_re->sp != op_im->sp) { set_error("complex apply: operators must share a space"); return 1; }
   hcurl_space *sp = op_re->sp;
@@ -729,7 +800,23 @@ int hcurl_op_apply_complex(hcurl_op *op_re, hcurl_op *op_im, const double *xr, c
   double *dxr = op_re->d_tmp, *dxi = dxr + next, *dyr = dxi + next, *dyi = dyr + next;
   HC_CUDA(cudaMemcpyAsync(dxr, xr, sizeof(double) * nt, kind_in(where), ctx->stream));
   HC_CUDA(cudaMemcpyAsync(dxi, xi, sizeof(double) * nt, kind_in(where), ctx->stream));
-  // essential rows of the block system are identity on both parts: constrain Ar, and
+  if (sp->geom == HCURL_GEOM_TET) {
+    // tets: ONE fused pass over the elements (tet_apply_complex_kernel): xr, xi gathered once, both packed element
+    // matrices streamed once, yr, yi scattered once; essential rows of the block system are the identity on both parts
+    if (op_re->n_ess != op_im->n_ess) { set_error("complex apply: both operators need the same essential dofs"); return 1; }
+    const uint32_t *map = op_re->d_map_ess ? op_re->d_map_ess : sp->d_map;
+    if (exchange_broadcast(sp, dxr) || exchange_broadcast(sp, dxi)) return 1;
+    HC_CUDA(cudaMemsetAsync(dyr, 0, sizeof(double) * 2 * next, ctx->stream));  // (dyr, dyi are adjacent)
+    if (tet_apply_complex_launch(op_re, op_im, map, dxr, dxi, dyr, dyi)) return 1;
+    if (exchange_reduce(sp, dyr) || exchange_reduce(sp, dyi)) return 1;
+    if (op_re->n_ess > 0) {
+      copy_idx_kernel<<<(op_re->n_ess + 255) / 256, 256, 0, ctx->stream>>>(op_re->n_ess, op_re->d_ess, dxr, dyr);
+      copy_idx_kernel<<<(op_re->n_ess + 255) / 256, 256, 0, ctx->stream>>>(op_re->n_ess, op_re->d_ess, dxi, dyi);
+      ctx->launches += 2;
+    }
+    HC_CUDA(cudaGetLastError());
+  } else {
+  // hexes: essential rows of the block system are identity on both parts: constrain Ar, and
   // apply Ai with the same essential masking but no identity contribution
   if (op_apply_ext(op_re, dxr, dyr, true, 1.0, false)) return 1;   // yr = Ar xr (ess: yr = xr)
   if (op_apply_ext(op_re, dxi, dyi, true, 1.0, false)) return 1;   // yi = Ar xi (ess: yi = xi)
@@ -745,6 +832,7 @@ int hcurl_op_apply_complex(hcurl_op *op_re, hcurl_op *op_im, const double *xr, c
     };
     if (run(dxi, dyr, -1.0)) return 1;  // yr -= Ai xi
     if (run(dxr, dyi, +1.0)) return 1;  // yi += Ai xr
+  }
   }
   HC_CUDA(cudaMemcpyAsync(yr, dyr, sizeof(double) * nt, kind_out(where), ctx->stream));
   HC_CUDA(cudaMemcpyAsync(yi, dyi, sizeof(double) * nt, kind_out(where), ctx->stream));
@@ -839,6 +927,9 @@ void hcurl_pcg_destroy(hcurl_pcg *s) {
   cudaFree(s->d_cres); cudaFree(s->d_cd); cudaFree(s->d_ct);
   cudaEventDestroy(s->ev0); cudaEventDestroy(s->ev1);
   if (s->ev_red) cudaEventDestroy(s->ev_red);
+  if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
+  if (s->graph) cudaGraphDestroy(s->graph);
+  cudaFree(s->d_state);
   delete s;
 }
 int hcurl_pcg_set(hcurl_pcg *s, double rtol, double atol, int max_iter, int print_level) {
@@ -995,6 +1086,62 @@ static int pcg_solve_chebyshev(hcurl_pcg *s, const double *b, double *x, int zer
   return 0;
 }
 
+// The Krylov loop as ONE graph launch: a WHILE conditional node (CUDA 12.4+) whose body is one iteration -- apply,
+// <p, A p>, fused update, direction update, pcg_check_kernel -- captured from the same enqueue code the host loop runs.
+// No host round trip per iteration: at the reference's problem sizes (TEAM7: 68 547 dofs) an iteration is a handful of
+// kernels of a few microseconds each, and the host loop's per-iteration event wait and launch latencies dominate it.
+// Single rank, Jacobi / no preconditioner, operators whose apply does not go through the patch kernels (their zeroing
+// watermark takes a per-launch host counter).  HCURL_PCG_GRAPH=0 keeps the host loop.
+static bool pcg_graph_wanted(const hcurl_pcg *s) {
+  static const bool on = [] { const char *e = getenv("HCURL_PCG_GRAPH"); return !(e && e[0] == '0'); }();
+  return on && s->ctx->nranks == 1 && s->op->sp->n_nbr == 0 && s->precond != HCURL_PC_CHEBYSHEV && s->print_level <= 1 && !hex_patch_eligible(s->op) &&
+         !hex_fast_eligible(s->op);
+}
+static int pcg_graph_build(hcurl_pcg *s) {
+  hcurl_ctx *ctx = s->ctx;
+  hcurl_op *op = s->op;
+  const int64_t nt = op->sp->n_tdof;
+  cudaStream_t st = ctx->stream;
+  double *S = ctx->d_red;
+  const int g = red_grid(ctx, nt);
+  const double *dinv = s->precond == HCURL_PC_JACOBI ? s->d_dinv : nullptr;
+  if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
+  if (s->graph) { cudaGraphDestroy(s->graph); s->graph = nullptr; }
+  if (!s->d_state) HC_CUDA(cudaMalloc(&s->d_state, sizeof(int) * 4));
+  // one ordinary apply first: lazily built device data (element matrices, constant tables, work vectors) must exist
+  // before the capture, which cannot allocate or synchronise
+  if (op_apply_ext(op, s->d_p, s->d_s, true, 1.0, false)) return 1;
+  HC_CUDA(cudaStreamSynchronize(st));
+  HC_CUDA(cudaGraphCreate(&s->graph, 0));
+  cudaGraphConditionalHandle handle;
+  HC_CUDA(cudaGraphConditionalHandleCreate(&handle, s->graph, 1, cudaGraphCondAssignDefault));
+  cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+  np.conditional.handle = handle;
+  np.conditional.type = cudaGraphCondTypeWhile;
+  np.conditional.size = 1;
+  cudaGraphNode_t node;
+  HC_CUDA(cudaGraphAddNode(&node, s->graph, nullptr, 0, &np));
+  cudaGraph_t body = np.conditional.phGraph_out[0];
+  const bool timed = op->timed;
+  op->timed = false;  // (timing events cannot be read back from a captured launch)
+  HC_CUDA(cudaStreamBeginCaptureToGraph(st, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+  int rc = op_apply_ext(op, s->d_p, s->d_s, true, 1.0, false);
+  if (!rc) {
+    dot_kernel<<<g, RED_THREADS, 0, st>>>(nt, s->d_s, s->d_p, ctx->d_partial, ctx->d_counter, S + 1);
+    pcg_update_kernel<<<g, RED_THREADS, 0, st>>>(nt, S + 0, S + 1, dinv, s->d_p, s->d_x, s->d_r, s->d_s, ctx->d_partial, ctx->d_counter, S + 2);
+    pcg_dir_kernel<<<g, RED_THREADS, 0, st>>>(nt, S + 2, S + 0, s->d_s, s->d_p);
+    pcg_check_kernel<<<1, 1, 0, st>>>(S, s->d_state, handle);
+  }
+  cudaGraph_t captured = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(st, &captured);
+  op->timed = timed;
+  if (rc) return 1;
+  if (ce != cudaSuccess) { set_error("PCG graph capture failed: %s", cudaGetErrorString(ce)); return 1; }
+  HC_CUDA(cudaGraphInstantiate(&s->graph_exec, s->graph, 0));
+  s->graph_generation = op->generation;
+  return 0;
+}
+
 int hcurl_pcg_solve(hcurl_pcg *s, const double *b, double *x, int zero_guess, int where, int *iters, double *final_rel,
                     int *converged) {
   if (s->precond == HCURL_PC_CHEBYSHEV) {
@@ -1053,6 +1200,34 @@ int hcurl_pcg_solve(hcurl_pcg *s, const double *b, double *x, int zero_guess, in
   //    same iteration count) overlaps with it instead of draining the GPU every iteration.  When the test says
   //    stop, the direction update already in flight only touched p, which is dead by then.
   if (!s->ev_red) HC_CUDA(cudaEventCreateWithFlags(&s->ev_red, cudaEventDisableTiming));
+  s->last_used_graph = false;
+  if (s->max_iter >= 1 && pcg_graph_wanted(s)) {
+    if (!s->graph_exec || s->graph_generation != op->generation) {
+      // (the warm-up apply of the build overwrites d_s only; p, r, x and S are as the prelude left them)
+      if (pcg_graph_build(s)) return 1;
+    }
+    const int state[4] = {0, 0, s->max_iter, 0};
+    HC_CUDA(cudaMemcpyAsync(s->d_state, state, sizeof(state), cudaMemcpyHostToDevice, st));
+    HC_CUDA(cudaMemcpyAsync(S + 4, &eps, sizeof(double), cudaMemcpyHostToDevice, st));
+    HC_CUDA(cudaEventRecord(s->ev0, st));
+    HC_CUDA(cudaGraphLaunch(s->graph_exec, st));
+    HC_CUDA(cudaEventRecord(s->ev1, st));
+    int hstate[4];
+    HC_CUDA(cudaMemcpyAsync(hstate, s->d_state, sizeof(hstate), cudaMemcpyDeviceToHost, st));
+    HC_CUDA(cudaMemcpyAsync(ctx->h_red, S, sizeof(double) * 4, cudaMemcpyDeviceToHost, st));
+    HC_CUDA(cudaMemcpyAsync(x, s->d_x, sizeof(double) * nt, kind_out(where), st));
+    HC_CUDA(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&s->last_loop_ms, s->ev0, s->ev1);
+    i = hstate[0]; conv = hstate[1]; gamma = ctx->h_red[0];
+    ctx->launches += (int64_t)i * 5;
+    s->last_used_graph = true;
+    if (iters) *iters = i;
+    if (final_rel) *final_rel = sqrt(fabs(gamma) / bi_prod);
+    if (converged) *converged = conv;
+    if (s->print_level > 0 && ctx->rank == 0)
+      printf("hcurl pcg: %d iterations, final relative residual %.6e%s\n", i, sqrt(fabs(gamma) / bi_prod), conv ? "" : " (not converged)");
+    return 0;
+  }
   HC_CUDA(cudaEventRecord(s->ev0, st));
   int go = 0;  // S[go] holds gamma, S[2 - go] receives gamma_new
   while (i + 1 <= s->max_iter) {
@@ -1095,6 +1270,7 @@ int hcurl_pcg_solve(hcurl_pcg *s, const double *b, double *x, int zero_guess, in
   return 0;
 }
 double hcurl_pcg_last_loop_ms(hcurl_pcg *s) { return s->last_loop_ms; }
+int hcurl_pcg_last_used_graph(const hcurl_pcg *s) { return s && s->last_used_graph ? 1 : 0; }
 
 // --------------------------------------------------------------- vector helpers ----
 double *hcurl_device_alloc(hcurl_ctx *ctx, int64_t n) {

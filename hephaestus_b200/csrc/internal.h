@@ -173,6 +173,7 @@ struct hcurl_ctx {
   int rank = 0, nranks = 1;
   cudaStream_t stream = nullptr;
   cudaStream_t comm_stream = nullptr;
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;  // copy streams of the pipelined batch apply, created on first use
   void *comm = nullptr;  // ncclComm_t
   double *d_red = nullptr;   // device reduction scratch (few doubles)
   double *h_red = nullptr;   // pinned host mirror
@@ -253,7 +254,10 @@ struct hcurl_op {
   int last_kernel = 0;             // which of them the most recent apply launched
   bool force_generic = false;
   // work vectors (extended length)
+  int generation = 0;  // bumped whenever device buffers the launches refer to may have been reallocated (coefficients, essential dofs, kernel choice)
   double *d_xin = nullptr, *d_yout = nullptr, *d_tmp = nullptr;
+  double *d_xin2 = nullptr, *d_yout2 = nullptr;  // second staging pair of the pipelined batch apply (hcurl_op_apply_batch)
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_run[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
   static constexpr int RING = 256;
@@ -276,6 +280,13 @@ struct hcurl_pcg {
   double *d_cres = nullptr, *d_cd = nullptr, *d_ct = nullptr;
   float last_loop_ms = 0.f;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_red = nullptr;
+  // whole Krylov loop as one CUDA graph with a device-side WHILE node (api.cu: pcg_graph_*): built on first use for the
+  // operator's current generation, replayed by later solves
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  int graph_generation = -1;
+  int *d_state = nullptr;  // [0] iterations done, [1] converged, [2] iteration limit
+  bool last_used_graph = false;
 };
 
 namespace hcurl {
@@ -309,6 +320,7 @@ int tet_build_emat(hcurl_op *op);
 int tet_set_rules(hcurl_op *op, int nqc, const double *pc, const double *wc, int nqm, const double *pm, const double *wm);
 int tet_apply_launch(hcurl_op *op, const uint32_t *d_map, const double *d_x, double *d_y, double scale);
 int tet_diag_launch(hcurl_op *op, double *d_diag);
+int tet_apply_complex_launch(hcurl_op *op_re, hcurl_op *op_im, const uint32_t *d_map, const double *d_xr, const double *d_xi, double *d_yr, double *d_yi);
 // exchange (comm.cu): broadcast owner->ghost on x_ext, reduce ghost->owner on y_ext
 // stream: where the exchange is enqueued (null = the context's main stream)
 int exchange_broadcast(hcurl_space *sp, double *d_ext, cudaStream_t stream = nullptr);

@@ -57,6 +57,78 @@ tet_apply_kernel(const int64_t n_elem, const int64_t n_pad, const uint32_t *__re
   }
 }
 
+// Complex (block) apply [[Ar, -Ai], [Ai, Ar]] in ONE pass: xr_e, xi_e gathered once, the two packed element matrices
+// streamed once, yr_e, yi_e scattered once (ComplexMaxwellOperator::Solve builds this block operator,
+// /root/reference/src/formulations/ComplexMaxwell/complex_maxwell_formulation.cpp:181-217).  Against four real applies
+// this halves the matrix traffic that bounds the tet kernel and reads x / writes y once instead of twice.
+template <int ND>
+__global__ void __launch_bounds__(128)
+tet_apply_complex_kernel(const int64_t n_elem, const int64_t n_pad, const uint32_t *__restrict__ map,
+                         const double *__restrict__ emat_re, const double *__restrict__ emat_im,
+                         const double *__restrict__ xr, const double *__restrict__ xi, double *__restrict__ yr, double *__restrict__ yi) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_elem) return;
+  double ar_[ND], ai_[ND], br_[ND], bi_[ND];  // x_e (re, im), y_e (re, im)
+  uint32_t mm[ND];
+#pragma unroll
+  for (int i = 0; i < ND; i++) {
+    mm[i] = __ldg(map + i * n_pad + e);
+    ar_[i] = tet_gather(xr, mm[i]);
+    ai_[i] = tet_gather(xi, mm[i]);
+    br_[i] = 0.0;
+    bi_[i] = 0.0;
+  }
+  int k = 0;
+#pragma unroll
+  for (int i = 0; i < ND; i++) {
+#pragma unroll
+    for (int j = i; j < ND; j++, k++) {
+      const double mr = __ldg(emat_re + (int64_t)k * n_pad + e), mi = __ldg(emat_im + (int64_t)k * n_pad + e);
+      br_[i] += mr * ar_[j] - mi * ai_[j];
+      bi_[i] += mi * ar_[j] + mr * ai_[j];
+      if (j != i) {
+        br_[j] += mr * ar_[i] - mi * ai_[i];
+        bi_[j] += mi * ar_[i] + mr * ai_[i];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < ND; i++) {
+    if (mm[i] & MAP_ESS) continue;
+    const bool neg = mm[i] & MAP_NEG;
+    atomicAdd(yr + (mm[i] & MAP_IDX), neg ? -br_[i] : br_[i]);
+    atomicAdd(yi + (mm[i] & MAP_IDX), neg ? -bi_[i] : bi_[i]);
+  }
+}
+
+__global__ void tet_apply_complex_kernel_generic(const int nd, const int64_t n_elem, const int64_t n_pad, const uint32_t *__restrict__ map,
+                                                 const double *__restrict__ emat_re, const double *__restrict__ emat_im,
+                                                 const double *__restrict__ xr, const double *__restrict__ xi,
+                                                 double *__restrict__ yr, double *__restrict__ yi) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_elem) return;
+  double ar_[45], ai_[45], br_[45], bi_[45];
+  for (int i = 0; i < nd; i++) {
+    const uint32_t m = __ldg(map + i * n_pad + e);
+    ar_[i] = tet_gather(xr, m); ai_[i] = tet_gather(xi, m); br_[i] = 0.0; bi_[i] = 0.0;
+  }
+  int k = 0;
+  for (int i = 0; i < nd; i++)
+    for (int j = i; j < nd; j++, k++) {
+      const double mr = __ldg(emat_re + (int64_t)k * n_pad + e), mi = __ldg(emat_im + (int64_t)k * n_pad + e);
+      br_[i] += mr * ar_[j] - mi * ai_[j];
+      bi_[i] += mi * ar_[j] + mr * ai_[j];
+      if (j != i) { br_[j] += mr * ar_[i] - mi * ai_[i]; bi_[j] += mi * ar_[i] + mr * ai_[i]; }
+    }
+  for (int i = 0; i < nd; i++) {
+    const uint32_t m = __ldg(map + i * n_pad + e);
+    if (m & MAP_ESS) continue;
+    const bool neg = m & MAP_NEG;
+    atomicAdd(yr + (m & MAP_IDX), neg ? -br_[i] : br_[i]);
+    atomicAdd(yi + (m & MAP_IDX), neg ? -bi_[i] : bi_[i]);
+  }
+}
+
 // generic (any nd) fallback used for nd = 45: x_e, y_e in local memory
 __global__ void tet_apply_kernel_generic(const int nd, const int64_t n_elem, const int64_t n_pad,
                                          const uint32_t *__restrict__ map, const double *__restrict__ emat,
@@ -236,6 +308,25 @@ int tet_apply_launch(hcurl_op *op, const uint32_t *d_map, const double *d_x, dou
     tet_apply_kernel_generic<<<grid, 128, 0, st>>>(sp->nd, sp->n_elem, sp->n_elem_pad, d_map, op->d_emat, d_x, d_y, scale);
   HC_CUDA(cudaGetLastError());
   op->ctx->launches++;
+  return 0;
+}
+
+// yr += Ar xr - Ai xi, yi += Ai xr + Ar xi over the element loop (essential dofs of the map: no input, no output)
+int tet_apply_complex_launch(hcurl_op *op_re, hcurl_op *op_im, const uint32_t *d_map, const double *d_xr, const double *d_xi,
+                             double *d_yr, double *d_yi) {
+  hcurl_space *sp = op_re->sp;
+  if (!op_re->emat_valid && tet_build_emat(op_re)) return 1;
+  if (!op_im->emat_valid && tet_build_emat(op_im)) return 1;
+  const unsigned grid = (unsigned)((sp->n_elem + 127) / 128);
+  cudaStream_t st = op_re->ctx->stream;
+  if (sp->nd == 6)
+    tet_apply_complex_kernel<6><<<grid, 128, 0, st>>>(sp->n_elem, sp->n_elem_pad, d_map, op_re->d_emat, op_im->d_emat, d_xr, d_xi, d_yr, d_yi);
+  else if (sp->nd == 20)
+    tet_apply_complex_kernel<20><<<grid, 128, 0, st>>>(sp->n_elem, sp->n_elem_pad, d_map, op_re->d_emat, op_im->d_emat, d_xr, d_xi, d_yr, d_yi);
+  else
+    tet_apply_complex_kernel_generic<<<grid, 128, 0, st>>>(sp->nd, sp->n_elem, sp->n_elem_pad, d_map, op_re->d_emat, op_im->d_emat, d_xr, d_xi, d_yr, d_yi);
+  HC_CUDA(cudaGetLastError());
+  op_re->ctx->launches++;
   return 0;
 }
 

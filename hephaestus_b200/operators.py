@@ -224,6 +224,17 @@ class HephGpuOperator:
         L.check(L.lib().hcurl_op_apply(self.h, L.ptr(x), L.ptr(y), L.HOST), "hcurl_op_apply")
         return y
 
+    def ArrayMult(self, xs, ys=None):
+        """y_j = A x_j for a list of host vectors (mfem::Operator::ArrayMult): uploads, applies and downloads of
+        consecutive vectors overlap (hcurl_op_apply_batch).  Pinned buffers (Context.pinned) make the copies asynchronous."""
+        xs = [L.as_f64(x) for x in xs]
+        ys = [np.empty_like(x) for x in xs] if ys is None else ys
+        n = len(xs)
+        px = (C.c_void_p * n)(*[x.ctypes.data for x in xs])
+        py = (C.c_void_p * n)(*[y.ctypes.data for y in ys])
+        L.check(L.lib().hcurl_op_apply_batch(self.h, n, px, py, L.HOST), "hcurl_op_apply_batch")
+        return ys
+
     def MultUnconstrained(self, x, y=None, scale=1.0, accumulate=False):
         x = L.as_f64(x)
         if y is None:
@@ -367,6 +378,9 @@ class HephGpuPCG:
 
     def last_loop_ms(self):
         return L.lib().hcurl_pcg_last_loop_ms(self.h)
+
+    def last_used_graph(self):
+        return bool(L.lib().hcurl_pcg_last_used_graph(self.h))
 
     def lambda_max(self):
         return L.lib().hcurl_pcg_lambda_max(self.h)

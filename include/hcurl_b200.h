@@ -190,6 +190,11 @@ int hcurl_op_apply(hcurl_op *op, const double *x, double *y, int where);
  * boundary lift  B -= A_e x_bc  of FormLinearSystem. */
 int hcurl_op_apply_unconstrained(hcurl_op *op, const double *x, double *y, double scale,
                                  int accumulate, int where);
+/* y_j = A x_j, j = 0 .. n-1 (mfem::Operator::ArrayMult -- EquationSystem is an mfem::Operator,
+ * /root/reference/src/equation_systems/equation_system.hpp:15-24; its Mult is equation_system.cpp:200-204).
+ * With HCURL_HOST buffers (pinned for the copies to be asynchronous) the upload of x_{j+1}, the apply of
+ * x_j and the download of y_{j-1} overlap, so both directions of the host link are busy at once. */
+int hcurl_op_apply_batch(hcurl_op *op, int n, const double *const *x, double *const *y, int where);
 /* Complex (HERMITIAN convention) block apply [[Ar, -Ai], [Ai, Ar]]
  * (/root/reference/src/formulations/ComplexMaxwell/complex_maxwell_formulation.cpp:181-217):
  * yr = Ar xr - Ai xi,  yi = Ai xr + Ar xi.  op_re and op_im share a space. */
@@ -234,6 +239,9 @@ int hcurl_pcg_set_chebyshev(hcurl_pcg *pcg, int order, int power_iters);
 double hcurl_pcg_lambda_max(const hcurl_pcg *pcg);
 /* device time (ms) spent inside the iteration loop of the most recent solve */
 double hcurl_pcg_last_loop_ms(hcurl_pcg *pcg);
+/* 1 when the last solve ran its Krylov loop as one CUDA graph (device-side WHILE node: no host round trip per
+ * iteration; single rank, Jacobi / no preconditioner, element-wise apply kernels), 0 for the host-driven loop. */
+int hcurl_pcg_last_used_graph(const hcurl_pcg *pcg);
 
 /* ---- discrete gradient / curl (hexes, orders 1..4) -------------------------------------------
  * Replaces: mfem::ParDiscreteLinearOperator + CurlInterpolator of CurlAuxSolver (B = curl A every step,

@@ -13,6 +13,8 @@ oracle's readers and committed as compressed fixtures:
   cylinder_hex_q2.npz   data/cylinder-hex-q2.gen 252 HEX27 -- TestHFormRod / TestEBFormRod / TestComplexAFormRod
                                                              (test/integration/test_hform_rod.cpp:40)
   team7.npz             data/team7.g             57 905 tets -- examples/team7/Main.cpp:154, TestComplexTeam7
+  team4.npz             data/team4.g             127 074 tets -- BASELINE configs[2] (closed_coil / team4 order-2 A-formulation), with
+                                                             team4_samples.npz: samples of the oracle's apply at order 2 (808 658 dofs)
   irises.npz            data/irises.g            8 346 HEX8 -- TestComplexIrisWaveguide, the reference's known-answer test
                                                              for the hex path (test/integration/test_complex_iris_wg.cpp:90,191-195;
                                                              `python scripts/make_golden.py irises` writes only this one and
@@ -70,10 +72,30 @@ def irises():
     print("irises", s.ndof, "dofs", A.nnz, "nnz")
 
 
+def team4():
+    """BASELINE.json configs[2]: data/team4.g (127 074 tets), order-2 Nedelec = 808 658 dofs.  The oracle needs two minutes
+    for this space and matrix, and its output vector would be 6.5 MB, so the fixture holds the mesh and SAMPLES of the
+    oracle's y = (K(alpha) + M(beta)) x and diagonal for the seeded x of the other fixtures: 4096 entries at seeded
+    positions plus x.y and |y|^2 (`python scripts/make_golden.py team4`)."""
+    m = om.read_exodus(os.path.join(DATA, "team4.g"))
+    save_mesh("team4", m)
+    s = osp.NDSpace(m, 2)
+    alpha, beta = coef_by_attr(m.attr, 0.5, 2.0), coef_by_attr(m.attr, 1.0, 1.0e3)
+    A = oa.assemble(s, alpha, beta)
+    x = np.random.default_rng(12345).standard_normal(s.ndof)
+    y = A @ x
+    idx = np.sort(np.random.default_rng(777).choice(s.ndof, 4096, replace=False))
+    np.savez_compressed(os.path.join(OUT, "team4_samples.npz"), ndof=np.array(s.ndof), idx=idx, y=y[idx], diag=A.diagonal()[idx],
+                        xdoty=np.array(x @ y), ynorm2=np.array(y @ y), ymax=np.array(np.abs(y).max()))
+    print("team4", s.ndof, "dofs", A.nnz, "nnz")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     if sys.argv[1:] == ["irises"]:
         return irises()
+    if sys.argv[1:] == ["team4"]:
+        return team4()
     irises()
     meshes = {
         "beam_tet": om.read_mfem_mesh(os.path.join(DATA, "beam-tet.mesh")),

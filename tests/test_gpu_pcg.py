@@ -3,6 +3,7 @@ DefaultJacobiPCGSolver (/root/reference/src/solvers/hephaestus_solvers.hpp:34-57
 import numpy as np
 import pytest
 
+from hephaestus_b200 import _lib as L
 from hephaestus_b200 import operators
 from oracle import assemble as oa
 from oracle import pcg as opcg
@@ -144,3 +145,42 @@ def test_pcg_chebyshev_matches_oracle(ctx, kind, n, p, order):
     s.SetOperator(op)
     s.Mult(b)
     assert s.converged and s.lambda_max() != lam0
+
+
+def test_graph_loop_is_used_and_equals_the_host_loop(ctx):
+    """Element-wise apply kernels (tets; perturbed hexes), single rank, Jacobi: the Krylov loop runs as one CUDA graph
+    with a device-side WHILE node.  Same iteration count and solution as the oracle's hypre-semantics loop, the iteration
+    limit is honoured, a second solve replays the graph, and a change of the essential dofs rebuilds it."""
+    op, Ac, sp = _setup(ctx, "tet", 3, 1, alpha_scale=0.05)
+    b = Ac @ np.random.default_rng(54321).standard_normal(sp.ndof)
+    s = operators.HephGpuPCG(ctx, tol=1e-9, max_iter=5000)
+    s.SetOperator(op)
+    x = s.Mult(b)
+    assert s.last_used_graph()
+    xo, it, res, conv, hist = opcg.pcg(Ac, b, diag=Ac.diagonal(), rtol=s.tol, atol=s.abstol, max_iter=5000)
+    assert s.converged and conv and abs(s.num_iterations - it) <= 2
+    assert rel_err(x, xo) < 1e-6
+    assert s.final_rel_res < s.tol
+    x2 = s.Mult(2.0 * b)                      # replay
+    assert s.last_used_graph() and s.converged and rel_err(x2, 2.0 * xo) < 1e-6
+    s.max_iter = 7                            # iteration limit
+    L.check(L.lib().hcurl_pcg_set(s.h, s.tol, s.abstol, 7, 0), "hcurl_pcg_set")
+    s.Mult(b)
+    assert s.num_iterations == 7 and not s.converged
+    _, it7, res7, _, _ = opcg.pcg(Ac, b, diag=Ac.diagonal(), rtol=s.tol, atol=s.abstol, max_iter=7)
+    assert abs(s.final_rel_res - res7) <= 1e-6 * res7
+    # other essential dofs: the operator's device maps are reallocated, the graph is rebuilt
+    ess2 = sp.boundary_dofs()[::2]
+    op.SetEssentialTrueDofs(ess2)
+    L.check(L.lib().hcurl_pcg_set(s.h, s.tol, s.abstol, 5000, 0), "hcurl_pcg_set")
+    s.SetOperator(op)
+    from oracle import assemble as oa2
+    m, sp_, mo, so = make_pair("tet", 3, 1, True)
+    # (the same mesh and coefficients as _setup: rebuild the eliminated matrix for the new essential set)
+    a, bb = coefficients(m)
+    A2, _ = oa2.eliminate(oa2.assemble(so, 0.05 * a, bb), ess2)
+    b2 = A2 @ np.random.default_rng(5).standard_normal(sp.ndof)
+    x3 = s.Mult(b2)
+    xo3, it3, _, conv3, _ = opcg.pcg(A2, b2, diag=A2.diagonal(), rtol=s.tol, atol=s.abstol, max_iter=5000)
+    assert s.last_used_graph() and s.converged and conv3 and abs(s.num_iterations - it3) <= 2
+    assert rel_err(x3, xo3) < 1e-6
