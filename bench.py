@@ -228,6 +228,33 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+# ---- correctness gate of every bench run (hex meshes of parallelepipeds): the closed-form energy of a rigid motion -------
+PARITY_W = np.array([0.3, -0.7, 1.1])     # u = w x r / 2 + c: curl u = w, held exactly by the Nedelec space of any order
+PARITY_C = np.array([0.5, 0.25, -1.0])
+PARITY_S = 0.5 * np.array([[0, -PARITY_W[2], PARITY_W[1]], [PARITY_W[2], 0, -PARITY_W[0]], [-PARITY_W[1], PARITY_W[0], 0]])
+
+
+def parity_field(X):
+    return X @ PARITY_S.T + PARITY_C
+
+
+def parity_energy(dims):
+    """int alpha |curl u|^2 + beta |u|^2 over the box [0,px] x [0,py] x [0,pz] with the bench's two attributes (split at
+    x = px / 2): the value x_u^T A x_u must take for the interpolant x_u of u (tests/test_zy_fullsize_properties.py)"""
+    px, py, pz = dims
+    e = 0.0
+    for attr, (x0, x1) in ((1, (0.0, 0.5 * px)), (2, (0.5 * px, float(px)))):
+        lo, hi = np.array([x0, 0.0, 0.0]), np.array([x1, float(py), float(pz)])
+        vol = np.prod(hi - lo)
+        m1 = vol * 0.5 * (lo + hi)
+        m2 = np.outer(m1, m1) / vol
+        m2[np.diag_indices(3)] = vol * (hi ** 3 - lo ** 3) / (3.0 * (hi - lo))
+        a, b = coefficients(np.array([attr]))
+        e += a[0] * (PARITY_W @ PARITY_W) * vol
+        e += b[0] * (np.trace(PARITY_S.T @ PARITY_S @ m2) + 2.0 * PARITY_C @ PARITY_S @ m1 + (PARITY_C @ PARITY_C) * vol)
+    return e
+
+
 def workload_config(args, n, n_dof, bounded=False):
     return {
         "workload": "synthetic structured %s cube %d^3 per GPU%s, order-%d Nedelec, K(dt*nu)+M(sigma) apply, %d DOFs%s" % (
@@ -304,6 +331,27 @@ def main():
     op.SetCoefficients(alpha, beta)
     op.SetEssentialTrueDofs(ess)
     t_setup = time.perf_counter() - t_setup
+    # ---------------- correctness gate: closed-form energy through the operator as set up (all ranks, exchange included) ----
+    nrank_parity = None
+    if args.geom == "hex" and not args.perturbed:
+        x_l = fespace.interpolate_affine_hex(space, parity_field)
+        if world == 1:
+            x_t = x_l
+        else:
+            own = np.nonzero(lp.local.ldof_ltdof >= 0)[0]
+            x_t = np.empty(n_tdof)
+            x_t[lp.local.ldof_ltdof[own]] = x_l[own]
+        y_t = op.MultUnconstrained(x_t)
+        e_loc = float(x_t @ y_t)
+        if dist is not None:
+            t = torch.tensor([e_loc], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t)
+            e_loc = float(t.item())
+        e_ref = parity_energy((1, 1, 1) if world == 1 else lp.dims)
+        nrank_parity = abs(e_loc - e_ref) / e_ref
+        del x_l, x_t, y_t
+        if nrank_parity > 1e-9:
+            raise SystemExit("bench: correctness gate failed: energy %.15g, closed form %.15g (rel %.2e)" % (e_loc, e_ref, nrank_parity))
     nd = gsp.nd
     rng = np.random.default_rng(12345 + rank)
     x = rng.standard_normal(n_tdof)
@@ -444,6 +492,7 @@ def main():
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, n, n_dof_global),
+        "nrank_parity": nrank_parity,
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "pcg": {"iters_per_s": 1e3 / pcg_iter_ms if pcg_iter_ms > 0 else 0.0, "ms_per_iter": pcg_iter_ms, "iters": solver.num_iterations,
                 "precond": "jacobi", "gdofs": n_dof_global / (pcg_iter_ms * 1e-3) / 1e9,

@@ -111,6 +111,7 @@ SIGNATURES = {
     "hcurl_host_patches_owned": (C.c_int64, [_P, _P, _P]),
     "hcurl_host_modal_tables_p2": (C.c_int, [_P]),
     "hcurl_host_hex_slot_codes": (C.c_int, [C.c_int, C.c_int64, _P, _P]),
+    "hcurl_host_hex_dof_nodes": (C.c_int, [C.c_int, _P, _P]),
     "hcurl_host_patches_create": (_P, [C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int64, _P, _P, _P]),
     "hcurl_host_patches_destroy": (None, [_P]),
     "hcurl_host_patches_count": (C.c_int64, [_P]),

@@ -566,6 +566,8 @@ hcurl_space *hcurl_space_create(hcurl_ctx *ctx, int geom, int geom_order, int or
     HC_CUDA_NULL(cudaMalloc(&sp->d_faceR, sizeof(double) * R.size()));
     HC_CUDA_NULL(h2d_sync(ctx, sp->d_faceR, R.data(), sizeof(double) * R.size()));
   }
+  // ---- several ranks: map the neighbours' landing buffers for the peer-memory exchange (collective; comm.cu)
+  if (ctx->nranks > 1 && p2p_setup(sp)) { hcurl_space_destroy(sp); return nullptr; }
   return sp;
 }
 
@@ -577,6 +579,7 @@ void hcurl_space_destroy(hcurl_space *sp) {
   hex_patch_free(sp);
   cudaFree(sp->d_mapT); cudaFree(sp->d_xyzT);
   cudaFree(sp->d_xyz); cudaFree(sp->d_map); cudaFree(sp->d_faceR); cudaFree(sp->d_own_idx);
+  p2p_free(sp);
   cudaFree(sp->d_ghost_sign); cudaFree(sp->d_sendbuf); cudaFree(sp->d_recvbuf);
   delete sp;
 }

@@ -397,3 +397,30 @@ void tri_face_transform(int p, const int32_t *lv, const int32_t *bv, double *R) 
 }
 
 }  // namespace hcurl
+
+// Nodes and tangents of the Nedelec hex dof functionals in MFEM's local order: dof_l(v) = t_l . v(node_l) on the reference
+// element (open points: Gauss-Legendre, closed points: Gauss-Lobatto -- the nodal basis the kernels use).  Host only:
+// interpolation of given fields for parity / property checks (hephaestus_b200/fespace.py: interpolate_affine_hex).
+extern "C" int hcurl_host_hex_dof_nodes(int p, double *nodes, double *tang) {
+  if (p < 1 || p > 4 || !nodes || !tang) { hcurl::set_error("hcurl_host_hex_dof_nodes: order 1..4 and two [nd][3] arrays needed"); return 1; }
+  using namespace hcurl;
+  std::vector<int> loc, sgn;
+  nd_hex_dof_map(p, loc, sgn);
+  double op[8], cp[8], w[8];
+  gauss_legendre01(p, op, w);
+  gauss_lobatto01(p + 1, cp);
+  const int nd = nd_hex_ndof(p);
+  for (int i = 0; i < nd * 3; i++) { nodes[i] = 0.0; tang[i] = 0.0; }
+  for (int c = 0; c < 3; c++) {
+    const int n0 = c == 0 ? p : p + 1, n1 = c == 1 ? p : p + 1, n2 = c == 2 ? p : p + 1;
+    for (int k = 0; k < n2; k++)
+      for (int j = 0; j < n1; j++)
+        for (int i = 0; i < n0; i++) {
+          const int idx[3] = {i, j, k};
+          const int t = tensor_index(p, c, i, j, k), l = loc[t];
+          for (int d = 0; d < 3; d++) nodes[l * 3 + d] = d == c ? op[idx[d]] : cp[idx[d]];
+          tang[l * 3 + c] = (double)sgn[t];
+        }
+  }
+  return 0;
+}

@@ -168,6 +168,8 @@ struct Nccl;  // dlopen'ed function table (comm.cpp)
 
 }  // namespace hcurl
 
+namespace hcurl { struct P2PExchange; }
+
 struct hcurl_ctx {
   int device = 0;
   int rank = 0, nranks = 1;
@@ -213,6 +215,7 @@ struct hcurl_space {
   int32_t *d_own_idx = nullptr;             // ext indices of own-shared dofs (concatenated)
   int8_t *d_ghost_sign = nullptr;           // [n_ghost] or null
   double *d_sendbuf = nullptr, *d_recvbuf = nullptr;  // size own_off.back()
+  hcurl::P2PExchange *p2p = nullptr;  // shared-dof exchange through NVLink peer memory (comm.cu), null = NCCL send / recv
   std::vector<int32_t> ldof_to_ext;  // host copy (for essential dofs etc.)
   std::vector<int32_t> own_ext;      // host copy of d_own_idx
   // fast order-2 path (hex_fast.cu): dof-major map / vertices, affine classification
@@ -326,6 +329,10 @@ int tet_apply_complex_launch(hcurl_op *op_re, hcurl_op *op_im, const uint32_t *d
 int exchange_broadcast(hcurl_space *sp, double *d_ext, cudaStream_t stream = nullptr);
 int exchange_reduce(hcurl_space *sp, double *d_ext, bool signed_values = true, cudaStream_t stream = nullptr);
 int allreduce_sum(hcurl_ctx *ctx, double *d_vals, int n);
+int p2p_setup(hcurl_space *sp);   // collective over the communicator: every rank calls it at space creation
+void p2p_free(hcurl_space *sp);
+int p2p_setup(hcurl_space *sp);   // collective over the communicator: every rank calls it at space creation
+void p2p_free(hcurl_space *sp);
 int comm_init(hcurl_ctx *ctx, const void *uid);
 void comm_destroy(hcurl_ctx *ctx);
 int comm_unique_id(void *out128);

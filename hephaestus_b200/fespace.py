@@ -434,3 +434,30 @@ class NativeNDSpace:
 
 
 NativeHexNDSpace = NativeNDSpace
+
+
+def interpolate_affine_hex(space, func, chunk=1 << 17):
+    """Nodal ND interpolant (GridFunction::ProjectCoefficient) of a vector field on a mesh of parallelepiped hexes, from
+    the signed element -> dof map (MFEM convention: -1-k = flipped) and the dof functionals dof = (J t) . F(x(node))
+    (hcurl_host_hex_dof_nodes).  Chunked over elements so that it also runs at the bench size (2 M hexes, 50 M dofs).
+    Checked against the oracle's own projection in tests/test_zy_fullsize_properties.py."""
+    from . import _lib as L
+    mesh = space.mesh
+    nd = 3 * space.p * (space.p + 1) ** 2
+    nodes, tang = np.zeros((nd, 3)), np.zeros((nd, 3))
+    L.check(L.lib().hcurl_host_hex_dof_nodes(space.p, L.ptr(nodes), L.ptr(tang)), "hcurl_host_hex_dof_nodes")
+    sd = space.signed_elem_dofs()
+    out = np.zeros(space.ndof)
+    for e0 in range(0, mesh.n_elem, chunk):
+        X = mesh.verts[mesh.elems[e0:e0 + chunk]]  # (ne, 8, 3), MFEM vertex order
+        v0 = X[:, 0]
+        J = np.stack([X[:, 1] - v0, X[:, 3] - v0, X[:, 4] - v0], axis=2)  # columns = edge vectors
+        ne = len(X)  # (ne*3, 3) @ (3, nd): one GEMM instead of ne small ones
+        xq = v0[:, None, :] + (J.reshape(ne * 3, 3) @ nodes.T).reshape(ne, 3, -1).transpose(0, 2, 1)
+        Jt = (J.reshape(ne * 3, 3) @ tang.T).reshape(ne, 3, -1).transpose(0, 2, 1)
+        F = np.asarray(func(xq.reshape(-1, 3))).reshape(xq.shape)
+        loc = np.einsum("eni,eni->en", Jt, F)
+        s = sd[e0:e0 + chunk]
+        flip = s < 0
+        out[np.where(flip, -1 - s, s).reshape(-1)] = np.where(flip, -loc, loc).reshape(-1)
+    return out

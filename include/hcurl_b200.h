@@ -401,6 +401,11 @@ int hcurl_host_exodus_read(const hcurl_host_exodus *x, double *xyz, int32_t *con
  * returns achieved TFLOP/s of dependent-chain-free DFMA on the device. */
 double hcurl_fp64_peak_tflops(hcurl_ctx *ctx);
 
+/* Host-side helper (no GPU): nodes[nd][3] and tangents[nd][3] of the Nedelec hex dof functionals in MFEM's local order,
+ * dof_l(v) = t_l . v(node_l) on the reference element (ND_HexahedronElement's Gauss-Legendre / Gauss-Lobatto nodal basis;
+ * what GridFunction::ProjectCoefficient evaluates).  Used to interpolate given fields for parity and property checks. */
+int hcurl_host_hex_dof_nodes(int order, double *nodes, double *tang);
+
 #ifdef __cplusplus
 }
 #endif
