@@ -861,17 +861,17 @@ int hcurl_op_form_rhs(hcurl_op *op, const double *x_bc, const double *b, double 
   if (ensure_work(op)) return 1;
   const int64_t nt = sp->n_tdof, next = sp->n_ext();
   // d_xin = x_bc restricted to essential dofs, d_yout = b - A_unconstrained d_xin, then B[ess] = x_bc[ess]
-  double *xfull = nullptr;
-  HC_CUDA(cudaMalloc(&xfull, sizeof(double) * next));
+  // (x_bc is staged in the operator's second work vector, allocated once: this runs every time step)
+  if (!op->d_xin2) HC_CUDA(cudaMalloc(&op->d_xin2, sizeof(double) * next));
+  double *xfull = op->d_xin2;
   HC_CUDA(cudaMemcpyAsync(xfull, x_bc, sizeof(double) * nt, kind_in(where), ctx->stream));
   HC_CUDA(cudaMemsetAsync(op->d_xin, 0, sizeof(double) * next, ctx->stream));
   if (op->n_ess > 0) copy_idx_kernel<<<(op->n_ess + 255) / 256, 256, 0, ctx->stream>>>(op->n_ess, op->d_ess, xfull, op->d_xin);
   HC_CUDA(cudaMemcpyAsync(op->d_yout, b, sizeof(double) * nt, kind_in(where), ctx->stream));
-  if (op_apply_ext(op, op->d_xin, op->d_yout, false, -1.0, true)) { cudaFree(xfull); return 1; }
+  if (op_apply_ext(op, op->d_xin, op->d_yout, false, -1.0, true)) return 1;
   if (op->n_ess > 0) copy_idx_kernel<<<(op->n_ess + 255) / 256, 256, 0, ctx->stream>>>(op->n_ess, op->d_ess, xfull, op->d_yout);
   HC_CUDA(cudaMemcpyAsync(B, op->d_yout, sizeof(double) * nt, kind_out(where), ctx->stream));
   HC_CUDA(cudaStreamSynchronize(ctx->stream));
-  cudaFree(xfull);
   return 0;
 }
 
