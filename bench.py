@@ -238,12 +238,14 @@ def parity_field(X):
     return X @ PARITY_S.T + PARITY_C
 
 
-def parity_energy(dims):
-    """int alpha |curl u|^2 + beta |u|^2 over the box [0,px] x [0,py] x [0,pz] with the bench's two attributes (split at
-    x = px / 2): the value x_u^T A x_u must take for the interpolant x_u of u (tests/test_zy_fullsize_properties.py)"""
+def parity_energy(dims, nx):
+    """int alpha |curl u|^2 + beta |u|^2 over the box [0,px] x [0,py] x [0,pz] of nx cells along x with the bench's two
+    attributes (attribute 1 for cells whose centre lies left of px / 2, fespace.cartesian_hex_mesh): the value x_u^T A x_u
+    must take for the interpolant x_u of u (tests/test_zy_fullsize_properties.py)"""
     px, py, pz = dims
+    xs = px * float(nx // 2) / nx   # cells i with i + 1/2 < nx / 2
     e = 0.0
-    for attr, (x0, x1) in ((1, (0.0, 0.5 * px)), (2, (0.5 * px, float(px)))):
+    for attr, (x0, x1) in ((1, (0.0, xs)), (2, (xs, float(px)))):
         lo, hi = np.array([x0, 0.0, 0.0]), np.array([x1, float(py), float(pz)])
         vol = np.prod(hi - lo)
         m1 = vol * 0.5 * (lo + hi)
@@ -347,7 +349,7 @@ def main():
             t = torch.tensor([e_loc], dtype=torch.float64, device="cuda")
             dist.all_reduce(t)
             e_loc = float(t.item())
-        e_ref = parity_energy((1, 1, 1) if world == 1 else lp.dims)
+        e_ref = parity_energy((1, 1, 1) if world == 1 else lp.dims, n if world == 1 else n * lp.dims[0])
         nrank_parity = abs(e_loc - e_ref) / e_ref
         del x_l, x_t, y_t
         if nrank_parity > 1e-9:

@@ -207,6 +207,7 @@ struct P2Elem {
   static constexpr int ROWS = 27;
   double A[3][18];  // nodal (s, d) values -> modal coefficients -> modal test values
   double G[12];     // GK (6) | GM (6), packed symmetric
+  uint32_t rev;     // !GENERAL: bit c*9 + r = slot pair (c, r) is a reversed line (kept from the pull for the result store)
 
   template <class Env> HCURL_BODY void geometry(Env &env, const PatchArgs &a, const int64_t k, const int el) {
     const double *g = a.edata + (size_t)k * 12 * FE + el;  // [12][FE] per patch: coalesced
@@ -214,6 +215,7 @@ struct P2Elem {
     for (int s = 0; s < 12; s++) G[s] = env.ldg(g + s * FE);
   }
   template <class Env> HCURL_BODY void pull(Env &, const PatchArgs &a, const double2 *Xs, const uint16_t *lidx) {
+    rev = 0u;
 #pragma unroll
     for (int c = 0; c < 3; c++) {
       double X[18];
@@ -229,6 +231,7 @@ struct P2Elem {
         } else {
           X[2 * r] = p2_flip(v.x + v.y, (l << 16) & 0x80000000u);
           X[2 * r + 1] = v.y - v.x;
+          rev |= ((l >> 15) & 1u) << (c * 9 + r);
         }
       }
       p2s_fwd_sd(a.modal, X, A[c]);
@@ -250,11 +253,12 @@ struct P2Elem {
       double2 *Eown = EY + (c * 9) * ST;
 #pragma unroll
       for (int r = 0; r < 9; r++) {
-        const uint32_t l = lidx[(c * 9 + r) * FE];  // orientation flags again (the table is still in shared memory)
         double2 v;
-        if (GENERAL) v = p2_local_to_pair(Y[2 * r] - Y[2 * r + 1], Y[2 * r] + Y[2 * r + 1], l);
-        else {
-          const double b0 = p2_flip(Y[2 * r], (l << 16) & 0x80000000u);
+        if (GENERAL) {
+          const uint32_t l = lidx[(c * 9 + r) * FE];  // orientation flags again (the table is still in shared memory)
+          v = p2_local_to_pair(Y[2 * r] - Y[2 * r + 1], Y[2 * r] + Y[2 * r + 1], l);
+        } else {
+          const double b0 = p2_flip(Y[2 * r], (rev << (31 - (c * 9 + r))) & 0x80000000u);
           v = make_double2(b0 - Y[2 * r + 1], b0 + Y[2 * r + 1]);
         }
         Eown[r * ST + (elx ^ a.swz_row[c * 9 + r])] = v;

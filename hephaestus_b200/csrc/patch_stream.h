@@ -171,10 +171,20 @@ HCURL_BODY void patch_stream(Env &env, const PatchArgs &a) {
       gather(1, 1);
     }
     if (!ACC) {  // prologue: zeros under the shared units my patches of iterations [0, 2 ZB) own
-      for (int j = 0; j < 2 * ZB && j < n_it; j++) {
-        const int64_t p = k0 + (int64_t)j * kstep;
-        const uint32_t u1 = env.ldg(a.own_off + p + 1);
-        for (uint32_t u = env.ldg(a.own_off + p) + dt; u < u1; u += ND) yu[env.ldg(a.own_idx + u)] = Unit::zero();
+      // the extents of the 2 ZB owned lists are loaded by 4 ZB threads at once and handed over through shared memory (the
+      // result buffer is unused until the element warps store patch 0, which they do after the XS_FULL signal below), so
+      // that the index loads of all patches are independent
+      constexpr int NJ = 2 * ZB;
+      uint32_t *ext = reinterpret_cast<uint32_t *>(bufE);  // [2 NJ]
+      for (int j = dt; j < 2 * NJ; j += ND) {
+        const int jj = j >> 1;
+        ext[j] = jj < n_it ? env.ldg(a.own_off + k0 + (int64_t)jj * kstep + (j & 1)) : 0u;
+      }
+      env.group_sync();
+#pragma unroll 4
+      for (int j = 0; j < NJ; j++) {
+        const uint32_t u1 = ext[2 * j + 1];
+        for (uint32_t u = ext[2 * j] + dt; u < u1; u += ND) yu[env.ldg(a.own_idx + u)] = Unit::zero();
       }
     }
     if (n_it > 1) env.gather_wait_prev(); else env.gather_wait();
