@@ -420,3 +420,37 @@ def test_batch_apply_matches_single_applies(ctx):
     op.ArrayMult([px[0], px[1], px[0]], [py[0], py[1], py[0]])
     assert rel_err(py[0], ref[0]) < 1e-13 and rel_err(py[1], ref[1]) < 1e-13
     assert op.ArrayMult([]) == []
+
+
+def test_patch_apply_run_to_run(ctx):
+    """What repeats bit for bit and what does not: a unit (dof pair) written by one patch is stored, one
+    shared by two patches receives 0 + a + b -- both independent of the order in which the persistent grid gets to the
+    patches; only the units shared by three or more patches (the dof lines along patch edges, ~2 % of the units) receive
+    their RED-adds in arrival order and may differ in the last bits between two applies."""
+    from hephaestus_b200 import fespace
+    from patch_emu_util import build_patches
+    n = 24
+    m = fespace.cartesian_hex_mesh(n, n, n)
+    sp = fespace.NativeNDSpace(m, 2)
+    gsp = operators.GpuNDSpace(ctx, sp)
+    op = operators.HephGpuOperator(ctx, gsp, 3)
+    a, b = coefficients(m)
+    op.SetCoefficients(a, b)
+    op.SetEssentialTrueDofs(sp.boundary_dofs())
+    x = np.random.default_rng(99).standard_normal(sp.ndof)
+    y0 = op.Mult(x)
+    assert op.LastKernel() == 3
+    P = build_patches(sp, m, 2, 64)
+    touched = np.zeros(sp.ndof // 2, np.int32)
+    for k in range(len(P["off"]) - 1):
+        B = P["blob"][int(P["off"][k]) * 4:]
+        np.add.at(touched, (B[32:32 + int(B[0])] & 0x0FFFFFFF).astype(np.int64), 1)
+    assert touched.min() >= 1
+    multi = np.repeat(touched >= 3, 2)
+    assert 0 < multi.mean() < 0.1
+    worst = 0.0
+    for _ in range(6):
+        y = op.Mult(x)
+        assert np.array_equal(y[~multi], y0[~multi])
+        worst = max(worst, float(np.abs(y[multi] - y0[multi]).max()))
+    assert worst <= 64 * np.finfo(float).eps * np.abs(y0).max()
