@@ -454,9 +454,11 @@ def main():
                 "kernel": "tet batched packed-symmetric element-matrix kernel (order %d)" % p if args.geom == "tet" else
                 "hex element kernel (order %d; %s)" % (
                     p, {1: "generic sum-factorised", 2: "element-wise register-blocked",
-                        3: ("patch kernel, warp-specialised streams: 2 element warps (one thread per element, modal operator) + 4 dof warps per "
-                            "64-element patch, setmaxnreg, mbarrier rings, persistent, zero-ahead watermark"
-                            if p == 2 and os.environ.get("HCURL_PATCH_STREAM", "1") != "0" and os.environ.get("HCURL_PATCH_FE", "64") == "64" else
+                        3: ("patch kernel, warp-specialised stream: 4 element warps (one thread per element, modal operator) + 12 dof warps per "
+                            "128-element patch, setmaxnreg, mbarrier rings, persistent, zero-ahead watermark"
+                            if p == 2 and os.environ.get("HCURL_PATCH_STREAM", "1") != "0" and os.environ.get("HCURL_PATCH_FE", "128") == "128" else
+                            "patch kernel, warp-specialised streams: 2 element warps + 4 dof warps per 64-element patch"
+                            if p == 2 and os.environ.get("HCURL_PATCH_STREAM", "1") != "0" and os.environ.get("HCURL_PATCH_FE") == "64" else
                             "patch pipeline: one thread per element, modal operator, persistent, zero-ahead watermark")}.get(op.LastKernel(), "?")),
                 "kernel_ms": kern_ms, "kernel_launches_timed": kern_n, "algorithmic_bytes_per_launch": abytes,
                 "bytes_per_dof": abytes / n_tdof, "kernel_share_of_step": kern_ms / ms_step if ms_step > 0 else None,

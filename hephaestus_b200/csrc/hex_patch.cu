@@ -166,17 +166,18 @@ int hex_patch_build(hcurl_space *sp, const double *elem_xyz, const int32_t *elem
   const char *off = getenv("HCURL_NO_PATCH");
   if (off && off[0] == '1') return 0;
   const bool p2 = sp->order == 2;
-  // Elements per patch and kernel.  Order 2: 64-element patches through the warp-specialised kernel (patch_stream.h)
-  // when its two streams fit into one CTA's shared memory, else 32-element patches through the single-warp pipeline
+  // Elements per patch and kernel.  Order 2: the warp-specialised kernel (patch_stream.h) with 128-element patches (one
+  // stream per SM: four element warps + twelve dof warps) when that fits into one CTA's shared memory, else with
+  // 64-element patches (two streams of 2 + 4 warps), else 32-element patches through the single-warp pipeline
   // (patch_pipeline.h; irregular meshes have longer unit lists).  Order 1: 128 (fastest of 64 / 128 / 256).
   // HCURL_PATCH_FE fixes the patch size, HCURL_PATCH_STREAM=0 the single-warp pipeline (measurements, tests).
-  int FE = p2 ? 64 : 128;
+  int FE = 128;
   bool fe_fixed = false, want_stream = p2;
   if (const char *s = getenv("HCURL_PATCH_STREAM")) want_stream = p2 && atoi(s) != 0;
   if (p2 && !want_stream) FE = 32;
   if (const char *s = getenv("HCURL_PATCH_FE")) { FE = atoi(s); fe_fixed = true; }
-  if (p2 ? (FE != 32 && FE != 64) : (FE != 32 && FE != 64 && FE != 128 && FE != 256)) {
-    set_error(p2 ? "HCURL_PATCH_FE must be 32 or 64 for order 2" : "HCURL_PATCH_FE must be 32, 64, 128 or 256 for order 1");
+  if (p2 ? (FE != 32 && FE != 64 && !(FE == 128 && want_stream)) : (FE != 32 && FE != 64 && FE != 128 && FE != 256)) {
+    set_error(p2 ? "HCURL_PATCH_FE must be 32, 64 or (stream kernel only) 128 for order 2" : "HCURL_PATCH_FE must be 32, 64, 128 or 256 for order 1");
     return 1;
   }
   const int64_t ne = sp->n_elem;
@@ -205,18 +206,22 @@ int hex_patch_build(hcurl_space *sp, const double *elem_xyz, const int32_t *elem
     for (int32_t d : sp->own_ext) xch[(size_t)(d / per)] = 1;
   }
   PatchHost H;
-  if (build_patches(nu, ne, FE, FE + 1, unit, n_units, cen.data(), code.data(), xch.empty() ? nullptr : xch.data(), H)) return 1;
-  if (p2 && FE == 64 && want_stream) {
+  const uint8_t *xchp = xch.empty() ? nullptr : xch.data();
+  for (;;) {
+    H = PatchHost();
+    if (build_patches(nu, ne, FE, FE + 1, unit, n_units, cen.data(), code.data(), xchp, H)) {
+      if (p2 && FE == 128 && !fe_fixed) { FE = 64; continue; }  // (e.g. the 16-bit slot offsets do not reach: try smaller patches)
+      return 1;
+    }
+    if (!(p2 && FE >= 64 && want_stream)) break;
     int optin = 0;
     HC_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, sp->ctx->device));
-    const size_t need = 2 * patch_stream_smem_bytes(64, H.max_d_words * 4, H.max_l_words * 4, H.max_t_words * 4, (H.max_dofs * 16u + 15u) & ~15u) + 1024;
+    const size_t need = (128 / FE) * patch_stream_smem_bytes(FE, H.max_d_words * 4, H.max_l_words * 4, H.max_t_words * 4, (H.max_dofs * 16u + 15u) & ~15u) + 2048;
     P.stream = sp->ctx->coop_ok && H.max_dofs <= 8191 && need <= (size_t)optin;
-    if (!P.stream && !fe_fixed) {  // the single-warp pipeline is fastest with 32-element patches
-      FE = 32;
-      H = PatchHost();
-      if (build_patches(nu, ne, FE, FE + 1, unit, n_units, cen.data(), code.data(), xch.empty() ? nullptr : xch.data(), H)) return 1;
-    }
+    if (P.stream || fe_fixed) break;
+    FE = FE == 128 ? 64 : 32;  // 64-element streams next; the single-warp pipeline is fastest with 32-element patches
   }
+  if (p2 && FE == 128 && !P.stream) { set_error("HCURL_PATCH_FE=128 (order 2) needs the stream kernel, which does not fit this mesh's patches into shared memory"); return 1; }
   if (H.max_dofs > 8191) return 0;  // 13-bit staging positions
   P.FE = FE; P.unit = unit; P.stride = H.stride; P.n_patch = H.n_patch; P.n_boundary = H.n_boundary;
   P.blob_words = (int64_t)H.blob.size(); P.max_d_words = H.max_d_words; P.max_l_words = H.max_l_words; P.max_t_words = H.max_t_words;

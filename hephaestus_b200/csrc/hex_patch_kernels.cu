@@ -129,10 +129,16 @@ __global__ void __launch_bounds__(FE) hex_patch_p1_kernel(const PatchArgs a) {
 // file -- the kernel is launched at <= 168 registers per thread, the element warp group then takes 248 and the dof warp
 // groups drop to 72.  (The same program with 32-element patches -- four streams of 1 + 3 warps -- measured 4 % slower:
 // profiles/README.md; it still runs in the host emulation, tests/test_patch_p2_emu.py.)
+#ifndef HCURL_STREAM_REG_DOF
+#define HCURL_STREAM_REG_DOF 72
+#endif
 template <int FE_, int ND_, int NSTREAM_>
 struct StreamDeviceEnv : PatchDeviceEnv {
   static constexpr int FE = FE_, ND = ND_, NSTREAM = NSTREAM_, NTHREADS = NSTREAM * (FE + ND);
-  static constexpr int REG_ELEMENT = 248, REG_DOF = 72;
+  static constexpr int REG_ELEMENT = 248, REG_DOF = HCURL_STREAM_REG_DOF;
+  // setmaxnreg re-distributes the registers the CTA was LAUNCHED with (at most 65536 / NTHREADS per thread, in steps of 8):
+  // an increase beyond that pool waits forever
+  static_assert(128 * REG_ELEMENT + NSTREAM * ND * REG_DOF <= ((65536 / NTHREADS) & ~7) * NTHREADS, "register pool of the CTA");
   static constexpr int FLAG0 = 8;  // mbarriers 0..6: bulk copies (D0 D1 D2 D3 L T0 T1); 8..13: flags
   static_assert(NSTREAM * FE == 128, "the element warps are exactly warp group 0");
   int tid_, s_;
@@ -189,7 +195,14 @@ struct StreamDeviceEnv : PatchDeviceEnv {
     }
   }
 };
-typedef StreamDeviceEnv<64, 128, 2> StreamEnv64;
+#ifndef HCURL_STREAM64_ND
+#define HCURL_STREAM64_ND 128
+#endif
+typedef StreamDeviceEnv<64, HCURL_STREAM64_ND, 2> StreamEnv64;
+#ifndef HCURL_STREAM128_ND
+#define HCURL_STREAM128_ND 384
+#endif
+typedef StreamDeviceEnv<128, HCURL_STREAM128_ND, 1> StreamEnv128;  // one stream of four element warps + twelve dof warps: the default
 
 // shared memory of ONE stream (a CTA holds 128 / FE of them)
 size_t patch_stream_smem_bytes(int FE, uint32_t d_cap, uint32_t l_cap, uint32_t t_cap, uint32_t xs_cap) {
@@ -326,6 +339,7 @@ int hex_patch_kernel_launch(hcurl_op *op, const PatchArgs &a, bool accumulate) {
   if (!ctx->coop_ok) { set_error("the device does not support cooperative launches (needed by the patch kernels)"); return 1; }
   const size_t smem = patch_smem_bytes(P.unit, P.FE, a.d_cap_bytes, a.l_cap_bytes, a.t_cap_bytes, a.xs_cap_bytes);
   if (P.unit == 16) {
+    if (P.stream && P.FE == 128) return P.general_orient ? launch_stream<StreamEnv128, true>(ctx, &P, 12, a, accumulate) : launch_stream<StreamEnv128, false>(ctx, &P, 13, a, accumulate);
     if (P.stream) return P.general_orient ? launch_stream<StreamEnv64, true>(ctx, &P, 10, a, accumulate) : launch_stream<StreamEnv64, false>(ctx, &P, 11, a, accumulate);
     if (P.FE == 32) return P.general_orient ? launch_p2<32, true>(ctx, &P, 0, a, smem, accumulate) : launch_p2<32, false>(ctx, &P, 1, a, smem, accumulate);
     if (P.FE == 64) return P.general_orient ? launch_p2<64, true>(ctx, &P, 2, a, smem, accumulate) : launch_p2<64, false>(ctx, &P, 3, a, smem, accumulate);

@@ -36,7 +36,7 @@ int run_stream_mode(const hcurl::PatchArgs &a, int64_t streams, size_t smem, boo
 }
 }  // namespace
 
-// order 1 (fe = 32 / 64 / 128) or 2 (fe = 32 / 64; general = orientation handling with independent swap / sign bits)
+// order 1 (fe = 32 / 64 / 128) or 2 (fe = 32 / 64, stream program also 128; general = orientation handling with independent swap / sign bits)
 extern "C" int emu_patch_apply(int order, int fe, int general, int accumulate, int64_t n_patch, int64_t k_begin, int64_t grid,
                                const uint32_t *blob_off, const uint32_t *part_off, const uint32_t *blob, const double *edata,
                                const double *x, double *y, double scale, uint32_t d_cap_bytes, uint32_t l_cap_bytes,
@@ -61,6 +61,7 @@ extern "C" int emu_patch_apply(int order, int fe, int general, int accumulate, i
     if (grid < 1) return 0;
     if (FE == 32) return general ? run_stream_mode<32, 96, true>(a, grid, ssm, acc) : run_stream_mode<32, 96, false>(a, grid, ssm, acc);
     if (FE == 64) return general ? run_stream_mode<64, 128, true>(a, grid, ssm, acc) : run_stream_mode<64, 128, false>(a, grid, ssm, acc);
+    if (FE == 128) return general ? run_stream_mode<128, 384, true>(a, grid, ssm, acc) : run_stream_mode<128, 384, false>(a, grid, ssm, acc);
     return -2;
   }
   if (grid > n_patch - k_begin) grid = n_patch - k_begin;

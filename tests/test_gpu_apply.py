@@ -212,9 +212,9 @@ def test_hex_p2_fast_paths_match_generic_and_oracle(ctx, perturb, n):
     assert rel_err(op.Mult(x), oa.constrained_apply(A2, essd, x)) < TOL
 
 
-@pytest.mark.parametrize("fe", [32, 64])
+@pytest.mark.parametrize("fe", [32, 64, 128])
 def test_hex_p2_patch_kernel_patch_sizes(ctx, fe, monkeypatch):
-    """Patch kernel with 32 / 64 elements per patch on a mesh with several patches,
+    """Patch kernel with 32 / 64 / 128 elements per patch (128: one stream of four element warps) on a mesh with several patches,
     a skewed (non axis-aligned) affine geometry and a device-resident repeat (determinism of the
     private-dof stores, RED only on patch-boundary dofs)."""
     monkeypatch.setenv("HCURL_PATCH_FE", str(fe))
@@ -311,7 +311,7 @@ def test_hex_p1_patch_kernel(ctx, n, fe, monkeypatch):
 
 
 @pytest.mark.parametrize("general", ["0", "1"])
-@pytest.mark.parametrize("fe", ["32", "64"])
+@pytest.mark.parametrize("fe", ["32", "64", "128"])
 @pytest.mark.parametrize("n", [(9, 8, 6), (5, 4, 3)])
 def test_hex_p2_patch_kernel_variants(ctx, n, fe, general, monkeypatch):
     """hex_patch_p2_kernel with 32- / 64-element patches, reversed-line and general orientation handling, on a scrambled

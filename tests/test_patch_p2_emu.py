@@ -18,7 +18,7 @@ def emu(tmp_path_factory, lib_built):
     return build_emu_lib(tmp_path_factory)
 
 
-VARIANTS = [(32, False), (64, False), (32, True), (-32, False), (-32, True), (-64, False), (-64, True)]   # (elements per patch, general orientation handling); negative: the warp-specialised stream program (patch_stream.h)
+VARIANTS = [(32, False), (64, False), (32, True), (-32, False), (-32, True), (-64, False), (-64, True), (-128, False)]   # (elements per patch, general orientation handling); negative: the warp-specialised stream program (patch_stream.h)
 
 
 # (6,6,5) = 180 elements -> 6 patches of 32: with grid 1 / 2 the pipeline wraps around; scrambled vertex numbering makes
