@@ -167,8 +167,8 @@ int hex_patch_build(hcurl_space *sp, const double *elem_xyz, const int32_t *elem
   if (off && off[0] == '1') return 0;
   const bool p2 = sp->order == 2;
   // Elements per patch and kernel.  Order 2: the warp-specialised kernel (patch_stream.h) with 128-element patches (one
-  // stream per SM: four element warps + twelve dof warps) when that fits into one CTA's shared memory, else with
-  // 64-element patches (two streams of 2 + 4 warps), else 32-element patches through the single-warp pipeline
+  // stream per SM: four element, eight sum and four gather warps) when that fits into one CTA's shared memory, else
+  // 32-element patches through the single-warp pipeline
   // (patch_pipeline.h; irregular meshes have longer unit lists).  Order 1: 128 (fastest of 64 / 128 / 256).
   // HCURL_PATCH_FE fixes the patch size, HCURL_PATCH_STREAM=0 the single-warp pipeline (measurements, tests).
   int FE = 128;
@@ -210,7 +210,7 @@ int hex_patch_build(hcurl_space *sp, const double *elem_xyz, const int32_t *elem
   for (;;) {
     H = PatchHost();
     if (build_patches(nu, ne, FE, FE + 1, unit, n_units, cen.data(), code.data(), xchp, H)) {
-      if (p2 && FE == 128 && !fe_fixed) { FE = 64; continue; }  // (e.g. the 16-bit slot offsets do not reach: try smaller patches)
+      if (p2 && FE == 128 && !fe_fixed) { FE = 32; continue; }  // (e.g. the 16-bit slot offsets do not reach: smaller patches)
       return 1;
     }
     if (!(p2 && FE >= 64 && want_stream)) break;
@@ -219,7 +219,7 @@ int hex_patch_build(hcurl_space *sp, const double *elem_xyz, const int32_t *elem
     const size_t need = (128 / FE) * patch_stream_smem_bytes(FE, H.max_d_words * 4, H.max_l_words * 4, H.max_t_words * 4, (H.max_dofs * 16u + 15u) & ~15u) + 2048;
     P.stream = sp->ctx->coop_ok && H.max_dofs <= 8191 && need <= (size_t)optin;
     if (P.stream || fe_fixed) break;
-    FE = FE == 128 ? 64 : 32;  // 64-element streams next; the single-warp pipeline is fastest with 32-element patches
+    FE = 32;  // the single-warp pipeline, fastest with 32-element patches (two streams of 64-element patches -- HCURL_PATCH_FE=64 -- measured slower than it in the three-role form)
   }
   if (p2 && FE == 128 && !P.stream) { set_error("HCURL_PATCH_FE=128 (order 2) needs the stream kernel, which does not fit this mesh's patches into shared memory"); return 1; }
   if (H.max_dofs > 8191) return 0;  // 13-bit staging positions

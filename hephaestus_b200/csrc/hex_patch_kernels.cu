@@ -124,42 +124,43 @@ __global__ void __launch_bounds__(FE) hex_patch_p1_kernel(const PatchArgs a) {
 }
 
 // ---- warp-specialised order-2 kernels (patch_stream.h): one CTA per SM ---------------------------------------------------
-// 64-element patches: two streams of two element warps + four dof warps (12 warps).  Warps 0-3 are the element warps (warp
-// group 0, one per scheduler / FP64 pipe), the dof warps fill the other two warp groups: setmaxnreg moves the register
-// file -- the kernel is launched at <= 168 registers per thread, the element warp group then takes 248 and the dof warp
-// groups drop to 72.  (The same program with 32-element patches -- four streams of 1 + 3 warps -- measured 4 % slower:
-// profiles/README.md; it still runs in the host emulation, tests/test_patch_p2_emu.py.)
-#ifndef HCURL_STREAM_REG_DOF
-#define HCURL_STREAM_REG_DOF 72
-#endif
-template <int FE_, int ND_, int NSTREAM_>
+// 64-element patches: two streams of two element warps + four sum warps + two gather warps (16 warps).  Warps 0-3 are the
+// element warps (warp group 0, one per scheduler / FP64 pipe), warps 4-11 the sum warps (warp groups 1, 2), warps 12-15 the
+// gather warps (warp group 3): setmaxnreg moves the register file -- the kernel is launched at <= 128 registers per thread,
+// the element warp group then takes 248, the sum warp groups drop to 72 and the gather warp group to 56.  (The same program
+// with 32-element patches -- four streams -- measured 4 % slower in its two-role form: profiles/README.md; it still runs in
+// the host emulation, tests/test_patch_p2_emu.py.)
+template <int FE_, int ND_, int NG_, int NSTREAM_>
 struct StreamDeviceEnv : PatchDeviceEnv {
-  static constexpr int FE = FE_, ND = ND_, NSTREAM = NSTREAM_, NTHREADS = NSTREAM * (FE + ND);
-  static constexpr int REG_ELEMENT = 248, REG_DOF = HCURL_STREAM_REG_DOF;
-  // setmaxnreg re-distributes the registers the CTA was LAUNCHED with (at most 65536 / NTHREADS per thread, in steps of 8):
-  // an increase beyond that pool waits forever
-  static_assert(128 * REG_ELEMENT + NSTREAM * ND * REG_DOF <= ((65536 / NTHREADS) & ~7) * NTHREADS, "register pool of the CTA");
+  static constexpr int FE = FE_, ND = ND_, NG = NG_, NSTREAM = NSTREAM_, NTHREADS = NSTREAM * (FE + ND + NG);
+  static constexpr int REG_ELEMENT = 248, REG_SUM = 72, REG_GATHER = 56;
   static constexpr int FLAG0 = 8;  // mbarriers 0..6: bulk copies (D0 D1 D2 D3 L T0 T1); 8..13: flags
   static_assert(NSTREAM * FE == 128, "the element warps are exactly warp group 0");
+  static_assert((NSTREAM * ND) % 128 == 0 && (NSTREAM * NG) % 128 == 0, "setmaxnreg acts on whole warp groups");
+  // setmaxnreg re-distributes the registers the CTA was LAUNCHED with (at most 65536 / NTHREADS per thread, in steps of 8):
+  // an increase beyond that pool waits forever
+  static_assert(128 * REG_ELEMENT + NSTREAM * ND * REG_SUM + NSTREAM * NG * REG_GATHER <= ((65536 / NTHREADS) & ~7) * NTHREADS, "register pool of the CTA");
   int tid_, s_;
 #ifdef HCURL_PHASE_PROFILE
-  long long *sprof_;  // shared, per stream: [0..31] cycles by phase, [32] / [33] last time stamps of the element warp / the dof group
+  long long *sprof_;  // shared, per stream: [0..31] cycles by phase, [32] / [33] / [34] last time stamps of the element warp / the sum group / the gather group
   __device__ __forceinline__ void smark(int k) const {
-    if (tid_ == 0 || tid_ == FE) { long long *last = sprof_ + 32 + (tid_ != 0); const long long t = clock64(); sprof_[k] += t - *last; *last = t; }
+    if (tid_ == 0 || tid_ == FE || tid_ == FE + ND) { long long *last = sprof_ + 32 + (tid_ != 0) + (tid_ == FE + ND); const long long t = clock64(); sprof_[k] += t - *last; *last = t; }
   }
 #endif
   __device__ __forceinline__ int tid() const { return tid_; }
   __device__ __forceinline__ int64_t block() const { return (int64_t)blockIdx.x * NSTREAM + s_; }
   __device__ __forceinline__ int64_t nblocks() const { return (int64_t)gridDim.x * NSTREAM; }
-  __device__ __forceinline__ void sync() const { asm volatile("bar.sync %0, %1;" ::"r"(1 + s_), "n"(FE + ND) : "memory"); }
+  __device__ __forceinline__ void sync() const { asm volatile("bar.sync %0, %1;" ::"r"(1 + s_), "n"(FE + ND + NG) : "memory"); }
   __device__ __forceinline__ void group_sync() const { asm volatile("bar.sync %0, %1;" ::"r"(1 + NSTREAM + s_), "n"(ND) : "memory"); }
+  __device__ __forceinline__ void ggroup_sync() const { asm volatile("bar.sync %0, %1;" ::"r"(1 + 3 * NSTREAM + s_), "n"(NG) : "memory"); }
   __device__ __forceinline__ void elem_sync() const {
     if (FE == 32) __syncwarp();
     else asm volatile("bar.sync %0, %1;" ::"r"(1 + 2 * NSTREAM + s_), "n"(FE) : "memory");
   }
-  __device__ __forceinline__ void role(bool element) const {
-    if (element) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REG_ELEMENT));
-    else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REG_DOF));
+  __device__ __forceinline__ void role(int r) const {
+    if (r == 0) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REG_ELEMENT));
+    else if (r == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REG_SUM));
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REG_GATHER));
   }
   __device__ __forceinline__ void gather_wait_prev() const { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
   __device__ __forceinline__ void bulk_request_w(int b, void *dst, const void *src, uint32_t bytes, int) const { bulk_request(b, dst, src, bytes); }
@@ -195,14 +196,8 @@ struct StreamDeviceEnv : PatchDeviceEnv {
     }
   }
 };
-#ifndef HCURL_STREAM64_ND
-#define HCURL_STREAM64_ND 128
-#endif
-typedef StreamDeviceEnv<64, HCURL_STREAM64_ND, 2> StreamEnv64;
-#ifndef HCURL_STREAM128_ND
-#define HCURL_STREAM128_ND 384
-#endif
-typedef StreamDeviceEnv<128, HCURL_STREAM128_ND, 1> StreamEnv128;  // one stream of four element warps + twelve dof warps: the default
+typedef StreamDeviceEnv<128, 256, 128, 1> StreamEnv128;  // one stream: 4 element + 8 sum + 4 gather warps on 128-element patches (the default)
+typedef StreamDeviceEnv<64, 128, 64, 2> StreamEnv64;     // two streams of 2 + 4 + 2 warps on 64-element patches (when the unit lists of 128 elements do not fit)
 
 // shared memory of ONE stream (a CTA holds 128 / FE of them)
 size_t patch_stream_smem_bytes(int FE, uint32_t d_cap, uint32_t l_cap, uint32_t t_cap, uint32_t xs_cap) {
@@ -214,18 +209,20 @@ template <class SEnv, bool ACC, bool DOT, bool GENERAL>
 __global__ void __launch_bounds__(SEnv::NTHREADS, 1) hex_patch_p2_stream_kernel(const PatchArgs a, const uint32_t stream_bytes) {
   extern __shared__ __align__(128) unsigned char smem_patch[];
   constexpr int EW = SEnv::FE / 32, NEW = SEnv::NSTREAM * EW;  // element warps per stream / per CTA
+  constexpr int NSW = SEnv::NSTREAM * SEnv::ND / 32;            // sum warps per CTA
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   SEnv env;
   if (warp < NEW) { env.s_ = warp / EW; env.tid_ = (warp % EW) * 32 + lane; }
-  else { env.s_ = (warp - NEW) % SEnv::NSTREAM; env.tid_ = SEnv::FE + ((warp - NEW) / SEnv::NSTREAM) * 32 + lane; }
+  else if (warp < NEW + NSW) { env.s_ = (warp - NEW) % SEnv::NSTREAM; env.tid_ = SEnv::FE + ((warp - NEW) / SEnv::NSTREAM) * 32 + lane; }
+  else { env.s_ = (warp - NEW - NSW) % SEnv::NSTREAM; env.tid_ = SEnv::FE + SEnv::ND + ((warp - NEW - NSW) / SEnv::NSTREAM) * 32 + lane; }
   env.smem_ = smem_patch + (size_t)env.s_ * stream_bytes;
 #ifdef HCURL_PHASE_PROFILE
-  __shared__ long long sprof[4][34];
+  __shared__ long long sprof[4][35];
   env.sprof_ = sprof[env.s_];
-  if (env.tid_ == 0) { for (int i = 0; i < 32; i++) sprof[env.s_][i] = 0; sprof[env.s_][32] = sprof[env.s_][33] = clock64(); }
+  if (env.tid_ == 0) { for (int i = 0; i < 32; i++) sprof[env.s_][i] = 0; sprof[env.s_][32] = sprof[env.s_][33] = sprof[env.s_][34] = clock64(); }
   __syncthreads();
 #endif
-  patch_stream<SEnv, P2Elem<SEnv::FE, GENERAL>, SEnv::FE, SEnv::ND, ACC, DOT>(env, a);
+  patch_stream<SEnv, P2Elem<SEnv::FE, GENERAL>, SEnv::FE, SEnv::ND, SEnv::NG, ACC, DOT>(env, a);
 #ifdef HCURL_PHASE_PROFILE
   __syncthreads();
   if (threadIdx.x < 32) for (int s = 0; s < SEnv::NSTREAM; s++) atomicAdd(g_phase_cycles + threadIdx.x, (unsigned long long)sprof[s][threadIdx.x]);

@@ -1,6 +1,6 @@
 // The WARP-SPECIALISED form of the persistent patch pipeline (patch_pipeline.h) for the order-2 affine hex kernel: the
-// same patch blobs, element side, per-unit sums, zero-ahead watermark and essential-row handling, but the element side
-// and the dof side of a patch run in DIFFERENT warps, connected by four one-bit flags per stream.
+// same patch blobs, element side, per-unit sums, zero-ahead watermark and essential-row handling, but the element side,
+// the x gather and the per-unit sums of a patch run in DIFFERENT warps, connected by four one-bit flags per stream.
 //
 // Operator and reference: y (+)= scale * (K(alpha) + M(beta)) x, CurlCurlKernel + VectorFEMassKernel
 // (/root/reference/src/kernels/curl_curl_kernel.cpp:21-24, vector_fe_mass_kernel.cpp:21-24) applied as EquationSystem::Mult
@@ -11,28 +11,36 @@
 // of which the element side (pull, modal operator, result store: all the FP64) is ~4 700 and the dof side (x gather,
 // zeroing ahead, per-unit sums, REDs) ~8 000, almost all of it exposed latency; at 255 registers only 7-8 such warps
 // fit on an SM, so neither side hides the other.  Here a STREAM is FE/32 element warps (248 registers, one thread per
-// element of an FE-element patch) plus ND/32 dof warps (few registers: setmaxnreg moves the register file to the element
-// warps), and an SM runs 128/FE streams -- one element warp per scheduler / FP64 pipe:
+// element of an FE-element patch), ND/32 SUM warps and NG/32 GATHER warps (few registers: setmaxnreg moves the register
+// file to the element warps), and an SM runs 128/FE streams -- one element warp per scheduler / FP64 pipe:
 //
 //   element warp, patch i:  wait T(i), XS_FULL[i%2] | pull | signal XS_FREE[i%2] | operator | wait EY_FREE (sums of patch i-1)
 //                           | results to EY | signal EY_FULL, request T(i+2)
-//   dof warps, patch i:     arrive | gather of patch i+1 (started an iteration ago) landed: signal XS_FULL[(i+1)%2] | wait D(i+2),
-//                           XS_FREE[i%2]: start the x gather of patch i+2 | zero ahead | wait L(i), EY_FULL | per-unit sums:
-//                           stores, watermark, REDs | signal EY_FREE, request L(i+1), D(i+4)
+//   gather warps, patch i:  arrive | the gather of patch i (started an iteration ago) has landed: signal XS_FULL[i%2] | wait
+//                           D(i+1), XS_FREE[(i+1)%2]: start the x gather of patch i+1 | zero ahead
+//   sum warps, patch i:     wait D(i), L(i), EY_FULL | per-unit sums: stores, watermark, REDs | signal EY_FREE, request
+//                           L(i+1), D(i+4)
 //
+// (Round 2, phase profile of the two-role form, where one dof group did the gather AND the sums: 7 900 cycles per
+// iteration and stream, ~1 300 of them waiting -- a single instruction stream of short, latency-exposed steps; the
+// element warp waited ~1 700 of its 7 900 for it.  Gather + zeroing are ~3 000 of those cycles, the sums ~4 800: in
+// different warps they overlap.)
 // The staging vector Xs is a DOUBLE-BUFFERED ring (one FULL / FREE flag pair per buffer: the usual producer / consumer
-// protocol, so a one-bit phase parity per flag is enough); the x gather runs two patches ahead (measured: 16-byte
-// scattered copies need ~3 000 cycles to land under load) and the unit lists four (bulk copies: ~2 000).  The element
-// warp pulls and applies patch i+1 while the dof warps sum patch i; it waits for them only if the sums take longer than
-// its pull + operator.  Everything else (blob format, ownership and zeroing batches, deadlock freedom by co-residency,
-// bit-reproducible two-patch sums) is as described in patch_pipeline.h and patch.cpp.
+// protocol, so a one-bit phase parity per flag is enough); the gather warps run as far ahead as the ring allows (16-byte
+// scattered copies need ~3 000 cycles to land under load) and the unit lists are requested four patches ahead (bulk
+// copies: ~2 000).  The unit list D(i) is read by the gather warps (indices) and, later, by the sum warps (counts, indices,
+// flags); its buffer is requested again by the sum warps once they are done with patch i -- the gather of patch i landed
+// before the element warp pulled it, i.e. before EY_FULL(i).  Everything else (blob format, ownership and zeroing
+// batches, deadlock freedom by co-residency, bit-reproducible two-patch sums) is as described in patch_pipeline.h and
+// patch.cpp.
 //
 // Shared memory of a stream:  [128 B: mbarriers D0 D1 D2 D3 L T0 T1 | 6 flags] [4 x d_cap] [l_cap] [2 x t_cap] [2 x Xs] [EY]
 //
-// Env (per THREAD of a stream; tid() in [0, 32): the element warp, [32, 32 + ND): the dof group), in addition to the
-// interface listed in patch_pipeline.h (block() / nblocks() count STREAMS, smem() is the stream's):
-//   void role(bool element)                       register re-allocation of the calling warp group (device: setmaxnreg)
-//   void group_sync()                             barrier of the dof group
+// Env (per THREAD of a stream; tid() in [0, FE): the element warps, [FE, FE + ND): the sum group, [FE + ND, FE + ND + NG):
+// the gather group), in addition to the interface listed in patch_pipeline.h (block() / nblocks() count STREAMS, smem() is
+// the stream's):
+//   void role(int r)                              register re-allocation of the calling warp group (device: setmaxnreg); 0 element, 1 sums, 2 gather
+//   void group_sync()  void ggroup_sync()         barrier of the sum group / of the gather group
 //   void elem_sync()                              barrier of the element warps of the stream (one warp when FE = 32)
 //   void bulk_request_w(int b, void *dst, const void *src, uint32_t bytes, int nwait)   as bulk_request; nwait threads will wait
 //   void flag_init(int f)  (thread 0, with bulk_init)   void flag_signal(int f)  (one thread, after a warp / group barrier)
@@ -49,7 +57,7 @@
 
 namespace hcurl {
 
-template <class Env, class Elem, int FE, int ND, bool ACC, bool DOT>
+template <class Env, class Elem, int FE, int ND, int NG, bool ACC, bool DOT>
 HCURL_BODY void patch_stream(Env &env, const PatchArgs &a) {
   typedef typename Elem::Unit Unit;
   typedef typename Unit::T T;
@@ -63,7 +71,7 @@ HCURL_BODY void patch_stream(Env &env, const PatchArgs &a) {
   unsigned char *bufX = bufT + 2 * (size_t)a.t_cap_bytes;
   unsigned char *bufE = bufX + 2 * (size_t)a.xs_cap_bytes;
   const int tid = env.tid();
-  const bool element = tid < FE;
+  const int role = tid < FE ? 0 : (tid < FE + ND ? 1 : 2);
   const int64_t k0 = a.k_begin + env.block(), kstep = env.nblocks();
   const int64_t n_it64 = (a.n_patch - k0 + kstep - 1) / kstep;
   const int n_it = n_it64 > 0 ? (int)n_it64 : 0;
@@ -74,10 +82,10 @@ HCURL_BODY void patch_stream(Env &env, const PatchArgs &a) {
     for (int f = 0; f < N_FLAG; f++) env.flag_init(f);
   }
   env.sync();  // mbarriers and flags initialised
-  env.role(element);
+  env.role(role);
 
-  if (element) {
-    // ================================================================ element warp
+  if (role == 0) {
+    // ================================================================ element warps
     const int el = tid;
     auto request_t = [&](int b, int64_t k) {  // per-slot table of patch k into table buffer b
       const uint32_t o0 = env.ldg(a.part_off + 2 * k + 1), o1 = env.ldg(a.blob_off + k + 1);
@@ -121,128 +129,28 @@ HCURL_BODY void patch_stream(Env &env, const PatchArgs &a) {
       }
       HCURL_SMARK(7);
     }
-  } else {
-    // ================================================================ dof group
+  } else if (role == 1) {
+    // ================================================================ sum group
     const int dt = tid - FE;
-    const T *xu = reinterpret_cast<const T *>(a.x);
-    T *yu = reinterpret_cast<T *>(a.y);
-    auto request_d = [&](int b, uint32_t o0, uint32_t o1) {
-      env.bulk_request_w(MB_D0 + b, bufD + (size_t)b * a.d_cap_bytes, a.blob + (size_t)o0 * 4, (o1 - o0) * 16u, ND);
+    auto request_d = [&](int b, uint32_t o0, uint32_t o1) {  // (waited for by the gather group and by the sum group)
+      env.bulk_request_w(MB_D0 + b, bufD + (size_t)b * a.d_cap_bytes, a.blob + (size_t)o0 * 4, (o1 - o0) * 16u, ND + NG);
     };
     auto request_l = [&](uint32_t o0, uint32_t o1) { env.bulk_request_w(MB_L, bufL, a.blob + (size_t)o0 * 4, (o1 - o0) * 16u, ND); };
-    auto gather = [&](int bd, int bx) {  // the x gather of the patch whose unit list sits in unit buffer bd, into staging buffer bx
-      const uint32_t *B = reinterpret_cast<const uint32_t *>(bufD + (size_t)bd * a.d_cap_bytes);
-      T *Xs = reinterpret_cast<T *>(bufX + (size_t)bx * a.xs_cap_bytes);
-      const uint32_t U = B[0];
-      const uint32_t *dof = B + HDR;
-      if (B[20] == 0) {  // no essential dof in this patch
-#pragma unroll 4
-        for (uint32_t u = dt; u < U; u += ND) Unit::gather(env, Xs + u, xu + (dof[u] & PATCH_IDX));
-      } else {
-#pragma unroll 2
-        for (uint32_t u = dt; u < U; u += ND) {
-          const uint32_t m = dof[u];
-          if (!(m & Unit::ESS)) Unit::gather(env, Xs + u, xu + (m & PATCH_IDX));
-          else Xs[u] = (m & Unit::ESS) == Unit::ESS ? Unit::zero() : Unit::free_part(env.ldg(xu + (m & PATCH_IDX)), m);  // essential dofs enter as zeros
-        }
-      }
-      env.gather_commit();
-    };
-    // zeroing ahead (patch_pipeline.h): batches of ZB iterations, one arrival per stream and batch
-    constexpr int ZB = HCURL_ZERO_BATCH, ZU = (6 * FE + ND - 1) / ND;
-    const int NB = (int)(((a.n_patch - a.k_begin + kstep - 1) / kstep + ZB - 1) / ZB);
-    uint32_t zn0 = 0, zn1 = 0;
-    if (!ACC && 2 * ZB < n_it) { zn0 = env.ldg(a.own_off + k0 + (int64_t)(2 * ZB) * kstep); zn1 = env.ldg(a.own_off + k0 + (int64_t)(2 * ZB) * kstep + 1); }
-    int arrived = 0;
-    bool passed = ACC;
     if (dt == 0 && n_it > 0) {
       const uint32_t o1 = env.ldg(a.part_off + 2 * k0), o2 = env.ldg(a.part_off + 2 * k0 + 1);
       request_d(0, env.ldg(a.blob_off + k0), o1);
       request_l(o1, o2);
-      if (n_it > 1) request_d(1, env.ldg(a.blob_off + k0 + kstep), env.ldg(a.part_off + 2 * (k0 + kstep)));
-      for (int j = 2; j < ND_BUF && j < n_it; j++) request_d(j, env.ldg(a.blob_off + k0 + j * kstep), env.ldg(a.part_off + 2 * (k0 + j * kstep)));
+      for (int j = 1; j < ND_BUF && j < n_it; j++) request_d(j, env.ldg(a.blob_off + k0 + j * kstep), env.ldg(a.part_off + 2 * (k0 + j * kstep)));
     }
-    if (n_it > 0) {
-      env.bulk_wait(MB_D0, 0);
-      gather(0, 0);
-    }
-    if (n_it > 1) {
-      env.bulk_wait(MB_D0 + 1, 0);
-      gather(1, 1);
-    }
-    if (!ACC) {  // prologue: zeros under the shared units my patches of iterations [0, 2 ZB) own
-      // the extents of the 2 ZB owned lists are loaded by 4 ZB threads at once and handed over through shared memory (the
-      // result buffer is unused until the element warps store patch 0, which they do after the XS_FULL signal below), so
-      // that the index loads of all patches are independent
-      constexpr int NJ = 2 * ZB;
-      uint32_t *ext = reinterpret_cast<uint32_t *>(bufE);  // [2 NJ]
-      for (int j = dt; j < 2 * NJ; j += ND) {
-        const int jj = j >> 1;
-        ext[j] = jj < n_it ? env.ldg(a.own_off + k0 + (int64_t)jj * kstep + (j & 1)) : 0u;
-      }
-      env.group_sync();
-#pragma unroll 4
-      for (int j = 0; j < NJ; j++) {
-        const uint32_t u1 = ext[2 * j + 1];
-        for (uint32_t u = ext[2 * j] + dt; u < u1; u += ND) yu[env.ldg(a.own_idx + u)] = Unit::zero();
-      }
-    }
-    if (n_it > 1) env.gather_wait_prev(); else env.gather_wait();
-    env.group_sync();  // Xs of the first patch complete; the zeros of batches 0, 1 issued by every thread of the group
-    if (dt == 0) {
-      if (n_it > 0) env.flag_signal(XS_FULL + 0);
-      if (!ACC) for (int m = 0; m < 2 && m < NB; m++) env.arrive(a.count + m);
-    }
-    if (!ACC) arrived = 2;
-
+    bool passed = ACC;
     for (int it = 0; it < n_it; it++) {
-      const int b = it & 1;
-      const uint32_t use = (uint32_t)(it >> 1);
       const int64_t k = k0 + (int64_t)it * kstep;
-      const int bd = it & (ND_BUF - 1), bd2 = (it + 2) & (ND_BUF - 1);  // unit buffers of patches it, it + 2
+      const int bd = it & (ND_BUF - 1);
       const uint32_t *B = reinterpret_cast<const uint32_t *>(bufD + (size_t)bd * a.d_cap_bytes);
       const uint32_t *Lw = reinterpret_cast<const uint32_t *>(bufL);
       const unsigned char *Eb = bufE;
-      // zeroing ahead: the owned shared units of my patch of iteration it + 2 ZB
-      uint32_t zu[ZU];
-      const uint32_t z0 = zn0 + dt, z1 = zn1;
-      if (!ACC) {
-#pragma unroll
-        for (int i = 0; i < ZU; i++) zu[i] = z0 + i * ND < z1 ? env.ldg(a.own_idx + z0 + i * ND) : 0xffffffffu;
-        zn0 = zn1 = 0;
-        if (it + 1 + 2 * ZB < n_it) { const int64_t pz = k + (int64_t)(2 * ZB + 1) * kstep; zn0 = env.ldg(a.own_off + pz); zn1 = env.ldg(a.own_off + pz + 1); }
-      }
-      if (!ACC && it % ZB == 0) {  // first iteration of batch m: arrive for batch m+1 (its zeros were written during batch m-1)
-        const int m = it / ZB;
-        if (m >= 1 && m + 1 < NB) {
-          if (dt == 0) env.arrive(a.count + m + 1);
-          arrived = m + 2;
-        }
-        passed = false;
-      }
+      if (!ACC && it % HCURL_ZERO_BATCH == 0) passed = false;
       HCURL_SMARK(8);
-      if (it + 1 < n_it) {  // the gather of patch it + 1 (started an iteration ago) has landed: hand it to the element warp first
-        env.gather_wait();
-        HCURL_SMARK(13);
-        env.group_sync();
-        if (dt == 0) env.flag_signal(XS_FULL + (b ^ 1));
-      }
-      // ---- the x gather of patch it + 2 into the staging buffer the element warp has pulled patch it from
-      const bool ahead = it + 2 < n_it;
-      if (ahead) {
-        env.bulk_wait(MB_D0 + bd2, (uint32_t)((it + 2) / ND_BUF) & 1u);
-        HCURL_SMARK(9);
-        env.flag_wait(XS_FREE + b, use);
-        HCURL_SMARK(10);
-        gather(bd2, b);
-      }
-      HCURL_SMARK(11);
-      if (!ACC && z0 < z1) {
-#pragma unroll
-        for (int i = 0; i < ZU; i++) if (zu[i] != 0xffffffffu) yu[zu[i]] = Unit::zero();
-        for (uint32_t u = z0 + ZU * ND; u < z1; u += ND) yu[env.ldg(a.own_idx + u)] = Unit::zero();  // (patches owning more than ZU ND units)
-      }
-      HCURL_SMARK(12);
       // thread 0 of the group: extents of the parts requested at the end of this iteration
       uint32_t nL = 0, nT = 0, qD = 0, qL = 0;
       if (dt == 0) {
@@ -251,29 +159,38 @@ HCURL_BODY void patch_stream(Env &env, const PatchArgs &a) {
       }
       HCURL_SMARK(14);
       // ---- per-unit sums of this patch
+      env.bulk_wait(MB_D0 + bd, (uint32_t)(it / ND_BUF) & 1u);
       env.bulk_wait(MB_L, (uint32_t)it & 1u);
       HCURL_SMARK(15);
-      env.flag_wait(EY_FULL, (uint32_t)it);
-      HCURL_SMARK(16);
       const bool essp = B[20] != 0;
-      if (essp) {
-        const double d = patch_unit_sums<Env, Unit, ND, ACC, DOT, 0, true>(env, a, B, Lw, Eb, dt);
-        if (DOT) dacc += d;
-      } else patch_unit_sums<Env, Unit, ND, ACC, false, 0, false>(env, a, B, Lw, Eb, dt);
-      HCURL_SMARK(17);
-      if (B[7] + B[8] + B[9] + B[2]) {
-        if (!passed) {  // every stream has arrived for this batch: all zeros under the shared units of its patches are visible
-          for (unsigned ns = 0; (int32_t)(env.counter_acquire(a.count + it / ZB) - a.count_target) < 0; ns++) env.backoff(ns);
+      const bool shared = B[7] + B[8] + B[9] + B[2] != 0;
+      // every stream has arrived for this batch: all zeros under the shared units of its patches are visible.  (Checked
+      // after the private sums: polled earlier, while the group waits for the element warps, the counter is more often
+      // not there yet and the back-off sleep then delays the sums -- measured 7 % slower.)
+      auto watermark = [&]() {
+        if (!passed && shared) {
+          for (unsigned ns = 0; (int32_t)(env.counter_acquire(a.count + it / HCURL_ZERO_BATCH) - a.count_target) < 0; ns++) env.backoff(ns);
           passed = true;
         }
+      };
+      env.flag_wait(EY_FULL, (uint32_t)it);
+      HCURL_SMARK(16);
+      if (essp) {
+        double d = patch_unit_sums<Env, Unit, ND, ACC, DOT, 0, true>(env, a, B, Lw, Eb, dt);
+        HCURL_SMARK(17);
+        watermark();
         HCURL_SMARK(18);
-        if (essp) {
-          const double d = patch_unit_sums<Env, Unit, ND, ACC, DOT, 1, true>(env, a, B, Lw, Eb, dt);
-          if (DOT) dacc += d;
-        } else patch_unit_sums<Env, Unit, ND, ACC, false, 1, false>(env, a, B, Lw, Eb, dt);
+        if (shared) d += patch_unit_sums<Env, Unit, ND, ACC, DOT, 1, true>(env, a, B, Lw, Eb, dt);
+        if (DOT) dacc += d;
+      } else {
+        patch_unit_sums<Env, Unit, ND, ACC, false, 0, false>(env, a, B, Lw, Eb, dt);
+        HCURL_SMARK(17);
+        watermark();
+        HCURL_SMARK(18);
+        if (shared) patch_unit_sums<Env, Unit, ND, ACC, false, 1, false>(env, a, B, Lw, Eb, dt);
       }
       HCURL_SMARK(19);
-      env.group_sync();  // EY, the lists and unit buffer bd are free
+      env.group_sync();  // EY, the lists and unit buffer bd are free (the gather of this patch landed before it was pulled)
       if (dt == 0) {
         env.flag_signal(EY_FREE);
         if (it + 1 < n_it) request_l(nL, nT);
@@ -281,7 +198,103 @@ HCURL_BODY void patch_stream(Env &env, const PatchArgs &a) {
       }
       HCURL_SMARK(20);
     }
-    if (!ACC && dt == 0) for (int m = arrived; m < NB; m++) env.arrive(a.count + m);  // (zeros of these batches: none of mine left)
+  } else {
+    // ================================================================ gather group
+    const int gt = tid - FE - ND;
+    const T *xu = reinterpret_cast<const T *>(a.x);
+    T *yu = reinterpret_cast<T *>(a.y);
+    auto gather = [&](int bd, int bx) {  // the x gather of the patch whose unit list sits in unit buffer bd, into staging buffer bx
+      const uint32_t *B = reinterpret_cast<const uint32_t *>(bufD + (size_t)bd * a.d_cap_bytes);
+      T *Xs = reinterpret_cast<T *>(bufX + (size_t)bx * a.xs_cap_bytes);
+      const uint32_t U = B[0];
+      const uint32_t *dof = B + HDR;
+      if (B[20] == 0) {  // no essential dof in this patch
+#pragma unroll 4
+        for (uint32_t u = gt; u < U; u += NG) Unit::gather(env, Xs + u, xu + (dof[u] & PATCH_IDX));
+      } else {
+#pragma unroll 2
+        for (uint32_t u = gt; u < U; u += NG) {
+          const uint32_t m = dof[u];
+          if (!(m & Unit::ESS)) Unit::gather(env, Xs + u, xu + (m & PATCH_IDX));
+          else Xs[u] = (m & Unit::ESS) == Unit::ESS ? Unit::zero() : Unit::free_part(env.ldg(xu + (m & PATCH_IDX)), m);  // essential dofs enter as zeros
+        }
+      }
+      env.gather_commit();
+    };
+    // zeroing ahead (patch_pipeline.h): batches of ZB iterations, one arrival per stream and batch
+    constexpr int ZB = HCURL_ZERO_BATCH, ZU = (6 * FE + NG - 1) / NG;
+    const int NB = (int)(((a.n_patch - a.k_begin + kstep - 1) / kstep + ZB - 1) / ZB);
+    uint32_t zn0 = 0, zn1 = 0;
+    if (!ACC && 2 * ZB < n_it) { zn0 = env.ldg(a.own_off + k0 + (int64_t)(2 * ZB) * kstep); zn1 = env.ldg(a.own_off + k0 + (int64_t)(2 * ZB) * kstep + 1); }
+    int arrived = 0;
+    if (n_it > 0) {
+      env.bulk_wait(MB_D0, 0);
+      gather(0, 0);
+    }
+    if (!ACC) {  // prologue: zeros under the shared units my patches of iterations [0, 2 ZB) own
+      // the extents of the 2 ZB owned lists are loaded by 4 ZB threads at once and handed over through shared memory (the
+      // second staging buffer is unused until the gather of patch 1), so that the index loads of all patches are independent
+      constexpr int NJ = 2 * ZB;
+      uint32_t *ext = reinterpret_cast<uint32_t *>(bufX + a.xs_cap_bytes);  // [2 NJ]
+      for (int j = gt; j < 2 * NJ; j += NG) {
+        const int jj = j >> 1;
+        ext[j] = jj < n_it ? env.ldg(a.own_off + k0 + (int64_t)jj * kstep + (j & 1)) : 0u;
+      }
+      env.ggroup_sync();
+#pragma unroll 4
+      for (int j = 0; j < NJ; j++) {
+        const uint32_t u1 = ext[2 * j + 1];
+        for (uint32_t u = ext[2 * j] + gt; u < u1; u += NG) yu[env.ldg(a.own_idx + u)] = Unit::zero();
+      }
+      env.ggroup_sync();  // the zeros of batches 0, 1 issued by every thread of the group
+      if (gt == 0) for (int m = 0; m < 2 && m < NB; m++) env.arrive(a.count + m);
+      arrived = 2;
+    }
+
+    for (int it = 0; it < n_it; it++) {
+      const int64_t k = k0 + (int64_t)it * kstep;
+      // zeroing ahead: the owned shared units of my patch of iteration it + 2 ZB
+      uint32_t zu[ZU];
+      const uint32_t z0 = zn0 + gt, z1 = zn1;
+      if (!ACC) {
+#pragma unroll
+        for (int i = 0; i < ZU; i++) zu[i] = z0 + i * NG < z1 ? env.ldg(a.own_idx + z0 + i * NG) : 0xffffffffu;
+        zn0 = zn1 = 0;
+        if (it + 1 + 2 * ZB < n_it) { const int64_t pz = k + (int64_t)(2 * ZB + 1) * kstep; zn0 = env.ldg(a.own_off + pz); zn1 = env.ldg(a.own_off + pz + 1); }
+      }
+      HCURL_SMARK(9);
+      // the gather of patch it (started an iteration ago) has landed: hand it to the element warps at once
+      env.gather_wait();
+      HCURL_SMARK(21);
+      env.ggroup_sync();  // ... for every thread of the group; the zeros of the previous iteration issued by every thread
+      if (gt == 0) env.flag_signal(XS_FULL + (it & 1));
+      if (!ACC && it % ZB == 0) {  // first iteration of batch m: arrive for batch m+1 (its zeros were written during batch m-1)
+        const int m = it / ZB;
+        if (m >= 1 && m + 1 < NB) {
+          if (gt == 0) env.arrive(a.count + m + 1);
+          arrived = m + 2;
+        }
+      }
+      HCURL_SMARK(22);
+      // ---- the x gather of patch it + 1 into the other staging buffer, once the element warps have pulled patch it - 1 from it
+      if (it + 1 < n_it) {
+        const int j = it + 1;
+        env.bulk_wait(MB_D0 + (j & (ND_BUF - 1)), (uint32_t)(j / ND_BUF) & 1u);
+        HCURL_SMARK(10);
+        if (j >= 2) env.flag_wait(XS_FREE + (j & 1), (uint32_t)((j - 2) >> 1));
+        HCURL_SMARK(11);
+        gather(j & (ND_BUF - 1), j & 1);
+      }
+      HCURL_SMARK(12);
+      if (!ACC && z0 < z1) {
+#pragma unroll
+        for (int i = 0; i < ZU; i++) if (zu[i] != 0xffffffffu) yu[zu[i]] = Unit::zero();
+        for (uint32_t u = z0 + ZU * NG; u < z1; u += NG) yu[env.ldg(a.own_idx + u)] = Unit::zero();  // (patches owning more than ZU NG units)
+      }
+      HCURL_SMARK(13);
+    }
+    env.ggroup_sync();  // the zeros of the last iteration issued by every thread
+    if (!ACC && gt == 0) for (int m = arrived; m < NB; m++) env.arrive(a.count + m);  // (zeros of these batches: none of mine left)
   }
   if (DOT) env.dot_finish(dacc, a, reinterpret_cast<double *>(bufE));
 }

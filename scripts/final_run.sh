@@ -1,9 +1,9 @@
 #!/bin/bash
 # Round evidence on one B200 (run under gpurun): GPU tests, the bench line, the reference arm, ncu launch list and full
-# capture of the dominant kernel, the other orders / kernels.  Outputs under gpurun_out/.     usage: final_run.sh TAG
+# capture of the dominant kernel, the other orders / kernels.  Outputs under gpurun_out/.     usage: final_run.sh TAG [notests]
 tag=${1:-r2}
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -x -q -m gpu -p no:cacheprovider > gpurun_out/pytest_gpu_$tag.log 2>&1; tail -3 gpurun_out/pytest_gpu_$tag.log
+if [ "$2" != "notests" ]; then timeout 1500 python -m pytest tests -x -q -m gpu -p no:cacheprovider > gpurun_out/pytest_gpu_$tag.log 2>&1; tail -3 gpurun_out/pytest_gpu_$tag.log; fi
 timeout 500 python bench.py > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err; tail -c 300 gpurun_out/bench_$tag.err
 timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$tag.json 2> gpurun_out/bench_ref_$tag.err; tail -c 300 gpurun_out/bench_ref_$tag.err
 BENCH="python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e --pcg-iters 3"
@@ -14,6 +14,7 @@ for cfg in "1 255" "3 85" "4 64"; do set -- $cfg; timeout 300 python bench.py --
 timeout 300 python bench.py --perturbed $S > gpurun_out/bench_p2pert_$tag.json 2>/dev/null
 timeout 300 python bench.py --quad mfem $S > gpurun_out/bench_p2mfem_$tag.json 2>/dev/null
 HCURL_PATCH_STREAM=0 timeout 300 python bench.py $S > gpurun_out/bench_p2pipeline32_$tag.json 2>/dev/null
+HCURL_PATCH_FE=64 timeout 300 python bench.py $S > gpurun_out/bench_p2stream64_$tag.json 2>/dev/null
 timeout 300 python bench.py --geom tet --order 2 --n 64 $S > gpurun_out/bench_ptet2_$tag.json 2>/dev/null
 timeout 300 python bench.py --geom tet --order 1 --n 100 $S > gpurun_out/bench_ptet1_$tag.json 2>/dev/null
 for f in gpurun_out/bench_$tag.json gpurun_out/bench_p*_$tag.json; do python - "$f" <<'PY'

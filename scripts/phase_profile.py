@@ -49,17 +49,21 @@ def main():
     assert f(out, 0) == 0
     v = np.array(list(out), dtype=np.float64)
     if os.environ.get("HCURL_PATCH_STREAM") == "1":
-        names = ["E: end of iteration -> top", "E: geometry issue + wait T", "E: wait XS_FULL", "E: pull + fwd + signal", "E: operator",
-                 "E: extents + wait EY_FREE", "E: bwd + store + warp sync", "E: signal + request T",
-                 "D: top (extents, zero indices, arrive)", "D: wait D(i+1)", "D: wait XS_FREE", "D: gather issue", "D: zero stores", "D: gather wait",
-                 "D: group sync + signal XS_FULL", "D: wait L", "D: wait EY_FULL", "D: sums private", "D: watermark", "D: sums shared", "D: group sync + requests"]
-        n_stream_it = 65536 * a.applies if a.n == 128 and a.order == 2 else None
-        e_tot, d_tot = v[:8].sum(), v[8:21].sum()
-        its = (a.n // 4) * (a.n // 4) * (a.n // 2) * a.applies
-        print("apply %.4f ms (instrumented); per pipeline iteration: element warp %.0f cycles, dof group %.0f cycles" % (ms, e_tot / its, d_tot / its))
-        for i, nm in enumerate(names):
-            tot = e_tot if i < 8 else d_tot
-            print("  %2d %-42s %8.0f cycles  %5.1f %%" % (i, nm, v[i] / its, 100 * v[i] / tot))
+        names = {0: "E: end of iteration -> top", 1: "E: geometry issue + wait T", 2: "E: wait XS_FULL", 3: "E: pull + fwd + signal", 4: "E: operator",
+                 5: "E: extents + wait EY_FREE", 6: "E: bwd + store + warp sync", 7: "E: signal + request T",
+                 8: "S: end of iteration -> top", 14: "S: extents of the next requests", 15: "S: wait D, L", 16: "S: wait EY_FULL", 17: "S: sums private",
+                 18: "S: watermark", 19: "S: sums shared", 20: "S: group sync + signal + requests",
+                 9: "G: top (zero indices)", 21: "G: gather wait", 22: "G: group sync + signal XS_FULL + arrive", 10: "G: wait D(i+1)",
+                 11: "G: wait XS_FREE", 12: "G: gather issue", 13: "G: zero stores"}
+        groups = [("element warps", [0, 1, 2, 3, 4, 5, 6, 7]), ("sum group", [8, 14, 15, 16, 17, 18, 19, 20]), ("gather group", [9, 21, 22, 10, 11, 12, 13])]
+        fe = int(os.environ.get("HCURL_PATCH_FE", "128"))
+        its = a.n ** 3 // fe * a.applies
+        print("apply %.4f ms (instrumented); cycles per pipeline iteration (%d-element patch) and stream" % (ms, fe))
+        for gname, ids in groups:
+            tot = sum(v[i] for i in ids)
+            print(" %s: %.0f cycles" % (gname, tot / its))
+            for i in ids:
+                print("  %2d %-42s %8.0f cycles  %5.1f %%" % (i, names[i], v[i] / its, 100 * v[i] / tot))
         return
     iters = v[15]
     tot = v[:15].sum()

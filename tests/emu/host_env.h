@@ -27,7 +27,10 @@ namespace emu {
 static constexpr int MAX_BAR = 7, MAX_FLAG = 8;
 enum { ERR_REARM = 1, ERR_ALIGN = 2, ERR_WAIT_UNARMED = 4, ERR_PARITY = 8, ERR_GATHER_LEFT = 16, ERR_BULK_LEFT = 32, ERR_FLAG_AHEAD = 64 };
 
-struct Pending { void *dst = nullptr; const void *src = nullptr; uint32_t bytes = 0; bool armed = false, landed = false; int nwait = 0; };
+// one bulk-copy request on an mbarrier: issued by one thread, waited for (once) by nwait threads, each of which counts its own
+// waits per mbarrier -- waiters of different warp groups may be a whole request apart (patch_stream.h: the gather group
+// waits for the unit list of patch i + 4 while the sum group has not yet looked at the one of patch i)
+struct Pending { void *dst = nullptr; const void *src = nullptr; uint32_t bytes = 0; bool active = false, landed = false; int nwait = 0, waited = 0; };
 
 struct WarpShared {
   std::barrier<> bar;
@@ -40,18 +43,22 @@ struct CtaShared {
   std::vector<unsigned char> smem;
   std::barrier<> bar;
   std::mutex mu[MAX_BAR];
-  Pending bulk[MAX_BAR];   // guarded by mu[b]
-  uint32_t phase[MAX_BAR]; // completed requests per mbarrier, guarded by mu[b]
-  int waiters[MAX_BAR];    // guarded by mu[b]
+  Pending bulk[MAX_BAR][2];            // requests r and r - 1 of the mbarrier (index r & 1), guarded by mu[b]
+  std::atomic<uint32_t> requests[MAX_BAR];  // requests issued so far per mbarrier
   std::vector<std::unique_ptr<WarpShared>> warp;
-  std::unique_ptr<std::barrier<>> group, elem;  // the dof group / the element warps of a stream (patch_stream.h): threads [n_elem, nt) / [0, n_elem)
+  std::unique_ptr<std::barrier<>> group, ggroup, elem;  // the sum group / the gather group / the element warps of a stream (patch_stream.h): threads [n_elem, n_elem + n_sum) / [n_elem + n_sum, nt) / [0, n_elem)
   int n_elem = 32;
   std::atomic<uint32_t> flag[MAX_FLAG];   // signals so far
   double dot_sum = 0.0;
   std::vector<double> dot_part;
-  void set_stream(int ne, int nt) { n_elem = ne; elem.reset(new std::barrier<>(ne)); group.reset(new std::barrier<>(nt - ne)); }
+  void set_stream(int ne, int nsum, int nt) {
+    n_elem = ne;
+    elem.reset(new std::barrier<>(ne));
+    group.reset(new std::barrier<>(nsum));
+    ggroup.reset(new std::barrier<>(nt - ne - nsum));
+  }
   CtaShared(size_t bytes, int nt) : smem(bytes + 16, 0xAB), bar(nt), dot_part((size_t)nt, 0.0) {
-    for (int b = 0; b < MAX_BAR; b++) { phase[b] = 0; waiters[b] = 0; }
+    for (int b = 0; b < MAX_BAR; b++) requests[b].store(0);
     for (auto &f : flag) f.store(0);
 
     for (int w = 0; w * 32 < nt; w++) warp.emplace_back(new WarpShared(std::min(32, nt - w * 32)));
@@ -73,6 +80,7 @@ struct HostEnv {
   unsigned vote_n = 0, shfl_n = 0;
   bool wait_may_precede_request = false;  // set by role(): the stream program
   unsigned commits = 0;  // committed gather groups
+  uint32_t my_waits[MAX_BAR] = {0, 0, 0, 0, 0, 0, 0};  // my waits so far per mbarrier
 
   int tid() const { return tid_; }
   int64_t block() const { return block_; }
@@ -84,32 +92,31 @@ struct HostEnv {
   void bulk_request(int b, void *dst, const void *src, uint32_t bytes) { bulk_request_w(b, dst, src, bytes, nt_); }
   void bulk_request_w(int b, void *dst, const void *src, uint32_t bytes, int nwait) {  // nwait threads will wait for this request
     std::lock_guard<std::mutex> lk(cta->mu[b]);
-    if (cta->bulk[b].armed) *error |= ERR_REARM;  // request on an mbarrier whose previous phase has not been consumed by everyone
+    const uint32_t r = cta->requests[b].load(std::memory_order_relaxed);
+    Pending &q = cta->bulk[b][r & 1u], &prev = cta->bulk[b][(r + 1u) & 1u];
+    // request r while a thread has not yet waited for request r - 2: the one-bit phase parity of its wait could not tell them apart
+    if (q.active && q.waited < q.nwait) *error |= ERR_REARM;
     if (bytes % 16 != 0 || ((uintptr_t)dst & 15) || ((uintptr_t)src & 15)) *error |= ERR_ALIGN;  // cp.async.bulk rules
+    if (prev.active && !prev.landed) { if (prev.bytes) memcpy(prev.dst, prev.src, prev.bytes); prev.landed = true; }
     if (bytes) memset(dst, 0xCD, bytes);  // the copy may start at once: whoever still reads the old content gets garbage
-    cta->bulk[b].dst = dst; cta->bulk[b].src = src; cta->bulk[b].bytes = bytes; cta->bulk[b].armed = true; cta->bulk[b].landed = false;
-    cta->bulk[b].nwait = nwait;
+    q.dst = dst; q.src = src; q.bytes = bytes; q.active = true; q.landed = false; q.nwait = nwait; q.waited = 0;
+    cta->requests[b].store(r + 1u, std::memory_order_release);
   }
   void bulk_wait(int b, uint32_t parity) {
     // a wait may come before its request (warp-specialised streams: the requesting thread runs on its own); on the
     // device the mbarrier phase is simply incomplete until then.  A wait whose request never comes hangs here as it would there.
-    for (unsigned tries = 0;; tries++) {
-      {
-        std::lock_guard<std::mutex> lk(cta->mu[b]);
-        if (cta->bulk[b].armed) break;
-      }
+    const uint32_t r = my_waits[b]++;  // the request this thread is waiting for
+    for (;;) {
+      if (cta->requests[b].load(std::memory_order_acquire) > r) break;
       if (!wait_may_precede_request) { *error |= ERR_WAIT_UNARMED; return; }
       std::this_thread::yield();
     }
     std::lock_guard<std::mutex> lk(cta->mu[b]);
-    Pending &q = cta->bulk[b];
-    if ((cta->phase[b] & 1u) != parity) *error |= ERR_PARITY;          // waiting on the wrong phase of the mbarrier
+    if (cta->requests[b].load(std::memory_order_relaxed) > r + 1u) { *error |= ERR_REARM; return; }  // my request's buffer has been requested again already
+    Pending &q = cta->bulk[b][r & 1u];
+    if ((r & 1u) != parity) *error |= ERR_PARITY;                     // waiting on the wrong phase of the mbarrier
     if (!q.landed) { if (q.bytes) memcpy(q.dst, q.src, q.bytes); q.landed = true; }  // ... and it completes as late as allowed
-    if (++cta->waiters[b] == q.nwait) {  // every thread concerned waits exactly once per request
-      cta->waiters[b] = 0;
-      cta->phase[b]++;
-      q.armed = false;
-    }
+    q.waited++;  // every thread concerned waits exactly once per request
   }
   void gather8(double *dst, const double *src) {
     *dst = std::numeric_limits<double>::quiet_NaN();  // in flight: readers that do not wait see garbage
@@ -153,8 +160,9 @@ struct HostEnv {
     return W.xch[n][(tid_ & 31) ^ lane_mask];
   }
   // ---- warp-specialised streams (patch_stream.h)
-  void role(bool) { wait_may_precede_request = true; }
+  void role(int) { wait_may_precede_request = true; }
   void group_sync() { cta->group->arrive_and_wait(); }
+  void ggroup_sync() { cta->ggroup->arrive_and_wait(); }
   void warp_sync() { cta->warp[(size_t)(tid_ >> 5)]->bar.arrive_and_wait(); }
   void elem_sync() { cta->elem->arrive_and_wait(); }
   void flag_init(int f) { cta->flag[f].store(0); }
@@ -186,11 +194,11 @@ struct HostEnv {
 
 // run `grid` CTAs of `nt` threads, all at the same time; body(env) is the per-thread program
 template <class Body>
-int run_grid(int64_t grid, int nt, size_t smem_bytes, const void *tables, double *dot_total, Body body, int stream_elem_threads = 0) {
+int run_grid(int64_t grid, int nt, size_t smem_bytes, const void *tables, double *dot_total, Body body, int stream_elem_threads = 0, int stream_sum_threads = 0) {
   std::vector<std::unique_ptr<CtaShared>> ctas;
   for (int64_t blk = 0; blk < grid; blk++) {
     ctas.emplace_back(new CtaShared(smem_bytes, nt));
-    if (stream_elem_threads) ctas.back()->set_stream(stream_elem_threads, nt);
+    if (stream_elem_threads) ctas.back()->set_stream(stream_elem_threads, stream_sum_threads, nt);
   }
   std::vector<int> err((size_t)(grid * nt), 0);
   std::vector<std::thread> th;
@@ -206,7 +214,8 @@ int run_grid(int64_t grid, int nt, size_t smem_bytes, const void *tables, double
   double dot = 0.0;
   for (int e : err) error |= e;
   for (auto &c : ctas) {
-    for (int b = 0; b < MAX_BAR; b++) if (c->bulk[b].armed) error |= ERR_BULK_LEFT;  // a requested copy was never consumed
+    for (int b = 0; b < MAX_BAR; b++)
+      for (int h = 0; h < 2; h++) if (c->bulk[b][h].active && c->bulk[b][h].waited != c->bulk[b][h].nwait) error |= ERR_BULK_LEFT;  // a requested copy was not consumed by everyone concerned
     dot += c->dot_sum;
   }
   if (dot_total) *dot_total = dot;

@@ -19,13 +19,14 @@ int run_mode(const hcurl::PatchArgs &a, int64_t grid, size_t smem, bool accumula
   if (a.dot_out) return accumulate ? -1 : run<Elem, FE, false, true>(a, grid, smem);
   return accumulate ? run<Elem, FE, true, false>(a, grid, smem) : run<Elem, FE, false, false>(a, grid, smem);
 }
-// warp-specialised stream program (patch_stream.h): an emulated "CTA" is one stream of FE element + ND dof threads
+// warp-specialised stream program (patch_stream.h): an emulated "CTA" is one stream of FE element + ND sum + NG gather threads
 template <int FE, int ND, bool GENERAL, bool ACC, bool DOT>
 int run_stream(const hcurl::PatchArgs &a, int64_t streams, size_t smem_bytes) {
   double dot = 0.0;
-  const int err = emu::run_grid(streams, FE + ND, smem_bytes, nullptr, &dot, [&](emu::HostEnv &env) {
-    hcurl::patch_stream<emu::HostEnv, hcurl::P2Elem<FE, GENERAL>, FE, ND, ACC, DOT>(env, a);
-  }, FE);
+  constexpr int NG = FE;
+  const int err = emu::run_grid(streams, FE + ND + NG, smem_bytes, nullptr, &dot, [&](emu::HostEnv &env) {
+    hcurl::patch_stream<emu::HostEnv, hcurl::P2Elem<FE, GENERAL>, FE, ND, NG, ACC, DOT>(env, a);
+  }, FE, ND);
   if (DOT && a.dot_out) *a.dot_out = a.dot_add ? *a.dot_out + dot : dot;
   return err;
 }
@@ -61,7 +62,7 @@ extern "C" int emu_patch_apply(int order, int fe, int general, int accumulate, i
     if (grid < 1) return 0;
     if (FE == 32) return general ? run_stream_mode<32, 96, true>(a, grid, ssm, acc) : run_stream_mode<32, 96, false>(a, grid, ssm, acc);
     if (FE == 64) return general ? run_stream_mode<64, 128, true>(a, grid, ssm, acc) : run_stream_mode<64, 128, false>(a, grid, ssm, acc);
-    if (FE == 128) return general ? run_stream_mode<128, 384, true>(a, grid, ssm, acc) : run_stream_mode<128, 384, false>(a, grid, ssm, acc);
+    if (FE == 128) return general ? run_stream_mode<128, 256, true>(a, grid, ssm, acc) : run_stream_mode<128, 256, false>(a, grid, ssm, acc);
     return -2;
   }
   if (grid > n_patch - k_begin) grid = n_patch - k_begin;
