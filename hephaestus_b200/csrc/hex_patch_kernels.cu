@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(FE) hex_patch_p1_kernel(const PatchArgs a) {
 template <int FE_, int ND_, int NG_, int NSTREAM_>
 struct StreamDeviceEnv : PatchDeviceEnv {
   static constexpr int FE = FE_, ND = ND_, NG = NG_, NSTREAM = NSTREAM_, NTHREADS = NSTREAM * (FE + ND + NG);
-  static constexpr int REG_ELEMENT = 248, REG_SUM = 72, REG_GATHER = 56;
+  static constexpr int REG_ELEMENT = 248, REG_SUM = 72, REG_GATHER = 88;
   static constexpr int FLAG0 = 8;  // mbarriers 0..6: bulk copies (D0 D1 D2 D3 L T0 T1); 8..13: flags
   static_assert(NSTREAM * FE == 128, "the element warps are exactly warp group 0");
   static_assert((NSTREAM * ND) % 128 == 0 && (NSTREAM * NG) % 128 == 0, "setmaxnreg acts on whole warp groups");
@@ -166,7 +166,7 @@ struct StreamDeviceEnv : PatchDeviceEnv {
   __device__ __forceinline__ void bulk_request_w(int b, void *dst, const void *src, uint32_t bytes, int) const { bulk_request(b, dst, src, bytes); }
   // flags: mbarriers of the stream with one arrival per phase.  A flag is never signalled twice before its waiter has
   // passed (ring protocol, patch_stream.h), so the one-bit phase parity identifies the n-th signal
-  __device__ __forceinline__ void flag_init(int f) const { mbar_init(mbar() + FLAG0 + f, 1); }
+  __device__ __forceinline__ void flag_init(int f, int arrivals) const { mbar_init(mbar() + FLAG0 + f, (uint32_t)arrivals); }
   __device__ __forceinline__ void flag_signal(int f) const {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(mbar() + FLAG0 + f)) : "memory");
   }

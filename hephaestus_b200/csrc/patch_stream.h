@@ -16,10 +16,11 @@
 //
 //   element warp, patch i:  wait T(i), XS_FULL[i%2] | pull | signal XS_FREE[i%2] | operator | wait EY_FREE (sums of patch i-1)
 //                           | results to EY | signal EY_FULL, request T(i+2)
-//   gather warps, patch i:  arrive | the gather of patch i (started an iteration ago) has landed: signal XS_FULL[i%2] | wait
-//                           D(i+1), XS_FREE[(i+1)%2]: start the x gather of patch i+1 | zero ahead
-//   sum warps, patch i:     wait D(i), L(i), EY_FULL | per-unit sums: stores, watermark, REDs | signal EY_FREE, request
-//                           L(i+1), D(i+4)
+//   gather warps, patch i:  the gather of patch i (started an iteration ago) has landed: signal XS_FULL[i%2], arrive | wait
+//                           D(i+1), XS_FREE[(i+1)%2]: start the x gather of patch i+1 | zero ahead | wait L(i-1), watermark,
+//                           EY_FULL(i-1): sums of the SHARED units of patch i-1 (REDs) | arrive on EY_FREE
+//   sum warps, patch i:     wait D(i), L(i), EY_FULL | sums of the PRIVATE units (stores) | arrive on EY_FREE; once the gather
+//                           group has arrived too: request L(i+1), D(i+4)
 //
 // (Round 2, phase profile of the two-role form, where one dof group did the gather AND the sums: 7 900 cycles per
 // iteration and stream, ~1 300 of them waiting -- a single instruction stream of short, latency-exposed steps; the
@@ -79,7 +80,7 @@ HCURL_BODY void patch_stream(Env &env, const PatchArgs &a) {
 
   if (tid == 0) {
     env.bulk_init(N_MB);
-    for (int f = 0; f < N_FLAG; f++) env.flag_init(f);
+    for (int f = 0; f < N_FLAG; f++) env.flag_init(f, f == EY_FREE ? 2 : 1);  // EY_FREE: one arrival of the sum group, one of the gather group
   }
   env.sync();  // mbarriers and flags initialised
   env.role(role);
@@ -135,21 +136,19 @@ HCURL_BODY void patch_stream(Env &env, const PatchArgs &a) {
     auto request_d = [&](int b, uint32_t o0, uint32_t o1) {  // (waited for by the gather group and by the sum group)
       env.bulk_request_w(MB_D0 + b, bufD + (size_t)b * a.d_cap_bytes, a.blob + (size_t)o0 * 4, (o1 - o0) * 16u, ND + NG);
     };
-    auto request_l = [&](uint32_t o0, uint32_t o1) { env.bulk_request_w(MB_L, bufL, a.blob + (size_t)o0 * 4, (o1 - o0) * 16u, ND); };
+    auto request_l = [&](uint32_t o0, uint32_t o1) { env.bulk_request_w(MB_L, bufL, a.blob + (size_t)o0 * 4, (o1 - o0) * 16u, ND + NG); };
     if (dt == 0 && n_it > 0) {
       const uint32_t o1 = env.ldg(a.part_off + 2 * k0), o2 = env.ldg(a.part_off + 2 * k0 + 1);
       request_d(0, env.ldg(a.blob_off + k0), o1);
       request_l(o1, o2);
       for (int j = 1; j < ND_BUF && j < n_it; j++) request_d(j, env.ldg(a.blob_off + k0 + j * kstep), env.ldg(a.part_off + 2 * (k0 + j * kstep)));
     }
-    bool passed = ACC;
     for (int it = 0; it < n_it; it++) {
       const int64_t k = k0 + (int64_t)it * kstep;
       const int bd = it & (ND_BUF - 1);
       const uint32_t *B = reinterpret_cast<const uint32_t *>(bufD + (size_t)bd * a.d_cap_bytes);
       const uint32_t *Lw = reinterpret_cast<const uint32_t *>(bufL);
       const unsigned char *Eb = bufE;
-      if (!ACC && it % HCURL_ZERO_BATCH == 0) passed = false;
       HCURL_SMARK(8);
       // thread 0 of the group: extents of the parts requested at the end of this iteration
       uint32_t nL = 0, nT = 0, qD = 0, qL = 0;
@@ -158,41 +157,22 @@ HCURL_BODY void patch_stream(Env &env, const PatchArgs &a) {
         if (it + ND_BUF < n_it) { qD = env.ldg(a.blob_off + k + ND_BUF * kstep); qL = env.ldg(a.part_off + 2 * (k + ND_BUF * kstep)); }
       }
       HCURL_SMARK(14);
-      // ---- per-unit sums of this patch
+      // ---- sums of the PRIVATE units of this patch (plain stores); the gather group adds the shared ones
       env.bulk_wait(MB_D0 + bd, (uint32_t)(it / ND_BUF) & 1u);
       env.bulk_wait(MB_L, (uint32_t)it & 1u);
       HCURL_SMARK(15);
-      const bool essp = B[20] != 0;
-      const bool shared = B[7] + B[8] + B[9] + B[2] != 0;
-      // every stream has arrived for this batch: all zeros under the shared units of its patches are visible.  (Checked
-      // after the private sums: polled earlier, while the group waits for the element warps, the counter is more often
-      // not there yet and the back-off sleep then delays the sums -- measured 7 % slower.)
-      auto watermark = [&]() {
-        if (!passed && shared) {
-          for (unsigned ns = 0; (int32_t)(env.counter_acquire(a.count + it / HCURL_ZERO_BATCH) - a.count_target) < 0; ns++) env.backoff(ns);
-          passed = true;
-        }
-      };
       env.flag_wait(EY_FULL, (uint32_t)it);
       HCURL_SMARK(16);
-      if (essp) {
-        double d = patch_unit_sums<Env, Unit, ND, ACC, DOT, 0, true>(env, a, B, Lw, Eb, dt);
-        HCURL_SMARK(17);
-        watermark();
-        HCURL_SMARK(18);
-        if (shared) d += patch_unit_sums<Env, Unit, ND, ACC, DOT, 1, true>(env, a, B, Lw, Eb, dt);
+      if (B[20] != 0) {
+        const double d = patch_unit_sums<Env, Unit, ND, ACC, DOT, 0, true>(env, a, B, Lw, Eb, dt);
         if (DOT) dacc += d;
-      } else {
-        patch_unit_sums<Env, Unit, ND, ACC, false, 0, false>(env, a, B, Lw, Eb, dt);
-        HCURL_SMARK(17);
-        watermark();
-        HCURL_SMARK(18);
-        if (shared) patch_unit_sums<Env, Unit, ND, ACC, false, 1, false>(env, a, B, Lw, Eb, dt);
-      }
-      HCURL_SMARK(19);
-      env.group_sync();  // EY, the lists and unit buffer bd are free (the gather of this patch landed before it was pulled)
+      } else patch_unit_sums<Env, Unit, ND, ACC, false, 0, false>(env, a, B, Lw, Eb, dt);
+      HCURL_SMARK(17);
+      env.group_sync();
       if (dt == 0) {
         env.flag_signal(EY_FREE);
+        // EY, the lists and unit buffer bd are free once the gather group has arrived as well
+        env.flag_wait(EY_FREE, (uint32_t)it);
         if (it + 1 < n_it) request_l(nL, nT);
         if (it + ND_BUF < n_it) request_d(bd, qD, qL);
       }
@@ -227,6 +207,32 @@ HCURL_BODY void patch_stream(Env &env, const PatchArgs &a) {
     uint32_t zn0 = 0, zn1 = 0;
     if (!ACC && 2 * ZB < n_it) { zn0 = env.ldg(a.own_off + k0 + (int64_t)(2 * ZB) * kstep); zn1 = env.ldg(a.own_off + k0 + (int64_t)(2 * ZB) * kstep + 1); }
     int arrived = 0;
+    bool passed = ACC;
+    // sums of the SHARED units of patch j (RED-adds), one patch behind the gather: the element warps store patch j while
+    // the gather of patch j + 2 is issued
+    auto shared_sums = [&](const int j) {
+      const uint32_t *B = reinterpret_cast<const uint32_t *>(bufD + (size_t)(j & (ND_BUF - 1)) * a.d_cap_bytes);  // (waited for when patch j was gathered)
+      const uint32_t *Lw = reinterpret_cast<const uint32_t *>(bufL);
+      env.bulk_wait(MB_L, (uint32_t)j & 1u);
+      if (!ACC && j % ZB == 0) passed = false;
+      const bool shared = B[7] + B[8] + B[9] + B[2] != 0;
+      if (!passed && shared) {  // every stream has arrived for this batch: all zeros under the shared units of its patches are visible
+        for (unsigned ns = 0; (int32_t)(env.counter_acquire(a.count + j / ZB) - a.count_target) < 0; ns++) env.backoff(ns);
+        passed = true;
+      }
+      HCURL_SMARK(18);
+      env.flag_wait(EY_FULL, (uint32_t)j);  // (also orders this group's EY_FREE arrivals: the element warps have seen EY_FREE(j - 1))
+      HCURL_SMARK(23);
+      if (shared) {
+        if (B[20] != 0) {
+          const double d = patch_unit_sums<Env, Unit, NG, ACC, DOT, 1, true>(env, a, B, Lw, bufE, gt);
+          if (DOT) dacc += d;
+        } else patch_unit_sums<Env, Unit, NG, ACC, false, 1, false>(env, a, B, Lw, bufE, gt);
+      }
+      HCURL_SMARK(19);
+      env.ggroup_sync();
+      if (gt == 0) env.flag_signal(EY_FREE);
+    };
     if (n_it > 0) {
       env.bulk_wait(MB_D0, 0);
       gather(0, 0);
@@ -292,7 +298,9 @@ HCURL_BODY void patch_stream(Env &env, const PatchArgs &a) {
         for (uint32_t u = z0 + ZU * NG; u < z1; u += NG) yu[env.ldg(a.own_idx + u)] = Unit::zero();  // (patches owning more than ZU NG units)
       }
       HCURL_SMARK(13);
+      if (it >= 1) shared_sums(it - 1);
     }
+    if (n_it >= 1) shared_sums(n_it - 1);
     env.ggroup_sync();  // the zeros of the last iteration issued by every thread
     if (!ACC && gt == 0) for (int m = arrived; m < NB; m++) env.arrive(a.count + m);  // (zeros of these batches: none of mine left)
   }

@@ -49,6 +49,7 @@ struct CtaShared {
   std::unique_ptr<std::barrier<>> group, ggroup, elem;  // the sum group / the gather group / the element warps of a stream (patch_stream.h): threads [n_elem, n_elem + n_sum) / [n_elem + n_sum, nt) / [0, n_elem)
   int n_elem = 32;
   std::atomic<uint32_t> flag[MAX_FLAG];   // signals so far
+  uint32_t flag_arrivals[MAX_FLAG] = {1, 1, 1, 1, 1, 1, 1, 1};  // signals per phase (mbarrier arrival count), set by flag_init
   double dot_sum = 0.0;
   std::vector<double> dot_part;
   void set_stream(int ne, int nsum, int nt) {
@@ -165,13 +166,14 @@ struct HostEnv {
   void ggroup_sync() { cta->ggroup->arrive_and_wait(); }
   void warp_sync() { cta->warp[(size_t)(tid_ >> 5)]->bar.arrive_and_wait(); }
   void elem_sync() { cta->elem->arrive_and_wait(); }
-  void flag_init(int f) { cta->flag[f].store(0); }
+  void flag_init(int f, int arrivals) { cta->flag[f].store(0); cta->flag_arrivals[f] = (uint32_t)arrivals; }
   void flag_signal(int f) { cta->flag[f].fetch_add(1u, std::memory_order_release); }
-  void flag_wait(int f, uint32_t n) {
+  void flag_wait(int f, uint32_t n) {  // until phase n of the flag (its arrivals n * per .. (n + 1) * per - 1) is complete
+    const uint32_t per = cta->flag_arrivals[f];
     for (;;) {
       const uint32_t c = cta->flag[f].load(std::memory_order_acquire);
-      if (c > n + 1) *error |= ERR_FLAG_AHEAD;  // the device's one-bit phase parity could not tell this signal from an older one
-      if (c >= n + 1) return;
+      if (c >= (n + 2) * per) *error |= ERR_FLAG_AHEAD;  // the device's one-bit phase parity could not tell this phase from the one after next
+      if (c >= (n + 1) * per) return;
       std::this_thread::yield();
     }
   }
