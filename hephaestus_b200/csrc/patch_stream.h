@@ -16,11 +16,11 @@
 //
 //   element warp, patch i:  wait T(i), XS_FULL[i%2] | pull | signal XS_FREE[i%2] | operator | wait EY_FREE (sums of patch i-1)
 //                           | results to EY | signal EY_FULL, request T(i+2)
-//   gather warps, patch i:  the gather of patch i (started an iteration ago) has landed: signal XS_FULL[i%2], arrive | wait
-//                           D(i+1), XS_FREE[(i+1)%2]: start the x gather of patch i+1 | zero ahead | wait L(i-1), watermark,
-//                           EY_FULL(i-1): sums of the SHARED units of patch i-1 (REDs) | arrive on EY_FREE
-//   sum warps, patch i:     wait D(i), L(i), EY_FULL | sums of the PRIVATE units (stores) | arrive on EY_FREE; once the gather
-//                           group has arrived too: request L(i+1), D(i+4)
+//   gather warps, patch i:  the gather of patch i (started an iteration ago) has landed: signal XS_FULL[i%2] | wait
+//                           D(i+1), XS_FREE[(i+1)%2]: start the x gather of patch i+1 | wait L(i-1), watermark, EY_FULL(i-1):
+//                           sums of the SHARED units of patch i-1 (REDs) | arrive on EY_FREE
+//   sum warps, patch i:     arrive (batch) | wait D(i), L(i) | zero ahead | wait EY_FULL | sums of the PRIVATE units (stores) |
+//                           arrive on EY_FREE; once the gather group has arrived too: request L(i+1), D(i+4)
 //
 // (Round 2, phase profile of the two-role form, where one dof group did the gather AND the sums: 7 900 cycles per
 // iteration and stream, ~1 300 of them waiting -- a single instruction stream of short, latency-exposed steps; the
@@ -143,12 +143,51 @@ HCURL_BODY void patch_stream(Env &env, const PatchArgs &a) {
       request_l(o1, o2);
       for (int j = 1; j < ND_BUF && j < n_it; j++) request_d(j, env.ldg(a.blob_off + k0 + j * kstep), env.ldg(a.part_off + 2 * (k0 + j * kstep)));
     }
+    // zeroing ahead (patch_pipeline.h): batches of ZB iterations, one arrival per stream and batch.  This group does it: it
+    // waits for the element warps anyway while the gather group is busy all the time
+    constexpr int ZB = HCURL_ZERO_BATCH, ZU = (6 * FE + ND - 1) / ND;
+    const int NB = (int)(((a.n_patch - a.k_begin + kstep - 1) / kstep + ZB - 1) / ZB);
+    T *yu = reinterpret_cast<T *>(a.y);
+    uint32_t zn0 = 0, zn1 = 0;
+    if (!ACC && 2 * ZB < n_it) { zn0 = env.ldg(a.own_off + k0 + (int64_t)(2 * ZB) * kstep); zn1 = env.ldg(a.own_off + k0 + (int64_t)(2 * ZB) * kstep + 1); }
+    int arrived = 0;
+    if (!ACC) {  // prologue: zeros under the shared units my patches of iterations [0, 2 ZB) own -- ND / (2 ZB) threads per patch, so
+      // that the extent and index loads of all patches are independent
+      constexpr int NJ = 2 * ZB, TP = ND / NJ;
+      static_assert(ND % NJ == 0, "threads per patch of the zeroing prologue");
+      const int j = dt / TP;
+      if (j < n_it) {
+        const int64_t p = k0 + (int64_t)j * kstep;
+        const uint32_t u1 = env.ldg(a.own_off + p + 1);
+#pragma unroll 4
+        for (uint32_t u = env.ldg(a.own_off + p) + (uint32_t)(dt % TP); u < u1; u += TP) yu[env.ldg(a.own_idx + u)] = Unit::zero();
+      }
+      env.group_sync();  // the zeros of batches 0, 1 issued by every thread of the group
+      if (dt == 0) for (int m = 0; m < 2 && m < NB; m++) env.arrive(a.count + m);
+      arrived = 2;
+    }
     for (int it = 0; it < n_it; it++) {
       const int64_t k = k0 + (int64_t)it * kstep;
       const int bd = it & (ND_BUF - 1);
       const uint32_t *B = reinterpret_cast<const uint32_t *>(bufD + (size_t)bd * a.d_cap_bytes);
       const uint32_t *Lw = reinterpret_cast<const uint32_t *>(bufL);
       const unsigned char *Eb = bufE;
+      // zeroing ahead: the owned shared units of my patch of iteration it + 2 ZB
+      uint32_t zu[ZU];
+      const uint32_t z0 = zn0 + dt, z1 = zn1;
+      if (!ACC) {
+#pragma unroll
+        for (int i = 0; i < ZU; i++) zu[i] = z0 + i * ND < z1 ? env.ldg(a.own_idx + z0 + i * ND) : 0xffffffffu;
+        zn0 = zn1 = 0;
+        if (it + 1 + 2 * ZB < n_it) { const int64_t pz = k + (int64_t)(2 * ZB + 1) * kstep; zn0 = env.ldg(a.own_off + pz); zn1 = env.ldg(a.own_off + pz + 1); }
+      }
+      if (!ACC && it % ZB == 0) {  // first iteration of batch m: arrive for batch m+1 (its zeros were written during batch m-1,
+        const int m = it / ZB;     // each iteration of which ended with a barrier of the group)
+        if (m >= 1 && m + 1 < NB) {
+          if (dt == 0) env.arrive(a.count + m + 1);
+          arrived = m + 2;
+        }
+      }
       HCURL_SMARK(8);
       // thread 0 of the group: extents of the parts requested at the end of this iteration
       uint32_t nL = 0, nT = 0, qD = 0, qL = 0;
@@ -161,6 +200,12 @@ HCURL_BODY void patch_stream(Env &env, const PatchArgs &a) {
       env.bulk_wait(MB_D0 + bd, (uint32_t)(it / ND_BUF) & 1u);
       env.bulk_wait(MB_L, (uint32_t)it & 1u);
       HCURL_SMARK(15);
+      if (!ACC && z0 < z1) {
+#pragma unroll
+        for (int i = 0; i < ZU; i++) if (zu[i] != 0xffffffffu) yu[zu[i]] = Unit::zero();
+        for (uint32_t u = z0 + ZU * ND; u < z1; u += ND) yu[env.ldg(a.own_idx + u)] = Unit::zero();  // (patches owning more than ZU ND units)
+      }
+      HCURL_SMARK(13);
       env.flag_wait(EY_FULL, (uint32_t)it);
       HCURL_SMARK(16);
       if (B[20] != 0) {
@@ -178,6 +223,7 @@ HCURL_BODY void patch_stream(Env &env, const PatchArgs &a) {
       }
       HCURL_SMARK(20);
     }
+    if (!ACC && dt == 0) for (int m = arrived; m < NB; m++) env.arrive(a.count + m);  // (zeros of these batches: none of mine left)
   } else {
     // ================================================================ gather group
     const int gt = tid - FE - ND;
@@ -201,12 +247,7 @@ HCURL_BODY void patch_stream(Env &env, const PatchArgs &a) {
       }
       env.gather_commit();
     };
-    // zeroing ahead (patch_pipeline.h): batches of ZB iterations, one arrival per stream and batch
-    constexpr int ZB = HCURL_ZERO_BATCH, ZU = (6 * FE + NG - 1) / NG;
-    const int NB = (int)(((a.n_patch - a.k_begin + kstep - 1) / kstep + ZB - 1) / ZB);
-    uint32_t zn0 = 0, zn1 = 0;
-    if (!ACC && 2 * ZB < n_it) { zn0 = env.ldg(a.own_off + k0 + (int64_t)(2 * ZB) * kstep); zn1 = env.ldg(a.own_off + k0 + (int64_t)(2 * ZB) * kstep + 1); }
-    int arrived = 0;
+    constexpr int ZB = HCURL_ZERO_BATCH;
     bool passed = ACC;
     // sums of the SHARED units of patch j (RED-adds), one patch behind the gather: the element warps store patch j while
     // the gather of patch j + 2 is issued
@@ -237,50 +278,13 @@ HCURL_BODY void patch_stream(Env &env, const PatchArgs &a) {
       env.bulk_wait(MB_D0, 0);
       gather(0, 0);
     }
-    if (!ACC) {  // prologue: zeros under the shared units my patches of iterations [0, 2 ZB) own
-      // the extents of the 2 ZB owned lists are loaded by 4 ZB threads at once and handed over through shared memory (the
-      // second staging buffer is unused until the gather of patch 1), so that the index loads of all patches are independent
-      constexpr int NJ = 2 * ZB;
-      uint32_t *ext = reinterpret_cast<uint32_t *>(bufX + a.xs_cap_bytes);  // [2 NJ]
-      for (int j = gt; j < 2 * NJ; j += NG) {
-        const int jj = j >> 1;
-        ext[j] = jj < n_it ? env.ldg(a.own_off + k0 + (int64_t)jj * kstep + (j & 1)) : 0u;
-      }
-      env.ggroup_sync();
-#pragma unroll 4
-      for (int j = 0; j < NJ; j++) {
-        const uint32_t u1 = ext[2 * j + 1];
-        for (uint32_t u = ext[2 * j] + gt; u < u1; u += NG) yu[env.ldg(a.own_idx + u)] = Unit::zero();
-      }
-      env.ggroup_sync();  // the zeros of batches 0, 1 issued by every thread of the group
-      if (gt == 0) for (int m = 0; m < 2 && m < NB; m++) env.arrive(a.count + m);
-      arrived = 2;
-    }
-
     for (int it = 0; it < n_it; it++) {
-      const int64_t k = k0 + (int64_t)it * kstep;
-      // zeroing ahead: the owned shared units of my patch of iteration it + 2 ZB
-      uint32_t zu[ZU];
-      const uint32_t z0 = zn0 + gt, z1 = zn1;
-      if (!ACC) {
-#pragma unroll
-        for (int i = 0; i < ZU; i++) zu[i] = z0 + i * NG < z1 ? env.ldg(a.own_idx + z0 + i * NG) : 0xffffffffu;
-        zn0 = zn1 = 0;
-        if (it + 1 + 2 * ZB < n_it) { const int64_t pz = k + (int64_t)(2 * ZB + 1) * kstep; zn0 = env.ldg(a.own_off + pz); zn1 = env.ldg(a.own_off + pz + 1); }
-      }
       HCURL_SMARK(9);
       // the gather of patch it (started an iteration ago) has landed: hand it to the element warps at once
       env.gather_wait();
       HCURL_SMARK(21);
-      env.ggroup_sync();  // ... for every thread of the group; the zeros of the previous iteration issued by every thread
+      env.ggroup_sync();  // ... for every thread of the group
       if (gt == 0) env.flag_signal(XS_FULL + (it & 1));
-      if (!ACC && it % ZB == 0) {  // first iteration of batch m: arrive for batch m+1 (its zeros were written during batch m-1)
-        const int m = it / ZB;
-        if (m >= 1 && m + 1 < NB) {
-          if (gt == 0) env.arrive(a.count + m + 1);
-          arrived = m + 2;
-        }
-      }
       HCURL_SMARK(22);
       // ---- the x gather of patch it + 1 into the other staging buffer, once the element warps have pulled patch it - 1 from it
       if (it + 1 < n_it) {
@@ -292,17 +296,9 @@ HCURL_BODY void patch_stream(Env &env, const PatchArgs &a) {
         gather(j & (ND_BUF - 1), j & 1);
       }
       HCURL_SMARK(12);
-      if (!ACC && z0 < z1) {
-#pragma unroll
-        for (int i = 0; i < ZU; i++) if (zu[i] != 0xffffffffu) yu[zu[i]] = Unit::zero();
-        for (uint32_t u = z0 + ZU * NG; u < z1; u += NG) yu[env.ldg(a.own_idx + u)] = Unit::zero();  // (patches owning more than ZU NG units)
-      }
-      HCURL_SMARK(13);
       if (it >= 1) shared_sums(it - 1);
     }
     if (n_it >= 1) shared_sums(n_it - 1);
-    env.ggroup_sync();  // the zeros of the last iteration issued by every thread
-    if (!ACC && gt == 0) for (int m = arrived; m < NB; m++) env.arrive(a.count + m);  // (zeros of these batches: none of mine left)
   }
   if (DOT) env.dot_finish(dacc, a, reinterpret_cast<double *>(bufE));
 }
