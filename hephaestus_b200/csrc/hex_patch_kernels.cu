@@ -134,7 +134,7 @@ template <int FE_, int ND_, int NG_, int NSTREAM_>
 struct StreamDeviceEnv : PatchDeviceEnv {
   static constexpr int FE = FE_, ND = ND_, NG = NG_, NSTREAM = NSTREAM_, NTHREADS = NSTREAM * (FE + ND + NG);
   static constexpr int REG_ELEMENT = 248, REG_SUM = 72, REG_GATHER = 88;
-  static constexpr int FLAG0 = 8;  // mbarriers 0..6: bulk copies (D0 D1 D2 D3 L T0 T1); 8..13: flags
+  static constexpr int FLAG0 = 8;  // mbarriers 0..7: bulk copies (D0 D1 D2 D3 L0 T0 T1 L1); 8..13: flags
   static_assert(NSTREAM * FE == 128, "the element warps are exactly warp group 0");
   static_assert((NSTREAM * ND) % 128 == 0 && (NSTREAM * NG) % 128 == 0, "setmaxnreg acts on whole warp groups");
   // setmaxnreg re-distributes the registers the CTA was LAUNCHED with (at most 65536 / NTHREADS per thread, in steps of 8):
@@ -201,7 +201,7 @@ typedef StreamDeviceEnv<64, 128, 64, 2> StreamEnv64;     // two streams of 2 + 4
 
 // shared memory of ONE stream (a CTA holds 128 / FE of them)
 size_t patch_stream_smem_bytes(int FE, uint32_t d_cap, uint32_t l_cap, uint32_t t_cap, uint32_t xs_cap) {
-  const size_t one = 128 + 4 * (size_t)d_cap + l_cap + 2 * (size_t)t_cap + 2 * (size_t)xs_cap + (size_t)27 * (FE + 1) * 16;
+  const size_t one = 128 + 4 * (size_t)d_cap + 2 * (size_t)l_cap + 2 * (size_t)t_cap + 2 * (size_t)xs_cap + (size_t)27 * (FE + 1) * 16;
   return (one + 127) & ~(size_t)127;
 }
 

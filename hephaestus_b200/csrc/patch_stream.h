@@ -35,7 +35,7 @@
 // batches, deadlock freedom by co-residency, bit-reproducible two-patch sums) is as described in patch_pipeline.h and
 // patch.cpp.
 //
-// Shared memory of a stream:  [128 B: mbarriers D0 D1 D2 D3 L T0 T1 | 6 flags] [4 x d_cap] [l_cap] [2 x t_cap] [2 x Xs] [EY]
+// Shared memory of a stream:  [128 B: mbarriers D0 D1 D2 D3 L0 T0 T1 L1 | 6 flags] [4 x d_cap] [2 x l_cap] [2 x t_cap] [2 x Xs] [EY]
 //
 // Env (per THREAD of a stream; tid() in [0, FE): the element warps, [FE, FE + ND): the sum group, [FE + ND, FE + ND + NG):
 // the gather group), in addition to the interface listed in patch_pipeline.h (block() / nblocks() count STREAMS, smem() is
@@ -63,12 +63,12 @@ HCURL_BODY void patch_stream(Env &env, const PatchArgs &a) {
   typedef typename Elem::Unit Unit;
   typedef typename Unit::T T;
   constexpr int HDR = PatchHost::HDR;
-  enum { MB_D0 = 0, ND_BUF = 4, MB_L = 4, MB_T0 = 5, N_MB = 7 };  // D0 D1 D2 D3 | L | T0 T1
+  enum { MB_D0 = 0, ND_BUF = 4, MB_L0 = 4, MB_T0 = 5, MB_L1 = 7, N_MB = 8 };  // D0 D1 D2 D3 | L0 | T0 T1 | L1
   enum { XS_FULL = 0, XS_FREE = 2, EY_FULL = 4, EY_FREE = 5, N_FLAG = 6 };  // XS_*: + buffer index
   unsigned char *smem = env.smem();
   unsigned char *bufD = smem + 128;
   unsigned char *bufL = bufD + ND_BUF * (size_t)a.d_cap_bytes;
-  unsigned char *bufT = bufL + a.l_cap_bytes;
+  unsigned char *bufT = bufL + 2 * (size_t)a.l_cap_bytes;  // (the slot lists are double-buffered: those of patch i + 1 are requested while patch i is summed)
   unsigned char *bufX = bufT + 2 * (size_t)a.t_cap_bytes;
   unsigned char *bufE = bufX + 2 * (size_t)a.xs_cap_bytes;
   const int tid = env.tid();
@@ -136,11 +136,13 @@ HCURL_BODY void patch_stream(Env &env, const PatchArgs &a) {
     auto request_d = [&](int b, uint32_t o0, uint32_t o1) {  // (waited for by the gather group and by the sum group)
       env.bulk_request_w(MB_D0 + b, bufD + (size_t)b * a.d_cap_bytes, a.blob + (size_t)o0 * 4, (o1 - o0) * 16u, ND + NG);
     };
-    auto request_l = [&](uint32_t o0, uint32_t o1) { env.bulk_request_w(MB_L, bufL, a.blob + (size_t)o0 * 4, (o1 - o0) * 16u, ND + NG); };
+    auto request_l = [&](int j, uint32_t o0, uint32_t o1) {  // the slot lists of patch j
+      env.bulk_request_w((j & 1) ? MB_L1 : MB_L0, bufL + (size_t)(j & 1) * a.l_cap_bytes, a.blob + (size_t)o0 * 4, (o1 - o0) * 16u, ND + NG);
+    };
     if (dt == 0 && n_it > 0) {
       const uint32_t o1 = env.ldg(a.part_off + 2 * k0), o2 = env.ldg(a.part_off + 2 * k0 + 1);
       request_d(0, env.ldg(a.blob_off + k0), o1);
-      request_l(o1, o2);
+      request_l(0, o1, o2);
       for (int j = 1; j < ND_BUF && j < n_it; j++) request_d(j, env.ldg(a.blob_off + k0 + j * kstep), env.ldg(a.part_off + 2 * (k0 + j * kstep)));
     }
     // zeroing ahead (patch_pipeline.h): batches of ZB iterations, one arrival per stream and batch.  This group does it: it
@@ -170,7 +172,7 @@ HCURL_BODY void patch_stream(Env &env, const PatchArgs &a) {
       const int64_t k = k0 + (int64_t)it * kstep;
       const int bd = it & (ND_BUF - 1);
       const uint32_t *B = reinterpret_cast<const uint32_t *>(bufD + (size_t)bd * a.d_cap_bytes);
-      const uint32_t *Lw = reinterpret_cast<const uint32_t *>(bufL);
+      const uint32_t *Lw = reinterpret_cast<const uint32_t *>(bufL + (size_t)(it & 1) * a.l_cap_bytes);
       const unsigned char *Eb = bufE;
       // zeroing ahead: the owned shared units of my patch of iteration it + 2 ZB
       uint32_t zu[ZU];
@@ -198,7 +200,7 @@ HCURL_BODY void patch_stream(Env &env, const PatchArgs &a) {
       HCURL_SMARK(14);
       // ---- sums of the PRIVATE units of this patch (plain stores); the gather group adds the shared ones
       env.bulk_wait(MB_D0 + bd, (uint32_t)(it / ND_BUF) & 1u);
-      env.bulk_wait(MB_L, (uint32_t)it & 1u);
+      env.bulk_wait((it & 1) ? MB_L1 : MB_L0, (uint32_t)(it >> 1) & 1u);
       HCURL_SMARK(15);
       if (!ACC && z0 < z1) {
 #pragma unroll
@@ -208,6 +210,9 @@ HCURL_BODY void patch_stream(Env &env, const PatchArgs &a) {
       HCURL_SMARK(13);
       env.flag_wait(EY_FULL, (uint32_t)it);
       HCURL_SMARK(16);
+      // the slot lists of the next patch into the other buffer: both groups are done with those of patch it - 1 (the element
+      // warps have seen EY_FREE(it - 1) before they stored patch it)
+      if (dt == 0 && it + 1 < n_it) request_l(it + 1, nL, nT);
       if (B[20] != 0) {
         const double d = patch_unit_sums<Env, Unit, ND, ACC, DOT, 0, true>(env, a, B, Lw, Eb, dt);
         if (DOT) dacc += d;
@@ -216,9 +221,8 @@ HCURL_BODY void patch_stream(Env &env, const PatchArgs &a) {
       env.group_sync();
       if (dt == 0) {
         env.flag_signal(EY_FREE);
-        // EY, the lists and unit buffer bd are free once the gather group has arrived as well
+        // unit buffer bd is free once the gather group has arrived as well
         env.flag_wait(EY_FREE, (uint32_t)it);
-        if (it + 1 < n_it) request_l(nL, nT);
         if (it + ND_BUF < n_it) request_d(bd, qD, qL);
       }
       HCURL_SMARK(20);
@@ -253,8 +257,8 @@ HCURL_BODY void patch_stream(Env &env, const PatchArgs &a) {
     // the gather of patch j + 2 is issued
     auto shared_sums = [&](const int j) {
       const uint32_t *B = reinterpret_cast<const uint32_t *>(bufD + (size_t)(j & (ND_BUF - 1)) * a.d_cap_bytes);  // (waited for when patch j was gathered)
-      const uint32_t *Lw = reinterpret_cast<const uint32_t *>(bufL);
-      env.bulk_wait(MB_L, (uint32_t)j & 1u);
+      const uint32_t *Lw = reinterpret_cast<const uint32_t *>(bufL + (size_t)(j & 1) * a.l_cap_bytes);
+      env.bulk_wait((j & 1) ? MB_L1 : MB_L0, (uint32_t)(j >> 1) & 1u);
       if (!ACC && j % ZB == 0) passed = false;
       const bool shared = B[7] + B[8] + B[9] + B[2] != 0;
       if (!passed && shared) {  // every stream has arrived for this batch: all zeros under the shared units of its patches are visible

@@ -24,7 +24,7 @@
 
 namespace emu {
 
-static constexpr int MAX_BAR = 7, MAX_FLAG = 8;
+static constexpr int MAX_BAR = 8, MAX_FLAG = 8;
 enum { ERR_REARM = 1, ERR_ALIGN = 2, ERR_WAIT_UNARMED = 4, ERR_PARITY = 8, ERR_GATHER_LEFT = 16, ERR_BULK_LEFT = 32, ERR_FLAG_AHEAD = 64 };
 
 // one bulk-copy request on an mbarrier: issued by one thread, waited for (once) by nwait threads, each of which counts its own
@@ -81,7 +81,7 @@ struct HostEnv {
   unsigned vote_n = 0, shfl_n = 0;
   bool wait_may_precede_request = false;  // set by role(): the stream program
   unsigned commits = 0;  // committed gather groups
-  uint32_t my_waits[MAX_BAR] = {0, 0, 0, 0, 0, 0, 0};  // my waits so far per mbarrier
+  uint32_t my_waits[MAX_BAR] = {0, 0, 0, 0, 0, 0, 0, 0};  // my waits so far per mbarrier
 
   int tid() const { return tid_; }
   int64_t block() const { return block_; }

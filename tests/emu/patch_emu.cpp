@@ -58,7 +58,7 @@ extern "C" int emu_patch_apply(int order, int fe, int general, int accumulate, i
   const bool acc = accumulate != 0;
   if (order == 2 && fe < 0) {  // the stream program; here `grid` counts streams and may exceed the number of patches (idle streams)
     const int FE = -fe;
-    const size_t ssm = 128 + 4 * (size_t)d_cap_bytes + l_cap_bytes + 2 * (size_t)t_cap_bytes + 2 * (size_t)xs_cap_bytes + (size_t)27 * (FE + 1) * 16;
+    const size_t ssm = 128 + 4 * (size_t)d_cap_bytes + 2 * (size_t)l_cap_bytes + 2 * (size_t)t_cap_bytes + 2 * (size_t)xs_cap_bytes + (size_t)27 * (FE + 1) * 16;
     if (grid < 1) return 0;
     if (FE == 32) return general ? run_stream_mode<32, 96, true>(a, grid, ssm, acc) : run_stream_mode<32, 96, false>(a, grid, ssm, acc);
     if (FE == 64) return general ? run_stream_mode<64, 128, true>(a, grid, ssm, acc) : run_stream_mode<64, 128, false>(a, grid, ssm, acc);
