@@ -454,10 +454,10 @@ def main():
                 "kernel": "tet batched packed-symmetric element-matrix kernel (order %d)" % p if args.geom == "tet" else
                 "hex element kernel (order %d; %s)" % (
                     p, {1: "generic sum-factorised", 2: "element-wise register-blocked",
-                        3: ("patch kernel, warp-specialised stream: 4 element warps (one thread per element, modal operator) + 12 dof warps per "
-                            "128-element patch, setmaxnreg, mbarrier rings, persistent, zero-ahead watermark"
+                        3: ("patch kernel, warp-specialised stream in three roles: 4 element warps (one thread per element, modal operator) + "
+                            "8 sum warps + 4 gather warps per 128-element patch, setmaxnreg, mbarrier rings, persistent, zero-ahead watermark"
                             if p == 2 and os.environ.get("HCURL_PATCH_STREAM", "1") != "0" and os.environ.get("HCURL_PATCH_FE", "128") == "128" else
-                            "patch kernel, warp-specialised streams: 2 element warps + 4 dof warps per 64-element patch"
+                            "patch kernel, warp-specialised streams: 2 element + 4 sum + 2 gather warps per 64-element patch"
                             if p == 2 and os.environ.get("HCURL_PATCH_STREAM", "1") != "0" and os.environ.get("HCURL_PATCH_FE") == "64" else
                             "patch pipeline: one thread per element, modal operator, persistent, zero-ahead watermark")}.get(op.LastKernel(), "?")),
                 "kernel_ms": kern_ms, "kernel_launches_timed": kern_n, "algorithmic_bytes_per_launch": abytes,
