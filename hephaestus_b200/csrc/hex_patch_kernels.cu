@@ -130,10 +130,16 @@ __global__ void __launch_bounds__(FE) hex_patch_p1_kernel(const PatchArgs a) {
 // the element warp group then takes 248, the sum warp groups drop to 72 and the gather warp group to 56.  (The same program
 // with 32-element patches -- four streams -- measured 4 % slower in its two-role form: profiles/README.md; it still runs in
 // the host emulation, tests/test_patch_p2_emu.py.)
+#ifndef HCURL_STREAM_REG_SUM
+#define HCURL_STREAM_REG_SUM 72
+#endif
+#ifndef HCURL_STREAM_REG_GATHER
+#define HCURL_STREAM_REG_GATHER 88
+#endif
 template <int FE_, int ND_, int NG_, int NSTREAM_>
 struct StreamDeviceEnv : PatchDeviceEnv {
   static constexpr int FE = FE_, ND = ND_, NG = NG_, NSTREAM = NSTREAM_, NTHREADS = NSTREAM * (FE + ND + NG);
-  static constexpr int REG_ELEMENT = 248, REG_SUM = 72, REG_GATHER = 88;
+  static constexpr int REG_ELEMENT = 248, REG_SUM = HCURL_STREAM_REG_SUM, REG_GATHER = HCURL_STREAM_REG_GATHER;
   static constexpr int FLAG0 = 8;  // mbarriers 0..7: bulk copies (D0 D1 D2 D3 L0 T0 T1 L1); 8..13: flags
   static_assert(NSTREAM * FE == 128, "the element warps are exactly warp group 0");
   static_assert((NSTREAM * ND) % 128 == 0 && (NSTREAM * NG) % 128 == 0, "setmaxnreg acts on whole warp groups");

@@ -50,6 +50,9 @@
 #pragma once
 #include "patch_pipeline.h"
 
+#ifndef HCURL_STREAM_GATHER_UNROLL
+#define HCURL_STREAM_GATHER_UNROLL 4
+#endif
 #ifdef HCURL_PHASE_PROFILE
 #define HCURL_SMARK(k) env.smark(k)
 #else
@@ -239,7 +242,7 @@ HCURL_BODY void patch_stream(Env &env, const PatchArgs &a) {
       const uint32_t U = B[0];
       const uint32_t *dof = B + HDR;
       if (B[20] == 0) {  // no essential dof in this patch
-#pragma unroll 4
+HCURL_UNROLL(HCURL_STREAM_GATHER_UNROLL)
         for (uint32_t u = gt; u < U; u += NG) Unit::gather(env, Xs + u, xu + (dof[u] & PATCH_IDX));
       } else {
 #pragma unroll 2
