@@ -1,6 +1,7 @@
 // The WARP-SPECIALISED form of the persistent patch pipeline (patch_pipeline.h) for the order-2 affine hex kernel: the
 // same patch blobs, element side, per-unit sums, zero-ahead watermark and essential-row handling, but the element side,
-// the x gather and the per-unit sums of a patch run in DIFFERENT warps, connected by four one-bit flags per stream.
+// the x gather (with the sums of the shared units) and the sums of the private units of a patch run in DIFFERENT warps,
+// connected by four one-bit flags per stream.
 //
 // Operator and reference: y (+)= scale * (K(alpha) + M(beta)) x, CurlCurlKernel + VectorFEMassKernel
 // (/root/reference/src/kernels/curl_curl_kernel.cpp:21-24, vector_fe_mass_kernel.cpp:21-24) applied as EquationSystem::Mult
@@ -22,18 +23,23 @@
 //   sum warps, patch i:     arrive (batch) | wait D(i), L(i) | zero ahead | wait EY_FULL | sums of the PRIVATE units (stores) |
 //                           arrive on EY_FREE; once the gather group has arrived too: request L(i+1), D(i+4)
 //
-// (Round 2, phase profile of the two-role form, where one dof group did the gather AND the sums: 7 900 cycles per
-// iteration and stream, ~1 300 of them waiting -- a single instruction stream of short, latency-exposed steps; the
-// element warp waited ~1 700 of its 7 900 for it.  Gather + zeroing are ~3 000 of those cycles, the sums ~4 800: in
-// different warps they overlap.)
+// How the roles were cut (round 2, phase profiles under profiles/: clock64 per phase): with one dof group doing the gather AND
+// the sums (two streams of 64-element patches) an iteration took 7 900 cycles per stream and the element warps waited 1 700
+// of them; on ONE stream of 128-element patches the three groups depend on each other patch by patch and their balance
+// decides -- the group whose waits were shortest gave work to the one that waited most: gather warps split off (0.407 ms
+// per apply), shared sums moved to them (0.378), zeroing moved to the sum warps (0.373), slot lists double-buffered (0.366 =
+// 71 % of the measured HBM copy bandwidth).
 // The staging vector Xs is a DOUBLE-BUFFERED ring (one FULL / FREE flag pair per buffer: the usual producer / consumer
 // protocol, so a one-bit phase parity per flag is enough); the gather warps run as far ahead as the ring allows (16-byte
 // scattered copies need ~3 000 cycles to land under load) and the unit lists are requested four patches ahead (bulk
-// copies: ~2 000).  The unit list D(i) is read by the gather warps (indices) and, later, by the sum warps (counts, indices,
-// flags); its buffer is requested again by the sum warps once they are done with patch i -- the gather of patch i landed
-// before the element warp pulled it, i.e. before EY_FULL(i).  Everything else (blob format, ownership and zeroing
-// batches, deadlock freedom by co-residency, bit-reproducible two-patch sums) is as described in patch_pipeline.h and
-// patch.cpp.
+// copies: ~2 000).  The unit list D(i) is read by the gather warps (indices for the gather; counts, indices and flags for
+// the shared sums) and by the sum warps; its buffer is requested again by the first sum thread once BOTH groups have
+// arrived on EY_FREE(i) (an mbarrier with two arrivals per phase; the element warps wait for the same phase before they
+// store patch i+1).  The slot lists L are double-buffered: L(i+1) is requested as soon as EY_FULL(i) has been seen -- the
+// element warps saw EY_FREE(i-1) before that, so both groups are done with L(i-1).  No flag can run two phases ahead of a
+// waiter: EY_FULL(i+1) needs EY_FREE(i), which needs the arrivals of both groups that wait for EY_FULL(i) (the host emulation
+// checks this for every wait).  Everything else (blob format, ownership and zeroing batches, deadlock freedom by
+// co-residency, bit-reproducible two-patch sums) is as described in patch_pipeline.h and patch.cpp.
 //
 // Shared memory of a stream:  [128 B: mbarriers D0 D1 D2 D3 L0 T0 T1 L1 | 6 flags] [4 x d_cap] [2 x l_cap] [2 x t_cap] [2 x Xs] [EY]
 //
@@ -44,9 +50,9 @@
 //   void group_sync()  void ggroup_sync()         barrier of the sum group / of the gather group
 //   void elem_sync()                              barrier of the element warps of the stream (one warp when FE = 32)
 //   void bulk_request_w(int b, void *dst, const void *src, uint32_t bytes, int nwait)   as bulk_request; nwait threads will wait
-//   void flag_init(int f)  (thread 0, with bulk_init)   void flag_signal(int f)  (one thread, after a warp / group barrier)
-//   void flag_wait(int f, uint32_t n)             until the flag has been signalled n + 1 times (n = 0, 1, ...: every value waited for in turn)
-//   void gather_wait_prev()                       all committed gather groups but the latest have landed
+//   void flag_init(int f, int arrivals)  (thread 0, with bulk_init; arrivals = signals per phase)
+//   void flag_signal(int f)                       (one thread, after a warp / group barrier)
+//   void flag_wait(int f, uint32_t n)             until phase n of the flag is complete (n = 0, 1, ...: every phase waited for in turn)
 #pragma once
 #include "patch_pipeline.h"
 
