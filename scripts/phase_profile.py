@@ -54,9 +54,9 @@ def main():
                  8: "S: end of iteration -> top", 14: "S: extents of the next requests", 15: "S: wait D, L", 16: "S: wait EY_FULL", 17: "S: sums private",
                  20: "S: group sync + arrive + wait EY_FREE + requests",
                  9: "G: top (zero indices)", 21: "G: gather wait", 22: "G: group sync + signal XS_FULL + arrive", 10: "G: wait D(i+1)",
-                 11: "G: wait XS_FREE", 12: "G: gather issue", 13: "G: zero stores", 18: "G: wait L + watermark", 23: "G: wait EY_FULL",
+                 11: "G: wait XS_FREE", 12: "G: gather issue", 13: "S: zero stores", 18: "G: wait L + watermark", 23: "G: wait EY_FULL",
                  19: "G: sums shared"}
-        groups = [("element warps", [0, 1, 2, 3, 4, 5, 6, 7]), ("sum group", [8, 14, 15, 16, 17, 20]), ("gather group", [9, 21, 22, 10, 11, 12, 13, 18, 23, 19])]
+        groups = [("element warps", [0, 1, 2, 3, 4, 5, 6, 7]), ("sum group", [8, 14, 15, 13, 16, 17, 20]), ("gather group", [9, 21, 22, 10, 11, 12, 18, 23, 19])]
         fe = int(os.environ.get("HCURL_PATCH_FE", "128"))
         its = a.n ** 3 // fe * a.applies
         print("apply %.4f ms (instrumented); cycles per pipeline iteration (%d-element patch) and stream" % (ms, fe))
