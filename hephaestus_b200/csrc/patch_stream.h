@@ -21,7 +21,7 @@
 //                           D(i+1), XS_FREE[(i+1)%2]: start the x gather of patch i+1 | wait L(i-1), watermark, EY_FULL(i-1):
 //                           sums of the SHARED units of patch i-1 (REDs) | arrive on EY_FREE
 //   sum warps, patch i:     arrive (batch) | wait D(i), L(i) | zero ahead | wait EY_FULL | sums of the PRIVATE units (stores) |
-//                           arrive on EY_FREE; once the gather group has arrived too: request L(i+1), D(i+4)
+//                           arrive on EY_FREE; once the gather group has arrived too: request L(i+2), D(i+4)
 //
 // How the roles were cut (round 2, phase profiles under profiles/: clock64 per phase): with one dof group doing the gather AND
 // the sums (two streams of 64-element patches) an iteration took 7 900 cycles per stream and the element warps waited 1 700
@@ -35,8 +35,8 @@
 // copies: ~2 000).  The unit list D(i) is read by the gather warps (indices for the gather; counts, indices and flags for
 // the shared sums) and by the sum warps; its buffer is requested again by the first sum thread once BOTH groups have
 // arrived on EY_FREE(i) (an mbarrier with two arrivals per phase; the element warps wait for the same phase before they
-// store patch i+1).  The slot lists L are double-buffered: L(i+1) is requested as soon as EY_FULL(i) has been seen -- the
-// element warps saw EY_FREE(i-1) before that, so both groups are done with L(i-1).  No flag can run two phases ahead of a
+// store patch i+1).  The slot lists L are double-buffered: L(i+2) is requested into the buffer of L(i) at the same moment, a
+// whole iteration ahead of its use.  No flag can run two phases ahead of a
 // waiter: EY_FULL(i+1) needs EY_FREE(i), which needs the arrivals of both groups that wait for EY_FULL(i) (the host emulation
 // checks this for every wait).  Everything else (blob format, ownership and zeroing batches, deadlock freedom by
 // co-residency, bit-reproducible two-patch sums) is as described in patch_pipeline.h and patch.cpp.
@@ -152,6 +152,7 @@ HCURL_BODY void patch_stream(Env &env, const PatchArgs &a) {
       const uint32_t o1 = env.ldg(a.part_off + 2 * k0), o2 = env.ldg(a.part_off + 2 * k0 + 1);
       request_d(0, env.ldg(a.blob_off + k0), o1);
       request_l(0, o1, o2);
+      if (n_it > 1) request_l(1, env.ldg(a.part_off + 2 * (k0 + kstep)), env.ldg(a.part_off + 2 * (k0 + kstep) + 1));
       for (int j = 1; j < ND_BUF && j < n_it; j++) request_d(j, env.ldg(a.blob_off + k0 + j * kstep), env.ldg(a.part_off + 2 * (k0 + j * kstep)));
     }
     // zeroing ahead (patch_pipeline.h): batches of ZB iterations, one arrival per stream and batch.  This group does it: it
@@ -203,7 +204,7 @@ HCURL_BODY void patch_stream(Env &env, const PatchArgs &a) {
       // thread 0 of the group: extents of the parts requested at the end of this iteration
       uint32_t nL = 0, nT = 0, qD = 0, qL = 0;
       if (dt == 0) {
-        if (it + 1 < n_it) { nL = env.ldg(a.part_off + 2 * (k + kstep)); nT = env.ldg(a.part_off + 2 * (k + kstep) + 1); }
+        if (it + 2 < n_it) { nL = env.ldg(a.part_off + 2 * (k + 2 * kstep)); nT = env.ldg(a.part_off + 2 * (k + 2 * kstep) + 1); }
         if (it + ND_BUF < n_it) { qD = env.ldg(a.blob_off + k + ND_BUF * kstep); qL = env.ldg(a.part_off + 2 * (k + ND_BUF * kstep)); }
       }
       HCURL_SMARK(14);
@@ -219,9 +220,6 @@ HCURL_BODY void patch_stream(Env &env, const PatchArgs &a) {
       HCURL_SMARK(13);
       env.flag_wait(EY_FULL, (uint32_t)it);
       HCURL_SMARK(16);
-      // the slot lists of the next patch into the other buffer: both groups are done with those of patch it - 1 (the element
-      // warps have seen EY_FREE(it - 1) before they stored patch it)
-      if (dt == 0 && it + 1 < n_it) request_l(it + 1, nL, nT);
       if (B[20] != 0) {
         const double d = patch_unit_sums<Env, Unit, ND, ACC, DOT, 0, true>(env, a, B, Lw, Eb, dt);
         if (DOT) dacc += d;
@@ -230,8 +228,9 @@ HCURL_BODY void patch_stream(Env &env, const PatchArgs &a) {
       env.group_sync();
       if (dt == 0) {
         env.flag_signal(EY_FREE);
-        // unit buffer bd is free once the gather group has arrived as well
+        // unit buffer bd and the slot lists of this patch are free once the gather group has arrived as well
         env.flag_wait(EY_FREE, (uint32_t)it);
+        if (it + 2 < n_it) request_l(it + 2, nL, nT);  // (into the buffer of the slot lists of this patch: a whole iteration ahead of their use)
         if (it + ND_BUF < n_it) request_d(bd, qD, qL);
       }
       HCURL_SMARK(20);
