@@ -155,3 +155,33 @@ def test_general_orientation_flags(emu):
     run_emu(emu, P, edata, x, y, grid=2, blob=blob, general=True)
     ref = S * (A @ (S * x))
     assert np.abs(y - ref).max() <= 1e-12 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("grid", [1, 2])
+def test_emulated_p2_stream128_zeroing_batches(emu, grid):
+    """the default form of the stream program (128-element patches, 4 element + 8 sum + 4 gather warps) over MANY pipeline
+    iterations per stream: 2304 elements = 18 patches, i.e. 18 / 9 iterations on 1 / 2 streams -- the batch arrivals of the
+    zeroing ahead (8 iterations per batch), the watermark waits of the gather group, the double-buffered slot lists and the
+    four-deep ring of unit lists all wrap around; reversed lines from a scrambled vertex numbering"""
+    m, mo = affine_pair("hex", (16, 12, 12))
+    perm = np.random.default_rng(11).permutation(len(m.verts))
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(len(perm))
+    m = fespace.Mesh("hex", m.verts[perm], inv[m.elems], m.attr)
+    mo = type(mo)("hex", mo.verts[perm], inv[mo.elems], mo.attr)
+    sp, so = fespace.NDSpace(m, 2), osp.NDSpace(mo, 2)
+    alpha, beta = coefficients(mo)
+    A = oa.assemble(so, alpha, beta, q_override=3).tocsr()
+    P = build_patches(sp, m, 2, 128)
+    assert len(P["off"]) - 1 == 18
+    edata = geometry_factors(m, P["perm"], 128, alpha, beta)
+    x = np.random.default_rng(12).standard_normal(sp.ndof)
+    y = np.full(sp.ndof, 1e30)   # nothing is cleared before an apply
+    dot = run_emu(emu, P, edata, x, y, grid=grid, dot=True, general=False, stream=True)
+    ref = A @ x
+    assert np.abs(y - ref).max() <= 1e-12 * np.abs(ref).max()
+    assert abs(dot - x @ ref) <= 1e-12 * abs(x @ ref)
+    y2 = np.random.default_rng(13).standard_normal(sp.ndof)
+    y2_0 = y2.copy()
+    run_emu(emu, P, edata, x, y2, scale=0.61, accumulate=True, grid=grid, general=False, stream=True)
+    assert np.abs(y2 - (y2_0 + 0.61 * ref)).max() <= 1e-12 * np.abs(ref).max()
