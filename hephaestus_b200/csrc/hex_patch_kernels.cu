@@ -168,7 +168,6 @@ struct StreamDeviceEnv : PatchDeviceEnv {
     else if (r == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REG_SUM));
     else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REG_GATHER));
   }
-  __device__ __forceinline__ void gather_wait_prev() const { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
   __device__ __forceinline__ void bulk_request_w(int b, void *dst, const void *src, uint32_t bytes, int) const { bulk_request(b, dst, src, bytes); }
   // flags: mbarriers of the stream with one arrival per phase.  A flag is never signalled twice before its waiter has
   // passed (ring protocol, patch_stream.h), so the one-bit phase parity identifies the n-th signal

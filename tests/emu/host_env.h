@@ -132,14 +132,6 @@ struct HostEnv {
     for (auto &p : pend) memcpy(p.dst, p.src, (size_t)p.bytes);
     pend.clear();
   }
-  void gather_wait_prev() {  // cp.async.wait_group 1: every committed group but the latest has landed
-    std::vector<Copy> keep;
-    for (auto &p : pend) {
-      if (p.grp + 1 < commits) memcpy(p.dst, p.src, (size_t)p.bytes);
-      else keep.push_back(p);
-    }
-    pend.swap(keep);
-  }
   void red_add(double *p, double v) {
     std::atomic_ref<double> r(*p);
     double old = r.load(std::memory_order_relaxed);
